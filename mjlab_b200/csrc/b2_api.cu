@@ -1,0 +1,172 @@
+// b2_api.cu - C ABI (include/b200sim.h) + kernel launches for sm_100a.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+// Launch shape: one warp per world, B2_WPB worlds per CTA; grid = ceil(nworld / B2_WPB).
+// Dynamic shared memory = B2_WPB * per-world slab (layout computed on the host from the model sizes).
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "b2_smooth.cuh"
+#include "b2_solve.cuh"
+
+static_assert(sizeof(KModel) == sizeof(b2_model), "KModel must mirror b2_model");
+static_assert(sizeof(KData) == sizeof(b2_data), "KData must mirror b2_data");
+
+#ifndef B2_WPB
+#define B2_WPB 4
+#endif
+#define B2_NCAND_MAX 256
+
+static char g_err[512] = "";
+static long long g_launches = 0;
+
+static int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+
+__global__ void __launch_bounds__(B2_WPB * 32) k_smooth(const KModel m, const KData d, const SmoothSmem L, int ncand_max) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  real* smem = reinterpret_cast<real*>(smem_raw);
+  int warp = threadIdx.x >> 5;
+  int w = blockIdx.x * B2_WPB + warp;
+  if (w >= d.nworld) return;
+  smooth_world(m, d, L, ncand_max, w, smem + (size_t)warp * L.total);
+}
+
+__global__ void __launch_bounds__(B2_WPB * 32) k_solve(const KModel m, const KData d, const SolveSmem L, int do_integrate) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  real* smem = reinterpret_cast<real*>(smem_raw);
+  int warp = threadIdx.x >> 5;
+  int w = blockIdx.x * B2_WPB + warp;
+  if (w >= d.nworld) return;
+  solve_world(m, d, L, w, smem + (size_t)warp * L.total, do_integrate);
+}
+
+// masked reset, one warp per world
+__global__ void k_reset(const KModel m, const KData d, const unsigned char* mask) {
+  int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= d.nworld) return;
+  if (mask && !mask[w]) return;
+  const int lane = threadIdx.x & 31;
+  const real* qpos0 = MF(B2_MF_QPOS0);
+  for (int i = lane; i < m.nq; i += 32) d.df[B2_DF_QPOS][(size_t)w * m.nq + i] = qpos0[i];
+  for (int i = lane; i < m.nv; i += 32) {
+    size_t o = (size_t)w * m.nv + i;
+    d.df[B2_DF_QVEL][o] = 0; d.df[B2_DF_QACC][o] = 0; d.df[B2_DF_QACC_WARMSTART][o] = 0; d.df[B2_DF_QFRC_APPLIED][o] = 0;
+  }
+  for (int i = lane; i < m.nu; i += 32) d.df[B2_DF_CTRL][(size_t)w * m.nu + i] = 0;
+  for (int i = lane; i < m.nbody * 6; i += 32) d.df[B2_DF_XFRC_APPLIED][(size_t)w * m.nbody * 6 + i] = 0;
+  for (int i = lane; i < m.nsensordata; i += 32) d.df[B2_DF_SENSORDATA][(size_t)w * m.nsensordata + i] = 0;
+  const int* mocap = MI(B2_MI_BODY_MOCAPID);
+  const real* bpos = MF(B2_MF_BODY_POS);
+  const real* bquat = MF(B2_MF_BODY_QUAT);
+  for (int b = lane; b < m.nbody; b += 32) {
+    int k = mocap[b];
+    if (k < 0) continue;
+    for (int c = 0; c < 3; ++c) d.df[B2_DF_MOCAP_POS][((size_t)w * m.nmocap + k) * 3 + c] = bpos[3 * b + c];
+    for (int c = 0; c < 4; ++c) d.df[B2_DF_MOCAP_QUAT][((size_t)w * m.nmocap + k) * 4 + c] = bquat[4 * b + c];
+  }
+  if (lane == 0) {
+    d.df[B2_DF_TIME][w] = 0;
+    d.di[B2_DI_NCON][w] = 0; d.di[B2_DI_NEFC][w] = 0; d.di[B2_DI_NL][w] = 0; d.di[B2_DI_SOLVER_NITER][w] = 0;
+  }
+}
+
+__global__ void k_repeat_rows(float* dst, const float* src, int row_len, long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) dst[i] = src[i % row_len];
+}
+
+struct Plan {
+  SmoothSmem ls;
+  SolveSmem lv;
+  size_t smem_smooth, smem_solve;
+};
+
+static int make_plan(const b2_model* m, const b2_data* d, Plan* p) {
+  p->ls = smooth_smem_layout(m->nq, m->nv, m->nu, m->nbody, m->njnt, B2_NCAND_MAX);
+  p->lv = solve_smem_layout(m->nv, d->njmax);
+  p->smem_smooth = (size_t)p->ls.total * sizeof(real) * B2_WPB;
+  p->smem_solve = (size_t)p->lv.total * sizeof(real) * B2_WPB;
+  return 0;
+}
+
+extern "C" {
+
+int b2_abi_version(void) { return 1; }
+const char* b2_last_error(void) { return g_err; }
+int b2_sizeof_model(void) { return (int)sizeof(b2_model); }
+int b2_sizeof_data(void) { return (int)sizeof(b2_data); }
+long long b2_launch_count(void) { return g_launches; }
+
+int b2_check(const b2_model* m, const b2_data* d) {
+  if (!m || !d) return fail("null model/data");
+  if (m->nv > 64) return fail("nv=%d exceeds the 64-dof limit of the per-world dof masks", m->nv);
+  if (m->nv < 1) return fail("nv must be >= 1");
+  if (m->cone != 0) return fail("only the pyramidal cone is supported");
+  if (m->solver != 2) return fail("only the Newton solver is supported");
+  if (m->integrator != B2_INT_EULER && m->integrator != B2_INT_IMPLICITFAST) return fail("unsupported integrator %d", m->integrator);
+  if (d->nworld < 1 || d->nconmax < 0 || d->njmax < 1) return fail("bad nworld/nconmax/njmax");
+  Plan p;
+  make_plan(m, d, &p);
+  int dev = 0, maxsmem = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail("no CUDA device: %s", cudaGetErrorString(cudaGetLastError()));
+  cudaDeviceGetAttribute(&maxsmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if ((int)p.smem_smooth > maxsmem || (int)p.smem_solve > maxsmem)
+    return fail("shared memory per CTA (%zu / %zu B) exceeds the device limit %d B; lower njmax or model size",
+                p.smem_smooth, p.smem_solve, maxsmem);
+  cudaError_t e;
+  e = cudaFuncSetAttribute(k_smooth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_smooth);
+  if (e != cudaSuccess) return fail("cudaFuncSetAttribute(k_smooth): %s", cudaGetErrorString(e));
+  e = cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_solve);
+  if (e != cudaSuccess) return fail("cudaFuncSetAttribute(k_solve): %s", cudaGetErrorString(e));
+  return 0;
+}
+
+static int run(const b2_model* m, b2_data* d, void* stream, int do_integrate) {
+  Plan p;
+  make_plan(m, d, &p);
+  cudaStream_t st = (cudaStream_t)stream;
+  const KModel& km = *reinterpret_cast<const KModel*>(m);
+  const KData& kd = *reinterpret_cast<const KData*>(d);
+  int grid = (d->nworld + B2_WPB - 1) / B2_WPB;
+  k_smooth<<<grid, B2_WPB * 32, p.smem_smooth, st>>>(km, kd, p.ls, B2_NCAND_MAX);
+  k_solve<<<grid, B2_WPB * 32, p.smem_solve, st>>>(km, kd, p.lv, do_integrate);
+  g_launches += 2;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("launch failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int b2_step(const b2_model* m, b2_data* d, void* stream) { return run(m, d, stream, 1); }
+int b2_forward(const b2_model* m, b2_data* d, void* stream) { return run(m, d, stream, 0); }
+
+int b2_reset(const b2_model* m, b2_data* d, const unsigned char* mask, void* stream) {
+  const KModel& km = *reinterpret_cast<const KModel*>(m);
+  const KData& kd = *reinterpret_cast<const KData*>(d);
+  int grid = (d->nworld + 3) / 4;
+  k_reset<<<grid, 128, 0, (cudaStream_t)stream>>>(km, kd, mask);
+  g_launches += 1;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("launch failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int b2_repeat_rows(float* dst, const float* src, int row_len, int nworld, void* stream) {
+  long long total = (long long)row_len * nworld;
+  if (total <= 0) return 0;
+  int grid = (int)((total + 255) / 256);
+  k_repeat_rows<<<grid, 256, 0, (cudaStream_t)stream>>>(dst, src, row_len, total);
+  g_launches += 1;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("launch failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+}  // extern "C"

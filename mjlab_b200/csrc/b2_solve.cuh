@@ -1,0 +1,836 @@
+// b2_solve.cuh - stage 2 of the physics step, one warp per world:
+//   constraint rows (joint limits, pyramidal contacts) -> efc_J / efc_D / efc_aref
+//   -> primal Newton solver with exact line search -> qacc, efc_force, qfrc_constraint
+//   -> sensors (IMU trio, subtree angular momentum, contact sensors, ...)
+//   -> integration (implicitfast | Euler), time, warm start
+//
+// Restates mj_makeConstraint / mj_fwdConstraint / mj_sensor* / mj_implicit as
+// executed by mujoco_warp's `_src.constraint`, `_src.solver`, `_src.sensor`,
+// `_src.derivative` modules.
+#pragma once
+#include "b2_common.cuh"
+
+#define B2_CHUNK 32  // efc rows staged through shared memory at a time
+
+struct SolveSmem {
+  int M, H, chunk, cdof, qvel, qacc, Ma, grad, search, Mv, qfs, qas, qfc, tmp, D, aref, jar, jv, total;
+};
+
+static inline SolveSmem solve_smem_layout(int nv, int njmax) {
+  SolveSmem s;
+  int o = 0;
+  auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
+  s.M = take(nv * nv); s.H = take(nv * nv); s.chunk = take(B2_CHUNK * nv);
+  s.cdof = take(6 * nv);
+  s.qvel = take(nv); s.qacc = take(nv); s.Ma = take(nv); s.grad = take(nv); s.search = take(nv); s.Mv = take(nv);
+  s.qfs = take(nv); s.qas = take(nv); s.qfc = take(nv); s.tmp = take(nv);
+  s.D = take(njmax); s.aref = take(njmax); s.jar = take(njmax); s.jv = take(njmax);
+  s.total = o;
+  return s;
+}
+
+// impedance / reference parameters of one row (mj_makeImpedance restated)
+B2_DEV void kbi(real timestep, const real* solref, const real* solimp, real pos, real& k, real& b, real& imp) {
+  real timeconst = solref[0], dampratio = solref[1];
+  real dmin = solimp[0], dmax = solimp[1], width = solimp[2], mid = solimp[3], power = solimp[4];
+  if (timeconst > 0) timeconst = fmax(timeconst, 2 * timestep);
+  dmin = clampr(dmin, B2_MINIMP, B2_MAXIMP);
+  dmax = clampr(dmax, B2_MINIMP, B2_MAXIMP);
+  width = fmax(B2_MINVAL, width);
+  mid = clampr(mid, B2_MINIMP, B2_MAXIMP);
+  power = fmax((real)1, power);
+  if (solref[0] > 0) k = (real)1 / (dmax * dmax * timeconst * timeconst * dampratio * dampratio);
+  else k = -solref[0] / (dmax * dmax);
+  if (solref[1] > 0) b = (real)2 / (dmax * timeconst);
+  else b = -solref[1] / dmax;
+  real x = fabs(pos) / width;
+  if (x >= 1) {
+    imp = dmax;
+  } else {
+    real y;
+    if (x < mid) y = pow(x, power) / pow(mid, power - 1);
+    else y = 1 - pow(1 - x, power) / pow(1 - mid, power - 1);
+    imp = dmin + y * (dmax - dmin);
+    real lo = fmin(dmin, dmax), hi = fmax(dmin, dmax);
+    imp = clampr(imp, lo, hi);
+  }
+}
+
+// y[r] (op)= J[r,:] . x  for all rows, staged through the shared chunk.
+// mode 0: y = Jx - sub   mode 1: y = Jx
+B2_DEV void rows_dot(const real* gJ, int nefc, int nv, const real* x, real* chunk, real* y, const real* sub) {
+  for (int base = 0; base < nefc; base += B2_CHUNK) {
+    int nr = nefc - base < B2_CHUNK ? nefc - base : B2_CHUNK;
+    B2_WSYNC();
+    for (int i = B2_LANE; i < nr * nv; i += B2_NLANE) chunk[i] = gJ[(size_t)base * nv + i];
+    B2_WSYNC();
+    for (int r = B2_LANE; r < nr; r += B2_NLANE) {
+      real acc = 0;
+      const real* c = chunk + r * nv;
+      for (int e = 0; e < nv; ++e) acc += c[e] * x[e];
+      y[base + r] = sub ? acc - sub[base + r] : acc;
+    }
+  }
+  B2_WSYNC();
+}
+
+struct LsPnt { real alpha, cost, d1, d2; };
+
+B2_DEV LsPnt ls_eval(real alpha, real q0g, real q1g, real q2g, const real* jar, const real* jv, const real* D, int nefc) {
+  real q0 = 0, q1 = 0, q2 = 0;
+  for (int r = B2_LANE; r < nefc; r += B2_NLANE) {
+    real x = jar[r] + alpha * jv[r];
+    if (x < 0) {
+      real dj = D[r] * jar[r];
+      q0 += (real)0.5 * dj * jar[r];
+      q1 += dj * jv[r];
+      q2 += (real)0.5 * D[r] * jv[r] * jv[r];
+    }
+  }
+  q0 = b2_wsum(q0) + q0g; q1 = b2_wsum(q1) + q1g; q2 = b2_wsum(q2) + q2g;
+  LsPnt p;
+  p.alpha = alpha;
+  p.cost = alpha * alpha * q2 + alpha * q1 + q0;
+  p.d1 = 2 * alpha * q2 + q1;
+  p.d2 = 2 * q2;
+  if (p.d2 <= 0) p.d2 = B2_MINVAL;
+  return p;
+}
+
+B2_DEV bool ls_update_bracket(LsPnt& p, const LsPnt* cand, LsPnt& pnext, int& nev, real q0g, real q1g, real q2g,
+                              const real* jar, const real* jv, const real* D, int nefc) {
+  bool flag = false;
+  for (int i = 0; i < 3; ++i) {
+    if (p.d1 < 0 && cand[i].d1 < 0 && p.d1 < cand[i].d1) { p = cand[i]; flag = true; }
+    else if (p.d1 > 0 && cand[i].d1 > 0 && p.d1 > cand[i].d1) { p = cand[i]; flag = true; }
+  }
+  if (flag) { pnext = ls_eval(p.alpha - p.d1 / p.d2, q0g, q1g, q2g, jar, jv, D, nefc); ++nev; }
+  return flag;
+}
+
+// Exact 1-D minimisation along `search` (MuJoCo's iterative primal line search:
+// Newton steps until the derivative changes sign, then bracket refinement).
+B2_DEV real linesearch(real q0g, real q1g, real q2g, real snorm, real tolerance, real ls_tolerance, int ls_iterations,
+                       real scale, const real* jar, const real* jv, const real* D, int nefc) {
+  if (snorm < B2_MINVAL) return 0;
+  real gtol = tolerance * ls_tolerance * snorm / scale;
+  int nev = 0;
+  LsPnt p0 = ls_eval(0, q0g, q1g, q2g, jar, jv, D, nefc);
+  LsPnt p1 = ls_eval(p0.alpha - p0.d1 / p0.d2, q0g, q1g, q2g, jar, jv, D, nefc); ++nev;
+  if (p0.cost < p1.cost) p1 = p0;
+  if (fabs(p1.d1) < gtol) return p1.alpha;
+  real dir = p1.d1 < 0 ? (real)1 : (real)-1;
+  LsPnt p2 = p1;
+  bool p2set = false;
+  while (p1.d1 * dir <= -gtol && nev < ls_iterations) {
+    p2 = p1; p2set = true;
+    p1 = ls_eval(p1.alpha - p1.d1 / p1.d2, q0g, q1g, q2g, jar, jv, D, nefc); ++nev;
+    if (fabs(p1.d1) < gtol) return p1.alpha;
+  }
+  if (nev >= ls_iterations || !p2set) return p1.alpha;
+  LsPnt p2next = p1;
+  LsPnt p1next = ls_eval(p1.alpha - p1.d1 / p1.d2, q0g, q1g, q2g, jar, jv, D, nefc); ++nev;
+  while (nev < ls_iterations) {
+    LsPnt pmid = ls_eval((real)0.5 * (p1.alpha + p2.alpha), q0g, q1g, q2g, jar, jv, D, nefc); ++nev;
+    LsPnt cand[3] = {p1next, p2next, pmid};
+    int best = -1;
+    for (int i = 0; i < 3; ++i)
+      if (fabs(cand[i].d1) < gtol && (best < 0 || cand[i].cost < cand[best].cost)) best = i;
+    if (best >= 0) return cand[best].alpha;
+    bool b1 = ls_update_bracket(p1, cand, p1next, nev, q0g, q1g, q2g, jar, jv, D, nefc);
+    bool b2 = ls_update_bracket(p2, cand, p2next, nev, q0g, q1g, q2g, jar, jv, D, nefc);
+    if (!b1 && !b2) return pmid.cost < p0.cost ? pmid.alpha : (real)0;
+  }
+  if (p1.cost <= p2.cost && p1.cost < p0.cost) return p1.alpha;
+  if (p2.cost <= p1.cost && p2.cost < p0.cost) return p2.alpha;
+  return 0;
+}
+
+// contact-frame force [normal, t1, t2] decoded from the pyramid edge forces
+B2_DEV void contact_force(real* out, int adr, int dim, const real* fri, const real* D, const real* jar) {
+  out[0] = out[1] = out[2] = 0;
+  if (adr < 0) return;
+  if (dim == 1) { real x = jar[adr]; out[0] = x < 0 ? -D[adr] * x : 0; return; }
+  for (int k = 1; k < dim; ++k) {
+    int r = adr + 2 * (k - 1);
+    real x1 = jar[r], x2 = jar[r + 1];
+    real f1 = x1 < 0 ? -D[r] * x1 : 0, f2 = x2 < 0 ? -D[r + 1] * x2 : 0;
+    out[0] += f1 + f2;
+    if (k < 3) out[k] = (f1 - f2) * fri[k - 1];
+  }
+}
+
+B2_DEV bool in_subtree(const int* body_parent, int body, int root) {
+  for (int b = body;; b = body_parent[b]) {
+    if (b == root) return true;
+    if (b == 0) return false;
+  }
+}
+B2_DEV bool match_side(const int* geom_body, const int* body_parent, int objtype, int objid, int geom) {
+  if (objid < 0) return true;
+  if (objtype == B2_OBJ_GEOM) return geom == objid;
+  int body = geom_body[geom];
+  if (objtype == B2_OBJ_BODY) return body == objid;
+  if (objtype == B2_OBJ_XBODY) return in_subtree(body_parent, body, objid);
+  return false;
+}
+
+B2_DEV void mat2quat(real* q, const real* R) {
+  real tr = R[0] + R[4] + R[8];
+  if (tr > 0) {
+    real s = sqrt(tr + 1) * 2;
+    q[0] = (real)0.25 * s; q[1] = (R[7] - R[5]) / s; q[2] = (R[2] - R[6]) / s; q[3] = (R[3] - R[1]) / s;
+  } else if (R[0] > R[4] && R[0] > R[8]) {
+    real s = sqrt(1 + R[0] - R[4] - R[8]) * 2;
+    q[0] = (R[7] - R[5]) / s; q[1] = (real)0.25 * s; q[2] = (R[1] + R[3]) / s; q[3] = (R[2] + R[6]) / s;
+  } else if (R[4] > R[8]) {
+    real s = sqrt(1 + R[4] - R[0] - R[8]) * 2;
+    q[0] = (R[2] - R[6]) / s; q[1] = (R[1] + R[3]) / s; q[2] = (real)0.25 * s; q[3] = (R[5] + R[7]) / s;
+  } else {
+    real s = sqrt(1 + R[8] - R[0] - R[4]) * 2;
+    q[0] = (R[3] - R[1]) / s; q[1] = (R[2] + R[6]) / s; q[2] = (R[5] + R[7]) / s; q[3] = (real)0.25 * s;
+  }
+  quat_normalize(q);
+}
+
+// ---------------------------------------------------------------------------
+// Stage 2 for world w.
+// ---------------------------------------------------------------------------
+B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int w, real* sm, int do_integrate) {
+  const int nv = m.nv, nb = m.nbody, nq = m.nq, nu = m.nu, njmax = d.njmax, nconmax = d.nconmax;
+  real* M = sm + L.M; real* H = sm + L.H; real* chunk = sm + L.chunk; real* cdof = sm + L.cdof;
+  real* qvel = sm + L.qvel; real* qacc = sm + L.qacc; real* Ma = sm + L.Ma; real* grad = sm + L.grad;
+  real* search = sm + L.search; real* Mv = sm + L.Mv; real* qfs = sm + L.qfs; real* qas = sm + L.qas;
+  real* qfc = sm + L.qfc; real* tmp = sm + L.tmp;
+  real* D = sm + L.D; real* aref = sm + L.aref; real* jar = sm + L.jar; real* jv = sm + L.jv;
+  int* rowsrc = (int*)jv;  // row -> source (contact id, or -(jnt+1)); dead before the line search needs jv
+
+  const int* body_parent = MI(B2_MI_BODY_PARENTID);
+  const int* body_root = MI(B2_MI_BODY_ROOTID);
+  const int* dofmask = MI(B2_MI_BODY_DOFMASK);
+  const int* geom_body = MI(B2_MI_GEOM_BODYID);
+  const int* jnt_type = MI(B2_MI_JNT_TYPE);
+  const int* jnt_qposadr = MI(B2_MI_JNT_QPOSADR);
+  const int* jnt_dofadr = MI(B2_MI_JNT_DOFADR);
+  const int* jnt_limited = MI(B2_MI_JNT_LIMITED);
+  const real timestep = MF(B2_MF_OPT_TIMESTEP)[0];
+
+  real* g_qpos = d.df[B2_DF_QPOS] + (size_t)w * nq;
+  real* g_qvel = d.df[B2_DF_QVEL] + (size_t)w * nv;
+  real* gJ = d.df[B2_DF_EFC_J] + (size_t)w * njmax * nv;
+  const real* g_scom = d.df[B2_DF_SUBTREE_COM] + (size_t)w * nb * 3;
+  const real* g_cdof = d.df[B2_DF_CDOF] + (size_t)w * nv * 6;
+  const real* g_M = d.df[B2_DF_QM] + (size_t)w * nv * nv;
+
+  for (int i = B2_LANE; i < nv * nv; i += B2_NLANE) M[i] = g_M[i];
+  for (int i = B2_LANE; i < 6 * nv; i += B2_NLANE) cdof[i] = g_cdof[i];
+  for (int i = B2_LANE; i < nv; i += B2_NLANE) {
+    qvel[i] = g_qvel[i];
+    qfs[i] = d.df[B2_DF_QFRC_SMOOTH][(size_t)w * nv + i];
+    qas[i] = d.df[B2_DF_QACC_SMOOTH][(size_t)w * nv + i];
+  }
+  B2_WSYNC();
+
+  // ---- joint-limit rows (ordered: joint, lower then upper) ----------------------
+  int nefc = 0;
+  {
+    const real* jnt_range = MF(B2_MF_JNT_RANGE);
+    const real* jnt_margin = MF(B2_MF_JNT_MARGIN);
+    for (int base = 0; base < 2 * m.njnt; base += B2_NLANE) {
+      int s = base + B2_LANE;
+      bool on = false;
+      real dist = 0;
+      int j = s >> 1, side = s & 1;
+      if (s < 2 * m.njnt && jnt_limited[j] && (jnt_type[j] == B2_JNT_HINGE || jnt_type[j] == B2_JNT_SLIDE)) {
+        real q = g_qpos[jnt_qposadr[j]];
+        dist = side == 0 ? q - jnt_range[2 * j] : jnt_range[2 * j + 1] - q;
+        on = dist < jnt_margin[j];
+      }
+      unsigned bal = b2_ballot(on);
+      if (on) {
+        int row = nefc + b2_popc(bal & b2_lanemask_lt());
+        if (row < njmax) {
+          real* Jr = gJ + (size_t)row * nv;
+          for (int e = 0; e < nv; ++e) Jr[e] = 0;
+          Jr[jnt_dofadr[j]] = side == 0 ? (real)1 : (real)-1;
+          rowsrc[row] = -(j + 1);
+          d.df[B2_DF_EFC_POS][(size_t)w * njmax + row] = dist;
+          d.df[B2_DF_EFC_MARGIN][(size_t)w * njmax + row] = jnt_margin[j];
+        }
+      }
+      nefc += b2_popc(bal);
+    }
+    if (nefc > njmax) nefc = njmax;
+  }
+  const int nl = nefc;
+
+  // ---- contact rows --------------------------------------------------------------
+  const int ncon = d.di[B2_DI_NCON][w];
+  const real* c_dist = d.df[B2_DF_CONTACT_DIST] + (size_t)w * nconmax;
+  const real* c_pos = d.df[B2_DF_CONTACT_POS] + (size_t)w * nconmax * 3;
+  const real* c_frame = d.df[B2_DF_CONTACT_FRAME] + (size_t)w * nconmax * 9;
+  const real* c_inc = d.df[B2_DF_CONTACT_INCLUDEMARGIN] + (size_t)w * nconmax;
+  const real* c_fri = d.df[B2_DF_CONTACT_FRICTION] + (size_t)w * nconmax * 5;
+  const real* c_solref = d.df[B2_DF_CONTACT_SOLREF] + (size_t)w * nconmax * 2;
+  const real* c_solimp = d.df[B2_DF_CONTACT_SOLIMP] + (size_t)w * nconmax * 5;
+  const int* c_geom = d.di[B2_DI_CONTACT_GEOM] + (size_t)w * nconmax * 2;
+  const int* c_dim = d.di[B2_DI_CONTACT_DIM] + (size_t)w * nconmax;
+  int* c_adr = d.di[B2_DI_CONTACT_EFC_ADDRESS] + (size_t)w * nconmax;
+  int ndrop = 0;
+  {
+    // row addresses by prefix sum over contacts; a contact is kept iff its rows fit below njmax
+    int run = nefc;
+    for (int base = 0; base < ncon; base += B2_NLANE) {
+      int c = base + B2_LANE;
+      int nrow = 0;
+      if (c < ncon && c_dist[c] < c_inc[c]) nrow = c_dim[c] == 1 ? 1 : 2 * (c_dim[c] - 1);
+      int incl = nrow;
+#ifndef B2_HOSTEMU
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (B2_LANE >= o) incl += t;
+      }
+      int total = __shfl_sync(0xffffffffu, incl, 31);
+#else
+      int total = incl;
+#endif
+      if (c < ncon) {
+        int adr = run + incl - nrow;
+        bool keep = nrow > 0 && adr + nrow <= njmax;
+        c_adr[c] = keep ? adr : -1;
+        if (nrow > 0 && !keep) ndrop += nrow;
+      }
+      run += total;
+    }
+    ndrop = b2_wsum_i(ndrop);
+    nefc = run - ndrop;
+    B2_WSYNC();
+  }
+  // Jacobian rows, contact by contact, lanes over dofs
+  {
+    for (int c = 0; c < ncon; ++c) {
+      int adr = c_adr[c];
+      if (adr < 0) continue;
+      int g1 = c_geom[2 * c], g2 = c_geom[2 * c + 1];
+      int b1 = geom_body[g1], b2 = geom_body[g2];
+      int r1 = body_root[b1], r2 = body_root[b2];
+      const real* p = c_pos + 3 * c;
+      real o1[3] = {p[0] - g_scom[3 * r1], p[1] - g_scom[3 * r1 + 1], p[2] - g_scom[3 * r1 + 2]};
+      real o2[3] = {p[0] - g_scom[3 * r2], p[1] - g_scom[3 * r2 + 1], p[2] - g_scom[3 * r2 + 2]};
+      const real* F = c_frame + 9 * c;
+      int dim = c_dim[c];
+      unsigned lo1 = (unsigned)dofmask[2 * b1], hi1 = (unsigned)dofmask[2 * b1 + 1];
+      unsigned lo2 = (unsigned)dofmask[2 * b2], hi2 = (unsigned)dofmask[2 * b2 + 1];
+      for (int e = B2_LANE; e < nv; e += B2_NLANE) {
+        bool in1 = e < 32 ? ((lo1 >> e) & 1u) : ((hi1 >> (e - 32)) & 1u);
+        bool in2 = e < 32 ? ((lo2 >> e) & 1u) : ((hi2 >> (e - 32)) & 1u);
+        real jd[3] = {0, 0, 0};
+        const real* cd = cdof + 6 * e;
+        if (in2) { real t[3]; cross3(t, cd, o2); jd[0] += cd[3] + t[0]; jd[1] += cd[4] + t[1]; jd[2] += cd[5] + t[2]; }
+        if (in1) { real t[3]; cross3(t, cd, o1); jd[0] -= cd[3] + t[0]; jd[1] -= cd[4] + t[1]; jd[2] -= cd[5] + t[2]; }
+        real jn = F[0] * jd[0] + F[1] * jd[1] + F[2] * jd[2];
+        if (dim == 1) {
+          gJ[(size_t)adr * nv + e] = jn;
+        } else {
+          for (int k = 1; k < dim; ++k) {
+            real jt = k < 3 ? F[3 * k] * jd[0] + F[3 * k + 1] * jd[1] + F[3 * k + 2] * jd[2] : (real)0;
+            real mu = c_fri[5 * c + k - 1];
+            gJ[(size_t)(adr + 2 * (k - 1)) * nv + e] = jn + mu * jt;
+            gJ[(size_t)(adr + 2 * (k - 1) + 1) * nv + e] = jn - mu * jt;
+          }
+        }
+      }
+      int nrow = dim == 1 ? 1 : 2 * (dim - 1);
+      for (int r = B2_LANE; r < nrow; r += B2_NLANE) {
+        rowsrc[adr + r] = c;
+        d.df[B2_DF_EFC_POS][(size_t)w * njmax + adr + r] = c_dist[c];
+        d.df[B2_DF_EFC_MARGIN][(size_t)w * njmax + adr + r] = c_inc[c];
+      }
+    }
+    B2_WSYNC();
+  }
+  if (B2_LANE == 0) {
+    d.di[B2_DI_NEFC][w] = nefc;
+    d.di[B2_DI_NL][w] = nl;
+    d.di[B2_DI_NEFC_DROPPED][w] = ndrop;
+  }
+
+  // ---- per-row impedance, D, aref ---------------------------------------------------
+  real* g_efcD = d.df[B2_DF_EFC_D] + (size_t)w * njmax;
+  real* g_aref = d.df[B2_DF_EFC_AREF] + (size_t)w * njmax;
+  real* g_force = d.df[B2_DF_EFC_FORCE] + (size_t)w * njmax;
+  if (nefc > 0) {
+    rows_dot(gJ, nefc, nv, qvel, chunk, jar, nullptr);  // jar <- J qvel (temporarily)
+    const real* biw = MF(B2_MF_BODY_INVWEIGHT0);
+    const real* diw = MF(B2_MF_DOF_INVWEIGHT0);
+    const real* jnt_solref = MF(B2_MF_JNT_SOLREF);
+    const real* jnt_solimp = MF(B2_MF_JNT_SOLIMP);
+    const real impratio = MF(B2_MF_OPT_IMPRATIO)[0];
+    const real* g_pos = d.df[B2_DF_EFC_POS] + (size_t)w * njmax;
+    const real* g_mar = d.df[B2_DF_EFC_MARGIN] + (size_t)w * njmax;
+    for (int r = B2_LANE; r < nefc; r += B2_NLANE) {
+      int src = rowsrc[r];
+      real invw, k, b, imp;
+      real pos = g_pos[r] - g_mar[r];
+      if (src < 0) {
+        int j = -src - 1;
+        invw = diw[jnt_dofadr[j]];
+        kbi(timestep, jnt_solref + 2 * j, jnt_solimp + 5 * j, pos, k, b, imp);
+      } else {
+        int c = src;
+        int b1 = geom_body[c_geom[2 * c]], b2 = geom_body[c_geom[2 * c + 1]];
+        invw = biw[2 * b1] + biw[2 * b2];
+        if (c_dim[c] > 1) {
+          real f0 = c_fri[5 * c];
+          invw = (invw + f0 * f0 * invw) * 2 * f0 * f0 / impratio;
+        }
+        kbi(timestep, c_solref + 2 * c, c_solimp + 5 * c, pos, k, b, imp);
+      }
+      real R = fmax(invw * (1 - imp) / imp, B2_MINVAL);
+      real Dr = (real)1 / R;
+      real ar = -b * jar[r] - k * imp * pos;
+      D[r] = Dr; aref[r] = ar;
+      g_efcD[r] = Dr; g_aref[r] = ar;
+    }
+    B2_WSYNC();
+  }
+
+  // ---- solve -----------------------------------------------------------------------------
+  int niter = 0;
+  real* g_qacc = d.df[B2_DF_QACC] + (size_t)w * nv;
+  real* g_qfc = d.df[B2_DF_QFRC_CONSTRAINT] + (size_t)w * nv;
+  if (nefc == 0) {
+    for (int i = B2_LANE; i < nv; i += B2_NLANE) { qacc[i] = qas[i]; qfc[i] = 0; }
+    B2_WSYNC();
+  } else {
+    const real tolerance = MF(B2_MF_OPT_TOLERANCE)[0];
+    const real ls_tolerance = MF(B2_MF_OPT_LS_TOLERANCE)[0];
+    const real meaninertia = MF(B2_MF_STAT_MEANINERTIA)[0];
+    const real scale = (real)1 / (meaninertia * (real)(nv > 1 ? nv : 1));
+    const real* g_ws = d.df[B2_DF_QACC_WARMSTART] + (size_t)w * nv;
+    // cost at qacc_smooth (Gauss term vanishes)
+    rows_dot(gJ, nefc, nv, qas, chunk, jar, aref);
+    real cs = 0;
+    for (int r = B2_LANE; r < nefc; r += B2_NLANE) { real x = jar[r]; if (x < 0) cs += (real)0.5 * D[r] * x * x; }
+    cs = b2_wsum(cs);
+    // cost at the warm start
+    for (int i = B2_LANE; i < nv; i += B2_NLANE) qacc[i] = g_ws[i];
+    B2_WSYNC();
+    rows_dot(gJ, nefc, nv, qacc, chunk, jar, aref);
+    real cw = 0;
+    for (int r = B2_LANE; r < nefc; r += B2_NLANE) { real x = jar[r]; if (x < 0) cw += (real)0.5 * D[r] * x * x; }
+    real gw = 0;
+    for (int i = B2_LANE; i < nv; i += B2_NLANE) {
+      real a = 0;
+      for (int e = 0; e < nv; ++e) a += M[i * nv + e] * qacc[e];
+      Ma[i] = a;
+      gw += (real)0.5 * (a - qfs[i]) * (qacc[i] - qas[i]);
+    }
+    cw = b2_wsum(cw + gw);
+    B2_WSYNC();
+    if (cw > cs) {
+      for (int i = B2_LANE; i < nv; i += B2_NLANE) qacc[i] = qas[i];
+      B2_WSYNC();
+      rows_dot(gJ, nefc, nv, qacc, chunk, jar, aref);
+      for (int i = B2_LANE; i < nv; i += B2_NLANE) {
+        real a = 0;
+        for (int e = 0; e < nv; ++e) a += M[i * nv + e] * qacc[e];
+        Ma[i] = a;
+      }
+      B2_WSYNC();
+    }
+    real cost = 0, gauss = 0;
+    for (int it = 0;; ++it) {
+      // -- constraint update: cost, qfrc_constraint, gradient, Hessian, Newton direction
+      real c1 = 0;
+      for (int r = B2_LANE; r < nefc; r += B2_NLANE) { real x = jar[r]; if (x < 0) c1 += (real)0.5 * D[r] * x * x; }
+      real g1 = 0;
+      for (int i = B2_LANE; i < nv; i += B2_NLANE) g1 += (real)0.5 * (Ma[i] - qfs[i]) * (qacc[i] - qas[i]);
+      gauss = b2_wsum(g1);
+      real newcost = b2_wsum(c1) + gauss;
+      // H = M + J^T diag(D*active) J and qfc = J^T force, one pass over J in chunks
+      for (int i = B2_LANE; i < nv * nv; i += B2_NLANE) H[i] = M[i];
+      for (int i = B2_LANE; i < nv; i += B2_NLANE) qfc[i] = 0;
+      for (int base = 0; base < nefc; base += B2_CHUNK) {
+        int nr = nefc - base < B2_CHUNK ? nefc - base : B2_CHUNK;
+        B2_WSYNC();
+        for (int i = B2_LANE; i < nr * nv; i += B2_NLANE) chunk[i] = gJ[(size_t)base * nv + i];
+        B2_WSYNC();
+        // qfc += J^T f (lanes over dofs)
+        for (int e = B2_LANE; e < nv; e += B2_NLANE) {
+          real a = 0;
+          for (int r = 0; r < nr; ++r) { real x = jar[base + r]; if (x < 0) a -= chunk[r * nv + e] * D[base + r] * x; }
+          qfc[e] += a;
+        }
+        // scale active rows by sqrt(D), zero inactive ones
+        B2_WSYNC();
+        for (int i = B2_LANE; i < nr * nv; i += B2_NLANE) {
+          int r = i / nv;
+          chunk[i] = jar[base + r] < 0 ? chunk[i] * sqrt(D[base + r]) : (real)0;
+        }
+        B2_WSYNC();
+        for (int i = 0; i < nv; ++i) {
+          for (int j = B2_LANE; j <= i; j += B2_NLANE) {
+            real a = 0;
+            for (int r = 0; r < nr; ++r) a += chunk[r * nv + i] * chunk[r * nv + j];
+            H[i * nv + j] += a;
+          }
+        }
+      }
+      B2_WSYNC();
+      for (int i = B2_LANE; i < nv; i += B2_NLANE) { real g = Ma[i] - qfs[i] - qfc[i]; grad[i] = g; tmp[i] = g; }
+      B2_WSYNC();
+      if (it > 0) {
+        real gn = 0;
+        for (int i = B2_LANE; i < nv; i += B2_NLANE) gn += grad[i] * grad[i];
+        gn = sqrt(b2_wsum(gn));
+        real improvement = scale * (cost - newcost);
+        cost = newcost;
+        if (improvement < tolerance || scale * gn < tolerance) break;
+      } else {
+        cost = newcost;
+      }
+      if (it >= m.iterations) break;
+      chol_factor(H, nv);
+      chol_solve(H, tmp, nv);
+      for (int i = B2_LANE; i < nv; i += B2_NLANE) search[i] = -tmp[i];
+      B2_WSYNC();
+      // -- line search
+      real sn = 0, q1 = 0, q2 = 0;
+      for (int i = B2_LANE; i < nv; i += B2_NLANE) {
+        real a = 0;
+        for (int e = 0; e < nv; ++e) a += M[i * nv + e] * search[e];
+        Mv[i] = a;
+        sn += search[i] * search[i];
+        q1 += search[i] * (Ma[i] - qfs[i]);
+        q2 += (real)0.5 * search[i] * a;
+      }
+      sn = sqrt(b2_wsum(sn)); q1 = b2_wsum(q1); q2 = b2_wsum(q2);
+      rows_dot(gJ, nefc, nv, search, chunk, jv, nullptr);
+      real alpha = linesearch(gauss, q1, q2, sn, tolerance, ls_tolerance, m.ls_iterations, scale, jar, jv, D, nefc);
+      if (alpha == 0) break;
+      for (int i = B2_LANE; i < nv; i += B2_NLANE) { qacc[i] += alpha * search[i]; Ma[i] += alpha * Mv[i]; }
+      for (int r = B2_LANE; r < nefc; r += B2_NLANE) jar[r] += alpha * jv[r];
+      B2_WSYNC();
+      niter = it + 1;
+    }
+    // qfc / efc_force at the final point: the loop exits right after a constraint update
+    // (break at the convergence test or iteration cap) or with alpha == 0 (state unchanged).
+    for (int r = B2_LANE; r < nefc; r += B2_NLANE) { real x = jar[r]; g_force[r] = x < 0 ? -D[r] * x : 0; }
+  }
+  for (int i = B2_LANE; i < nv; i += B2_NLANE) { g_qacc[i] = qacc[i]; g_qfc[i] = qfc[i]; }
+  if (B2_LANE == 0) d.di[B2_DI_SOLVER_NITER][w] = niter;
+  B2_WSYNC();
+
+  // ---- sensors -------------------------------------------------------------------------
+  if (m.nsensor > 0) {
+    const int* s_type = MI(B2_MI_SENSOR_TYPE);
+    const int* s_objtype = MI(B2_MI_SENSOR_OBJTYPE);
+    const int* s_objid = MI(B2_MI_SENSOR_OBJID);
+    const int* s_reftype = MI(B2_MI_SENSOR_REFTYPE);
+    const int* s_refid = MI(B2_MI_SENSOR_REFID);
+    const int* s_intprm = MI(B2_MI_SENSOR_INTPRM);
+    const int* s_dim = MI(B2_MI_SENSOR_DIM);
+    const int* s_adr = MI(B2_MI_SENSOR_ADR);
+    const real* s_cutoff = MF(B2_MF_SENSOR_CUTOFF);
+    const int* site_body = MI(B2_MI_SITE_BODYID);
+    const int* level_adr = MI(B2_MI_LEVEL_ADR);
+    const int* level_body = MI(B2_MI_LEVEL_BODY);
+    const int* child_adr = MI(B2_MI_CHILD_ADR);
+    const int* child_body = MI(B2_MI_CHILD_BODY);
+    const int* body_dofnum = MI(B2_MI_BODY_DOFNUM);
+    const int* body_dofadr = MI(B2_MI_BODY_DOFADR);
+    const real* g_cvel = d.df[B2_DF_CVEL] + (size_t)w * nb * 6;
+    const real* g_cdofdot = d.df[B2_DF_CDOF_DOT] + (size_t)w * nv * 6;
+    const real* g_xipos = d.df[B2_DF_XIPOS] + (size_t)w * nb * 3;
+    const real* g_ximat = d.df[B2_DF_XIMAT] + (size_t)w * nb * 9;
+    const real* g_sxpos = d.df[B2_DF_SITE_XPOS] + (size_t)w * m.nsite * 3;
+    const real* g_sxmat = d.df[B2_DF_SITE_XMAT] + (size_t)w * m.nsite * 9;
+    real* g_cacc = d.df[B2_DF_CACC] + (size_t)w * nb * 6;
+    real* g_slin = d.df[B2_DF_SUBTREE_LINVEL] + (size_t)w * nb * 3;
+    real* g_sang = d.df[B2_DF_SUBTREE_ANGMOM] + (size_t)w * nb * 3;
+    real* sd = d.df[B2_DF_SENSORDATA] + (size_t)w * m.nsensordata;
+    const real* body_mass = MF(B2_MF_BODY_MASS);
+    const real* body_inertia = MF(B2_MF_BODY_INERTIA);
+
+    if (m.has_accelerometer) {
+      // cacc including qacc (rne_postconstraint, acceleration part), forward over levels
+      const real* grav = MF(B2_MF_OPT_GRAVITY);
+      for (int lev = 0; lev < m.nlevel; ++lev) {
+        for (int k = level_adr[lev] + B2_LANE; k < level_adr[lev + 1]; k += B2_NLANE) {
+          int b = level_body[k];
+          real a[6];
+          if (b == 0) {
+            a[0] = a[1] = a[2] = 0; a[3] = -grav[0]; a[4] = -grav[1]; a[5] = -grav[2];
+          } else {
+            int p = body_parent[b];
+            for (int c = 0; c < 6; ++c) a[c] = g_cacc[6 * p + c];
+            for (int e = 0; e < body_dofnum[b]; ++e) {
+              int dd = body_dofadr[b] + e;
+              for (int c = 0; c < 6; ++c) a[c] += g_cdofdot[6 * dd + c] * qvel[dd] + cdof[6 * dd + c] * qacc[dd];
+            }
+          }
+          for (int c = 0; c < 6; ++c) g_cacc[6 * b + c] = a[c];
+        }
+        B2_WSYNC();
+      }
+    }
+    if (m.has_subtreevel) {
+      // subtree linear velocity: backward gather of body momenta
+      // per-body com velocity and own angular momentum stored first
+      for (int b = B2_LANE; b < nb; b += B2_NLANE) {
+        int r = body_root[b];
+        const real* v = g_cvel + 6 * b;
+        real off[3] = {g_xipos[3 * b] - g_scom[3 * r], g_xipos[3 * b + 1] - g_scom[3 * r + 1], g_xipos[3 * b + 2] - g_scom[3 * r + 2]};
+        real t[3];
+        cross3(t, v, off);
+        real ms = body_mass[b];
+        g_slin[3 * b] = ms * (v[3] + t[0]); g_slin[3 * b + 1] = ms * (v[4] + t[1]); g_slin[3 * b + 2] = ms * (v[5] + t[2]);
+        const real* Ri = g_ximat + 9 * b;
+        real wl[3], Iw[3];
+        mulmTv3(wl, Ri, v);
+        wl[0] *= body_inertia[3 * b]; wl[1] *= body_inertia[3 * b + 1]; wl[2] *= body_inertia[3 * b + 2];
+        mulmv3(Iw, Ri, wl);
+        g_sang[3 * b] = Iw[0]; g_sang[3 * b + 1] = Iw[1]; g_sang[3 * b + 2] = Iw[2];
+      }
+      B2_WSYNC();
+      // angular momentum about each subtree's com: gather children bottom-up.  Keep momentum P, mass m and
+      // L about own subtree com; combining child c into parent p:  L_p += L_c + (com_c - com_p) x P_c  is exact
+      // when L is taken about com with absolute velocities: L_about_com = sum r_i x m_i v_i (since sum m_i r_i = 0).
+      // Stage A: L_b (about xipos_b, own body) -> shift to subtree com later, so store body term about its own com.
+      // Stage B: bottom-up: for parent p: P_p = P_own + sum P_c ; L_p(about com_p) = L_own + (xipos_p - com_p) x P_own
+      //          + sum_c [ L_c + (com_c - com_p) x P_c ].
+      for (int lev = m.nlevel - 1; lev >= 0; --lev) {
+        for (int k = level_adr[lev] + B2_LANE; k < level_adr[lev + 1]; k += B2_NLANE) {
+          int b = level_body[k];
+          real P[3] = {g_slin[3 * b], g_slin[3 * b + 1], g_slin[3 * b + 2]};
+          real Lb[3] = {g_sang[3 * b], g_sang[3 * b + 1], g_sang[3 * b + 2]};
+          real dx[3] = {g_xipos[3 * b] - g_scom[3 * b], g_xipos[3 * b + 1] - g_scom[3 * b + 1], g_xipos[3 * b + 2] - g_scom[3 * b + 2]};
+          real t[3];
+          cross3(t, dx, P);
+          Lb[0] += t[0]; Lb[1] += t[1]; Lb[2] += t[2];
+          for (int c = child_adr[b]; c < child_adr[b + 1]; ++c) {
+            int ch = child_body[c];
+            real Pc[3] = {g_slin[3 * ch], g_slin[3 * ch + 1], g_slin[3 * ch + 2]};
+            real dc[3] = {g_scom[3 * ch] - g_scom[3 * b], g_scom[3 * ch + 1] - g_scom[3 * b + 1], g_scom[3 * ch + 2] - g_scom[3 * b + 2]};
+            cross3(t, dc, Pc);
+            Lb[0] += g_sang[3 * ch] + t[0]; Lb[1] += g_sang[3 * ch + 1] + t[1]; Lb[2] += g_sang[3 * ch + 2] + t[2];
+            P[0] += Pc[0]; P[1] += Pc[1]; P[2] += Pc[2];
+          }
+          g_slin[3 * b] = P[0]; g_slin[3 * b + 1] = P[1]; g_slin[3 * b + 2] = P[2];
+          g_sang[3 * b] = Lb[0]; g_sang[3 * b + 1] = Lb[1]; g_sang[3 * b + 2] = Lb[2];
+        }
+        B2_WSYNC();
+      }
+      // momentum -> velocity
+      const real* stm = MF(B2_MF_BODY_SUBTREEMASS);
+      for (int b = B2_LANE; b < nb; b += B2_NLANE) {
+        real inv = stm[b] > B2_MINVAL ? (real)1 / stm[b] : (real)0;
+        g_slin[3 * b] *= inv; g_slin[3 * b + 1] *= inv; g_slin[3 * b + 2] *= inv;
+      }
+      B2_WSYNC();
+    }
+    B2_WSYNC();
+    for (int s = B2_LANE; s < m.nsensor; s += B2_NLANE) {
+      int t = s_type[s], oid = s_objid[s], adr = s_adr[s], dim = s_dim[s];
+      real* out = sd + adr;
+      for (int e = 0; e < dim; ++e) out[e] = 0;
+      if (t == B2_SENS_GYRO || t == B2_SENS_VELOCIMETER || t == B2_SENS_ACCELEROMETER) {
+        int b = site_body[oid], r = body_root[b];
+        const real* R = g_sxmat + 9 * oid;
+        const real* v = g_cvel + 6 * b;
+        real off[3] = {g_sxpos[3 * oid] - g_scom[3 * r], g_sxpos[3 * oid + 1] - g_scom[3 * r + 1], g_sxpos[3 * oid + 2] - g_scom[3 * r + 2]};
+        real tt[3], lin[3], angl[3], linl[3];
+        cross3(tt, v, off);
+        lin[0] = v[3] + tt[0]; lin[1] = v[4] + tt[1]; lin[2] = v[5] + tt[2];
+        mulmTv3(angl, R, v);
+        mulmTv3(linl, R, lin);
+        if (t == B2_SENS_GYRO) { out[0] = angl[0]; out[1] = angl[1]; out[2] = angl[2]; }
+        else if (t == B2_SENS_VELOCIMETER) { out[0] = linl[0]; out[1] = linl[1]; out[2] = linl[2]; }
+        else {
+          const real* a = g_cacc + 6 * b;
+          real al[3], acc[3], cor[3];
+          cross3(tt, a, off);
+          al[0] = a[3] + tt[0]; al[1] = a[4] + tt[1]; al[2] = a[5] + tt[2];
+          mulmTv3(acc, R, al);
+          cross3(cor, angl, linl);
+          out[0] = acc[0] + cor[0]; out[1] = acc[1] + cor[1]; out[2] = acc[2] + cor[2];
+        }
+      } else if (t == B2_SENS_JOINTPOS) {
+        out[0] = g_qpos[jnt_qposadr[oid]];
+      } else if (t == B2_SENS_JOINTVEL) {
+        out[0] = qvel[jnt_dofadr[oid]];
+      } else if (t == B2_SENS_SUBTREECOM) {
+        out[0] = g_scom[3 * oid]; out[1] = g_scom[3 * oid + 1]; out[2] = g_scom[3 * oid + 2];
+      } else if (t == B2_SENS_SUBTREELINVEL) {
+        out[0] = g_slin[3 * oid]; out[1] = g_slin[3 * oid + 1]; out[2] = g_slin[3 * oid + 2];
+      } else if (t == B2_SENS_SUBTREEANGMOM) {
+        out[0] = g_sang[3 * oid]; out[1] = g_sang[3 * oid + 1]; out[2] = g_sang[3 * oid + 2];
+      } else if (t == B2_SENS_FRAMEPOS || t == B2_SENS_FRAMEQUAT || t == B2_SENS_FRAMELINVEL || t == B2_SENS_FRAMEANGVEL) {
+        int ot = s_objtype[s];
+        const real *pos, *R;
+        int b;
+        if (ot == B2_OBJ_SITE) { pos = g_sxpos + 3 * oid; R = g_sxmat + 9 * oid; b = site_body[oid]; }
+        else if (ot == B2_OBJ_GEOM) { pos = d.df[B2_DF_GEOM_XPOS] + ((size_t)w * m.ngeom + oid) * 3; R = d.df[B2_DF_GEOM_XMAT] + ((size_t)w * m.ngeom + oid) * 9; b = geom_body[oid]; }
+        else if (ot == B2_OBJ_XBODY) { pos = d.df[B2_DF_XPOS] + ((size_t)w * nb + oid) * 3; R = d.df[B2_DF_XMAT] + ((size_t)w * nb + oid) * 9; b = oid; }
+        else { pos = g_xipos + 3 * oid; R = g_ximat + 9 * oid; b = oid; }
+        if (t == B2_SENS_FRAMEPOS) { out[0] = pos[0]; out[1] = pos[1]; out[2] = pos[2]; }
+        else if (t == B2_SENS_FRAMEQUAT) { mat2quat(out, R); }
+        else {
+          int r = body_root[b];
+          const real* v = g_cvel + 6 * b;
+          real off[3] = {pos[0] - g_scom[3 * r], pos[1] - g_scom[3 * r + 1], pos[2] - g_scom[3 * r + 2]};
+          real tt[3];
+          cross3(tt, v, off);
+          if (t == B2_SENS_FRAMELINVEL) { out[0] = v[3] + tt[0]; out[1] = v[4] + tt[1]; out[2] = v[5] + tt[2]; }
+          else { out[0] = v[0]; out[1] = v[1]; out[2] = v[2]; }
+        }
+      } else if (t == B2_SENS_CONTACT) {
+        int bits = s_intprm[3 * s], reduce = s_intprm[3 * s + 1], num = s_intprm[3 * s + 2];
+        int ot = s_objtype[s], rt = s_reftype[s], rid = s_refid[s];
+        int per_slot = dim / (num > 0 ? num : 1);
+        int nfound = 0;
+        real net[3] = {0, 0, 0};
+        // pass 1: count matches (and net force)
+        for (int c = 0; c < ncon; ++c) {
+          int g1 = c_geom[2 * c], g2 = c_geom[2 * c + 1];
+          real sgn = 0;
+          if (match_side(geom_body, body_parent, ot, oid, g1) && match_side(geom_body, body_parent, rt, rid, g2)) sgn = 1;
+          else if (match_side(geom_body, body_parent, ot, oid, g2) && match_side(geom_body, body_parent, rt, rid, g1)) sgn = -1;
+          if (sgn == 0) continue;
+          ++nfound;
+          if (reduce == 3 && (bits & 2)) {
+            real fc[3], fg[3];
+            contact_force(fc, nefc > 0 ? c_adr[c] : -1, c_dim[c], c_fri + 5 * c, D, jar);
+            mulmTv3(fg, c_frame + 9 * c, fc);
+            net[0] += sgn * fg[0]; net[1] += sgn * fg[1]; net[2] += sgn * fg[2];
+          }
+        }
+        if (nfound > 0) {
+          if (reduce == 3) {
+            int p = 0;
+            if (bits & 1) out[p++] = (real)nfound;
+            if (bits & 2) { out[p] = net[0]; out[p + 1] = net[1]; out[p + 2] = net[2]; p += 3; }
+          } else {
+            // slots: first `num` matches in contact order (reduce none) or ranked by dist / force
+            int filled = 0;
+            real lastkey = 0; int lastc = -1;
+            for (int slot = 0; slot < num && slot < nfound; ++slot) {
+              int pick = -1; real pickkey = 0, picksgn = 0;
+              for (int c = 0; c < ncon; ++c) {
+                int g1 = c_geom[2 * c], g2 = c_geom[2 * c + 1];
+                real sgn = 0;
+                if (match_side(geom_body, body_parent, ot, oid, g1) && match_side(geom_body, body_parent, rt, rid, g2)) sgn = 1;
+                else if (match_side(geom_body, body_parent, ot, oid, g2) && match_side(geom_body, body_parent, rt, rid, g1)) sgn = -1;
+                if (sgn == 0) continue;
+                real key;
+                if (reduce == 0) key = (real)c;
+                else if (reduce == 1) key = c_dist[c];
+                else {
+                  real fc[3];
+                  contact_force(fc, nefc > 0 ? c_adr[c] : -1, c_dim[c], c_fri + 5 * c, D, jar);
+                  key = -sqrt(dot3(fc, fc));
+                }
+                // strict ordering by (key, c) to enumerate matches in sorted order
+                bool after_last = lastc < 0 || key > lastkey || (key == lastkey && c > lastc);
+                if (!after_last) continue;
+                if (pick < 0 || key < pickkey || (key == pickkey && c < pick)) { pick = c; pickkey = key; picksgn = sgn; }
+              }
+              if (pick < 0) break;
+              lastkey = pickkey; lastc = pick;
+              int p = slot * per_slot;
+              int c = pick;
+              if (bits & 1) out[p++] = (real)nfound;
+              if (bits & 2) {
+                real fc[3];
+                contact_force(fc, nefc > 0 ? c_adr[c] : -1, c_dim[c], c_fri + 5 * c, D, jar);
+                out[p] = picksgn * fc[0]; out[p + 1] = picksgn * fc[1]; out[p + 2] = picksgn * fc[2]; p += 3;
+              }
+              if (bits & 4) p += 3;
+              if (bits & 8) out[p++] = c_dist[c];
+              if (bits & 16) { out[p] = c_pos[3 * c]; out[p + 1] = c_pos[3 * c + 1]; out[p + 2] = c_pos[3 * c + 2]; p += 3; }
+              if (bits & 32) { out[p] = picksgn * c_frame[9 * c]; out[p + 1] = picksgn * c_frame[9 * c + 1]; out[p + 2] = picksgn * c_frame[9 * c + 2]; p += 3; }
+              if (bits & 64) { out[p] = picksgn * c_frame[9 * c + 3]; out[p + 1] = picksgn * c_frame[9 * c + 4]; out[p + 2] = picksgn * c_frame[9 * c + 5]; p += 3; }
+              ++filled;
+            }
+            (void)filled;
+          }
+        }
+      }
+      real cut = s_cutoff[s];
+      if (cut > 0 && t != B2_SENS_CONTACT)
+        for (int e = 0; e < dim; ++e) out[e] = clampr(out[e], -cut, cut);
+    }
+    B2_WSYNC();
+  }
+
+  // ---- integrate ---------------------------------------------------------------------------
+  if (do_integrate) {
+    const real* damping = MF(B2_MF_DOF_DAMPING);
+    real* g_ws = d.df[B2_DF_QACC_WARMSTART] + (size_t)w * nv;
+    bool implicit = false;
+    if (m.integrator == B2_INT_IMPLICITFAST) implicit = true;
+    else {
+      int anyd = 0;
+      for (int i = B2_LANE; i < nv; i += B2_NLANE) anyd |= damping[i] > 0;
+      implicit = b2_wor_i(anyd) != 0;
+    }
+    for (int i = B2_LANE; i < nv; i += B2_NLANE) tmp[i] = qacc[i];
+    B2_WSYNC();
+    if (implicit) {
+      // (M - h*qDeriv) a = qfrc_smooth + qfrc_constraint, qDeriv diagonal: -damping (+ actuator velocity gain)
+      for (int i = B2_LANE; i < nv * nv; i += B2_NLANE) H[i] = M[i];
+      B2_WSYNC();
+      const int* trnid = MI(B2_MI_ACTUATOR_TRNID);
+      const int* biastype = MI(B2_MI_ACTUATOR_BIASTYPE);
+      const int* flim = MI(B2_MI_ACTUATOR_FORCELIMITED);
+      const real* biasprm = MF(B2_MF_ACTUATOR_BIASPRM);
+      const real* gear = MF(B2_MF_ACTUATOR_GEAR);
+      const real* frange = MF(B2_MF_ACTUATOR_FORCERANGE);
+      const real* g_af = d.df[B2_DF_ACTUATOR_FORCE] + (size_t)w * nu;
+      for (int i = B2_LANE; i < nv; i += B2_NLANE) {
+        real qd = -damping[i];
+        if (m.integrator == B2_INT_IMPLICITFAST) {
+          for (int a = 0; a < nu; ++a) {
+            if (biastype[a] != 1 || jnt_dofadr[trnid[2 * a]] != i) continue;
+            real fa = g_af[a];
+            if (flim[a] && (fa <= frange[2 * a] || fa >= frange[2 * a + 1])) continue;
+            qd += gear[6 * a] * gear[6 * a] * biasprm[10 * a + 2];
+          }
+        }
+        H[i * nv + i] -= timestep * qd;
+        tmp[i] = qfs[i] + qfc[i];
+      }
+      B2_WSYNC();
+      chol_factor(H, nv);
+      chol_solve(H, tmp, nv);
+    }
+    for (int i = B2_LANE; i < nv; i += B2_NLANE) {
+      real v = qvel[i] + timestep * tmp[i];
+      qvel[i] = v;
+      g_qvel[i] = v;
+      g_ws[i] = qacc[i];
+    }
+    B2_WSYNC();
+    for (int j = B2_LANE; j < m.njnt; j += B2_NLANE) {
+      int qa = jnt_qposadr[j], da = jnt_dofadr[j];
+      if (jnt_type[j] == B2_JNT_FREE) {
+        g_qpos[qa] += timestep * qvel[da]; g_qpos[qa + 1] += timestep * qvel[da + 1]; g_qpos[qa + 2] += timestep * qvel[da + 2];
+        real q[4] = {g_qpos[qa + 3], g_qpos[qa + 4], g_qpos[qa + 5], g_qpos[qa + 6]};
+        real wv[3] = {qvel[da + 3], qvel[da + 4], qvel[da + 5]};
+        real n = sqrt(dot3(wv, wv));
+        if (n >= B2_MINVAL) {
+          real ax[3] = {wv[0] / n, wv[1] / n, wv[2] / n}, dq[4], q2[4];
+          axisangle2quat(dq, ax, timestep * n);
+          quat_mul(q2, q, dq);
+          q[0] = q2[0]; q[1] = q2[1]; q[2] = q2[2]; q[3] = q2[3];
+        }
+        quat_normalize(q);
+        g_qpos[qa + 3] = q[0]; g_qpos[qa + 4] = q[1]; g_qpos[qa + 5] = q[2]; g_qpos[qa + 6] = q[3];
+      } else {
+        g_qpos[qa] += timestep * qvel[da];
+      }
+    }
+    if (B2_LANE == 0) d.df[B2_DF_TIME][w] += timestep;
+  }
+}

@@ -1,0 +1,32 @@
+"""Compile the BASELINE robot scenes into committed model files.
+
+Run in the build container (needs /root/reference for the robot MJCF, which is
+input data, not code):
+
+    python tools/make_models.py
+
+Writes mjlab_b200/assets/{g1_flat,go1_flat}.npz.  Nothing at run time reads
+/root/reference; the GPU box only sees the .npz files.
+"""
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+from mjlab_b200 import robots  # noqa: E402
+
+REF = Path("/root/reference/src/mjlab/asset_zoo/robots")
+SRC = {
+  "g1": REF / "unitree_g1/xmls/g1.xml",
+  "go1": REF / "unitree_go1/xmls/go1.xml",
+}
+
+if __name__ == "__main__":
+  out = ROOT / "mjlab_b200" / "assets"
+  out.mkdir(exist_ok=True)
+  for which, xml in SRC.items():
+    scene = robots.build_scene(xml.read_text(), which)
+    m = scene.compile()
+    m.save(out / f"{which}_flat.npz")
+    print(which, dict(nq=m.nq, nv=m.nv, nu=m.nu, nbody=m.nbody, ngeom=m.ngeom, nsite=m.nsite,
+                      nsensordata=m.nsensordata, npair=m.npair, meaninertia=round(m.stat_meaninertia, 5)))
