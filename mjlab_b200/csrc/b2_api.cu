@@ -144,6 +144,22 @@ static int run(const b2_model* m, b2_data* d, void* stream, int do_integrate) {
   return 0;
 }
 
+int b2_stage(const b2_model* m, b2_data* d, int stage, int do_integrate, void* stream) {
+  Plan p;
+  make_plan(m, d, &p);
+  cudaStream_t st = (cudaStream_t)stream;
+  const KModel& km = *reinterpret_cast<const KModel*>(m);
+  const KData& kd = *reinterpret_cast<const KData*>(d);
+  int grid = (d->nworld + B2_WPB - 1) / B2_WPB;
+  if (stage == 0) k_smooth<<<grid, B2_WPB * 32, p.smem_smooth, st>>>(km, kd, p.ls, B2_NCAND_MAX);
+  else if (stage == 1) k_solve<<<grid, B2_WPB * 32, p.smem_solve, st>>>(km, kd, p.lv, do_integrate);
+  else return fail("unknown stage %d", stage);
+  g_launches += 1;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("launch failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 int b2_step(const b2_model* m, b2_data* d, void* stream) { return run(m, d, stream, 1); }
 int b2_forward(const b2_model* m, b2_data* d, void* stream) { return run(m, d, stream, 0); }
 

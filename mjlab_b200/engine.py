@@ -277,6 +277,8 @@ def load_library() -> C.CDLL:
   for name in ("b2_step", "b2_forward"):
     getattr(lib, name).argtypes = [C.POINTER(B2Model), C.POINTER(B2Data), C.c_void_p]
     getattr(lib, name).restype = C.c_int
+  lib.b2_stage.argtypes = [C.POINTER(B2Model), C.POINTER(B2Data), C.c_int, C.c_int, C.c_void_p]
+  lib.b2_stage.restype = C.c_int
   lib.b2_reset.argtypes = [C.POINTER(B2Model), C.POINTER(B2Data), C.c_void_p, C.c_void_p]
   lib.b2_reset.restype = C.c_int
   lib.b2_repeat_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]

@@ -1,0 +1,129 @@
+"""GPU parity: CUDA path (through the C ABI via Simulation) vs the float64 oracle.
+
+Bit-exact: contact counts, contact geom-pair lists, efc row counts.
+Tolerance (stated per assertion): fp32 device arithmetic vs fp64 oracle,
+1e-4 relative per step on qpos/qvel (north_star), looser where noted.
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def make_sim(m, nworld, nconmax=35, njmax=300, integrator="implicitfast"):
+  from mjlab_b200.sim import MujocoCfg, Simulation, SimulationCfg
+  cfg = SimulationCfg(nconmax=nconmax, njmax=njmax,
+                      mujoco=MujocoCfg(timestep=0.005, iterations=10, ls_iterations=20, integrator=integrator))
+  return Simulation(nworld, cfg, m, "cuda:0")
+
+
+def load_state(sim, qpos, qvel, ctrl, xfrc):
+  f = lambda a: torch.as_tensor(a, dtype=torch.float32, device="cuda:0")
+  sim.data.qpos[:] = f(qpos)
+  sim.data.qvel[:] = f(qvel)
+  sim.data.ctrl[:] = f(ctrl)
+  sim.data.xfrc_applied[:] = f(xfrc)
+  sim.data.qacc_warmstart[:] = 0
+  sim.data.time[:] = 0
+
+
+def relerr(a, b):
+  a, b = np.asarray(a, float), np.asarray(b, float)
+  return np.abs(a - b).max() / max(np.abs(b).max(), 1e-6)
+
+
+@pytest.mark.parametrize("name", ["go1_flat", "g1_flat"])
+def test_forward_stagewise(name):
+  import mjlab_b200
+  m = mjlab_b200.load_model(name)
+  nw = 8
+  qpos, qvel, ctrl, xfrc = util.random_states(m, nw, seed=1, xfrc_world=3)
+  sim = make_sim(m, nw, nconmax=64)
+  load_state(sim, qpos, qvel, ctrl, xfrc)
+  sim.forward()
+  torch.cuda.synchronize()
+  ds = util.oracle_rollout(m, qpos, qvel, ctrl, xfrc, 1, 64, 300, integrate_last=False)
+  D = sim.data
+  for w, d in enumerate(ds):
+    assert int(D.ncon[w]) == len(d.contacts)
+    assert D.contact_geom[w, : len(d.contacts)].cpu().tolist() == [list(p) for p in util.contact_pairs(d)]
+    assert int(D.nefc[w]) == d.nefc
+    for fld, tol in [("xpos", 1e-6), ("xquat", 1e-6), ("geom_xpos", 1e-6), ("subtree_com", 1e-6), ("cdof", 2e-6),
+                     ("qM", 1e-5), ("cvel", 1e-5), ("qfrc_bias", 1e-4), ("qfrc_actuator", 1e-5), ("qfrc_smooth", 1e-4),
+                     ("qacc_smooth", 1e-3)]:
+      assert relerr(getattr(D, fld)[w].cpu().numpy(), getattr(d, fld)) < tol, (w, fld)
+    n = d.nefc
+    if n:
+      assert relerr(D.efc_J[w, :n].cpu().numpy(), d.efc_J) < 1e-5
+      assert relerr(D.efc_D[w, :n].cpu().numpy(), d.efc_D) < 1e-4
+      assert relerr(D.efc_aref[w, :n].cpu().numpy(), d.efc_aref) < 1e-3
+      assert relerr(D.efc_force[w, :n].cpu().numpy(), d.efc_force) < 5e-3
+    assert relerr(D.qacc[w].cpu().numpy(), d.qacc) < 1e-3
+    assert relerr(D.sensordata[w].cpu().numpy(), d.sensordata) < 1e-3
+
+
+@pytest.mark.parametrize("name,integrator", [("go1_flat", "implicitfast"), ("g1_flat", "implicitfast"), ("go1_flat", "euler")])
+def test_step_trajectory(name, integrator):
+  import mjlab_b200
+  m = mjlab_b200.load_model(name)
+  m.opt_integrator = {"euler": 0, "implicitfast": 3}[integrator]
+  nw, nstep = 6, 5
+  qpos, qvel, ctrl, xfrc = util.random_states(m, nw, seed=2)
+  sim = make_sim(m, nw, integrator=integrator)
+  load_state(sim, qpos, qvel, ctrl, xfrc)
+  for _ in range(nstep):
+    sim.step()
+  torch.cuda.synchronize()
+  ds = util.oracle_rollout(m, qpos, qvel, ctrl, xfrc, nstep, 35, 300)
+  worst_q = worst_v = 0.0
+  for w, d in enumerate(ds):
+    assert int(sim.data.ncon[w]) == len(d.contacts)
+    worst_q = max(worst_q, relerr(sim.data.qpos[w].cpu().numpy(), d.qpos))
+    worst_v = max(worst_v, relerr(sim.data.qvel[w].cpu().numpy(), d.qvel))
+    assert abs(float(sim.data.time[w]) - d.time) < 1e-6
+  # 1e-4 relative per step (north_star), accumulated over nstep steps
+  assert worst_q < 1e-4 * nstep, worst_q
+  assert worst_v < 1e-3 * nstep, worst_v
+
+
+def test_reset_and_graph_replay(go1):
+  nw = 16
+  sim = make_sim(go1, nw)
+  qpos, qvel, ctrl, xfrc = util.random_states(go1, nw, seed=3)
+  load_state(sim, qpos, qvel, ctrl, xfrc)
+  for _ in range(4):
+    sim.step()
+  ids = torch.tensor([1, 5, 7], device="cuda:0")
+  before = sim.data.qpos.clone()
+  sim.reset(ids)
+  torch.cuda.synchronize()
+  q0 = torch.as_tensor(go1.qpos0, dtype=torch.float32, device="cuda:0")
+  for w in range(nw):
+    if w in (1, 5, 7):
+      assert torch.equal(sim.data.qpos[w], q0)
+      assert float(sim.data.qvel[w].abs().max()) == 0.0
+      assert float(sim.data.qacc_warmstart[w].abs().max()) == 0.0
+      assert float(sim.data.time[w]) == 0.0
+    else:
+      assert torch.equal(sim.data.qpos[w], before[w])
+  sim.reset()
+  torch.cuda.synchronize()
+  assert torch.equal(sim.data.qpos, q0.expand(nw, -1))
+
+
+def test_determinism(g1):
+  nw = 32
+  outs = []
+  for _ in range(2):
+    sim = make_sim(g1, nw)
+    qpos, qvel, ctrl, xfrc = util.random_states(g1, nw, seed=4)
+    load_state(sim, qpos, qvel, ctrl, xfrc)
+    for _ in range(8):
+      sim.step()
+    torch.cuda.synchronize()
+    outs.append((sim.data.qpos.clone(), sim.data.qvel.clone(), sim.data.sensordata.clone()))
+  for a, b in zip(outs[0], outs[1]):
+    assert torch.equal(a, b)
