@@ -151,7 +151,7 @@ enum b2_df {
   B2_DF_CDOF_DOT,        /* nv*6 */
   B2_DF_CVEL,            /* nbody*6 */
   B2_DF_CACC,            /* nbody*6 */
-  B2_DF_QM,              /* nv*nv dense */
+  B2_DF_QM,              /* nv*ld dense, row stride ld = b2 leading dimension (>= nv, ld % 8 == 4) */
   B2_DF_QFRC_BIAS,       /* nv */
   B2_DF_QFRC_PASSIVE,    /* nv */
   B2_DF_QFRC_ACTUATOR,   /* nv */
@@ -201,6 +201,8 @@ typedef struct b2_model {
   int solver;        /* 2 newton (only supported solver) */
   int iterations, ls_iterations, disableflags;
   int has_accelerometer, has_subtreevel;
+  int nlimited;      /* number of limited hinge/slide joints (bounds the joint-limit rows) */
+  int maxchain;      /* max over candidate pairs of |dofs(body1) U dofs(body2)| (compact row width bound) */
   const float* mf[B2_MF_COUNT];
   int mf_stride[B2_MF_COUNT]; /* floats between consecutive worlds; 0 = shared */
   const int* mi[B2_MI_COUNT];
@@ -208,6 +210,7 @@ typedef struct b2_model {
 
 typedef struct b2_data {
   int nworld, nconmax, njmax;
+  int flags;         /* bit 0: also write the dense efc_J rows to HBM (tests / API consumers); off on the hot path */
   float* df[B2_DF_COUNT];
   int* di[B2_DI_COUNT];
 } b2_data;

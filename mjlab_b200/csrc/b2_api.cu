@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "b2_smooth.cuh"
@@ -15,9 +16,12 @@ static_assert(sizeof(KModel) == sizeof(b2_model), "KModel must mirror b2_model")
 static_assert(sizeof(KData) == sizeof(b2_data), "KData must mirror b2_data");
 
 #ifndef B2_WPB
-#define B2_WPB 4
+#define B2_WPB 2
 #endif
 #define B2_NCAND_MAX 256
+#ifndef B2_SOLVE_MINB
+#define B2_SOLVE_MINB 5
+#endif
 
 static char g_err[512] = "";
 static long long g_launches = 0;
@@ -39,7 +43,7 @@ __global__ void __launch_bounds__(B2_WPB * 32) k_smooth(const KModel m, const KD
   smooth_world(m, d, L, ncand_max, w, smem + (size_t)warp * L.total);
 }
 
-__global__ void __launch_bounds__(B2_WPB * 32) k_solve(const KModel m, const KData d, const SolveSmem L, int do_integrate) {
+__global__ void __launch_bounds__(B2_WPB * 32, B2_SOLVE_MINB) k_solve(const KModel m, const KData d, const SolveSmem L, int do_integrate) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   real* smem = reinterpret_cast<real*>(smem_raw);
   int warp = threadIdx.x >> 5;
@@ -91,7 +95,20 @@ struct Plan {
 
 static int make_plan(const b2_model* m, const b2_data* d, Plan* p) {
   p->ls = smooth_smem_layout(m->nq, m->nv, m->nu, m->nbody, m->njnt, B2_NCAND_MAX);
-  p->lv = solve_smem_layout(m->nv, d->njmax);
+  // true upper bounds on rows / runs, so shared memory is not sized by a generous njmax hint
+  int rows_cap = 4 * d->nconmax + 2 * m->nlimited;
+  if (rows_cap > d->njmax) rows_cap = d->njmax;
+  if (rows_cap < 1) rows_cap = 1;
+  int runs_cap = 2 * m->nlimited + d->nconmax + 1;
+  int wpad = m->maxchain | 1;
+  int jpool_cap = rows_cap * wpad;
+  int budget = 2048;
+  if (const char* e = getenv("B200SIM_JPOOL")) budget = atoi(e);
+  if (jpool_cap > budget) jpool_cap = budget;
+  if (jpool_cap > 65535) jpool_cap = 65535;
+  if (jpool_cap < 2 * m->nlimited + wpad * 6) jpool_cap = 2 * m->nlimited + wpad * 6;
+  int dofs_cap = 2 * m->nlimited + d->nconmax * m->maxchain;
+  p->lv = solve_smem_layout(m->nv, rows_cap, runs_cap, d->nconmax > 0 ? d->nconmax : 1, jpool_cap, dofs_cap);
   p->smem_smooth = (size_t)p->ls.total * sizeof(real) * B2_WPB;
   p->smem_solve = (size_t)p->lv.total * sizeof(real) * B2_WPB;
   return 0;

@@ -92,12 +92,14 @@ struct KModel {
   int nq, nv, nu, nbody, njnt, ngeom, nsite, nsensor, nsensordata, npair, nmocap, nlevel;
   int integrator, cone, solver, iterations, ls_iterations, disableflags;
   int has_accelerometer, has_subtreevel;
+  int nlimited, maxchain;
   const real* mf[B2_MF_COUNT];
   int mf_stride[B2_MF_COUNT];
   const int* mi[B2_MI_COUNT];
 };
 struct KData {
   int nworld, nconmax, njmax;
+  int flags;
   real* df[B2_DF_COUNT];
   int* di[B2_DI_COUNT];
 };
@@ -172,40 +174,110 @@ B2_DEV void cross_force(real* r, const real* v, const real* f) {
 B2_DEV real clampr(real x, real lo, real hi) { return x < lo ? lo : (x > hi ? hi : x); }
 
 // ---------------------------------------------------------------------------
-// dense SPD helpers for one world (n <= 64), matrix row-major with stride n.
+// Dense SPD factor + solve for one world (n <= 64), one warp.
+//
+// The matrix lives in shared memory, row-major with leading dimension ld = b2_ld(n):
+// ld % 8 == 4, so (a) rows are 16-byte aligned for 128-bit loads and (b) the eight lanes
+// of a quarter-warp reading consecutive rows hit eight distinct 4-bank groups, i.e. the
+// LDS.128 of a lane's own row is conflict-free.
+//
+// Left-looking (Crout) order: column j of L needs, for every row i >= j,
+//   s_i = A[i][j] - sum_{k<j} L[i][k] * L[j][k]
+// Lane <-> row, the k loop only LOADS (own row: conflict-free, pivot row: broadcast), so
+// it pipelines; one store per (row, column) and one __syncwarp per column.  The code is a
+// few hundred bytes: an earlier fully unrolled register/shuffle variant was faster per
+// instruction but its ~35 KB of straight-line code made the kernel instruction-fetch bound
+// (ncu: 63 % of stall cycles "no_instruction", profiles/).
 // ---------------------------------------------------------------------------
-// In-place lower Cholesky A = L L^T (upper triangle left untouched).
-B2_DEV void chol_factor(real* A, int n) {
-  for (int k = 0; k < n; ++k) {
+static inline
+#ifndef B2_HOSTEMU
+__host__ __device__
+#endif
+int b2_ld(int n) { int ld = (n + 3) & ~3; if ((ld & 7) != 4) ld += 4; return ld; }
+
+#ifdef B2_HOSTEMU
+B2_DEV real b2_shfl(real x, int) { return x; }
+#else
+B2_DEV real b2_shfl(real x, int src) { return __shfl_sync(0xffffffffu, x, src); }
+#endif
+
+// In-place lower Cholesky of A (lower triangle valid, upper ignored). invd[j] <- 1 / L[j][j].
+B2_DEV void chol_factor(real* A, int n, int ld, real* invd) {
+  for (int j = 0; j < n; ++j) {
     B2_WSYNC();
-    real dkk = A[k * n + k];
-    real inv = b2_rsqrt(dkk > B2_MINVAL ? dkk : B2_MINVAL);
-    B2_WSYNC();
-    for (int i = k + B2_LANE; i < n; i += B2_NLANE) A[i * n + k] *= inv;  // diagonal becomes sqrt(dkk)
-    B2_WSYNC();
-    // trailing update of the lower triangle: one row per lane
-    for (int i = k + 1 + B2_LANE; i < n; i += B2_NLANE) {
-      real lik = A[i * n + k];
-      for (int j = k + 1; j <= i; ++j) A[i * n + j] -= lik * A[j * n + k];
+    const real* rj = A + j * ld;
+    real inv = 0;
+    for (int base = j; base < n; base += B2_NLANE) {
+      int i = base + B2_LANE;
+      real s = 0;
+      if (i < n) {
+        const real* ri = A + i * ld;
+        s = ri[j];
+        int k = 0;
+#ifndef B2_HOSTEMU
+        real s2 = 0;
+        for (; k + 4 <= j; k += 4) {
+          float4 a = *reinterpret_cast<const float4*>(ri + k);
+          float4 b = *reinterpret_cast<const float4*>(rj + k);
+          s = fmaf(-a.x, b.x, s); s2 = fmaf(-a.y, b.y, s2);
+          s = fmaf(-a.z, b.z, s); s2 = fmaf(-a.w, b.w, s2);
+        }
+        s += s2;
+#endif
+        for (; k < j; ++k) s -= ri[k] * rj[k];
+      }
+      if (base == j) {
+        real piv = b2_shfl(s, 0);
+        inv = b2_rsqrt(piv > B2_MINVAL ? piv : B2_MINVAL);
+        if (B2_LANE == 0) invd[j] = inv;
+      }
+      if (i < n) A[i * ld + j] = s * inv;
     }
   }
   B2_WSYNC();
 }
-// x <- (L L^T)^-1 x
-B2_DEV void chol_solve(const real* L, real* x, int n) {
+
+// x <- (L L^T)^-1 x, x in shared memory.
+B2_DEV void chol_solve(const real* L, int n, int ld, const real* invd, real* x) {
+#ifdef B2_HOSTEMU
   for (int k = 0; k < n; ++k) {
-    B2_WSYNC();
-    real xk = x[k] / L[k * n + k];
-    B2_WSYNC();
-    if (B2_LANE == 0) x[k] = xk;
-    for (int i = k + 1 + B2_LANE; i < n; i += B2_NLANE) x[i] -= L[i * n + k] * xk;
+    real xk = x[k] * invd[k];
+    x[k] = xk;
+    for (int i = k + 1; i < n; ++i) x[i] -= L[i * ld + k] * xk;
   }
   for (int k = n - 1; k >= 0; --k) {
-    B2_WSYNC();
-    real xk = x[k] / L[k * n + k];
-    B2_WSYNC();
-    if (B2_LANE == 0) x[k] = xk;
-    for (int i = B2_LANE; i < k; i += B2_NLANE) x[i] -= L[k * n + i] * xk;
+    real xk = x[k] * invd[k];
+    x[k] = xk;
+    for (int i = 0; i < k; ++i) x[i] -= L[k * ld + i] * xk;
   }
+#else
+  // lane i keeps x[i] and x[i+32] in registers; x_k is broadcast with a dynamic-lane shuffle
+  const int lane = B2_LANE;
+  const int row0 = lane, row1 = lane + 32;
+  real x0 = row0 < n ? x[row0] : (real)0;
+  real x1 = row1 < n ? x[row1] : (real)0;
+  for (int k = 0; k < n; ++k) {
+    real l0 = row0 > k && row0 < n ? L[row0 * ld + k] : (real)0;
+    real l1 = row1 > k && row1 < n ? L[row1 * ld + k] : (real)0;
+    real xk = b2_shfl(k < 32 ? x0 : x1, k & 31) * invd[k];
+    if (row0 == k) x0 = xk; else x0 = fmaf(-l0, xk, x0);
+    if (row1 == k) x1 = xk; else x1 = fmaf(-l1, xk, x1);
+  }
+  for (int k = n - 1; k >= 0; --k) {
+    real l0 = row0 < k ? L[k * ld + row0] : (real)0;
+    real l1 = row1 < k ? L[k * ld + row1] : (real)0;
+    real xk = b2_shfl(k < 32 ? x0 : x1, k & 31) * invd[k];
+    if (row0 == k) x0 = xk; else x0 = fmaf(-l0, xk, x0);
+    if (row1 == k) x1 = xk; else x1 = fmaf(-l1, xk, x1);
+  }
+  if (row0 < n) x[row0] = x0;
+  if (row1 < n) x[row1] = x1;
+#endif
   B2_WSYNC();
+}
+
+// A (n x n, leading dimension ld, lower triangle valid) <- chol(A);  x <- A^-1 x.
+B2_DEV void spd_factor_solve(real* A, int n, int ld, real* x, real* invd) {
+  chol_factor(A, n, ld, invd);
+  chol_solve(A, n, ld, invd, x);
 }

@@ -17,7 +17,7 @@
 // Per-world shared-memory layout for stage 1 (offsets in reals).
 struct SmoothSmem {
   int qpos, qvel, xpos, xquat, xmat, xipos, xanchor, xaxis, scom, smass, cinert, crb, cdof, cdofdot, cvel, cacc, cfrc, M, f,
-      aforce, cand, total;
+      aforce, cand, invd, total;
 };
 
 static inline SmoothSmem smooth_smem_layout(int nq, int nv, int nu, int nbody, int njnt, int ncand) {
@@ -33,9 +33,10 @@ static inline SmoothSmem smooth_smem_layout(int nq, int nv, int nu, int nbody, i
   s.cvel = take(6 * nbody);
   s.cacc = s.crb;            // crb is dead once qM is assembled; cacc (6*nbody) fits in 10*nbody
   s.cfrc = take(6 * nbody);
-  s.M = take(nv * nv); s.f = take(nv);
+  s.M = take(nv * b2_ld(nv)); s.f = take(nv);
   s.aforce = take(nu);
   s.cand = take(ncand);      // candidate pair ids (ints stored in real-sized slots)
+  s.invd = take(64);
   s.total = o;
   return s;
 }
@@ -438,25 +439,26 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
     }
     B2_WSYNC();
   }
-  for (int i = B2_LANE; i < nv * nv; i += B2_NLANE) M[i] = 0;
+  const int ld = b2_ld(nv);
+  for (int i = B2_LANE; i < nv * ld; i += B2_NLANE) M[i] = 0;
   B2_WSYNC();
   const real* armature = MF(B2_MF_DOF_ARMATURE);
   for (int i = B2_LANE; i < nv; i += B2_NLANE) {
     real buf[6];
     inert_mul(buf, crb + 10 * dof_bodyid[i], cdof + 6 * i);
     const real* ci = cdof + 6 * i;
-    M[i * nv + i] = armature[i] + ci[0] * buf[0] + ci[1] * buf[1] + ci[2] * buf[2] + ci[3] * buf[3] + ci[4] * buf[4] + ci[5] * buf[5];
+    M[i * ld + i] = armature[i] + ci[0] * buf[0] + ci[1] * buf[1] + ci[2] * buf[2] + ci[3] * buf[3] + ci[4] * buf[4] + ci[5] * buf[5];
     for (int j = dof_parentid[i]; j >= 0; j = dof_parentid[j]) {
       const real* cj = cdof + 6 * j;
       real v = cj[0] * buf[0] + cj[1] * buf[1] + cj[2] * buf[2] + cj[3] * buf[3] + cj[4] * buf[4] + cj[5] * buf[5];
-      M[i * nv + j] = v;
-      M[j * nv + i] = v;
+      M[i * ld + j] = v;
+      M[j * ld + i] = v;
     }
   }
   B2_WSYNC();
   {
-    real* g = d.df[B2_DF_QM] + (size_t)w * nv * nv;
-    for (int i = B2_LANE; i < nv * nv; i += B2_NLANE) g[i] = M[i];
+    real* g = d.df[B2_DF_QM] + (size_t)w * nv * ld;
+    for (int i = B2_LANE; i < nv * ld; i += B2_NLANE) g[i] = M[i];
   }
 
   // ---- collision ---------------------------------------------------------------
@@ -751,8 +753,7 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
     B2_WSYNC();
   }
   // ---- qacc_smooth = M^-1 qfrc_smooth (M already copied to HBM; factor in place) ---------
-  chol_factor(M, nv);
-  chol_solve(M, f, nv);
+  spd_factor_solve(M, nv, ld, f, sm + L.invd);
   {
     real* g = d.df[B2_DF_QACC_SMOOTH] + (size_t)w * nv;
     for (int i = B2_LANE; i < nv; i += B2_NLANE) g[i] = f[i];

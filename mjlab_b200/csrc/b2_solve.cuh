@@ -10,21 +10,42 @@
 #pragma once
 #include "b2_common.cuh"
 
-#define B2_CHUNK 32  // efc rows staged through shared memory at a time
-
+// Per-world shared-memory layout for stage 2 (offsets in reals).
+//
+// Constraint Jacobian rows are stored COMPACT: a row only keeps the entries of the dofs on the
+// kinematic chains of the two bodies in contact (the other entries are structurally zero).
+// Consecutive contacts between the same pair of bodies form a RUN and share one dof list, so
+// J^T D J is accumulated run by run over w*(w+1)/2 dof pairs instead of nv*(nv+1)/2
+// (G1 foot-ground contact: w = 12 of nv = 35).
 struct SolveSmem {
-  int M, H, chunk, cdof, qvel, qacc, Ma, grad, search, Mv, qfs, qas, qfc, tmp, D, aref, jar, jv, total;
+  int M, H, cdof, qvel, qacc, Ma, grad, search, Mv, qfs, qas, qfc, tmp, invd;
+  int D, aref, jar, jv, rowinfo, rowsrc, runinfo, rundofs, cinfo, jpool;
+  int rows_cap, runs_cap, jpool_cap, dofs_cap, total;
 };
 
-static inline SolveSmem solve_smem_layout(int nv, int njmax) {
+static inline SolveSmem solve_smem_layout(int nv, int rows_cap, int runs_cap, int nconmax, int jpool_cap, int dofs_cap) {
   SolveSmem s;
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
-  s.M = take(nv * nv); s.H = take(nv * nv); s.chunk = take(B2_CHUNK * nv);
-  s.cdof = take(6 * nv);
+  s.M = -1;  // qM stays in HBM/L2 (read coalesced through its symmetry), not staged
+  s.H = take(nv * b2_ld(nv));
   s.qvel = take(nv); s.qacc = take(nv); s.Ma = take(nv); s.grad = take(nv); s.search = take(nv); s.Mv = take(nv);
-  s.qfs = take(nv); s.qas = take(nv); s.qfc = take(nv); s.tmp = take(nv);
-  s.D = take(njmax); s.aref = take(njmax); s.jar = take(njmax); s.jv = take(njmax);
+  s.qfs = take(nv); s.qas = take(nv); s.qfc = take(nv); s.tmp = take(nv); s.invd = take(64);
+  // D and aref are first written after the Jacobian rows are assembled; cdof is only read
+  // during that assembly, so the two share storage (needs 2*rows_cap >= 6*nv, else padded).
+  int dd = 2 * ((rows_cap + 3) & ~3);
+  int need = (6 * nv + 3) & ~3;
+  s.D = take(dd > need ? dd : need);
+  s.aref = s.D + ((rows_cap + 3) & ~3);
+  s.cdof = s.D;
+  s.jar = take(rows_cap); s.jv = take(rows_cap);
+  s.rowsrc = s.jv;                   // int: contact id, or -(jnt+1); dead before the line search writes jv
+  s.rowinfo = take(rows_cap);        // int: pool offset | run << 16
+  s.runinfo = take(2 * runs_cap);    // int2: (dofoff | w << 16), (row0 | nrow << 16)
+  s.rundofs = take((dofs_cap + 3) / 4);  // bytes
+  s.cinfo = take(4 * nconmax);       // int4 per contact: adr, dim, body1, body2
+  s.jpool = take(jpool_cap);
+  s.rows_cap = rows_cap; s.runs_cap = runs_cap; s.jpool_cap = jpool_cap; s.dofs_cap = dofs_cap;
   s.total = o;
   return s;
 }
@@ -56,27 +77,31 @@ B2_DEV void kbi(real timestep, const real* solref, const real* solimp, real pos,
   }
 }
 
-// y[r] (op)= J[r,:] . x  for all rows, staged through the shared chunk.
-// mode 0: y = Jx - sub   mode 1: y = Jx
-B2_DEV void rows_dot(const real* gJ, int nefc, int nv, const real* x, real* chunk, real* y, const real* sub) {
-  for (int base = 0; base < nefc; base += B2_CHUNK) {
-    int nr = nefc - base < B2_CHUNK ? nefc - base : B2_CHUNK;
-    B2_WSYNC();
-    for (int i = B2_LANE; i < nr * nv; i += B2_NLANE) chunk[i] = gJ[(size_t)base * nv + i];
-    B2_WSYNC();
-    for (int r = B2_LANE; r < nr; r += B2_NLANE) {
-      real acc = 0;
-      const real* c = chunk + r * nv;
-      for (int e = 0; e < nv; ++e) acc += c[e] * x[e];
-      y[base + r] = sub ? acc - sub[base + r] : acc;
-    }
+// y[r] = J[r,:] . x (- sub[r]) over compact rows; lanes over rows.
+B2_DEV void rows_dot(const real* jpool, const int* rowinfo, const int* runinfo, const unsigned char* rundofs, int nefc,
+                     const real* x, real* y, const real* sub) {
+  for (int r = B2_LANE; r < nefc; r += B2_NLANE) {
+    int info = rowinfo[r];
+    int off = info & 0xffff, run = info >> 16;
+    int ri = runinfo[2 * run];
+    int dofoff = ri & 0xffff, wd = ri >> 16;
+    const real* jr = jpool + off;
+    const unsigned char* dl = rundofs + dofoff;
+    real acc = 0;
+    for (int a = 0; a < wd; ++a) acc += jr[a] * x[dl[a]];
+    y[r] = sub ? acc - sub[r] : acc;
   }
   B2_WSYNC();
 }
 
 struct LsPnt { real alpha, cost, d1, d2; };
 
-B2_DEV LsPnt ls_eval(real alpha, real q0g, real q1g, real q2g, const real* jar, const real* jv, const real* D, int nefc) {
+#ifdef B2_HOSTEMU
+B2_DEV
+#else
+__device__ __noinline__
+#endif
+LsPnt ls_eval(real alpha, real q0g, real q1g, real q2g, const real* jar, const real* jv, const real* D, int nefc) {
   real q0 = 0, q1 = 0, q2 = 0;
   for (int r = B2_LANE; r < nefc; r += B2_NLANE) {
     real x = jar[r] + alpha * jv[r];
@@ -198,12 +223,20 @@ B2_DEV void mat2quat(real* q, const real* R) {
 // ---------------------------------------------------------------------------
 B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int w, real* sm, int do_integrate) {
   const int nv = m.nv, nb = m.nbody, nq = m.nq, nu = m.nu, njmax = d.njmax, nconmax = d.nconmax;
-  real* M = sm + L.M; real* H = sm + L.H; real* chunk = sm + L.chunk; real* cdof = sm + L.cdof;
+  real* H = sm + L.H; real* cdof = sm + L.cdof;
   real* qvel = sm + L.qvel; real* qacc = sm + L.qacc; real* Ma = sm + L.Ma; real* grad = sm + L.grad;
   real* search = sm + L.search; real* Mv = sm + L.Mv; real* qfs = sm + L.qfs; real* qas = sm + L.qas;
-  real* qfc = sm + L.qfc; real* tmp = sm + L.tmp;
+  real* qfc = sm + L.qfc; real* tmp = sm + L.tmp; real* invd = sm + L.invd;
   real* D = sm + L.D; real* aref = sm + L.aref; real* jar = sm + L.jar; real* jv = sm + L.jv;
-  int* rowsrc = (int*)jv;  // row -> source (contact id, or -(jnt+1)); dead before the line search needs jv
+  real* wgt = jv;  // D*active per row; consumed by the Hessian pass before the line search reuses jv
+  int* rowinfo = (int*)(sm + L.rowinfo);
+  int* rowsrc = (int*)(sm + L.rowsrc);
+  int* runinfo = (int*)(sm + L.runinfo);
+  unsigned char* rundofs = (unsigned char*)(sm + L.rundofs);
+  int* cinfo = (int*)(sm + L.cinfo);
+  real* jpool = sm + L.jpool;
+  const int rows_cap = L.rows_cap < njmax ? L.rows_cap : njmax;
+  const int ld = b2_ld(nv);
 
   const int* body_parent = MI(B2_MI_BODY_PARENTID);
   const int* body_root = MI(B2_MI_BODY_ROOTID);
@@ -214,15 +247,17 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
   const int* jnt_dofadr = MI(B2_MI_JNT_DOFADR);
   const int* jnt_limited = MI(B2_MI_JNT_LIMITED);
   const real timestep = MF(B2_MF_OPT_TIMESTEP)[0];
+  const bool export_J = (d.flags & 1) != 0;
 
   real* g_qpos = d.df[B2_DF_QPOS] + (size_t)w * nq;
   real* g_qvel = d.df[B2_DF_QVEL] + (size_t)w * nv;
   real* gJ = d.df[B2_DF_EFC_J] + (size_t)w * njmax * nv;
+  real* g_pos = d.df[B2_DF_EFC_POS] + (size_t)w * njmax;
+  real* g_mar = d.df[B2_DF_EFC_MARGIN] + (size_t)w * njmax;
   const real* g_scom = d.df[B2_DF_SUBTREE_COM] + (size_t)w * nb * 3;
   const real* g_cdof = d.df[B2_DF_CDOF] + (size_t)w * nv * 6;
-  const real* g_M = d.df[B2_DF_QM] + (size_t)w * nv * nv;
+  const real* M = d.df[B2_DF_QM] + (size_t)w * nv * b2_ld(nv);  // [nv][ld]; symmetric, so column i is read coalesced as M[e*ld + i]
 
-  for (int i = B2_LANE; i < nv * nv; i += B2_NLANE) M[i] = g_M[i];
   for (int i = B2_LANE; i < 6 * nv; i += B2_NLANE) cdof[i] = g_cdof[i];
   for (int i = B2_LANE; i < nv; i += B2_NLANE) {
     qvel[i] = g_qvel[i];
@@ -231,7 +266,7 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
   }
   B2_WSYNC();
 
-  // ---- joint-limit rows (ordered: joint, lower then upper) ----------------------
+  // ---- joint-limit rows (ordered: joint, lower then upper); each is its own run of width 1 ----
   int nefc = 0;
   {
     const real* jnt_range = MF(B2_MF_JNT_RANGE);
@@ -249,22 +284,31 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
       unsigned bal = b2_ballot(on);
       if (on) {
         int row = nefc + b2_popc(bal & b2_lanemask_lt());
-        if (row < njmax) {
-          real* Jr = gJ + (size_t)row * nv;
-          for (int e = 0; e < nv; ++e) Jr[e] = 0;
-          Jr[jnt_dofadr[j]] = side == 0 ? (real)1 : (real)-1;
+        if (row < rows_cap) {
+          real val = side == 0 ? (real)1 : (real)-1;
+          int dof = jnt_dofadr[j];
+          jpool[row] = val;
+          rundofs[row] = (unsigned char)dof;
+          rowinfo[row] = row | (row << 16);
+          runinfo[2 * row] = row | (1 << 16);
+          runinfo[2 * row + 1] = row | (1 << 16);
           rowsrc[row] = -(j + 1);
-          d.df[B2_DF_EFC_POS][(size_t)w * njmax + row] = dist;
-          d.df[B2_DF_EFC_MARGIN][(size_t)w * njmax + row] = jnt_margin[j];
+          g_pos[row] = dist;
+          g_mar[row] = jnt_margin[j];
+          if (export_J) {
+            real* Jr = gJ + (size_t)row * nv;
+            for (int e = 0; e < nv; ++e) Jr[e] = 0;
+            Jr[dof] = val;
+          }
         }
       }
       nefc += b2_popc(bal);
     }
-    if (nefc > njmax) nefc = njmax;
+    if (nefc > rows_cap) nefc = rows_cap;
   }
   const int nl = nefc;
 
-  // ---- contact rows --------------------------------------------------------------
+  // ---- contact rows ---------------------------------------------------------------------------
   const int ncon = d.di[B2_DI_NCON][w];
   const real* c_dist = d.df[B2_DF_CONTACT_DIST] + (size_t)w * nconmax;
   const real* c_pos = d.df[B2_DF_CONTACT_POS] + (size_t)w * nconmax * 3;
@@ -278,7 +322,7 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
   int* c_adr = d.di[B2_DI_CONTACT_EFC_ADDRESS] + (size_t)w * nconmax;
   int ndrop = 0;
   {
-    // row addresses by prefix sum over contacts; a contact is kept iff its rows fit below njmax
+    // row addresses by prefix sum over contacts; a contact is kept iff its rows fit below the cap
     int run = nefc;
     for (int base = 0; base < ncon; base += B2_NLANE) {
       int c = base + B2_LANE;
@@ -296,9 +340,13 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
 #endif
       if (c < ncon) {
         int adr = run + incl - nrow;
-        bool keep = nrow > 0 && adr + nrow <= njmax;
-        c_adr[c] = keep ? adr : -1;
+        bool keep = nrow > 0 && adr + nrow <= rows_cap;
         if (nrow > 0 && !keep) ndrop += nrow;
+        int g1 = c_geom[2 * c], g2 = c_geom[2 * c + 1];
+        cinfo[4 * c] = keep ? adr : -1;
+        cinfo[4 * c + 1] = c_dim[c];
+        cinfo[4 * c + 2] = geom_body[g1];
+        cinfo[4 * c + 3] = geom_body[g2];
       }
       run += total;
     }
@@ -306,22 +354,53 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
     nefc = run - ndrop;
     B2_WSYNC();
   }
-  // Jacobian rows, contact by contact, lanes over dofs
+  // compact Jacobian rows, contact by contact (uniform loop), lanes over the run's dof list
+  int nrun = nl;
   {
+    int pooloff = nl, dofcount = nl;
+    int pb1 = -1, pb2 = -1, cur_dofoff = 0, cur_w = 0, cur_run = -1, cur_row0 = 0, cur_nrow = 0;
+    bool overflow = false;
     for (int c = 0; c < ncon; ++c) {
-      int adr = c_adr[c];
+      int adr = cinfo[4 * c];
       if (adr < 0) continue;
-      int g1 = c_geom[2 * c], g2 = c_geom[2 * c + 1];
-      int b1 = geom_body[g1], b2 = geom_body[g2];
+      int dim = cinfo[4 * c + 1], b1 = cinfo[4 * c + 2], b2 = cinfo[4 * c + 3];
+      int nrow = dim == 1 ? 1 : 2 * (dim - 1);
+      unsigned lo1 = (unsigned)dofmask[2 * b1], hi1 = (unsigned)dofmask[2 * b1 + 1];
+      unsigned lo2 = (unsigned)dofmask[2 * b2], hi2 = (unsigned)dofmask[2 * b2 + 1];
+      if (!overflow && (b1 != pb1 || b2 != pb2)) {
+        unsigned lo = lo1 | lo2, hi = hi1 | hi2;
+        int cl = b2_popc(lo), wd = cl + b2_popc(hi);
+        if (dofcount + wd > L.dofs_cap || nrun >= L.runs_cap) overflow = true;
+        else {
+          if (cur_run >= 0 && B2_LANE == 0) runinfo[2 * cur_run + 1] = cur_row0 | (cur_nrow << 16);
+#ifndef B2_HOSTEMU
+          if ((lo >> B2_LANE) & 1u) rundofs[dofcount + b2_popc(lo & b2_lanemask_lt())] = (unsigned char)B2_LANE;
+          if ((hi >> B2_LANE) & 1u) rundofs[dofcount + cl + b2_popc(hi & b2_lanemask_lt())] = (unsigned char)(B2_LANE + 32);
+#else
+          { int k = 0; for (int e = 0; e < 64; ++e) { bool in = e < 32 ? ((lo >> e) & 1u) : ((hi >> (e - 32)) & 1u); if (in) rundofs[dofcount + k++] = (unsigned char)e; } }
+#endif
+          cur_run = nrun++; cur_dofoff = dofcount; cur_w = wd; cur_row0 = adr; cur_nrow = 0;
+          dofcount += wd;
+          if (B2_LANE == 0) runinfo[2 * cur_run] = cur_dofoff | (cur_w << 16);
+          pb1 = b1; pb2 = b2;
+          B2_WSYNC();
+        }
+      }
+      const int wpad = cur_w | 1;  // odd row stride: rows of a run hit distinct banks
+      if (!overflow && pooloff + nrow * wpad > L.jpool_cap) overflow = true;
+      if (overflow) {
+        // shared-memory pools exhausted: this and all later contacts lose their rows
+        if (B2_LANE == 0) { cinfo[4 * c] = -1; }
+        ndrop += nrow;
+        continue;
+      }
       int r1 = body_root[b1], r2 = body_root[b2];
       const real* p = c_pos + 3 * c;
       real o1[3] = {p[0] - g_scom[3 * r1], p[1] - g_scom[3 * r1 + 1], p[2] - g_scom[3 * r1 + 2]};
       real o2[3] = {p[0] - g_scom[3 * r2], p[1] - g_scom[3 * r2 + 1], p[2] - g_scom[3 * r2 + 2]};
       const real* F = c_frame + 9 * c;
-      int dim = c_dim[c];
-      unsigned lo1 = (unsigned)dofmask[2 * b1], hi1 = (unsigned)dofmask[2 * b1 + 1];
-      unsigned lo2 = (unsigned)dofmask[2 * b2], hi2 = (unsigned)dofmask[2 * b2 + 1];
-      for (int e = B2_LANE; e < nv; e += B2_NLANE) {
+      for (int a = B2_LANE; a < cur_w; a += B2_NLANE) {
+        int e = rundofs[cur_dofoff + a];
         bool in1 = e < 32 ? ((lo1 >> e) & 1u) : ((hi1 >> (e - 32)) & 1u);
         bool in2 = e < 32 ? ((lo2 >> e) & 1u) : ((hi2 >> (e - 32)) & 1u);
         real jd[3] = {0, 0, 0};
@@ -330,44 +409,69 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
         if (in1) { real t[3]; cross3(t, cd, o1); jd[0] -= cd[3] + t[0]; jd[1] -= cd[4] + t[1]; jd[2] -= cd[5] + t[2]; }
         real jn = F[0] * jd[0] + F[1] * jd[1] + F[2] * jd[2];
         if (dim == 1) {
-          gJ[(size_t)adr * nv + e] = jn;
+          jpool[pooloff + a] = jn;
         } else {
           for (int k = 1; k < dim; ++k) {
             real jt = k < 3 ? F[3 * k] * jd[0] + F[3 * k + 1] * jd[1] + F[3 * k + 2] * jd[2] : (real)0;
             real mu = c_fri[5 * c + k - 1];
-            gJ[(size_t)(adr + 2 * (k - 1)) * nv + e] = jn + mu * jt;
-            gJ[(size_t)(adr + 2 * (k - 1) + 1) * nv + e] = jn - mu * jt;
+            jpool[pooloff + (2 * (k - 1)) * wpad + a] = jn + mu * jt;
+            jpool[pooloff + (2 * (k - 1) + 1) * wpad + a] = jn - mu * jt;
           }
         }
       }
-      int nrow = dim == 1 ? 1 : 2 * (dim - 1);
       for (int r = B2_LANE; r < nrow; r += B2_NLANE) {
+        rowinfo[adr + r] = (pooloff + r * wpad) | (cur_run << 16);
         rowsrc[adr + r] = c;
-        d.df[B2_DF_EFC_POS][(size_t)w * njmax + adr + r] = c_dist[c];
-        d.df[B2_DF_EFC_MARGIN][(size_t)w * njmax + adr + r] = c_inc[c];
+        g_pos[adr + r] = c_dist[c];
+        g_mar[adr + r] = c_inc[c];
       }
+      pooloff += nrow * wpad;
+      cur_nrow += nrow;
+    }
+    if (cur_run >= 0 && B2_LANE == 0) runinfo[2 * cur_run + 1] = cur_row0 | (cur_nrow << 16);
+    B2_WSYNC();
+    if (overflow) {
+      // rows form a prefix: recompute nefc as the end of the last kept contact
+      int last = nl;
+      for (int c = 0; c < ncon; ++c) {
+        int adr = cinfo[4 * c];
+        if (adr >= 0) { int dim = cinfo[4 * c + 1]; last = adr + (dim == 1 ? 1 : 2 * (dim - 1)); }
+      }
+      nefc = last;
     }
     B2_WSYNC();
-  }
-  if (B2_LANE == 0) {
-    d.di[B2_DI_NEFC][w] = nefc;
-    d.di[B2_DI_NL][w] = nl;
-    d.di[B2_DI_NEFC_DROPPED][w] = ndrop;
+    for (int c = B2_LANE; c < ncon; c += B2_NLANE) c_adr[c] = cinfo[4 * c];
+    if (B2_LANE == 0) {
+      d.di[B2_DI_NEFC][w] = nefc;
+      d.di[B2_DI_NL][w] = nl;
+      d.di[B2_DI_NEFC_DROPPED][w] = ndrop;
+    }
+    // dense export for tests / API consumers that ask for efc_J
+    if (export_J) {
+      for (int r = nl; r < nefc; ++r) {
+        int info = rowinfo[r];
+        int off = info & 0xffff, run = info >> 16;
+        int ri = runinfo[2 * run];
+        int dofoff = ri & 0xffff, wd = ri >> 16;
+        for (int e = B2_LANE; e < nv; e += B2_NLANE) gJ[(size_t)r * nv + e] = 0;
+        B2_WSYNC();
+        for (int a = B2_LANE; a < wd; a += B2_NLANE) gJ[(size_t)r * nv + rundofs[dofoff + a]] = jpool[off + a];
+      }
+      B2_WSYNC();
+    }
   }
 
-  // ---- per-row impedance, D, aref ---------------------------------------------------
+  // ---- per-row impedance, D, aref -----------------------------------------------------------------
   real* g_efcD = d.df[B2_DF_EFC_D] + (size_t)w * njmax;
   real* g_aref = d.df[B2_DF_EFC_AREF] + (size_t)w * njmax;
   real* g_force = d.df[B2_DF_EFC_FORCE] + (size_t)w * njmax;
   if (nefc > 0) {
-    rows_dot(gJ, nefc, nv, qvel, chunk, jar, nullptr);  // jar <- J qvel (temporarily)
+    rows_dot(jpool, rowinfo, runinfo, rundofs, nefc, qvel, jar, nullptr);  // jar <- J qvel (temporarily)
     const real* biw = MF(B2_MF_BODY_INVWEIGHT0);
     const real* diw = MF(B2_MF_DOF_INVWEIGHT0);
     const real* jnt_solref = MF(B2_MF_JNT_SOLREF);
     const real* jnt_solimp = MF(B2_MF_JNT_SOLIMP);
     const real impratio = MF(B2_MF_OPT_IMPRATIO)[0];
-    const real* g_pos = d.df[B2_DF_EFC_POS] + (size_t)w * njmax;
-    const real* g_mar = d.df[B2_DF_EFC_MARGIN] + (size_t)w * njmax;
     for (int r = B2_LANE; r < nefc; r += B2_NLANE) {
       int src = rowsrc[r];
       real invw, k, b, imp;
@@ -378,9 +482,8 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
         kbi(timestep, jnt_solref + 2 * j, jnt_solimp + 5 * j, pos, k, b, imp);
       } else {
         int c = src;
-        int b1 = geom_body[c_geom[2 * c]], b2 = geom_body[c_geom[2 * c + 1]];
-        invw = biw[2 * b1] + biw[2 * b2];
-        if (c_dim[c] > 1) {
+        invw = biw[2 * cinfo[4 * c + 2]] + biw[2 * cinfo[4 * c + 3]];
+        if (cinfo[4 * c + 1] > 1) {
           real f0 = c_fri[5 * c];
           invw = (invw + f0 * f0 * invw) * 2 * f0 * f0 / impratio;
         }
@@ -395,7 +498,7 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
     B2_WSYNC();
   }
 
-  // ---- solve -----------------------------------------------------------------------------
+  // ---- solve ------------------------------------------------------------------------------------------
   int niter = 0;
   real* g_qacc = d.df[B2_DF_QACC] + (size_t)w * nv;
   real* g_qfc = d.df[B2_DF_QFRC_CONSTRAINT] + (size_t)w * nv;
@@ -409,20 +512,20 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
     const real scale = (real)1 / (meaninertia * (real)(nv > 1 ? nv : 1));
     const real* g_ws = d.df[B2_DF_QACC_WARMSTART] + (size_t)w * nv;
     // cost at qacc_smooth (Gauss term vanishes)
-    rows_dot(gJ, nefc, nv, qas, chunk, jar, aref);
+    rows_dot(jpool, rowinfo, runinfo, rundofs, nefc, qas, jar, aref);
     real cs = 0;
     for (int r = B2_LANE; r < nefc; r += B2_NLANE) { real x = jar[r]; if (x < 0) cs += (real)0.5 * D[r] * x * x; }
     cs = b2_wsum(cs);
     // cost at the warm start
     for (int i = B2_LANE; i < nv; i += B2_NLANE) qacc[i] = g_ws[i];
     B2_WSYNC();
-    rows_dot(gJ, nefc, nv, qacc, chunk, jar, aref);
+    rows_dot(jpool, rowinfo, runinfo, rundofs, nefc, qacc, jar, aref);
     real cw = 0;
     for (int r = B2_LANE; r < nefc; r += B2_NLANE) { real x = jar[r]; if (x < 0) cw += (real)0.5 * D[r] * x * x; }
     real gw = 0;
     for (int i = B2_LANE; i < nv; i += B2_NLANE) {
       real a = 0;
-      for (int e = 0; e < nv; ++e) a += M[i * nv + e] * qacc[e];
+      for (int e = 0; e < nv; ++e) a += M[e * ld + i] * qacc[e];
       Ma[i] = a;
       gw += (real)0.5 * (a - qfs[i]) * (qacc[i] - qas[i]);
     }
@@ -431,82 +534,115 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
     if (cw > cs) {
       for (int i = B2_LANE; i < nv; i += B2_NLANE) qacc[i] = qas[i];
       B2_WSYNC();
-      rows_dot(gJ, nefc, nv, qacc, chunk, jar, aref);
+      rows_dot(jpool, rowinfo, runinfo, rundofs, nefc, qacc, jar, aref);
       for (int i = B2_LANE; i < nv; i += B2_NLANE) {
         real a = 0;
-        for (int e = 0; e < nv; ++e) a += M[i * nv + e] * qacc[e];
+        for (int e = 0; e < nv; ++e) a += M[e * ld + i] * qacc[e];
         Ma[i] = a;
       }
       B2_WSYNC();
     }
     real cost = 0, gauss = 0;
+    // rounding floor of the cost difference in this arithmetic: below it "improvement" is noise
+    const real eps_real = sizeof(real) == 4 ? (real)1.1920929e-7 : (real)2.220446e-16;
     for (int it = 0;; ++it) {
-      // -- constraint update: cost, qfrc_constraint, gradient, Hessian, Newton direction
+      // -- constraint update, part 1: row weights, cost, qfrc_constraint, gradient
       real c1 = 0;
-      for (int r = B2_LANE; r < nefc; r += B2_NLANE) { real x = jar[r]; if (x < 0) c1 += (real)0.5 * D[r] * x * x; }
+      for (int r = B2_LANE; r < nefc; r += B2_NLANE) {
+        real x = jar[r];
+        real wr = x < 0 ? D[r] : (real)0;
+        wgt[r] = wr;
+        c1 += (real)0.5 * wr * x * x;
+      }
       real g1 = 0;
-      for (int i = B2_LANE; i < nv; i += B2_NLANE) g1 += (real)0.5 * (Ma[i] - qfs[i]) * (qacc[i] - qas[i]);
+      for (int i = B2_LANE; i < nv; i += B2_NLANE) { g1 += (real)0.5 * (Ma[i] - qfs[i]) * (qacc[i] - qas[i]); qfc[i] = 0; }
       gauss = b2_wsum(g1);
       real newcost = b2_wsum(c1) + gauss;
-      // H = M + J^T diag(D*active) J and qfc = J^T force, one pass over J in chunks
-      for (int i = B2_LANE; i < nv * nv; i += B2_NLANE) H[i] = M[i];
-      for (int i = B2_LANE; i < nv; i += B2_NLANE) qfc[i] = 0;
-      for (int base = 0; base < nefc; base += B2_CHUNK) {
-        int nr = nefc - base < B2_CHUNK ? nefc - base : B2_CHUNK;
-        B2_WSYNC();
-        for (int i = B2_LANE; i < nr * nv; i += B2_NLANE) chunk[i] = gJ[(size_t)base * nv + i];
-        B2_WSYNC();
-        // qfc += J^T f (lanes over dofs)
-        for (int e = B2_LANE; e < nv; e += B2_NLANE) {
-          real a = 0;
-          for (int r = 0; r < nr; ++r) { real x = jar[base + r]; if (x < 0) a -= chunk[r * nv + e] * D[base + r] * x; }
-          qfc[e] += a;
-        }
-        // scale active rows by sqrt(D), zero inactive ones
-        B2_WSYNC();
-        for (int i = B2_LANE; i < nr * nv; i += B2_NLANE) {
-          int r = i / nv;
-          chunk[i] = jar[base + r] < 0 ? chunk[i] * sqrt(D[base + r]) : (real)0;
-        }
-        B2_WSYNC();
-        for (int i = 0; i < nv; ++i) {
-          for (int j = B2_LANE; j <= i; j += B2_NLANE) {
-            real a = 0;
-            for (int r = 0; r < nr; ++r) a += chunk[r * nv + i] * chunk[r * nv + j];
-            H[i * nv + j] += a;
-          }
-        }
-      }
       B2_WSYNC();
-      for (int i = B2_LANE; i < nv; i += B2_NLANE) { real g = Ma[i] - qfs[i] - qfc[i]; grad[i] = g; tmp[i] = g; }
+      if (nl > 0) {  // limit rows, gathered per dof (deterministic even if two rows share a dof)
+        for (int e = B2_LANE; e < nv; e += B2_NLANE) {
+          real ff = 0;
+          for (int r = 0; r < nl; ++r)
+            if (rundofs[r] == e) ff -= jpool[r] * wgt[r] * jar[r];
+          qfc[e] += ff;
+        }
+        B2_WSYNC();
+      }
+      for (int run = nl; run < nrun; ++run) {  // contact runs: qfc += J^T f over the run's dofs
+        int ri0 = runinfo[2 * run], ri1 = runinfo[2 * run + 1];
+        int dofoff = ri0 & 0xffff, wd = ri0 >> 16, row0 = ri1 & 0xffff, nrow = ri1 >> 16;
+        const int wpad = wd | 1;
+        const int off0 = rowinfo[row0] & 0xffff;
+        const unsigned char* dl = rundofs + dofoff;
+        for (int a = B2_LANE; a < wd; a += B2_NLANE) {
+          real ff = 0;
+          for (int q = 0; q < nrow; ++q) ff -= jpool[off0 + q * wpad + a] * wgt[row0 + q] * jar[row0 + q];
+          qfc[dl[a]] += ff;
+        }
+        B2_WSYNC();
+      }
+      real gn = 0;
+      for (int i = B2_LANE; i < nv; i += B2_NLANE) { real g = Ma[i] - qfs[i] - qfc[i]; grad[i] = g; tmp[i] = g; gn += g * g; }
       B2_WSYNC();
       if (it > 0) {
-        real gn = 0;
-        for (int i = B2_LANE; i < nv; i += B2_NLANE) gn += grad[i] * grad[i];
         gn = sqrt(b2_wsum(gn));
         real improvement = scale * (cost - newcost);
+        real floor_ = fmax(tolerance, 8 * eps_real * scale * fabs(newcost));
         cost = newcost;
-        if (improvement < tolerance || scale * gn < tolerance) break;
+        if (improvement < floor_ || scale * gn < tolerance) break;
       } else {
         cost = newcost;
       }
       if (it >= m.iterations) break;
-      chol_factor(H, nv);
-      chol_solve(H, tmp, nv);
+      // -- part 2: H = M + J^T diag(w) J, only when another Newton step will be taken
+      for (int i = B2_LANE; i < nv * ld; i += B2_NLANE) H[i] = M[i];
+      B2_WSYNC();
+      if (nl > 0) {
+        for (int e = B2_LANE; e < nv; e += B2_NLANE) {
+          real hh = 0;
+          for (int r = 0; r < nl; ++r)
+            if (rundofs[r] == e) hh += wgt[r];
+          H[e * ld + e] += hh;
+        }
+        B2_WSYNC();
+      }
+      for (int run = nl; run < nrun; ++run) {  // J^T diag(w) J over the run's dof pairs
+        int ri0 = runinfo[2 * run], ri1 = runinfo[2 * run + 1];
+        int dofoff = ri0 & 0xffff, wd = ri0 >> 16, row0 = ri1 & 0xffff, nrow = ri1 >> 16;
+        const int wpad = wd | 1;
+        const int off0 = rowinfo[row0] & 0xffff;
+        const unsigned char* dl = rundofs + dofoff;
+        const int npair = wd * (wd + 1) / 2;
+        for (int pr = B2_LANE; pr < npair; pr += B2_NLANE) {
+          int a = (int)((sqrt((real)(8 * pr + 1)) - 1) * (real)0.5);
+          while (a * (a + 1) / 2 > pr) --a;
+          while ((a + 1) * (a + 2) / 2 <= pr) ++a;
+          int b = pr - a * (a + 1) / 2;
+          real acc = 0;
+          for (int q = 0; q < nrow; ++q) {
+            const real* jr = jpool + off0 + q * wpad;
+            acc += wgt[row0 + q] * jr[a] * jr[b];
+          }
+          int da = dl[a], db = dl[b];  // dof lists are ascending: da >= db
+          H[da * ld + db] += acc;
+        }
+        B2_WSYNC();
+      }
+      spd_factor_solve(H, nv, ld, tmp, invd);
       for (int i = B2_LANE; i < nv; i += B2_NLANE) search[i] = -tmp[i];
       B2_WSYNC();
       // -- line search
       real sn = 0, q1 = 0, q2 = 0;
       for (int i = B2_LANE; i < nv; i += B2_NLANE) {
         real a = 0;
-        for (int e = 0; e < nv; ++e) a += M[i * nv + e] * search[e];
+        for (int e = 0; e < nv; ++e) a += M[e * ld + i] * search[e];
         Mv[i] = a;
         sn += search[i] * search[i];
         q1 += search[i] * (Ma[i] - qfs[i]);
         q2 += (real)0.5 * search[i] * a;
       }
       sn = sqrt(b2_wsum(sn)); q1 = b2_wsum(q1); q2 = b2_wsum(q2);
-      rows_dot(gJ, nefc, nv, search, chunk, jv, nullptr);
+      rows_dot(jpool, rowinfo, runinfo, rundofs, nefc, search, jv, nullptr);
       real alpha = linesearch(gauss, q1, q2, sn, tolerance, ls_tolerance, m.ls_iterations, scale, jar, jv, D, nefc);
       if (alpha == 0) break;
       for (int i = B2_LANE; i < nv; i += B2_NLANE) { qacc[i] += alpha * search[i]; Ma[i] += alpha * Mv[i]; }
@@ -567,7 +703,7 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
             for (int c = 0; c < 6; ++c) a[c] = g_cacc[6 * p + c];
             for (int e = 0; e < body_dofnum[b]; ++e) {
               int dd = body_dofadr[b] + e;
-              for (int c = 0; c < 6; ++c) a[c] += g_cdofdot[6 * dd + c] * qvel[dd] + cdof[6 * dd + c] * qacc[dd];
+              for (int c = 0; c < 6; ++c) a[c] += g_cdofdot[6 * dd + c] * qvel[dd] + g_cdof[6 * dd + c] * qacc[dd];
             }
           }
           for (int c = 0; c < 6; ++c) g_cacc[6 * b + c] = a[c];
@@ -779,7 +915,7 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
     B2_WSYNC();
     if (implicit) {
       // (M - h*qDeriv) a = qfrc_smooth + qfrc_constraint, qDeriv diagonal: -damping (+ actuator velocity gain)
-      for (int i = B2_LANE; i < nv * nv; i += B2_NLANE) H[i] = M[i];
+      for (int i = B2_LANE; i < nv * ld; i += B2_NLANE) H[i] = M[i];
       B2_WSYNC();
       const int* trnid = MI(B2_MI_ACTUATOR_TRNID);
       const int* biastype = MI(B2_MI_ACTUATOR_BIASTYPE);
@@ -798,12 +934,11 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
             qd += gear[6 * a] * gear[6 * a] * biasprm[10 * a + 2];
           }
         }
-        H[i * nv + i] -= timestep * qd;
+        H[i * ld + i] -= timestep * qd;
         tmp[i] = qfs[i] + qfc[i];
       }
       B2_WSYNC();
-      chol_factor(H, nv);
-      chol_solve(H, tmp, nv);
+      spd_factor_solve(H, nv, ld, tmp, invd);
     }
     for (int i = B2_LANE; i < nv; i += B2_NLANE) {
       real v = qvel[i] + timestep * tmp[i];

@@ -111,7 +111,7 @@ DATA_FLOAT_FIELDS = [
   ("CDOF_DOT", "cdof_dot", lambda m, c, j: (m.nv, 6)),
   ("CVEL", "cvel", lambda m, c, j: (m.nbody, 6)),
   ("CACC", "cacc", lambda m, c, j: (m.nbody, 6)),
-  ("QM", "qM", lambda m, c, j: (m.nv, m.nv)),
+  ("QM", "qM", lambda m, c, j: (m.nv, leading_dim(m.nv))),  # padded rows; the API view slices [..., :nv]
   ("QFRC_BIAS", "qfrc_bias", lambda m, c, j: (m.nv,)),
   ("QFRC_PASSIVE", "qfrc_passive", lambda m, c, j: (m.nv,)),
   ("QFRC_ACTUATOR", "qfrc_actuator", lambda m, c, j: (m.nv,)),
@@ -151,6 +151,14 @@ DATA_INT_FIELDS = [
   ("NEFC_DROPPED", "nefc_dropped", lambda m, c, j: ()),
 ]
 
+def leading_dim(n: int) -> int:
+  """Row stride of dense nv x nv matrices in the engine (b2_ld in csrc/b2_common.cuh)."""
+  ld = (n + 3) & ~3
+  if (ld & 7) != 4:
+    ld += 4
+  return ld
+
+
 NMF, NMI, NDF, NDI = len(MODEL_FLOAT_FIELDS), len(MODEL_INT_FIELDS), len(DATA_FLOAT_FIELDS), len(DATA_INT_FIELDS)
 
 
@@ -158,13 +166,13 @@ class B2Model(C.Structure):
   _fields_ = (
     [(n, C.c_int) for n in ("nq", "nv", "nu", "nbody", "njnt", "ngeom", "nsite", "nsensor", "nsensordata", "npair",
                             "nmocap", "nlevel", "integrator", "cone", "solver", "iterations", "ls_iterations",
-                            "disableflags", "has_accelerometer", "has_subtreevel")]
+                            "disableflags", "has_accelerometer", "has_subtreevel", "nlimited", "maxchain")]
     + [("mf", C.c_void_p * NMF), ("mf_stride", C.c_int * NMF), ("mi", C.c_void_p * NMI)]
   )
 
 
 class B2Data(C.Structure):
-  _fields_ = [("nworld", C.c_int), ("nconmax", C.c_int), ("njmax", C.c_int), ("df", C.c_void_p * NDF), ("di", C.c_void_p * NDI)]
+  _fields_ = [("nworld", C.c_int), ("nconmax", C.c_int), ("njmax", C.c_int), ("flags", C.c_int), ("df", C.c_void_p * NDF), ("di", C.c_void_p * NDI)]
 
 
 def derived_int_tables(m) -> dict[str, np.ndarray]:
@@ -237,7 +245,19 @@ def model_scalars(m, tables) -> dict[str, int]:
     cone=int(m.opt_cone), solver=int(m.opt_solver), iterations=int(m.opt_iterations),
     ls_iterations=int(m.opt_ls_iterations), disableflags=int(m.opt_disableflags),
     has_accelerometer=int(np.any(st == 1)), has_subtreevel=int(np.any((st == 35) | (st == 36))),
+    nlimited=int(np.sum((np.asarray(m.jnt_limited) != 0) & (np.asarray(m.jnt_type) >= 2))) if m.njnt else 0,
+    maxchain=_max_chain(m, tables),
   )
+
+
+def _max_chain(m, tables) -> int:
+  mask = tables["body_dofmask"].view(np.uint32).astype(np.uint64)
+  full = mask[:, 0] | (mask[:, 1] << np.uint64(32))
+  best = 1
+  for g1, g2 in np.asarray(m.pair_geom).reshape(-1, 2):
+    u = int(full[m.geom_bodyid[g1]] | full[m.geom_bodyid[g2]])
+    best = max(best, bin(u).count("1"))
+  return best
 
 
 def model_float_array(m, attr: str) -> np.ndarray:

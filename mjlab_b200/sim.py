@@ -72,6 +72,7 @@ class SimulationCfg:
   nconmax: int | None = None
   njmax: int | None = None
   ls_parallel: bool = True  # accepted for API parity; the engine always runs the exact iterative line search
+  export_efc_J: bool = False  # also write the dense constraint Jacobian to HBM every step (off on the hot path)
   contact_sensor_maxmatch: int = 64
   mujoco: MujocoCfg = field(default_factory=MujocoCfg)
 
@@ -215,6 +216,7 @@ class Simulation:
     # ---- data allocation (put_data) ----------------------------------------------------
     self._cd = E.B2Data()
     self._cd.nworld, self._cd.nconmax, self._cd.njmax = num_envs, self.nconmax, self.njmax
+    self._cd.flags = 1 if cfg.export_efc_J else 0
     self._data_fields: dict[str, Any] = {"nworld": num_envs}
     for i, (_, attr, shp) in enumerate(E.DATA_FLOAT_FIELDS):
       shape = (num_envs,) + tuple(shp(model, self.nconmax, self.njmax))
@@ -225,7 +227,7 @@ class Simulation:
         self._cd.df[i] = pad.data_ptr()
       else:
         self._cd.df[i] = t.data_ptr()
-      self._data_fields[attr] = t
+      self._data_fields[attr] = t[..., : model.nv] if attr == "qM" else t
     for i, (_, attr, shp) in enumerate(E.DATA_INT_FIELDS):
       shape = (num_envs,) + tuple(shp(model, self.nconmax, self.njmax))
       t = torch.zeros(shape, dtype=torch.int32, device=dev)

@@ -514,6 +514,10 @@ def make_constraint(m, d, njmax=None):
         rows_solimp.append(m.jnt_solimp[j])
         rows_type.append(0)
         rows_id.append(j)
+  if njmax is not None and len(rows_J) > njmax:
+    for lst in (rows_J, rows_pos, rows_margin, rows_invw, rows_solref, rows_solimp, rows_type, rows_id):
+      del lst[njmax:]
+  virtual_adr = len(rows_J)
   # contacts (pyramidal cone)
   biw = getattr(d, "body_invweight0", m.body_invweight0)
   for ci, c in enumerate(d.contacts):
@@ -525,7 +529,11 @@ def make_constraint(m, d, njmax=None):
     jc = c.frame @ jd  # rows: normal, t1, t2
     invw = biw[b1, 0] + biw[b2, 0]
     nrow = 1 if c.dim == 1 else 2 * (c.dim - 1)
-    if njmax is not None and len(rows_J) + nrow > njmax:
+    # row addresses are a running sum over all active contacts; a contact is kept iff
+    # its rows fit below njmax (so everything after the first overflow is dropped)
+    adr = virtual_adr
+    virtual_adr += nrow
+    if njmax is not None and adr + nrow > njmax:
       continue
     c.efc_address = len(rows_J)
     if c.dim == 1:
@@ -813,7 +821,9 @@ def solve(m, d):
     niter += 1
     improvement = scale * (oldcost - st["cost"])
     gradient = scale * np.linalg.norm(st["grad"])
-    if improvement < m.opt_tolerance or gradient < m.opt_tolerance:
+    # the float64 rounding floor keeps the rule identical to the fp32 device code, where it matters
+    floor = max(m.opt_tolerance, 8 * np.finfo(float).eps * scale * abs(st["cost"]))
+    if improvement < floor or gradient < m.opt_tolerance:
       break
   d.qacc = qacc
   d.efc_force = st["force"]

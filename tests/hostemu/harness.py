@@ -27,7 +27,7 @@ def build(real: str = "float") -> Path:
   if out.exists() and all(out.stat().st_mtime >= s.stat().st_mtime for s in srcs):
     return out
   cmd = ["g++", "-O2", "-std=c++17", "-DB2_HOSTEMU", f"-DB2_REAL={real}", "-shared", "-fPIC", "-ffp-contract=off",
-         "-o", str(out), str(HERE / "hostemu.cpp")]
+         "-Wno-unused-variable", "-o", str(out), str(HERE / "hostemu.cpp")]
   subprocess.run(cmd, check=True)
   return out
 
@@ -62,6 +62,7 @@ class HostSim:
       self.cm.mi[i] = a.ctypes.data
     self.cd = E.B2Data()
     self.cd.nworld, self.cd.nconmax, self.cd.njmax = nworld, nconmax, njmax
+    self.cd.flags = 1  # export dense efc_J for comparison with the oracle
     self.nworld = nworld
     for i, (_, attr, shp) in enumerate(E.DATA_FLOAT_FIELDS):
       a = np.zeros((nworld,) + tuple(shp(m, nconmax, njmax)), self.dtype)

@@ -13,9 +13,9 @@ from tests import util
 pytestmark = pytest.mark.gpu
 
 
-def make_sim(m, nworld, nconmax=35, njmax=300, integrator="implicitfast"):
+def make_sim(m, nworld, nconmax=35, njmax=300, integrator="implicitfast", export_efc_J=True):
   from mjlab_b200.sim import MujocoCfg, Simulation, SimulationCfg
-  cfg = SimulationCfg(nconmax=nconmax, njmax=njmax,
+  cfg = SimulationCfg(nconmax=nconmax, njmax=njmax, export_efc_J=export_efc_J,
                       mujoco=MujocoCfg(timestep=0.005, iterations=10, ls_iterations=20, integrator=integrator))
   return Simulation(nworld, cfg, m, "cuda:0")
 

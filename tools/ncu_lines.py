@@ -1,0 +1,72 @@
+"""Attribute an ncu SASS-level source page to CUDA source lines.
+
+  ncu -i prof.ncu-rep --page source --csv > sass.csv
+  python tools/ncu_lines.py sass.csv mjlab_b200/libb200sim.so k_solve [top]
+
+Joins the per-instruction rows of the ncu export with `nvdisasm -g` line info of
+the same cubin (instruction order is identical) and prints the hottest source
+lines by stall samples and by executed instructions.
+"""
+import csv
+import re
+import subprocess
+import sys
+import tempfile
+from collections import defaultdict
+from pathlib import Path
+
+
+def line_table(so: str, kernel: str):
+  with tempfile.TemporaryDirectory() as td:
+    subprocess.run(["cuobjdump", "-xelf", "all", str(Path(so).resolve())], cwd=td, check=True, capture_output=True)
+    cubin = next(Path(td).glob("*.cubin"))
+    txt = subprocess.run(["nvdisasm", "-g", "-c", str(cubin)], capture_output=True, text=True, check=True).stdout
+  out, cur, inside = [], ("?", 0), False
+  for ln in txt.splitlines():
+    if ln.startswith("\t.section"):
+      inside = (".text." in ln) and (kernel in ln)
+      continue
+    if not inside:
+      continue
+    mm = re.search(r'//## File "([^"]+)", line (\d+)', ln)
+    if mm:
+      cur = (Path(mm.group(1)).name, int(mm.group(2)))
+      continue
+    if re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+\S", ln):
+      out.append(cur)
+  return out
+
+
+def main():
+  sass_csv, so, kernel = sys.argv[1:4]
+  top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+  rows = list(csv.reader(open(sass_csv)))
+  hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
+  hdr = rows[hdr_i]
+  body = rows[hdr_i + 1:]
+  lines = line_table(so, kernel)
+  if len(lines) != len(body):
+    print(f"warning: {len(lines)} disassembled instructions vs {len(body)} profiled rows", file=sys.stderr)
+  ci = {n: hdr.index(n) for n in ("# Samples", "Instructions Executed", "Source")}
+  samples, insts = defaultdict(int), defaultdict(int)
+  for (f, l), r in zip(lines, body):
+    samples[(f, l)] += int(r[ci["# Samples"]] or 0)
+    insts[(f, l)] += int(r[ci["Instructions Executed"]] or 0)
+  ts, ti = sum(samples.values()), sum(insts.values())
+  src_cache = {}
+
+  def text(f, l):
+    if f not in src_cache:
+      cands = list(Path(".").rglob(f))
+      src_cache[f] = cands[0].read_text().splitlines() if cands else []
+    s = src_cache[f]
+    return s[l - 1].strip()[:110] if 0 < l <= len(s) else ""
+
+  print(f"total samples {ts}, warp instructions {ti}")
+  print("--- by stall samples")
+  for k, v in sorted(samples.items(), key=lambda kv: -kv[1])[:top]:
+    print(f"{100*v/ts:5.1f}% smp {100*insts[k]/ti:5.1f}% ins  {k[0]}:{k[1]:<4d} {text(*k)}")
+
+
+if __name__ == "__main__":
+  main()
