@@ -23,6 +23,8 @@ typedef B2_REAL real;
 
 #ifdef B2_HOSTEMU
 #define B2_DEV static inline
+#define B2_DEVN static
+#define B2_UNROLL1
 #define B2_LANE 0
 #define B2_NLANE 1
 #define B2_WSYNC() ((void)0)
@@ -38,6 +40,10 @@ B2_DEV real b2_rsqrt(real x) { return (real)1 / sqrt(x); }
 #define B2_LDG(p) (*(p))
 #else
 #define B2_DEV __device__ __forceinline__
+// Out-of-line device helpers + rolled loops on the Newton path: the solver kernel is instruction-fetch
+// bound (ncu: stall_no_instruction), so hot code is kept small enough for the instruction caches.
+#define B2_DEVN static __device__ __noinline__
+#define B2_UNROLL1 _Pragma("unroll 1")
 #define B2_LANE ((int)(threadIdx.x & 31))
 #define B2_NLANE 32
 #define B2_WSYNC() __syncwarp()
@@ -65,7 +71,7 @@ B2_DEV unsigned b2_ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
 B2_DEV int b2_popc(unsigned x) { return __popc(x); }
 B2_DEV int b2_popcll(unsigned long long x) { return __popcll(x); }
 B2_DEV unsigned b2_lanemask_lt() { return (1u << (threadIdx.x & 31)) - 1u; }
-B2_DEV real b2_rsqrt(real x) { return (real)1 / sqrtf(x); }
+B2_DEV real b2_rsqrt(real x) { return rsqrtf(x); }
 #define B2_LDG(p) __ldg(p)
 #endif
 
@@ -202,11 +208,13 @@ B2_DEV real b2_shfl(real x, int src) { return __shfl_sync(0xffffffffu, x, src); 
 #endif
 
 // In-place lower Cholesky of A (lower triangle valid, upper ignored). invd[j] <- 1 / L[j][j].
-B2_DEV void chol_factor(real* A, int n, int ld, real* invd) {
+B2_DEVN void chol_factor(real* A, int n, int ld, real* invd) {
+  B2_UNROLL1
   for (int j = 0; j < n; ++j) {
     B2_WSYNC();
     const real* rj = A + j * ld;
     real inv = 0;
+    B2_UNROLL1
     for (int base = j; base < n; base += B2_NLANE) {
       int i = base + B2_LANE;
       real s = 0;
@@ -216,6 +224,7 @@ B2_DEV void chol_factor(real* A, int n, int ld, real* invd) {
         int k = 0;
 #ifndef B2_HOSTEMU
         real s2 = 0;
+        B2_UNROLL1
         for (; k + 4 <= j; k += 4) {
           float4 a = *reinterpret_cast<const float4*>(ri + k);
           float4 b = *reinterpret_cast<const float4*>(rj + k);
@@ -224,6 +233,7 @@ B2_DEV void chol_factor(real* A, int n, int ld, real* invd) {
         }
         s += s2;
 #endif
+        B2_UNROLL1
         for (; k < j; ++k) s -= ri[k] * rj[k];
       }
       if (base == j) {
@@ -238,7 +248,7 @@ B2_DEV void chol_factor(real* A, int n, int ld, real* invd) {
 }
 
 // x <- (L L^T)^-1 x, x in shared memory.
-B2_DEV void chol_solve(const real* L, int n, int ld, const real* invd, real* x) {
+B2_DEVN void chol_solve(const real* L, int n, int ld, const real* invd, real* x) {
 #ifdef B2_HOSTEMU
   for (int k = 0; k < n; ++k) {
     real xk = x[k] * invd[k];
@@ -256,6 +266,7 @@ B2_DEV void chol_solve(const real* L, int n, int ld, const real* invd, real* x) 
   const int row0 = lane, row1 = lane + 32;
   real x0 = row0 < n ? x[row0] : (real)0;
   real x1 = row1 < n ? x[row1] : (real)0;
+  B2_UNROLL1
   for (int k = 0; k < n; ++k) {
     real l0 = row0 > k && row0 < n ? L[row0 * ld + k] : (real)0;
     real l1 = row1 > k && row1 < n ? L[row1 * ld + k] : (real)0;
@@ -263,6 +274,7 @@ B2_DEV void chol_solve(const real* L, int n, int ld, const real* invd, real* x) 
     if (row0 == k) x0 = xk; else x0 = fmaf(-l0, xk, x0);
     if (row1 == k) x1 = xk; else x1 = fmaf(-l1, xk, x1);
   }
+  B2_UNROLL1
   for (int k = n - 1; k >= 0; --k) {
     real l0 = row0 < k ? L[k * ld + row0] : (real)0;
     real l1 = row1 < k ? L[k * ld + row1] : (real)0;
@@ -273,6 +285,20 @@ B2_DEV void chol_solve(const real* L, int n, int ld, const real* invd, real* x) 
   if (row0 < n) x[row0] = x0;
   if (row1 < n) x[row1] = x1;
 #endif
+  B2_WSYNC();
+}
+
+// y = M x for a symmetric M [n][ld] in global memory: lane i walks column i (== row i), so every
+// load of the warp is one coalesced segment.
+B2_DEVN void symv_global(const real* M, int n, int ld, const real* x, real* y) {
+  B2_UNROLL1
+  for (int i = B2_LANE; i < n; i += B2_NLANE) {
+    real a = 0, b = 0;
+    int e = 0;
+    for (; e + 2 <= n; e += 2) { a += M[e * ld + i] * x[e]; b += M[(e + 1) * ld + i] * x[e + 1]; }
+    if (e < n) a += M[e * ld + i] * x[e];
+    y[i] = a + b;
+  }
   B2_WSYNC();
 }
 

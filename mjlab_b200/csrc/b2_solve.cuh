@@ -78,8 +78,9 @@ B2_DEV void kbi(real timestep, const real* solref, const real* solimp, real pos,
 }
 
 // y[r] = J[r,:] . x (- sub[r]) over compact rows; lanes over rows.
-B2_DEV void rows_dot(const real* jpool, const int* rowinfo, const int* runinfo, const unsigned char* rundofs, int nefc,
+B2_DEVN void rows_dot(const real* jpool, const int* rowinfo, const int* runinfo, const unsigned char* rundofs, int nefc,
                      const real* x, real* y, const real* sub) {
+  B2_UNROLL1
   for (int r = B2_LANE; r < nefc; r += B2_NLANE) {
     int info = rowinfo[r];
     int off = info & 0xffff, run = info >> 16;
@@ -88,6 +89,7 @@ B2_DEV void rows_dot(const real* jpool, const int* rowinfo, const int* runinfo, 
     const real* jr = jpool + off;
     const unsigned char* dl = rundofs + dofoff;
     real acc = 0;
+    B2_UNROLL1
     for (int a = 0; a < wd; ++a) acc += jr[a] * x[dl[a]];
     y[r] = sub ? acc - sub[r] : acc;
   }
@@ -96,12 +98,7 @@ B2_DEV void rows_dot(const real* jpool, const int* rowinfo, const int* runinfo, 
 
 struct LsPnt { real alpha, cost, d1, d2; };
 
-#ifdef B2_HOSTEMU
-B2_DEV
-#else
-__device__ __noinline__
-#endif
-LsPnt ls_eval(real alpha, real q0g, real q1g, real q2g, const real* jar, const real* jv, const real* D, int nefc) {
+B2_DEVN LsPnt ls_eval(real alpha, real q0g, real q1g, real q2g, const real* jar, const real* jv, const real* D, int nefc) {
   real q0 = 0, q1 = 0, q2 = 0;
   for (int r = B2_LANE; r < nefc; r += B2_NLANE) {
     real x = jar[r] + alpha * jv[r];
@@ -122,7 +119,7 @@ LsPnt ls_eval(real alpha, real q0g, real q1g, real q2g, const real* jar, const r
   return p;
 }
 
-B2_DEV bool ls_update_bracket(LsPnt& p, const LsPnt* cand, LsPnt& pnext, int& nev, real q0g, real q1g, real q2g,
+B2_DEVN bool ls_update_bracket(LsPnt& p, const LsPnt* cand, LsPnt& pnext, int& nev, real q0g, real q1g, real q2g,
                               const real* jar, const real* jv, const real* D, int nefc) {
   bool flag = false;
   for (int i = 0; i < 3; ++i) {
@@ -135,7 +132,7 @@ B2_DEV bool ls_update_bracket(LsPnt& p, const LsPnt* cand, LsPnt& pnext, int& ne
 
 // Exact 1-D minimisation along `search` (MuJoCo's iterative primal line search:
 // Newton steps until the derivative changes sign, then bracket refinement).
-B2_DEV real linesearch(real q0g, real q1g, real q2g, real snorm, real tolerance, real ls_tolerance, int ls_iterations,
+B2_DEVN real linesearch(real q0g, real q1g, real q2g, real snorm, real tolerance, real ls_tolerance, int ls_iterations,
                        real scale, const real* jar, const real* jv, const real* D, int nefc) {
   if (snorm < B2_MINVAL) return 0;
   real gtol = tolerance * ls_tolerance * snorm / scale;
@@ -523,24 +520,15 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
     real cw = 0;
     for (int r = B2_LANE; r < nefc; r += B2_NLANE) { real x = jar[r]; if (x < 0) cw += (real)0.5 * D[r] * x * x; }
     real gw = 0;
-    for (int i = B2_LANE; i < nv; i += B2_NLANE) {
-      real a = 0;
-      for (int e = 0; e < nv; ++e) a += M[e * ld + i] * qacc[e];
-      Ma[i] = a;
-      gw += (real)0.5 * (a - qfs[i]) * (qacc[i] - qas[i]);
-    }
+    symv_global(M, nv, ld, qacc, Ma);
+    for (int i = B2_LANE; i < nv; i += B2_NLANE) gw += (real)0.5 * (Ma[i] - qfs[i]) * (qacc[i] - qas[i]);
     cw = b2_wsum(cw + gw);
     B2_WSYNC();
     if (cw > cs) {
       for (int i = B2_LANE; i < nv; i += B2_NLANE) qacc[i] = qas[i];
       B2_WSYNC();
       rows_dot(jpool, rowinfo, runinfo, rundofs, nefc, qacc, jar, aref);
-      for (int i = B2_LANE; i < nv; i += B2_NLANE) {
-        real a = 0;
-        for (int e = 0; e < nv; ++e) a += M[e * ld + i] * qacc[e];
-        Ma[i] = a;
-      }
-      B2_WSYNC();
+      symv_global(M, nv, ld, qacc, Ma);
     }
     real cost = 0, gauss = 0;
     // rounding floor of the cost difference in this arithmetic: below it "improvement" is noise
@@ -576,6 +564,7 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
         const unsigned char* dl = rundofs + dofoff;
         for (int a = B2_LANE; a < wd; a += B2_NLANE) {
           real ff = 0;
+          B2_UNROLL1
           for (int q = 0; q < nrow; ++q) ff -= jpool[off0 + q * wpad + a] * wgt[row0 + q] * jar[row0 + q];
           qfc[dl[a]] += ff;
         }
@@ -595,6 +584,7 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
       }
       if (it >= m.iterations) break;
       // -- part 2: H = M + J^T diag(w) J, only when another Newton step will be taken
+      B2_UNROLL1
       for (int i = B2_LANE; i < nv * ld; i += B2_NLANE) H[i] = M[i];
       B2_WSYNC();
       if (nl > 0) {
@@ -619,6 +609,7 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
           while ((a + 1) * (a + 2) / 2 <= pr) ++a;
           int b = pr - a * (a + 1) / 2;
           real acc = 0;
+          B2_UNROLL1
           for (int q = 0; q < nrow; ++q) {
             const real* jr = jpool + off0 + q * wpad;
             acc += wgt[row0 + q] * jr[a] * jr[b];
@@ -633,13 +624,11 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
       B2_WSYNC();
       // -- line search
       real sn = 0, q1 = 0, q2 = 0;
+      symv_global(M, nv, ld, search, Mv);
       for (int i = B2_LANE; i < nv; i += B2_NLANE) {
-        real a = 0;
-        for (int e = 0; e < nv; ++e) a += M[e * ld + i] * search[e];
-        Mv[i] = a;
         sn += search[i] * search[i];
         q1 += search[i] * (Ma[i] - qfs[i]);
-        q2 += (real)0.5 * search[i] * a;
+        q2 += (real)0.5 * search[i] * Mv[i];
       }
       sn = sqrt(b2_wsum(sn)); q1 = b2_wsum(q1); q2 = b2_wsum(q2);
       rows_dot(jpool, rowinfo, runinfo, rundofs, nefc, search, jv, nullptr);

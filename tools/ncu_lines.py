@@ -48,6 +48,9 @@ def main():
   if len(lines) != len(body):
     print(f"warning: {len(lines)} disassembled instructions vs {len(body)} profiled rows", file=sys.stderr)
   ci = {n: hdr.index(n) for n in ("# Samples", "Instructions Executed", "Source")}
+  reason = sys.argv[5] if len(sys.argv) > 5 else None  # e.g. stall_no_inst: rank by that stall reason
+  if reason:
+    ci["# Samples"] = hdr.index(reason)
   samples, insts = defaultdict(int), defaultdict(int)
   for (f, l), r in zip(lines, body):
     samples[(f, l)] += int(r[ci["# Samples"]] or 0)
