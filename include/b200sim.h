@@ -119,6 +119,7 @@ enum b2_mi {
   B2_MI_SENSOR_INTPRM,     /* nsensor*3 */
   B2_MI_SENSOR_DIM,        /* nsensor */
   B2_MI_SENSOR_ADR,        /* nsensor */
+  B2_MI_DOF_ACTID,         /* nv: the actuator driving this dof, -1 none, -2 several (kernels then scan) */
   B2_MI_COUNT
 };
 

@@ -208,11 +208,15 @@ B2_DEV real b2_shfl(real x, int src) { return __shfl_sync(0xffffffffu, x, src); 
 #endif
 
 // In-place lower Cholesky of A (lower triangle valid, upper ignored). invd[j] <- 1 / L[j][j].
-B2_DEVN void chol_factor(real* A, int n, int ld, real* invd) {
+B2_DEVN void chol_factor(real* A, int n, int ld, real* invd, real* prow) {
   B2_UNROLL1
   for (int j = 0; j < n; ++j) {
     B2_WSYNC();
+    // pivot row, zero-padded to a multiple of 4 so the k loop needs no scalar tail
     const real* rj = A + j * ld;
+    for (int k = B2_LANE; k < ld; k += B2_NLANE) prow[k] = k < j ? rj[k] : (real)0;
+    B2_WSYNC();
+    const int j4 = (j + 3) & ~3;
     real inv = 0;
     B2_UNROLL1
     for (int base = j; base < n; base += B2_NLANE) {
@@ -221,20 +225,19 @@ B2_DEVN void chol_factor(real* A, int n, int ld, real* invd) {
       if (i < n) {
         const real* ri = A + i * ld;
         s = ri[j];
-        int k = 0;
 #ifndef B2_HOSTEMU
         real s2 = 0;
         B2_UNROLL1
-        for (; k + 4 <= j; k += 4) {
+        for (int k = 0; k < j4; k += 4) {
           float4 a = *reinterpret_cast<const float4*>(ri + k);
-          float4 b = *reinterpret_cast<const float4*>(rj + k);
+          float4 b = *reinterpret_cast<const float4*>(prow + k);
           s = fmaf(-a.x, b.x, s); s2 = fmaf(-a.y, b.y, s2);
           s = fmaf(-a.z, b.z, s); s2 = fmaf(-a.w, b.w, s2);
         }
         s += s2;
+#else
+        for (int k = 0; k < j4; ++k) s -= ri[k] * prow[k];
 #endif
-        B2_UNROLL1
-        for (; k < j; ++k) s -= ri[k] * rj[k];
       }
       if (base == j) {
         real piv = b2_shfl(s, 0);
@@ -293,17 +296,41 @@ B2_DEVN void chol_solve(const real* L, int n, int ld, const real* invd, real* x)
 B2_DEVN void symv_global(const real* M, int n, int ld, const real* x, real* y) {
   B2_UNROLL1
   for (int i = B2_LANE; i < n; i += B2_NLANE) {
-    real a = 0, b = 0;
+    real a0 = 0, a1 = 0, a2 = 0, a3 = 0;
     int e = 0;
-    for (; e + 2 <= n; e += 2) { a += M[e * ld + i] * x[e]; b += M[(e + 1) * ld + i] * x[e + 1]; }
-    if (e < n) a += M[e * ld + i] * x[e];
-    y[i] = a + b;
+    B2_UNROLL1
+    for (; e + 4 <= n; e += 4) {
+      real m0 = M[e * ld + i], m1 = M[(e + 1) * ld + i], m2 = M[(e + 2) * ld + i], m3 = M[(e + 3) * ld + i];
+      a0 += m0 * x[e]; a1 += m1 * x[e + 1]; a2 += m2 * x[e + 2]; a3 += m3 * x[e + 3];
+    }
+    for (; e < n; ++e) a0 += M[e * ld + i] * x[e];
+    y[i] = (a0 + a1) + (a2 + a3);
   }
+  B2_WSYNC();
+}
+
+// dst[0..count) = src[0..count) (global -> shared), count % 4 == 0, both 16-byte aligned:
+// 128-bit loads, four in flight per lane so the L2 latency is paid once per batch.
+B2_DEVN void copy_g2s(real* dst, const real* src, int count) {
+#ifdef B2_HOSTEMU
+  for (int i = 0; i < count; ++i) dst[i] = src[i];
+#else
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+  float4* d4 = reinterpret_cast<float4*>(dst);
+  const int n4 = count >> 2;
+  int i = B2_LANE;
+  B2_UNROLL1
+  for (; i + 96 < n4; i += 128) {
+    float4 v0 = s4[i], v1 = s4[i + 32], v2 = s4[i + 64], v3 = s4[i + 96];
+    d4[i] = v0; d4[i + 32] = v1; d4[i + 64] = v2; d4[i + 96] = v3;
+  }
+  for (; i < n4; i += 32) d4[i] = s4[i];
+#endif
   B2_WSYNC();
 }
 
 // A (n x n, leading dimension ld, lower triangle valid) <- chol(A);  x <- A^-1 x.
 B2_DEV void spd_factor_solve(real* A, int n, int ld, real* x, real* invd) {
-  chol_factor(A, n, ld, invd);
+  chol_factor(A, n, ld, invd, invd + 64);
   chol_solve(A, n, ld, invd, x);
 }

@@ -36,7 +36,7 @@ static inline SmoothSmem smooth_smem_layout(int nq, int nv, int nu, int nbody, i
   s.M = take(nv * b2_ld(nv)); s.f = take(nv);
   s.aforce = take(nu);
   s.cand = take(ncand);      // candidate pair ids (ints stored in real-sized slots)
-  s.invd = take(64);
+  s.invd = take(64 + 72);  // 1/diag, then the zero-padded pivot row of the Cholesky
   s.total = o;
   return s;
 }
@@ -705,6 +705,7 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
     const real* qspring = MF(B2_MF_QPOS_SPRING);
     const int* dof_jntid = MI(B2_MI_DOF_JNTID);
     const int* trnid = MI(B2_MI_ACTUATOR_TRNID);
+    const int* dof_actid = MI(B2_MI_DOF_ACTID);
     const real* gear = MF(B2_MF_ACTUATOR_GEAR);
     const real* qfrc_applied = d.df[B2_DF_QFRC_APPLIED] + (size_t)w * nv;
     const real* xfrc = d.df[B2_DF_XFRC_APPLIED] + (size_t)w * nb * 6;
@@ -729,8 +730,12 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
         pas -= stiffness[j] * (qpos[qa] - qspring[qa]);
       }
       real act = 0;
-      for (int a = 0; a < nu; ++a)
-        if (jnt_dofadr[trnid[2 * a]] == i) act += gear[6 * a] * aforce[a];
+      {
+        int aid = dof_actid[i];
+        int a_lo = aid >= 0 ? aid : 0, a_hi = aid >= 0 ? aid + 1 : (aid == -2 ? nu : 0);
+        for (int a = a_lo; a < a_hi; ++a)
+          if (jnt_dofadr[trnid[2 * a]] == i) act += gear[6 * a] * aforce[a];
+      }
       real fs = pas - bias + act + qfrc_applied[i];
       if (anyx) {
         for (int b = 1; b < nb; ++b) {

@@ -30,7 +30,7 @@ static inline SolveSmem solve_smem_layout(int nv, int rows_cap, int runs_cap, in
   s.M = -1;  // qM stays in HBM/L2 (read coalesced through its symmetry), not staged
   s.H = take(nv * b2_ld(nv));
   s.qvel = take(nv); s.qacc = take(nv); s.Ma = take(nv); s.grad = take(nv); s.search = take(nv); s.Mv = take(nv);
-  s.qfs = take(nv); s.qas = take(nv); s.qfc = take(nv); s.tmp = take(nv); s.invd = take(64);
+  s.qfs = take(nv); s.qas = take(nv); s.qfc = take(nv); s.tmp = take(nv); s.invd = take(64 + 72);  // 1/diag, then the zero-padded pivot row of the Cholesky
   // D and aref are first written after the Jacobian rows are assembled; cdof is only read
   // during that assembly, so the two share storage (needs 2*rows_cap >= 6*nv, else padded).
   int dd = 2 * ((rows_cap + 3) & ~3);
@@ -584,9 +584,7 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
       }
       if (it >= m.iterations) break;
       // -- part 2: H = M + J^T diag(w) J, only when another Newton step will be taken
-      B2_UNROLL1
-      for (int i = B2_LANE; i < nv * ld; i += B2_NLANE) H[i] = M[i];
-      B2_WSYNC();
+      copy_g2s(H, M, nv * ld);
       if (nl > 0) {
         for (int e = B2_LANE; e < nv; e += B2_NLANE) {
           real hh = 0;
@@ -904,9 +902,9 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
     B2_WSYNC();
     if (implicit) {
       // (M - h*qDeriv) a = qfrc_smooth + qfrc_constraint, qDeriv diagonal: -damping (+ actuator velocity gain)
-      for (int i = B2_LANE; i < nv * ld; i += B2_NLANE) H[i] = M[i];
-      B2_WSYNC();
+      copy_g2s(H, M, nv * ld);
       const int* trnid = MI(B2_MI_ACTUATOR_TRNID);
+      const int* dof_actid = MI(B2_MI_DOF_ACTID);
       const int* biastype = MI(B2_MI_ACTUATOR_BIASTYPE);
       const int* flim = MI(B2_MI_ACTUATOR_FORCELIMITED);
       const real* biasprm = MF(B2_MF_ACTUATOR_BIASPRM);
@@ -916,7 +914,9 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
       for (int i = B2_LANE; i < nv; i += B2_NLANE) {
         real qd = -damping[i];
         if (m.integrator == B2_INT_IMPLICITFAST) {
-          for (int a = 0; a < nu; ++a) {
+          int aid = dof_actid[i];
+          int a_lo = aid >= 0 ? aid : 0, a_hi = aid >= 0 ? aid + 1 : (aid == -2 ? nu : 0);
+          for (int a = a_lo; a < a_hi; ++a) {
             if (biastype[a] != 1 || jnt_dofadr[trnid[2 * a]] != i) continue;
             real fa = g_af[a];
             if (flim[a] && (fa <= frange[2 * a] || fa >= frange[2 * a + 1])) continue;

@@ -79,7 +79,7 @@ MODEL_INT_FIELDS = [
   ("ACTUATOR_FORCELIMITED", "actuator_forcelimited"), ("ACTUATOR_CTRLLIMITED", "actuator_ctrllimited"),
   ("SENSOR_TYPE", "sensor_type"), ("SENSOR_OBJTYPE", "sensor_objtype"), ("SENSOR_OBJID", "sensor_objid"),
   ("SENSOR_REFTYPE", "sensor_reftype"), ("SENSOR_REFID", "sensor_refid"), ("SENSOR_INTPRM", "sensor_intprm"),
-  ("SENSOR_DIM", "sensor_dim"), ("SENSOR_ADR", "sensor_adr"),
+  ("SENSOR_DIM", "sensor_dim"), ("SENSOR_ADR", "sensor_adr"), ("DOF_ACTID", "dof_actid"),
 ]
 
 # (enum name, attribute on Data, per-world shape as a function of (model, nconmax, njmax))
@@ -205,12 +205,17 @@ def derived_int_tables(m) -> dict[str, np.ndarray]:
       lastdof[i] = m.body_dofadr[i] + m.body_dofnum[i] - 1
       for k in range(m.body_dofnum[i]):
         mask[i] |= np.uint64(1) << np.uint64(m.body_dofadr[i] + k)
+  dof_actid = -np.ones(max(m.nv, 1), np.int32)
+  for a in range(m.nu):
+    dof = int(m.jnt_dofadr[m.actuator_trnid[a, 0]])
+    dof_actid[dof] = a if dof_actid[dof] == -1 else -2
   dofmask = np.zeros((nb, 2), np.uint32)
   dofmask[:, 0] = (mask & np.uint64(0xFFFFFFFF)).astype(np.uint32)
   dofmask[:, 1] = (mask >> np.uint64(32)).astype(np.uint32)
   return dict(
     nlevel=nlevel, level_adr=level_adr, level_body=order, child_adr=child_adr,
     child_body=np.array(flat if flat else [0], np.int32), body_lastdof=lastdof, body_dofmask=dofmask.view(np.int32),
+    dof_actid=dof_actid,
   )
 
 

@@ -1,0 +1,66 @@
+"""The C-ABI library loads and exports every symbol include/b200sim.h declares; the Python field tables mirror
+the header enums; the product refuses to run without the CUDA library (no CPU fallback)."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+
+from mjlab_b200 import engine as E
+
+ROOT = Path(__file__).resolve().parents[1]
+HEADER = (ROOT / "include" / "b200sim.h").read_text()
+
+
+def enum_names(tag):
+  body = re.search(r"enum %s \{(.*?)\};" % tag, HEADER, re.S).group(1)
+  body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+  return [n.split("=")[0].strip() for n in body.split(",") if n.strip()]
+
+
+@pytest.mark.parametrize("tag,prefix,table", [
+  ("b2_mf", "B2_MF_", E.MODEL_FLOAT_FIELDS), ("b2_mi", "B2_MI_", E.MODEL_INT_FIELDS),
+  ("b2_df", "B2_DF_", E.DATA_FLOAT_FIELDS), ("b2_di", "B2_DI_", E.DATA_INT_FIELDS)])
+def test_field_tables_mirror_header(tag, prefix, table):
+  names = enum_names(tag)
+  assert names[-1] == prefix + "COUNT"
+  assert [prefix + t[0] for t in table] == names[:-1]
+
+
+def declared_functions():
+  return re.findall(r"^\s*(?:int|long long|const char\*)\s+(b2_\w+)\s*\(", HEADER, re.M)
+
+
+def test_library_exports_declared_symbols():
+  __import__("__graft_entry__").build()
+  lib = ctypes.CDLL(str(E.LIB_PATH))
+  fns = declared_functions()
+  assert {"b2_step", "b2_forward", "b2_reset", "b2_repeat_rows", "b2_check", "b2_stage", "b2_last_error"} <= set(fns)
+  for fn in fns:
+    assert hasattr(lib, fn), fn
+  assert lib.b2_abi_version() == 1
+  assert lib.b2_sizeof_model() == ctypes.sizeof(E.B2Model)
+  assert lib.b2_sizeof_data() == ctypes.sizeof(E.B2Data)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+  monkeypatch.setattr(E, "_lib", None)
+  monkeypatch.setenv("B200SIM_LIB", str(tmp_path / "nope.so"))
+  with pytest.raises(RuntimeError, match="no CPU fallback"):
+    E.load_library()
+
+
+def test_simulation_requires_cuda():
+  import mjlab_b200
+  from mjlab_b200.sim import Simulation, SimulationCfg
+  m = mjlab_b200.load_model("go1_flat")
+  with pytest.raises(RuntimeError):
+    Simulation(2, SimulationCfg(), m, "cpu")
+
+
+def test_product_does_not_import_oracle():
+  """The oracle is test infrastructure: nothing under mjlab_b200/ may import or execute it."""
+  for p in (ROOT / "mjlab_b200").rglob("*.py"):
+    src = p.read_text()
+    assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), p
+    assert "hostemu" not in src, p

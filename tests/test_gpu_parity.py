@@ -127,3 +127,56 @@ def test_determinism(g1):
     outs.append((sim.data.qpos.clone(), sim.data.qvel.clone(), sim.data.sensordata.clone()))
   for a, b in zip(outs[0], outs[1]):
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("name", ["go1_flat", "g1_flat"])
+def test_gpu_matches_committed_golden(name):
+  """CUDA path against tests/golden (made by tools/make_golden.py); no oracle needed at run time."""
+  import mjlab_b200
+  g = np.load(f"tests/golden/physics_{name}.npz")
+  m = mjlab_b200.load_model(name)
+  nw = g["qpos0"].shape[0]
+  sim = make_sim(m, nw, nconmax=int(g["nconmax"]), njmax=int(g["njmax"]))
+  load_state(sim, g["qpos0"], g["qvel0"], g["ctrl"], g["xfrc"])
+  for _ in range(int(g["nstep"])):
+    sim.step()
+  torch.cuda.synchronize()
+  # bit-exact integer results
+  assert sim.data.ncon.cpu().tolist() == g["ncon"].tolist()
+  assert sim.data.nefc.cpu().tolist() == g["nefc"].tolist()
+  for w in range(nw):
+    n = int(g["ncon"][w])
+    assert sim.data.contact_geom[w, :n].cpu().tolist() == g["contact_geom"][w, :n].tolist()
+  # fp32 vs fp64: 1e-4 relative per step on qpos / qvel (north_star), nstep steps
+  nstep = int(g["nstep"])
+  assert relerr(sim.data.qpos.cpu().numpy(), g["qpos"]) < 1e-4 * nstep
+  assert relerr(sim.data.qvel.cpu().numpy(), g["qvel"]) < 1e-3 * nstep
+  assert relerr(sim.data.xpos.cpu().numpy(), g["xpos"]) < 1e-4 * nstep
+
+
+def test_full_size_properties(g1):
+  """BASELINE size (4096 worlds): size-independent properties instead of an oracle run.
+  Identical worlds give identical results (batch invariance), quaternions stay normalised, no NaNs,
+  contact counts bounded, a reset world equals a freshly constructed one."""
+  nw = 4096
+  sim = make_sim(g1, nw, export_efc_J=False)
+  qpos, qvel, ctrl, xfrc = util.random_states(g1, 8, seed=7)
+  reps = nw // 8
+  load_state(sim, np.tile(qpos, (reps, 1)), np.tile(qvel, (reps, 1)), np.tile(ctrl, (reps, 1)), np.tile(xfrc, (reps, 1, 1)))
+  for _ in range(10):
+    sim.step()
+  torch.cuda.synchronize()
+  q = sim.data.qpos.view(reps, 8, -1)
+  assert torch.equal(q, q[:1].expand_as(q))
+  s = sim.data.sensordata.view(reps, 8, -1)
+  assert torch.equal(s, s[:1].expand_as(s))
+  assert torch.isfinite(sim.data.qpos).all() and torch.isfinite(sim.data.qvel).all()
+  assert torch.allclose(sim.data.qpos[:, 3:7].norm(dim=1), torch.ones(nw, device="cuda:0"), atol=1e-5)
+  assert int(sim.data.ncon.max()) <= 35 and int(sim.data.nefc.max()) <= 300
+  # small case == same worlds inside the big batch
+  small = make_sim(g1, 8, export_efc_J=False)
+  load_state(small, qpos, qvel, ctrl, xfrc)
+  for _ in range(10):
+    small.step()
+  torch.cuda.synchronize()
+  assert torch.equal(small.data.qpos, sim.data.qpos[:8])
