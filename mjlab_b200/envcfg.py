@@ -1,0 +1,210 @@
+"""Resolved configuration of the velocity task (G1 / Go1, flat) for the env kernels.
+
+Restates, as plain arrays, what the reference resolves at `load_managers()` time from
+`make_velocity_env_cfg()` (src/mjlab/tasks/velocity/velocity_env_cfg.py:33-353) and the per-robot overrides
+(config/g1/env_cfgs.py:20-173, config/go1/env_cfgs.py:15-127): index maps of the robot entity
+(entity/entity.py:754-813), default state and soft joint limits (entity/entity.py:409-462), action scale
+(g1_constants.py:287-295), sensor addresses, reward weights / parameters, observation noise ranges, command,
+push and reset ranges.
+"""
+
+from __future__ import annotations
+
+import math
+import re
+from dataclasses import dataclass, field
+
+import numpy as np
+
+REWARD_NAMES = (
+  "track_linear_velocity", "track_angular_velocity", "upright", "pose", "body_ang_vel", "angular_momentum",
+  "dof_pos_limits", "action_rate_l2", "air_time", "foot_clearance", "foot_swing_height", "foot_slip", "soft_landing",
+  "self_collisions",
+)
+TERMINATION_NAMES = ("time_out", "fell_over", "illegal_contact")
+
+_G1_STD_WALK = {
+  r".*hip_pitch.*": 0.3, r".*hip_roll.*": 0.15, r".*hip_yaw.*": 0.15, r".*knee.*": 0.35, r".*ankle_pitch.*": 0.25,
+  r".*ankle_roll.*": 0.1, r".*waist_yaw.*": 0.2, r".*waist_roll.*": 0.08, r".*waist_pitch.*": 0.1,
+  r".*shoulder_pitch.*": 0.15, r".*shoulder_roll.*": 0.15, r".*shoulder_yaw.*": 0.1, r".*elbow.*": 0.15, r".*wrist.*": 0.3,
+}
+_G1_STD_RUN = {
+  r".*hip_pitch.*": 0.5, r".*hip_roll.*": 0.2, r".*hip_yaw.*": 0.2, r".*knee.*": 0.6, r".*ankle_pitch.*": 0.35,
+  r".*ankle_roll.*": 0.15, r".*waist_yaw.*": 0.3, r".*waist_roll.*": 0.08, r".*waist_pitch.*": 0.2,
+  r".*shoulder_pitch.*": 0.5, r".*shoulder_roll.*": 0.2, r".*shoulder_yaw.*": 0.15, r".*elbow.*": 0.35, r".*wrist.*": 0.3,
+}
+_GO1_HT = r".*(FR|FL|RR|RL)_(hip|thigh)_joint.*"
+_GO1_C = r".*(FR|FL|RR|RL)_calf_joint.*"
+
+
+@dataclass
+class VelocityCfg:
+  robot: str
+  nj: int
+  nfeet: int
+  root_body: int
+  body_ids: np.ndarray
+  geom_ids: np.ndarray
+  site_ids: np.ndarray
+  joint_ids: np.ndarray
+  joint_names: list
+  joint_q_adr: np.ndarray
+  joint_v_adr: np.ndarray
+  ctrl_ids: np.ndarray
+  default_root_state: np.ndarray
+  default_joint_pos: np.ndarray
+  joint_pos_limits: np.ndarray
+  soft_joint_pos_limits: np.ndarray
+  action_scale: np.ndarray
+  foot_site_names: tuple
+  foot_site_local_ids: tuple
+  foot_site_ids: np.ndarray
+  foot_found_adr: np.ndarray
+  foot_force_adr: np.ndarray
+  linvel_adr: int
+  angvel_adr: int
+  angmom_adr: int
+  selfcol_adr: int
+  illegal_adr: int
+  illegal_count: int
+  upright_body: int
+  upright_body_local: int
+  reward_weights: np.ndarray
+  std_standing: np.ndarray
+  std_walking: np.ndarray
+  std_running: np.ndarray
+  std_standing_map: dict
+  std_walking_map: dict
+  std_running_map: dict
+  noise_lo: np.ndarray
+  noise_hi: np.ndarray
+  n_obs_policy: int
+  n_obs_critic: int
+  step_dt: float = 0.02
+  decimation: int = 4
+  max_episode_length: int = 1000
+  max_episode_length_s: float = 20.0
+  limit_angle: float = math.radians(70.0)
+  # reward parameters (velocity_env_cfg.py:183-278)
+  std_lin: float = math.sqrt(0.25)
+  std_ang: float = math.sqrt(0.5)
+  std_upright: float = math.sqrt(0.2)
+  walking_threshold: float = 0.05
+  running_threshold: float = 1.5
+  air_thr_min: float = 0.05
+  air_thr_max: float = 0.5
+  air_cmd_threshold: float = 0.5
+  target_height: float = 0.1
+  cmd_threshold: float = 0.05
+  # command (velocity_env_cfg.py:121-139)
+  cmd_resample: tuple = (3.0, 8.0)
+  cmd_lin_x: tuple = (-1.0, 1.0)
+  cmd_lin_y: tuple = (-1.0, 1.0)
+  cmd_ang_z: tuple = (-0.5, 0.5)
+  cmd_heading: tuple = (-math.pi, math.pi)
+  rel_standing: float = 0.1
+  rel_heading: float = 0.3
+  heading_stiffness: float = 0.5
+  # events (velocity_env_cfg.py:145-181)
+  reset_x: tuple = (-0.5, 0.5)
+  reset_y: tuple = (-0.5, 0.5)
+  reset_yaw: tuple = (-3.14, 3.14)
+  reset_joint_pos: tuple = (0.0, 0.0)
+  reset_joint_vel: tuple = (0.0, 0.0)
+  push_interval: tuple = (1.0, 3.0)
+  push_x: tuple = (-0.5, 0.5)
+  push_y: tuple = (-0.5, 0.5)
+  enable_corruption: bool = True
+  push_enabled: bool = True
+  extra: dict = field(default_factory=dict)
+
+
+def _resolve_values(mapping: dict, names: list[str]) -> np.ndarray:
+  """resolve_matching_names_values (utils/lab_api/string.py:274-340): each name takes the value of the key it fullmatches."""
+  out = []
+  for n in names:
+    hit = [v for k, v in mapping.items() if re.fullmatch(k, n)]
+    if len(hit) != 1:
+      raise ValueError(f"'{n}' matches {len(hit)} keys of {list(mapping)}")
+    out.append(hit[0])
+  return np.array(out, float)
+
+
+def velocity_cfg(m, robot: str, play: bool = False) -> VelocityCfg:
+  pre = "robot/"
+  body_ids = np.array([i for i, n in enumerate(m.body_names) if n.startswith(pre)])
+  geom_ids = np.array([i for i, n in enumerate(m.geom_names) if n.startswith(pre)])
+  site_ids = np.array([i for i, n in enumerate(m.site_names) if n.startswith(pre)])
+  joint_ids = np.array([j for j in range(m.njnt) if m.jnt_type[j] != 0 and m.jnt_names[j].startswith(pre)])
+  joint_names = [m.jnt_names[j] for j in joint_ids]
+  local_names = [n.removeprefix(pre) for n in joint_names]
+  nj = len(joint_ids)
+  joint_q_adr = m.jnt_qposadr[joint_ids]
+  joint_v_adr = m.jnt_dofadr[joint_ids]
+  act_of_joint = {int(m.actuator_trnid[a, 0]): a for a in range(m.nu)}
+  ctrl_ids = np.array([act_of_joint[int(j)] for j in joint_ids])
+  kq = m.key_qpos[0]
+  default_root_state = np.concatenate([kq[0:7], np.zeros(6)])
+  default_joint_pos = kq[joint_q_adr]
+  lim = m.jnt_range[joint_ids]
+  mean, rng = 0.5 * (lim[:, 0] + lim[:, 1]), lim[:, 1] - lim[:, 0]
+  soft = np.stack([mean - 0.5 * rng * 0.9, mean + 0.5 * rng * 0.9], 1)
+  scale = 0.25 * m.actuator_forcerange[ctrl_ids, 1] / m.actuator_gainprm[ctrl_ids, 0]
+
+  def sadr(name):
+    return int(m.sensor_adr[m.sensor_names.index(name)])
+
+  site_local = [n.removeprefix(pre) for n in (m.site_names[i] for i in site_ids)]
+  body_local = [n.removeprefix(pre) for n in (m.body_names[i] for i in body_ids)]
+  if robot == "g1":
+    feet_sites = ("left_foot", "right_foot")
+    prims = ("left_ankle_roll_link", "right_ankle_roll_link")
+    upright = "torso_link"
+    weights = dict(track_linear_velocity=2.0, track_angular_velocity=2.0, upright=1.0, pose=1.0, body_ang_vel=-0.05,
+                   angular_momentum=-0.02, dof_pos_limits=-1.0, action_rate_l2=-0.1, air_time=0.0, foot_clearance=-2.0,
+                   foot_swing_height=-0.25, foot_slip=-0.1, soft_landing=-1e-5, self_collisions=-1.0)
+    std_stand, std_walk, std_run = {".*": 0.05}, _G1_STD_WALK, _G1_STD_RUN
+    selfcol = sadr("self_collision_pelvis_found")
+    illegal_adr, illegal_count = -1, 0
+  elif robot == "go1":
+    feet_sites = ("FR", "FL", "RR", "RL")
+    prims = tuple(f"{n}_foot_collision" for n in feet_sites)
+    upright = "trunk"
+    weights = dict(track_linear_velocity=2.0, track_angular_velocity=2.0, upright=1.0, pose=1.0, body_ang_vel=0.0,
+                   angular_momentum=0.0, dof_pos_limits=-1.0, action_rate_l2=-0.1, air_time=0.0, foot_clearance=-2.0,
+                   foot_swing_height=-0.25, foot_slip=-0.1, soft_landing=-1e-5, self_collisions=0.0)
+    std_stand = {_GO1_HT: 0.05, _GO1_C: 0.1}
+    std_walk = {_GO1_HT: 0.3, _GO1_C: 0.6}
+    std_run = {_GO1_HT: 0.3, _GO1_C: 0.6}
+    selfcol = -1
+    nf_names = [n for n in m.sensor_names if n.startswith("nonfoot_ground_touch_")]
+    illegal_adr, illegal_count = sadr(nf_names[0]), len(nf_names)
+    assert [sadr(n) for n in nf_names] == list(range(illegal_adr, illegal_adr + illegal_count))
+  else:
+    raise ValueError(robot)
+  foot_local = tuple(site_local.index(s) for s in feet_sites)
+  n_pol = 3 + 3 + 3 + nj + nj + nj + 3
+  nfeet = len(feet_sites)
+  n_cri = n_pol + nfeet + nfeet + nfeet + 3 * nfeet
+  lo = np.zeros(n_pol)
+  hi = np.zeros(n_pol)
+  for a, b, (l, h) in ((0, 3, (-0.5, 0.5)), (3, 6, (-0.2, 0.2)), (6, 9, (-0.05, 0.05)), (9, 9 + nj, (-0.01, 0.01)),
+                       (9 + nj, 9 + 2 * nj, (-1.5, 1.5))):
+    lo[a:b], hi[a:b] = l, h
+  return VelocityCfg(
+    robot=robot, nj=nj, nfeet=nfeet, root_body=int(body_ids[0]), body_ids=body_ids, geom_ids=geom_ids, site_ids=site_ids,
+    joint_ids=joint_ids, joint_names=joint_names, joint_q_adr=joint_q_adr, joint_v_adr=joint_v_adr, ctrl_ids=ctrl_ids,
+    default_root_state=default_root_state, default_joint_pos=default_joint_pos, joint_pos_limits=lim,
+    soft_joint_pos_limits=soft, action_scale=scale, foot_site_names=feet_sites, foot_site_local_ids=foot_local,
+    foot_site_ids=site_ids[list(foot_local)],
+    foot_found_adr=np.array([sadr(f"feet_ground_contact_{p}_found") for p in prims]),
+    foot_force_adr=np.array([sadr(f"feet_ground_contact_{p}_force") for p in prims]),
+    linvel_adr=sadr("robot/imu_lin_vel"), angvel_adr=sadr("robot/imu_ang_vel"), angmom_adr=sadr("robot/root_angmom"),
+    selfcol_adr=selfcol, illegal_adr=illegal_adr, illegal_count=illegal_count,
+    upright_body=int(body_ids[body_local.index(upright)]), upright_body_local=body_local.index(upright),
+    reward_weights=np.array([weights[n] for n in REWARD_NAMES]),
+    std_standing=_resolve_values(std_stand, local_names), std_walking=_resolve_values(std_walk, local_names),
+    std_running=_resolve_values(std_run, local_names), std_standing_map=std_stand, std_walking_map=std_walk,
+    std_running_map=std_run, noise_lo=lo, noise_hi=hi, n_obs_policy=n_pol, n_obs_critic=n_cri,
+    max_episode_length=int(1e9 / 0.02) if play else 1000, enable_corruption=not play, push_enabled=not play,
+  )
