@@ -3,18 +3,17 @@
   python bench.py --gpus N --steps K --warmup W            # own arm (CUDA engine)
   python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the reference algorithm's CPU restatement
 
-One "step" is one env step of the reference's hot loop
-(src/mjlab/envs/manager_based_rl_env.py:272-313): process a fresh action batch,
-then `decimation` = 4 physics steps, each preceded by the ctrl write of the
-builtin position actuators (src/mjlab/actuator/builtin_group.py:68-81).
-`config.workload` says exactly which parts of the env step are inside the timed
-region.
+One "step" is one `ManagerBasedRlEnv.step` of the reference's hot loop
+(src/mjlab/envs/manager_based_rl_env.py:272-313) over all envs of the rank: action processing,
+`decimation` = 4 physics steps with the contact air-time update, terminations, rewards, resets,
+the forward pass after resets, commands, push events and observations.  `config.workload`
+spells out what is inside the timed region.
 
 Timing: CUDA events on the launching stream around every env step, an L2 flush
 (256 MiB memset) between timed steps, >= 3 warm-up steps, barrier + synchronize
-on both sides, max over ranks.  Roofline: a second pass replays the same steps
-with the two stages launched separately (b2_stage) and CUDA events around each
-k_solve launch; see DESIGN.md for the algorithmic-bytes definition.
+on both sides, max over ranks.  Roofline: a second pass enqueues the same
+step eagerly with CUDA events around every kernel launch; see DESIGN.md for the algorithmic-bytes
+definition.
 """
 
 from __future__ import annotations
@@ -49,6 +48,8 @@ def parse():
   ap.add_argument("--num-envs", type=int, default=NUM_ENVS)
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-roofline-pass", action="store_true")
+  ap.add_argument("--forward-mode", default="reference", choices=["reference", "masked"],
+                  help="forward pass after resets: all envs when any env reset (the reference's behaviour) or only the reset envs")
   return ap.parse_args()
 
 
@@ -123,21 +124,53 @@ class Clocks:
 # CPU arm: the oracle port stepped on the host cores
 # ---------------------------------------------------------------------------------------------
 def _cpu_worker(args):
+  """The same env step on the host: oracle physics (one world at a time) + oracle env stage (batched over the worlds)."""
   name, seed, nworld, nsteps = args
+  from types import SimpleNamespace as NS
+
   import mjlab_b200
+  from mjlab_b200 import envcfg
+  from oracle import envstep as OE
   from oracle import mjstep as O
   m = mjlab_b200.load_model(name)
+  cfg = envcfg.velocity_cfg(m, name.split("_")[0])
+  cfg.seed = seed
   rng = np.random.default_rng(seed)
-  scale = action_scale(m)
-  t0 = time.perf_counter()
-  for _ in range(nworld):
-    d = O.Data(m)
+  fields = ["qpos", "qvel", "ctrl", "xpos", "xquat", "subtree_com", "cvel", "site_xpos", "sensordata", "qacc_warmstart", "qacc"]
+  ds = [O.Data(m) for _ in range(nworld)]
+  for d in ds:
     d.qpos[:] = m.key_qpos[0]
-    for _ in range(nsteps):
-      act = rng.uniform(-1, 1, m.nu)
-      d.ctrl[:] = m.key_ctrl[0] + scale * act
-      for _ in range(DECIMATION):
+    O.forward(m, d, 35, 300)
+
+  def batch():
+    b = NS(**{f: np.stack([np.asarray(getattr(x, f), np.float64) for x in ds]) for f in fields})
+    b.time = np.array([x.time for x in ds])
+    return b
+
+  def scatter(b):
+    for w, x in enumerate(ds):
+      x.qpos[:], x.qvel[:], x.ctrl[:], x.qacc_warmstart[:] = b.qpos[w], b.qvel[w], b.ctrl[w], b.qacc_warmstart[w]
+      x.time = float(b.time[w])
+
+  s = OE.make_state(cfg, nworld)
+  t0 = time.perf_counter()
+  for _ in range(nsteps):
+    b = batch()
+    OE.apply_action(cfg, s, b, rng.uniform(-1, 1, (nworld, cfg.nj)))
+    scatter(b)
+    for _ in range(DECIMATION):
+      for d in ds:
         O.step(m, d, nconmax=35, njmax=300)
+      b = batch()
+      OE.update_air_time(cfg, s, b.sensordata.astype(np.float32), b.time)
+    OE.post(cfg, m, s, b)
+    scatter(b)
+    if s.reset_buf.any():
+      for d in ds:
+        O.forward(m, d, 35, 300)
+      b = batch()
+    OE.obs_stage(cfg, m, s, b)
+    scatter(b)
   return time.perf_counter() - t0
 
 
@@ -172,7 +205,7 @@ def run_reference(args):
     "impl": "reference", "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
     "steps": k, "warmup": w, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
     "dtype": "f64", "data": "synthetic",
-    "config": {"workload": workload_name(args.model, args.num_envs), "num_envs_per_gpu": args.num_envs,
+    "config": {"workload": workload_name(args.model, args.num_envs, args.forward_mode), "num_envs_per_gpu": args.num_envs,
                "decimation": DECIMATION, "timestep": 0.005},
     "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
                      "sample": f"{cores} worlds x {nsteps_sample} env steps (x{DECIMATION} physics steps), one world per "
@@ -183,23 +216,23 @@ def run_reference(args):
   print(json.dumps(line))
 
 
-def workload_name(model: str, num_envs: int) -> str:
-  return (f"{model} velocity env step, {num_envs} envs/GPU: action->ctrl (builtin position actuators) + "
-          f"{DECIMATION} physics steps (FK, CRB, collision, Newton solve, sensors, implicitfast) + staggered resets; "
-          "observation/reward/termination managers NOT yet inside the step (round 1)")
+def workload_name(model: str, num_envs: int, forward_mode: str = "reference") -> str:
+  return (f"{model} velocity task, ManagerBasedRlEnv.step, {num_envs} envs/GPU: action -> ctrl, {DECIMATION} x (physics step + "
+          "contact air-time update), terminations, 14 reward terms, resets (sim + events + managers), "
+          f"forward after resets ({forward_mode}), commands, push events, observations (policy+critic, noise) - one CUDA graph")
 
 
 # ---------------------------------------------------------------------------------------------
 # own arm
 # ---------------------------------------------------------------------------------------------
 def run_b200(args):
+  import ctypes as C
+
   import torch
   import torch.distributed as dist
 
-  import mjlab_b200
   from mjlab_b200 import engine as E
-  from mjlab_b200.sim import MujocoCfg, Simulation, SimulationCfg
-  import ctypes as C
+  from mjlab_b200.env import ManagerBasedRlEnv, VelocityEnvCfg
 
   world = int(os.environ.get("WORLD_SIZE", "1"))
   rank = int(os.environ.get("RANK", "0"))
@@ -209,48 +242,26 @@ def run_b200(args):
   if world > 1:
     dist.init_process_group("nccl", device_id=torch.device(dev))
 
-  m = mjlab_b200.load_model(args.model)
   nw = args.num_envs
-  cfg = SimulationCfg(nconmax=35, njmax=300, mujoco=MujocoCfg(timestep=0.005, iterations=10, ls_iterations=20))
-  sim = Simulation(nw, cfg, m, dev)
-  torch.manual_seed(42 + rank)  # seed + rank (src/mjlab/scripts/train.py:59)
+  robot = args.model.split("_")[0]
+  # one independent world batch per rank, seed + rank (src/mjlab/scripts/train.py:59)
+  env = ManagerBasedRlEnv(VelocityEnvCfg(robot=robot, num_envs=nw, seed=42 + rank, forward_mode=args.forward_mode), dev)
+  m, cfg = env.sim.mj_model, env.vcfg
+  sim = env.sim
+  nj = cfg.nj
+  gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+  env.reset()
+  # rsl_rl's init_at_random_ep_len (src/mjlab/scripts/train.py:167-169): staggered time-outs from the first step on
+  env.episode_length_buf = torch.randint(0, cfg.max_episode_length, (nw,), device=dev, generator=gen)
 
-  f32 = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float32, device=dev)
-  key_qpos, key_ctrl, scale = f32(m.key_qpos[0]), f32(m.key_ctrl[0]), f32(action_scale(m))
-  phase = torch.arange(nw, device=dev) % EPISODE_STEPS
-  counter = torch.zeros((), dtype=torch.long, device=dev)
-  host_actions = torch.empty((nw, m.nu), dtype=torch.float32).pin_memory()
-  dev_actions = torch.empty((nw, m.nu), dtype=torch.float32, device=dev)
-  host_result = torch.empty((nw, m.nq + m.nv), dtype=torch.float32).pin_memory()
-  dev_result = torch.empty((nw, m.nq + m.nv), dtype=torch.float32, device=dev)
-
-  def reset_all():
-    sim.reset()
-    sim.data.qpos[:] = key_qpos
-    sim.data.qpos[:, 0:2] += torch.rand((nw, 2), device=dev) - 0.5
-    sim.data.ctrl[:] = key_ctrl
-    counter.zero_()
-
-  def staggered_reset():
-    mask = (phase + counter) % EPISODE_STEPS == 0
-    sim._reset_mask.copy_(mask)
-    sim.reset_graph.replay()
-    sim.data.qpos[:] = torch.where(mask[:, None], key_qpos, sim.data.qpos)
-    sim.data.ctrl[:] = torch.where(mask[:, None], key_ctrl, sim.data.ctrl)
-    counter.add_(1)
-
-  def env_step(actions, split=None):
-    """actions: device tensor [nw, nu] in [-1, 1]."""
-    target = key_ctrl + scale * actions          # JointAction.process_actions (joint_actions.py:84-86)
-    for _ in range(DECIMATION):
-      sim.data.ctrl[:] = target                   # apply_action + write_data_to_sim
-      if split is None:
-        sim.step()
-      else:
-        split()
-    staggered_reset()
-
+  nout = cfg.n_obs_policy + cfg.n_obs_critic + 3
+  host_actions = torch.empty((nw, nj), dtype=torch.float32).pin_memory()
+  host_result = torch.empty((nw, nout), dtype=torch.float32).pin_memory()
+  dev_result = torch.empty((nw, nout), dtype=torch.float32, device=dev)
   flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+  def rand_actions(k):
+    return torch.rand((k, nw, nj), device=dev, generator=gen) * 2 - 1
 
   def barrier():
     torch.cuda.synchronize()
@@ -258,87 +269,105 @@ def run_b200(args):
       dist.barrier()
     torch.cuda.synchronize()
 
-  reset_all()
-  for _ in range(max(args.warmup, 3)):
-    env_step(torch.rand((nw, m.nu), device=dev) * 2 - 1)
+  warm = max(args.warmup, 3)
+  wa = rand_actions(warm)
+  for k in range(warm):
+    env.step(wa[k])
   barrier()
 
   # ---- timed region: device-resident inputs ----------------------------------------------------
   clocks = Clocks(local)
   clocks.start()
   ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-  acts = torch.rand((args.steps, nw, m.nu), device=dev) * 2 - 1
+  acts = rand_actions(args.steps)
+  resets = torch.zeros((), dtype=torch.float32, device=dev)
   barrier()
   t_wall0 = time.perf_counter()
   for k in range(args.steps):
     flush.zero_()
     ev[k][0].record()
-    env_step(acts[k])
+    env.step(acts[k])
     ev[k][1].record()
+    resets += env._buf["any_reset"][0]
   barrier()
   t_wall = time.perf_counter() - t_wall0
   elapsed_ms = sum(a.elapsed_time(b) for a, b in ev)
+  mean_resets = resets.item() / args.steps
 
-  # ---- e2e: host buffers in, host result out, copies inside the timed region --------------------
+  # ---- e2e: host actions in, host observations / reward / dones out, copies inside the timed region --------
   ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-  host_all = (torch.rand((args.steps, nw, m.nu)) * 2 - 1)
+  host_all = torch.rand((args.steps, nw, nj)) * 2 - 1
   barrier()
   for k in range(args.steps):
     host_actions.copy_(host_all[k])
     flush.zero_()
     ev2[k][0].record()
-    dev_actions.copy_(host_actions, non_blocking=True)
-    env_step(dev_actions)
-    dev_result[:, : m.nq] = sim.data.qpos
-    dev_result[:, m.nq:] = sim.data.qvel
+    obs, rew, term, trunc, _ = env.step(host_actions)      # the H2D copy of the action batch is inside step()
+    dev_result[:, : cfg.n_obs_policy] = obs["policy"]
+    dev_result[:, cfg.n_obs_policy: cfg.n_obs_policy + cfg.n_obs_critic] = obs["critic"]
+    dev_result[:, -3] = rew
+    dev_result[:, -2] = term
+    dev_result[:, -1] = trunc
     host_result.copy_(dev_result, non_blocking=True)
     ev2[k][1].record()
-    ev2[k][1].synchronize()  # the caller consumes the result before issuing the next action
+    ev2[k][1].synchronize()  # the policy consumes the observations before it can produce the next action
   barrier()
   e2e_ms = sum(a.elapsed_time(b) for a, b in ev2)
   clk = clocks.stop()
 
-  # ---- roofline pass: stage-split launches, CUDA events around each k_solve ----------------------
+  # ---- roofline pass: the same step enqueued eagerly with CUDA events around every kernel -------------
   roof = None
-  solve_ms = smooth_ms = None
   if not args.no_roofline_pass:
-    lib, cm, cd = sim._lib, sim._cm, sim._cd
-    pairs: list = []
+    from mjlab_b200 import envabi as A
+    lib = env._lib
+    pm, pd, pe = C.byref(sim._cm), C.byref(sim._cd), C.byref(env._ce)
+    times: dict[str, list] = {}
 
-    def split():
-      st = torch.cuda.current_stream().cuda_stream
-      a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    def timed(name, fn):
+      a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
       a.record()
-      E.check_call(lib, lib.b2_stage(C.byref(cm), C.byref(cd), 0, 1, st))
+      E.check_call(lib, fn(torch.cuda.current_stream().cuda_stream))
       b.record()
-      E.check_call(lib, lib.b2_stage(C.byref(cm), C.byref(cd), 1, 1, st))
-      c.record()
-      pairs.append((a, b, c))
+      times.setdefault(name, []).append((a, b))
 
+    mask = env._buf["reset_buf"].data_ptr() if args.forward_mode == "masked" else None
+    gate = env._buf["any_reset"].data_ptr()
     nroof = min(args.steps, 25)
     barrier()
     for k in range(nroof):
       flush.zero_()
-      env_step(acts[k], split=split)
+      env._buf["action_in"].copy_(acts[k])
+      timed("k_env_action", lambda st: lib.b2_env_action(pm, pd, pe, st))
+      for _ in range(DECIMATION):
+        timed("k_smooth", lambda st: lib.b2_stage(pm, pd, 0, 1, st))
+        timed("k_solve", lambda st: lib.b2_stage(pm, pd, 1, 1, st))
+        timed("k_env_airtime", lambda st: lib.b2_env_airtime(pm, pd, pe, st))
+      timed("k_env_post", lambda st: lib.b2_env_post(pm, pd, pe, st))
+      timed("forward_after_reset", lambda st: lib.b2_forward_masked(pm, pd, mask, gate, st))
+      timed("k_env_obs", lambda st: lib.b2_env_obs(pm, pd, pe, 1, st))
+      timed("k_env_log", lambda st: lib.b2_env_log(pd, pe, st))
     barrier()
-    smooth_ms = statistics.mean(a.elapsed_time(b) for a, b, c in pairs)
-    solve_ms = statistics.mean(b.elapsed_time(c) for a, b, c in pairs)
+    avg = {k: statistics.mean(a.elapsed_time(b) for a, b in v) for k, v in times.items()}
+    per_step = {k: avg[k] * len(v) / nroof for k, v in times.items()}
     b_smooth, b_solve = algorithmic_bytes(m)
+    b_env = DECIMATION * (b_smooth + b_solve) + 4 * (cfg.n_obs_policy + cfg.n_obs_critic + nj + 3)
     peaks = {}
     try:
       peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
     except Exception:
       pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    dom_bytes, dom_ms, dom = (b_solve, solve_ms, "k_solve") if solve_ms >= smooth_ms else (b_smooth, smooth_ms, "k_smooth")
-    achieved = dom_bytes * nw / (dom_ms * 1e-3) / 1e9
+    dom = "k_solve" if avg["k_solve"] >= avg["k_smooth"] else "k_smooth"
+    dom_bytes = b_solve if dom == "k_solve" else b_smooth
+    achieved = dom_bytes * nw / (avg[dom] * 1e-3) / 1e9
+    step_ms = elapsed_ms / args.steps
     roof = {
       "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-      "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
-      "algorithmic_bytes_per_world": {"k_smooth": b_smooth, "k_solve": b_solve},
-      "avg_launch_ms": {"k_smooth": smooth_ms, "k_solve": solve_ms},
-      "whole_step": {"bytes_per_world": b_smooth + b_solve,
-                     "achieved": (b_smooth + b_solve) * nw / ((smooth_ms + solve_ms) * 1e-3) / 1e9},
+      "traffic": None, "peak_source": "measured burst (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback (B200_PROFILING.md)",
+      "algorithmic_bytes_per_world": {"k_smooth": b_smooth, "k_solve": b_solve, "env_step": b_env},
+      "avg_launch_ms": avg, "ms_per_env_step_by_kernel": per_step,
+      "whole_step": {"bytes_per_env_step": b_env, "achieved": b_env * nw / (step_ms * 1e-3) / 1e9,
+                     "frac": b_env * nw / (step_ms * 1e-3) / 1e9 / peak},
     }
 
   # solver statistics of the final state (explains the latency-bound kernel)
@@ -358,15 +387,15 @@ def run_b200(args):
   if rank == 0:
     line = {
       "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
-      "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+      "warmup": warm, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
       "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-      "config": {"workload": workload_name(args.model, nw), "num_envs_per_gpu": nw, "decimation": DECIMATION,
+      "config": {"workload": workload_name(args.model, nw, args.forward_mode), "num_envs_per_gpu": nw, "decimation": DECIMATION,
                  "timestep": 0.005, "nconmax": 35, "njmax": 300, "parallelism": f"replicas x{world} (no physics collective)",
-                 "l2": "256 MiB flush between timed steps", "actions": "U(-1,1) redrawn every env step",
+                 "l2": "256 MiB flush between timed steps", "actions": "U(-1,1) redrawn every env step (random policy)",
+                 "forward_mode": args.forward_mode, "mean_resets_per_step": mean_resets,
                  "mean_solver_niter": niter, "mean_nefc": nefc, "mean_ncon": ncon},
-      "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": nw * m.nu * 4,
-              "d2h_bytes_per_step": nw * (m.nq + m.nv) * 4},
-      "gpu_launches": args.steps * (DECIMATION * 2 + 1),
+      "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": nw * nj * 4, "d2h_bytes_per_step": nw * nout * 4},
+      "gpu_launches": args.steps * env.launches_per_step,
       "clocks": clk,
       "wall_s": t_wall,
     }
@@ -375,8 +404,8 @@ def run_b200(args):
     if world == 1 and not args.no_cpu_baseline:
       v, secs = cpu_env_steps_per_s(args.model, 1, 4, 2)
       line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": 1, "kind": "port",
-                              "sample": f"4 worlds x 2 env steps (x{DECIMATION} physics steps) of the same workload, "
-                                        f"numpy float64 oracle/mjstep.py, {secs:.1f} s"}
+                              "sample": f"4 worlds x 2 env steps (x{DECIMATION} physics steps + env stage) of the same workload, "
+                                        f"numpy oracle (oracle/mjstep.py float64 + oracle/envstep.py), {secs:.1f} s"}
     print(json.dumps(line))
   if world > 1:
     dist.destroy_process_group()

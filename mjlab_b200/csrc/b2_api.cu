@@ -11,9 +11,11 @@
 
 #include "b2_smooth.cuh"
 #include "b2_solve.cuh"
+#include "b2_env.cuh"
 
 static_assert(sizeof(KModel) == sizeof(b2_model), "KModel must mirror b2_model");
 static_assert(sizeof(KData) == sizeof(b2_data), "KData must mirror b2_data");
+static_assert(sizeof(KEnv) == sizeof(b2_env), "KEnv must mirror b2_env");
 
 #ifndef B2_WPB
 #define B2_WPB 2
@@ -34,21 +36,25 @@ static int fail(const char* fmt, ...) {
   return 1;
 }
 
-__global__ void __launch_bounds__(B2_WPB * 32) k_smooth(const KModel m, const KData d, const SmoothSmem L, int ncand_max) {
+__global__ void __launch_bounds__(B2_WPB * 32) k_smooth(const KModel m, const KData d, const SmoothSmem L, int ncand_max, const unsigned char* mask, const int* gate) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   real* smem = reinterpret_cast<real*>(smem_raw);
   int warp = threadIdx.x >> 5;
   int w = blockIdx.x * B2_WPB + warp;
   if (w >= d.nworld) return;
+  if (gate && *gate == 0) return;
+  if (mask && !mask[w]) return;
   smooth_world(m, d, L, ncand_max, w, smem + (size_t)warp * L.total);
 }
 
-__global__ void __launch_bounds__(B2_WPB * 32, B2_SOLVE_MINB) k_solve(const KModel m, const KData d, const SolveSmem L, int do_integrate) {
+__global__ void __launch_bounds__(B2_WPB * 32, B2_SOLVE_MINB) k_solve(const KModel m, const KData d, const SolveSmem L, int do_integrate, const unsigned char* mask, const int* gate) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   real* smem = reinterpret_cast<real*>(smem_raw);
   int warp = threadIdx.x >> 5;
   int w = blockIdx.x * B2_WPB + warp;
   if (w >= d.nworld) return;
+  if (gate && *gate == 0) return;
+  if (mask && !mask[w]) return;
   solve_world(m, d, L, w, smem + (size_t)warp * L.total, do_integrate);
 }
 
@@ -57,29 +63,7 @@ __global__ void k_reset(const KModel m, const KData d, const unsigned char* mask
   int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (w >= d.nworld) return;
   if (mask && !mask[w]) return;
-  const int lane = threadIdx.x & 31;
-  const real* qpos0 = MF(B2_MF_QPOS0);
-  for (int i = lane; i < m.nq; i += 32) d.df[B2_DF_QPOS][(size_t)w * m.nq + i] = qpos0[i];
-  for (int i = lane; i < m.nv; i += 32) {
-    size_t o = (size_t)w * m.nv + i;
-    d.df[B2_DF_QVEL][o] = 0; d.df[B2_DF_QACC][o] = 0; d.df[B2_DF_QACC_WARMSTART][o] = 0; d.df[B2_DF_QFRC_APPLIED][o] = 0;
-  }
-  for (int i = lane; i < m.nu; i += 32) d.df[B2_DF_CTRL][(size_t)w * m.nu + i] = 0;
-  for (int i = lane; i < m.nbody * 6; i += 32) d.df[B2_DF_XFRC_APPLIED][(size_t)w * m.nbody * 6 + i] = 0;
-  for (int i = lane; i < m.nsensordata; i += 32) d.df[B2_DF_SENSORDATA][(size_t)w * m.nsensordata + i] = 0;
-  const int* mocap = MI(B2_MI_BODY_MOCAPID);
-  const real* bpos = MF(B2_MF_BODY_POS);
-  const real* bquat = MF(B2_MF_BODY_QUAT);
-  for (int b = lane; b < m.nbody; b += 32) {
-    int k = mocap[b];
-    if (k < 0) continue;
-    for (int c = 0; c < 3; ++c) d.df[B2_DF_MOCAP_POS][((size_t)w * m.nmocap + k) * 3 + c] = bpos[3 * b + c];
-    for (int c = 0; c < 4; ++c) d.df[B2_DF_MOCAP_QUAT][((size_t)w * m.nmocap + k) * 4 + c] = bquat[4 * b + c];
-  }
-  if (lane == 0) {
-    d.df[B2_DF_TIME][w] = 0;
-    d.di[B2_DI_NCON][w] = 0; d.di[B2_DI_NEFC][w] = 0; d.di[B2_DI_NL][w] = 0; d.di[B2_DI_SOLVER_NITER][w] = 0;
-  }
+  reset_world(m, d, w);
 }
 
 __global__ void k_repeat_rows(float* dst, const float* src, int row_len, long long total) {
@@ -146,15 +130,15 @@ int b2_check(const b2_model* m, const b2_data* d) {
   return 0;
 }
 
-static int run(const b2_model* m, b2_data* d, void* stream, int do_integrate) {
+static int run(const b2_model* m, b2_data* d, void* stream, int do_integrate, const unsigned char* mask = nullptr, const int* gate = nullptr) {
   Plan p;
   make_plan(m, d, &p);
   cudaStream_t st = (cudaStream_t)stream;
   const KModel& km = *reinterpret_cast<const KModel*>(m);
   const KData& kd = *reinterpret_cast<const KData*>(d);
   int grid = (d->nworld + B2_WPB - 1) / B2_WPB;
-  k_smooth<<<grid, B2_WPB * 32, p.smem_smooth, st>>>(km, kd, p.ls, B2_NCAND_MAX);
-  k_solve<<<grid, B2_WPB * 32, p.smem_solve, st>>>(km, kd, p.lv, do_integrate);
+  k_smooth<<<grid, B2_WPB * 32, p.smem_smooth, st>>>(km, kd, p.ls, B2_NCAND_MAX, mask, gate);
+  k_solve<<<grid, B2_WPB * 32, p.smem_solve, st>>>(km, kd, p.lv, do_integrate, mask, gate);
   g_launches += 2;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail("launch failed: %s", cudaGetErrorString(e));
@@ -168,8 +152,8 @@ int b2_stage(const b2_model* m, b2_data* d, int stage, int do_integrate, void* s
   const KModel& km = *reinterpret_cast<const KModel*>(m);
   const KData& kd = *reinterpret_cast<const KData*>(d);
   int grid = (d->nworld + B2_WPB - 1) / B2_WPB;
-  if (stage == 0) k_smooth<<<grid, B2_WPB * 32, p.smem_smooth, st>>>(km, kd, p.ls, B2_NCAND_MAX);
-  else if (stage == 1) k_solve<<<grid, B2_WPB * 32, p.smem_solve, st>>>(km, kd, p.lv, do_integrate);
+  if (stage == 0) k_smooth<<<grid, B2_WPB * 32, p.smem_smooth, st>>>(km, kd, p.ls, B2_NCAND_MAX, nullptr, nullptr);
+  else if (stage == 1) k_solve<<<grid, B2_WPB * 32, p.smem_solve, st>>>(km, kd, p.lv, do_integrate, nullptr, nullptr);
   else return fail("unknown stage %d", stage);
   g_launches += 1;
   cudaError_t e = cudaGetLastError();
@@ -202,4 +186,10 @@ int b2_repeat_rows(float* dst, const float* src, int row_len, int nworld, void* 
   return 0;
 }
 
+int b2_forward_masked(const b2_model* m, b2_data* d, const unsigned char* mask, const int* gate, void* stream) {
+  return run(m, d, stream, 0, mask, gate);
+}
+
 }  // extern "C"
+
+#include "b2_env_api.inl"

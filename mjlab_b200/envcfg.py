@@ -116,7 +116,27 @@ class VelocityCfg:
   push_y: tuple = (-0.5, 0.5)
   enable_corruption: bool = True
   push_enabled: bool = True
+  heading_command: bool = True
+  seed: int = 0
+  foot_site_body: np.ndarray = None  # body of each foot site (site velocities, entity/data.py:323-331)
   extra: dict = field(default_factory=dict)
+
+  @staticmethod
+  def _ranges6(d: dict) -> np.ndarray:
+    """{"x": (lo, hi), ...} -> [6, 2] in the order x y z roll pitch yaw (envs/mdp/events.py:104-107)."""
+    return np.array([d.get(k, (0.0, 0.0)) for k in ("x", "y", "z", "roll", "pitch", "yaw")], float)
+
+  @property
+  def reset_pose(self) -> np.ndarray:
+    return self._ranges6({"x": self.reset_x, "y": self.reset_y, "yaw": self.reset_yaw})
+
+  @property
+  def reset_vel(self) -> np.ndarray:
+    return self._ranges6({})
+
+  @property
+  def push_vel(self) -> np.ndarray:
+    return self._ranges6({"x": self.push_x, "y": self.push_y})
 
 
 def _resolve_values(mapping: dict, names: list[str]) -> np.ndarray:
@@ -206,5 +226,7 @@ def velocity_cfg(m, robot: str, play: bool = False) -> VelocityCfg:
     std_standing=_resolve_values(std_stand, local_names), std_walking=_resolve_values(std_walk, local_names),
     std_running=_resolve_values(std_run, local_names), std_standing_map=std_stand, std_walking_map=std_walk,
     std_running_map=std_run, noise_lo=lo, noise_hi=hi, n_obs_policy=n_pol, n_obs_critic=n_cri,
-    max_episode_length=int(1e9 / 0.02) if play else 1000, enable_corruption=not play, push_enabled=not play,
+    max_episode_length=math.ceil(int(1e9) / 0.02) if play else 1000, max_episode_length_s=float(int(1e9)) if play else 20.0,
+    enable_corruption=not play, push_enabled=not play,
+    foot_site_body=np.asarray(m.site_bodyid)[site_ids[list(foot_local)]].astype(int),
   )

@@ -1,0 +1,86 @@
+"""Event terms that run outside the fused step: model-field domain randomisation.
+
+`randomize_field` follows mjlab's unified randomiser (src/mjlab/envs/mdp/events.py:292-520): "abs" overwrites the target
+axes and keeps the others, "scale" / "add" always start from the compiled defaults (`sim.get_default_field`) so repeated
+calls do not accumulate (tests/test_domain_randomization.py:182-240).  The field must have been made per-world with
+`sim.expand_model_fields` first, as `ManagerBasedRlEnv.__init__` does for every DR field (manager_based_rl_env.py:118-129).
+Startup / reset-time work on a handful of geoms: plain torch indexing on the engine's model views, not a hot path.
+"""
+
+from __future__ import annotations
+
+import math
+
+import torch
+
+# field -> (entity kind, default axes) (events.py:264-289)
+FIELD_SPECS = {
+  "dof_armature": ("dof", None), "dof_frictionloss": ("dof", None), "dof_damping": ("dof", None),
+  "jnt_range": ("joint", None), "jnt_stiffness": ("joint", None),
+  "body_mass": ("body", None), "body_ipos": ("body", [0, 1, 2]), "body_iquat": ("body", [0, 1, 2, 3]), "body_inertia": ("body", None),
+  "body_pos": ("body", [0, 1, 2]), "body_quat": ("body", [0, 1, 2, 3]),
+  "geom_friction": ("geom", [0]), "geom_pos": ("geom", [0, 1, 2]), "geom_quat": ("geom", [0, 1, 2, 3]),
+  "site_pos": ("site", [0, 1, 2]), "site_quat": ("site", [0, 1, 2, 3]), "qpos0": ("qpos", None),
+}
+
+
+def _sample(distribution: str, lo: float, hi: float, shape, device) -> torch.Tensor:
+  if distribution == "uniform":
+    return torch.rand(shape, device=device) * (hi - lo) + lo
+  if distribution == "log_uniform":
+    return torch.exp(torch.rand(shape, device=device) * (math.log(hi) - math.log(lo)) + math.log(lo))
+  if distribution == "gaussian":
+    return torch.randn(shape, device=device) * hi + lo
+  raise ValueError(f"Unknown distribution: {distribution}")
+
+
+def randomize_field(env, env_ids, field: str, ranges, distribution: str = "uniform", operation: str = "abs", axes=None,
+                    geom_names=None, body_names=None, joint_names=None, site_names=None) -> None:
+  if field not in FIELD_SPECS:
+    raise ValueError(f"Unknown field '{field}'. Supported fields: {list(FIELD_SPECS)}")
+  kind, default_axes = FIELD_SPECS[field]
+  robot, dev = env.scene["robot"], env.device
+  ix = robot.indexing
+  if kind == "geom":
+    ids = ix.geom_ids[robot.find_geoms(geom_names)[0]] if geom_names else ix.geom_ids
+  elif kind == "body":
+    ids = ix.body_ids[robot.find_bodies(body_names)[0]] if body_names else ix.body_ids
+  elif kind == "site":
+    ids = ix.site_ids[robot.find_sites(site_names)[0]] if site_names else ix.site_ids
+  else:
+    sel = robot.find_joints(joint_names)[0] if joint_names else slice(None)
+    ids = {"dof": ix.joint_v_adr, "joint": ix.joint_ids, "qpos": ix.joint_q_adr}[kind][sel]
+  model_field = getattr(env.sim.model, field)
+  if model_field.shape[0] != env.num_envs or model_field.stride(0) == 0:
+    raise ValueError(f"'{field}' is shared by all worlds; call sim.expand_model_fields(('{field}',)) first")
+  env_ids = torch.arange(env.num_envs, device=dev) if env_ids is None else env_ids.to(dev)
+  eg, ig = torch.meshgrid(env_ids.long(), ids.long(), indexing="ij")
+  cur = model_field[eg, ig]
+  if axes is not None:
+    target = list(axes)
+  elif isinstance(ranges, dict):
+    target = list(ranges)
+  elif default_axes is not None:
+    target = default_axes
+  else:
+    target = list(range(model_field.shape[-1])) if model_field.dim() > 2 else [0]
+  rng = {a: ranges for a in target} if isinstance(ranges, tuple) else {a: ranges[a] for a in target}
+  if operation in ("scale", "add"):
+    base = env.sim.get_default_field(field)[ids.long()].unsqueeze(0).expand_as(cur)
+  else:
+    base = cur
+  rnd = torch.ones_like(cur) if operation == "scale" else torch.zeros_like(cur) if operation == "add" else cur.clone()
+  for a in target:
+    lo, hi = rng[a]
+    if cur.dim() > 2:
+      rnd[..., a] = _sample(distribution, lo, hi, cur.shape[:-1], dev)
+    else:
+      rnd = _sample(distribution, lo, hi, cur.shape, dev)
+  if operation == "add":
+    model_field[eg, ig] = base + rnd
+  elif operation == "scale":
+    model_field[eg, ig] = base * rnd
+  elif operation == "abs":
+    model_field[eg, ig] = rnd
+  else:
+    raise ValueError(f"Unknown operation: {operation}")

@@ -15,6 +15,7 @@ from pathlib import Path
 import numpy as np
 
 from mjlab_b200 import engine as E
+from mjlab_b200 import envabi as A
 
 HERE = Path(__file__).resolve().parent
 ROOT = HERE.parents[1]
@@ -91,3 +92,46 @@ class HostSim:
 
   def forward(self):
     self.lib.b2h_run(C.byref(self.cm), C.byref(self.cd), 0, 0, self.nworld)
+
+
+_NP = {"f4": None, "i4": np.int32, "i8": np.int64, "u1": np.uint8}
+
+
+class HostEnv:
+  """The env-layer device code (b2_env.cuh) host-emulated on top of a HostSim."""
+
+  def __init__(self, sim: HostSim, cfg, inject=False):
+    self.sim, self.cfg = sim, cfg
+    assert sim.lib.b2h_sizeof_env() == C.sizeof(A.B2Env)
+    self.ce = A.B2Env()
+    A.fill_params(self.ce, cfg)
+    tables = A.table_values(cfg)
+    self.bufs = {}
+    for i, (_, attr, kind, dt, shp) in enumerate(A.BUFFERS):
+      dtype = sim.dtype if dt == "f4" else _NP[dt]
+      if kind == "table":
+        a = np.ascontiguousarray(np.asarray(tables[attr]).astype(dtype))
+      elif kind == "state":
+        a = np.zeros((sim.nworld,) + tuple(shp(cfg)), dtype)
+      else:
+        a = np.zeros(tuple(shp(cfg)), dtype)
+      self.bufs[attr] = a
+      self.ce.buf[i] = a.ctypes.data
+    self.inject = None
+    if inject:
+      self.inject = np.zeros((sim.nworld, A.NDRAW), sim.dtype)
+      self.ce.buf[A.K["B2E_B_INJECT_U"]] = self.inject.ctypes.data
+
+  def __getattr__(self, name):
+    try:
+      return self.__dict__["bufs"][name]
+    except KeyError:
+      raise AttributeError(name) from None
+
+  def stage(self, k: int) -> None:
+    rc = self.sim.lib.b2h_env_stage(C.byref(self.sim.cm), C.byref(self.sim.cd), C.byref(self.ce), k)
+    assert rc == 0
+
+  def forward_masked(self, mask=None) -> None:
+    ptr = None if mask is None else np.ascontiguousarray(mask, np.uint8).ctypes.data
+    self.sim.lib.b2h_forward_masked(C.byref(self.sim.cm), C.byref(self.sim.cd), C.c_void_p(ptr))

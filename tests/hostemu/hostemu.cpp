@@ -12,6 +12,7 @@
 
 #include "../../mjlab_b200/csrc/b2_smooth.cuh"
 #include "../../mjlab_b200/csrc/b2_solve.cuh"
+#include "../../mjlab_b200/csrc/b2_env.cuh"
 
 extern "C" {
 
@@ -45,4 +46,37 @@ int b2h_smooth(const KModel* m, KData* d) {
   for (int w = 0; w < d->nworld; ++w) smooth_world(*m, *d, ls, 256, w, a.data());
   return 0;
 }
+
+// ---- env layer (b2_env.cuh), one call per stage over all envs ----
+int b2h_sizeof_env(void) { return (int)sizeof(KEnv); }
+int b2h_env_stage(const KModel* m, KData* d, const KEnv* e, int stage) {
+  for (int w = 0; w < d->nworld; ++w) {
+    switch (stage) {
+      case 0: env_action_world(*m, *d, *e, w); break;
+      case 1: env_airtime_world(*m, *d, *e, w); break;
+      case 2: env_post_world(*m, *d, *e, w); break;
+      case 3: env_obs_world(*m, *d, *e, w, 1); break;
+      default: return 1;
+    }
+  }
+  if (stage == 2 || stage == 3) {  // k_env_log
+    real* log_env = reinterpret_cast<real*>(e->buf[B2E_B_LOG_ENV]);
+    real* log = reinterpret_cast<real*>(e->buf[B2E_B_LOG]);
+    for (int c = 0; c < B2E_NLOG; ++c) {
+      real acc = 0;
+      for (int w = 0; w < d->nworld; ++w) acc += log_env[(size_t)w * B2E_NLOG + c];
+      if (stage == 3 || c == B2E_LOG_NRESET) log[c] = acc;
+    }
+    if (stage == 2) reinterpret_cast<int*>(e->buf[B2E_B_ANY_RESET])[0] = (int)log[B2E_LOG_NRESET];
+    if (stage == 3) reinterpret_cast<long long*>(e->buf[B2E_B_STEP_COUNTER])[0] += 1;
+  }
+  return 0;
+}
+// masked forward: worlds with mask[w] == 0 are skipped
+int b2h_forward_masked(const KModel* m, KData* d, const unsigned char* mask) {
+  for (int w = 0; w < d->nworld; ++w)
+    if (!mask || mask[w]) b2h_run(m, d, 0, w, w + 1);
+  return 0;
+}
+float b2h_dc_clip(float effort, float vel, float limit, float sat, float vlim) { return b2_dc_clip(effort, vel, limit, sat, vlim); }
 }

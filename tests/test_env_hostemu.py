@@ -1,0 +1,135 @@
+"""The env-layer device code (mjlab_b200/csrc/b2_env.cuh, compiled single-lane for the host) against
+(a) golden vectors from the reference's own functions and (b) the env oracle including resets, command
+resampling, pushes and observation noise with the in-kernel Philox draws."""
+import numpy as np
+import pytest
+
+import mjlab_b200
+from mjlab_b200 import envabi as A
+from mjlab_b200 import envcfg
+from oracle import envstep as OE
+from tests.envutil import FIELDS, init_state_from_golden, load_golden, snapshot
+from tests.hostemu.harness import HostEnv, HostSim
+
+TOL = dict(rtol=3e-5, atol=3e-6)
+STATE = ["action", "prev_action", "prev_prev_action", "raw_action", "joint_pos_target", "command", "heading_target", "cmd_time_left",
+         "cmd_metrics", "cmd_counter", "is_heading", "is_standing", "air_state", "air_last_time", "peak_heights", "push_time_left",
+         "episode_length", "reward", "step_reward", "episode_sums", "term_dones", "terminated", "time_outs", "reset_buf", "obs_policy",
+         "obs_critic", "log_env"]
+
+
+def upload(sim, d):
+  for f in FIELDS + ["ctrl"]:
+    getattr(sim, f)[...] = getattr(d, f).reshape(getattr(sim, f).shape)
+
+
+def compare_state(env, s, names=STATE):
+  for n in names:
+    a, b = getattr(env, n), getattr(s, n)
+    if a.dtype.kind == "f":
+      np.testing.assert_allclose(a, b.reshape(a.shape), err_msg=n, **TOL)
+    else:
+      np.testing.assert_array_equal(a.astype(np.int64), np.asarray(b).astype(np.int64).reshape(a.shape), err_msg=n)
+
+
+@pytest.mark.parametrize("robot", ["g1", "go1"])
+def test_kernels_match_reference_golden(robot):
+  """Before an env's first reset the kernels must reproduce the reference's reward terms / observations / flags."""
+  m = mjlab_b200.load_model(f"{robot}_flat")
+  cfg = envcfg.velocity_cfg(m, robot)
+  cfg.enable_corruption = False
+  cfg.push_enabled = False
+  g = load_golden(robot)
+  T, B = g["actions"].shape[:2]
+  sim = HostSim(m, B, nconmax=35, njmax=300)
+  env = HostEnv(sim, cfg)
+  init_state_from_golden(env, g)
+  env.cmd_time_left[:] = 1e6
+  alive = np.ones(B, bool)
+  checked = 0
+  for t in range(T):
+    d = snapshot(g, t, m)
+    env.action_in[:] = g["actions"][t]
+    env.stage(0)
+    for k in range(4):
+      sim.sensordata[:] = g["sub_sensordata"][t, k]
+      sim.time[:] = g["sub_time"][t, k].reshape(sim.time.shape)
+      env.stage(1)
+    np.testing.assert_allclose(env.air_state.transpose(1, 0, 2)[:, alive], g["ref_air"][t][:, alive], **TOL)
+    upload(sim, d)
+    env.stage(2)
+    np.testing.assert_array_equal(env.term_dones[alive, 0], g["ref_time_out"][t][alive])
+    np.testing.assert_array_equal(env.term_dones[alive, 1], g["ref_fell_over"][t][alive])
+    np.testing.assert_array_equal(env.term_dones[alive, 2], g["ref_illegal"][t][alive])
+    w = cfg.reward_weights.astype(np.float32)
+    np.testing.assert_allclose(env.step_reward[alive], (g["ref_rew_terms"][t] * w)[alive], **TOL)
+    np.testing.assert_allclose(env.reward[alive], g["ref_reward"][t][alive], **TOL)
+    alive &= ~env.reset_buf.astype(bool)
+    np.testing.assert_allclose(env.peak_heights[alive], g["ref_peak"][t][alive], **TOL)
+    upload(sim, d)  # the reset rewrote qpos/qvel of done envs; the golden observations come from the un-reset snapshot
+    env.stage(3)
+    np.testing.assert_allclose(env.command[alive], g["ref_cmd_after"][t][alive], rtol=3e-5, atol=5e-6)
+    np.testing.assert_allclose(env.heading_error[alive], g["ref_heading_error"][t][alive], rtol=3e-5, atol=5e-6)
+    np.testing.assert_allclose(env.obs_policy[alive], g["ref_obs_policy"][t][alive], **TOL)
+    np.testing.assert_allclose(env.obs_critic[alive], g["ref_obs_critic"][t][alive], **TOL)
+    checked += int(alive.sum())
+  assert checked > B * T // 2
+
+
+@pytest.mark.parametrize("robot,inject", [("g1", False), ("go1", False), ("g1", True)])
+def test_kernels_match_oracle_with_resets(robot, inject):
+  """Full stage sequence incl. resets / resampling / push / noise: kernel state == oracle state after every stage."""
+  m = mjlab_b200.load_model(f"{robot}_flat")
+  cfg = envcfg.velocity_cfg(m, robot)
+  cfg.seed = 0x1234_5678_9ABC
+  cfg.max_episode_length = 6       # several time-outs inside the fixture
+  cfg.cmd_resample = (0.03, 0.09)  # timed resamples every 2-5 env steps
+  cfg.push_interval = (0.03, 0.07)
+  cfg.reset_joint_pos = (-0.1, 0.1)
+  cfg.reset_joint_vel = (-0.2, 0.2)
+  g = load_golden(robot)
+  T, B = g["actions"].shape[:2]
+  origins = np.random.default_rng(3).uniform(-4, 4, (B, 3)).astype(np.float32)
+  sim = HostSim(m, B, nconmax=35, njmax=300)
+  env = HostEnv(sim, cfg, inject=inject)
+  s = OE.make_state(cfg, B, origins)
+  env.env_origins[:] = origins
+  init_state_from_golden(env, g)
+  init_state_from_golden(s, g)
+  s.episode_length[:] = env.episode_length[:] = np.arange(B) % 5
+  rng = np.random.default_rng(11)
+  enc = rng.uniform(-0.02, 0.02, (B, cfg.nj)).astype(np.float32)
+  env.encoder_bias[:] = enc
+  s.encoder_bias[:] = enc
+  nreset = npush = 0
+  for t in range(T):
+    d = snapshot(g, t, m)
+    u = rng.uniform(0, 1, (B, A.NDRAW)).astype(np.float32) if inject else OE.draws(cfg.seed, B, t)
+    if inject:
+      env.inject[:] = u
+    env.action_in[:] = g["actions"][t]
+    env.stage(0)
+    OE.apply_action(cfg, s, d, g["actions"][t])
+    np.testing.assert_allclose(sim.ctrl, d.ctrl, **TOL)
+    for k in range(4):
+      sim.sensordata[:] = g["sub_sensordata"][t, k]
+      sim.time[:] = g["sub_time"][t, k].reshape(sim.time.shape)
+      env.stage(1)
+      OE.update_air_time(cfg, s, g["sub_sensordata"][t, k].astype(np.float32), g["sub_time"][t, k])
+    upload(sim, d)
+    env.stage(2)
+    OE.post(cfg, m, s, d, u=u)
+    compare_state(env, s, [n for n in STATE if n not in ("obs_policy", "obs_critic")])
+    for f in ("qpos", "qvel", "ctrl", "time"):
+      np.testing.assert_allclose(getattr(sim, f).reshape(getattr(d, f).shape), getattr(d, f), err_msg=f, **TOL)
+    assert env.any_reset[0] == int(s.reset_buf.sum())
+    nreset += int(s.reset_buf.sum())
+    before = d.qvel.copy()
+    env.stage(3)
+    OE.obs_stage(cfg, m, s, d, u=u)
+    npush += int(np.any(before != d.qvel, axis=1).sum())
+    compare_state(env, s)
+    np.testing.assert_allclose(sim.qvel, d.qvel, **TOL)
+    np.testing.assert_allclose(env.log, s.log, rtol=1e-4, atol=1e-5)
+    assert int(env.step_counter[0]) == s.step_counter == t + 1
+  assert nreset >= B and npush > 0
