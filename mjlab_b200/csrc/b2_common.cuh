@@ -28,7 +28,7 @@ typedef B2_REAL real;
 #define B2_LANE 0
 #define B2_NLANE 1
 #define B2_WSYNC() ((void)0)
-B2_DEV real b2_wsum(real x) { return x; }
+B2_DEV real b2_wsum(real x) { return x; }  // @region shuffle_reduce
 B2_DEV real b2_wmax(real x) { return x; }
 B2_DEV int b2_wsum_i(int x) { return x; }
 B2_DEV unsigned b2_ballot(bool p) { return p ? 1u : 0u; }
@@ -116,7 +116,7 @@ struct KData {
 // ---------------------------------------------------------------------------
 // small vector / quaternion math (row-major 3x3)
 // ---------------------------------------------------------------------------
-B2_DEV real dot3(const real* a, const real* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+B2_DEV real dot3(const real* a, const real* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }  // @region vecmath
 B2_DEV void cross3(real* r, const real* a, const real* b) {
   real x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
   r[0] = x; r[1] = y; r[2] = z;
@@ -208,12 +208,13 @@ B2_DEV real b2_shfl(real x, int src) { return __shfl_sync(0xffffffffu, x, src); 
 #endif
 
 // In-place lower Cholesky of A (lower triangle valid, upper ignored). invd[j] <- 1 / L[j][j].
-B2_DEVN void chol_factor(real* A, int n, int ld, real* invd, real* prow) {
+B2_DEVN void chol_factor(real* A, int n, int ld, real* invd, real* prow) {  // @region chol_factor
   B2_UNROLL1
   for (int j = 0; j < n; ++j) {
     B2_WSYNC();
     // pivot row, zero-padded to a multiple of 4 so the k loop needs no scalar tail
     const real* rj = A + j * ld;
+    B2_UNROLL1
     for (int k = B2_LANE; k < ld; k += B2_NLANE) prow[k] = k < j ? rj[k] : (real)0;
     B2_WSYNC();
     const int j4 = (j + 3) & ~3;
@@ -236,6 +237,7 @@ B2_DEVN void chol_factor(real* A, int n, int ld, real* invd, real* prow) {
         }
         s += s2;
 #else
+        B2_UNROLL1
         for (int k = 0; k < j4; ++k) s -= ri[k] * prow[k];
 #endif
       }
@@ -251,16 +253,20 @@ B2_DEVN void chol_factor(real* A, int n, int ld, real* invd, real* prow) {
 }
 
 // x <- (L L^T)^-1 x, x in shared memory.
-B2_DEVN void chol_solve(const real* L, int n, int ld, const real* invd, real* x) {
+B2_DEVN void chol_solve(const real* L, int n, int ld, const real* invd, real* x) {  // @region chol_solve
 #ifdef B2_HOSTEMU
+  B2_UNROLL1
   for (int k = 0; k < n; ++k) {
     real xk = x[k] * invd[k];
     x[k] = xk;
+    B2_UNROLL1
     for (int i = k + 1; i < n; ++i) x[i] -= L[i * ld + k] * xk;
   }
+  B2_UNROLL1
   for (int k = n - 1; k >= 0; --k) {
     real xk = x[k] * invd[k];
     x[k] = xk;
+    B2_UNROLL1
     for (int i = 0; i < k; ++i) x[i] -= L[k * ld + i] * xk;
   }
 #else
@@ -293,7 +299,7 @@ B2_DEVN void chol_solve(const real* L, int n, int ld, const real* invd, real* x)
 
 // y = M x for a symmetric M [n][ld] in global memory: lane i walks column i (== row i), so every
 // load of the warp is one coalesced segment.
-B2_DEVN void symv_global(const real* M, int n, int ld, const real* x, real* y) {
+B2_DEVN void symv_global(const real* M, int n, int ld, const real* x, real* y) {  // @region symv_global
   B2_UNROLL1
   for (int i = B2_LANE; i < n; i += B2_NLANE) {
     real a0 = 0, a1 = 0, a2 = 0, a3 = 0;
@@ -303,6 +309,7 @@ B2_DEVN void symv_global(const real* M, int n, int ld, const real* x, real* y) {
       real m0 = M[e * ld + i], m1 = M[(e + 1) * ld + i], m2 = M[(e + 2) * ld + i], m3 = M[(e + 3) * ld + i];
       a0 += m0 * x[e]; a1 += m1 * x[e + 1]; a2 += m2 * x[e + 2]; a3 += m3 * x[e + 3];
     }
+    B2_UNROLL1
     for (; e < n; ++e) a0 += M[e * ld + i] * x[e];
     y[i] = (a0 + a1) + (a2 + a3);
   }
@@ -311,8 +318,9 @@ B2_DEVN void symv_global(const real* M, int n, int ld, const real* x, real* y) {
 
 // dst[0..count) = src[0..count) (global -> shared), count % 4 == 0, both 16-byte aligned:
 // 128-bit loads, four in flight per lane so the L2 latency is paid once per batch.
-B2_DEVN void copy_g2s(real* dst, const real* src, int count) {
+B2_DEVN void copy_g2s(real* dst, const real* src, int count) {  // @region copy_g2s
 #ifdef B2_HOSTEMU
+  B2_UNROLL1
   for (int i = 0; i < count; ++i) dst[i] = src[i];
 #else
   const float4* s4 = reinterpret_cast<const float4*>(src);
@@ -324,6 +332,7 @@ B2_DEVN void copy_g2s(real* dst, const real* src, int count) {
     float4 v0 = s4[i], v1 = s4[i + 32], v2 = s4[i + 64], v3 = s4[i + 96];
     d4[i] = v0; d4[i + 32] = v1; d4[i + 64] = v2; d4[i + 96] = v3;
   }
+  B2_UNROLL1
   for (; i < n4; i += 32) d4[i] = s4[i];
 #endif
   B2_WSYNC();

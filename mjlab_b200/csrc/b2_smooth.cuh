@@ -145,6 +145,7 @@ B2_DEV void narrowphase(LaneContacts& lc, int t1, int t2, const real* p1, const 
       real q2[3] = {p2[0] + a2[0] * x2, p2[1] + a2[1] * x2, p2[2] + a2[2] * x2};
       sphere_sphere(lc, q1, s1[0], q2, s2[0], margin);
     } else {
+      B2_UNROLL1
       for (int e = 0; e < 2 && lc.n < 2; ++e) {
         real sg = e == 0 ? (real)1 : (real)-1;
         real v1[3] = {p1[0] + a1[0] * l1 * sg, p1[1] + a1[1] * l1 * sg, p1[2] + a1[2] * l1 * sg};
@@ -153,6 +154,7 @@ B2_DEV void narrowphase(LaneContacts& lc, int t1, int t2, const real* p1, const 
         real q2[3] = {p2[0] + a2[0] * x2, p2[1] + a2[1] * x2, p2[2] + a2[2] * x2};
         sphere_sphere(lc, v1, s1[0], q2, s2[0], margin);
       }
+      B2_UNROLL1
       for (int e = 0; e < 2 && lc.n < 2; ++e) {
         real sg = e == 0 ? (real)1 : (real)-1;
         real v2[3] = {p2[0] + a2[0] * l2 * sg, p2[1] + a2[1] * l2 * sg, p2[2] + a2[2] * l2 * sg};
@@ -220,7 +222,9 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
   real* g_qpos = d.df[B2_DF_QPOS] + (size_t)w * nq;
   const real* g_qvel = d.df[B2_DF_QVEL] + (size_t)w * nv;
 
+  B2_UNROLL1
   for (int i = B2_LANE; i < nq; i += B2_NLANE) qpos[i] = g_qpos[i];
+  B2_UNROLL1
   for (int i = B2_LANE; i < nv; i += B2_NLANE) qvel[i] = g_qvel[i];
   B2_WSYNC();
 
@@ -233,7 +237,9 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
   const real* jnt_pos = MF(B2_MF_JNT_POS);
   const real* jnt_axis = MF(B2_MF_JNT_AXIS);
   real* g_ximat = d.df[B2_DF_XIMAT] + (size_t)w * nb * 9;
+  B2_UNROLL1
   for (int lev = 0; lev < m.nlevel; ++lev) {
+    B2_UNROLL1
     for (int k = level_adr[lev] + B2_LANE; k < level_adr[lev + 1]; k += B2_NLANE) {
       int b = level_body[k];
       real pos[3], quat[4], R[9];
@@ -253,6 +259,7 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
           pos[0] = xpos[3 * p] + t[0]; pos[1] = xpos[3 * p + 1] + t[1]; pos[2] = xpos[3 * p + 2] + t[2];
           quat_mul(quat, xquat + 4 * p, body_quat + 4 * b);
         }
+        B2_UNROLL1
         for (int jj = 0; jj < body_jntnum[b]; ++jj) {
           int j = body_jntadr[b] + jj;
           int qa = jnt_qposadr[j];
@@ -323,6 +330,7 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
     const real* geom_quat = MF(B2_MF_GEOM_QUAT);
     real* gx = d.df[B2_DF_GEOM_XPOS] + (size_t)w * m.ngeom * 3;
     real* gm = d.df[B2_DF_GEOM_XMAT] + (size_t)w * m.ngeom * 9;
+    B2_UNROLL1
     for (int g = B2_LANE; g < m.ngeom; g += B2_NLANE) {
       int b = geom_body[g];
       real t[3], q[4], R[9];
@@ -337,6 +345,7 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
     const real* site_quat = MF(B2_MF_SITE_QUAT);
     real* sx = d.df[B2_DF_SITE_XPOS] + (size_t)w * m.nsite * 3;
     real* smx = d.df[B2_DF_SITE_XMAT] + (size_t)w * m.nsite * 9;
+    B2_UNROLL1
     for (int s = B2_LANE; s < m.nsite; s += B2_NLANE) {
       int b = site_body[s];
       real t[3], q[4], R[9];
@@ -351,11 +360,14 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
   // ---- subtree com (backward gather over levels) ----------------------------
   const real* body_mass = MF(B2_MF_BODY_MASS);
   const real* body_inertia = MF(B2_MF_BODY_INERTIA);
+  B2_UNROLL1
   for (int lev = m.nlevel - 1; lev >= 0; --lev) {
+    B2_UNROLL1
     for (int k = level_adr[lev] + B2_LANE; k < level_adr[lev + 1]; k += B2_NLANE) {
       int b = level_body[k];
       real ms = body_mass[b];
       real a0 = ms * xipos[3 * b], a1 = ms * xipos[3 * b + 1], a2 = ms * xipos[3 * b + 2];
+      B2_UNROLL1
       for (int c = child_adr[b]; c < child_adr[b + 1]; ++c) {
         int ch = child_body[c];
         a0 += scom[3 * ch]; a1 += scom[3 * ch + 1]; a2 += scom[3 * ch + 2];
@@ -365,6 +377,7 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
     }
     B2_WSYNC();
   }
+  B2_UNROLL1
   for (int b = B2_LANE; b < nb; b += B2_NLANE) {
     real ms = smass[b];
     if (ms > B2_MINVAL) {
@@ -379,9 +392,11 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
   B2_WSYNC();
   {
     real* g = d.df[B2_DF_SUBTREE_COM] + (size_t)w * nb * 3;
+    B2_UNROLL1
     for (int i = B2_LANE; i < 3 * nb; i += B2_NLANE) g[i] = scom[i];
   }
   // ---- cinert, cdof -----------------------------------------------------------
+  B2_UNROLL1
   for (int b = B2_LANE; b < nb; b += B2_NLANE) {
     int r = body_root[b];
     real o[3] = {xipos[3 * b] - scom[3 * r], xipos[3 * b + 1] - scom[3 * r + 1], xipos[3 * b + 2] - scom[3 * r + 2]};
@@ -399,6 +414,7 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
     ci[6] = ms * o[0]; ci[7] = ms * o[1]; ci[8] = ms * o[2]; ci[9] = ms;
     for (int c = 0; c < 10; ++c) crb[10 * b + c] = ci[c];
   }
+  B2_UNROLL1
   for (int j = B2_LANE; j < nj; j += B2_NLANE) {
     int b = jnt_bodyid[j], da = jnt_dofadr[j], r = body_root[b];
     real off[3] = {scom[3 * r] - xanchor[3 * j], scom[3 * r + 1] - xanchor[3 * j + 1], scom[3 * r + 2] - xanchor[3 * j + 2]};
@@ -424,14 +440,19 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
   B2_WSYNC();
   {
     real* g = d.df[B2_DF_CINERT] + (size_t)w * nb * 10;
+    B2_UNROLL1
     for (int i = B2_LANE; i < 10 * nb; i += B2_NLANE) g[i] = cinert[i];
     g = d.df[B2_DF_CDOF] + (size_t)w * nv * 6;
+    B2_UNROLL1
     for (int i = B2_LANE; i < 6 * nv; i += B2_NLANE) g[i] = cdof[i];
   }
   // ---- composite rigid body inertias, dense qM --------------------------------
+  B2_UNROLL1
   for (int lev = m.nlevel - 1; lev >= 1; --lev) {
+    B2_UNROLL1
     for (int k = level_adr[lev] + B2_LANE; k < level_adr[lev + 1]; k += B2_NLANE) {
       int b = level_body[k];
+      B2_UNROLL1
       for (int c = child_adr[b]; c < child_adr[b + 1]; ++c) {
         int ch = child_body[c];
         for (int e = 0; e < 10; ++e) crb[10 * b + e] += crb[10 * ch + e];
@@ -440,14 +461,17 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
     B2_WSYNC();
   }
   const int ld = b2_ld(nv);
+  B2_UNROLL1
   for (int i = B2_LANE; i < nv * ld; i += B2_NLANE) M[i] = 0;
   B2_WSYNC();
   const real* armature = MF(B2_MF_DOF_ARMATURE);
+  B2_UNROLL1
   for (int i = B2_LANE; i < nv; i += B2_NLANE) {
     real buf[6];
     inert_mul(buf, crb + 10 * dof_bodyid[i], cdof + 6 * i);
     const real* ci = cdof + 6 * i;
     M[i * ld + i] = armature[i] + ci[0] * buf[0] + ci[1] * buf[1] + ci[2] * buf[2] + ci[3] * buf[3] + ci[4] * buf[4] + ci[5] * buf[5];
+    B2_UNROLL1
     for (int j = dof_parentid[i]; j >= 0; j = dof_parentid[j]) {
       const real* cj = cdof + 6 * j;
       real v = cj[0] * buf[0] + cj[1] * buf[1] + cj[2] * buf[2] + cj[3] * buf[3] + cj[4] * buf[4] + cj[5] * buf[5];
@@ -458,6 +482,7 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
   B2_WSYNC();
   {
     real* g = d.df[B2_DF_QM] + (size_t)w * nv * ld;
+    B2_UNROLL1
     for (int i = B2_LANE; i < nv * ld; i += B2_NLANE) g[i] = M[i];
   }
 
@@ -480,6 +505,7 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
     B2_WSYNC();  // geom poses written above by other lanes
     // broadphase: ordered compaction of surviving pair ids
     int ncand = 0;
+    B2_UNROLL1
     for (int base = 0; base < m.npair; base += B2_NLANE) {
       int k = base + B2_LANE;
       bool hit = false;
@@ -516,6 +542,7 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
     int* c_geom = d.di[B2_DI_CONTACT_GEOM] + (size_t)w * nconmax * 2;
     int* c_dim = d.di[B2_DI_CONTACT_DIM] + (size_t)w * nconmax;
     int ncon = 0, ndrop = 0;
+    B2_UNROLL1
     for (int base = 0; base < ncand; base += B2_NLANE) {
       int ci = base + B2_LANE;
       LaneContacts lc;
@@ -533,6 +560,7 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
       // exclusive prefix sum of lc.n over lanes
       int incl = lc.n;
 #ifndef B2_HOSTEMU
+      B2_UNROLL1
       for (int o = 1; o < 32; o <<= 1) {
         int t = __shfl_up_sync(0xffffffffu, incl, o);
         if (B2_LANE >= o) incl += t;
@@ -572,6 +600,7 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
         }
         real F[9];
         make_frame(F, lc.normal, lc.tangent);
+        B2_UNROLL1
         for (int q = 0; q < lc.n; ++q) {
           int slot = start + q;
           if (slot >= nconmax) break;
@@ -597,13 +626,16 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
   }
 
   // ---- com_vel: cvel, cdof_dot (forward over levels) ----------------------------
+  B2_UNROLL1
   for (int lev = 0; lev < m.nlevel; ++lev) {
+    B2_UNROLL1
     for (int k = level_adr[lev] + B2_LANE; k < level_adr[lev + 1]; k += B2_NLANE) {
       int b = level_body[k];
       real v[6] = {0, 0, 0, 0, 0, 0};
       if (b > 0) {
         int p = body_parent[b];
         for (int c = 0; c < 6; ++c) v[c] = cvel[6 * p + c];
+        B2_UNROLL1
         for (int jj = 0; jj < body_jntnum[b]; ++jj) {
           int j = body_jntadr[b] + jj, da = jnt_dofadr[j];
           if (jnt_type[j] == B2_JNT_FREE) {
@@ -625,8 +657,10 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
   }
   {
     real* g = d.df[B2_DF_CVEL] + (size_t)w * nb * 6;
+    B2_UNROLL1
     for (int i = B2_LANE; i < 6 * nb; i += B2_NLANE) g[i] = cvel[i];
     g = d.df[B2_DF_CDOF_DOT] + (size_t)w * nv * 6;
+    B2_UNROLL1
     for (int i = B2_LANE; i < 6 * nv; i += B2_NLANE) g[i] = cdofdot[i];
   }
 
@@ -645,6 +679,7 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
     real* g_af = d.df[B2_DF_ACTUATOR_FORCE] + (size_t)w * nu;
     real* g_al = d.df[B2_DF_ACTUATOR_LENGTH] + (size_t)w * nu;
     real* g_av = d.df[B2_DF_ACTUATOR_VELOCITY] + (size_t)w * nu;
+    B2_UNROLL1
     for (int i = B2_LANE; i < nu; i += B2_NLANE) {
       int j = trnid[2 * i];
       real gr = gear[6 * i];
@@ -663,7 +698,9 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
 
   // ---- RNE bias (cacc aliases crb) -----------------------------------------------------
   const real* grav = MF(B2_MF_OPT_GRAVITY);
+  B2_UNROLL1
   for (int lev = 0; lev < m.nlevel; ++lev) {
+    B2_UNROLL1
     for (int k = level_adr[lev] + B2_LANE; k < level_adr[lev + 1]; k += B2_NLANE) {
       int b = level_body[k];
       real a[6];
@@ -673,6 +710,7 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
       } else {
         int p = body_parent[b];
         for (int c = 0; c < 6; ++c) a[c] = cacc[6 * p + c];
+        B2_UNROLL1
         for (int e = 0; e < body_dofnum[b]; ++e) {
           int dd = body_dofadr[b] + e;
           for (int c = 0; c < 6; ++c) a[c] += cdofdot[6 * dd + c] * qvel[dd];
@@ -687,9 +725,12 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
     }
     B2_WSYNC();
   }
+  B2_UNROLL1
   for (int lev = m.nlevel - 1; lev >= 1; --lev) {
+    B2_UNROLL1
     for (int k = level_adr[lev] + B2_LANE; k < level_adr[lev + 1]; k += B2_NLANE) {
       int b = level_body[k];
+      B2_UNROLL1
       for (int c = child_adr[b]; c < child_adr[b + 1]; ++c) {
         int ch = child_body[c];
         for (int e = 0; e < 6; ++e) cfrc[6 * b + e] += cfrc[6 * ch + e];
@@ -712,12 +753,14 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
     const int* dofmask = MI(B2_MI_BODY_DOFMASK);
     // any external wrench at all? (common case: none)
     int anyx = 0;
+    B2_UNROLL1
     for (int i = B2_LANE; i < 6 * nb; i += B2_NLANE) anyx |= (xfrc[i] != 0);
     anyx = b2_wor_i(anyx);
     real* g_bias = d.df[B2_DF_QFRC_BIAS] + (size_t)w * nv;
     real* g_pas = d.df[B2_DF_QFRC_PASSIVE] + (size_t)w * nv;
     real* g_act = d.df[B2_DF_QFRC_ACTUATOR] + (size_t)w * nv;
     real* g_smooth = d.df[B2_DF_QFRC_SMOOTH] + (size_t)w * nv;
+    B2_UNROLL1
     for (int i = B2_LANE; i < nv; i += B2_NLANE) {
       const real* ci = cdof + 6 * i;
       const real* cf = cfrc + 6 * dof_bodyid[i];
@@ -733,11 +776,13 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
       {
         int aid = dof_actid[i];
         int a_lo = aid >= 0 ? aid : 0, a_hi = aid >= 0 ? aid + 1 : (aid == -2 ? nu : 0);
+        B2_UNROLL1
         for (int a = a_lo; a < a_hi; ++a)
           if (jnt_dofadr[trnid[2 * a]] == i) act += gear[6 * a] * aforce[a];
       }
       real fs = pas - bias + act + qfrc_applied[i];
       if (anyx) {
+        B2_UNROLL1
         for (int b = 1; b < nb; ++b) {
           unsigned lo = (unsigned)dofmask[2 * b], hi = (unsigned)dofmask[2 * b + 1];
           bool in = i < 32 ? ((lo >> i) & 1u) : ((hi >> (i - 32)) & 1u);
@@ -761,6 +806,7 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
   spd_factor_solve(M, nv, ld, f, sm + L.invd);
   {
     real* g = d.df[B2_DF_QACC_SMOOTH] + (size_t)w * nv;
+    B2_UNROLL1
     for (int i = B2_LANE; i < nv; i += B2_NLANE) g[i] = f[i];
   }
 }

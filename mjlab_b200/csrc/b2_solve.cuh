@@ -51,7 +51,7 @@ static inline SolveSmem solve_smem_layout(int nv, int rows_cap, int runs_cap, in
 }
 
 // impedance / reference parameters of one row (mj_makeImpedance restated)
-B2_DEV void kbi(real timestep, const real* solref, const real* solimp, real pos, real& k, real& b, real& imp) {
+B2_DEV void kbi(real timestep, const real* solref, const real* solimp, real pos, real& k, real& b, real& imp) {  // @region kbi
   real timeconst = solref[0], dampratio = solref[1];
   real dmin = solimp[0], dmax = solimp[1], width = solimp[2], mid = solimp[3], power = solimp[4];
   if (timeconst > 0) timeconst = fmax(timeconst, 2 * timestep);
@@ -78,7 +78,7 @@ B2_DEV void kbi(real timestep, const real* solref, const real* solimp, real pos,
 }
 
 // y[r] = J[r,:] . x (- sub[r]) over compact rows; lanes over rows.
-B2_DEVN void rows_dot(const real* jpool, const int* rowinfo, const int* runinfo, const unsigned char* rundofs, int nefc,
+B2_DEVN void rows_dot(const real* jpool, const int* rowinfo, const int* runinfo, const unsigned char* rundofs, int nefc,  // @region rows_dot
                      const real* x, real* y, const real* sub) {
   B2_UNROLL1
   for (int r = B2_LANE; r < nefc; r += B2_NLANE) {
@@ -98,8 +98,9 @@ B2_DEVN void rows_dot(const real* jpool, const int* rowinfo, const int* runinfo,
 
 struct LsPnt { real alpha, cost, d1, d2; };
 
-B2_DEVN LsPnt ls_eval(real alpha, real q0g, real q1g, real q2g, const real* jar, const real* jv, const real* D, int nefc) {
+B2_DEVN LsPnt ls_eval(real alpha, real q0g, real q1g, real q2g, const real* jar, const real* jv, const real* D, int nefc) {  // @region linesearch
   real q0 = 0, q1 = 0, q2 = 0;
+  B2_UNROLL1
   for (int r = B2_LANE; r < nefc; r += B2_NLANE) {
     real x = jar[r] + alpha * jv[r];
     if (x < 0) {
@@ -169,10 +170,11 @@ B2_DEVN real linesearch(real q0g, real q1g, real q2g, real snorm, real tolerance
 }
 
 // contact-frame force [normal, t1, t2] decoded from the pyramid edge forces
-B2_DEV void contact_force(real* out, int adr, int dim, const real* fri, const real* D, const real* jar) {
+B2_DEV void contact_force(real* out, int adr, int dim, const real* fri, const real* D, const real* jar) {  // @region sensor_helpers
   out[0] = out[1] = out[2] = 0;
   if (adr < 0) return;
   if (dim == 1) { real x = jar[adr]; out[0] = x < 0 ? -D[adr] * x : 0; return; }
+  B2_UNROLL1
   for (int k = 1; k < dim; ++k) {
     int r = adr + 2 * (k - 1);
     real x1 = jar[r], x2 = jar[r + 1];
@@ -183,6 +185,7 @@ B2_DEV void contact_force(real* out, int adr, int dim, const real* fri, const re
 }
 
 B2_DEV bool in_subtree(const int* body_parent, int body, int root) {
+  B2_UNROLL1
   for (int b = body;; b = body_parent[b]) {
     if (b == root) return true;
     if (b == 0) return false;
@@ -218,7 +221,7 @@ B2_DEV void mat2quat(real* q, const real* R) {
 // ---------------------------------------------------------------------------
 // Stage 2 for world w.
 // ---------------------------------------------------------------------------
-B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int w, real* sm, int do_integrate) {
+B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int w, real* sm, int do_integrate) {  // @region setup_loads
   const int nv = m.nv, nb = m.nbody, nq = m.nq, nu = m.nu, njmax = d.njmax, nconmax = d.nconmax;
   real* H = sm + L.H; real* cdof = sm + L.cdof;
   real* qvel = sm + L.qvel; real* qacc = sm + L.qacc; real* Ma = sm + L.Ma; real* grad = sm + L.grad;
@@ -255,7 +258,9 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
   const real* g_cdof = d.df[B2_DF_CDOF] + (size_t)w * nv * 6;
   const real* M = d.df[B2_DF_QM] + (size_t)w * nv * b2_ld(nv);  // [nv][ld]; symmetric, so column i is read coalesced as M[e*ld + i]
 
+  B2_UNROLL1
   for (int i = B2_LANE; i < 6 * nv; i += B2_NLANE) cdof[i] = g_cdof[i];
+  B2_UNROLL1
   for (int i = B2_LANE; i < nv; i += B2_NLANE) {
     qvel[i] = g_qvel[i];
     qfs[i] = d.df[B2_DF_QFRC_SMOOTH][(size_t)w * nv + i];
@@ -263,11 +268,12 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
   }
   B2_WSYNC();
 
-  // ---- joint-limit rows (ordered: joint, lower then upper); each is its own run of width 1 ----
+  // ---- joint-limit rows (ordered: joint, lower then upper); each is its own run of width 1 ----  // @region limit_rows
   int nefc = 0;
   {
     const real* jnt_range = MF(B2_MF_JNT_RANGE);
     const real* jnt_margin = MF(B2_MF_JNT_MARGIN);
+    B2_UNROLL1
     for (int base = 0; base < 2 * m.njnt; base += B2_NLANE) {
       int s = base + B2_LANE;
       bool on = false;
@@ -294,6 +300,7 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
           g_mar[row] = jnt_margin[j];
           if (export_J) {
             real* Jr = gJ + (size_t)row * nv;
+            B2_UNROLL1
             for (int e = 0; e < nv; ++e) Jr[e] = 0;
             Jr[dof] = val;
           }
@@ -305,7 +312,7 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
   }
   const int nl = nefc;
 
-  // ---- contact rows ---------------------------------------------------------------------------
+  // ---- contact rows ---------------------------------------------------------------------------  // @region contact_rows
   const int ncon = d.di[B2_DI_NCON][w];
   const real* c_dist = d.df[B2_DF_CONTACT_DIST] + (size_t)w * nconmax;
   const real* c_pos = d.df[B2_DF_CONTACT_POS] + (size_t)w * nconmax * 3;
@@ -321,12 +328,14 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
   {
     // row addresses by prefix sum over contacts; a contact is kept iff its rows fit below the cap
     int run = nefc;
+    B2_UNROLL1
     for (int base = 0; base < ncon; base += B2_NLANE) {
       int c = base + B2_LANE;
       int nrow = 0;
       if (c < ncon && c_dist[c] < c_inc[c]) nrow = c_dim[c] == 1 ? 1 : 2 * (c_dim[c] - 1);
       int incl = nrow;
 #ifndef B2_HOSTEMU
+      B2_UNROLL1
       for (int o = 1; o < 32; o <<= 1) {
         int t = __shfl_up_sync(0xffffffffu, incl, o);
         if (B2_LANE >= o) incl += t;
@@ -357,6 +366,7 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
     int pooloff = nl, dofcount = nl;
     int pb1 = -1, pb2 = -1, cur_dofoff = 0, cur_w = 0, cur_run = -1, cur_row0 = 0, cur_nrow = 0;
     bool overflow = false;
+    B2_UNROLL1
     for (int c = 0; c < ncon; ++c) {
       int adr = cinfo[4 * c];
       if (adr < 0) continue;
@@ -396,6 +406,7 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
       real o1[3] = {p[0] - g_scom[3 * r1], p[1] - g_scom[3 * r1 + 1], p[2] - g_scom[3 * r1 + 2]};
       real o2[3] = {p[0] - g_scom[3 * r2], p[1] - g_scom[3 * r2 + 1], p[2] - g_scom[3 * r2 + 2]};
       const real* F = c_frame + 9 * c;
+      B2_UNROLL1
       for (int a = B2_LANE; a < cur_w; a += B2_NLANE) {
         int e = rundofs[cur_dofoff + a];
         bool in1 = e < 32 ? ((lo1 >> e) & 1u) : ((hi1 >> (e - 32)) & 1u);
@@ -408,6 +419,7 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
         if (dim == 1) {
           jpool[pooloff + a] = jn;
         } else {
+          B2_UNROLL1
           for (int k = 1; k < dim; ++k) {
             real jt = k < 3 ? F[3 * k] * jd[0] + F[3 * k + 1] * jd[1] + F[3 * k + 2] * jd[2] : (real)0;
             real mu = c_fri[5 * c + k - 1];
@@ -416,6 +428,7 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
           }
         }
       }
+      B2_UNROLL1
       for (int r = B2_LANE; r < nrow; r += B2_NLANE) {
         rowinfo[adr + r] = (pooloff + r * wpad) | (cur_run << 16);
         rowsrc[adr + r] = c;
@@ -430,6 +443,7 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
     if (overflow) {
       // rows form a prefix: recompute nefc as the end of the last kept contact
       int last = nl;
+      B2_UNROLL1
       for (int c = 0; c < ncon; ++c) {
         int adr = cinfo[4 * c];
         if (adr >= 0) { int dim = cinfo[4 * c + 1]; last = adr + (dim == 1 ? 1 : 2 * (dim - 1)); }
@@ -437,6 +451,7 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
       nefc = last;
     }
     B2_WSYNC();
+    B2_UNROLL1
     for (int c = B2_LANE; c < ncon; c += B2_NLANE) c_adr[c] = cinfo[4 * c];
     if (B2_LANE == 0) {
       d.di[B2_DI_NEFC][w] = nefc;
@@ -445,20 +460,23 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
     }
     // dense export for tests / API consumers that ask for efc_J
     if (export_J) {
+      B2_UNROLL1
       for (int r = nl; r < nefc; ++r) {
         int info = rowinfo[r];
         int off = info & 0xffff, run = info >> 16;
         int ri = runinfo[2 * run];
         int dofoff = ri & 0xffff, wd = ri >> 16;
+        B2_UNROLL1
         for (int e = B2_LANE; e < nv; e += B2_NLANE) gJ[(size_t)r * nv + e] = 0;
         B2_WSYNC();
+        B2_UNROLL1
         for (int a = B2_LANE; a < wd; a += B2_NLANE) gJ[(size_t)r * nv + rundofs[dofoff + a]] = jpool[off + a];
       }
       B2_WSYNC();
     }
   }
 
-  // ---- per-row impedance, D, aref -----------------------------------------------------------------
+  // ---- per-row impedance, D, aref -----------------------------------------------------------------  // @region impedance
   real* g_efcD = d.df[B2_DF_EFC_D] + (size_t)w * njmax;
   real* g_aref = d.df[B2_DF_EFC_AREF] + (size_t)w * njmax;
   real* g_force = d.df[B2_DF_EFC_FORCE] + (size_t)w * njmax;
@@ -469,6 +487,7 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
     const real* jnt_solref = MF(B2_MF_JNT_SOLREF);
     const real* jnt_solimp = MF(B2_MF_JNT_SOLIMP);
     const real impratio = MF(B2_MF_OPT_IMPRATIO)[0];
+    B2_UNROLL1
     for (int r = B2_LANE; r < nefc; r += B2_NLANE) {
       int src = rowsrc[r];
       real invw, k, b, imp;
@@ -495,11 +514,12 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
     B2_WSYNC();
   }
 
-  // ---- solve ------------------------------------------------------------------------------------------
+  // ---- solve ------------------------------------------------------------------------------------------  // @region solve_init
   int niter = 0;
   real* g_qacc = d.df[B2_DF_QACC] + (size_t)w * nv;
   real* g_qfc = d.df[B2_DF_QFRC_CONSTRAINT] + (size_t)w * nv;
   if (nefc == 0) {
+    B2_UNROLL1
     for (int i = B2_LANE; i < nv; i += B2_NLANE) { qacc[i] = qas[i]; qfc[i] = 0; }
     B2_WSYNC();
   } else {
@@ -511,20 +531,25 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
     // cost at qacc_smooth (Gauss term vanishes)
     rows_dot(jpool, rowinfo, runinfo, rundofs, nefc, qas, jar, aref);
     real cs = 0;
+    B2_UNROLL1
     for (int r = B2_LANE; r < nefc; r += B2_NLANE) { real x = jar[r]; if (x < 0) cs += (real)0.5 * D[r] * x * x; }
     cs = b2_wsum(cs);
     // cost at the warm start
+    B2_UNROLL1
     for (int i = B2_LANE; i < nv; i += B2_NLANE) qacc[i] = g_ws[i];
     B2_WSYNC();
     rows_dot(jpool, rowinfo, runinfo, rundofs, nefc, qacc, jar, aref);
     real cw = 0;
+    B2_UNROLL1
     for (int r = B2_LANE; r < nefc; r += B2_NLANE) { real x = jar[r]; if (x < 0) cw += (real)0.5 * D[r] * x * x; }
     real gw = 0;
     symv_global(M, nv, ld, qacc, Ma);
+    B2_UNROLL1
     for (int i = B2_LANE; i < nv; i += B2_NLANE) gw += (real)0.5 * (Ma[i] - qfs[i]) * (qacc[i] - qas[i]);
     cw = b2_wsum(cw + gw);
     B2_WSYNC();
     if (cw > cs) {
+      B2_UNROLL1
       for (int i = B2_LANE; i < nv; i += B2_NLANE) qacc[i] = qas[i];
       B2_WSYNC();
       rows_dot(jpool, rowinfo, runinfo, rundofs, nefc, qacc, jar, aref);
@@ -533,9 +558,11 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
     real cost = 0, gauss = 0;
     // rounding floor of the cost difference in this arithmetic: below it "improvement" is noise
     const real eps_real = sizeof(real) == 4 ? (real)1.1920929e-7 : (real)2.220446e-16;
+    B2_UNROLL1
     for (int it = 0;; ++it) {
-      // -- constraint update, part 1: row weights, cost, qfrc_constraint, gradient
+      // -- constraint update, part 1: row weights, cost, qfrc_constraint, gradient  // @region newton_update
       real c1 = 0;
+      B2_UNROLL1
       for (int r = B2_LANE; r < nefc; r += B2_NLANE) {
         real x = jar[r];
         real wr = x < 0 ? D[r] : (real)0;
@@ -543,25 +570,30 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
         c1 += (real)0.5 * wr * x * x;
       }
       real g1 = 0;
+      B2_UNROLL1
       for (int i = B2_LANE; i < nv; i += B2_NLANE) { g1 += (real)0.5 * (Ma[i] - qfs[i]) * (qacc[i] - qas[i]); qfc[i] = 0; }
       gauss = b2_wsum(g1);
       real newcost = b2_wsum(c1) + gauss;
       B2_WSYNC();
       if (nl > 0) {  // limit rows, gathered per dof (deterministic even if two rows share a dof)
+        B2_UNROLL1
         for (int e = B2_LANE; e < nv; e += B2_NLANE) {
           real ff = 0;
+          B2_UNROLL1
           for (int r = 0; r < nl; ++r)
             if (rundofs[r] == e) ff -= jpool[r] * wgt[r] * jar[r];
           qfc[e] += ff;
         }
         B2_WSYNC();
       }
+      B2_UNROLL1
       for (int run = nl; run < nrun; ++run) {  // contact runs: qfc += J^T f over the run's dofs
         int ri0 = runinfo[2 * run], ri1 = runinfo[2 * run + 1];
         int dofoff = ri0 & 0xffff, wd = ri0 >> 16, row0 = ri1 & 0xffff, nrow = ri1 >> 16;
         const int wpad = wd | 1;
         const int off0 = rowinfo[row0] & 0xffff;
         const unsigned char* dl = rundofs + dofoff;
+        B2_UNROLL1
         for (int a = B2_LANE; a < wd; a += B2_NLANE) {
           real ff = 0;
           B2_UNROLL1
@@ -571,6 +603,7 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
         B2_WSYNC();
       }
       real gn = 0;
+      B2_UNROLL1
       for (int i = B2_LANE; i < nv; i += B2_NLANE) { real g = Ma[i] - qfs[i] - qfc[i]; grad[i] = g; tmp[i] = g; gn += g * g; }
       B2_WSYNC();
       if (it > 0) {
@@ -583,17 +616,20 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
         cost = newcost;
       }
       if (it >= m.iterations) break;
-      // -- part 2: H = M + J^T diag(w) J, only when another Newton step will be taken
+      // -- part 2: H = M + J^T diag(w) J, only when another Newton step will be taken  // @region hessian
       copy_g2s(H, M, nv * ld);
       if (nl > 0) {
+        B2_UNROLL1
         for (int e = B2_LANE; e < nv; e += B2_NLANE) {
           real hh = 0;
+          B2_UNROLL1
           for (int r = 0; r < nl; ++r)
             if (rundofs[r] == e) hh += wgt[r];
           H[e * ld + e] += hh;
         }
         B2_WSYNC();
       }
+      B2_UNROLL1
       for (int run = nl; run < nrun; ++run) {  // J^T diag(w) J over the run's dof pairs
         int ri0 = runinfo[2 * run], ri1 = runinfo[2 * run + 1];
         int dofoff = ri0 & 0xffff, wd = ri0 >> 16, row0 = ri1 & 0xffff, nrow = ri1 >> 16;
@@ -601,6 +637,7 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
         const int off0 = rowinfo[row0] & 0xffff;
         const unsigned char* dl = rundofs + dofoff;
         const int npair = wd * (wd + 1) / 2;
+        B2_UNROLL1
         for (int pr = B2_LANE; pr < npair; pr += B2_NLANE) {
           int a = (int)((sqrt((real)(8 * pr + 1)) - 1) * (real)0.5);
           while (a * (a + 1) / 2 > pr) --a;
@@ -617,12 +654,14 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
         }
         B2_WSYNC();
       }
-      spd_factor_solve(H, nv, ld, tmp, invd);
+      spd_factor_solve(H, nv, ld, tmp, invd);  // @region factor_call
+      B2_UNROLL1
       for (int i = B2_LANE; i < nv; i += B2_NLANE) search[i] = -tmp[i];
       B2_WSYNC();
-      // -- line search
+      // -- line search  // @region ls_setup
       real sn = 0, q1 = 0, q2 = 0;
       symv_global(M, nv, ld, search, Mv);
+      B2_UNROLL1
       for (int i = B2_LANE; i < nv; i += B2_NLANE) {
         sn += search[i] * search[i];
         q1 += search[i] * (Ma[i] - qfs[i]);
@@ -632,20 +671,24 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
       rows_dot(jpool, rowinfo, runinfo, rundofs, nefc, search, jv, nullptr);
       real alpha = linesearch(gauss, q1, q2, sn, tolerance, ls_tolerance, m.ls_iterations, scale, jar, jv, D, nefc);
       if (alpha == 0) break;
+      B2_UNROLL1
       for (int i = B2_LANE; i < nv; i += B2_NLANE) { qacc[i] += alpha * search[i]; Ma[i] += alpha * Mv[i]; }
+      B2_UNROLL1
       for (int r = B2_LANE; r < nefc; r += B2_NLANE) jar[r] += alpha * jv[r];
       B2_WSYNC();
       niter = it + 1;
     }
     // qfc / efc_force at the final point: the loop exits right after a constraint update
     // (break at the convergence test or iteration cap) or with alpha == 0 (state unchanged).
+    B2_UNROLL1
     for (int r = B2_LANE; r < nefc; r += B2_NLANE) { real x = jar[r]; g_force[r] = x < 0 ? -D[r] * x : 0; }
   }
+  B2_UNROLL1
   for (int i = B2_LANE; i < nv; i += B2_NLANE) { g_qacc[i] = qacc[i]; g_qfc[i] = qfc[i]; }
   if (B2_LANE == 0) d.di[B2_DI_SOLVER_NITER][w] = niter;
   B2_WSYNC();
 
-  // ---- sensors -------------------------------------------------------------------------
+  // ---- sensors -------------------------------------------------------------------------  // @region sensors
   if (m.nsensor > 0) {
     const int* s_type = MI(B2_MI_SENSOR_TYPE);
     const int* s_objtype = MI(B2_MI_SENSOR_OBJTYPE);
@@ -679,7 +722,9 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
     if (m.has_accelerometer) {
       // cacc including qacc (rne_postconstraint, acceleration part), forward over levels
       const real* grav = MF(B2_MF_OPT_GRAVITY);
+      B2_UNROLL1
       for (int lev = 0; lev < m.nlevel; ++lev) {
+        B2_UNROLL1
         for (int k = level_adr[lev] + B2_LANE; k < level_adr[lev + 1]; k += B2_NLANE) {
           int b = level_body[k];
           real a[6];
@@ -688,6 +733,7 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
           } else {
             int p = body_parent[b];
             for (int c = 0; c < 6; ++c) a[c] = g_cacc[6 * p + c];
+            B2_UNROLL1
             for (int e = 0; e < body_dofnum[b]; ++e) {
               int dd = body_dofadr[b] + e;
               for (int c = 0; c < 6; ++c) a[c] += g_cdofdot[6 * dd + c] * qvel[dd] + g_cdof[6 * dd + c] * qacc[dd];
@@ -701,6 +747,7 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
     if (m.has_subtreevel) {
       // subtree linear velocity: backward gather of body momenta
       // per-body com velocity and own angular momentum stored first
+      B2_UNROLL1
       for (int b = B2_LANE; b < nb; b += B2_NLANE) {
         int r = body_root[b];
         const real* v = g_cvel + 6 * b;
@@ -723,7 +770,9 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
       // Stage A: L_b (about xipos_b, own body) -> shift to subtree com later, so store body term about its own com.
       // Stage B: bottom-up: for parent p: P_p = P_own + sum P_c ; L_p(about com_p) = L_own + (xipos_p - com_p) x P_own
       //          + sum_c [ L_c + (com_c - com_p) x P_c ].
+      B2_UNROLL1
       for (int lev = m.nlevel - 1; lev >= 0; --lev) {
+        B2_UNROLL1
         for (int k = level_adr[lev] + B2_LANE; k < level_adr[lev + 1]; k += B2_NLANE) {
           int b = level_body[k];
           real P[3] = {g_slin[3 * b], g_slin[3 * b + 1], g_slin[3 * b + 2]};
@@ -732,6 +781,7 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
           real t[3];
           cross3(t, dx, P);
           Lb[0] += t[0]; Lb[1] += t[1]; Lb[2] += t[2];
+          B2_UNROLL1
           for (int c = child_adr[b]; c < child_adr[b + 1]; ++c) {
             int ch = child_body[c];
             real Pc[3] = {g_slin[3 * ch], g_slin[3 * ch + 1], g_slin[3 * ch + 2]};
@@ -747,6 +797,7 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
       }
       // momentum -> velocity
       const real* stm = MF(B2_MF_BODY_SUBTREEMASS);
+      B2_UNROLL1
       for (int b = B2_LANE; b < nb; b += B2_NLANE) {
         real inv = stm[b] > B2_MINVAL ? (real)1 / stm[b] : (real)0;
         g_slin[3 * b] *= inv; g_slin[3 * b + 1] *= inv; g_slin[3 * b + 2] *= inv;
@@ -754,9 +805,11 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
       B2_WSYNC();
     }
     B2_WSYNC();
+    B2_UNROLL1
     for (int s = B2_LANE; s < m.nsensor; s += B2_NLANE) {
       int t = s_type[s], oid = s_objid[s], adr = s_adr[s], dim = s_dim[s];
       real* out = sd + adr;
+      B2_UNROLL1
       for (int e = 0; e < dim; ++e) out[e] = 0;
       if (t == B2_SENS_GYRO || t == B2_SENS_VELOCIMETER || t == B2_SENS_ACCELEROMETER) {
         int b = site_body[oid], r = body_root[b];
@@ -815,6 +868,7 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
         int nfound = 0;
         real net[3] = {0, 0, 0};
         // pass 1: count matches (and net force)
+        B2_UNROLL1
         for (int c = 0; c < ncon; ++c) {
           int g1 = c_geom[2 * c], g2 = c_geom[2 * c + 1];
           real sgn = 0;
@@ -838,8 +892,10 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
             // slots: first `num` matches in contact order (reduce none) or ranked by dist / force
             int filled = 0;
             real lastkey = 0; int lastc = -1;
+            B2_UNROLL1
             for (int slot = 0; slot < num && slot < nfound; ++slot) {
               int pick = -1; real pickkey = 0, picksgn = 0;
+              B2_UNROLL1
               for (int c = 0; c < ncon; ++c) {
                 int g1 = c_geom[2 * c], g2 = c_geom[2 * c + 1];
                 real sgn = 0;
@@ -882,12 +938,13 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
       }
       real cut = s_cutoff[s];
       if (cut > 0 && t != B2_SENS_CONTACT)
+        B2_UNROLL1
         for (int e = 0; e < dim; ++e) out[e] = clampr(out[e], -cut, cut);
     }
     B2_WSYNC();
   }
 
-  // ---- integrate ---------------------------------------------------------------------------
+  // ---- integrate ---------------------------------------------------------------------------  // @region integrate
   if (do_integrate) {
     const real* damping = MF(B2_MF_DOF_DAMPING);
     real* g_ws = d.df[B2_DF_QACC_WARMSTART] + (size_t)w * nv;
@@ -895,9 +952,11 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
     if (m.integrator == B2_INT_IMPLICITFAST) implicit = true;
     else {
       int anyd = 0;
+      B2_UNROLL1
       for (int i = B2_LANE; i < nv; i += B2_NLANE) anyd |= damping[i] > 0;
       implicit = b2_wor_i(anyd) != 0;
     }
+    B2_UNROLL1
     for (int i = B2_LANE; i < nv; i += B2_NLANE) tmp[i] = qacc[i];
     B2_WSYNC();
     if (implicit) {
@@ -911,11 +970,13 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
       const real* gear = MF(B2_MF_ACTUATOR_GEAR);
       const real* frange = MF(B2_MF_ACTUATOR_FORCERANGE);
       const real* g_af = d.df[B2_DF_ACTUATOR_FORCE] + (size_t)w * nu;
+      B2_UNROLL1
       for (int i = B2_LANE; i < nv; i += B2_NLANE) {
         real qd = -damping[i];
         if (m.integrator == B2_INT_IMPLICITFAST) {
           int aid = dof_actid[i];
           int a_lo = aid >= 0 ? aid : 0, a_hi = aid >= 0 ? aid + 1 : (aid == -2 ? nu : 0);
+          B2_UNROLL1
           for (int a = a_lo; a < a_hi; ++a) {
             if (biastype[a] != 1 || jnt_dofadr[trnid[2 * a]] != i) continue;
             real fa = g_af[a];
@@ -929,6 +990,7 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
       B2_WSYNC();
       spd_factor_solve(H, nv, ld, tmp, invd);
     }
+    B2_UNROLL1
     for (int i = B2_LANE; i < nv; i += B2_NLANE) {
       real v = qvel[i] + timestep * tmp[i];
       qvel[i] = v;
@@ -936,6 +998,7 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
       g_ws[i] = qacc[i];
     }
     B2_WSYNC();
+    B2_UNROLL1
     for (int j = B2_LANE; j < m.njnt; j += B2_NLANE) {
       int qa = jnt_qposadr[j], da = jnt_dofadr[j];
       if (jnt_type[j] == B2_JNT_FREE) {

@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from collections.abc import Mapping
 from dataclasses import dataclass, field
 from typing import Any, Literal
@@ -268,7 +269,7 @@ class ManagerBasedRlEnv:
       A.fill_params(self._ce, self.vcfg)
     self._next_stage = 0
     self._graph: torch.cuda.CUDAGraph | None = None
-    self.use_cuda_graph = True
+    self.use_cuda_graph = os.environ.get("B200SIM_NO_GRAPH", "0") != "1"  # eager launches for profilers
     self._capture()
 
   # ---- properties (manager_based_rl_env.py:171-203) --------------------------------------------------

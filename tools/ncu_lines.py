@@ -37,6 +37,35 @@ def line_table(so: str, kernel: str):
   return out
 
 
+def region_of(key):
+  """Map (file, line) to a named region using `// @region name` markers in the source file."""
+  f, l = key
+  marks = _marks(f)
+  name = f
+  for ml, mn in marks:
+    if ml <= l:
+      name = f"{f}:{mn}"
+    else:
+      break
+  return name
+
+
+_MARKS = {}
+
+
+def _marks(f):
+  if f not in _MARKS:
+    cands = list(Path(".").rglob(f))
+    out = []
+    if cands:
+      for i, ln in enumerate(cands[0].read_text().splitlines(), 1):
+        mm = re.search(r"//\s*@region\s+(\S+)", ln)
+        if mm:
+          out.append((i, mm.group(1)))
+    _MARKS[f] = out
+  return _MARKS[f]
+
+
 def main():
   sass_csv, so, kernel = sys.argv[1:4]
   top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
@@ -69,6 +98,18 @@ def main():
   print("--- by stall samples")
   for k, v in sorted(samples.items(), key=lambda kv: -kv[1])[:top]:
     print(f"{100*v/ts:5.1f}% smp {100*insts[k]/ti:5.1f}% ins  {k[0]}:{k[1]:<4d} {text(*k)}")
+  print("--- by executed warp instructions")
+  for k, v in sorted(insts.items(), key=lambda kv: -kv[1])[:top]:
+    print(f"{100*samples[k]/ts:5.1f}% smp {100*v/ti:5.1f}% ins  {k[0]}:{k[1]:<4d} {text(*k)}")
+  # coarse regions: consecutive source-line ranges of the solver file (see tools/ncu_lines.py REGIONS)
+  regions = defaultdict(lambda: [0, 0])
+  for k in insts:
+    name = region_of(k)
+    regions[name][0] += samples[k]
+    regions[name][1] += insts[k]
+  print("--- by region")
+  for name, (sv, iv) in sorted(regions.items(), key=lambda kv: -kv[1][1]):
+    print(f"{100*sv/ts:5.1f}% smp {100*iv/ti:5.1f}% ins  {name}")
 
 
 if __name__ == "__main__":
