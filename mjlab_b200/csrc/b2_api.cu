@@ -92,9 +92,10 @@ static int make_plan(const b2_model* m, const b2_data* d, Plan* p) {
   if (jpool_cap > 65535) jpool_cap = 65535;
   if (jpool_cap < 2 * m->nlimited + wpad * 6) jpool_cap = 2 * m->nlimited + wpad * 6;
   int dofs_cap = 2 * m->nlimited + d->nconmax * m->maxchain;
-  p->lv = solve_smem_layout(m->nv, rows_cap, runs_cap, d->nconmax > 0 ? d->nconmax : 1, jpool_cap, dofs_cap);
+  p->lv = solve_smem_layout(m->nv, rows_cap, runs_cap, d->nconmax > 0 ? d->nconmax : 1, jpool_cap, dofs_cap, m->maxchain);
   p->smem_smooth = (size_t)p->ls.total * sizeof(real) * B2_WPB;
   p->smem_solve = (size_t)p->lv.total * sizeof(real) * B2_WPB;
+  if (const char* e = getenv("B200SIM_SMEM_PAD")) p->smem_solve += (size_t)atoi(e);  // occupancy experiments only
   return 0;
 }
 

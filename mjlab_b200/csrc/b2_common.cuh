@@ -207,38 +207,40 @@ B2_DEV real b2_shfl(real x, int) { return x; }
 B2_DEV real b2_shfl(real x, int src) { return __shfl_sync(0xffffffffu, x, src); }
 #endif
 
-// In-place lower Cholesky of A (lower triangle valid, upper ignored). invd[j] <- 1 / L[j][j].
-B2_DEVN void chol_factor(real* A, int n, int ld, real* invd, real* prow) {  // @region chol_factor
+// In-place lower Cholesky of A (lower triangle valid, upper ignored) with the forward substitution fused in:
+// x (the right-hand side on entry) is treated as row n of the matrix, so on exit x = L^-1 b at no extra pass.
+// invd[j] <- 1 / L[j][j].  The pivot row is read in place (its entries k < j are final), 128-bit loads for the
+// 4-aligned part of the k range and a predicated scalar tail of at most 3 elements.
+B2_DEVN void chol_factor(real* A, int n, int ld, real* invd, real* x) {  // @region chol_factor
+  const int nrows = x ? n + 1 : n;
   B2_UNROLL1
   for (int j = 0; j < n; ++j) {
     B2_WSYNC();
-    // pivot row, zero-padded to a multiple of 4 so the k loop needs no scalar tail
     const real* rj = A + j * ld;
-    B2_UNROLL1
-    for (int k = B2_LANE; k < ld; k += B2_NLANE) prow[k] = k < j ? rj[k] : (real)0;
-    B2_WSYNC();
-    const int j4 = (j + 3) & ~3;
+    const int j0 = j & ~3;
     real inv = 0;
     B2_UNROLL1
-    for (int base = j; base < n; base += B2_NLANE) {
+    for (int base = j; base < nrows; base += B2_NLANE) {
       int i = base + B2_LANE;
       real s = 0;
-      if (i < n) {
-        const real* ri = A + i * ld;
+      const real* ri = i < n ? A + i * ld : x;
+      if (i < nrows) {
         s = ri[j];
 #ifndef B2_HOSTEMU
         real s2 = 0;
         B2_UNROLL1
-        for (int k = 0; k < j4; k += 4) {
+        for (int k = 0; k < j0; k += 4) {
           float4 a = *reinterpret_cast<const float4*>(ri + k);
-          float4 b = *reinterpret_cast<const float4*>(prow + k);
+          float4 b = *reinterpret_cast<const float4*>(rj + k);
           s = fmaf(-a.x, b.x, s); s2 = fmaf(-a.y, b.y, s2);
           s = fmaf(-a.z, b.z, s); s2 = fmaf(-a.w, b.w, s2);
         }
+        if (j0 < j) s = fmaf(-ri[j0], rj[j0], s);
+        if (j0 + 1 < j) s2 = fmaf(-ri[j0 + 1], rj[j0 + 1], s2);
+        if (j0 + 2 < j) s = fmaf(-ri[j0 + 2], rj[j0 + 2], s);
         s += s2;
 #else
-        B2_UNROLL1
-        for (int k = 0; k < j4; ++k) s -= ri[k] * prow[k];
+        for (int k = 0; k < j; ++k) s -= ri[k] * rj[k];
 #endif
       }
       if (base == j) {
@@ -246,27 +248,19 @@ B2_DEVN void chol_factor(real* A, int n, int ld, real* invd, real* prow) {  // @
         inv = b2_rsqrt(piv > B2_MINVAL ? piv : B2_MINVAL);
         if (B2_LANE == 0) invd[j] = inv;
       }
-      if (i < n) A[i * ld + j] = s * inv;
+      if (i < n) A[i * ld + j] = s * inv;  // column j is not read by anyone during this column
+      else if (i == n && x) x[j] = s * inv;
     }
   }
   B2_WSYNC();
 }
 
-// x <- (L L^T)^-1 x, x in shared memory.
-B2_DEVN void chol_solve(const real* L, int n, int ld, const real* invd, real* x) {  // @region chol_solve
+// x <- L^-T x (backward substitution), x in shared memory.
+B2_DEVN void chol_backsolve(const real* L, int n, int ld, const real* invd, real* x) {  // @region chol_solve
 #ifdef B2_HOSTEMU
-  B2_UNROLL1
-  for (int k = 0; k < n; ++k) {
-    real xk = x[k] * invd[k];
-    x[k] = xk;
-    B2_UNROLL1
-    for (int i = k + 1; i < n; ++i) x[i] -= L[i * ld + k] * xk;
-  }
-  B2_UNROLL1
   for (int k = n - 1; k >= 0; --k) {
     real xk = x[k] * invd[k];
     x[k] = xk;
-    B2_UNROLL1
     for (int i = 0; i < k; ++i) x[i] -= L[k * ld + i] * xk;
   }
 #else
@@ -276,20 +270,19 @@ B2_DEVN void chol_solve(const real* L, int n, int ld, const real* invd, real* x)
   real x0 = row0 < n ? x[row0] : (real)0;
   real x1 = row1 < n ? x[row1] : (real)0;
   B2_UNROLL1
-  for (int k = 0; k < n; ++k) {
-    real l0 = row0 > k && row0 < n ? L[row0 * ld + k] : (real)0;
-    real l1 = row1 > k && row1 < n ? L[row1 * ld + k] : (real)0;
-    real xk = b2_shfl(k < 32 ? x0 : x1, k & 31) * invd[k];
-    if (row0 == k) x0 = xk; else x0 = fmaf(-l0, xk, x0);
+  for (int k = n - 1; k >= 32; --k) {
+    const real* Lk = L + k * ld;
+    real l0 = Lk[row0];
+    real l1 = row1 < k ? Lk[row1] : (real)0;
+    real xk = b2_shfl(x1, k & 31) * invd[k];
+    x0 = fmaf(-l0, xk, x0);
     if (row1 == k) x1 = xk; else x1 = fmaf(-l1, xk, x1);
   }
   B2_UNROLL1
-  for (int k = n - 1; k >= 0; --k) {
+  for (int k = (n < 32 ? n : 32) - 1; k >= 0; --k) {
     real l0 = row0 < k ? L[k * ld + row0] : (real)0;
-    real l1 = row1 < k ? L[k * ld + row1] : (real)0;
-    real xk = b2_shfl(k < 32 ? x0 : x1, k & 31) * invd[k];
+    real xk = b2_shfl(x0, k) * invd[k];
     if (row0 == k) x0 = xk; else x0 = fmaf(-l0, xk, x0);
-    if (row1 == k) x1 = xk; else x1 = fmaf(-l1, xk, x1);
   }
   if (row0 < n) x[row0] = x0;
   if (row1 < n) x[row1] = x1;
@@ -340,6 +333,6 @@ B2_DEVN void copy_g2s(real* dst, const real* src, int count) {  // @region copy_
 
 // A (n x n, leading dimension ld, lower triangle valid) <- chol(A);  x <- A^-1 x.
 B2_DEV void spd_factor_solve(real* A, int n, int ld, real* x, real* invd) {
-  chol_factor(A, n, ld, invd, invd + 64);
-  chol_solve(A, n, ld, invd, x);
+  chol_factor(A, n, ld, invd, x);
+  chol_backsolve(A, n, ld, invd, x);
 }

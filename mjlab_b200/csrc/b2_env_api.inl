@@ -2,24 +2,24 @@
 
 #define B2E_WPB 4  // envs (warps) per CTA for the env kernels
 
-__global__ void __launch_bounds__(B2E_WPB * 32) k_env_action(const KModel m, const KData d, const KEnv e) {
+__global__ void __launch_bounds__(B2E_WPB * 32) k_env_action(const __grid_constant__ KModel m, const __grid_constant__ KData d, const __grid_constant__ KEnv e) {
   int w = blockIdx.x * B2E_WPB + (threadIdx.x >> 5);
   if (w < d.nworld) env_action_world(m, d, e, w);
 }
-__global__ void __launch_bounds__(B2E_WPB * 32) k_env_airtime(const KModel m, const KData d, const KEnv e) {
+__global__ void __launch_bounds__(B2E_WPB * 32) k_env_airtime(const __grid_constant__ KModel m, const __grid_constant__ KData d, const __grid_constant__ KEnv e) {
   int w = blockIdx.x * B2E_WPB + (threadIdx.x >> 5);
   if (w < d.nworld) env_airtime_world(m, d, e, w);
 }
-__global__ void __launch_bounds__(B2E_WPB * 32) k_env_post(const KModel m, const KData d, const KEnv e) {
+__global__ void __launch_bounds__(B2E_WPB * 32) k_env_post(const __grid_constant__ KModel m, const __grid_constant__ KData d, const __grid_constant__ KEnv e) {
   int w = blockIdx.x * B2E_WPB + (threadIdx.x >> 5);
   if (w < d.nworld) env_post_world(m, d, e, w);
 }
-__global__ void __launch_bounds__(B2E_WPB * 32) k_env_obs(const KModel m, const KData d, const KEnv e, int with_update) {
+__global__ void __launch_bounds__(B2E_WPB * 32) k_env_obs(const __grid_constant__ KModel m, const __grid_constant__ KData d, const __grid_constant__ KEnv e, int with_update) {
   int w = blockIdx.x * B2E_WPB + (threadIdx.x >> 5);
   if (w < d.nworld) env_obs_world(m, d, e, w, with_update);
 }
 // _reset_idx for the envs selected by mask (NULL = all); clears the per-env log rows first
-__global__ void __launch_bounds__(B2E_WPB * 32) k_env_reset(const KModel m, const KData d, const KEnv e, const unsigned char* mask) {
+__global__ void __launch_bounds__(B2E_WPB * 32) k_env_reset(const __grid_constant__ KModel m, const __grid_constant__ KData d, const __grid_constant__ KEnv e, const unsigned char* mask) {
   int w = blockIdx.x * B2E_WPB + (threadIdx.x >> 5);
   if (w >= d.nworld) return;
   float* logv = reinterpret_cast<float*>(e.buf[B2E_B_LOG_ENV]) + (size_t)w * B2E_NLOG;

@@ -36,7 +36,7 @@ static inline SmoothSmem smooth_smem_layout(int nq, int nv, int nu, int nbody, i
   s.M = take(nv * b2_ld(nv)); s.f = take(nv);
   s.aforce = take(nu);
   s.cand = take(ncand);      // candidate pair ids (ints stored in real-sized slots)
-  s.invd = take(64 + 72);  // 1/diag, then the zero-padded pivot row of the Cholesky
+  s.invd = take(64);  // 1 / diag(L)
   s.total = o;
   return s;
 }

@@ -19,18 +19,18 @@
 // (G1 foot-ground contact: w = 12 of nv = 35).
 struct SolveSmem {
   int M, H, cdof, qvel, qacc, Ma, grad, search, Mv, qfs, qas, qfc, tmp, invd;
-  int D, aref, jar, jv, rowinfo, rowsrc, runinfo, rundofs, cinfo, jpool;
+  int D, aref, jar, jv, rowinfo, rowsrc, runinfo, rundofs, cinfo, jpool, pairtab;
   int rows_cap, runs_cap, jpool_cap, dofs_cap, total;
 };
 
-static inline SolveSmem solve_smem_layout(int nv, int rows_cap, int runs_cap, int nconmax, int jpool_cap, int dofs_cap) {
+static inline SolveSmem solve_smem_layout(int nv, int rows_cap, int runs_cap, int nconmax, int jpool_cap, int dofs_cap, int maxchain) {
   SolveSmem s;
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
   s.M = -1;  // qM stays in HBM/L2 (read coalesced through its symmetry), not staged
   s.H = take(nv * b2_ld(nv));
   s.qvel = take(nv); s.qacc = take(nv); s.Ma = take(nv); s.grad = take(nv); s.search = take(nv); s.Mv = take(nv);
-  s.qfs = take(nv); s.qas = take(nv); s.qfc = take(nv); s.tmp = take(nv); s.invd = take(64 + 72);  // 1/diag, then the zero-padded pivot row of the Cholesky
+  s.qfs = take(nv); s.qas = take(nv); s.qfc = take(nv); s.tmp = take(nv); s.invd = take(64);  // 1 / diag(L)
   // D and aref are first written after the Jacobian rows are assembled; cdof is only read
   // during that assembly, so the two share storage (needs 2*rows_cap >= 6*nv, else padded).
   int dd = 2 * ((rows_cap + 3) & ~3);
@@ -45,6 +45,7 @@ static inline SolveSmem solve_smem_layout(int nv, int rows_cap, int runs_cap, in
   s.rundofs = take((dofs_cap + 3) / 4);  // bytes
   s.cinfo = take(4 * nconmax);       // int4 per contact: adr, dim, body1, body2
   s.jpool = take(jpool_cap);
+  s.pairtab = take((maxchain * (maxchain + 1) / 2 + 1) / 2);  // ushort (a << 8 | b) per lower-triangle pair index
   s.rows_cap = rows_cap; s.runs_cap = runs_cap; s.jpool_cap = jpool_cap; s.dofs_cap = dofs_cap;
   s.total = o;
   return s;
@@ -69,7 +70,10 @@ B2_DEV void kbi(real timestep, const real* solref, const real* solimp, real pos,
     imp = dmax;
   } else {
     real y;
-    if (x < mid) y = pow(x, power) / pow(mid, power - 1);
+    if (power == 2) {  // MuJoCo's default solimp power: same value as pow(), without fetching the powf code
+      if (x < mid) y = x * x / mid;
+      else y = 1 - (1 - x) * (1 - x) / (1 - mid);
+    } else if (x < mid) y = pow(x, power) / pow(mid, power - 1);
     else y = 1 - pow(1 - x, power) / pow(1 - mid, power - 1);
     imp = dmin + y * (dmax - dmin);
     real lo = fmin(dmin, dmax), hi = fmax(dmin, dmax);
@@ -235,6 +239,8 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
   unsigned char* rundofs = (unsigned char*)(sm + L.rundofs);
   int* cinfo = (int*)(sm + L.cinfo);
   real* jpool = sm + L.jpool;
+  unsigned short* pairtab = (unsigned short*)(sm + L.pairtab);
+  real* frc = aref;  // -D*active*jar per row; aref itself is dead once jar has been initialised
   const int rows_cap = L.rows_cap < njmax ? L.rows_cap : njmax;
   const int ld = b2_ld(nv);
 
@@ -476,6 +482,18 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
     }
   }
 
+  // pair-index -> (a, b) table of the lower triangle (a >= b), shared by every run: pr = a (a + 1) / 2 + b
+  if (nefc > nl) {
+    const int npairmax = m.maxchain * (m.maxchain + 1) / 2;
+    B2_UNROLL1
+    for (int pr = B2_LANE; pr < npairmax; pr += B2_NLANE) {
+      int a = (int)((sqrt((real)(8 * pr + 1)) - 1) * (real)0.5);
+      while (a * (a + 1) / 2 > pr) --a;
+      while ((a + 1) * (a + 2) / 2 <= pr) ++a;
+      pairtab[pr] = (unsigned short)((a << 8) | (pr - a * (a + 1) / 2));
+    }
+    B2_WSYNC();
+  }
   // ---- per-row impedance, D, aref -----------------------------------------------------------------  // @region impedance
   real* g_efcD = d.df[B2_DF_EFC_D] + (size_t)w * njmax;
   real* g_aref = d.df[B2_DF_EFC_AREF] + (size_t)w * njmax;
@@ -567,6 +585,7 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
         real x = jar[r];
         real wr = x < 0 ? D[r] : (real)0;
         wgt[r] = wr;
+        frc[r] = -wr * x;
         c1 += (real)0.5 * wr * x * x;
       }
       real g1 = 0;
@@ -581,7 +600,7 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
           real ff = 0;
           B2_UNROLL1
           for (int r = 0; r < nl; ++r)
-            if (rundofs[r] == e) ff -= jpool[r] * wgt[r] * jar[r];
+            if (rundofs[r] == e) ff += jpool[r] * frc[r];
           qfc[e] += ff;
         }
         B2_WSYNC();
@@ -597,7 +616,7 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
         for (int a = B2_LANE; a < wd; a += B2_NLANE) {
           real ff = 0;
           B2_UNROLL1
-          for (int q = 0; q < nrow; ++q) ff -= jpool[off0 + q * wpad + a] * wgt[row0 + q] * jar[row0 + q];
+          for (int q = 0; q < nrow; ++q) ff = fma(jpool[off0 + q * wpad + a], frc[row0 + q], ff);
           qfc[dl[a]] += ff;
         }
         B2_WSYNC();
@@ -639,18 +658,22 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
         const int npair = wd * (wd + 1) / 2;
         B2_UNROLL1
         for (int pr = B2_LANE; pr < npair; pr += B2_NLANE) {
-          int a = (int)((sqrt((real)(8 * pr + 1)) - 1) * (real)0.5);
-          while (a * (a + 1) / 2 > pr) --a;
-          while ((a + 1) * (a + 2) / 2 <= pr) ++a;
-          int b = pr - a * (a + 1) / 2;
-          real acc = 0;
+          const int ab = pairtab[pr];
+          const int a = ab >> 8, b = ab & 0xff;
+          const real* ja = jpool + off0 + a;
+          const real* jb = jpool + off0 + b;
+          const real* wq = wgt + row0;
+          real acc = 0, acc2 = 0;
+          int q = 0;
           B2_UNROLL1
-          for (int q = 0; q < nrow; ++q) {
-            const real* jr = jpool + off0 + q * wpad;
-            acc += wgt[row0 + q] * jr[a] * jr[b];
+          for (; q + 2 <= nrow; q += 2) {
+            acc = fma(wq[q] * ja[0], jb[0], acc);
+            acc2 = fma(wq[q + 1] * ja[wpad], jb[wpad], acc2);
+            ja += 2 * wpad; jb += 2 * wpad;
           }
+          if (q < nrow) acc = fma(wq[q] * ja[0], jb[0], acc);
           int da = dl[a], db = dl[b];  // dof lists are ascending: da >= db
-          H[da * ld + db] += acc;
+          H[da * ld + db] += acc + acc2;
         }
         B2_WSYNC();
       }

@@ -31,7 +31,7 @@ int b2h_run(const KModel* m, KData* d, int do_integrate, int world_lo, int world
   int jpool_cap = rows_cap * wpad;
   if (jpool_budget > 0 && jpool_cap > jpool_budget) jpool_cap = jpool_budget;
   SolveSmem lv = solve_smem_layout(m->nv, rows_cap, 2 * m->nlimited + d->nconmax + 1, d->nconmax > 0 ? d->nconmax : 1,
-                                   jpool_cap, 2 * m->nlimited + d->nconmax * m->maxchain);
+                                   jpool_cap, 2 * m->nlimited + d->nconmax * m->maxchain, m->maxchain);
   std::vector<real> a(ls.total), b(lv.total);
   for (int w = world_lo; w < world_hi && w < d->nworld; ++w) {
     smooth_world(*m, *d, ls, 256, w, a.data());
