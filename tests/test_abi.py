@@ -64,3 +64,34 @@ def test_product_does_not_import_oracle():
     src = p.read_text()
     assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), p
     assert "hostemu" not in src, p
+
+
+ENV_HEADER = (ROOT / "include" / "b200env.h").read_text()
+
+
+def test_env_header_symbols_exported_and_struct_matches():
+  """include/b200env.h: every declared entry point is exported, and the ctypes mirror (mjlab_b200/envabi.py, which reads
+  the enum values from the header itself) has the size the library reports."""
+  from mjlab_b200 import envabi as A
+  __import__("__graft_entry__").build()
+  lib = ctypes.CDLL(str(E.LIB_PATH))
+  fns = re.findall(r"^\s*int\s+(b2_\w+)\s*\(", ENV_HEADER, re.M)
+  assert {"b2_env_action", "b2_env_airtime", "b2_env_post", "b2_env_obs", "b2_env_log", "b2_env_reset", "b2_forward_masked",
+          "b2_actuator_pd", "b2_delay_step", "b2_actuator_mlp", "b2_env_check", "b2_sizeof_env"} <= set(fns)
+  for fn in fns:
+    assert hasattr(lib, fn), fn
+  lib.b2_sizeof_env.restype = ctypes.c_int
+  assert lib.b2_sizeof_env() == ctypes.sizeof(A.B2Env)
+  # the buffer table follows the header enum order, and the reward / termination name lists match the enum sizes
+  from mjlab_b200 import envcfg
+  assert len(envcfg.REWARD_NAMES) == A.NREW and len(envcfg.TERMINATION_NAMES) == A.NTERM
+  assert A.K["B2E_DRAW_NOISE"] + 160 == A.NDRAW
+
+
+def test_env_requires_cuda():
+  from mjlab_b200.env import ManagerBasedRlEnv, VelocityEnvCfg
+  with pytest.raises(RuntimeError):
+    ManagerBasedRlEnv(VelocityEnvCfg(robot="go1", num_envs=2), "cpu")
+  from mjlab_b200.actuators import IdealPdActuator
+  with pytest.raises(RuntimeError):
+    IdealPdActuator(2, 3, 1.0, 0.1, device="cpu")

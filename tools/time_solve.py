@@ -47,3 +47,7 @@ d = env.sim.data
 print(f"{os.environ.get('B200SIM_LIB', 'default'):40s} jpool={os.environ.get('B200SIM_JPOOL', '-'):>5s} k_smooth {statistics.mean(ts):.4f} ms  "
       f"k_solve {statistics.mean(tv):.4f} ms  (min {min(tv):.4f})  nefc {d.nefc.float().mean().item():.1f} niter {d.solver_niter.float().mean().item():.2f} "
       f"dropped {int(d.nefc_dropped.sum().item())}")
+ne = d.nefc.float()
+q = torch.tensor([0.5, 0.75, 0.9, 0.95, 0.99, 1.0], device=ne.device)
+print("nefc quantiles 50/75/90/95/99/100:", torch.quantile(ne, q).tolist(), " frac>64:", (ne > 64).float().mean().item(), " frac>96:", (ne > 96).float().mean().item(),
+      " ncon q:", torch.quantile(d.ncon.float(), q).tolist(), " niter q:", torch.quantile(d.solver_niter.float(), q).tolist())
