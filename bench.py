@@ -341,6 +341,7 @@ def run_b200(args):
       for _ in range(DECIMATION):
         timed("k_smooth", lambda st: lib.b2_stage(pm, pd, 0, 1, st))
         timed("k_solve", lambda st: lib.b2_stage(pm, pd, 1, 1, st))
+        timed("k_post", lambda st: lib.b2_stage(pm, pd, 2, 1, st))
         timed("k_env_airtime", lambda st: lib.b2_env_airtime(pm, pd, pe, st))
       timed("k_env_post", lambda st: lib.b2_env_post(pm, pd, pe, st))
       timed("forward_after_reset", lambda st: lib.b2_forward_masked(pm, pd, mask, gate, st))

@@ -236,10 +236,10 @@ int b2_check(const b2_model* m, const b2_data* d);
 int b2_step(const b2_model* m, b2_data* d, void* stream);
 int b2_forward(const b2_model* m, b2_data* d, void* stream);
 
-/* One stage of b2_step on its own (0 = k_smooth: position/velocity stage,
- * 1 = k_solve: constraints, solver, sensors, integration when do_integrate != 0).
- * b2_step == stage 0 then stage 1 with do_integrate = 1.  Used by bench.py to
- * bracket each kernel with CUDA events and by stage-wise tests. */
+/* One stage of b2_step on its own: 0 = k_smooth (position / velocity stage), 1 = k_solve (constraint rows + Newton
+ * solver), 2 = k_post (sensors, and integration when do_integrate != 0).  b2_step == stages 0, 1, 2 with
+ * do_integrate = 1; b2_forward the same with do_integrate = 0.  Used by bench.py to bracket each kernel with CUDA events
+ * and by stage-wise tests. */
 int b2_stage(const b2_model* m, b2_data* d, int stage, int do_integrate, void* stream);
 
 /* mjwarp.reset_data(m, d, reset=mask): worlds with mask[w] != 0 (bool bytes)

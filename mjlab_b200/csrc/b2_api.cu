@@ -22,7 +22,7 @@ static_assert(sizeof(KEnv) == sizeof(b2_env), "KEnv must mirror b2_env");
 #endif
 #define B2_NCAND_MAX 256
 #ifndef B2_SOLVE_MINB
-#define B2_SOLVE_MINB 5
+#define B2_SOLVE_MINB 8
 #endif
 
 static char g_err[512] = "";
@@ -47,15 +47,32 @@ __global__ void __launch_bounds__(B2_WPB * 32) k_smooth(const KModel m, const KD
   smooth_world(m, d, L, ncand_max, w, smem + (size_t)warp * L.total);
 }
 
-__global__ void __launch_bounds__(B2_WPB * 32, B2_SOLVE_MINB) k_solve(const KModel m, const KData d, const SolveSmem L, int do_integrate, const unsigned char* mask, const int* gate) {
+__global__ void __launch_bounds__(B2_WPB * 32, B2_SOLVE_MINB) k_solve(const KModel m, const KData d, const SolveSmem L, const unsigned char* mask, const int* gate) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  real* smem = reinterpret_cast<real*>(smem_raw);
+  // [fixed part of world 0 | ... | fixed part of world B2_WPB-1 | row arena | arena control words]
+  real* arena = smem + (size_t)B2_WPB * L.fixed_total;
+  int* actl = reinterpret_cast<int*>(arena + L.arena_cap);
+  if (threadIdx.x == 0) { actl[0] = 0; actl[1] = 0; }
+  __syncthreads();
+  int warp = threadIdx.x >> 5;
+  int w = blockIdx.x * B2_WPB + warp;
+  bool run = w < d.nworld && !(gate && *gate == 0) && !(mask && !mask[w]);
+  if (run) solve_world(m, d, L, w, smem + (size_t)warp * L.fixed_total, arena, actl);
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) { __threadfence_block(); atomicAdd(&actl[1], 1); }  // releases a world waiting for arena space
+}
+
+#define B2_POST_WPB 4
+__global__ void __launch_bounds__(B2_POST_WPB * 32) k_post(const KModel m, const KData d, const PostSmem L, int do_integrate, const unsigned char* mask, const int* gate) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   real* smem = reinterpret_cast<real*>(smem_raw);
   int warp = threadIdx.x >> 5;
-  int w = blockIdx.x * B2_WPB + warp;
+  int w = blockIdx.x * B2_POST_WPB + warp;
   if (w >= d.nworld) return;
   if (gate && *gate == 0) return;
   if (mask && !mask[w]) return;
-  solve_world(m, d, L, w, smem + (size_t)warp * L.total, do_integrate);
+  post_world(m, d, L, w, smem + (size_t)warp * L.total, do_integrate);
 }
 
 // masked reset, one warp per world
@@ -74,27 +91,31 @@ __global__ void k_repeat_rows(float* dst, const float* src, int row_len, long lo
 struct Plan {
   SmoothSmem ls;
   SolveSmem lv;
-  size_t smem_smooth, smem_solve;
+  PostSmem lp;
+  size_t smem_smooth, smem_solve, smem_post;
 };
+
+static_assert(B2_WPB <= 2, "the arena hand-over in k_solve assumes at most two worlds per CTA");
 
 static int make_plan(const b2_model* m, const b2_data* d, Plan* p) {
   p->ls = smooth_smem_layout(m->nq, m->nv, m->nu, m->nbody, m->njnt, B2_NCAND_MAX);
-  // true upper bounds on rows / runs, so shared memory is not sized by a generous njmax hint
-  int rows_cap = 4 * d->nconmax + 2 * m->nlimited;
-  if (rows_cap > d->njmax) rows_cap = d->njmax;
-  if (rows_cap < 1) rows_cap = 1;
-  int runs_cap = 2 * m->nlimited + d->nconmax + 1;
+  // true upper bounds on rows / runs / pools of ONE world; the arena of a CTA holds one such world, and two worlds
+  // whenever their actual demand fits (the common case: demand is an order of magnitude below the bound)
+  int rows_max = 4 * d->nconmax + 2 * m->nlimited;
+  if (rows_max > d->njmax) rows_max = d->njmax;
+  if (rows_max < 1) rows_max = 1;
+  int runs_max = 2 * m->nlimited + d->nconmax + 1;
   int wpad = m->maxchain | 1;
-  int jpool_cap = rows_cap * wpad;
-  int budget = 2048;
-  if (const char* e = getenv("B200SIM_JPOOL")) budget = atoi(e);
-  if (jpool_cap > budget) jpool_cap = budget;
-  if (jpool_cap > 65535) jpool_cap = 65535;
-  if (jpool_cap < 2 * m->nlimited + wpad * 6) jpool_cap = 2 * m->nlimited + wpad * 6;
-  int dofs_cap = 2 * m->nlimited + d->nconmax * m->maxchain;
-  p->lv = solve_smem_layout(m->nv, rows_cap, runs_cap, d->nconmax > 0 ? d->nconmax : 1, jpool_cap, dofs_cap, m->maxchain);
+  int pool_max = 2 * m->nlimited + 4 * d->nconmax * wpad;
+  if (pool_max > 65535) pool_max = 65535;
+  int dofs_max = 2 * m->nlimited + d->nconmax * m->maxchain;
+  int arena = solve_arena_need(rows_max, runs_max, dofs_max, pool_max, d->nconmax > 0 ? d->nconmax : 1);
+  if (const char* e = getenv("B200SIM_ARENA")) arena = atoi(e);  // experiments: smaller arena = more resident CTAs, rows may drop
+  p->lv = solve_smem_layout(m->nv, rows_max, m->maxchain, arena);
+  p->lp = post_smem_layout(m->nv);
   p->smem_smooth = (size_t)p->ls.total * sizeof(real) * B2_WPB;
-  p->smem_solve = (size_t)p->lv.total * sizeof(real) * B2_WPB;
+  p->smem_solve = ((size_t)p->lv.fixed_total * B2_WPB + p->lv.arena_cap) * sizeof(real) + 16;
+  p->smem_post = (size_t)p->lp.total * sizeof(real) * B2_POST_WPB;
   if (const char* e = getenv("B200SIM_SMEM_PAD")) p->smem_solve += (size_t)atoi(e);  // occupancy experiments only
   return 0;
 }
@@ -120,7 +141,7 @@ int b2_check(const b2_model* m, const b2_data* d) {
   int dev = 0, maxsmem = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return fail("no CUDA device: %s", cudaGetErrorString(cudaGetLastError()));
   cudaDeviceGetAttribute(&maxsmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  if ((int)p.smem_smooth > maxsmem || (int)p.smem_solve > maxsmem)
+  if ((int)p.smem_smooth > maxsmem || (int)p.smem_solve > maxsmem || (int)p.smem_post > maxsmem)
     return fail("shared memory per CTA (%zu / %zu B) exceeds the device limit %d B; lower njmax or model size",
                 p.smem_smooth, p.smem_solve, maxsmem);
   cudaError_t e;
@@ -128,6 +149,8 @@ int b2_check(const b2_model* m, const b2_data* d) {
   if (e != cudaSuccess) return fail("cudaFuncSetAttribute(k_smooth): %s", cudaGetErrorString(e));
   e = cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_solve);
   if (e != cudaSuccess) return fail("cudaFuncSetAttribute(k_solve): %s", cudaGetErrorString(e));
+  e = cudaFuncSetAttribute(k_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_post);
+  if (e != cudaSuccess) return fail("cudaFuncSetAttribute(k_post): %s", cudaGetErrorString(e));
   return 0;
 }
 
@@ -139,8 +162,9 @@ static int run(const b2_model* m, b2_data* d, void* stream, int do_integrate, co
   const KData& kd = *reinterpret_cast<const KData*>(d);
   int grid = (d->nworld + B2_WPB - 1) / B2_WPB;
   k_smooth<<<grid, B2_WPB * 32, p.smem_smooth, st>>>(km, kd, p.ls, B2_NCAND_MAX, mask, gate);
-  k_solve<<<grid, B2_WPB * 32, p.smem_solve, st>>>(km, kd, p.lv, do_integrate, mask, gate);
-  g_launches += 2;
+  k_solve<<<grid, B2_WPB * 32, p.smem_solve, st>>>(km, kd, p.lv, mask, gate);
+  k_post<<<(d->nworld + B2_POST_WPB - 1) / B2_POST_WPB, B2_POST_WPB * 32, p.smem_post, st>>>(km, kd, p.lp, do_integrate, mask, gate);
+  g_launches += 3;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail("launch failed: %s", cudaGetErrorString(e));
   return 0;
@@ -154,7 +178,8 @@ int b2_stage(const b2_model* m, b2_data* d, int stage, int do_integrate, void* s
   const KData& kd = *reinterpret_cast<const KData*>(d);
   int grid = (d->nworld + B2_WPB - 1) / B2_WPB;
   if (stage == 0) k_smooth<<<grid, B2_WPB * 32, p.smem_smooth, st>>>(km, kd, p.ls, B2_NCAND_MAX, nullptr, nullptr);
-  else if (stage == 1) k_solve<<<grid, B2_WPB * 32, p.smem_solve, st>>>(km, kd, p.lv, do_integrate, nullptr, nullptr);
+  else if (stage == 1) k_solve<<<grid, B2_WPB * 32, p.smem_solve, st>>>(km, kd, p.lv, nullptr, nullptr);
+  else if (stage == 2) k_post<<<(d->nworld + B2_POST_WPB - 1) / B2_POST_WPB, B2_POST_WPB * 32, p.smem_post, st>>>(km, kd, p.lp, do_integrate, nullptr, nullptr);
   else return fail("unknown stage %d", stage);
   g_launches += 1;
   cudaError_t e = cudaGetLastError();

@@ -25,6 +25,7 @@ typedef B2_REAL real;
 #define B2_DEV static inline
 #define B2_DEVN static
 #define B2_UNROLL1
+#define B2_UNROLL_HOT
 #define B2_LANE 0
 #define B2_NLANE 1
 #define B2_WSYNC() ((void)0)
@@ -44,6 +45,14 @@ B2_DEV real b2_rsqrt(real x) { return (real)1 / sqrt(x); }
 // bound (ncu: stall_no_instruction), so hot code is kept small enough for the instruction caches.
 #define B2_DEVN static __device__ __noinline__
 #define B2_UNROLL1 _Pragma("unroll 1")
+// hottest inner loops only: a small unroll factor buys instruction-level parallelism (loads of the next iteration issue
+// under the FMAs of the current one); B2_HOT_UNROLL is a build-time knob for the tuning experiments in DESIGN.md
+#ifndef B2_HOT_UNROLL
+#define B2_HOT_UNROLL 2
+#endif
+#define B2_PRAGMA_(x) _Pragma(#x)
+#define B2_PRAGMA(x) B2_PRAGMA_(x)
+#define B2_UNROLL_HOT B2_PRAGMA(unroll B2_HOT_UNROLL)
 #define B2_LANE ((int)(threadIdx.x & 31))
 #define B2_NLANE 32
 #define B2_WSYNC() __syncwarp()
@@ -228,7 +237,7 @@ B2_DEVN void chol_factor(real* A, int n, int ld, real* invd, real* x) {  // @reg
         s = ri[j];
 #ifndef B2_HOSTEMU
         real s2 = 0;
-        B2_UNROLL1
+        B2_UNROLL_HOT
         for (int k = 0; k < j0; k += 4) {
           float4 a = *reinterpret_cast<const float4*>(ri + k);
           float4 b = *reinterpret_cast<const float4*>(rj + k);
@@ -252,6 +261,33 @@ B2_DEVN void chol_factor(real* A, int n, int ld, real* invd, real* x) {  // @reg
       else if (i == n && x) x[j] = s * inv;
     }
   }
+  B2_WSYNC();
+}
+
+// x <- L^-1 x (forward substitution) for a factor that is already in place.
+B2_DEVN void chol_forwardsolve(const real* L, int n, int ld, const real* invd, real* x) {
+#ifdef B2_HOSTEMU
+  for (int k = 0; k < n; ++k) {
+    real s = x[k];
+    for (int i = 0; i < k; ++i) s -= L[k * ld + i] * x[i];
+    x[k] = s * invd[k];
+  }
+#else
+  const int lane = B2_LANE;
+  const int row0 = lane, row1 = lane + 32;
+  real x0 = row0 < n ? x[row0] : (real)0;
+  real x1 = row1 < n ? x[row1] : (real)0;
+  B2_UNROLL1
+  for (int k = 0; k < n; ++k) {
+    real l0 = row0 > k && row0 < n ? L[row0 * ld + k] : (real)0;
+    real l1 = row1 > k && row1 < n ? L[row1 * ld + k] : (real)0;
+    real xk = b2_shfl(k < 32 ? x0 : x1, k & 31) * invd[k];
+    if (row0 == k) x0 = xk; else x0 = fmaf(-l0, xk, x0);
+    if (row1 == k) x1 = xk; else x1 = fmaf(-l1, xk, x1);
+  }
+  if (row0 < n) x[row0] = x0;
+  if (row1 < n) x[row1] = x1;
+#endif
   B2_WSYNC();
 }
 

@@ -18,36 +18,39 @@
 // J^T D J is accumulated run by run over w*(w+1)/2 dof pairs instead of nv*(nv+1)/2
 // (G1 foot-ground contact: w = 12 of nv = 35).
 struct SolveSmem {
-  int M, H, cdof, qvel, qacc, Ma, grad, search, Mv, qfs, qas, qfc, tmp, invd;
-  int D, aref, jar, jv, rowinfo, rowsrc, runinfo, rundofs, cinfo, jpool, pairtab;
-  int rows_cap, runs_cap, jpool_cap, dofs_cap, total;
+  int H, cdof, qvel, qacc, Ma, grad, search, Mv, qfs, qas, qfc, tmp, invd, pairtab, actmask;  // fixed part, per world
+  int fixed_total;  // reals per world
+  int arena_cap;    // reals of the row arena shared by the worlds of one CTA (>= the demand of one worst-case world)
+  int rows_max;     // bound on constraint rows per world
 };
 
-static inline SolveSmem solve_smem_layout(int nv, int rows_cap, int runs_cap, int nconmax, int jpool_cap, int dofs_cap, int maxchain) {
+// Row storage is carved from an arena per CTA by actual demand (median world: ~30 rows; worst case: ~200), so the
+// resident warps per SM are set by what worlds typically need, not by the worst case.  Arena demand in reals:
+//   D, frc/aref, jar, jv/wgt, rowinfo [rows each] | runinfo [2 runs] | rundofs [dofs bytes] | cinfo [4 ncon] | jpool [pool]
+static inline
+#ifndef B2_HOSTEMU
+__host__ __device__
+#endif
+int solve_arena_need(int rows, int runs, int dofs, int pool, int ncon) {
+  auto r4 = [](int n) { return (n + 3) & ~3; };
+  int cd = r4(2 * r4(rows));
+  return cd + 3 * r4(rows) + r4(2 * runs) + r4((dofs + 3) / 4) + r4(4 * ncon) + r4(pool);
+}
+
+static inline SolveSmem solve_smem_layout(int nv, int rows_max, int maxchain, int arena_cap) {
   SolveSmem s;
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
-  s.M = -1;  // qM stays in HBM/L2 (read coalesced through its symmetry), not staged
+  // qM stays in HBM/L2 (read coalesced through its symmetry), not staged
   s.H = take(nv * b2_ld(nv));
+  s.cdof = s.H;  // cdof is only read while the Jacobian rows are assembled, H is first written in the Newton loop
   s.qvel = take(nv); s.qacc = take(nv); s.Ma = take(nv); s.grad = take(nv); s.search = take(nv); s.Mv = take(nv);
   s.qfs = take(nv); s.qas = take(nv); s.qfc = take(nv); s.tmp = take(nv); s.invd = take(64);  // 1 / diag(L)
-  // D and aref are first written after the Jacobian rows are assembled; cdof is only read
-  // during that assembly, so the two share storage (needs 2*rows_cap >= 6*nv, else padded).
-  int dd = 2 * ((rows_cap + 3) & ~3);
-  int need = (6 * nv + 3) & ~3;
-  s.D = take(dd > need ? dd : need);
-  s.aref = s.D + ((rows_cap + 3) & ~3);
-  s.cdof = s.D;
-  s.jar = take(rows_cap); s.jv = take(rows_cap);
-  s.rowsrc = s.jv;                   // int: contact id, or -(jnt+1); dead before the line search writes jv
-  s.rowinfo = take(rows_cap);        // int: pool offset | run << 16
-  s.runinfo = take(2 * runs_cap);    // int2: (dofoff | w << 16), (row0 | nrow << 16)
-  s.rundofs = take((dofs_cap + 3) / 4);  // bytes
-  s.cinfo = take(4 * nconmax);       // int4 per contact: adr, dim, body1, body2
-  s.jpool = take(jpool_cap);
   s.pairtab = take((maxchain * (maxchain + 1) / 2 + 1) / 2);  // ushort (a << 8 | b) per lower-triangle pair index
-  s.rows_cap = rows_cap; s.runs_cap = runs_cap; s.jpool_cap = jpool_cap; s.dofs_cap = dofs_cap;
-  s.total = o;
+  s.actmask = take((rows_max + 31) / 32);  // bit r: row r was active at the last Hessian factorisation
+  s.fixed_total = o;
+  s.arena_cap = arena_cap;
+  s.rows_max = rows_max;
   return s;
 }
 
@@ -93,7 +96,7 @@ B2_DEVN void rows_dot(const real* jpool, const int* rowinfo, const int* runinfo,
     const real* jr = jpool + off;
     const unsigned char* dl = rundofs + dofoff;
     real acc = 0;
-    B2_UNROLL1
+    B2_UNROLL_HOT
     for (int a = 0; a < wd; ++a) acc += jr[a] * x[dl[a]];
     y[r] = sub ? acc - sub[r] : acc;
   }
@@ -174,15 +177,13 @@ B2_DEVN real linesearch(real q0g, real q1g, real q2g, real snorm, real tolerance
 }
 
 // contact-frame force [normal, t1, t2] decoded from the pyramid edge forces
-B2_DEV void contact_force(real* out, int adr, int dim, const real* fri, const real* D, const real* jar) {  // @region sensor_helpers
+B2_DEV void contact_force(real* out, int adr, int dim, const real* fri, const real* efc_force) {  // @region sensor_helpers
   out[0] = out[1] = out[2] = 0;
   if (adr < 0) return;
-  if (dim == 1) { real x = jar[adr]; out[0] = x < 0 ? -D[adr] * x : 0; return; }
-  B2_UNROLL1
+  if (dim == 1) { out[0] = efc_force[adr]; return; }
   for (int k = 1; k < dim; ++k) {
     int r = adr + 2 * (k - 1);
-    real x1 = jar[r], x2 = jar[r + 1];
-    real f1 = x1 < 0 ? -D[r] * x1 : 0, f2 = x2 < 0 ? -D[r + 1] * x2 : 0;
+    real f1 = efc_force[r], f2 = efc_force[r + 1];
     out[0] += f1 + f2;
     if (k < 3) out[k] = (f1 - f2) * fri[k - 1];
   }
@@ -225,25 +226,17 @@ B2_DEV void mat2quat(real* q, const real* R) {
 // ---------------------------------------------------------------------------
 // Stage 2 for world w.
 // ---------------------------------------------------------------------------
-B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int w, real* sm, int do_integrate) {  // @region setup_loads
+// `sm`: this world's fixed part; `arena` / `actl`: the CTA's row arena and its control words (actl[0] reals handed out,
+// actl[1] worlds of the CTA that are done).
+B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int w, real* sm, real* arena, int* actl) {  // @region setup_loads
   const int nv = m.nv, nb = m.nbody, nq = m.nq, nu = m.nu, njmax = d.njmax, nconmax = d.nconmax;
   real* H = sm + L.H; real* cdof = sm + L.cdof;
   real* qvel = sm + L.qvel; real* qacc = sm + L.qacc; real* Ma = sm + L.Ma; real* grad = sm + L.grad;
   real* search = sm + L.search; real* Mv = sm + L.Mv; real* qfs = sm + L.qfs; real* qas = sm + L.qas;
   real* qfc = sm + L.qfc; real* tmp = sm + L.tmp; real* invd = sm + L.invd;
-  real* D = sm + L.D; real* aref = sm + L.aref; real* jar = sm + L.jar; real* jv = sm + L.jv;
-  real* wgt = jv;  // D*active per row; consumed by the Hessian pass before the line search reuses jv
-  int* rowinfo = (int*)(sm + L.rowinfo);
-  int* rowsrc = (int*)(sm + L.rowsrc);
-  int* runinfo = (int*)(sm + L.runinfo);
-  unsigned char* rundofs = (unsigned char*)(sm + L.rundofs);
-  int* cinfo = (int*)(sm + L.cinfo);
-  real* jpool = sm + L.jpool;
   unsigned short* pairtab = (unsigned short*)(sm + L.pairtab);
-  real* frc = aref;  // -D*active*jar per row; aref itself is dead once jar has been initialised
-  const int rows_cap = L.rows_cap < njmax ? L.rows_cap : njmax;
+  unsigned* actmask = (unsigned*)(sm + L.actmask);
   const int ld = b2_ld(nv);
-
   const int* body_parent = MI(B2_MI_BODY_PARENTID);
   const int* body_root = MI(B2_MI_BODY_ROOTID);
   const int* dofmask = MI(B2_MI_BODY_DOFMASK);
@@ -274,11 +267,84 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
   }
   B2_WSYNC();
 
+  // ---- arena demand of this world (counts only; the passes below fill the arrays) --------------------------  // @region arena_alloc
+  const int ncon = d.di[B2_DI_NCON][w];
+  const real* c_dist = d.df[B2_DF_CONTACT_DIST] + (size_t)w * nconmax;
+  const real* c_inc = d.df[B2_DF_CONTACT_INCLUDEMARGIN] + (size_t)w * nconmax;
+  const int* c_geom = d.di[B2_DI_CONTACT_GEOM] + (size_t)w * nconmax * 2;
+  const int* c_dim = d.di[B2_DI_CONTACT_DIM] + (size_t)w * nconmax;
+  const real* jnt_range = MF(B2_MF_JNT_RANGE);
+  const real* jnt_margin = MF(B2_MF_JNT_MARGIN);
+  int rows_cap, runs_cap, dofs_cap, jpool_cap;
+  {
+    int nlim = 0, crow = 0, ckept = 0, cdofs = 0, cpool = 0;
+    B2_UNROLL1
+    for (int base = 0; base < 2 * m.njnt; base += B2_NLANE) {
+      int s = base + B2_LANE;
+      bool on = false;
+      int j = s >> 1, side = s & 1;
+      if (s < 2 * m.njnt && jnt_limited[j] && (jnt_type[j] == B2_JNT_HINGE || jnt_type[j] == B2_JNT_SLIDE)) {
+        real q = g_qpos[jnt_qposadr[j]];
+        real dist = side == 0 ? q - jnt_range[2 * j] : jnt_range[2 * j + 1] - q;
+        on = dist < jnt_margin[j];
+      }
+      nlim += b2_popc(b2_ballot(on));
+    }
+    B2_UNROLL1
+    for (int c = B2_LANE; c < ncon; c += B2_NLANE) {
+      if (c_dist[c] < c_inc[c]) {
+        int nrow = c_dim[c] == 1 ? 1 : 2 * (c_dim[c] - 1);
+        int b1 = geom_body[c_geom[2 * c]], b2 = geom_body[c_geom[2 * c + 1]];
+        int wd = b2_popc((unsigned)(dofmask[2 * b1] | dofmask[2 * b2])) + b2_popc((unsigned)(dofmask[2 * b1 + 1] | dofmask[2 * b2 + 1]));
+        crow += nrow; ckept += 1; cdofs += wd; cpool += nrow * (wd | 1);
+      }
+    }
+    crow = b2_wsum_i(crow); ckept = b2_wsum_i(ckept); cdofs = b2_wsum_i(cdofs); cpool = b2_wsum_i(cpool);
+    rows_cap = nlim + crow;
+    if (rows_cap > njmax) rows_cap = njmax;
+    if (rows_cap > L.rows_max) rows_cap = L.rows_max;
+    if (rows_cap < 1) rows_cap = 1;
+    runs_cap = nlim + ckept + 1;          // every kept contact could start a run (upper bound)
+    dofs_cap = nlim + cdofs;
+    jpool_cap = nlim + cpool;
+    if (jpool_cap > 65535) jpool_cap = 65535;
+  }
+  int need = solve_arena_need(rows_cap, runs_cap, dofs_cap, jpool_cap, ncon > 0 ? ncon : 1);
+  if (need > L.arena_cap) {  // cannot happen when the arena holds one worst-case world; keep the pools inside it regardless
+    jpool_cap -= need - L.arena_cap;
+    if (jpool_cap < 0) jpool_cap = 0;
+    need = solve_arena_need(rows_cap, runs_cap, dofs_cap, jpool_cap, ncon > 0 ? ncon : 1);
+  }
+  int aoff = 0;
+#ifndef B2_HOSTEMU
+  if (B2_LANE == 0) {
+    aoff = atomicAdd(&actl[0], need);
+    if (aoff + need > L.arena_cap) {
+      // no room next to the CTA's other world: wait until it is done, then use the arena from its start
+      while (atomicAdd(&actl[1], 0) == 0) __nanosleep(200);
+      aoff = 0;
+    }
+  }
+  aoff = __shfl_sync(0xffffffffu, aoff, 0);
+#endif
+  real* D; real* aref; real* jar; real* jv; int* rowinfo; int* runinfo; unsigned char* rundofs; int* cinfo; real* jpool;
+  {
+    real* a = arena + aoff;
+    const int r4 = (rows_cap + 3) & ~3;
+    D = a; aref = a + r4; a += (2 * r4 + 3) & ~3;
+    jar = a; a += r4; jv = a; a += r4; rowinfo = (int*)a; a += r4;
+    runinfo = (int*)a; a += (2 * runs_cap + 3) & ~3;
+    rundofs = (unsigned char*)a; a += ((dofs_cap + 3) / 4 + 3) & ~3;
+    cinfo = (int*)a; a += (4 * (ncon > 0 ? ncon : 1) + 3) & ~3;
+    jpool = a;
+  }
+  real* wgt = jv;          // D*active per row; consumed by the Hessian pass before the line search reuses jv
+  int* rowsrc = (int*)jv;  // contact id, or -(jnt+1); dead before the line search writes jv
+  real* frc = aref;        // -D*active*jar per row; aref itself is dead once jar has been initialised
+
   // ---- joint-limit rows (ordered: joint, lower then upper); each is its own run of width 1 ----  // @region limit_rows
   int nefc = 0;
   {
-    const real* jnt_range = MF(B2_MF_JNT_RANGE);
-    const real* jnt_margin = MF(B2_MF_JNT_MARGIN);
     B2_UNROLL1
     for (int base = 0; base < 2 * m.njnt; base += B2_NLANE) {
       int s = base + B2_LANE;
@@ -319,16 +385,11 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
   const int nl = nefc;
 
   // ---- contact rows ---------------------------------------------------------------------------  // @region contact_rows
-  const int ncon = d.di[B2_DI_NCON][w];
-  const real* c_dist = d.df[B2_DF_CONTACT_DIST] + (size_t)w * nconmax;
   const real* c_pos = d.df[B2_DF_CONTACT_POS] + (size_t)w * nconmax * 3;
   const real* c_frame = d.df[B2_DF_CONTACT_FRAME] + (size_t)w * nconmax * 9;
-  const real* c_inc = d.df[B2_DF_CONTACT_INCLUDEMARGIN] + (size_t)w * nconmax;
   const real* c_fri = d.df[B2_DF_CONTACT_FRICTION] + (size_t)w * nconmax * 5;
   const real* c_solref = d.df[B2_DF_CONTACT_SOLREF] + (size_t)w * nconmax * 2;
   const real* c_solimp = d.df[B2_DF_CONTACT_SOLIMP] + (size_t)w * nconmax * 5;
-  const int* c_geom = d.di[B2_DI_CONTACT_GEOM] + (size_t)w * nconmax * 2;
-  const int* c_dim = d.di[B2_DI_CONTACT_DIM] + (size_t)w * nconmax;
   int* c_adr = d.di[B2_DI_CONTACT_EFC_ADDRESS] + (size_t)w * nconmax;
   int ndrop = 0;
   {
@@ -383,7 +444,7 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
       if (!overflow && (b1 != pb1 || b2 != pb2)) {
         unsigned lo = lo1 | lo2, hi = hi1 | hi2;
         int cl = b2_popc(lo), wd = cl + b2_popc(hi);
-        if (dofcount + wd > L.dofs_cap || nrun >= L.runs_cap) overflow = true;
+        if (dofcount + wd > dofs_cap || nrun >= runs_cap) overflow = true;
         else {
           if (cur_run >= 0 && B2_LANE == 0) runinfo[2 * cur_run + 1] = cur_row0 | (cur_nrow << 16);
 #ifndef B2_HOSTEMU
@@ -400,7 +461,7 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
         }
       }
       const int wpad = cur_w | 1;  // odd row stride: rows of a run hit distinct banks
-      if (!overflow && pooloff + nrow * wpad > L.jpool_cap) overflow = true;
+      if (!overflow && pooloff + nrow * wpad > jpool_cap) overflow = true;
       if (overflow) {
         // shared-memory pools exhausted: this and all later contacts lose their rows
         if (B2_LANE == 0) { cinfo[4 * c] = -1; }
@@ -579,14 +640,33 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
     B2_UNROLL1
     for (int it = 0;; ++it) {
       // -- constraint update, part 1: row weights, cost, qfrc_constraint, gradient  // @region newton_update
+      // The Hessian M + J^T diag(D*active) J only depends on WHICH rows are active: when the active set equals the one
+      // of the last factorisation, the factor still in H is reused (same result, no copy / J^T D J / Cholesky).
       real c1 = 0;
+      bool same_set = it > 0;
       B2_UNROLL1
-      for (int r = B2_LANE; r < nefc; r += B2_NLANE) {
-        real x = jar[r];
-        real wr = x < 0 ? D[r] : (real)0;
-        wgt[r] = wr;
-        frc[r] = -wr * x;
-        c1 += (real)0.5 * wr * x * x;
+      for (int base = 0; base < nefc; base += B2_NLANE) {
+        int r = base + B2_LANE;
+        bool act = false;
+        if (r < nefc) {
+          real x = jar[r];
+          act = x < 0;
+          real wr = act ? D[r] : (real)0;
+          wgt[r] = wr;
+          frc[r] = -wr * x;
+          c1 += (real)0.5 * wr * x * x;
+        }
+        unsigned bal = b2_ballot(act);
+#ifdef B2_HOSTEMU
+        unsigned* slot = actmask + (base >> 5);
+        unsigned prev = (*slot >> (base & 31)) & 1u;
+        if (it == 0 || prev != bal) same_set = false;
+        *slot = (*slot & ~(1u << (base & 31))) | (bal << (base & 31));
+#else
+        if (it == 0 || actmask[base >> 5] != bal) same_set = false;
+        B2_WSYNC();
+        if (B2_LANE == 0) actmask[base >> 5] = bal;
+#endif
       }
       real g1 = 0;
       B2_UNROLL1
@@ -615,7 +695,7 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
         B2_UNROLL1
         for (int a = B2_LANE; a < wd; a += B2_NLANE) {
           real ff = 0;
-          B2_UNROLL1
+          B2_UNROLL_HOT
           for (int q = 0; q < nrow; ++q) ff = fma(jpool[off0 + q * wpad + a], frc[row0 + q], ff);
           qfc[dl[a]] += ff;
         }
@@ -629,6 +709,9 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
         gn = sqrt(b2_wsum(gn));
         real improvement = scale * (cost - newcost);
         real floor_ = fmax(tolerance, 8 * eps_real * scale * fabs(newcost));
+#ifdef B2_TRACE
+        printf("w%d it%d cost %.9g new %.9g impr %.3g floor %.3g gn*scale %.3g same %d nefc %d\n", w, it, (double)cost, (double)newcost, (double)improvement, (double)floor_, (double)(scale * gn), (int)same_set, nefc);
+#endif
         cost = newcost;
         if (improvement < floor_ || scale * gn < tolerance) break;
       } else {
@@ -636,6 +719,10 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
       }
       if (it >= m.iterations) break;
       // -- part 2: H = M + J^T diag(w) J, only when another Newton step will be taken  // @region hessian
+      if (same_set) {
+        chol_forwardsolve(H, nv, ld, invd, tmp);
+        chol_backsolve(H, nv, ld, invd, tmp);
+      } else {
       copy_g2s(H, M, nv * ld);
       if (nl > 0) {
         B2_UNROLL1
@@ -678,6 +765,7 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
         B2_WSYNC();
       }
       spd_factor_solve(H, nv, ld, tmp, invd);  // @region factor_call
+      }
       B2_UNROLL1
       for (int i = B2_LANE; i < nv; i += B2_NLANE) search[i] = -tmp[i];
       B2_WSYNC();
@@ -709,6 +797,65 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
   B2_UNROLL1
   for (int i = B2_LANE; i < nv; i += B2_NLANE) { g_qacc[i] = qacc[i]; g_qfc[i] = qfc[i]; }
   if (B2_LANE == 0) d.di[B2_DI_SOLVER_NITER][w] = niter;
+  B2_WSYNC();
+
+}
+
+// Shared-memory layout of the post stage (sensors + integration): the integrator's matrix and a few vectors.
+struct PostSmem {
+  int H, qvel, qacc, qfs, qfc, tmp, invd, total;
+};
+static inline PostSmem post_smem_layout(int nv) {
+  PostSmem s;
+  int o = 0;
+  auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
+  s.H = take(nv * b2_ld(nv));
+  s.qvel = take(nv); s.qacc = take(nv); s.qfs = take(nv); s.qfc = take(nv); s.tmp = take(nv); s.invd = take(64);
+  s.total = o;
+  return s;
+}
+
+// ---------------------------------------------------------------------------
+// Stage 3 for world w: sensors, then integration.  A kernel of its own so that the Newton loop of stage 2 shares the
+// instruction cache with nothing else (profiles/: k_solve was instruction-fetch bound while this code lived in it).
+// Inputs come from the global outputs of stages 1-2 (qacc, qfrc_*, efc_force, contact efc addresses).
+// ---------------------------------------------------------------------------
+B2_DEV void post_world(const KModel& m, const KData& d, const PostSmem& L, int w, real* sm, int do_integrate) {
+  const int nv = m.nv, nb = m.nbody, nq = m.nq, nu = m.nu, njmax = d.njmax, nconmax = d.nconmax;
+  real* H = sm + L.H; real* qvel = sm + L.qvel; real* qacc = sm + L.qacc; real* qfs = sm + L.qfs; real* qfc = sm + L.qfc;
+  real* tmp = sm + L.tmp; real* invd = sm + L.invd;
+  const int ld = b2_ld(nv);
+  const int* body_parent = MI(B2_MI_BODY_PARENTID);
+  const int* body_root = MI(B2_MI_BODY_ROOTID);
+  const int* geom_body = MI(B2_MI_GEOM_BODYID);
+  const int* jnt_type = MI(B2_MI_JNT_TYPE);
+  const int* jnt_qposadr = MI(B2_MI_JNT_QPOSADR);
+  const int* jnt_dofadr = MI(B2_MI_JNT_DOFADR);
+  const real timestep = MF(B2_MF_OPT_TIMESTEP)[0];
+  real* g_qpos = d.df[B2_DF_QPOS] + (size_t)w * nq;
+  real* g_qvel = d.df[B2_DF_QVEL] + (size_t)w * nv;
+  const real* g_scom = d.df[B2_DF_SUBTREE_COM] + (size_t)w * nb * 3;
+  const real* g_cdof = d.df[B2_DF_CDOF] + (size_t)w * nv * 6;
+  const real* M = d.df[B2_DF_QM] + (size_t)w * nv * b2_ld(nv);
+  const int ncon = d.di[B2_DI_NCON][w];
+  const int nefc = d.di[B2_DI_NEFC][w];
+  const real* c_dist = d.df[B2_DF_CONTACT_DIST] + (size_t)w * nconmax;
+  const real* c_pos = d.df[B2_DF_CONTACT_POS] + (size_t)w * nconmax * 3;
+  const real* c_frame = d.df[B2_DF_CONTACT_FRAME] + (size_t)w * nconmax * 9;
+  const real* c_fri = d.df[B2_DF_CONTACT_FRICTION] + (size_t)w * nconmax * 5;
+  const int* c_geom = d.di[B2_DI_CONTACT_GEOM] + (size_t)w * nconmax * 2;
+  const int* c_dim = d.di[B2_DI_CONTACT_DIM] + (size_t)w * nconmax;
+  const int* c_adr = d.di[B2_DI_CONTACT_EFC_ADDRESS] + (size_t)w * nconmax;
+  const real* efc_force = d.df[B2_DF_EFC_FORCE] + (size_t)w * njmax;
+  (void)nu; (void)c_dist;
+  B2_UNROLL1
+  for (int i = B2_LANE; i < nv; i += B2_NLANE) {
+    size_t o = (size_t)w * nv + i;
+    qvel[i] = g_qvel[i];
+    qacc[i] = d.df[B2_DF_QACC][o];
+    qfs[i] = d.df[B2_DF_QFRC_SMOOTH][o];
+    qfc[i] = d.df[B2_DF_QFRC_CONSTRAINT][o];
+  }
   B2_WSYNC();
 
   // ---- sensors -------------------------------------------------------------------------  // @region sensors
@@ -901,7 +1048,7 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
           ++nfound;
           if (reduce == 3 && (bits & 2)) {
             real fc[3], fg[3];
-            contact_force(fc, nefc > 0 ? c_adr[c] : -1, c_dim[c], c_fri + 5 * c, D, jar);
+            contact_force(fc, nefc > 0 ? c_adr[c] : -1, c_dim[c], c_fri + 5 * c, efc_force);
             mulmTv3(fg, c_frame + 9 * c, fc);
             net[0] += sgn * fg[0]; net[1] += sgn * fg[1]; net[2] += sgn * fg[2];
           }
@@ -930,7 +1077,7 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
                 else if (reduce == 1) key = c_dist[c];
                 else {
                   real fc[3];
-                  contact_force(fc, nefc > 0 ? c_adr[c] : -1, c_dim[c], c_fri + 5 * c, D, jar);
+                  contact_force(fc, nefc > 0 ? c_adr[c] : -1, c_dim[c], c_fri + 5 * c, efc_force);
                   key = -sqrt(dot3(fc, fc));
                 }
                 // strict ordering by (key, c) to enumerate matches in sorted order
@@ -945,7 +1092,7 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
               if (bits & 1) out[p++] = (real)nfound;
               if (bits & 2) {
                 real fc[3];
-                contact_force(fc, nefc > 0 ? c_adr[c] : -1, c_dim[c], c_fri + 5 * c, D, jar);
+                contact_force(fc, nefc > 0 ? c_adr[c] : -1, c_dim[c], c_fri + 5 * c, efc_force);
                 out[p] = picksgn * fc[0]; out[p + 1] = picksgn * fc[1]; out[p + 2] = picksgn * fc[2]; p += 3;
               }
               if (bits & 4) p += 3;

@@ -324,8 +324,8 @@ class ManagerBasedRlEnv:
     torch.cuda.current_stream(self._dev).wait_stream(side)
     self._graph = g
 
-  #: kernels enqueued per env step: action, decimation x (smooth, solve, airtime), post + gate, forward (2), obs, log
-  launches_per_step = property(lambda self: 1 + 3 * self.cfg.decimation + 2 + 2 + 1 + 1)
+  #: kernels enqueued per env step: action, decimation x (smooth, solve, post, airtime), env_post + gate, forward (3), obs, log
+  launches_per_step = property(lambda self: 1 + 4 * self.cfg.decimation + 2 + 3 + 1 + 1)
 
   # ---- API ------------------------------------------------------------------------------------------
   def seed(self, seed: int = -1) -> int:

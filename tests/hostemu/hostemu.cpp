@@ -25,17 +25,21 @@ void b2h_set_jpool_budget(int b) { jpool_budget = b; }
 
 int b2h_run(const KModel* m, KData* d, int do_integrate, int world_lo, int world_hi) {
   SmoothSmem ls = smooth_smem_layout(m->nq, m->nv, m->nu, m->nbody, m->njnt, 256);
-  int rows_cap = 4 * d->nconmax + 2 * m->nlimited;
-  if (rows_cap > d->njmax) rows_cap = d->njmax;
+  int rows_max = 4 * d->nconmax + 2 * m->nlimited;
+  if (rows_max > d->njmax) rows_max = d->njmax;
   int wpad = m->maxchain | 1;
-  int jpool_cap = rows_cap * wpad;
-  if (jpool_budget > 0 && jpool_cap > jpool_budget) jpool_cap = jpool_budget;
-  SolveSmem lv = solve_smem_layout(m->nv, rows_cap, 2 * m->nlimited + d->nconmax + 1, d->nconmax > 0 ? d->nconmax : 1,
-                                   jpool_cap, 2 * m->nlimited + d->nconmax * m->maxchain, m->maxchain);
-  std::vector<real> a(ls.total), b(lv.total);
+  int pool_max = 2 * m->nlimited + 4 * d->nconmax * wpad;
+  int arena = solve_arena_need(rows_max, 2 * m->nlimited + d->nconmax + 1, 2 * m->nlimited + d->nconmax * m->maxchain, pool_max,
+                               d->nconmax > 0 ? d->nconmax : 1);
+  if (jpool_budget > 0) arena = jpool_budget;  // tests of the overflow path: an arena smaller than the worst case
+  SolveSmem lv = solve_smem_layout(m->nv, rows_max, m->maxchain, arena);
+  PostSmem lp = post_smem_layout(m->nv);
+  std::vector<real> a(ls.total), b(lv.fixed_total), ar(arena + 4), c(lp.total);
+  int actl[2] = {0, 0};
   for (int w = world_lo; w < world_hi && w < d->nworld; ++w) {
     smooth_world(*m, *d, ls, 256, w, a.data());
-    solve_world(*m, *d, lv, w, b.data(), do_integrate);
+    solve_world(*m, *d, lv, w, b.data(), ar.data(), actl);
+    post_world(*m, *d, lp, w, c.data(), do_integrate);
   }
   return 0;
 }

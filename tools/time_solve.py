@@ -27,7 +27,7 @@ for _ in range(40):
   env.step(torch.rand(nw, env.vcfg.nj, device="cuda:0", generator=gen) * 2 - 1)
 lib, pm, pd = env._lib, C.byref(env.sim._cm), C.byref(env.sim._cd)
 flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device="cuda:0")
-ts, tv = [], []
+ts, tv, tp = [], [], []
 for k in range(40):
   if k % 4 == 0:
     env._buf["action_in"].copy_(torch.rand(nw, env.vcfg.nj, device="cuda:0", generator=gen) * 2 - 1)
@@ -40,12 +40,16 @@ for k in range(40):
   b.record()
   E.check_call(lib, lib.b2_stage(pm, pd, 1, 1, st))
   c.record()
+  E.check_call(lib, lib.b2_stage(pm, pd, 2, 1, st))
+  c2 = torch.cuda.Event(enable_timing=True)
+  c2.record()
   torch.cuda.synchronize()
   ts.append(a.elapsed_time(b))
   tv.append(b.elapsed_time(c))
+  tp.append(c.elapsed_time(c2))
 d = env.sim.data
 print(f"{os.environ.get('B200SIM_LIB', 'default'):40s} jpool={os.environ.get('B200SIM_JPOOL', '-'):>5s} k_smooth {statistics.mean(ts):.4f} ms  "
-      f"k_solve {statistics.mean(tv):.4f} ms  (min {min(tv):.4f})  nefc {d.nefc.float().mean().item():.1f} niter {d.solver_niter.float().mean().item():.2f} "
+      f"k_solve {statistics.mean(tv):.4f} ms  (min {min(tv):.4f}) k_post {statistics.mean(tp):.4f}  nefc {d.nefc.float().mean().item():.1f} niter {d.solver_niter.float().mean().item():.2f} "
       f"dropped {int(d.nefc_dropped.sum().item())}")
 ne = d.nefc.float()
 q = torch.tensor([0.5, 0.75, 0.9, 0.95, 0.99, 1.0], device=ne.device)
