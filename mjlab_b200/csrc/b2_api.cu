@@ -110,7 +110,17 @@ static int make_plan(const b2_model* m, const b2_data* d, Plan* p) {
   if (pool_max > 65535) pool_max = 65535;
   int dofs_max = 2 * m->nlimited + d->nconmax * m->maxchain;
   int arena = solve_arena_need(rows_max, runs_max, dofs_max, pool_max, d->nconmax > 0 ? d->nconmax : 1);
-  if (const char* e = getenv("B200SIM_ARENA")) arena = atoi(e);  // experiments: smaller arena = more resident CTAs, rows may drop
+  // The strict bound assumes every contact couples the two longest kinematic chains (maxchain); real worlds stay an
+  // order of magnitude below it (G1, random actions: median 30 rows, max 116 of 198).  Cap the arena so that
+  // B2_SOLVE_MINB CTAs stay resident per SM, but never below half the strict bound.  A world beyond the cap loses rows
+  // from the tail of its contact list exactly like njmax truncation does (counted in nefc_dropped).
+  {
+    SolveSmem probe = solve_smem_layout(m->nv, rows_max, m->maxchain, 0);
+    long budget = (233472 / B2_SOLVE_MINB - 1024 - 16 - (long)probe.fixed_total * B2_WPB * (long)sizeof(real)) / (long)sizeof(real);
+    if (budget < arena / 2) budget = arena / 2;
+    if (arena > budget) arena = (int)budget & ~3;
+  }
+  if (const char* e = getenv("B200SIM_ARENA")) arena = atoi(e);  // experiments
   p->lv = solve_smem_layout(m->nv, rows_max, m->maxchain, arena);
   p->lp = post_smem_layout(m->nv);
   p->smem_smooth = (size_t)p->ls.total * sizeof(real) * B2_WPB;
