@@ -192,6 +192,8 @@ enum b2_di {
   B2_DI_CONTACT_EFC_ADDRESS, /* nconmax */
   B2_DI_NCON_DROPPED,      /* 1: contacts dropped because nconmax was reached */
   B2_DI_NEFC_DROPPED,      /* 1: rows dropped because njmax was reached */
+  B2_DI_SOLVE_ORDER,       /* 1: world processed by solver slot w (worlds sorted by contact count, heaviest first, so the
+                              long-running worlds start at once and do not stretch the kernel's tail); internal */
   B2_DI_COUNT
 };
 

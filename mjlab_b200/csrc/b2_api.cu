@@ -56,11 +56,38 @@ __global__ void __launch_bounds__(B2_WPB * 32, B2_SOLVE_MINB) k_solve(const KMod
   if (threadIdx.x == 0) { actl[0] = 0; actl[1] = 0; }
   __syncthreads();
   int warp = threadIdx.x >> 5;
-  int w = blockIdx.x * B2_WPB + warp;
+  int slot = blockIdx.x * B2_WPB + warp;
+  int w = slot < d.nworld ? d.di[B2_DI_SOLVE_ORDER][slot] : d.nworld;
   bool run = w < d.nworld && !(gate && *gate == 0) && !(mask && !mask[w]);
   if (run) solve_world(m, d, L, w, smem + (size_t)warp * L.fixed_total, arena, actl);
   __syncwarp();
   if ((threadIdx.x & 31) == 0) { __threadfence_block(); atomicAdd(&actl[1], 1); }  // releases a world waiting for arena space
+}
+
+// Counting sort of the worlds by contact count, heaviest first (one CTA).  Which solver slot a world lands in has no
+// effect on its results; the atomics only make the order inside a bucket arbitrary.
+#define B2_ORDER_BINS 64
+__global__ void __launch_bounds__(1024) k_order(const KData d) {
+  __shared__ int hist[B2_ORDER_BINS], base[B2_ORDER_BINS];
+  const int* ncon = d.di[B2_DI_NCON];
+  int* order = d.di[B2_DI_SOLVE_ORDER];
+  if (threadIdx.x < B2_ORDER_BINS) hist[threadIdx.x] = 0;
+  __syncthreads();
+  for (int w = threadIdx.x; w < d.nworld; w += blockDim.x) {
+    int k = ncon[w];
+    atomicAdd(&hist[k < B2_ORDER_BINS ? k : B2_ORDER_BINS - 1], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int k = B2_ORDER_BINS - 1; k >= 0; --k) { base[k] = acc; acc += hist[k]; }
+  }
+  __syncthreads();
+  for (int w = threadIdx.x; w < d.nworld; w += blockDim.x) {
+    int k = ncon[w];
+    k = k < B2_ORDER_BINS ? k : B2_ORDER_BINS - 1;
+    order[atomicAdd(&base[k], 1)] = w;
+  }
 }
 
 #define B2_POST_WPB 4
@@ -172,9 +199,10 @@ static int run(const b2_model* m, b2_data* d, void* stream, int do_integrate, co
   const KData& kd = *reinterpret_cast<const KData*>(d);
   int grid = (d->nworld + B2_WPB - 1) / B2_WPB;
   k_smooth<<<grid, B2_WPB * 32, p.smem_smooth, st>>>(km, kd, p.ls, B2_NCAND_MAX, mask, gate);
+  k_order<<<1, 1024, 0, st>>>(kd);
   k_solve<<<grid, B2_WPB * 32, p.smem_solve, st>>>(km, kd, p.lv, mask, gate);
   k_post<<<(d->nworld + B2_POST_WPB - 1) / B2_POST_WPB, B2_POST_WPB * 32, p.smem_post, st>>>(km, kd, p.lp, do_integrate, mask, gate);
-  g_launches += 3;
+  g_launches += 4;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail("launch failed: %s", cudaGetErrorString(e));
   return 0;
@@ -187,7 +215,11 @@ int b2_stage(const b2_model* m, b2_data* d, int stage, int do_integrate, void* s
   const KModel& km = *reinterpret_cast<const KModel*>(m);
   const KData& kd = *reinterpret_cast<const KData*>(d);
   int grid = (d->nworld + B2_WPB - 1) / B2_WPB;
-  if (stage == 0) k_smooth<<<grid, B2_WPB * 32, p.smem_smooth, st>>>(km, kd, p.ls, B2_NCAND_MAX, nullptr, nullptr);
+  if (stage == 0) {
+    k_smooth<<<grid, B2_WPB * 32, p.smem_smooth, st>>>(km, kd, p.ls, B2_NCAND_MAX, nullptr, nullptr);
+    k_order<<<1, 1024, 0, st>>>(kd);
+    g_launches += 1;
+  }
   else if (stage == 1) k_solve<<<grid, B2_WPB * 32, p.smem_solve, st>>>(km, kd, p.lv, nullptr, nullptr);
   else if (stage == 2) k_post<<<(d->nworld + B2_POST_WPB - 1) / B2_POST_WPB, B2_POST_WPB * 32, p.smem_post, st>>>(km, kd, p.lp, do_integrate, nullptr, nullptr);
   else return fail("unknown stage %d", stage);

@@ -329,19 +329,52 @@ B2_DEVN void chol_backsolve(const real* L, int n, int ld, const real* invd, real
 // y = M x for a symmetric M [n][ld] in global memory: lane i walks column i (== row i), so every
 // load of the warp is one coalesced segment.
 B2_DEVN void symv_global(const real* M, int n, int ld, const real* x, real* y) {  // @region symv_global
-  B2_UNROLL1
-  for (int i = B2_LANE; i < n; i += B2_NLANE) {
+#ifdef B2_HOSTEMU
+  for (int i = 0; i < n; ++i) {
+    real a = 0;
+    for (int e = 0; e < n; ++e) a += M[e * ld + i] * x[e];
+    y[i] = a;
+  }
+#else
+  // Latency-bound on L2: keep many independent loads in flight (12 per batch), no dependent scalar tail.
+  const int i = B2_LANE;
+  if (i < n) {
+    const real* Mi = M + i;
     real a0 = 0, a1 = 0, a2 = 0, a3 = 0;
     int e = 0;
     B2_UNROLL1
-    for (; e + 4 <= n; e += 4) {
-      real m0 = M[e * ld + i], m1 = M[(e + 1) * ld + i], m2 = M[(e + 2) * ld + i], m3 = M[(e + 3) * ld + i];
-      a0 += m0 * x[e]; a1 += m1 * x[e + 1]; a2 += m2 * x[e + 2]; a3 += m3 * x[e + 3];
+    for (; e + 12 <= n; e += 12) {
+      real m[12];
+#pragma unroll
+      for (int k = 0; k < 12; ++k) m[k] = Mi[(e + k) * ld];
+#pragma unroll
+      for (int k = 0; k < 12; k += 4) {
+        a0 = fmaf(m[k], x[e + k], a0); a1 = fmaf(m[k + 1], x[e + k + 1], a1);
+        a2 = fmaf(m[k + 2], x[e + k + 2], a2); a3 = fmaf(m[k + 3], x[e + k + 3], a3);
+      }
     }
-    B2_UNROLL1
-    for (; e < n; ++e) a0 += M[e * ld + i] * x[e];
+    {
+      real m[12];
+#pragma unroll
+      for (int k = 0; k < 12; ++k) m[k] = e + k < n ? Mi[(e + k) * ld] : (real)0;
+#pragma unroll
+      for (int k = 0; k < 12; k += 4) {
+        a0 = fmaf(m[k], e + k < n ? x[e + k] : (real)0, a0); a1 = fmaf(m[k + 1], e + k + 1 < n ? x[e + k + 1] : (real)0, a1);
+        a2 = fmaf(m[k + 2], e + k + 2 < n ? x[e + k + 2] : (real)0, a2); a3 = fmaf(m[k + 3], e + k + 3 < n ? x[e + k + 3] : (real)0, a3);
+      }
+    }
     y[i] = (a0 + a1) + (a2 + a3);
   }
+  // rows 32..n-1 (n > 32): lanes across the row (coalesced), one reduction per row
+  B2_UNROLL1
+  for (int r = 32; r < n; ++r) {
+    real acc = 0;
+    B2_UNROLL1
+    for (int e = B2_LANE; e < n; e += B2_NLANE) acc = fmaf(M[r * ld + e], x[e], acc);
+    acc = b2_wsum(acc);
+    if (B2_LANE == 0) y[r] = acc;
+  }
+#endif
   B2_WSYNC();
 }
 

@@ -149,6 +149,7 @@ DATA_INT_FIELDS = [
   ("CONTACT_EFC_ADDRESS", "contact_efc_address", lambda m, c, j: (c,)),
   ("NCON_DROPPED", "ncon_dropped", lambda m, c, j: ()),
   ("NEFC_DROPPED", "nefc_dropped", lambda m, c, j: ()),
+  ("SOLVE_ORDER", "solve_order", lambda m, c, j: ()),
 ]
 
 def leading_dim(n: int) -> int:

@@ -324,8 +324,8 @@ class ManagerBasedRlEnv:
     torch.cuda.current_stream(self._dev).wait_stream(side)
     self._graph = g
 
-  #: kernels enqueued per env step: action, decimation x (smooth, solve, post, airtime), env_post + gate, forward (3), obs, log
-  launches_per_step = property(lambda self: 1 + 4 * self.cfg.decimation + 2 + 3 + 1 + 1)
+  #: kernels enqueued per env step: action, decimation x (smooth, order, solve, post, airtime), env_post + gate, forward (4), obs, log
+  launches_per_step = property(lambda self: 1 + 5 * self.cfg.decimation + 2 + 4 + 1 + 1)
 
   # ---- API ------------------------------------------------------------------------------------------
   def seed(self, seed: int = -1) -> int:
