@@ -35,7 +35,8 @@ sys.path.insert(0, str(ROOT))
 
 DECIMATION = 4
 NUM_ENVS = 4096
-EPISODE_STEPS = 250  # staggered synthetic resets keep a mix of standing / falling worlds
+# DRAM bytes per launch from the committed ncu captures of this workload (profiles/r01_final_k_*.txt)
+NCU_TRAFFIC_BYTES = {"k_solve": 38_520_832, "k_smooth": 37_670_400, "k_post": 53_158_656}
 
 
 def parse():
@@ -364,7 +365,9 @@ def run_b200(args):
     step_ms = elapsed_ms / args.steps
     roof = {
       "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-      "traffic": None, "peak_source": "measured burst (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback (B200_PROFILING.md)",
+      "traffic": NCU_TRAFFIC_BYTES.get(dom) if (args.model == "g1_flat" and nw == NUM_ENVS) else None,
+      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, profiles/r01_final_*.txt",
+      "peak_source": "measured burst (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback (B200_PROFILING.md)",
       "algorithmic_bytes_per_world": {"k_smooth": b_smooth, "k_solve": b_solve, "env_step": b_env},
       "avg_launch_ms": avg, "ms_per_env_step_by_kernel": per_step,
       "whole_step": {"bytes_per_env_step": b_env, "achieved": b_env * nw / (step_ms * 1e-3) / 1e9,
