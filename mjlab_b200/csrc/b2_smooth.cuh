@@ -51,7 +51,7 @@ struct LaneContacts {
   real tangent[3];  // zero => pick default
 };
 
-B2_DEV void sphere_sphere(LaneContacts& lc, const real* p1, real r1, const real* p2, real r2, real margin) {
+B2_DEV void sphere_sphere(LaneContacts& lc, const real* p1, real r1, const real* p2, real r2, real margin) {  // @region narrowphase_fns
   real dif[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
   real c = sqrt(dot3(dif, dif));
   if (c > margin + r1 + r2) return;
@@ -189,7 +189,7 @@ B2_DEV void make_frame(real* F, const real* normal, const real* tangent) {
 // ---------------------------------------------------------------------------
 // Stage 1 for world w.  sm: this warp's shared-memory slab.
 // ---------------------------------------------------------------------------
-B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, int ncand_max, int w, real* sm) {
+B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, int ncand_max, int w, real* sm) {  // @region setup
   const int nq = m.nq, nv = m.nv, nu = m.nu, nb = m.nbody, nj = m.njnt;
   real* qpos = sm + L.qpos; real* qvel = sm + L.qvel;
   real* xpos = sm + L.xpos; real* xquat = sm + L.xquat; real* xmat = sm + L.xmat; real* xipos = sm + L.xipos;
@@ -228,7 +228,7 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
   for (int i = B2_LANE; i < nv; i += B2_NLANE) qvel[i] = g_qvel[i];
   B2_WSYNC();
 
-  // ---- kinematics, level by level ------------------------------------------
+  // ---- kinematics, level by level ------------------------------------------  // @region kinematics
   const real* qpos0 = MF(B2_MF_QPOS0);
   const real* body_pos = MF(B2_MF_BODY_POS);
   const real* body_quat = MF(B2_MF_BODY_QUAT);
@@ -357,7 +357,7 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
     }
   }
 
-  // ---- subtree com (backward gather over levels) ----------------------------
+  // ---- subtree com (backward gather over levels) ----------------------------  // @region subtree_com
   const real* body_mass = MF(B2_MF_BODY_MASS);
   const real* body_inertia = MF(B2_MF_BODY_INERTIA);
   B2_UNROLL1
@@ -395,7 +395,7 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
     B2_UNROLL1
     for (int i = B2_LANE; i < 3 * nb; i += B2_NLANE) g[i] = scom[i];
   }
-  // ---- cinert, cdof -----------------------------------------------------------
+  // ---- cinert, cdof -----------------------------------------------------------  // @region cinert_cdof
   B2_UNROLL1
   for (int b = B2_LANE; b < nb; b += B2_NLANE) {
     int r = body_root[b];
@@ -446,7 +446,7 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
     B2_UNROLL1
     for (int i = B2_LANE; i < 6 * nv; i += B2_NLANE) g[i] = cdof[i];
   }
-  // ---- composite rigid body inertias, dense qM --------------------------------
+  // ---- composite rigid body inertias, dense qM --------------------------------  // @region crb_qM
   B2_UNROLL1
   for (int lev = m.nlevel - 1; lev >= 1; --lev) {
     B2_UNROLL1
@@ -486,7 +486,7 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
     for (int i = B2_LANE; i < nv * ld; i += B2_NLANE) g[i] = M[i];
   }
 
-  // ---- collision ---------------------------------------------------------------
+  // ---- collision ---------------------------------------------------------------  // @region collision
   {
     const int* pair_geom = MI(B2_MI_PAIR_GEOM);
     const int* geom_type = MI(B2_MI_GEOM_TYPE);
@@ -625,7 +625,7 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
     }
   }
 
-  // ---- com_vel: cvel, cdof_dot (forward over levels) ----------------------------
+  // ---- com_vel: cvel, cdof_dot (forward over levels) ----------------------------  // @region com_vel
   B2_UNROLL1
   for (int lev = 0; lev < m.nlevel; ++lev) {
     B2_UNROLL1
@@ -664,7 +664,7 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
     for (int i = B2_LANE; i < 6 * nv; i += B2_NLANE) g[i] = cdofdot[i];
   }
 
-  // ---- actuation ------------------------------------------------------------------
+  // ---- actuation ------------------------------------------------------------------  // @region actuation
   {
     const int* trnid = MI(B2_MI_ACTUATOR_TRNID);
     const int* biastype = MI(B2_MI_ACTUATOR_BIASTYPE);
@@ -696,7 +696,7 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
     B2_WSYNC();
   }
 
-  // ---- RNE bias (cacc aliases crb) -----------------------------------------------------
+  // ---- RNE bias (cacc aliases crb) -----------------------------------------------------  // @region rne
   const real* grav = MF(B2_MF_OPT_GRAVITY);
   B2_UNROLL1
   for (int lev = 0; lev < m.nlevel; ++lev) {
@@ -739,7 +739,7 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
     B2_WSYNC();
   }
 
-  // ---- passive + actuator + applied forces -> qfrc_smooth ------------------------------
+  // ---- passive + actuator + applied forces -> qfrc_smooth ------------------------------  // @region qfrc_smooth
   {
     const real* damping = MF(B2_MF_DOF_DAMPING);
     const real* stiffness = MF(B2_MF_JNT_STIFFNESS);
@@ -802,7 +802,7 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
     }
     B2_WSYNC();
   }
-  // ---- qacc_smooth = M^-1 qfrc_smooth (M already copied to HBM; factor in place) ---------
+  // ---- qacc_smooth = M^-1 qfrc_smooth (M already copied to HBM; factor in place) ---------  // @region factor_solve
   spd_factor_solve(M, nv, ld, f, sm + L.invd);
   {
     real* g = d.df[B2_DF_QACC_SMOOTH] + (size_t)w * nv;

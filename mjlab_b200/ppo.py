@@ -1,0 +1,277 @@
+"""PPO learner for the B200 env (the step after the hot path in `train`).
+
+The reference trains with rsl-rl-lib 3.1.0's `OnPolicyRunner` (src/mjlab/scripts/train.py:141-169, configured by
+src/mjlab/rl/config.py:7-112 and src/mjlab/tasks/velocity/config/g1/rl_cfg.py:10-39); that package is not in the
+reference tree and not installable here, so this module restates the algorithm it runs for the velocity tasks:
+actor / critic MLPs (ELU, 512-256-128) with empirical observation normalisation and a state-independent scalar std,
+24 steps per env per iteration, GAE(0.99, 0.95) with time-out bootstrapping, 5 epochs x 4 mini-batches of the clipped
+surrogate + clipped value loss + entropy bonus, KL-adaptive learning rate, gradient-norm clipping, and for multi-GPU runs
+(`--gpu-ids`, docs/api/distributed_training.md) one process per GPU with independent env batches whose gradients are
+averaged by an NCCL all-reduce before every optimiser step (the only collective of the training path).
+
+This is host-side plumbing around the env hot path: plain PyTorch modules (their GEMMs are cuBLAS library calls), no
+custom kernels.  It exists so that BASELINE config 3 ("full PPO train step") can be measured end to end on this engine
+and so that the env can be validated by actually learning on it.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+
+@dataclass
+class PpoCfg:
+  """rl/config.py:7-112 + config/g1/rl_cfg.py:10-39."""
+
+  num_steps_per_env: int = 24
+  actor_hidden_dims: tuple = (512, 256, 128)
+  critic_hidden_dims: tuple = (512, 256, 128)
+  init_noise_std: float = 1.0
+  actor_obs_normalization: bool = True
+  critic_obs_normalization: bool = True
+  num_learning_epochs: int = 5
+  num_mini_batches: int = 4
+  learning_rate: float = 1.0e-3
+  schedule: str = "adaptive"
+  gamma: float = 0.99
+  lam: float = 0.95
+  entropy_coef: float = 0.01
+  desired_kl: float = 0.01
+  max_grad_norm: float = 1.0
+  value_loss_coef: float = 1.0
+  use_clipped_value_loss: bool = True
+  clip_param: float = 0.2
+  clip_actions: float | None = None
+  seed: int = 42
+  obs_groups: dict = field(default_factory=lambda: {"policy": ("policy",), "critic": ("critic",)})
+
+
+class EmpiricalNormalization(nn.Module):
+  """Running mean / variance normalisation, updated while the module is in training mode."""
+
+  def __init__(self, dim: int, eps: float = 1e-2):
+    super().__init__()
+    self.eps = eps
+    self.register_buffer("mean", torch.zeros(1, dim))
+    self.register_buffer("var", torch.ones(1, dim))
+    self.register_buffer("std", torch.ones(1, dim))
+    self.register_buffer("count", torch.zeros((), dtype=torch.long))
+
+  @torch.no_grad()
+  def update(self, x: torch.Tensor) -> None:
+    n = x.shape[0]
+    self.count += n
+    rate = n / self.count.to(x.dtype)
+    mean_x = x.mean(0, keepdim=True)
+    var_x = x.var(0, unbiased=False, keepdim=True)
+    delta = mean_x - self.mean
+    self.mean += rate * delta
+    self.var += rate * (var_x - self.var + delta * (mean_x - self.mean))
+    self.std.copy_(self.var.sqrt())
+
+  def forward(self, x: torch.Tensor) -> torch.Tensor:
+    return (x - self.mean) / (self.std + self.eps)
+
+
+def _mlp(n_in: int, hidden: tuple, n_out: int) -> nn.Sequential:
+  layers: list[nn.Module] = []
+  d = n_in
+  for h in hidden:
+    layers += [nn.Linear(d, h), nn.ELU()]
+    d = h
+  layers.append(nn.Linear(d, n_out))
+  return nn.Sequential(*layers)
+
+
+class ActorCritic(nn.Module):
+  def __init__(self, n_actor_obs: int, n_critic_obs: int, n_actions: int, cfg: PpoCfg):
+    super().__init__()
+    self.actor = _mlp(n_actor_obs, cfg.actor_hidden_dims, n_actions)
+    self.critic = _mlp(n_critic_obs, cfg.critic_hidden_dims, 1)
+    self.actor_norm = EmpiricalNormalization(n_actor_obs) if cfg.actor_obs_normalization else nn.Identity()
+    self.critic_norm = EmpiricalNormalization(n_critic_obs) if cfg.critic_obs_normalization else nn.Identity()
+    self.std = nn.Parameter(cfg.init_noise_std * torch.ones(n_actions))
+
+  def distribution(self, obs: torch.Tensor) -> torch.distributions.Normal:
+    mean = self.actor(self.actor_norm(obs))
+    return torch.distributions.Normal(mean, self.std.expand_as(mean))
+
+  def act_inference(self, obs: torch.Tensor) -> torch.Tensor:
+    return self.actor(self.actor_norm(obs))
+
+  def evaluate(self, critic_obs: torch.Tensor) -> torch.Tensor:
+    return self.critic(self.critic_norm(critic_obs))
+
+  @torch.no_grad()
+  def update_normalization(self, obs: torch.Tensor, critic_obs: torch.Tensor) -> None:
+    if isinstance(self.actor_norm, EmpiricalNormalization):
+      self.actor_norm.update(obs)
+    if isinstance(self.critic_norm, EmpiricalNormalization):
+      self.critic_norm.update(critic_obs)
+
+
+def reduce_gradients(params, world_size: int) -> None:
+  """Average the gradients over ranks with ONE all-reduce of the flattened vector (1.76 MB for the G1 nets)."""
+  grads = [p.grad.view(-1) for p in params if p.grad is not None]
+  flat = torch.cat(grads)
+  dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+  flat /= world_size
+  o = 0
+  for p in params:
+    if p.grad is not None:
+      n = p.numel()
+      p.grad.copy_(flat[o:o + n].view_as(p.grad))
+      o += n
+
+
+class OnPolicyRunner:
+  """Roll-out + PPO update loop over a `ManagerBasedRlEnv` (through `RslRlVecEnvWrapper`)."""
+
+  def __init__(self, venv, cfg: PpoCfg | None = None, device: str | None = None):
+    self.env, self.cfg = venv, cfg or PpoCfg()
+    self.device = torch.device(device or venv.device)
+    self.distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    self.world_size = dist.get_world_size() if self.distributed else 1
+    self.rank = dist.get_rank() if self.distributed else 0
+    obs = venv.get_observations()
+    self.n_obs, self.n_critic = obs["policy"].shape[1], obs["critic"].shape[1]
+    self.n_act = venv.num_actions
+    torch.manual_seed(self.cfg.seed)  # identical initial parameters on every rank; env batches differ by seed + rank
+    self.policy = ActorCritic(self.n_obs, self.n_critic, self.n_act, self.cfg).to(self.device)
+    if self.distributed:
+      for t in list(self.policy.parameters()) + list(self.policy.buffers()):
+        dist.broadcast(t.data, src=0)
+    self.optimizer = torch.optim.Adam(self.policy.parameters(), lr=self.cfg.learning_rate)
+    self.learning_rate = self.cfg.learning_rate
+    T, B = self.cfg.num_steps_per_env, venv.num_envs
+    z = lambda *s: torch.zeros(T, B, *s, device=self.device)  # noqa: E731
+    self.st = dict(obs=z(self.n_obs), critic=z(self.n_critic), actions=z(self.n_act), rewards=z(), dones=z(), values=z(),
+                   logp=z(), mu=z(self.n_act), sigma=z(self.n_act))
+    self.iteration = 0
+    self.tot_steps = 0
+    self.history: list[dict] = []
+    self._ep_ret = torch.zeros(B, device=self.device)
+    self._ep_len = torch.zeros(B, device=self.device)
+
+  # ---- roll-out -------------------------------------------------------------------------------------
+  @torch.no_grad()
+  def collect(self) -> dict:
+    cfg, st, env = self.cfg, self.st, self.env
+    obs = env.get_observations()
+    done_ret, done_len, done_n = 0.0, 0.0, 0
+    self.policy.train()
+    for t in range(cfg.num_steps_per_env):
+      o, c = obs["policy"], obs["critic"]
+      st["obs"][t].copy_(o)          # the env's observation buffers are overwritten by the next step
+      st["critic"][t].copy_(c)
+      dist_ = self.policy.distribution(st["obs"][t])
+      a = dist_.sample()
+      st["actions"][t] = a
+      st["values"][t] = self.policy.evaluate(st["critic"][t]).squeeze(-1)
+      st["logp"][t] = dist_.log_prob(a).sum(-1)
+      st["mu"][t], st["sigma"][t] = dist_.mean, dist_.stddev
+      obs, rew, dones, extras = env.step(a)
+      self.policy.update_normalization(obs["policy"], obs["critic"])
+      r = rew.clone()
+      if "time_outs" in extras:  # bootstrap the value of truncated episodes
+        r += cfg.gamma * st["values"][t] * extras["time_outs"].to(r.dtype)
+      st["rewards"][t] = r
+      st["dones"][t] = dones.to(r.dtype)
+      self._ep_ret += rew
+      self._ep_len += 1
+      d = dones.bool()
+      done_n_t = d.sum()
+      done_ret = done_ret + (self._ep_ret * d).sum()
+      done_len = done_len + (self._ep_len * d).sum()
+      done_n = done_n + done_n_t
+      self._ep_ret.masked_fill_(d, 0.0)
+      self._ep_len.masked_fill_(d, 0.0)
+    last_values = self.policy.evaluate(obs["critic"]).squeeze(-1)
+    # GAE
+    adv = torch.zeros_like(last_values)
+    returns = torch.zeros_like(st["rewards"])
+    for t in reversed(range(cfg.num_steps_per_env)):
+      nv = last_values if t == cfg.num_steps_per_env - 1 else st["values"][t + 1]
+      nonterminal = 1.0 - st["dones"][t]
+      delta = st["rewards"][t] + nonterminal * cfg.gamma * nv - st["values"][t]
+      adv = delta + nonterminal * cfg.gamma * cfg.lam * adv
+      returns[t] = adv + st["values"][t]
+    advantages = returns - st["values"]
+    advantages = (advantages - advantages.mean()) / (advantages.std() + 1e-8)
+    self.tot_steps += cfg.num_steps_per_env * env.num_envs * self.world_size
+    return dict(returns=returns, advantages=advantages, mean_step_reward=st["rewards"].mean(), done_ret=done_ret, done_len=done_len, done_n=done_n)
+
+  # ---- update ------------------------------------------------------------------------------------------
+  def update(self, ro: dict) -> dict:
+    cfg, st = self.cfg, self.st
+    N = cfg.num_steps_per_env * self.env.num_envs
+    flat = {k: v.reshape(N, *v.shape[2:]) for k, v in st.items()}
+    ret, adv = ro["returns"].reshape(N), ro["advantages"].reshape(N)
+    mb = N // cfg.num_mini_batches
+    params = list(self.policy.parameters())
+    stats = dict(value=0.0, surrogate=0.0, entropy=0.0, kl=0.0)
+    self.policy.train()
+    for _ in range(cfg.num_learning_epochs):
+      perm = torch.randperm(cfg.num_mini_batches * mb, device=self.device)
+      for i in range(cfg.num_mini_batches):
+        idx = perm[i * mb:(i + 1) * mb]
+        dist_ = self.policy.distribution(flat["obs"][idx])
+        logp = dist_.log_prob(flat["actions"][idx]).sum(-1)
+        value = self.policy.evaluate(flat["critic"][idx]).squeeze(-1)
+        mu, sigma, entropy = dist_.mean, dist_.stddev, dist_.entropy().sum(-1)
+        with torch.no_grad():
+          old_mu, old_sigma = flat["mu"][idx], flat["sigma"][idx]
+          kl = torch.sum(torch.log(sigma / old_sigma + 1e-5) + (old_sigma.square() + (old_mu - mu).square()) / (2.0 * sigma.square()) - 0.5, -1).mean()
+          if self.distributed:
+            dist.all_reduce(kl, op=dist.ReduceOp.SUM)
+            kl /= self.world_size
+        if cfg.schedule == "adaptive" and cfg.desired_kl is not None:
+          k = kl.item()
+          if k > cfg.desired_kl * 2.0:
+            self.learning_rate = max(1e-5, self.learning_rate / 1.5)
+          elif 0.0 < k < cfg.desired_kl / 2.0:
+            self.learning_rate = min(1e-2, self.learning_rate * 1.5)
+          for g in self.optimizer.param_groups:
+            g["lr"] = self.learning_rate
+        ratio = torch.exp(logp - flat["logp"][idx])
+        a = adv[idx]
+        surrogate = torch.max(-a * ratio, -a * torch.clamp(ratio, 1.0 - cfg.clip_param, 1.0 + cfg.clip_param)).mean()
+        if cfg.use_clipped_value_loss:
+          old_v = flat["values"][idx]
+          v_clip = old_v + (value - old_v).clamp(-cfg.clip_param, cfg.clip_param)
+          v_loss = torch.max((value - ret[idx]).square(), (v_clip - ret[idx]).square()).mean()
+        else:
+          v_loss = (ret[idx] - value).square().mean()
+        loss = surrogate + cfg.value_loss_coef * v_loss - cfg.entropy_coef * entropy.mean()
+        self.optimizer.zero_grad(set_to_none=False)
+        loss.backward()
+        if self.distributed:
+          reduce_gradients(params, self.world_size)
+        nn.utils.clip_grad_norm_(params, cfg.max_grad_norm)
+        self.optimizer.step()
+        stats["value"] += v_loss.detach()
+        stats["surrogate"] += surrogate.detach()
+        stats["entropy"] += entropy.mean().detach()
+        stats["kl"] += kl
+    n = cfg.num_learning_epochs * cfg.num_mini_batches
+    return {k: v / n for k, v in stats.items()}
+
+  def learn(self, num_iterations: int, init_at_random_ep_len: bool = True, log_every: int = 0) -> list[dict]:
+    if init_at_random_ep_len and self.iteration == 0:  # scripts/train.py:167-169
+      self.env.episode_length_buf = torch.randint_like(self.env.episode_length_buf, high=int(self.env.max_episode_length))
+    for _ in range(num_iterations):
+      ro = self.collect()
+      up = self.update(ro)
+      self.iteration += 1
+      n = max(float(ro["done_n"]), 1.0)
+      rec = dict(iteration=self.iteration, mean_step_reward=float(ro["mean_step_reward"]), episodes=float(ro["done_n"]),
+                 mean_episode_return=float(ro["done_ret"]) / n, mean_episode_length=float(ro["done_len"]) / n,
+                 lr=self.learning_rate, noise_std=float(self.policy.std.detach().mean()), **{k: float(v) for k, v in up.items()})
+      self.history.append(rec)
+      if log_every and self.rank == 0 and self.iteration % log_every == 0:
+        print({k: (round(v, 5) if isinstance(v, float) else v) for k, v in rec.items()}, flush=True)
+    return self.history

@@ -298,3 +298,17 @@ def test_env_full_size_properties(robot):
   ids = env.robot.indexing.geom_ids[env.robot.find_geoms(env._foot_geom_names())[0]]
   f0 = fr[:, ids, 0]
   assert f0.min() >= 0.3 and f0.max() <= 1.2 and f0.std() > 0.1
+
+
+def test_ppo_learns_on_the_env():
+  """End-to-end: 30 PPO iterations on Go1 (1024 envs) raise the mean step reward and lengthen episodes."""
+  from mjlab_b200.env import ManagerBasedRlEnv, VelocityEnvCfg
+  from mjlab_b200.ppo import OnPolicyRunner, PpoCfg
+  from mjlab_b200.vecenv import RslRlVecEnvWrapper
+  env = ManagerBasedRlEnv(VelocityEnvCfg(robot="go1", num_envs=1024, seed=1), DEV)
+  runner = OnPolicyRunner(RslRlVecEnvWrapper(env), PpoCfg())
+  hist = runner.learn(30)
+  first = np.mean([h["mean_step_reward"] for h in hist[:3]])
+  last = np.mean([h["mean_step_reward"] for h in hist[-3:]])
+  assert all(np.isfinite(h["mean_step_reward"]) and np.isfinite(h["kl"]) for h in hist)
+  assert last > first, (first, last)

@@ -1,0 +1,50 @@
+"""Train the velocity task with the PPO learner on the B200 engine (the reference's `train` CLI for this task,
+src/mjlab/scripts/train.py:46-171, minus logging / checkpoint plumbing).
+
+  python tools/train_velocity.py --robot g1 --num-envs 4096 --iterations 300
+  python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/train_velocity.py ...   # --gpu-ids path
+"""
+import argparse
+import json
+import os
+import sys
+import time
+from pathlib import Path
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+from mjlab_b200.env import ManagerBasedRlEnv, VelocityEnvCfg  # noqa: E402
+from mjlab_b200.ppo import OnPolicyRunner, PpoCfg  # noqa: E402
+from mjlab_b200.vecenv import RslRlVecEnvWrapper  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--robot", default="g1")
+ap.add_argument("--num-envs", type=int, default=4096)
+ap.add_argument("--iterations", type=int, default=300)
+ap.add_argument("--forward-mode", default="reference")
+ap.add_argument("--log-every", type=int, default=10)
+ap.add_argument("--out", default="")
+a = ap.parse_args()
+world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dev = f"cuda:{local}"
+if world > 1:
+  dist.init_process_group("nccl", device_id=torch.device(dev))
+env = ManagerBasedRlEnv(VelocityEnvCfg(robot=a.robot, num_envs=a.num_envs, seed=42 + rank, forward_mode=a.forward_mode), dev)
+runner = OnPolicyRunner(RslRlVecEnvWrapper(env), PpoCfg())
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+hist = runner.learn(a.iterations, log_every=a.log_every)
+torch.cuda.synchronize()
+dt = time.perf_counter() - t0
+if rank == 0:
+  sps = a.iterations * 24 * a.num_envs * world / dt
+  summary = {"robot": a.robot, "num_envs_per_gpu": a.num_envs, "n_gpus": world, "iterations": a.iterations, "wall_s": dt, "train_env_steps_per_s": sps,
+             "first": hist[0], "last": hist[-1]}
+  print(json.dumps(summary))
+  if a.out:
+    Path(a.out).write_text(json.dumps({"summary": summary, "history": hist}))
+if world > 1:
+  dist.destroy_process_group()
