@@ -312,3 +312,31 @@ def test_ppo_learns_on_the_env():
   last = np.mean([h["mean_step_reward"] for h in hist[-3:]])
   assert all(np.isfinite(h["mean_step_reward"]) and np.isfinite(h["kl"]) for h in hist)
   assert last > first, (first, last)
+
+
+def test_play_zero_agent():
+  """BASELINE config 1 (`play --agent zero`, 64 envs).  Go1: the position actuators hold the default pose and the robot
+  stays upright (it sags 5 cm under the soft gains until the calves touch the ground, as in the f64 host build).  G1: the shipped gains (knee kp 99 N m/rad
+  under a 35 kg robot) do not hold the pose open loop - the robot tips forward within 1.5 s in the oracle as well - so the
+  fall is detected, the env resets and the loop keeps running with finite values."""
+  from mjlab_b200.env import ManagerBasedRlEnv, VelocityEnvCfg
+  for robot in ("go1", "g1"):
+    env = ManagerBasedRlEnv(VelocityEnvCfg(robot=robot, num_envs=64, play=True, seed=42), DEV)
+    assert not env.vcfg.enable_corruption and not env.vcfg.push_enabled and env.max_episode_length > 10**9
+    env.reset()
+    z0 = env.sim.data.qpos[:, 2].clone()
+    zero = torch.zeros(64, env.vcfg.nj, device=DEV)
+    fell = torch.zeros(64, dtype=torch.bool, device=DEV)
+    for _ in range(300):
+      obs, rew, term, trunc, _ = env.step(zero)
+      fell |= env.termination_manager.get_term("fell_over")
+      assert torch.isfinite(obs["critic"]).all() and torch.isfinite(rew).all()
+    assert not bool(trunc.any())
+    if robot == "go1":
+      assert int(fell.sum()) == 0                                # never tips over ...
+      assert float(obs["policy"][:, 8].mean()) < -0.95           # ... projected gravity z stays near -1
+      z = env.sim.data.qpos[:, 2]
+      assert float((z - z0).abs().max()) < 0.08                  # sags < 8 cm (episodes may end on calf-ground contact)
+    else:
+      assert bool(fell.all())                                    # open-loop G1 tips over ...
+      assert int(env.episode_length_buf.max()) < 150             # ... every episode ends and restarts
