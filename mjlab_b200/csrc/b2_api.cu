@@ -12,6 +12,7 @@
 #include "b2_smooth.cuh"
 #include "b2_solve.cuh"
 #include "b2_env.cuh"
+#include "b2_trk.cuh"
 
 static_assert(sizeof(KModel) == sizeof(b2_model), "KModel must mirror b2_model");
 static_assert(sizeof(KData) == sizeof(b2_data), "KData must mirror b2_data");
@@ -261,3 +262,4 @@ int b2_forward_masked(const b2_model* m, b2_data* d, const unsigned char* mask, 
 }  // extern "C"
 
 #include "b2_env_api.inl"
+#include "b2_trk_api.inl"

@@ -230,3 +230,98 @@ def velocity_cfg(m, robot: str, play: bool = False) -> VelocityCfg:
     enable_corruption=not play, push_enabled=not play,
     foot_site_body=np.asarray(m.site_bodyid)[site_ids[list(foot_local)]].astype(int),
   )
+
+
+# ---------------------------------------------------------------------------------------------------------
+# tracking task (tasks/tracking/tracking_env_cfg.py:44-317, config/g1/env_cfgs.py:15-100)
+# ---------------------------------------------------------------------------------------------------------
+TRACKING_REWARD_NAMES = ("motion_global_root_pos", "motion_global_root_ori", "motion_body_pos", "motion_body_ori", "motion_body_lin_vel",
+                         "motion_body_ang_vel", "action_rate_l2", "joint_limit", "self_collisions")
+TRACKING_TERMINATION_NAMES = ("time_out", "anchor_pos", "anchor_ori", "ee_body_pos")
+G1_TRACKED_BODIES = ("pelvis", "left_hip_roll_link", "left_knee_link", "left_ankle_roll_link", "right_hip_roll_link", "right_knee_link",
+                     "right_ankle_roll_link", "torso_link", "left_shoulder_roll_link", "left_elbow_link", "left_wrist_yaw_link",
+                     "right_shoulder_roll_link", "right_elbow_link", "right_wrist_yaw_link")
+G1_EE_BODIES = ("left_ankle_roll_link", "right_ankle_roll_link", "left_wrist_yaw_link", "right_wrist_yaw_link")
+_TRACKING_VELOCITY_RANGE = {"x": (-0.5, 0.5), "y": (-0.5, 0.5), "z": (-0.2, 0.2), "roll": (-0.52, 0.52), "pitch": (-0.52, 0.52), "yaw": (-0.78, 0.78)}
+
+
+@dataclass
+class TrackingCfg:
+  nj: int
+  nbody: int               # tracked bodies
+  nbody_motion: int        # robot bodies stored per motion frame
+  root_body: int
+  body_ids: np.ndarray     # global ids of all robot bodies (motion order)
+  body_sel: np.ndarray     # tracked bodies as indices into body_ids
+  anchor_sel: int          # anchor inside the tracked list
+  ee_sel: np.ndarray       # end-effector bodies inside the tracked list
+  joint_q_adr: np.ndarray
+  joint_v_adr: np.ndarray
+  ctrl_ids: np.ndarray
+  default_joint_pos: np.ndarray
+  soft_joint_pos_limits: np.ndarray
+  action_scale: np.ndarray
+  linvel_adr: int
+  angvel_adr: int
+  selfcol_adr: int
+  noise_lo: np.ndarray
+  noise_hi: np.ndarray
+  n_obs_policy: int
+  n_obs_critic: int
+  time_step_total: int
+  bin_count: int
+  reward_weights: np.ndarray
+  step_dt: float = 0.02
+  max_episode_length: int = 500
+  max_episode_length_s: float = 10.0
+  anchor_pos_threshold: float = 0.25
+  anchor_ori_threshold: float = 0.8
+  ee_pos_threshold: float = 0.25
+  std_anchor_pos: float = 0.3
+  std_anchor_ori: float = 0.4
+  std_body_pos: float = 0.3
+  std_body_ori: float = 0.4
+  std_body_lin_vel: float = 1.0
+  std_body_ang_vel: float = 3.14
+  sampling_mode: str = "adaptive"
+  adaptive_kernel_size: int = 1
+  adaptive_lambda: float = 0.8
+  adaptive_uniform_ratio: float = 0.1
+  adaptive_alpha: float = 0.001
+  pose_range: np.ndarray = None
+  velocity_range: np.ndarray = None
+  joint_position_range: tuple = (-0.1, 0.1)
+  push_interval: tuple = (1.0, 3.0)
+  push_vel: np.ndarray = None
+  enable_corruption: bool = True
+  push_enabled: bool = True
+  seed: int = 0
+
+
+def tracking_cfg(m, time_step_total: int, robot: str = "g1", play: bool = False, tracked=G1_TRACKED_BODIES, anchor="torso_link", ee=G1_EE_BODIES) -> TrackingCfg:
+  v = velocity_cfg(m, robot)   # index maps, default pose, soft limits, action scale, sensor addresses are shared
+  body_local = [n.removeprefix("robot/") for n in (m.body_names[i] for i in v.body_ids)]
+  body_sel = np.array([body_local.index(n) for n in tracked])
+  nj, nb = v.nj, len(tracked)
+  n_pol = 5 * nj + 15
+  lo, hi = np.zeros(n_pol), np.zeros(n_pol)
+  c = 2 * nj
+  for a, b, (l, h) in ((c, c + 3, (-0.25, 0.25)), (c + 3, c + 9, (-0.05, 0.05)), (c + 9, c + 12, (-0.5, 0.5)), (c + 12, c + 15, (-0.2, 0.2)),
+                       (c + 15, c + 15 + nj, (-0.01, 0.01)), (c + 15 + nj, c + 15 + 2 * nj, (-0.5, 0.5))):
+    lo[a:b], hi[a:b] = l, h
+  r6 = VelocityCfg._ranges6
+  step_dt = 0.02
+  return TrackingCfg(
+    nj=nj, nbody=nb, nbody_motion=len(v.body_ids), root_body=v.root_body, body_ids=v.body_ids, body_sel=body_sel,
+    anchor_sel=list(tracked).index(anchor), ee_sel=np.array([list(tracked).index(n) for n in ee]), joint_q_adr=v.joint_q_adr,
+    joint_v_adr=v.joint_v_adr, ctrl_ids=v.ctrl_ids, default_joint_pos=v.default_joint_pos, soft_joint_pos_limits=v.soft_joint_pos_limits,
+    action_scale=v.action_scale, linvel_adr=v.linvel_adr, angvel_adr=v.angvel_adr, selfcol_adr=v.selfcol_adr, noise_lo=lo, noise_hi=hi,
+    n_obs_policy=n_pol, n_obs_critic=n_pol + 9 * nb, time_step_total=int(time_step_total),
+    bin_count=int(time_step_total // (1 / step_dt)) + 1,
+    reward_weights=np.array([0.5, 0.5, 1.0, 1.0, 1.0, 1.0, -0.1, -10.0, -10.0]), step_dt=step_dt,
+    max_episode_length=math.ceil(int(1e9) / step_dt) if play else 500, max_episode_length_s=float(int(1e9)) if play else 10.0,
+    sampling_mode="start" if play else "adaptive",
+    pose_range=r6({} if play else {"x": (-0.05, 0.05), "y": (-0.05, 0.05), "z": (-0.01, 0.01), "roll": (-0.1, 0.1), "pitch": (-0.1, 0.1), "yaw": (-0.2, 0.2)}),
+    velocity_range=r6({} if play else _TRACKING_VELOCITY_RANGE), push_vel=r6(_TRACKING_VELOCITY_RANGE),
+    enable_corruption=not play, push_enabled=not play,
+  )

@@ -1,0 +1,310 @@
+"""`ManagerBasedRlEnv` for the motion-tracking task (`Mjlab-Tracking-Flat-Unitree-G1`) on the B200 engine.
+
+Mirror of the reference env configured by src/mjlab/tasks/tracking/tracking_env_cfg.py:44-317 and
+config/g1/env_cfgs.py:15-100 (BeyondMimic re-implementation): the `MotionCommand` (src/mjlab/tasks/tracking/mdp/commands.py)
+plays a reference clip, the policy tracks it.  Same public surface as `mjlab_b200.env.ManagerBasedRlEnv`; one env step is
+one CUDA graph of the kernels behind include/b200trk.h:
+
+    b2_trk_action -> decimation x b2_step -> b2_trk_post (terminations, 9 rewards, resets incl. start-frame sampling)
+    -> conditional forward -> b2_trk_obs (metrics, frame advance, anchor-relative targets, push, observations) -> b2_trk_log
+
+Startup domain randomisation as in the reference (tracking_env_cfg.py:179-208): torso COM offset (`body_ipos`, add),
+encoder bias, foot friction.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+from typing import Any, Literal
+
+import numpy as np
+import torch
+
+from . import engine as E
+from . import envcfg
+from . import trkabi as A
+from .entity import Entity
+from .env import _TORCH, env_origins_grid
+from .motion import MotionLoader, synthetic_motion
+from .sim import MujocoCfg, Simulation, SimulationCfg
+
+
+def _default_sim_cfg() -> SimulationCfg:
+  # tasks/tracking/tracking_env_cfg.py:305-313
+  return SimulationCfg(nconmax=35, njmax=250, mujoco=MujocoCfg(timestep=0.005, iterations=10, ls_iterations=20))
+
+
+@dataclass
+class TrackingEnvCfg:
+  num_envs: int = 4096
+  play: bool = False
+  seed: int = 42
+  decimation: int = 4
+  env_spacing: float = 2.0
+  motion_file: str | None = None          # npz in the reference's format; None -> the synthetic clip of SURVEY 8(d)
+  synthetic_frames: int = 500
+  sampling_mode: Literal["adaptive", "uniform", "start"] | None = None   # None: "adaptive" (train) / "start" (play)
+  domain_randomization: bool = True
+  forward_mode: Literal["reference", "masked"] = "reference"
+  log_metrics: bool = True
+  sim: SimulationCfg = field(default_factory=_default_sim_cfg)
+
+
+class TrackingRlEnv:
+  is_vector_env = True
+
+  def __init__(self, cfg: TrackingEnvCfg, device: str = "cuda:0", render_mode: str | None = None, **kwargs: Any):
+    from . import load_model
+    self.cfg, self.device, self.render_mode = cfg, device, render_mode
+    self._lib = A.load_library()
+    model = load_model("g1_flat")
+    dev = torch.device(device)
+    self._dev = dev
+    if cfg.motion_file is not None:
+      motion = dict(np.load(cfg.motion_file))
+    else:
+      motion = synthetic_motion(model, cfg.synthetic_frames, device=device)
+    self.sim = Simulation(cfg.num_envs, cfg.sim, model, device)
+    self.vcfg = envcfg.tracking_cfg(model, motion["joint_pos"].shape[0], play=cfg.play)
+    self.vcfg.seed = int(cfg.seed)
+    if cfg.sampling_mode is not None:
+      self.vcfg.sampling_mode = cfg.sampling_mode
+    self.vcfg.step_dt = cfg.decimation * cfg.sim.mujoco.timestep
+    n = cfg.num_envs
+    torch.manual_seed(cfg.seed)
+    self.motion = MotionLoader(motion, torch.as_tensor(self.vcfg.body_sel, device=dev), device=device)
+
+    self._ce = A.B2Trk()
+    A.fill_params(self._ce, self.vcfg)
+    tables = A.table_values(self.vcfg)
+    self._buf: dict[str, torch.Tensor] = {}
+    for i, (_, attr, kind, dt, shp) in enumerate(A.BUFFERS):
+      if kind == "table":
+        t = torch.as_tensor(np.ascontiguousarray(np.asarray(tables[attr])), device=dev).to(_TORCH[dt]).contiguous()
+      elif kind == "motion":
+        t = torch.as_tensor(np.ascontiguousarray(motion[attr]), dtype=torch.float32, device=dev).contiguous()
+      elif kind == "state":
+        t = torch.zeros((n,) + tuple(shp(self.vcfg)), dtype=_TORCH[dt], device=dev)
+      else:
+        t = torch.zeros(tuple(shp(self.vcfg)), dtype=_TORCH[dt], device=dev)
+      self._buf["m_" + attr if kind == "motion" else attr] = t
+      self._ce.buf[i] = t.data_ptr()
+    self._buf["rel_quat"][..., 0] = 1.0
+    self._buf["env_origins"][:] = torch.as_tensor(env_origins_grid(n, cfg.env_spacing), device=dev)
+    if self.vcfg.push_enabled:
+      lo, hi = self.vcfg.push_interval
+      self._buf["push_time_left"][:] = torch.rand(n, device=dev) * (hi - lo) + lo
+    E.check_call(self._lib, self._lib.b2_trk_check(C.byref(self.sim._cm), C.byref(self.sim._cd), C.byref(self._ce)))
+
+    self.robot = Entity("robot", self.sim, joint_pos_target=self._buf["joint_pos_target"], encoder_bias=self._buf["encoder_bias"])
+    self.scene = {"robot": self.robot}
+    self.extras: dict[str, Any] = {"log": {}}
+    self.common_step_counter = 0
+    self.obs_buf = {"policy": self._buf["obs_policy"], "critic": self._buf["obs_critic"]}
+    self.reward_buf = self._buf["reward"]
+    self.reset_buf = self._buf["reset_buf"].view(torch.bool)
+    self.reset_terminated = self._buf["terminated"].view(torch.bool)
+    self.reset_time_outs = self._buf["time_outs"].view(torch.bool)
+
+    if cfg.domain_randomization:   # startup events (tracking_env_cfg.py:179-208)
+      from .events import randomize_field
+      self.sim.expand_model_fields(("body_ipos", "geom_friction"))
+      randomize_field(self, None, "body_ipos", {0: (-0.025, 0.025), 1: (-0.05, 0.05), 2: (-0.05, 0.05)}, operation="add", body_names=("torso_link",))
+      randomize_field(self, None, "geom_friction", (0.3, 1.2), operation="abs", geom_names=r"^(left|right)_foot[1-7]_collision$")
+      self._buf["encoder_bias"][:] = torch.rand(n, self.vcfg.nj, device=dev) * 0.02 - 0.01   # randomize_encoder_bias, events.py:709-744
+
+    self._graph: torch.cuda.CUDAGraph | None = None
+    self.use_cuda_graph = os.environ.get("B200SIM_NO_GRAPH", "0") != "1"
+    self._capture()
+
+  num_envs = property(lambda self: self.cfg.num_envs)
+  physics_dt = property(lambda self: self.cfg.sim.mujoco.timestep)
+  step_dt = property(lambda self: self.cfg.sim.mujoco.timestep * self.cfg.decimation)
+  max_episode_length_s = property(lambda self: self.vcfg.max_episode_length_s)
+  max_episode_length = property(lambda self: self.vcfg.max_episode_length)
+  unwrapped = property(lambda self: self)
+  launches_per_step = property(lambda self: 1 + 4 * self.cfg.decimation + 2 + 4 + 1 + 1)
+
+  @property
+  def episode_length_buf(self) -> torch.Tensor:
+    return self._buf["episode_length"]
+
+  @episode_length_buf.setter
+  def episode_length_buf(self, value: torch.Tensor) -> None:
+    self._buf["episode_length"].copy_(value)
+
+  # minimal manager facades (same attribute names as the reference's managers)
+  class _AM:
+    def __init__(self, env):
+      self._e = env
+    total_action_dim = property(lambda self: self._e.vcfg.nj)
+    action = property(lambda self: self._e._buf["action"])
+    prev_action = property(lambda self: self._e._buf["prev_action"])
+
+  class _OM:
+    def __init__(self, env):
+      self._e = env
+
+    def compute(self, update_history: bool = False):
+      return self._e.obs_buf
+
+  class _CM:
+    def __init__(self, env):
+      self._e = env
+    time_steps = property(lambda self: self._e._buf["time_steps"])
+    body_pos_relative_w = property(lambda self: self._e._buf["rel_pos"])
+    body_quat_relative_w = property(lambda self: self._e._buf["rel_quat"])
+    bin_failed_count = property(lambda self: self._e._buf["bin_failed_count"])
+    metrics = property(lambda self: {n: self._e._buf["metrics"][:, k] for k, n in enumerate(
+      ("error_anchor_pos", "error_anchor_rot", "error_anchor_lin_vel", "error_anchor_ang_vel", "error_body_pos", "error_body_rot",
+       "error_joint_pos", "error_joint_vel"))})
+
+    def get_command(self, name: str) -> torch.Tensor:
+      e = self._e
+      t = e._buf["time_steps"]
+      return torch.cat([e.motion.joint_pos[t], e.motion.joint_vel[t]], dim=1)
+
+  class _TM:
+    active_terms = list(envcfg.TRACKING_TERMINATION_NAMES)
+
+    def __init__(self, env):
+      self._e = env
+    terminated = property(lambda self: self._e._buf["terminated"].view(torch.bool))
+    time_outs = property(lambda self: self._e._buf["time_outs"].view(torch.bool))
+
+    def get_term(self, name: str) -> torch.Tensor:
+      return self._e._buf["term_dones"][:, self.active_terms.index(name)].view(torch.bool)
+
+  class _RM:
+    active_terms = list(envcfg.TRACKING_REWARD_NAMES)
+
+    def __init__(self, env):
+      self._e = env
+    _step_reward = property(lambda self: self._e._buf["step_reward"])
+    _episode_sums = property(lambda self: {n: self._e._buf["episode_sums"][:, k] for k, n in enumerate(self.active_terms)})
+
+  action_manager = property(lambda self: TrackingRlEnv._AM(self))
+  observation_manager = property(lambda self: TrackingRlEnv._OM(self))
+  command_manager = property(lambda self: TrackingRlEnv._CM(self))
+  termination_manager = property(lambda self: TrackingRlEnv._TM(self))
+  reward_manager = property(lambda self: TrackingRlEnv._RM(self))
+
+  def _stream(self) -> int:
+    return torch.cuda.current_stream(self._dev).cuda_stream
+
+  def _enqueue_step(self) -> None:
+    lib, m, d, e, chk = self._lib, C.byref(self.sim._cm), C.byref(self.sim._cd), C.byref(self._ce), E.check_call
+    st = self._stream()
+    chk(lib, lib.b2_trk_action(m, d, e, st))
+    for _ in range(self.cfg.decimation):
+      chk(lib, lib.b2_step(m, d, st))
+    chk(lib, lib.b2_trk_post(m, d, e, st))
+    mask = self._buf["reset_buf"].data_ptr() if self.cfg.forward_mode == "masked" else None
+    chk(lib, lib.b2_forward_masked(m, d, mask, self._buf["any_reset"].data_ptr(), st))
+    chk(lib, lib.b2_trk_obs(m, d, e, 1, st))
+    chk(lib, lib.b2_trk_log(d, e, st))
+
+  def _capture(self) -> None:
+    self._graph = None
+    if not self.use_cuda_graph:
+      return
+    torch.cuda.synchronize(self._dev)
+    side = torch.cuda.Stream(self._dev)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+      with torch.cuda.graph(g, stream=side):
+        self._enqueue_step()
+    torch.cuda.current_stream(self._dev).wait_stream(side)
+    self._graph = g
+
+  def seed(self, seed: int = -1) -> int:
+    if seed == -1:
+      seed = int(np.random.randint(0, 10_000))
+    self.vcfg.seed = int(seed)
+    self._ce.seed = int(seed) & (2**64 - 1)
+    torch.manual_seed(seed)
+    self._capture()
+    return seed
+
+  def reset(self, *, seed: int | None = None, env_ids: torch.Tensor | None = None, options: dict | None = None):
+    del options
+    if seed is not None:
+      self.seed(seed)
+    lib, m, d, e = self._lib, C.byref(self.sim._cm), C.byref(self.sim._cd), C.byref(self._ce)
+    mask = None
+    if env_ids is not None:
+      mt = torch.zeros(self.num_envs, dtype=torch.uint8, device=self._dev)
+      mt[env_ids] = 1
+      mask = mt.data_ptr()
+    st = self._stream()
+    E.check_call(lib, lib.b2_trk_reset(m, d, e, mask, st))
+    E.check_call(lib, lib.b2_forward(m, d, st))
+    E.check_call(lib, lib.b2_trk_obs(m, d, e, 0, st))
+    self._publish_log()
+    return self.obs_buf, self.extras
+
+  def step(self, action: torch.Tensor):
+    if action.shape[-1] != self.vcfg.nj:
+      raise ValueError(f"Invalid action shape, expected: {self.vcfg.nj}, received: {action.shape[-1]}.")
+    self._buf["action_in"].copy_(action, non_blocking=True)
+    if self._graph is not None:
+      self._graph.replay()
+    else:
+      self._enqueue_step()
+    self.common_step_counter += 1
+    self._publish_log()
+    return self.obs_buf, self.reward_buf, self.reset_terminated, self.reset_time_outs, self.extras
+
+  def _publish_log(self) -> None:
+    if self.cfg.log_metrics:
+      self.extras["log"] = _TrkLog(self, self._buf["log"].clone())
+
+  def get_observations(self):
+    return self.obs_buf
+
+  def close(self) -> None:
+    self._graph = None
+
+
+class _TrkLog(dict):
+  """extras["log"]: resolved lazily from a snapshot of the device log sums (one small D2H on first access)."""
+
+  def __init__(self, env: TrackingRlEnv, snap: torch.Tensor):
+    super().__init__()
+    self._env, self._snap, self._done = env, snap, False
+
+  def _resolve(self):
+    if not self._done:
+      v, K, cfg = self._snap.tolist(), A.K, self._env.vcfg
+      n = max(v[K["B2T_LOG_NRESET"]], 1.0)
+      for k, name in enumerate(envcfg.TRACKING_REWARD_NAMES):
+        super().__setitem__("Episode_Reward/" + name, v[K["B2T_LOG_EPISODE_SUM"] + k] / n / cfg.max_episode_length_s)
+      for k, name in enumerate(envcfg.TRACKING_TERMINATION_NAMES):
+        super().__setitem__("Episode_Termination/" + name, v[K["B2T_LOG_TERM_COUNT"] + k])
+      for k, name in enumerate(("error_anchor_pos", "error_anchor_rot", "error_anchor_lin_vel", "error_anchor_ang_vel", "error_body_pos",
+                                "error_body_rot", "error_joint_pos", "error_joint_vel")):
+        super().__setitem__("Metrics/motion/" + name, v[K["B2T_LOG_METRIC"] + k] / n)
+      super().__setitem__("Episode/num_resets", v[K["B2T_LOG_NRESET"]])
+      self._done = True
+
+  def __getitem__(self, k):
+    self._resolve()
+    return super().__getitem__(k)
+
+  def __iter__(self):
+    self._resolve()
+    return super().__iter__()
+
+  def __len__(self):
+    self._resolve()
+    return super().__len__()
+
+  def keys(self):
+    self._resolve()
+    return super().keys()
+
+  def items(self):
+    self._resolve()
+    return super().items()

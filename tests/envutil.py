@@ -26,3 +26,21 @@ def init_state_from_golden(s, g):
   s.is_heading[:] = g["is_heading"]
   s.is_standing[:] = g["is_standing"]
   s.episode_length[:] = g["episode_len0"]
+
+
+def snapshot_from(name):
+  """path of a golden fixture; snapshot_from.load(g, t, m) -> data namespace of env step t."""
+  return GOLDEN / f"{name}.npz"
+
+
+def _load(g, t, m, dtype=np.float32):
+  d = NS(**{f: np.array(g[f"data_{f}"][t], dtype) for f in FIELDS if f"data_{f}" in g.files})
+  B = d.qpos.shape[0]
+  d.ctrl = np.zeros((B, m.nu), dtype)
+  d.qacc_warmstart = np.zeros((B, m.nv), dtype)
+  d.qacc = np.zeros((B, m.nv), dtype)
+  d.time = np.zeros(B, dtype)
+  return d
+
+
+snapshot_from.load = _load

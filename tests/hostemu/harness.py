@@ -16,6 +16,7 @@ import numpy as np
 
 from mjlab_b200 import engine as E
 from mjlab_b200 import envabi as A
+from mjlab_b200 import trkabi as TA
 
 HERE = Path(__file__).resolve().parent
 ROOT = HERE.parents[1]
@@ -135,3 +136,45 @@ class HostEnv:
   def forward_masked(self, mask=None) -> None:
     ptr = None if mask is None else np.ascontiguousarray(mask, np.uint8).ctypes.data
     self.sim.lib.b2h_forward_masked(C.byref(self.sim.cm), C.byref(self.sim.cd), C.c_void_p(ptr))
+
+
+class HostTrk:
+  """The tracking-env device code (b2_trk.cuh) host-emulated on top of a HostSim."""
+
+  def __init__(self, sim: HostSim, cfg, motion: dict, inject=False):
+    self.sim, self.cfg = sim, cfg
+    assert sim.lib.b2h_sizeof_trk() == C.sizeof(TA.B2Trk)
+    self.ce = TA.B2Trk()
+    TA.fill_params(self.ce, cfg)
+    tables = TA.table_values(cfg)
+    self.bufs = {}
+    for i, (_, attr, kind, dt, shp) in enumerate(TA.BUFFERS):
+      dtype = sim.dtype if dt == "f4" else _NP[dt]
+      if kind == "table":
+        a = np.ascontiguousarray(np.asarray(tables[attr]).astype(dtype))
+      elif kind == "motion":
+        a = np.ascontiguousarray(np.asarray(motion[attr]).astype(dtype))
+      elif kind == "state":
+        a = np.zeros((sim.nworld,) + tuple(shp(cfg)), dtype)
+      else:
+        a = np.zeros(tuple(shp(cfg)), dtype)
+      self.bufs["m_" + attr if kind == "motion" else attr] = a
+      self.ce.buf[i] = a.ctypes.data
+    self.bufs["rel_quat"][..., 0] = 1
+    self.inject = None
+    if inject:
+      self.inject = np.zeros((sim.nworld, TA.NDRAW), sim.dtype)
+      self.ce.buf[TA.K["B2T_B_INJECT_U"]] = self.inject.ctypes.data
+
+  def __getattr__(self, name):
+    try:
+      return self.__dict__["bufs"][name]
+    except KeyError:
+      raise AttributeError(name) from None
+
+  def refresh(self):
+    TA.fill_params(self.ce, self.cfg)
+
+  def stage(self, k: int) -> None:
+    rc = self.sim.lib.b2h_trk_stage(C.byref(self.sim.cm), C.byref(self.sim.cd), C.byref(self.ce), k)
+    assert rc == 0

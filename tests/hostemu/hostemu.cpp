@@ -13,6 +13,7 @@
 #include "../../mjlab_b200/csrc/b2_smooth.cuh"
 #include "../../mjlab_b200/csrc/b2_solve.cuh"
 #include "../../mjlab_b200/csrc/b2_env.cuh"
+#include "../../mjlab_b200/csrc/b2_trk.cuh"
 
 extern "C" {
 
@@ -83,4 +84,37 @@ int b2h_forward_masked(const KModel* m, KData* d, const unsigned char* mask) {
   return 0;
 }
 float b2h_dc_clip(float effort, float vel, float limit, float sat, float vlim) { return b2_dc_clip(effort, vel, limit, sat, vlim); }
+
+// ---- tracking env (b2_trk.cuh) ----
+int b2h_sizeof_trk(void) { return (int)sizeof(KTrk); }
+int b2h_trk_stage(const KModel* m, KData* d, const KTrk* e, int stage) {
+  for (int w = 0; w < d->nworld; ++w) {
+    switch (stage) {
+      case 0: trk_action_world(*m, *d, *e, w); break;
+      case 2: trk_post_world(*m, *d, *e, w); break;
+      case 3: trk_obs_world(*m, *d, *e, w, 1); break;
+      default: return 1;
+    }
+  }
+  if (stage == 2 || stage == 3) {
+    real* log_env = reinterpret_cast<real*>(e->buf[B2T_B_LOG_ENV]);
+    real* log = reinterpret_cast<real*>(e->buf[B2T_B_LOG]);
+    for (int c = 0; c < B2T_NLOG; ++c) {
+      real acc = 0;
+      for (int w = 0; w < d->nworld; ++w) acc += log_env[(size_t)w * B2T_NLOG + c];
+      if (stage == 3 || c == B2T_LOG_NRESET) log[c] = acc;
+    }
+    if (stage == 2) reinterpret_cast<int*>(e->buf[B2T_B_ANY_RESET])[0] = (int)log[B2T_LOG_NRESET];
+    if (stage == 3) {
+      reinterpret_cast<long long*>(e->buf[B2T_B_STEP_COUNTER])[0] += 1;
+      if (e->ip[B2T_IP_SAMPLING_MODE] == 2) {
+        real* bfc = reinterpret_cast<real*>(e->buf[B2T_B_BIN_FAILED_COUNT]);
+        real* cur = reinterpret_cast<real*>(e->buf[B2T_B_CURRENT_BIN_FAILED]);
+        const real alpha = (real)e->fp[B2T_FP_ADAPTIVE_ALPHA];
+        for (int b = 0; b < e->ip[B2T_IP_BIN_COUNT]; ++b) { bfc[b] = alpha * cur[b] + (1 - alpha) * bfc[b]; cur[b] = 0; }
+      }
+    }
+  }
+  return 0;
+}
 }
