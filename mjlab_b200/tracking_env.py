@@ -55,7 +55,8 @@ class TrackingEnvCfg:
 class TrackingRlEnv:
   is_vector_env = True
 
-  def __init__(self, cfg: TrackingEnvCfg, device: str = "cuda:0", render_mode: str | None = None, **kwargs: Any):
+  def __init__(self, cfg: TrackingEnvCfg, device: str = "cuda:0", render_mode: str | None = None, vcfg_edit=None, **kwargs: Any):
+    """`vcfg_edit(resolved_cfg)` may adjust the resolved task parameters before the buffers are sized (tests, curricula)."""
     from . import load_model
     self.cfg, self.device, self.render_mode = cfg, device, render_mode
     self._lib = A.load_library()
@@ -72,6 +73,8 @@ class TrackingRlEnv:
     if cfg.sampling_mode is not None:
       self.vcfg.sampling_mode = cfg.sampling_mode
     self.vcfg.step_dt = cfg.decimation * cfg.sim.mujoco.timestep
+    if vcfg_edit is not None:
+      vcfg_edit(self.vcfg)
     n = cfg.num_envs
     torch.manual_seed(cfg.seed)
     self.motion = MotionLoader(motion, torch.as_tensor(self.vcfg.body_sel, device=dev), device=device)

@@ -46,7 +46,8 @@ _bound = False
 
 def load_library() -> C.CDLL:
   global _bound
-  lib = E.load_library()
+  from . import envabi
+  lib = envabi.load_library()   # also binds b2_forward_masked and the other shared entry points
   if _bound:
     return lib
   pm, pd, pe, vp = C.POINTER(E.B2Model), C.POINTER(E.B2Data), C.POINTER(B2Trk), C.c_void_p
