@@ -46,6 +46,8 @@ def parse():
   ap.add_argument("--warmup", type=int, default=20)
   ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
   ap.add_argument("--model", default="g1_flat")
+  ap.add_argument("--task", default="velocity", choices=["velocity", "tracking"],
+                  help="velocity (BASELINE configs 2/3, the headline) or tracking (config 5: synthetic clip, domain randomisation on)")
   ap.add_argument("--num-envs", type=int, default=NUM_ENVS)
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-roofline-pass", action="store_true")
@@ -217,7 +219,11 @@ def run_reference(args):
   print(json.dumps(line))
 
 
-def workload_name(model: str, num_envs: int, forward_mode: str = "reference") -> str:
+def workload_name(model: str, num_envs: int, forward_mode: str = "reference", task: str = "velocity") -> str:
+  if task == "tracking":
+    return (f"{model} motion-tracking task (synthetic 500-frame clip, domain randomisation on), env step, {num_envs} envs/GPU: action -> ctrl, "
+            f"{DECIMATION} physics steps, 4 terminations, 9 reward terms, resets with adaptive start-frame sampling, forward after resets "
+            f"({forward_mode}), frame advance + anchor-relative targets, push events, observations (policy 160 + critic 286, noise) - one CUDA graph")
   return (f"{model} velocity task, ManagerBasedRlEnv.step, {num_envs} envs/GPU: action -> ctrl, {DECIMATION} x (physics step + "
           "contact air-time update), terminations, 14 reward terms, resets (sim + events + managers), "
           f"forward after resets ({forward_mode}), commands, push events, observations (policy+critic, noise) - one CUDA graph")
@@ -246,7 +252,13 @@ def run_b200(args):
   nw = args.num_envs
   robot = args.model.split("_")[0]
   # one independent world batch per rank, seed + rank (src/mjlab/scripts/train.py:59)
-  env = ManagerBasedRlEnv(VelocityEnvCfg(robot=robot, num_envs=nw, seed=42 + rank, forward_mode=args.forward_mode), dev)
+  def make_env(forward_mode):
+    if args.task == "tracking":
+      from mjlab_b200.tracking_env import TrackingEnvCfg, TrackingRlEnv
+      return TrackingRlEnv(TrackingEnvCfg(num_envs=nw, seed=42 + rank, forward_mode=forward_mode), dev)
+    return ManagerBasedRlEnv(VelocityEnvCfg(robot=robot, num_envs=nw, seed=42 + rank, forward_mode=forward_mode), dev)
+
+  env = make_env(args.forward_mode)
   m, cfg = env.sim.mj_model, env.vcfg
   sim = env.sim
   nj = cfg.nj
@@ -338,21 +350,23 @@ def run_b200(args):
     for k in range(nroof):
       flush.zero_()
       env._buf["action_in"].copy_(acts[k])
-      timed("k_env_action", lambda st: lib.b2_env_action(pm, pd, pe, st))
+      trk = args.task == "tracking"
+      timed("k_env_action", lambda st: (lib.b2_trk_action if trk else lib.b2_env_action)(pm, pd, pe, st))
       for _ in range(DECIMATION):
         timed("k_smooth", lambda st: lib.b2_stage(pm, pd, 0, 1, st))
         timed("k_solve", lambda st: lib.b2_stage(pm, pd, 1, 1, st))
         timed("k_post", lambda st: lib.b2_stage(pm, pd, 2, 1, st))
-        timed("k_env_airtime", lambda st: lib.b2_env_airtime(pm, pd, pe, st))
-      timed("k_env_post", lambda st: lib.b2_env_post(pm, pd, pe, st))
+        if not trk:
+          timed("k_env_airtime", lambda st: lib.b2_env_airtime(pm, pd, pe, st))
+      timed("k_env_post", lambda st: (lib.b2_trk_post if trk else lib.b2_env_post)(pm, pd, pe, st))
       timed("forward_after_reset", lambda st: lib.b2_forward_masked(pm, pd, mask, gate, st))
-      timed("k_env_obs", lambda st: lib.b2_env_obs(pm, pd, pe, 1, st))
-      timed("k_env_log", lambda st: lib.b2_env_log(pd, pe, st))
+      timed("k_env_obs", lambda st: (lib.b2_trk_obs if trk else lib.b2_env_obs)(pm, pd, pe, 1, st))
+      timed("k_env_log", lambda st: (lib.b2_trk_log if trk else lib.b2_env_log)(pd, pe, st))
     barrier()
     avg = {k: statistics.mean(a.elapsed_time(b) for a, b in v) for k, v in times.items()}
     per_step = {k: avg[k] * len(v) / nroof for k, v in times.items()}
     b_smooth, b_solve = algorithmic_bytes(m)
-    b_env = DECIMATION * (b_smooth + b_solve) + 4 * (cfg.n_obs_policy + cfg.n_obs_critic + nj + 3)
+    b_env = DECIMATION * (b_smooth + b_solve) + 4 * (cfg.n_obs_policy + cfg.n_obs_critic + nj + 3)   # B_env
     peaks = {}
     try:
       peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
@@ -377,7 +391,7 @@ def run_b200(args):
   # ---- secondary number: forward pass restricted to the reset envs (not the reference's behaviour; reported, not the headline)
   alt = None
   if args.forward_mode == "reference" and not args.no_roofline_pass:
-    env2 = ManagerBasedRlEnv(VelocityEnvCfg(robot=robot, num_envs=nw, seed=42 + rank, forward_mode="masked"), dev)
+    env2 = make_env("masked")
     env2.reset()
     env2.episode_length_buf = env.episode_length_buf.clone()
     for k in range(warm):
@@ -413,7 +427,7 @@ def run_b200(args):
       "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
       "warmup": warm, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
       "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-      "config": {"workload": workload_name(args.model, nw, args.forward_mode), "num_envs_per_gpu": nw, "decimation": DECIMATION,
+      "config": {"workload": workload_name(args.model, nw, args.forward_mode, args.task), "num_envs_per_gpu": nw, "decimation": DECIMATION,
                  "timestep": 0.005, "nconmax": 35, "njmax": 300, "parallelism": f"replicas x{world} (no physics collective)",
                  "l2": "256 MiB flush between timed steps", "actions": "U(-1,1) redrawn every env step (random policy)",
                  "forward_mode": args.forward_mode, "mean_resets_per_step": mean_resets,
@@ -427,7 +441,7 @@ def run_b200(args):
       line["roofline"] = roof
     if alt is not None:
       line["config"]["alt_masked_forward"] = alt
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.task == "velocity":
       v, secs = cpu_env_steps_per_s(args.model, 1, 4, 2)
       line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": 1, "kind": "port",
                               "sample": f"4 worlds x 2 env steps (x{DECIMATION} physics steps + env stage) of the same workload, "

@@ -1,8 +1,9 @@
-"""Train the velocity task with the PPO learner on the B200 engine (the reference's `train` CLI for this task,
-src/mjlab/scripts/train.py:46-171, minus logging / checkpoint plumbing).
+"""Train a task with the PPO learner on the B200 engine (the reference's `train` CLI, src/mjlab/scripts/train.py:46-171,
+minus logging / checkpoint plumbing).
 
-  python tools/train_velocity.py --robot g1 --num-envs 4096 --iterations 300
-  python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/train_velocity.py ...   # --gpu-ids path
+  python tools/train.py --task velocity --robot g1 --num-envs 4096 --iterations 300
+  python tools/train.py --task tracking --iterations 300                       # synthetic clip unless --motion-file is given
+  python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/train.py ...   # --gpu-ids path
 """
 import argparse
 import json
@@ -20,6 +21,8 @@ from mjlab_b200.ppo import OnPolicyRunner, PpoCfg  # noqa: E402
 from mjlab_b200.vecenv import RslRlVecEnvWrapper  # noqa: E402
 
 ap = argparse.ArgumentParser()
+ap.add_argument("--task", default="velocity", choices=["velocity", "tracking"])
+ap.add_argument("--motion-file", default=None)
 ap.add_argument("--robot", default="g1")
 ap.add_argument("--num-envs", type=int, default=4096)
 ap.add_argument("--iterations", type=int, default=300)
@@ -32,7 +35,11 @@ torch.cuda.set_device(local)
 dev = f"cuda:{local}"
 if world > 1:
   dist.init_process_group("nccl", device_id=torch.device(dev))
-env = ManagerBasedRlEnv(VelocityEnvCfg(robot=a.robot, num_envs=a.num_envs, seed=42 + rank, forward_mode=a.forward_mode), dev)
+if a.task == "tracking":
+  from mjlab_b200.tracking_env import TrackingEnvCfg, TrackingRlEnv
+  env = TrackingRlEnv(TrackingEnvCfg(num_envs=a.num_envs, seed=42 + rank, forward_mode=a.forward_mode, motion_file=a.motion_file), dev)
+else:
+  env = ManagerBasedRlEnv(VelocityEnvCfg(robot=a.robot, num_envs=a.num_envs, seed=42 + rank, forward_mode=a.forward_mode), dev)
 runner = OnPolicyRunner(RslRlVecEnvWrapper(env), PpoCfg())
 torch.cuda.synchronize()
 t0 = time.perf_counter()
@@ -41,7 +48,7 @@ torch.cuda.synchronize()
 dt = time.perf_counter() - t0
 if rank == 0:
   sps = a.iterations * 24 * a.num_envs * world / dt
-  summary = {"robot": a.robot, "num_envs_per_gpu": a.num_envs, "n_gpus": world, "iterations": a.iterations, "wall_s": dt, "train_env_steps_per_s": sps,
+  summary = {"task": a.task, "robot": a.robot, "num_envs_per_gpu": a.num_envs, "n_gpus": world, "iterations": a.iterations, "wall_s": dt, "train_env_steps_per_s": sps,
              "first": hist[0], "last": hist[-1]}
   print(json.dumps(summary))
   if a.out:
