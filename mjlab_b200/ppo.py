@@ -46,6 +46,9 @@ class PpoCfg:
   use_clipped_value_loss: bool = True
   clip_param: float = 0.2
   clip_actions: float | None = None
+  # "high": TF32 tensor-core GEMMs for the actor / critic (the one place of the training loop where tensor cores apply;
+  # mini-batches of 24 576 x 512); "highest" = rsl_rl's plain fp32
+  matmul_precision: str = "high"
   seed: int = 42
   obs_groups: dict = field(default_factory=lambda: {"policy": ("policy",), "critic": ("critic",)})
 
@@ -134,6 +137,7 @@ class OnPolicyRunner:
   def __init__(self, venv, cfg: PpoCfg | None = None, device: str | None = None):
     self.env, self.cfg = venv, cfg or PpoCfg()
     self.device = torch.device(device or venv.device)
+    torch.set_float32_matmul_precision(self.cfg.matmul_precision)
     self.distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
     self.world_size = dist.get_world_size() if self.distributed else 1
     self.rank = dist.get_rank() if self.distributed else 0

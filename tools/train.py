@@ -29,6 +29,7 @@ ap.add_argument("--iterations", type=int, default=300)
 ap.add_argument("--forward-mode", default="reference")
 ap.add_argument("--log-every", type=int, default=10)
 ap.add_argument("--out", default="")
+ap.add_argument("--matmul-precision", default="high", choices=["highest", "high"])
 a = ap.parse_args()
 world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
@@ -40,15 +41,22 @@ if a.task == "tracking":
   env = TrackingRlEnv(TrackingEnvCfg(num_envs=a.num_envs, seed=42 + rank, forward_mode=a.forward_mode, motion_file=a.motion_file), dev)
 else:
   env = ManagerBasedRlEnv(VelocityEnvCfg(robot=a.robot, num_envs=a.num_envs, seed=42 + rank, forward_mode=a.forward_mode), dev)
-runner = OnPolicyRunner(RslRlVecEnvWrapper(env), PpoCfg())
+runner = OnPolicyRunner(RslRlVecEnvWrapper(env), PpoCfg(matmul_precision=a.matmul_precision))
 torch.cuda.synchronize()
 t0 = time.perf_counter()
 hist = runner.learn(a.iterations, log_every=a.log_every)
 torch.cuda.synchronize()
 dt = time.perf_counter() - t0
+# split of one iteration: roll-out (env steps + policy inference) vs PPO update
+torch.cuda.synchronize(); t1 = time.perf_counter()
+ro = runner.collect()
+torch.cuda.synchronize(); t2 = time.perf_counter()
+runner.update(ro)
+torch.cuda.synchronize(); t3 = time.perf_counter()
 if rank == 0:
   sps = a.iterations * 24 * a.num_envs * world / dt
   summary = {"task": a.task, "robot": a.robot, "num_envs_per_gpu": a.num_envs, "n_gpus": world, "iterations": a.iterations, "wall_s": dt, "train_env_steps_per_s": sps,
+             "iteration_split_ms": {"rollout_24_steps": 1e3 * (t2 - t1), "ppo_update": 1e3 * (t3 - t2)},
              "first": hist[0], "last": hist[-1]}
   print(json.dumps(summary))
   if a.out:
