@@ -32,6 +32,7 @@ typedef B2_REAL real;
 B2_DEV real b2_wsum(real x) { return x; }  // @region shuffle_reduce
 B2_DEV real b2_wmax(real x) { return x; }
 B2_DEV int b2_wsum_i(int x) { return x; }
+B2_DEV void b2_wsum3(real&, real&, real&) {}
 B2_DEV unsigned b2_ballot(bool p) { return p ? 1u : 0u; }
 B2_DEV int b2_wor_i(int x) { return x; }
 B2_DEV int b2_popc(unsigned x) { return __builtin_popcount(x); }
@@ -75,6 +76,23 @@ B2_DEV int b2_wor_i(int x) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) x |= __shfl_xor_sync(0xffffffffu, x, o);
   return x;
+}
+// Sums of three values over the warp with 9 shuffles instead of 15: after the xor-16 and xor-8 exchanges each lane
+// carries ONE of the (padded to four) values, the remaining three butterfly steps finish that value, three broadcasts
+// hand every lane all three sums.
+B2_DEV void b2_wsum3(real& a, real& b, real& c) {
+  const unsigned lane = threadIdx.x & 31;
+  const bool hi = lane & 16, mid = lane & 8;
+  real r1 = __shfl_xor_sync(0xffffffffu, hi ? a : c, 16);
+  real r2 = __shfl_xor_sync(0xffffffffu, hi ? b : (real)0, 16);
+  real A = (hi ? c : a) + r1, B = (hi ? (real)0 : b) + r2;      // !hi: (a, b) partial sums; hi: (c, 0)
+  real C = (mid ? B : A) + __shfl_xor_sync(0xffffffffu, mid ? A : B, 8);
+  C += __shfl_xor_sync(0xffffffffu, C, 4);
+  C += __shfl_xor_sync(0xffffffffu, C, 2);
+  C += __shfl_xor_sync(0xffffffffu, C, 1);
+  a = __shfl_sync(0xffffffffu, C, 0);
+  b = __shfl_sync(0xffffffffu, C, 8);
+  c = __shfl_sync(0xffffffffu, C, 16);
 }
 B2_DEV unsigned b2_ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
 B2_DEV int b2_popc(unsigned x) { return __popc(x); }

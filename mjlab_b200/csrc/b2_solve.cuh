@@ -117,7 +117,8 @@ B2_DEVN LsPnt ls_eval(real alpha, real q0g, real q1g, real q2g, const real* jar,
       q2 += (real)0.5 * D[r] * jv[r] * jv[r];
     }
   }
-  q0 = b2_wsum(q0) + q0g; q1 = b2_wsum(q1) + q1g; q2 = b2_wsum(q2) + q2g;
+  b2_wsum3(q0, q1, q2);
+  q0 += q0g; q1 += q1g; q2 += q2g;
   LsPnt p;
   p.alpha = alpha;
   p.cost = alpha * alpha * q2 + alpha * q1 + q0;
