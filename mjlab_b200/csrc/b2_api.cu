@@ -18,6 +18,9 @@ static_assert(sizeof(KModel) == sizeof(b2_model), "KModel must mirror b2_model")
 static_assert(sizeof(KData) == sizeof(b2_data), "KData must mirror b2_data");
 static_assert(sizeof(KEnv) == sizeof(b2_env), "KEnv must mirror b2_env");
 
+#ifndef B2_SMOOTH_WPB
+#define B2_SMOOTH_WPB 1   // worlds per CTA of k_smooth (finer scheduling granularity: -3 % vs 2)
+#endif
 #ifndef B2_WPB
 #define B2_WPB 2
 #endif
@@ -37,11 +40,11 @@ static int fail(const char* fmt, ...) {
   return 1;
 }
 
-__global__ void __launch_bounds__(B2_WPB * 32) k_smooth(const KModel m, const KData d, const SmoothSmem L, int ncand_max, const unsigned char* mask, const int* gate) {
+__global__ void __launch_bounds__(B2_SMOOTH_WPB * 32) k_smooth(const KModel m, const KData d, const SmoothSmem L, int ncand_max, const unsigned char* mask, const int* gate) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   real* smem = reinterpret_cast<real*>(smem_raw);
   int warp = threadIdx.x >> 5;
-  int w = blockIdx.x * B2_WPB + warp;
+  int w = blockIdx.x * B2_SMOOTH_WPB + warp;
   if (w >= d.nworld) return;
   if (gate && *gate == 0) return;
   if (mask && !mask[w]) return;
@@ -151,7 +154,7 @@ static int make_plan(const b2_model* m, const b2_data* d, Plan* p) {
   if (const char* e = getenv("B200SIM_ARENA")) arena = atoi(e);  // experiments
   p->lv = solve_smem_layout(m->nv, rows_max, m->maxchain, arena);
   p->lp = post_smem_layout(m->nv);
-  p->smem_smooth = (size_t)p->ls.total * sizeof(real) * B2_WPB;
+  p->smem_smooth = (size_t)p->ls.total * sizeof(real) * B2_SMOOTH_WPB;
   p->smem_solve = ((size_t)p->lv.fixed_total * B2_WPB + p->lv.arena_cap) * sizeof(real) + 16;
   p->smem_post = (size_t)p->lp.total * sizeof(real) * B2_POST_WPB;
   if (const char* e = getenv("B200SIM_SMEM_PAD")) p->smem_solve += (size_t)atoi(e);  // occupancy experiments only
@@ -199,7 +202,7 @@ static int run(const b2_model* m, b2_data* d, void* stream, int do_integrate, co
   const KModel& km = *reinterpret_cast<const KModel*>(m);
   const KData& kd = *reinterpret_cast<const KData*>(d);
   int grid = (d->nworld + B2_WPB - 1) / B2_WPB;
-  k_smooth<<<grid, B2_WPB * 32, p.smem_smooth, st>>>(km, kd, p.ls, B2_NCAND_MAX, mask, gate);
+  k_smooth<<<(d->nworld + B2_SMOOTH_WPB - 1) / B2_SMOOTH_WPB, B2_SMOOTH_WPB * 32, p.smem_smooth, st>>>(km, kd, p.ls, B2_NCAND_MAX, mask, gate);
   k_order<<<1, 1024, 0, st>>>(kd);
   k_solve<<<grid, B2_WPB * 32, p.smem_solve, st>>>(km, kd, p.lv, mask, gate);
   k_post<<<(d->nworld + B2_POST_WPB - 1) / B2_POST_WPB, B2_POST_WPB * 32, p.smem_post, st>>>(km, kd, p.lp, do_integrate, mask, gate);
@@ -217,7 +220,7 @@ int b2_stage(const b2_model* m, b2_data* d, int stage, int do_integrate, void* s
   const KData& kd = *reinterpret_cast<const KData*>(d);
   int grid = (d->nworld + B2_WPB - 1) / B2_WPB;
   if (stage == 0) {
-    k_smooth<<<grid, B2_WPB * 32, p.smem_smooth, st>>>(km, kd, p.ls, B2_NCAND_MAX, nullptr, nullptr);
+    k_smooth<<<(d->nworld + B2_SMOOTH_WPB - 1) / B2_SMOOTH_WPB, B2_SMOOTH_WPB * 32, p.smem_smooth, st>>>(km, kd, p.ls, B2_NCAND_MAX, nullptr, nullptr);
     k_order<<<1, 1024, 0, st>>>(kd);
     g_launches += 1;
   }
