@@ -36,7 +36,7 @@ sys.path.insert(0, str(ROOT))
 DECIMATION = 4
 NUM_ENVS = 4096
 # DRAM bytes per launch from the committed ncu captures of this workload (profiles/r01_final_k_*.txt)
-NCU_TRAFFIC_BYTES = {"k_solve": 38_520_832, "k_smooth": 37_670_400, "k_post": 53_158_656}
+NCU_TRAFFIC_BYTES = {"k_solve": 38_628_352, "k_smooth": 38_490_112, "k_post": 52_912_128}
 
 
 def parse():
