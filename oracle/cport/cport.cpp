@@ -1,0 +1,54 @@
+// cport.cpp - multi-threaded CPU build of the physics step for bench.py's CPU baseline (TEST / MEASUREMENT INFRASTRUCTURE).
+//
+// The physics algorithm is written once, in mjlab_b200/csrc/b2_{smooth,solve}.cuh, against a small execution-model shim
+// (b2_common.cuh): with -DB2_HOSTEMU the same source compiles as plain single-lane C++.  This file wraps that build in a
+// thread pool over worlds so that the CPU baseline of bench.py measures a compiled, all-cores implementation of the SAME
+// algorithm (float64), instead of the numpy oracle, whose interpreter overhead says nothing about CPUs.  It is not an
+// independent checker - parity is checked against oracle/mjstep.py (numpy, written separately) - and nothing under
+// mjlab_b200/ loads it.  Built by oracle/cport/Makefile into oracle/_build/libcport.so.
+#include <atomic>
+#include <thread>
+#include <vector>
+
+#define B2_HOSTEMU 1
+#ifndef B2_REAL
+#define B2_REAL double
+#endif
+#include "../../mjlab_b200/csrc/b2_smooth.cuh"
+#include "../../mjlab_b200/csrc/b2_solve.cuh"
+
+extern "C" {
+
+int cport_sizeof_real(void) { return (int)sizeof(real); }
+
+// nstep physics steps for every world, worlds distributed over nthread threads (dynamic chunks of 1 world).
+int cport_steps(const KModel* m, KData* d, int nstep, int nthread) {
+  SmoothSmem ls = smooth_smem_layout(m->nq, m->nv, m->nu, m->nbody, m->njnt, 256);
+  int rows_max = 4 * d->nconmax + 2 * m->nlimited;
+  if (rows_max > d->njmax) rows_max = d->njmax;
+  int wpad = m->maxchain | 1;
+  int arena = solve_arena_need(rows_max, 2 * m->nlimited + d->nconmax + 1, 2 * m->nlimited + d->nconmax * m->maxchain,
+                               2 * m->nlimited + 4 * d->nconmax * wpad, d->nconmax > 0 ? d->nconmax : 1);
+  SolveSmem lv = solve_smem_layout(m->nv, rows_max, m->maxchain, arena);
+  PostSmem lp = post_smem_layout(m->nv);
+  std::atomic<int> next(0);
+  auto work = [&]() {
+    std::vector<real> a(ls.total), b(lv.fixed_total), ar(arena + 4), c(lp.total);
+    int actl[2] = {0, 0};
+    for (;;) {
+      int w = next.fetch_add(1);
+      if (w >= d->nworld) break;
+      for (int s = 0; s < nstep; ++s) {
+        smooth_world(*m, *d, ls, 256, w, a.data());
+        solve_world(*m, *d, lv, w, b.data(), ar.data(), actl);
+        post_world(*m, *d, lp, w, c.data(), 1);
+      }
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < nthread; ++t) pool.emplace_back(work);
+  work();
+  for (auto& t : pool) t.join();
+  return 0;
+}
+}
