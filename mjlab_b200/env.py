@@ -323,6 +323,7 @@ class ManagerBasedRlEnv:
         self._enqueue_step()
     torch.cuda.current_stream(self._dev).wait_stream(side)
     self._graph = g
+    self._capture_epoch = getattr(self, "_capture_epoch", 0) + 1   # callers that captured _enqueue_step themselves must re-capture
 
   #: kernels enqueued per env step: action, decimation x (smooth, order, solve, post, airtime), env_post + gate, forward (4), obs, log
   launches_per_step = property(lambda self: 1 + 5 * self.cfg.decimation + 2 + 4 + 1 + 1)
@@ -370,6 +371,14 @@ class ManagerBasedRlEnv:
       self._apply_velocity_stages()
     self._publish_log()
     return self.obs_buf, self.reward_buf, self.reset_terminated, self.reset_time_outs, self.extras
+
+  def note_steps(self, n: int) -> None:
+    """Host-side bookkeeping for `n` env steps that were enqueued through `_enqueue_step` by the caller (a roll-out graph)."""
+    self.common_step_counter += n
+    self._sim_step_counter += n * self.cfg.decimation
+    if self._next_stage < len(self.cfg.velocity_stages) and self.common_step_counter > self.cfg.velocity_stages[self._next_stage]["step"]:
+      self._apply_velocity_stages()
+    self._publish_log()
 
   def _publish_log(self) -> None:
     if self.cfg.log_metrics:

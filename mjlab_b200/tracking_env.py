@@ -221,6 +221,7 @@ class TrackingRlEnv:
         self._enqueue_step()
     torch.cuda.current_stream(self._dev).wait_stream(side)
     self._graph = g
+    self._capture_epoch = getattr(self, "_capture_epoch", 0) + 1   # callers that captured _enqueue_step themselves must re-capture
 
   def seed(self, seed: int = -1) -> int:
     if seed == -1:
@@ -259,6 +260,10 @@ class TrackingRlEnv:
     self.common_step_counter += 1
     self._publish_log()
     return self.obs_buf, self.reward_buf, self.reset_terminated, self.reset_time_outs, self.extras
+
+  def note_steps(self, n: int) -> None:
+    self.common_step_counter += n
+    self._publish_log()
 
   def _publish_log(self) -> None:
     if self.cfg.log_metrics:
