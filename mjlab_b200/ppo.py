@@ -52,6 +52,9 @@ class PpoCfg:
   # capture the whole 24-step roll-out (policy inference + the env's kernels + GAE) in ONE CUDA graph: removes ~2000 eager
   # launches per iteration; needs the env's raw enqueue API, falls back to eager otherwise
   rollout_cuda_graph: bool = True
+  # capture the 20 mini-batch updates of an iteration (forward, backward, clip, Adam, KL-adaptive learning rate on the
+  # device) in ONE CUDA graph; single-process only (the distributed path all-reduces gradients eagerly)
+  update_cuda_graph: bool = True
   seed: int = 42
   obs_groups: dict = field(default_factory=lambda: {"policy": ("policy",), "critic": ("critic",)})
 
@@ -152,8 +155,11 @@ class OnPolicyRunner:
     if self.distributed:
       for t in list(self.policy.parameters()) + list(self.policy.buffers()):
         dist.broadcast(t.data, src=0)
-    self.optimizer = torch.optim.Adam(self.policy.parameters(), lr=self.cfg.learning_rate)
-    self.learning_rate = self.cfg.learning_rate
+    # the learning rate lives on the device (KL-adaptive rule without a host round trip per mini-batch)
+    cuda = self.device.type == "cuda"
+    self._lr = torch.tensor(float(self.cfg.learning_rate), device=self.device)
+    self.optimizer = torch.optim.Adam(self.policy.parameters(), lr=self._lr, capturable=cuda, foreach=cuda)
+    self._update_graph, self._update_warm = None, 0
     T, B = self.cfg.num_steps_per_env, venv.num_envs
     z = lambda *s: torch.zeros(T, B, *s, device=self.device)  # noqa: E731
     self.st = dict(obs=z(self.n_obs), critic=z(self.n_critic), actions=z(self.n_act), rewards=z(), dones=z(), values=z(),
@@ -255,19 +261,24 @@ class OnPolicyRunner:
     return self.ro
 
   # ---- update ------------------------------------------------------------------------------------------
-  def update(self, ro: dict) -> dict:
-    cfg, st = self.cfg, self.st
+  @property
+  def learning_rate(self) -> float:
+    return float(self._lr)
+
+  def _update_body(self) -> None:
+    """All epochs x mini-batches of one PPO update; reads `self._perm`, writes `self._stats` (device tensors)."""
+    cfg, st, ro = self.cfg, self.st, self.ro
     N = cfg.num_steps_per_env * self.env.num_envs
     flat = {k: v.reshape(N, *v.shape[2:]) for k, v in st.items()}
     ret, adv = ro["returns"].reshape(N), ro["advantages"].reshape(N)
     mb = N // cfg.num_mini_batches
     params = list(self.policy.parameters())
-    stats = dict(value=0.0, surrogate=0.0, entropy=0.0, kl=0.0)
+    stats = self._stats
+    stats.zero_()
     self.policy.train()
-    for _ in range(cfg.num_learning_epochs):
-      perm = torch.randperm(cfg.num_mini_batches * mb, device=self.device)
+    for e in range(cfg.num_learning_epochs):
       for i in range(cfg.num_mini_batches):
-        idx = perm[i * mb:(i + 1) * mb]
+        idx = self._perm[e, i * mb:(i + 1) * mb]
         dist_ = self.policy.distribution(flat["obs"][idx])
         logp = dist_.log_prob(flat["actions"][idx]).sum(-1)
         value = self.policy.evaluate(flat["critic"][idx]).squeeze(-1)
@@ -278,14 +289,11 @@ class OnPolicyRunner:
           if self.distributed:
             dist.all_reduce(kl, op=dist.ReduceOp.SUM)
             kl /= self.world_size
-        if cfg.schedule == "adaptive" and cfg.desired_kl is not None:
-          k = kl.item()
-          if k > cfg.desired_kl * 2.0:
-            self.learning_rate = max(1e-5, self.learning_rate / 1.5)
-          elif 0.0 < k < cfg.desired_kl / 2.0:
-            self.learning_rate = min(1e-2, self.learning_rate * 1.5)
-          for g in self.optimizer.param_groups:
-            g["lr"] = self.learning_rate
+          if cfg.schedule == "adaptive" and cfg.desired_kl is not None:
+            lr = self._lr
+            down = torch.clamp(lr / 1.5, min=1e-5)
+            up = torch.clamp(lr * 1.5, max=1e-2)
+            lr.copy_(torch.where(kl > cfg.desired_kl * 2.0, down, torch.where((kl > 0.0) & (kl < cfg.desired_kl / 2.0), up, lr)))
         ratio = torch.exp(logp - flat["logp"][idx])
         a = adv[idx]
         surrogate = torch.max(-a * ratio, -a * torch.clamp(ratio, 1.0 - cfg.clip_param, 1.0 + cfg.clip_param)).mean()
@@ -300,14 +308,33 @@ class OnPolicyRunner:
         loss.backward()
         if self.distributed:
           reduce_gradients(params, self.world_size)
-        nn.utils.clip_grad_norm_(params, cfg.max_grad_norm)
+        nn.utils.clip_grad_norm_(params, cfg.max_grad_norm, foreach=self.device.type == "cuda")
         self.optimizer.step()
-        stats["value"] += v_loss.detach()
-        stats["surrogate"] += surrogate.detach()
-        stats["entropy"] += entropy.mean().detach()
-        stats["kl"] += kl
-    n = cfg.num_learning_epochs * cfg.num_mini_batches
-    return {k: v / n for k, v in stats.items()}
+        with torch.no_grad():
+          stats += torch.stack((v_loss.detach(), surrogate.detach(), entropy.mean().detach(), kl))
+    stats /= cfg.num_learning_epochs * cfg.num_mini_batches
+
+  def update(self, ro: dict) -> dict:
+    cfg = self.cfg
+    N = cfg.num_steps_per_env * self.env.num_envs
+    if not hasattr(self, "_perm"):
+      self._perm = torch.zeros(cfg.num_learning_epochs, N, dtype=torch.long, device=self.device)
+      self._stats = torch.zeros(4, device=self.device)
+    for e in range(cfg.num_learning_epochs):
+      self._perm[e].copy_(torch.randperm(N, device=self.device))
+    use_graph = cfg.update_cuda_graph and self.device.type == "cuda" and not self.distributed
+    if not use_graph or self._update_warm < 2:
+      self._update_body()               # eager: also the warm-up that creates Adam's state and the .grad tensors
+      self._update_warm += 1
+    else:
+      if self._update_graph is None:
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+          self._update_body()           # capture executes nothing; the replay below is this iteration's update
+        self._update_graph = g
+      self._update_graph.replay()
+    return dict(zip(("value", "surrogate", "entropy", "kl"), self._stats.clone().unbind()))
 
   def learn(self, num_iterations: int, init_at_random_ep_len: bool = True, log_every: int = 0) -> list[dict]:
     if init_at_random_ep_len and self.iteration == 0:  # scripts/train.py:167-169
