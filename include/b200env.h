@@ -62,6 +62,9 @@ enum b2e_ip {
   B2E_IP_ENABLE_CORRUPTION, /* policy-group observation noise */
   B2E_IP_PUSH_ENABLED,
   B2E_IP_HEADING_COMMAND,
+  B2E_IP_TERRAIN_MODE,      /* bit 0: terrain_levels_vel curriculum at reset (tasks/velocity/mdp/curriculums.py:30-64);
+                               bit 1: randomize_terrain reset event of play mode (envs/mdp/events.py:26-37); 0: flat plane */
+  B2E_IP_TERRAIN_ROWS, B2E_IP_TERRAIN_COLS,
   B2E_IP_FOOT_SITE,         /* [B2E_MAXFEET] global site ids */
   B2E_IP_FOOT_SITE_BODY = B2E_IP_FOOT_SITE + B2E_MAXFEET,    /* [B2E_MAXFEET] body of each foot site */
   B2E_IP_FOOT_FOUND_ADR = B2E_IP_FOOT_SITE_BODY + B2E_MAXFEET,
@@ -78,6 +81,7 @@ enum b2e_fp {
   B2E_FP_WALKING_THRESHOLD, B2E_FP_RUNNING_THRESHOLD,
   B2E_FP_AIR_THR_MIN, B2E_FP_AIR_THR_MAX, B2E_FP_AIR_CMD_THRESHOLD,
   B2E_FP_TARGET_HEIGHT, B2E_FP_CMD_THRESHOLD,
+  B2E_FP_TERRAIN_HALF_SIZE, /* terrain_generator.size[0] / 2: an env that walked farther than this moves up a level */
   B2E_FP_CMD_RESAMPLE,      /* [2] */
   B2E_FP_CMD_LIN_X = B2E_FP_CMD_RESAMPLE + 2,
   B2E_FP_CMD_LIN_Y = B2E_FP_CMD_LIN_X + 2,
@@ -106,8 +110,10 @@ enum b2e_buf {
   B2E_B_ACTION_SCALE, B2E_B_ACTION_OFFSET, B2E_B_STD_STANDING, B2E_B_STD_WALKING, B2E_B_STD_RUNNING,
   B2E_B_NOISE_LO, B2E_B_NOISE_HI,          /* [n_obs_policy] */
   B2E_B_DEFAULT_ROOT_STATE, /* [13] */
+  B2E_B_TERRAIN_ORIGINS,    /* [rows, cols, 3] spawn origin of every sub-terrain (terrain_importer.py:176-190); [3] dummy when flat */
   /* per-env state, [nworld, ...] float unless noted */
   B2E_B_ENV_ORIGINS,        /* [3] */
+  B2E_B_TERRAIN_LEVEL, B2E_B_TERRAIN_TYPE,   /* int [1]: row (difficulty) and column (type) of the env's sub-terrain */
   B2E_B_ACTION_IN,          /* [nj] the policy's action for this step (input) */
   B2E_B_ACTION, B2E_B_PREV_ACTION, B2E_B_PREV_PREV_ACTION,  /* [nj] ActionManager history */
   B2E_B_RAW_ACTION, B2E_B_PROCESSED_ACTION,                  /* [nj] JointAction */
@@ -150,6 +156,7 @@ enum b2e_log {
   B2E_LOG_PEAK_SUM, B2E_LOG_LANDINGS,        /* feet_swing_height metric */
   B2E_LOG_SLIP_SUM, B2E_LOG_NCONTACT,        /* feet_slip metric */
   B2E_LOG_LANDING_FORCE_SUM,                 /* soft_landing metric (denominator: LANDINGS) */
+  B2E_LOG_TERRAIN_LEVEL,                     /* sum over all envs of the terrain level (Curriculum/terrain_levels = mean) */
   B2E_NLOG
 };
 
@@ -163,7 +170,8 @@ enum b2e_draw {
   B2E_DRAW_RESET_JOINT_POS = 33,             /* [nj] */
   B2E_DRAW_RESET_JOINT_VEL = 33 + 32,        /* [nj] */
   B2E_DRAW_NOISE = 33 + 64,                  /* [n_obs_policy] */
-  B2E_NDRAW = 33 + 64 + 160
+  B2E_DRAW_TERRAIN = 33 + 64 + 160,          /* [3]: restart level of the curriculum; level, type of randomize_terrain */
+  B2E_NDRAW = 33 + 64 + 160 + 3
 };
 
 typedef struct b2_env {

@@ -75,6 +75,10 @@ enum b2_mf {
   B2_MF_ACTUATOR_FORCERANGE, /* nu*2 */
   B2_MF_ACTUATOR_CTRLRANGE,  /* nu*2 */
   B2_MF_SENSOR_CUTOFF,    /* nsensor */
+  B2_MF_SGEOM_XPOS,       /* ngeom*3: world position of static geoms (bodies welded to the world); 0 for moving geoms */
+  B2_MF_SGEOM_XMAT,       /* ngeom*9 */
+  B2_MF_FIELD_AABB,       /* nfield*6: world AABB (centre, half extents) of each field geom */
+  B2_MF_FIELD_GRID,       /* 4: x0, y0, cell edge, 1 / cell edge of the uniform xy grid over the field */
   B2_MF_COUNT
 };
 
@@ -120,6 +124,12 @@ enum b2_mi {
   B2_MI_SENSOR_DIM,        /* nsensor */
   B2_MI_SENSOR_ADR,        /* nsensor */
   B2_MI_DOF_ACTID,         /* nv: the actuator driving this dof, -1 none, -2 several (kernels then scan) */
+  B2_MI_DYN_GEOM,          /* ndyn: geoms that move (forward kinematics runs for these only) */
+  B2_MI_FIELD_GEOM,        /* nfield: geom id of each field geom (static terrain boxes, see b2_model.nfield) */
+  B2_MI_FIELD_CELL0,       /* nfield*2: lowest grid cell (ix, iy) the geom's AABB touches */
+  B2_MI_FIELD_CELL_ADR,    /* field_nx*field_ny+1: CSR offsets into FIELD_CELL_ITEM, cell = ix*field_ny + iy */
+  B2_MI_FIELD_CELL_ITEM,   /* field indices whose AABB overlaps the cell, ascending */
+  B2_MI_FQ_GEOM,           /* nfq: moving geoms (spheres, capsules) that can touch the field, in geom order */
   B2_MI_COUNT
 };
 
@@ -206,6 +216,9 @@ typedef struct b2_model {
   int has_accelerometer, has_subtreevel;
   int nlimited;      /* number of limited hinge/slide joints (bounds the joint-limit rows) */
   int maxchain;      /* max over candidate pairs of |dofs(body1) U dofs(body2)| (compact row width bound) */
+  /* geom field: a large set of static boxes (the rough-terrain grid, terrains/terrain_generator.py) is not enumerated as
+   * candidate pairs; moving "query" geoms look the boxes up in a uniform xy grid.  nfield == 0: no field. */
+  int nfield, nfq, ndyn, field_nx, field_ny;
   const float* mf[B2_MF_COUNT];
   int mf_stride[B2_MF_COUNT]; /* floats between consecutive worlds; 0 = shared */
   const int* mi[B2_MI_COUNT];
@@ -248,6 +261,10 @@ int b2_stage(const b2_model* m, b2_data* d, int stage, int do_integrate, void* s
  * return to qpos0 / zero velocity, controls, warm start, applied forces, time;
  * mask == NULL resets every world. */
 int b2_reset(const b2_model* m, b2_data* d, const unsigned char* mask, void* stream);
+
+/* Writes the world pose of the static geoms (B2_MF_SGEOM_*) into every world's geom_xpos / geom_xmat rows.  The step
+ * kernels only update moving geoms, so call this once after the data buffers are allocated. */
+int b2_init_static(const b2_model* m, b2_data* d, void* stream);
 
 /* repeat_array_kernel: dst[w, :] = src[:] for w in [0, nworld). */
 int b2_repeat_rows(float* dst, const float* src, int row_len, int nworld, void* stream);

@@ -119,6 +119,24 @@ __global__ void k_repeat_rows(float* dst, const float* src, int row_len, long lo
   if (i < total) dst[i] = src[i % row_len];
 }
 
+// static geoms: every world's geom_xpos / geom_xmat row gets the model constant (one thread per (world, geom, component))
+__global__ void k_init_static(const KModel m, const KData d) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)d.nworld * m.ngeom * 12;
+  if (i >= total) return;
+  int c = (int)(i % 12);
+  long long wg = i / 12;
+  int g = (int)(wg % m.ngeom);
+  int w = (int)(wg / m.ngeom);
+  // a geom is static iff it is not in dyn_geom; dyn_geom is ascending, so binary search
+  const int* dyn = m.mi[B2_MI_DYN_GEOM];
+  int lo = 0, hi = m.ndyn;
+  while (lo < hi) { int mid = (lo + hi) >> 1; if (dyn[mid] < g) lo = mid + 1; else hi = mid; }
+  if (lo < m.ndyn && dyn[lo] == g) return;
+  if (c < 3) d.df[B2_DF_GEOM_XPOS][((size_t)w * m.ngeom + g) * 3 + c] = (m.mf[B2_MF_SGEOM_XPOS] + (size_t)w * m.mf_stride[B2_MF_SGEOM_XPOS])[3 * g + c];
+  else d.df[B2_DF_GEOM_XMAT][((size_t)w * m.ngeom + g) * 9 + (c - 3)] = (m.mf[B2_MF_SGEOM_XMAT] + (size_t)w * m.mf_stride[B2_MF_SGEOM_XMAT])[9 * g + c - 3];
+}
+
 struct Plan {
   SmoothSmem ls;
   SolveSmem lv;
@@ -241,6 +259,18 @@ int b2_reset(const b2_model* m, b2_data* d, const unsigned char* mask, void* str
   const KData& kd = *reinterpret_cast<const KData*>(d);
   int grid = (d->nworld + 3) / 4;
   k_reset<<<grid, 128, 0, (cudaStream_t)stream>>>(km, kd, mask);
+  g_launches += 1;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("launch failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int b2_init_static(const b2_model* m, b2_data* d, void* stream) {
+  const KModel& km = *reinterpret_cast<const KModel*>(m);
+  const KData& kd = *reinterpret_cast<const KData*>(d);
+  long long total = (long long)d->nworld * m->ngeom * 12;
+  if (total <= 0) return 0;
+  k_init_static<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(km, kd);
   g_launches += 1;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail("launch failed: %s", cudaGetErrorString(e));

@@ -126,6 +126,7 @@ struct KModel {
   int integrator, cone, solver, iterations, ls_iterations, disableflags;
   int has_accelerometer, has_subtreevel;
   int nlimited, maxchain;
+  int nfield, nfq, ndyn, field_nx, field_ny;
   const real* mf[B2_MF_COUNT];
   int mf_stride[B2_MF_COUNT];
   const int* mi[B2_MI_COUNT];

@@ -366,6 +366,7 @@ B2_DEV void env_post_world(const KModel& m, const KData& d, const KEnv& e, int w
   }
   B2_WSYNC();
   if (reset) env_reset_world(m, d, e, w, step);
+  if (EI(B2E_IP_TERRAIN_MODE) && B2_LANE == 0) logv[B2E_LOG_TERRAIN_LEVEL] = (real)EBI(B2E_B_TERRAIN_LEVEL)[w];
 }
 
 // ---------------------------------------------------------------------------
@@ -387,6 +388,28 @@ B2_DEVN void env_reset_world(const KModel& m, const KData& d, const KEnv& e, int
     met[0] = 0; met[1] = 0;
     EBL(B2E_B_EPISODE_LENGTH)[w] = 0;
   }
+  const int tmode = EI(B2E_IP_TERRAIN_MODE);
+  if ((tmode & 1) && B2_LANE == 0) {
+    // curriculum_manager.compute first (manager_based_rl_env.py:382): terrain_levels_vel (tasks/velocity/mdp/curriculums.py:30-64)
+    // on the pre-reset state + TerrainImporter.update_env_origins (terrains/terrain_importer.py:196-209)
+    const real* rp = d.df[B2_DF_XPOS] + ((size_t)w * m.nbody + EI(B2E_IP_ROOT_BODY)) * 3;   // root_link_pos_w
+    real* org = EBR(B2E_B_ENV_ORIGINS) + (size_t)w * 3;
+    const real* cmd = EBR(B2E_B_COMMAND) + (size_t)w * 3;
+    const real dx = rp[0] - org[0], dy = rp[1] - org[1];
+    const real dist = sqrt(dx * dx + dy * dy);
+    const bool up = dist > EF(B2E_FP_TERRAIN_HALF_SIZE);
+    const bool down = (dist < sqrt(cmd[0] * cmd[0] + cmd[1] * cmd[1]) * EF(B2E_FP_MAX_EPISODE_LENGTH_S) * (real)0.5) && !up;
+    const int rows = EI(B2E_IP_TERRAIN_ROWS), cols = EI(B2E_IP_TERRAIN_COLS);
+    int lv = EBI(B2E_B_TERRAIN_LEVEL)[w] + (up ? 1 : 0) - (down ? 1 : 0);
+    if (lv >= rows) {   // past the hardest row: restart at a uniformly drawn level
+      lv = (int)(env_draw(e, nworld, w, step, B2E_DRAW_TERRAIN) * (real)rows);
+      if (lv > rows - 1) lv = rows - 1;
+    } else if (lv < 0) lv = 0;
+    EBI(B2E_B_TERRAIN_LEVEL)[w] = lv;
+    const real* to = EBR(B2E_B_TERRAIN_ORIGINS) + ((size_t)lv * cols + EBI(B2E_B_TERRAIN_TYPE)[w]) * 3;
+    org[0] = to[0]; org[1] = to[1]; org[2] = to[2];
+  }
+  B2_WSYNC();
   reset_world(m, d, w);                                   // sim.reset
   {                                                       // scene.reset: entity.clear_state + contact sensor reset
     real* st = EBR(B2E_B_AIR_STATE) + (size_t)w * 4 * nf;
@@ -416,6 +439,19 @@ B2_DEVN void env_reset_world(const KModel& m, const KData& d, const KEnv& e, int
     for (int k = 0; k < 6; ++k) vel[k] = drs[7 + k] + vs[k];
     env_quat_apply_inv(angb, q, vel + 3);
     for (int c = 0; c < 3; ++c) { qv[c] = vel[c]; qv[3 + c] = angb[c]; }
+    if (tmode & 2) {
+      // play mode: randomize_terrain (envs/mdp/events.py:26-37) is the LAST reset event, so the root pose above used the
+      // previous origin and the new sub-terrain takes effect at the next reset - as in the reference
+      const int rows = EI(B2E_IP_TERRAIN_ROWS), cols = EI(B2E_IP_TERRAIN_COLS);
+      int lv = (int)(env_draw(e, nworld, w, step, B2E_DRAW_TERRAIN + 1) * (real)rows);
+      int ty = (int)(env_draw(e, nworld, w, step, B2E_DRAW_TERRAIN + 2) * (real)cols);
+      if (lv > rows - 1) lv = rows - 1;
+      if (ty > cols - 1) ty = cols - 1;
+      EBI(B2E_B_TERRAIN_LEVEL)[w] = lv; EBI(B2E_B_TERRAIN_TYPE)[w] = ty;
+      real* o2 = EBR(B2E_B_ENV_ORIGINS) + (size_t)w * 3;
+      const real* to = EBR(B2E_B_TERRAIN_ORIGINS) + ((size_t)lv * cols + ty) * 3;
+      o2[0] = to[0]; o2[1] = to[1]; o2[2] = to[2];
+    }
   }
   {
     // reset_joints_by_offset (events.py:171-206)

@@ -28,6 +28,7 @@ __global__ void __launch_bounds__(B2E_WPB * 32) k_env_reset(const __grid_constan
   const bool sel = !mask || mask[w];
   if ((threadIdx.x & 31) == 0) reinterpret_cast<unsigned char*>(e.buf[B2E_B_RESET_BUF])[w] = sel;
   if (sel) env_reset_world(m, d, e, w, reinterpret_cast<const long long*>(e.buf[B2E_B_STEP_COUNTER])[0]);
+  if (e.ip[B2E_IP_TERRAIN_MODE] && (threadIdx.x & 31) == 0) logv[B2E_LOG_TERRAIN_LEVEL] = (float)reinterpret_cast<const int*>(e.buf[B2E_B_TERRAIN_LEVEL])[w];
 }
 
 // One CTA per log column; fixed-order strided partial sums + shared-memory tree => deterministic.

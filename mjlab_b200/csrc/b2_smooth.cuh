@@ -49,6 +49,8 @@ struct LaneContacts {
   real pos[B2_MAXCON_PER_PAIR][3];
   real normal[3];
   real tangent[3];  // zero => pick default
+  real normal_b[3]; // contacts nb_from.. carry their own normal (capsule-box: one sphere-box test per contact)
+  int nb_from;
 };
 
 B2_DEV void sphere_sphere(LaneContacts& lc, const real* p1, real r1, const real* p2, real r2, real margin) {  // @region narrowphase_fns
@@ -81,10 +83,111 @@ B2_DEV void plane_sphere(LaneContacts& lc, const real* pp, const real* pn, const
   lc.n = k + 1;
 }
 
+// Sphere against box (MuJoCo's sphere-box routine as published: clamp the centre into the box; a centre inside the
+// box leaves through the nearest face).  Appends at most one contact; normal from the sphere towards the box.
+B2_DEV void sphere_box(LaneContacts& lc, const real* sp, real r, const real* bp, const real* bR, const real* bs, real margin) {
+  real t[3] = {sp[0] - bp[0], sp[1] - bp[1], sp[2] - bp[2]}, c[3], dif[3];
+  mulmTv3(c, bR, t);
+  for (int j = 0; j < 3; ++j) dif[j] = clampr(c[j], -bs[j], bs[j]) - c[j];
+  real dd = sqrt(dot3(dif, dif));
+  if (dd - r > margin) return;
+  real nb[3] = {0, 0, 0}, pb[3], dist;
+  if (dd <= B2_MINVAL) {
+    real closest = 2 * (bs[0] + bs[1] + bs[2]);
+    int k = 0;
+    for (int i = 0; i < 6; ++i) {
+      real fd = fabs(((i & 1) ? bs[i >> 1] : -bs[i >> 1]) - c[i >> 1]);
+      if (fd < closest) { closest = fd; k = i; }
+    }
+    real sg = (k & 1) ? (real)-1 : (real)1;
+    if ((k >> 1) == 0) nb[0] = sg; else if ((k >> 1) == 1) nb[1] = sg; else nb[2] = sg;
+    real s = (r - closest) * (real)0.5;
+    pb[0] = c[0] + nb[0] * s; pb[1] = c[1] + nb[1] * s; pb[2] = c[2] + nb[2] * s;
+    dist = -closest - r;
+  } else {
+    real id = (real)1 / dd;
+    nb[0] = dif[0] * id; nb[1] = dif[1] * id; nb[2] = dif[2] * id;
+    dist = dd - r;
+    real s = r + (real)0.5 * dist;     // midway between the sphere's deepest point and the box surface
+    pb[0] = c[0] + nb[0] * s; pb[1] = c[1] + nb[1] * s; pb[2] = c[2] + nb[2] * s;
+  }
+  int k = lc.n;
+  if (k >= B2_MAXCON_PER_PAIR) return;
+  real n[3], p[3];
+  mulmv3(n, bR, nb);
+  mulmv3(p, bR, pb);
+  lc.dist[k] = dist;
+  lc.pos[k][0] = bp[0] + p[0]; lc.pos[k][1] = bp[1] + p[1]; lc.pos[k][2] = bp[2] + p[2];
+  if (k == 0) { lc.normal[0] = n[0]; lc.normal[1] = n[1]; lc.normal[2] = n[2]; }
+  else { lc.normal_b[0] = n[0]; lc.normal_b[1] = n[1]; lc.normal_b[2] = n[2]; lc.nb_from = k; }
+  lc.n = k + 1;
+}
+
+// g(t) = 1/2 d/dt dist^2(p + a t, box): nondecreasing and piecewise linear in t (the squared distance to a box is convex)
+B2_DEV real capsule_box_slope(const real* p, const real* a, const real* bs, real t) {
+  real s = 0;
+  for (int j = 0; j < 3; ++j) {
+    real q = p[j] + a[j] * t;
+    real e = q > bs[j] ? q - bs[j] : (q < -bs[j] ? q + bs[j] : (real)0);
+    s += a[j] * e;
+  }
+  return s;
+}
+
+#define B2_CAPBOX_BISECT 24
+
+// Capsule against box: up to two contacts, each a sphere-box test at a point of the capsule's segment (as MuJoCo's
+// capsule-box routine emits them).  The points: the two ends [ta, tb] of the stretch of the segment that is closest to the
+// box when that stretch has a length (segment parallel to a face, or inside the box), else the closest point and the
+// segment end farther from it.  [ta, tb] come from bisecting the monotone slope g(t).
+B2_DEV void capsule_box(LaneContacts& lc, const real* cp, const real* cR, const real* cs, const real* bp, const real* bR,
+                        const real* bs, real margin) {
+  const real r = cs[0], h = cs[1];
+  real ax[3] = {cR[2], cR[5], cR[8]};
+  real t[3] = {cp[0] - bp[0], cp[1] - bp[1], cp[2] - bp[2]}, p[3], a[3];
+  mulmTv3(p, bR, t);
+  mulmTv3(a, bR, ax);
+  real g_lo = capsule_box_slope(p, a, bs, -h), g_hi = capsule_box_slope(p, a, bs, h);
+  real ta, tb;
+  if (g_lo >= 0) ta = -h;
+  else if (g_hi < 0) ta = h;
+  else {
+    real lo = -h, hi = h;
+    B2_UNROLL1
+    for (int it = 0; it < B2_CAPBOX_BISECT; ++it) {
+      real mid = (real)0.5 * (lo + hi);
+      if (capsule_box_slope(p, a, bs, mid) >= 0) hi = mid; else lo = mid;
+    }
+    ta = hi;
+  }
+  if (g_hi <= 0) tb = h;
+  else if (g_lo > 0) tb = -h;
+  else {
+    real lo = -h, hi = h;
+    B2_UNROLL1
+    for (int it = 0; it < B2_CAPBOX_BISECT; ++it) {
+      real mid = (real)0.5 * (lo + hi);
+      if (capsule_box_slope(p, a, bs, mid) <= 0) lo = mid; else hi = mid;
+    }
+    tb = lo;
+  }
+  const real tol = (real)1e-4 * h;
+  real t1, t2;
+  if (tb - ta > tol) { t1 = ta; t2 = tb; }
+  else { t1 = (real)0.5 * (ta + tb); t2 = t1 > 0 ? -h : h; }
+  real q[3] = {cp[0] + ax[0] * t1, cp[1] + ax[1] * t1, cp[2] + ax[2] * t1};
+  sphere_box(lc, q, r, bp, bR, bs, margin);
+  if (fabs(t2 - t1) > tol) {
+    q[0] = cp[0] + ax[0] * t2; q[1] = cp[1] + ax[1] * t2; q[2] = cp[2] + ax[2] * t2;
+    sphere_box(lc, q, r, bp, bR, bs, margin);
+  }
+}
+
 // Narrowphase for one geom pair (types t1 <= t2). Normal points from geom1 to geom2.
 B2_DEV void narrowphase(LaneContacts& lc, int t1, int t2, const real* p1, const real* R1, const real* s1, const real* p2,
                         const real* R2, const real* s2, real margin) {
   lc.n = 0;
+  lc.nb_from = B2_MAXCON_PER_PAIR;
   lc.tangent[0] = lc.tangent[1] = lc.tangent[2] = 0;
   if (t1 == B2_GEOM_PLANE) {
     real n[3] = {R1[2], R1[5], R1[8]};
@@ -164,8 +267,12 @@ B2_DEV void narrowphase(LaneContacts& lc, int t1, int t2, const real* p1, const 
         sphere_sphere(lc, q1, s1[0], v2, s2[0], margin);
       }
     }
+  } else if (t1 == B2_GEOM_SPHERE && t2 == B2_GEOM_BOX) {
+    sphere_box(lc, p1, s1[0], p2, R2, s2, margin);
+  } else if (t1 == B2_GEOM_CAPSULE && t2 == B2_GEOM_BOX) {
+    capsule_box(lc, p1, R1, s1, p2, R2, s2, margin);
   }
-  // unsupported pairs (box-box, capsule-box, ...) are rejected on the host by b2_check
+  // unsupported pairs (box-box, meshes, ...) are rejected on the host (engine.check_supported)
 }
 
 // Contact frame rows [normal; t1; t2] from a normal and an optional tangent hint.
@@ -330,8 +437,11 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
     const real* geom_quat = MF(B2_MF_GEOM_QUAT);
     real* gx = d.df[B2_DF_GEOM_XPOS] + (size_t)w * m.ngeom * 3;
     real* gm = d.df[B2_DF_GEOM_XMAT] + (size_t)w * m.ngeom * 9;
+    // moving geoms only: static ones (terrain) hold the constant pose b2_init_static wrote
+    const int* dyn_geom = MI(B2_MI_DYN_GEOM);
     B2_UNROLL1
-    for (int g = B2_LANE; g < m.ngeom; g += B2_NLANE) {
+    for (int gi = B2_LANE; gi < m.ndyn; gi += B2_NLANE) {
+      int g = dyn_geom[gi];
       int b = geom_body[g];
       real t[3], q[4], R[9];
       mulmv3(t, xmat + 9 * b, geom_pos + 3 * g);
@@ -528,6 +638,79 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
       }
       ncand += b2_popc(bal);
     }
+    // geom field (static terrain boxes): every query geom looks up the grid cells under its bounding sphere; a box met
+    // in several cells is taken from the first cell the two cell ranges share.  Two passes (count, then write) keep the
+    // candidate order deterministic: by query geom, cell, field index.
+    const int* fq_geom = MI(B2_MI_FQ_GEOM);
+    const int* f_geom = MI(B2_MI_FIELD_GEOM);
+    const real* sg_xpos = MF(B2_MF_SGEOM_XPOS);
+    const real* sg_xmat = MF(B2_MF_SGEOM_XMAT);
+    if (m.nfield > 0) {
+      const int* f_cell0 = MI(B2_MI_FIELD_CELL0);
+      const int* f_adr = MI(B2_MI_FIELD_CELL_ADR);
+      const int* f_item = MI(B2_MI_FIELD_CELL_ITEM);
+      const real* f_aabb = MF(B2_MF_FIELD_AABB);
+      const real* grid = MF(B2_MF_FIELD_GRID);
+      B2_UNROLL1
+      for (int base = 0; base < m.nfq; base += B2_NLANE) {
+        int qi = base + B2_LANE;
+        int cx0 = 0, cx1 = -1, cy0 = 0, cy1 = -1;
+        real c[3] = {0, 0, 0}, rb = 0;
+        if (qi < m.nfq) {
+          int g = fq_geom[qi];
+          c[0] = gx[3 * g]; c[1] = gx[3 * g + 1]; c[2] = gx[3 * g + 2];
+          rb = geom_rbound[g] + geom_margin[g];
+          cx0 = (int)floor((c[0] - rb - grid[0]) * grid[3]); cx1 = (int)floor((c[0] + rb - grid[0]) * grid[3]);
+          cy0 = (int)floor((c[1] - rb - grid[1]) * grid[3]); cy1 = (int)floor((c[1] + rb - grid[1]) * grid[3]);
+          if (cx0 < 0) cx0 = 0;
+          if (cy0 < 0) cy0 = 0;
+          if (cx1 > m.field_nx - 1) cx1 = m.field_nx - 1;
+          if (cy1 > m.field_ny - 1) cy1 = m.field_ny - 1;
+        }
+        int start = 0, total = 0;
+        B2_UNROLL1
+        for (int pass = 0; pass < 2; ++pass) {
+          int k = 0;
+          B2_UNROLL1
+          for (int cx = cx0; cx <= cx1; ++cx) {
+            B2_UNROLL1
+            for (int cy = cy0; cy <= cy1; ++cy) {
+              int cell = cx * m.field_ny + cy;
+              B2_UNROLL1
+              for (int it = f_adr[cell]; it < f_adr[cell + 1]; ++it) {
+                int fi = f_item[it];
+                int fx0 = f_cell0[2 * fi], fy0 = f_cell0[2 * fi + 1];
+                if (cx != (cx0 > fx0 ? cx0 : fx0) || cy != (cy0 > fy0 ? cy0 : fy0)) continue;
+                const real* a = f_aabb + 6 * fi;
+                real ex = fabs(c[0] - a[0]) - a[3], ey = fabs(c[1] - a[1]) - a[4], ez = fabs(c[2] - a[2]) - a[5];
+                ex = ex > 0 ? ex : 0; ey = ey > 0 ? ey : 0; ez = ez > 0 ? ez : 0;
+                if (ex * ex + ey * ey + ez * ez > rb * rb) continue;
+                if (pass == 1) {
+                  int slot = start + k;
+                  if (slot < ncand_max) cand[slot] = m.npair + qi * m.nfield + fi;
+                }
+                ++k;
+              }
+            }
+          }
+          if (pass == 0) {
+            int incl = k;
+#ifndef B2_HOSTEMU
+            B2_UNROLL1
+            for (int o = 1; o < 32; o <<= 1) {
+              int t = __shfl_up_sync(0xffffffffu, incl, o);
+              if (B2_LANE >= o) incl += t;
+            }
+            total = __shfl_sync(0xffffffffu, incl, 31);
+#else
+            total = incl;
+#endif
+            start = ncand + incl - k;
+          }
+        }
+        ncand += total;
+      }
+    }
     if (ncand > ncand_max) ncand = ncand_max;
     B2_WSYNC();
     // narrowphase: ordered compaction of contacts into the world's contact rows
@@ -547,15 +730,24 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
       int ci = base + B2_LANE;
       LaneContacts lc;
       lc.n = 0;
+      lc.nb_from = B2_MAXCON_PER_PAIR;
       int g1 = 0, g2 = 0;
       real margin = 0, gap = 0;
       if (ci < ncand) {
         int k = cand[ci];
-        g1 = pair_geom[2 * k]; g2 = pair_geom[2 * k + 1];
+        const real *x2, *R2;
+        if (k < m.npair) {
+          g1 = pair_geom[2 * k]; g2 = pair_geom[2 * k + 1];
+          x2 = gx + 3 * g2; R2 = gm + 9 * g2;
+        } else {   // (query geom, field box): the box pose is a model constant shared by all worlds
+          k -= m.npair;
+          g1 = fq_geom[k / m.nfield]; g2 = f_geom[k % m.nfield];
+          x2 = sg_xpos + 3 * g2; R2 = sg_xmat + 9 * g2;
+        }
         margin = fmax(geom_margin[g1], geom_margin[g2]);
         gap = fmax(geom_gap[g1], geom_gap[g2]);
-        narrowphase(lc, geom_type[g1], geom_type[g2], gx + 3 * g1, gm + 9 * g1, geom_size + 3 * g1, gx + 3 * g2,
-                    gm + 9 * g2, geom_size + 3 * g2, margin);
+        narrowphase(lc, geom_type[g1], geom_type[g2], gx + 3 * g1, gm + 9 * g1, geom_size + 3 * g1, x2, R2,
+                    geom_size + 3 * g2, margin);
       }
       // exclusive prefix sum of lc.n over lanes
       int incl = lc.n;
@@ -604,6 +796,7 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
         for (int q = 0; q < lc.n; ++q) {
           int slot = start + q;
           if (slot >= nconmax) break;
+          if (q == lc.nb_from) make_frame(F, lc.normal_b, lc.tangent);
           c_dist[slot] = lc.dist[q];
           c_pos[3 * slot] = lc.pos[q][0]; c_pos[3 * slot + 1] = lc.pos[q][1]; c_pos[3 * slot + 2] = lc.pos[q][2];
           for (int e = 0; e < 9; ++e) c_frame[9 * slot + e] = F[e];

@@ -64,6 +64,10 @@ MODEL_FLOAT_FIELDS = [
   ("ACTUATOR_FORCERANGE", "actuator_forcerange", lambda m: m.nu * 2),
   ("ACTUATOR_CTRLRANGE", "actuator_ctrlrange", lambda m: m.nu * 2),
   ("SENSOR_CUTOFF", "sensor_cutoff", lambda m: m.nsensor),
+  ("SGEOM_XPOS", "sgeom_xpos", lambda m: m.ngeom * 3),
+  ("SGEOM_XMAT", "sgeom_xmat", lambda m: m.ngeom * 9),
+  ("FIELD_AABB", "field_aabb", lambda m: m.nfield * 6),
+  ("FIELD_GRID", "field_grid", lambda m: 4),
 ]
 
 MODEL_INT_FIELDS = [
@@ -80,6 +84,8 @@ MODEL_INT_FIELDS = [
   ("SENSOR_TYPE", "sensor_type"), ("SENSOR_OBJTYPE", "sensor_objtype"), ("SENSOR_OBJID", "sensor_objid"),
   ("SENSOR_REFTYPE", "sensor_reftype"), ("SENSOR_REFID", "sensor_refid"), ("SENSOR_INTPRM", "sensor_intprm"),
   ("SENSOR_DIM", "sensor_dim"), ("SENSOR_ADR", "sensor_adr"), ("DOF_ACTID", "dof_actid"),
+  ("DYN_GEOM", "dyn_geom"), ("FIELD_GEOM", "field_geom"), ("FIELD_CELL0", "field_cell0"),
+  ("FIELD_CELL_ADR", "field_cell_adr"), ("FIELD_CELL_ITEM", "field_cell_item"), ("FQ_GEOM", "fq_geom"),
 ]
 
 # (enum name, attribute on Data, per-world shape as a function of (model, nconmax, njmax))
@@ -167,7 +173,8 @@ class B2Model(C.Structure):
   _fields_ = (
     [(n, C.c_int) for n in ("nq", "nv", "nu", "nbody", "njnt", "ngeom", "nsite", "nsensor", "nsensordata", "npair",
                             "nmocap", "nlevel", "integrator", "cone", "solver", "iterations", "ls_iterations",
-                            "disableflags", "has_accelerometer", "has_subtreevel", "nlimited", "maxchain")]
+                            "disableflags", "has_accelerometer", "has_subtreevel", "nlimited", "maxchain",
+                            "nfield", "nfq", "ndyn", "field_nx", "field_ny")]
     + [("mf", C.c_void_p * NMF), ("mf_stride", C.c_int * NMF), ("mi", C.c_void_p * NMI)]
   )
 
@@ -220,7 +227,7 @@ def derived_int_tables(m) -> dict[str, np.ndarray]:
   )
 
 
-SUPPORTED_PAIRS = {(0, 2), (0, 3), (0, 6), (2, 2), (2, 3), (3, 3)}  # (plane|sphere|capsule|box) subset
+SUPPORTED_PAIRS = {(0, 2), (0, 3), (0, 6), (2, 2), (2, 3), (3, 3), (2, 6), (3, 6)}  # (plane|sphere|capsule|box) subset
 
 
 def check_supported(m) -> None:
@@ -253,6 +260,7 @@ def model_scalars(m, tables) -> dict[str, int]:
     has_accelerometer=int(np.any(st == 1)), has_subtreevel=int(np.any((st == 35) | (st == 36))),
     nlimited=int(np.sum((np.asarray(m.jnt_limited) != 0) & (np.asarray(m.jnt_type) >= 2))) if m.njnt else 0,
     maxchain=_max_chain(m, tables),
+    nfield=int(m.nfield), nfq=int(m.nfq), ndyn=int(m.ndyn), field_nx=int(m.field_nx), field_ny=int(m.field_ny),
   )
 
 
@@ -263,6 +271,8 @@ def _max_chain(m, tables) -> int:
   for g1, g2 in np.asarray(m.pair_geom).reshape(-1, 2):
     u = int(full[m.geom_bodyid[g1]] | full[m.geom_bodyid[g2]])
     best = max(best, bin(u).count("1"))
+  for g in np.asarray(m.fq_geom).reshape(-1):   # field geoms are static: the chain is the query geom's own
+    best = max(best, bin(int(full[m.geom_bodyid[g]])).count("1"))
   return best
 
 
@@ -275,6 +285,14 @@ def model_int_array(m, attr: str, tables) -> np.ndarray:
   v = tables[attr] if attr in tables else getattr(m, attr)
   a = np.ascontiguousarray(np.asarray(v).reshape(-1)).astype(np.int32, copy=False)
   return a if a.size else np.zeros(1, np.int32)
+
+
+def init_static_numpy(m, geom_xpos: np.ndarray, geom_xmat: np.ndarray) -> None:
+  """Host-side twin of b2_init_static for the numpy-backed test / baseline builds of the device code."""
+  static = np.ones(m.ngeom, bool)
+  static[np.asarray(m.dyn_geom, np.int64)] = False
+  geom_xpos[:, static] = np.asarray(m.sgeom_xpos)[static]
+  geom_xmat[:, static] = np.asarray(m.sgeom_xmat).reshape(m.ngeom, 3, 3)[static].reshape((-1,) + geom_xmat.shape[2:])
 
 
 _lib = None
@@ -309,6 +327,8 @@ def load_library() -> C.CDLL:
   lib.b2_reset.restype = C.c_int
   lib.b2_repeat_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
   lib.b2_repeat_rows.restype = C.c_int
+  lib.b2_init_static.argtypes = [C.POINTER(B2Model), C.POINTER(B2Data), C.c_void_p]
+  lib.b2_init_static.restype = C.c_int
   if lib.b2_sizeof_model() != C.sizeof(B2Model) or lib.b2_sizeof_data() != C.sizeof(B2Data):
     raise RuntimeError("libb200sim.so ABI mismatch with mjlab_b200/engine.py (rebuild the extension)")
   _lib = lib

@@ -33,7 +33,8 @@ from .entity import Entity
 from .sim import MujocoCfg, Simulation, SimulationCfg
 
 _TORCH = {"f4": torch.float32, "i4": torch.int32, "i8": torch.int64, "u1": torch.uint8}
-_TASK_ROBOT = {"Mjlab-Velocity-Flat-Unitree-G1": "g1", "Mjlab-Velocity-Flat-Unitree-Go1": "go1"}
+_TASK_ROBOT = {"Mjlab-Velocity-Flat-Unitree-G1": ("g1", "flat"), "Mjlab-Velocity-Flat-Unitree-Go1": ("go1", "flat"),
+               "Mjlab-Velocity-Rough-Unitree-G1": ("g1", "rough")}
 
 
 def _default_sim_cfg() -> SimulationCfg:
@@ -46,6 +47,9 @@ class VelocityEnvCfg:
   """What `load_env_cfg("Mjlab-Velocity-Flat-Unitree-<robot>", play=...)` resolves to (tasks/registry.py:48-55)."""
 
   robot: Literal["g1", "go1"] = "g1"
+  # "flat": ground plane (the Flat tasks); "rough": the ROUGH_TERRAINS_CFG box grid with the terrain-level curriculum
+  # (velocity_env_cfg.py:296-324, config/g1/env_cfgs.py:20-150; terrain seed fixed to 0, SURVEY.md section 8(d) config 4)
+  terrain: Literal["flat", "rough"] = "flat"
   num_envs: int = 4096
   play: bool = False
   seed: int = 42
@@ -68,7 +72,8 @@ class VelocityEnvCfg:
   def from_task(cls, task: str, play: bool = False, **kw) -> "VelocityEnvCfg":
     if task not in _TASK_ROBOT:
       raise ValueError(f"Unknown task '{task}'. Available: {sorted(_TASK_ROBOT)}")
-    return cls(robot=_TASK_ROBOT[task], play=play, **kw)
+    robot, terrain = _TASK_ROBOT[task]
+    return cls(robot=robot, terrain=terrain, play=play, **kw)
 
 
 def env_origins_grid(num_envs: int, spacing: float) -> np.ndarray:
@@ -108,6 +113,8 @@ class _LogView(Mapping):
       out["Metrics/slip_velocity_mean"] = v[K["B2E_LOG_SLIP_SUM"]] / max(v[K["B2E_LOG_NCONTACT"]], 1.0)
       out["Metrics/landing_force_mean"] = v[K["B2E_LOG_LANDING_FORCE_SUM"]] / land
       out["Episode/num_resets"] = v[K["B2E_LOG_NRESET"]]
+      if cfg.terrain_mode:
+        out["Curriculum/terrain_levels"] = v[K["B2E_LOG_TERRAIN_LEVEL"]] / B
       self._vals = out
     return self._vals
 
@@ -209,7 +216,9 @@ class ManagerBasedRlEnv:
     self.device = device
     self.render_mode = render_mode
     self._lib = A.load_library()
-    model = load_model(f"{cfg.robot}_flat")
+    if cfg.terrain == "rough" and cfg.robot != "g1":
+      raise ValueError("the rough-terrain scene is built for the G1 (box-box contacts of the Go1 trunk are not implemented)")
+    model = load_model(f"{cfg.robot}_flat" if cfg.terrain == "flat" else ("g1_rough_play" if cfg.play else "g1_rough"))
     self.sim = Simulation(cfg.num_envs, cfg.sim, model, device)
     dev = torch.device(device)
     self._dev = dev
@@ -234,7 +243,19 @@ class ManagerBasedRlEnv:
         t = torch.zeros(tuple(shp(self.vcfg)), dtype=_TORCH[dt], device=dev)
       self._buf[attr] = t
       self._ce.buf[i] = t.data_ptr()
-    self._buf["env_origins"][:] = torch.as_tensor(env_origins_grid(n, cfg.env_spacing), device=dev)
+    if self.vcfg.terrain_mode:
+      # TerrainImporter._compute_env_origins_curriculum (terrains/terrain_importer.py:224-244): column by env index, a
+      # uniformly drawn start row up to max_init_terrain_level
+      from . import terrains
+      org = self.vcfg.terrain_origins
+      rows, cols = org.shape[:2]
+      types = terrains.terrain_types(n, cols)
+      levels = np.random.default_rng(cfg.seed).integers(0, min(self.vcfg.max_init_terrain_level, rows - 1) + 1, n)
+      self._buf["terrain_type"][:] = torch.as_tensor(types, device=dev).to(torch.int32)
+      self._buf["terrain_level"][:] = torch.as_tensor(levels, device=dev).to(torch.int32)
+      self._buf["env_origins"][:] = torch.as_tensor(org[levels, types], dtype=torch.float32, device=dev)
+    else:
+      self._buf["env_origins"][:] = torch.as_tensor(env_origins_grid(n, cfg.env_spacing), device=dev)
     if self.vcfg.push_enabled:  # EventManager._prepare_terms (managers/event_manager.py:196-210)
       lo, hi = self.vcfg.push_interval
       self._buf["push_time_left"][:] = torch.rand(n, device=dev) * (hi - lo) + lo

@@ -100,7 +100,10 @@ BUFFERS = [
   ("NOISE_LO", "noise_lo", "table", "f4", lambda c: (c.n_obs_policy,)),
   ("NOISE_HI", "noise_hi", "table", "f4", lambda c: (c.n_obs_policy,)),
   ("DEFAULT_ROOT_STATE", "default_root_state", "table", "f4", lambda c: (13,)),
+  ("TERRAIN_ORIGINS", "terrain_origins", "table", "f4", lambda c: (max(c.terrain_rows, 1), max(c.terrain_cols, 1), 3)),
   ("ENV_ORIGINS", "env_origins", "state", "f4", lambda c: (3,)),
+  ("TERRAIN_LEVEL", "terrain_level", "state", "i4", lambda c: ()),
+  ("TERRAIN_TYPE", "terrain_type", "state", "i4", lambda c: ()),
   ("ACTION_IN", "action_in", "state", "f4", lambda c: (c.nj,)),
   ("ACTION", "action", "state", "f4", lambda c: (c.nj,)),
   ("PREV_ACTION", "prev_action", "state", "f4", lambda c: (c.nj,)),
@@ -147,6 +150,7 @@ def table_values(cfg) -> dict:
     default_joint_vel=np.zeros(cfg.nj), soft_lo=cfg.soft_joint_pos_limits[:, 0], soft_hi=cfg.soft_joint_pos_limits[:, 1],
     action_scale=cfg.action_scale, action_offset=cfg.default_joint_pos, std_standing=cfg.std_standing, std_walking=cfg.std_walking,
     std_running=cfg.std_running, noise_lo=cfg.noise_lo, noise_hi=cfg.noise_hi, default_root_state=cfg.default_root_state,
+    terrain_origins=cfg.terrain_origins if cfg.terrain_origins is not None else np.zeros((1, 1, 3)),
   )
 
 
@@ -158,7 +162,8 @@ def fill_params(ce: B2Env, cfg) -> None:
                   ("ANGVEL_ADR", cfg.angvel_adr), ("ANGMOM_ADR", cfg.angmom_adr), ("SELFCOL_ADR", cfg.selfcol_adr),
                   ("ILLEGAL_ADR", max(cfg.illegal_adr, 0)), ("ILLEGAL_COUNT", cfg.illegal_count),
                   ("MAX_EPISODE_LENGTH", min(int(cfg.max_episode_length), 2**31 - 1)), ("ENABLE_CORRUPTION", int(cfg.enable_corruption)),
-                  ("PUSH_ENABLED", int(cfg.push_enabled)), ("HEADING_COMMAND", int(cfg.heading_command))):
+                  ("PUSH_ENABLED", int(cfg.push_enabled)), ("HEADING_COMMAND", int(cfg.heading_command)),
+                  ("TERRAIN_MODE", int(cfg.terrain_mode)), ("TERRAIN_ROWS", int(cfg.terrain_rows)), ("TERRAIN_COLS", int(cfg.terrain_cols))):
     ip[K["B2E_IP_" + name]] = int(v)
   for f in range(cfg.nfeet):
     ip[K["B2E_IP_FOOT_SITE"] + f] = int(cfg.foot_site_ids[f])
@@ -170,6 +175,7 @@ def fill_params(ce: B2Env, cfg) -> None:
                   ("WALKING_THRESHOLD", cfg.walking_threshold), ("RUNNING_THRESHOLD", cfg.running_threshold),
                   ("AIR_THR_MIN", cfg.air_thr_min), ("AIR_THR_MAX", cfg.air_thr_max), ("AIR_CMD_THRESHOLD", cfg.air_cmd_threshold),
                   ("TARGET_HEIGHT", cfg.target_height), ("CMD_THRESHOLD", cfg.cmd_threshold), ("REL_STANDING", cfg.rel_standing),
+                  ("TERRAIN_HALF_SIZE", cfg.terrain_half_size),
                   ("REL_HEADING", cfg.rel_heading), ("HEADING_STIFFNESS", cfg.heading_stiffness)):
     fp[K["B2E_FP_" + name]] = float(v)
   for name, pair in (("CMD_RESAMPLE", cfg.cmd_resample), ("CMD_LIN_X", cfg.cmd_lin_x), ("CMD_LIN_Y", cfg.cmd_lin_y),

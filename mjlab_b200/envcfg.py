@@ -119,7 +119,20 @@ class VelocityCfg:
   heading_command: bool = True
   seed: int = 0
   foot_site_body: np.ndarray = None  # body of each foot site (site velocities, entity/data.py:323-331)
+  # rough terrain (velocity_env_cfg.py:296-324): bit 0 = terrain_levels_vel curriculum, bit 1 = play-mode randomize_terrain
+  terrain_mode: int = 0
+  terrain_origins: np.ndarray = None  # [rows, cols, 3]
+  terrain_half_size: float = 4.0
+  max_init_terrain_level: int = 5
   extra: dict = field(default_factory=dict)
+
+  @property
+  def terrain_rows(self) -> int:
+    return 0 if self.terrain_origins is None else int(self.terrain_origins.shape[0])
+
+  @property
+  def terrain_cols(self) -> int:
+    return 0 if self.terrain_origins is None else int(self.terrain_origins.shape[1])
 
   @staticmethod
   def _ranges6(d: dict) -> np.ndarray:
@@ -229,7 +242,17 @@ def velocity_cfg(m, robot: str, play: bool = False) -> VelocityCfg:
     max_episode_length=math.ceil(int(1e9) / 0.02) if play else 1000, max_episode_length_s=float(int(1e9)) if play else 20.0,
     enable_corruption=not play, push_enabled=not play,
     foot_site_body=np.asarray(m.site_bodyid)[site_ids[list(foot_local)]].astype(int),
+    **_terrain_fields(m, play),
   )
+
+
+def _terrain_fields(m, play: bool) -> dict:
+  """Scenes compiled with a generated terrain carry its spawn origins (tools/make_models.py)."""
+  org = getattr(m, "terrain_origins", None)
+  if org is None:
+    return {}
+  return dict(terrain_mode=1 | (2 if play else 0), terrain_origins=np.asarray(org, float),
+              terrain_half_size=float(np.asarray(m.terrain_size)[0]) / 2.0)
 
 
 # ---------------------------------------------------------------------------------------------------------

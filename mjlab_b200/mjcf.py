@@ -846,6 +846,88 @@ def _infer_inertial(b: SBody):
 # ---------------------------------------------------------------------------
 # Compile: Spec -> ModelDesc.
 # ---------------------------------------------------------------------------
+FIELD_MIN_GEOMS = 16     # fewer static geoms than this stay ordinary candidate pairs
+FIELD_CELL = 1.0         # grid cell edge [m]
+
+
+def _build_geom_field(m: "ModelDesc", fld: np.ndarray, body_parentid, excl) -> None:
+  """Uniform-grid index over the static field geoms `fld` (see `_compile`).
+
+  Writes: field_geom[nfield] (geom id), field_aabb[nfield, 6] (centre, half extents of the world AABB),
+  field_cell0[nfield, 2] (lowest grid cell the AABB touches: a pair met in several cells is reported from the first
+  common one), field_grid = [x0, y0, cell, 1 / cell], field_nx / field_ny, field_cell_adr[ncell + 1], field_cell_item[...]
+  (field indices, ascending within a cell), fq_geom[nfq] (moving geoms that can touch the field, in geom order).
+  """
+  nf = len(fld)
+  m.nfield = nf
+  m.field_geom = fld.astype(np.int32)
+  m.field_aabb = np.zeros((nf, 6))
+  m.field_cell0 = np.zeros((nf, 2), np.int32)
+  m.field_grid = np.array([0.0, 0.0, FIELD_CELL, 1.0 / FIELD_CELL])
+  m.field_nx = m.field_ny = 0
+  m.field_cell_adr = np.zeros(1, np.int32)
+  m.field_cell_item = np.zeros(0, np.int32)
+  m.fq_geom = np.zeros(0, np.int32)
+  m.nfq = 0
+  if nf == 0:
+    return
+  for i, g in enumerate(fld):
+    R = m.sgeom_xmat[g].reshape(3, 3)
+    t, sz = m.geom_type[g], m.geom_size[g]
+    if t == GEOM_BOX:
+      half = np.abs(R) @ sz
+    elif t == GEOM_SPHERE:
+      half = np.full(3, sz[0])
+    else:
+      half = np.abs(R[:, 2]) * sz[1] + sz[0]
+    m.field_aabb[i] = np.concatenate([m.sgeom_xpos[g], half])
+  lo = (m.field_aabb[:, :2] - m.field_aabb[:, 3:5]).min(0)
+  hi = (m.field_aabb[:, :2] + m.field_aabb[:, 3:5]).max(0)
+  cell = FIELD_CELL
+  nx, ny = (int(math.ceil((hi[k] - lo[k]) / cell)) + 1 for k in range(2))
+  m.field_grid = np.array([lo[0], lo[1], cell, 1.0 / cell])
+  m.field_nx, m.field_ny = nx, ny
+  c0 = np.floor((m.field_aabb[:, :2] - m.field_aabb[:, 3:5] - lo) / cell).astype(np.int64)
+  c1 = np.floor((m.field_aabb[:, :2] + m.field_aabb[:, 3:5] - lo) / cell).astype(np.int64)
+  c0[:, 0], c1[:, 0] = np.clip(c0[:, 0], 0, nx - 1), np.clip(c1[:, 0], 0, nx - 1)
+  c0[:, 1], c1[:, 1] = np.clip(c0[:, 1], 0, ny - 1), np.clip(c1[:, 1], 0, ny - 1)
+  m.field_cell0 = c0.astype(np.int32)
+  counts = np.zeros(nx * ny + 1, np.int64)
+  for i in range(nf):
+    xs, ys = np.arange(c0[i, 0], c1[i, 0] + 1), np.arange(c0[i, 1], c1[i, 1] + 1)
+    np.add.at(counts, (xs[:, None] * ny + ys[None, :]).ravel() + 1, 1)
+  adr = np.cumsum(counts)
+  items = np.zeros(adr[-1], np.int32)
+  fill = adr[:-1].copy()
+  for i in range(nf):     # ascending i => ascending field index inside every cell
+    xs, ys = np.arange(c0[i, 0], c1[i, 0] + 1), np.arange(c0[i, 1], c1[i, 1] + 1)
+    cells = (xs[:, None] * ny + ys[None, :]).ravel()
+    items[fill[cells]] = i
+    fill[cells] += 1
+  m.field_cell_adr, m.field_cell_item = adr.astype(np.int32), items
+  # query geoms: the collision filter of every (moving geom, field geom) pair, which must not depend on the field geom
+  ct, ca = m.geom_contype, m.geom_conaffinity
+  fct, fca = np.unique(ct[fld]), np.unique(ca[fld])
+  fbody = np.unique(m.geom_bodyid[fld])
+  if len(fct) != 1 or len(fca) != 1:
+    raise NotImplementedError("field geoms with differing contype / conaffinity")
+  q = []
+  for g in m.dyn_geom:
+    if not ((ct[g] & fca[0]) or (fct[0] & ca[g])):
+      continue
+    b = m.geom_bodyid[g]
+    if any((min(b, fb), max(b, fb)) in excl for fb in fbody):
+      raise NotImplementedError("<exclude> between a moving body and a field body")
+    if m.geom_type[g] not in (GEOM_SPHERE, GEOM_CAPSULE):
+      raise NotImplementedError(f"geom '{m.geom_names[g]}': only spheres and capsules collide with a geom field "
+                                "(box-box / mesh narrowphase is not implemented)")
+    if m.geom_type[g] > GEOM_BOX or np.any(m.geom_type[fld] != GEOM_BOX):
+      raise NotImplementedError("geom fields hold boxes only")
+    q.append(g)
+  m.fq_geom = np.array(q, np.int32)
+  m.nfq = len(q)
+
+
 def _compile(spec: Spec) -> ModelDesc:
   bodies: list[SBody] = []
   parent: list[int] = []
@@ -1125,10 +1207,39 @@ def _compile(spec: Spec) -> ModelDesc:
     ia, ib = body_names.index(a), body_names.index(b)
     excl.add((min(ia, ib), max(ia, ib)))
   m.exclude_pairs = np.array(sorted(excl), np.int32).reshape(-1, 2)
-  pairs = []
+  # static geometry: geoms of bodies welded to the world never move, so their world pose is a model constant
+  # (`sgeom_xpos/xmat`) and the kernels only run forward kinematics for `dyn_geom`
   gb, gw = m.geom_bodyid, body_weldid
-  for g1 in range(ngeom):
-    for g2 in range(g1 + 1, ngeom):
+  sxpos, sxquat = np.zeros((nbody, 3)), np.tile([1.0, 0, 0, 0], (nbody, 1))
+  for b in range(1, nbody):
+    if gw[b] == 0 and body_mocapid[b] < 0:
+      pb = body_parentid[b]
+      sxpos[b] = sxpos[pb] + quat_to_mat(sxquat[pb]) @ body_pos[b]
+      sxquat[b] = quat_mul(sxquat[pb], body_quat[b])
+  static = np.array([gw[gb[g]] == 0 and body_mocapid[gb[g]] < 0 for g in range(ngeom)], bool) if ngeom else np.zeros(0, bool)
+  m.dyn_geom = np.flatnonzero(~static).astype(np.int32)
+  m.ndyn = len(m.dyn_geom)
+  m.sgeom_xpos, m.sgeom_xmat = np.zeros((ngeom, 3)), np.zeros((ngeom, 9))
+  for g in np.flatnonzero(static):
+    Rb = quat_to_mat(sxquat[gb[g]])
+    m.sgeom_xpos[g] = sxpos[gb[g]] + Rb @ m.geom_pos[g]
+    m.sgeom_xmat[g] = quat_to_mat(quat_mul(sxquat[gb[g]], m.geom_quat[g])).reshape(9)
+
+  # geom field: many static, bounded, collidable geoms (terrain boxes) are not enumerated pair by pair; they go into a
+  # uniform xy grid (cell -> field geoms whose AABB overlaps it) that each moving "query" geom looks up at run time
+  collidable = (m.geom_contype != 0) | (m.geom_conaffinity != 0)
+  bounded = np.isin(m.geom_type, (GEOM_SPHERE, GEOM_CAPSULE, GEOM_BOX))
+  fld = np.flatnonzero(static & collidable & bounded)
+  if len(fld) < FIELD_MIN_GEOMS:
+    fld = fld[:0]
+  in_field = np.zeros(ngeom, bool)
+  in_field[fld] = True
+  _build_geom_field(m, fld, body_parentid, excl)
+
+  pairs = []
+  active = [g for g in range(ngeom) if collidable[g] and not in_field[g]]
+  for ia, g1 in enumerate(active):
+    for g2 in active[ia + 1:]:
       b1, b2 = gb[g1], gb[g2]
       ct1, ca1, ct2, ca2 = m.geom_contype[g1], m.geom_conaffinity[g1], m.geom_contype[g2], m.geom_conaffinity[g2]
       if not ((ct1 & ca2) or (ct2 & ca1)):

@@ -252,13 +252,19 @@ def build_entity(robot: Spec, acts, coll: CollisionCfg, init) -> Spec:
   return robot
 
 
-def build_scene(robot_xml: str, which: str, *, timestep=0.005, iterations=10, ls_iterations=20) -> Spec:
-  """terrain plane + robot + sensors, as Scene.__init__ (scene/scene.py:29-45)."""
+def build_scene(robot_xml: str, which: str, *, terrain=None, timestep=0.005, iterations=10, ls_iterations=20) -> Spec:
+  """terrain + robot + sensors, as Scene.__init__ (scene/scene.py:29-45).  `terrain=None`: the ground plane
+  (terrain_importer.py:154-163); a `terrains.Terrain`: its boxes as geoms `terrain_<i>` of the body "terrain"
+  (terrain_generator.py:93-116)."""
   acts, coll, init, sensors = {"g1": g1_cfg, "go1": go1_cfg}[which]()
   robot = build_entity(Spec.from_string(robot_xml), acts, coll, init)
   scene = Spec()
-  terrain = scene.worldbody.add_body(name="terrain")
-  terrain.add_geom(name="terrain", type=mjcf.GEOM_PLANE, size=(0, 0, 0.01))
+  tbody = scene.worldbody.add_body(name="terrain")
+  if terrain is None:
+    tbody.add_geom(name="terrain", type=mjcf.GEOM_PLANE, size=(0, 0, 0.01))
+  else:
+    for i, row in enumerate(terrain.boxes):
+      tbody.add_geom(name=f"terrain_{i}", type=mjcf.GEOM_BOX, pos=row[:3], size=row[3:6])
   key = robot.keys[0]
   robot.keys.clear()
   scene.attach(robot, prefix="robot/")

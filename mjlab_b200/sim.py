@@ -241,6 +241,8 @@ class Simulation:
     self._reset_mask = torch.zeros(num_envs, dtype=torch.bool, device=dev)
 
     E.check_call(self._lib, self._lib.b2_check(C.byref(self._cm), C.byref(self._cd)))
+    # static geoms (terrain): their world pose is written once; the step kernels only update moving geoms
+    E.check_call(self._lib, self._lib.b2_init_static(C.byref(self._cm), C.byref(self._cd), self._stream()))
 
     self._model_bridge = TensorBridge(_ModelFields(self))
     self._data_bridge = TensorBridge(self._data_fields)

@@ -61,6 +61,7 @@ class CpuSim:
       setattr(self, attr, a)
       self.cd.di[i] = a.ctypes.data
     self.qpos[:] = m.qpos0
+    E.init_static_numpy(m, self.geom_xpos, self.geom_xmat)
 
   def step(self, nstep: int = 1, nthread: int = 1) -> None:
     self.lib.cport_steps(C.byref(self.cm), C.byref(self.cd), int(nstep), int(nthread))

@@ -100,6 +100,7 @@ def make_state(cfg, nworld: int, env_origins=None) -> NS:
   z = lambda *s: np.zeros((nworld,) + s, F)  # noqa: E731
   return NS(
     env_origins=z(3) if env_origins is None else np.asarray(env_origins, F),
+    terrain_level=np.zeros(nworld, np.int32), terrain_type=np.zeros(nworld, np.int32),
     action=z(nj), prev_action=z(nj), prev_prev_action=z(nj), raw_action=z(nj), processed_action=z(nj), encoder_bias=z(nj),
     joint_pos_target=z(nj), command=z(3), heading_target=z(), heading_error=z(), cmd_time_left=z(), cmd_metrics=z(2),
     cmd_counter=np.zeros(nworld, np.int32), is_heading=np.zeros(nworld, bool), is_standing=np.zeros(nworld, bool),
@@ -334,6 +335,8 @@ def post(cfg, m, s, d, u=None, do_reset=True) -> None:
   if not do_reset:
     return
   reset_idx(cfg, m, s, d, np.nonzero(s.reset_buf)[0], u)
+  if cfg.terrain_mode:
+    s.log_env[:, K["B2E_LOG_TERRAIN_LEVEL"]] = s.terrain_level
 
 
 def reset_idx(cfg, m, s, d, ids, u) -> None:
@@ -346,6 +349,18 @@ def reset_idx(cfg, m, s, d, ids, u) -> None:
   s.log_env[ids, K["B2E_LOG_TERM_COUNT"]: K["B2E_LOG_TERM_COUNT"] + A.NTERM] = s.term_dones[ids]
   s.log_env[ids, K["B2E_LOG_CMD_ERR_XY"]] = s.cmd_metrics[ids, 0]
   s.log_env[ids, K["B2E_LOG_CMD_ERR_YAW"]] = s.cmd_metrics[ids, 1]
+  # curriculum_manager.compute comes first (manager_based_rl_env.py:382): terrain_levels_vel on the pre-reset state
+  # (tasks/velocity/mdp/curriculums.py:30-64) + TerrainImporter.update_env_origins (terrains/terrain_importer.py:196-209)
+  if cfg.terrain_mode & 1:
+    rows = cfg.terrain_rows
+    dist = np.sqrt(np.sum(np.square(d.xpos[ids, cfg.root_body, :2].astype(F) - s.env_origins[ids, :2]), 1))
+    up = dist > F(cfg.terrain_half_size)
+    down = (dist < np.sqrt(np.sum(np.square(s.command[ids, :2]), 1)) * F(cfg.max_episode_length_s) * F(0.5)) & ~up
+    lv = s.terrain_level[ids] + up.astype(np.int32) - down.astype(np.int32)
+    restart = np.minimum((u[ids, K["B2E_DRAW_TERRAIN"]] * F(rows)).astype(np.int32), rows - 1)
+    lv = np.where(lv >= rows, restart, np.maximum(lv, 0))
+    s.terrain_level[ids] = lv
+    s.env_origins[ids] = cfg.terrain_origins.astype(F)[lv, s.terrain_type[ids]]
   # sim.reset (mjwarp.reset_data, sim/sim.py:275-286)
   d.qpos[ids] = m.qpos0
   for f in ("qvel", "qacc", "qacc_warmstart", "ctrl", "time"):
@@ -365,6 +380,12 @@ def reset_idx(cfg, m, s, d, ids, u) -> None:
   vel = drs[None, 7:13] + vs
   d.qpos[ids, 0:3], d.qpos[ids, 3:7] = pos, quat
   d.qvel[ids, 0:3], d.qvel[ids, 3:6] = vel[:, 0:3], quat_apply_inverse(quat, vel[:, 3:6])  # entity/data.py:99-110
+  if cfg.terrain_mode & 2:
+    # play mode: randomize_terrain (envs/mdp/events.py:26-37) is the last reset event; the pose above used the old origin
+    rows, cols = cfg.terrain_rows, cfg.terrain_cols
+    s.terrain_level[ids] = np.minimum((u[ids, K["B2E_DRAW_TERRAIN"] + 1] * F(rows)).astype(np.int32), rows - 1)
+    s.terrain_type[ids] = np.minimum((u[ids, K["B2E_DRAW_TERRAIN"] + 2] * F(cols)).astype(np.int32), cols - 1)
+    s.env_origins[ids] = cfg.terrain_origins.astype(F)[s.terrain_level[ids], s.terrain_type[ids]]
   # reset_joints_by_offset (envs/mdp/events.py:171-206)
   nj = cfg.nj
   jp = cfg.default_joint_pos.astype(F)[None] + _uni(u[ids, K["B2E_DRAW_RESET_JOINT_POS"]: K["B2E_DRAW_RESET_JOINT_POS"] + nj], *cfg.reset_joint_pos)

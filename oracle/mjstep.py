@@ -209,12 +209,21 @@ def kinematics(m, d):
   for i in range(nb):
     d.xipos[i] = d.xpos[i] + d.xmat[i] @ m.body_ipos[i]
     d.ximat[i] = quat_to_mat(quat_mul(d.xquat[i], m.body_iquat[i]))
-  d.geom_xpos = np.zeros((m.ngeom, 3))
-  d.geom_xmat = np.zeros((m.ngeom, 3, 3))
-  for g in range(m.ngeom):
+  # geoms of bodies welded to the world never move: evaluate them (through the same body FK) once per Data
+  cache = getattr(d, "_static_geoms", None)
+  if cache is None:
+    weld0 = np.array([m.body_weldid[m.geom_bodyid[g]] == 0 and m.body_mocapid[m.geom_bodyid[g]] < 0 for g in range(m.ngeom)], bool)
+    d.geom_xpos = np.zeros((m.ngeom, 3))
+    d.geom_xmat = np.zeros((m.ngeom, 3, 3))
+    todo = range(m.ngeom)
+  else:
+    weld0 = cache
+    todo = np.flatnonzero(~weld0)
+  for g in todo:
     b = m.geom_bodyid[g]
     d.geom_xpos[g] = d.xpos[b] + d.xmat[b] @ m.geom_pos[g]
     d.geom_xmat[g] = quat_to_mat(quat_mul(d.xquat[b], m.geom_quat[g]))
+  d._static_geoms = weld0
   d.site_xpos = np.zeros((m.nsite, 3))
   d.site_xmat = np.zeros((m.nsite, 3, 3))
   for s in range(m.nsite):
@@ -383,8 +392,104 @@ def _narrowphase(m, d, g1, g2, margin):
         r = _sphere_sphere(p1 + a1 * x1, s1[0], v2, s2[0], margin)
         if r:
           out.append((r[0], r[1], r[2], None))
+  elif t1 == GEOM_SPHERE and t2 == GEOM_BOX:
+    r = _sphere_box(p1, s1[0], p2, R2, s2, margin)
+    if r:
+      out.append((r[0], r[1], r[2], None))
+  elif t1 == GEOM_CAPSULE and t2 == GEOM_BOX:
+    for r in _capsule_box(p1, R1[:, 2], s1[0], s1[1], p2, R2, s2, margin):
+      out.append((r[0], r[1], r[2], None))
   else:
     raise NotImplementedError(f"geom pair types ({t1},{t2}) outside the supported subset")
+  return out
+
+
+def _sphere_box(sp, r, bp, bR, bs, margin):
+  """Sphere against box, after MuJoCo's published sphere-box routine (engine_collision_box.c `mjraw_SphereBox`; the
+  reference reaches it through mujoco_warp's collision_primitive.sphere_box): clamp the sphere centre into the box; when the
+  centre is inside, leave through the nearest face.  Normal points from the sphere to the box."""
+  c = bR.T @ (sp - bp)
+  clamped = np.clip(c, -bs, bs)
+  dif = clamped - c
+  dd = np.linalg.norm(dif)
+  if dd - r > margin:
+    return None
+  if dd <= MINVAL:
+    closest, k = 2 * bs.sum(), 0
+    for i in range(6):
+      fd = abs((bs[i // 2] if i % 2 else -bs[i // 2]) - c[i // 2])
+      if fd < closest:
+        closest, k = fd, i
+    nb = np.zeros(3)
+    nb[k // 2] = -1.0 if k % 2 else 1.0
+    pb = c + nb * (r - closest) * 0.5
+    dist = -closest - r
+  else:
+    nb = dif / dd
+    dist = dd - r
+    pb = c + nb * (r + 0.5 * dist)
+  return dist, bp + bR @ pb, bR @ nb
+
+
+CAPBOX_BISECT = 24
+
+
+def _capsule_box(cp, ax, r, h, bp, bR, bs, margin):
+  """Capsule against box: up to two contacts, each a sphere-box test at a point of the capsule's segment, which is how
+  MuJoCo's capsule-box routine emits its contacts.  The choice of the two points is this engine's own, simpler rule (MuJoCo
+  enumerates face / edge / corner configurations): the squared distance from the segment point p + a t to the box is convex
+  in t, so its half-derivative g(t) is nondecreasing; [ta, tb] = the stretch where g == 0 within [-h, h] (one point unless
+  the segment runs parallel to a face or inside the box), found by bisection.  A stretch with a length gives its two ends;
+  a single closest point gives itself plus the segment end farther from it.  Parity for this pair type is unpinned."""
+  p = bR.T @ (cp - bp)
+  a = bR.T @ ax
+
+  def g(t):
+    q = p + a * t
+    e = np.where(q > bs, q - bs, np.where(q < -bs, q + bs, 0.0))
+    return float(np.dot(a, e))
+
+  g_lo, g_hi = g(-h), g(h)
+  if g_lo >= 0:
+    ta = -h
+  elif g_hi < 0:
+    ta = h
+  else:
+    lo, hi = -h, h
+    for _ in range(CAPBOX_BISECT):
+      mid = 0.5 * (lo + hi)
+      if g(mid) >= 0:
+        hi = mid
+      else:
+        lo = mid
+    ta = hi
+  if g_hi <= 0:
+    tb = h
+  elif g_lo > 0:
+    tb = -h
+  else:
+    lo, hi = -h, h
+    for _ in range(CAPBOX_BISECT):
+      mid = 0.5 * (lo + hi)
+      if g(mid) <= 0:
+        lo = mid
+      else:
+        hi = mid
+    tb = lo
+  tol = 1e-4 * h
+  if tb - ta > tol:
+    t1, t2 = ta, tb
+  else:
+    t1 = 0.5 * (ta + tb)
+    t2 = -h if t1 > 0 else h
+  out = []
+  r1 = _sphere_box(cp + ax * t1, r, bp, bR, bs, margin)
+  if r1:
+    out.append(r1)
+  if abs(t2 - t1) > tol:
+    r2 = _sphere_box(cp + ax * t2, r, bp, bR, bs, margin)
+    if r2:
+      out.append(r2)
   return out
 
 
@@ -418,13 +523,44 @@ def _mix_params(m, d, g1, g2):
   return int(condim), solref, solimp, friction, margin, gap
 
 
+def _field_candidates(m, d):
+  """(query geom, field geom) pairs under the bounding sphere of each query geom, in the order the uniform grid yields
+  them: by query geom, grid cell (x-major), field index; a box met in several cells comes from the first shared one."""
+  x0, y0, _, inv = m.field_grid
+  out = []
+  for g in m.fq_geom:
+    c = d.geom_xpos[g]
+    rb = m.geom_rbound[g] + m.geom_margin[g]
+    cx0 = max(int(np.floor((c[0] - rb - x0) * inv)), 0)
+    cx1 = min(int(np.floor((c[0] + rb - x0) * inv)), m.field_nx - 1)
+    cy0 = max(int(np.floor((c[1] - rb - y0) * inv)), 0)
+    cy1 = min(int(np.floor((c[1] + rb - y0) * inv)), m.field_ny - 1)
+    for cx in range(cx0, cx1 + 1):
+      for cy in range(cy0, cy1 + 1):
+        cell = cx * m.field_ny + cy
+        for fi in m.field_cell_item[m.field_cell_adr[cell]:m.field_cell_adr[cell + 1]]:
+          fx0, fy0 = m.field_cell0[fi]
+          if cx != max(cx0, fx0) or cy != max(cy0, fy0):
+            continue
+          a = m.field_aabb[fi]
+          e = np.maximum(np.abs(c - a[:3]) - a[3:], 0.0)
+          if np.dot(e, e) > rb * rb:
+            continue
+          out.append((int(g), int(m.field_geom[fi])))
+  return out
+
+
 def collision(m, d, nconmax=None):
   d.contacts = []
-  for k in range(m.npair):
-    g1, g2 = m.pair_geom[k]
+  cands = [(int(a), int(b), False) for a, b in np.asarray(m.pair_geom).reshape(-1, 2)]
+  if getattr(m, "nfield", 0) > 0:
+    cands += [(a, b, True) for a, b in _field_candidates(m, d)]
+  for g1, g2, from_field in cands:
     condim, solref, solimp, friction, margin, gap = _mix_params(m, d, g1, g2)
-    # bounding-sphere broadphase (planes are unbounded)
-    if m.geom_type[g1] == GEOM_PLANE:
+    # bounding-sphere broadphase (planes are unbounded; field pairs passed their sphere-vs-AABB test already)
+    if from_field:
+      pass
+    elif m.geom_type[g1] == GEOM_PLANE:
       n = d.geom_xmat[g1][:, 2]
       if np.dot(d.geom_xpos[g2] - d.geom_xpos[g1], n) > margin + m.geom_rbound[g2]:
         continue

@@ -77,6 +77,7 @@ class HostSim:
       setattr(self, attr, a)
       self.cd.di[i] = a.ctypes.data
     self.qpos[:] = m.qpos0
+    E.init_static_numpy(m, self.geom_xpos, self.geom_xmat)
 
   def expand(self, attr: str) -> np.ndarray:
     """Per-world copy of a model float field (expand_model_fields)."""

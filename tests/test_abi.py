@@ -85,7 +85,7 @@ def test_env_header_symbols_exported_and_struct_matches():
   # the buffer table follows the header enum order, and the reward / termination name lists match the enum sizes
   from mjlab_b200 import envcfg
   assert len(envcfg.REWARD_NAMES) == A.NREW and len(envcfg.TERMINATION_NAMES) == A.NTERM
-  assert A.K["B2E_DRAW_NOISE"] + 160 == A.NDRAW
+  assert A.K["B2E_DRAW_NOISE"] + 160 == A.K["B2E_DRAW_TERRAIN"] and A.K["B2E_DRAW_TERRAIN"] + 3 == A.NDRAW
 
 
 def test_env_requires_cuda():

@@ -5,7 +5,8 @@ input data, not code):
 
     python tools/make_models.py
 
-Writes mjlab_b200/assets/{g1_flat,go1_flat}.npz.  Nothing at run time reads
+Writes mjlab_b200/assets/{g1_flat,go1_flat,g1_rough,g1_rough_play}.npz (rough: the ROUGH_TERRAINS_CFG box grid with the
+fixed terrain seed 0 of SURVEY.md section 8(d), config 4).  Nothing at run time reads
 /root/reference; the GPU box only sees the .npz files.
 """
 import sys
@@ -13,7 +14,9 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
-from mjlab_b200 import robots  # noqa: E402
+import numpy as np  # noqa: E402
+
+from mjlab_b200 import robots, terrains  # noqa: E402
 
 REF = Path("/root/reference/src/mjlab/asset_zoo/robots")
 SRC = {
@@ -30,3 +33,11 @@ if __name__ == "__main__":
     m.save(out / f"{which}_flat.npz")
     print(which, dict(nq=m.nq, nv=m.nv, nu=m.nu, nbody=m.nbody, ngeom=m.ngeom, nsite=m.nsite,
                       nsensordata=m.nsensordata, npair=m.npair, meaninertia=round(m.stat_meaninertia, 5)))
+  for name, play in (("g1_rough", False), ("g1_rough_play", True)):
+    ter = terrains.generate(terrains.rough_terrains_cfg(play=play, seed=0))
+    m = robots.build_scene(SRC["g1"].read_text(), "g1", terrain=ter).compile()
+    m.terrain_origins = np.asarray(ter.origins, float)
+    m.terrain_size = np.asarray(ter.cfg.size, float)
+    m.save(out / f"{name}.npz")
+    print(name, dict(ngeom=m.ngeom, npair=m.npair, nfield=m.nfield, nfq=m.nfq, ndyn=m.ndyn, grid=(m.field_nx, m.field_ny),
+                     items=len(m.field_cell_item)))
