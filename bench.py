@@ -46,14 +46,19 @@ def parse():
   ap.add_argument("--warmup", type=int, default=20)
   ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
   ap.add_argument("--model", default="g1_flat")
-  ap.add_argument("--task", default="velocity", choices=["velocity", "tracking"],
+  ap.add_argument("--task", default="velocity", choices=["velocity", "tracking", "rough"],
                   help="velocity (BASELINE configs 2/3, the headline) or tracking (config 5: synthetic clip, domain randomisation on)")
-  ap.add_argument("--num-envs", type=int, default=NUM_ENVS)
+  ap.add_argument("--num-envs", type=int, default=None, help="envs per GPU (default 4096; 8192 for --task rough, BASELINE config 4)")
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-roofline-pass", action="store_true")
   ap.add_argument("--forward-mode", default="reference", choices=["reference", "masked"],
                   help="forward pass after resets: all envs when any env reset (the reference's behaviour) or only the reset envs")
-  return ap.parse_args()
+  args = ap.parse_args()
+  if args.task == "rough":
+    args.model = "g1_rough"
+  if args.num_envs is None:
+    args.num_envs = 8192 if args.task == "rough" else NUM_ENVS
+  return args
 
 
 def action_scale(m) -> np.ndarray:
@@ -65,7 +70,8 @@ def action_scale(m) -> np.ndarray:
 
 def algorithmic_bytes(m):
   """bytes that must cross HBM per world per physics step, split by stage."""
-  nq, nv, nu, nb, ng, ns, nsd = m.nq, m.nv, m.nu, m.nbody, m.ngeom, m.nsite, m.nsensordata
+  nq, nv, nu, nb, ns, nsd = m.nq, m.nv, m.nu, m.nbody, m.nsite, m.nsensordata
+  ng = m.ngeom if m.nfield == 0 else m.ndyn   # terrain-field geoms are static: their pose is never rewritten
   smooth_r = nq + nv + nu + 6 * nb
   smooth_w = nb * (3 + 4 + 3 + 3 + 6) + ng * 12 + ns * 12 + nu + nv
   solve_r = nv + 1
@@ -264,6 +270,8 @@ def workload_name(model: str, num_envs: int, forward_mode: str = "reference", ta
     return (f"{model} motion-tracking task (synthetic 500-frame clip, domain randomisation on), env step, {num_envs} envs/GPU: action -> ctrl, "
             f"{DECIMATION} physics steps, 4 terminations, 9 reward terms, resets with adaptive start-frame sampling, forward after resets "
             f"({forward_mode}), frame advance + anchor-relative targets, push events, observations (policy 160 + critic 286, noise) - one CUDA graph")
+  if task == "rough":
+    model += " (3564-box ROUGH_TERRAINS_CFG grid, terrain seed 0, terrain-level curriculum)"
   return (f"{model} velocity task, ManagerBasedRlEnv.step, {num_envs} envs/GPU: action -> ctrl, {DECIMATION} x (physics step + "
           "contact air-time update), terminations, 14 reward terms, resets (sim + events + managers), "
           f"forward after resets ({forward_mode}), commands, push events, observations (policy+critic, noise) - one CUDA graph")
@@ -296,7 +304,8 @@ def run_b200(args):
     if args.task == "tracking":
       from mjlab_b200.tracking_env import TrackingEnvCfg, TrackingRlEnv
       return TrackingRlEnv(TrackingEnvCfg(num_envs=nw, seed=42 + rank, forward_mode=forward_mode), dev)
-    return ManagerBasedRlEnv(VelocityEnvCfg(robot=robot, num_envs=nw, seed=42 + rank, forward_mode=forward_mode), dev)
+    return ManagerBasedRlEnv(VelocityEnvCfg(robot=robot, terrain="rough" if args.task == "rough" else "flat", num_envs=nw,
+                                            seed=42 + rank, forward_mode=forward_mode), dev)
 
   env = make_env(args.forward_mode)
   m, cfg = env.sim.mj_model, env.vcfg
@@ -481,7 +490,7 @@ def run_b200(args):
       line["roofline"] = roof
     if alt is not None:
       line["config"]["alt_masked_forward"] = alt
-    if world == 1 and not args.no_cpu_baseline and args.task == "velocity":
+    if world == 1 and not args.no_cpu_baseline and args.task in ("velocity", "rough"):
       cores = os.cpu_count() or 1
       v, secs, desc = cpu_compiled_env_steps_per_s(args.model, cores, target_s=12.0)
       line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": desc}

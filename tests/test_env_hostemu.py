@@ -133,3 +133,52 @@ def test_kernels_match_oracle_with_resets(robot, inject):
     np.testing.assert_allclose(env.log, s.log, rtol=1e-4, atol=1e-5)
     assert int(env.step_counter[0]) == s.step_counter == t + 1
   assert nreset >= B and npush > 0
+
+
+@pytest.mark.parametrize("mode", [1, 3])
+def test_terrain_curriculum_matches_oracle(mode):
+  """Rough-terrain reset path: terrain_levels_vel + update_env_origins (mode bit 0) and the play-mode randomize_terrain
+  event (bit 1) inside the reset kernel == the env oracle, level by level, including the random restart past the top row."""
+  m = mjlab_b200.load_model("g1_flat")
+  cfg = envcfg.velocity_cfg(m, "g1")
+  cfg.seed = 0xBEEF
+  cfg.max_episode_length = 4
+  rng = np.random.default_rng(5)
+  rows, cols = 4, 3
+  cfg.terrain_mode, cfg.terrain_half_size = mode, 4.0
+  cfg.terrain_origins = rng.uniform(-6.0, 6.0, (rows, cols, 3))      # roots sit near (0, 0): distances 0 .. 8.5 m
+  cfg.terrain_origins[..., 2] = rng.uniform(-0.5, 0.5, (rows, cols))
+  g = load_golden("g1")
+  T, B = g["actions"].shape[:2]
+  sim = HostSim(m, B, nconmax=35, njmax=300)
+  env = HostEnv(sim, cfg)
+  s = OE.make_state(cfg, B)
+  lv, ty = rng.integers(0, rows, B).astype(np.int32), rng.integers(0, cols, B).astype(np.int32)
+  for st in (env, s):
+    init_state_from_golden(st, g)
+    st.terrain_level[:], st.terrain_type[:] = lv, ty
+    st.env_origins[:] = cfg.terrain_origins[lv, ty].astype(np.float32)
+    st.episode_length[:] = np.arange(B) % 4
+  moved = wrapped = 0
+  for t in range(T):
+    d = snapshot(g, t, m)
+    u = OE.draws(cfg.seed, B, t)
+    env.action_in[:] = g["actions"][t]
+    env.stage(0)
+    OE.apply_action(cfg, s, d, g["actions"][t])
+    upload(sim, d)
+    before = s.terrain_level.copy()
+    env.stage(2)
+    OE.post(cfg, m, s, d, u=u)
+    compare_state(env, s, ["terrain_level", "terrain_type", "env_origins", "reset_buf", "log_env"])
+    for f in ("qpos", "qvel"):
+      np.testing.assert_allclose(getattr(sim, f).reshape(getattr(d, f).shape), getattr(d, f), err_msg=f, **TOL)
+    moved += int((before != s.terrain_level).sum())
+    wrapped += int(((before == rows - 1) & s.reset_buf & (s.terrain_level != rows - 1)).sum())
+    env.stage(3)
+    OE.obs_stage(cfg, m, s, d, u=u)
+    np.testing.assert_allclose(env.log, s.log, rtol=1e-4, atol=1e-5)
+    assert np.isclose(env.log[A.K["B2E_LOG_TERRAIN_LEVEL"]], s.terrain_level.sum())
+  assert moved > B // 2 and (mode == 3 or wrapped > 0)
+  # reset poses sit on the (possibly updated) origins
+  assert np.all((s.terrain_level >= 0) & (s.terrain_level < rows)) and np.all((s.terrain_type >= 0) & (s.terrain_type < cols))
