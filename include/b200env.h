@@ -193,6 +193,10 @@ int b2_env_action(const b2_model* m, b2_data* d, const b2_env* e, void* stream);
 /* scene.update(dt) after each physics step: contact-sensor air-time state machine at the physics rate. */
 int b2_env_airtime(const b2_model* m, b2_data* d, const b2_env* e, void* stream);
 
+/* decimation x [sim.step(); scene.update(dt)] (manager_based_rl_env.py:276-283): nsub physics steps, each followed by the
+ * air-time update, chunked over side streams like b2_substeps. */
+int b2_env_substeps(const b2_model* m, b2_data* d, const b2_env* e, int nsub, void* stream);
+
 /* episode counters, terminations, rewards, then the reset of every done env (sim reset, reset events, manager
  * resets).  Writes reset_buf (the mask the following conditional forward consumes) and any_reset. */
 int b2_env_post(const b2_model* m, b2_data* d, const b2_env* e, void* stream);

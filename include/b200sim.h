@@ -204,6 +204,8 @@ enum b2_di {
   B2_DI_NEFC_DROPPED,      /* 1: rows dropped because njmax was reached */
   B2_DI_SOLVE_ORDER,       /* 1: world processed by solver slot w (worlds sorted by contact count, heaviest first, so the
                               long-running worlds start at once and do not stretch the kernel's tail); internal */
+  B2_DI_SOLVE_NEXT,        /* 1: element [w0] is the work counter of the solver launch over worlds [w0, w1): its warps pull
+                              solver slots from it until the list is empty (set by the ordering kernel); internal */
   B2_DI_COUNT
 };
 
@@ -250,6 +252,11 @@ int b2_check(const b2_model* m, const b2_data* d);
  * stream is a cudaStream_t passed as void*.  Return 0 on successful enqueue. */
 int b2_step(const b2_model* m, b2_data* d, void* stream);
 int b2_forward(const b2_model* m, b2_data* d, void* stream);
+
+/* nsub consecutive b2_step calls (the decimation loop of an env step) in one call.  With B200SIM_CHUNKS=N (default 1) the
+ * batch is cut into N chunks whose kernel chains run on library-owned side streams forked from / joined to `stream` (graph
+ * edges under stream capture); results are identical for any N. */
+int b2_substeps(const b2_model* m, b2_data* d, int nsub, void* stream);
 
 /* One stage of b2_step on its own: 0 = k_smooth (position / velocity stage), 1 = k_solve (constraint rows + Newton
  * solver), 2 = k_post (sensors, and integration when do_integrate != 0).  b2_step == stages 0, 1, 2 with

@@ -40,46 +40,90 @@ static int fail(const char* fmt, ...) {
   return 1;
 }
 
-__global__ void __launch_bounds__(B2_SMOOTH_WPB * 32) k_smooth(const KModel m, const KData d, const SmoothSmem L, int ncand_max, const unsigned char* mask, const int* gate) {
+__global__ void __launch_bounds__(B2_SMOOTH_WPB * 32) k_smooth(const KModel m, const KData d, const SmoothSmem L, int ncand_max, const unsigned char* mask, const int* gate, int w0, int w1) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   real* smem = reinterpret_cast<real*>(smem_raw);
   int warp = threadIdx.x >> 5;
-  int w = blockIdx.x * B2_SMOOTH_WPB + warp;
-  if (w >= d.nworld) return;
+  int w = w0 + blockIdx.x * B2_SMOOTH_WPB + warp;   // this launch covers the worlds [w0, w1)
+  if (w >= w1) return;
   if (gate && *gate == 0) return;
   if (mask && !mask[w]) return;
   smooth_world(m, d, L, ncand_max, w, smem + (size_t)warp * L.total);
 }
 
-__global__ void __launch_bounds__(B2_WPB * 32, B2_SOLVE_MINB) k_solve(const KModel m, const KData d, const SolveSmem L, const unsigned char* mask, const int* gate) {
+#ifdef B2_TIMING
+// diagnostics build only (tools/solve_timeline.py): per-world start / end of the solver in globaltimer ns + the SM id
+__device__ unsigned long long g_tim[3 * 16384];
+extern "C" int b2_debug_phases(unsigned long long* out, int n) { return (int)cudaMemcpyFromSymbol(out, g_phase, sizeof(unsigned long long) * 8 * n); }
+__device__ __forceinline__ unsigned long long b2_gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned b2_smid() { unsigned s; asm volatile("mov.u32 %0, %%smid;" : "=r"(s)); return s; }
+extern "C" int b2_debug_timing(unsigned long long* out, int n) { return (int)cudaMemcpyFromSymbol(out, g_tim, sizeof(unsigned long long) * 3 * n); }
+#endif
+
+// Number of solver CTAs for n worlds: all resident at once (B2_SOLVE_MINB per SM), each warp then pulls further worlds.
+#define B2_SOLVE_MAX_CTAS (148 * B2_SOLVE_MINB)
+static __host__ __device__ inline int solve_grid(int n) {
+  int g = (n + B2_WPB - 1) / B2_WPB;
+  return g < B2_SOLVE_MAX_CTAS ? g : B2_SOLVE_MAX_CTAS;
+}
+
+// Persistent warps: warp (CTA c, index i) starts on solver slot B2_WPB*c + i, then pulls the next unclaimed slot from the
+// launch's work counter until the list is empty, so a warp-slot never idles while worlds are waiting (with one world per
+// warp and two per CTA, the slot of a light world stayed blocked until its heavy CTA-mate was done).
+__global__ void __launch_bounds__(B2_WPB * 32, B2_SOLVE_MINB) k_solve(const KModel m, const KData d, const SolveSmem L, const unsigned char* mask, const int* gate, int w0, int w1) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   real* smem = reinterpret_cast<real*>(smem_raw);
-  // [fixed part of world 0 | ... | fixed part of world B2_WPB-1 | row arena | arena control words]
+  // [fixed part of world 0 | ... | fixed part of world B2_WPB-1 | row arena | arena control word]
   real* arena = smem + (size_t)B2_WPB * L.fixed_total;
   int* actl = reinterpret_cast<int*>(arena + L.arena_cap);
   if (threadIdx.x == 0) { actl[0] = 0; actl[1] = 0; }
   __syncthreads();
-  int warp = threadIdx.x >> 5;
+  if (gate && *gate == 0) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = w1 - w0;
+  int* next = d.di[B2_DI_SOLVE_NEXT] + w0;
   int slot = blockIdx.x * B2_WPB + warp;
-  int w = slot < d.nworld ? d.di[B2_DI_SOLVE_ORDER][slot] : d.nworld;
-  bool run = w < d.nworld && !(gate && *gate == 0) && !(mask && !mask[w]);
-  if (run) solve_world(m, d, L, w, smem + (size_t)warp * L.fixed_total, arena, actl);
-  __syncwarp();
-  if ((threadIdx.x & 31) == 0) { __threadfence_block(); atomicAdd(&actl[1], 1); }  // releases a world waiting for arena space
+  while (slot < n) {
+    int w = d.di[B2_DI_SOLVE_ORDER][w0 + slot];
+    if (!(mask && !mask[w])) {
+#ifdef B2_TIMING
+      unsigned long long t0 = b2_gtime();
+#endif
+      solve_world(m, d, L, w, smem + (size_t)warp * L.fixed_total, arena, actl);
+      __syncwarp();
+#ifdef B2_TIMING
+      if (lane == 0 && w < 16384) { g_tim[3 * w] = t0; g_tim[3 * w + 1] = b2_gtime(); g_tim[3 * w + 2] = b2_smid(); }
+#endif
+      if (lane == 0) {  // release this warp's arena block
+        __threadfence_block();
+        atomicAnd(reinterpret_cast<unsigned*>(actl), (warp & 1) ? 0x0000ffffu : 0xffff0000u);
+      }
+    }
+    if (lane == 0) slot = atomicAdd(next, 1);
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+  }
 }
 
 // Counting sort of the worlds by contact count, heaviest first (one CTA).  Which solver slot a world lands in has no
 // effect on its results; the atomics only make the order inside a bucket arbitrary.
 #define B2_ORDER_BINS 64
-__global__ void __launch_bounds__(1024) k_order(const KData d) {
+// Sort key = contact count.  (Weighting it with the Newton iteration count of the world's previous solve was tried: the
+// iteration count is too noisy from step to step - a 92-row world predicted "light" started late and became the tail.)
+static __device__ __forceinline__ int order_key(int ncon, int niter_prev) {
+  (void)niter_prev;
+  return ncon < B2_ORDER_BINS ? ncon : B2_ORDER_BINS - 1;
+}
+__global__ void __launch_bounds__(1024) k_order(const KData d, int w0, int w1) {
   __shared__ int hist[B2_ORDER_BINS], base[B2_ORDER_BINS];
   const int* ncon = d.di[B2_DI_NCON];
+  const int* niter = d.di[B2_DI_SOLVER_NITER];   // of the world's previous solve: the best cheap predictor of this one
   int* order = d.di[B2_DI_SOLVE_ORDER];
   if (threadIdx.x < B2_ORDER_BINS) hist[threadIdx.x] = 0;
+  if (threadIdx.x == 0) d.di[B2_DI_SOLVE_NEXT][w0] = solve_grid(w1 - w0) * B2_WPB;   // first slot no warp starts on
   __syncthreads();
-  for (int w = threadIdx.x; w < d.nworld; w += blockDim.x) {
-    int k = ncon[w];
-    atomicAdd(&hist[k < B2_ORDER_BINS ? k : B2_ORDER_BINS - 1], 1);
+  for (int w = w0 + threadIdx.x; w < w1; w += blockDim.x) {
+    int k = order_key(ncon[w], niter[w]);
+    atomicAdd(&hist[k], 1);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -87,20 +131,29 @@ __global__ void __launch_bounds__(1024) k_order(const KData d) {
     for (int k = B2_ORDER_BINS - 1; k >= 0; --k) { base[k] = acc; acc += hist[k]; }
   }
   __syncthreads();
-  for (int w = threadIdx.x; w < d.nworld; w += blockDim.x) {
-    int k = ncon[w];
-    k = k < B2_ORDER_BINS ? k : B2_ORDER_BINS - 1;
-    order[atomicAdd(&base[k], 1)] = w;
+  for (int w = w0 + threadIdx.x; w < w1; w += blockDim.x) {
+    int k = order_key(ncon[w], niter[w]);
+    // Rank p in the heaviest-first order -> solver slot.  G CTAs of two warps are resident; warp (c, i) starts on slot
+    // 2c + i and then pulls slots 2G, 2G+1, ... in order.  The two worlds of a CTA share one row arena and a world that
+    // does not fit next to its CTA-mate waits for the mate to finish (per-world timers: 55 % of the latency of the
+    // heaviest worlds was that wait while they were paired with each other), so the first wave pairs the c-th heaviest
+    // world with the c-th lightest; the warps of the light worlds are free within microseconds and take the remaining
+    // worlds longest-first, which keeps the tail of the launch short.
+    int p = atomicAdd(&base[k], 1), n = w1 - w0, G = solve_grid(n);
+    // (the lightest world of all sits next to rank G-1, not next to rank 0: the first warps to come free then have a
+    // small CTA-mate, and the medium-heavy world they pull fits beside it)
+    int slot = p < G ? 2 * p : (p >= n - G ? 2 * (p - (n - G)) + 1 : 2 * G + (p - G));
+    order[w0 + slot] = w;   // slots [w0, w1) hold a permutation of the worlds [w0, w1)
   }
 }
 
 #define B2_POST_WPB 4
-__global__ void __launch_bounds__(B2_POST_WPB * 32) k_post(const KModel m, const KData d, const PostSmem L, int do_integrate, const unsigned char* mask, const int* gate) {
+__global__ void __launch_bounds__(B2_POST_WPB * 32) k_post(const KModel m, const KData d, const PostSmem L, int do_integrate, const unsigned char* mask, const int* gate, int w0, int w1) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   real* smem = reinterpret_cast<real*>(smem_raw);
   int warp = threadIdx.x >> 5;
-  int w = blockIdx.x * B2_POST_WPB + warp;
-  if (w >= d.nworld) return;
+  int w = w0 + blockIdx.x * B2_POST_WPB + warp;
+  if (w >= w1) return;
   if (gate && *gate == 0) return;
   if (mask && !mask[w]) return;
   post_world(m, d, L, w, smem + (size_t)warp * L.total, do_integrate);
@@ -213,18 +266,103 @@ int b2_check(const b2_model* m, const b2_data* d) {
   return 0;
 }
 
+// One physics step (do_integrate) or forward pass for the worlds [w0, w1) on stream st: four launches.
+static void launch_range(const Plan& p, const KModel& km, const KData& kd, cudaStream_t st, int do_integrate, const unsigned char* mask,
+                         const int* gate, int w0, int w1) {
+  int n = w1 - w0;
+  k_smooth<<<(n + B2_SMOOTH_WPB - 1) / B2_SMOOTH_WPB, B2_SMOOTH_WPB * 32, p.smem_smooth, st>>>(km, kd, p.ls, B2_NCAND_MAX, mask, gate, w0, w1);
+  k_order<<<1, 1024, 0, st>>>(kd, w0, w1);
+  k_solve<<<solve_grid(n), B2_WPB * 32, p.smem_solve, st>>>(km, kd, p.lv, mask, gate, w0, w1);
+  k_post<<<(n + B2_POST_WPB - 1) / B2_POST_WPB, B2_POST_WPB * 32, p.smem_post, st>>>(km, kd, p.lp, do_integrate, mask, gate, w0, w1);
+  g_launches += 4;
+}
+
 static int run(const b2_model* m, b2_data* d, void* stream, int do_integrate, const unsigned char* mask = nullptr, const int* gate = nullptr) {
   Plan p;
   make_plan(m, d, &p);
-  cudaStream_t st = (cudaStream_t)stream;
+  launch_range(p, *reinterpret_cast<const KModel*>(m), *reinterpret_cast<const KData*>(d), (cudaStream_t)stream, do_integrate, mask, gate, 0, d->nworld);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("launch failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+// ---- chunked, multi-stream execution (opt-in: B200SIM_CHUNKS=N) --------------------------------------------------------
+// Worlds never interact, so the batch can be cut into chunks whose kernel CHAINS run on separate streams, forked from and
+// joined to the caller's stream (graph edges under stream capture: the env step stays ONE graph).  The idea was to let one
+// chunk's solver tail overlap the other chunks' kinematics / sensors / next solver.  Measured (G1, 4096 envs): no gain at
+// 2 / 4 / 8 chunks - while a solver launch is resident it holds every register of the SMs it runs on, so the other chunks'
+// kernels only start once it drains, and the chain of each chunk is still 4 x the latency of its heaviest world.  What did
+// shorten the tail is inside k_solve (persistent warps + heavy/light pairing).  Kept as an experiment knob, default 1.
+#define B2_MAX_CHUNKS 16
+struct ChunkStreams {
+  int dev = -1, n = 0;
+  cudaStream_t side[B2_MAX_CHUNKS];
+  cudaEvent_t fork, join[B2_MAX_CHUNKS];
+};
+static ChunkStreams g_cs[16];
+
+static int chunk_count(int nworld) {
+  // read on every call (a getenv per enqueue is nothing next to a launch): tests flip these in-process
+  const char* e = getenv("B200SIM_CHUNKS");
+  const char* emin = getenv("B200SIM_CHUNK_MIN");
+  int c = e && atoi(e) > 0 ? atoi(e) : 1;   // default: one chunk (see the note above run_chunked)
+  int min_worlds = emin && atoi(emin) > 0 ? atoi(emin) : 512;   // below this many worlds per chunk the launches only add overhead
+  if (c > B2_MAX_CHUNKS) c = B2_MAX_CHUNKS;
+  while (c > 1 && nworld / c < min_worlds) c >>= 1;
+  return c < 1 ? 1 : c;
+}
+
+static ChunkStreams* chunk_streams(int want) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  ChunkStreams& cs = g_cs[dev];
+  if (cs.dev != dev) {
+    if (cudaEventCreateWithFlags(&cs.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    cs.dev = dev;
+    cs.n = 0;
+  }
+  while (cs.n < want) {
+    if (cudaStreamCreateWithFlags(&cs.side[cs.n], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&cs.join[cs.n], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    cs.n += 1;
+  }
+  return &cs;
+}
+
+typedef void (*chunk_hook)(const void* ctx, cudaStream_t st, int w0, int w1);
+
+// nsub x [physics step or forward; hook] for every world, chunk chains on side streams forked from / joined to `stream`.
+static int run_chunked(const b2_model* m, b2_data* d, void* stream, int nsub, int do_integrate, const unsigned char* mask, const int* gate,
+                       chunk_hook hook, const void* hook_ctx) {
+  Plan p;
+  make_plan(m, d, &p);
   const KModel& km = *reinterpret_cast<const KModel*>(m);
   const KData& kd = *reinterpret_cast<const KData*>(d);
-  int grid = (d->nworld + B2_WPB - 1) / B2_WPB;
-  k_smooth<<<(d->nworld + B2_SMOOTH_WPB - 1) / B2_SMOOTH_WPB, B2_SMOOTH_WPB * 32, p.smem_smooth, st>>>(km, kd, p.ls, B2_NCAND_MAX, mask, gate);
-  k_order<<<1, 1024, 0, st>>>(kd);
-  k_solve<<<grid, B2_WPB * 32, p.smem_solve, st>>>(km, kd, p.lv, mask, gate);
-  k_post<<<(d->nworld + B2_POST_WPB - 1) / B2_POST_WPB, B2_POST_WPB * 32, p.smem_post, st>>>(km, kd, p.lp, do_integrate, mask, gate);
-  g_launches += 4;
+  cudaStream_t main_st = (cudaStream_t)stream;
+  int nc = chunk_count(d->nworld);
+  ChunkStreams* cs = nc > 1 ? chunk_streams(nc) : nullptr;
+  if (!cs) {
+    for (int s = 0; s < nsub; ++s) {
+      launch_range(p, km, kd, main_st, do_integrate, mask, gate, 0, d->nworld);
+      if (hook) hook(hook_ctx, main_st, 0, d->nworld);
+    }
+  } else {
+    // chunk boundaries on multiples of 4 worlds (k_post packs 4 worlds per CTA, the env kernels too)
+    int per = ((d->nworld + nc - 1) / nc + 3) & ~3;
+    if (cudaEventRecord(cs->fork, main_st) != cudaSuccess) return fail("event record: %s", cudaGetErrorString(cudaGetLastError()));
+    for (int c = 0; c < nc; ++c) {
+      int w0 = c * per, w1 = w0 + per < d->nworld ? w0 + per : d->nworld;
+      if (w0 >= w1) continue;
+      cudaStream_t st = cs->side[c];
+      if (cudaStreamWaitEvent(st, cs->fork, 0) != cudaSuccess) return fail("stream wait: %s", cudaGetErrorString(cudaGetLastError()));
+      for (int s = 0; s < nsub; ++s) {
+        launch_range(p, km, kd, st, do_integrate, mask, gate, w0, w1);
+        if (hook) hook(hook_ctx, st, w0, w1);
+      }
+      if (cudaEventRecord(cs->join[c], st) != cudaSuccess) return fail("event record: %s", cudaGetErrorString(cudaGetLastError()));
+      if (cudaStreamWaitEvent(main_st, cs->join[c], 0) != cudaSuccess) return fail("stream wait: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail("launch failed: %s", cudaGetErrorString(e));
   return 0;
@@ -238,12 +376,12 @@ int b2_stage(const b2_model* m, b2_data* d, int stage, int do_integrate, void* s
   const KData& kd = *reinterpret_cast<const KData*>(d);
   int grid = (d->nworld + B2_WPB - 1) / B2_WPB;
   if (stage == 0) {
-    k_smooth<<<(d->nworld + B2_SMOOTH_WPB - 1) / B2_SMOOTH_WPB, B2_SMOOTH_WPB * 32, p.smem_smooth, st>>>(km, kd, p.ls, B2_NCAND_MAX, nullptr, nullptr);
-    k_order<<<1, 1024, 0, st>>>(kd);
+    k_smooth<<<(d->nworld + B2_SMOOTH_WPB - 1) / B2_SMOOTH_WPB, B2_SMOOTH_WPB * 32, p.smem_smooth, st>>>(km, kd, p.ls, B2_NCAND_MAX, nullptr, nullptr, 0, d->nworld);
+    k_order<<<1, 1024, 0, st>>>(kd, 0, d->nworld);
     g_launches += 1;
   }
-  else if (stage == 1) k_solve<<<grid, B2_WPB * 32, p.smem_solve, st>>>(km, kd, p.lv, nullptr, nullptr);
-  else if (stage == 2) k_post<<<(d->nworld + B2_POST_WPB - 1) / B2_POST_WPB, B2_POST_WPB * 32, p.smem_post, st>>>(km, kd, p.lp, do_integrate, nullptr, nullptr);
+  else if (stage == 1) k_solve<<<solve_grid(d->nworld), B2_WPB * 32, p.smem_solve, st>>>(km, kd, p.lv, nullptr, nullptr, 0, d->nworld);
+  else if (stage == 2) k_post<<<(d->nworld + B2_POST_WPB - 1) / B2_POST_WPB, B2_POST_WPB * 32, p.smem_post, st>>>(km, kd, p.lp, do_integrate, nullptr, nullptr, 0, d->nworld);
   else return fail("unknown stage %d", stage);
   g_launches += 1;
   cudaError_t e = cudaGetLastError();
@@ -289,7 +427,12 @@ int b2_repeat_rows(float* dst, const float* src, int row_len, int nworld, void* 
 }
 
 int b2_forward_masked(const b2_model* m, b2_data* d, const unsigned char* mask, const int* gate, void* stream) {
-  return run(m, d, stream, 0, mask, gate);
+  return run_chunked(m, d, stream, 1, 0, mask, gate, nullptr, nullptr);
+}
+
+int b2_substeps(const b2_model* m, b2_data* d, int nsub, void* stream) {
+  if (nsub < 0) return fail("nsub must be >= 0");
+  return run_chunked(m, d, stream, nsub, 1, nullptr, nullptr, nullptr, nullptr);
 }
 
 }  // extern "C"

@@ -6,9 +6,9 @@ __global__ void __launch_bounds__(B2E_WPB * 32) k_env_action(const __grid_consta
   int w = blockIdx.x * B2E_WPB + (threadIdx.x >> 5);
   if (w < d.nworld) env_action_world(m, d, e, w);
 }
-__global__ void __launch_bounds__(B2E_WPB * 32) k_env_airtime(const __grid_constant__ KModel m, const __grid_constant__ KData d, const __grid_constant__ KEnv e) {
-  int w = blockIdx.x * B2E_WPB + (threadIdx.x >> 5);
-  if (w < d.nworld) env_airtime_world(m, d, e, w);
+__global__ void __launch_bounds__(B2E_WPB * 32) k_env_airtime(const __grid_constant__ KModel m, const __grid_constant__ KData d, const __grid_constant__ KEnv e, int w0, int w1) {
+  int w = w0 + blockIdx.x * B2E_WPB + (threadIdx.x >> 5);
+  if (w < w1) env_airtime_world(m, d, e, w);
 }
 __global__ void __launch_bounds__(B2E_WPB * 32) k_env_post(const __grid_constant__ KModel m, const __grid_constant__ KData d, const __grid_constant__ KEnv e) {
   int w = blockIdx.x * B2E_WPB + (threadIdx.x >> 5);
@@ -168,7 +168,29 @@ int b2_env_check(const b2_model* m, const b2_data* d, const b2_env* e) {
   return 0;
 
 int b2_env_action(const b2_model* m, b2_data* d, const b2_env* e, void* stream) { B2E_LAUNCH(k_env_action) }
-int b2_env_airtime(const b2_model* m, b2_data* d, const b2_env* e, void* stream) { B2E_LAUNCH(k_env_airtime) }
+int b2_env_airtime(const b2_model* m, b2_data* d, const b2_env* e, void* stream) {
+  const KModel& km = *reinterpret_cast<const KModel*>(m);
+  const KData& kd = *reinterpret_cast<const KData*>(d);
+  const KEnv& ke = *reinterpret_cast<const KEnv*>(e);
+  k_env_airtime<<<(d->nworld + B2E_WPB - 1) / B2E_WPB, B2E_WPB * 32, 0, (cudaStream_t)stream>>>(km, kd, ke, 0, d->nworld);
+  g_launches += 1;
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return fail("launch failed: %s", cudaGetErrorString(err));
+  return 0;
+}
+
+struct AirtimeCtx { const KModel* m; const KData* d; const KEnv* e; };
+static void airtime_hook(const void* ctx, cudaStream_t st, int w0, int w1) {
+  const AirtimeCtx& c = *static_cast<const AirtimeCtx*>(ctx);
+  k_env_airtime<<<(w1 - w0 + B2E_WPB - 1) / B2E_WPB, B2E_WPB * 32, 0, st>>>(*c.m, *c.d, *c.e, w0, w1);
+  g_launches += 1;
+}
+
+int b2_env_substeps(const b2_model* m, b2_data* d, const b2_env* e, int nsub, void* stream) {
+  if (nsub < 0) return fail("nsub must be >= 0");
+  AirtimeCtx c{reinterpret_cast<const KModel*>(m), reinterpret_cast<const KData*>(d), reinterpret_cast<const KEnv*>(e)};
+  return run_chunked(m, d, stream, nsub, 1, nullptr, nullptr, airtime_hook, &c);
+}
 
 int b2_env_obs(const b2_model* m, b2_data* d, const b2_env* e, int with_update, void* stream) {
   const KModel& km = *reinterpret_cast<const KModel*>(m);

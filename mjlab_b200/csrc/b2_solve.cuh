@@ -229,7 +229,19 @@ B2_DEV void mat2quat(real* q, const real* R) {
 // ---------------------------------------------------------------------------
 // `sm`: this world's fixed part; `arena` / `actl`: the CTA's row arena and its control words (actl[0] reals handed out,
 // actl[1] worlds of the CTA that are done).
+#if defined(B2_TIMING) && !defined(B2_HOSTEMU)
+__device__ unsigned long long g_phase[8 * 16384];
+#define B2_PH_BEGIN() long long ph_t = clock64(); unsigned long long ph_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define B2_PH(k) { long long ph_n = clock64(); ph_acc[k] += (unsigned long long)(ph_n - ph_t); ph_t = ph_n; }
+#define B2_PH_END() if (B2_LANE == 0 && w < 16384) { for (int k = 0; k < 8; ++k) g_phase[8 * w + k] = ph_acc[k]; }
+#else
+#define B2_PH_BEGIN()
+#define B2_PH(k)
+#define B2_PH_END()
+#endif
+
 B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int w, real* sm, real* arena, int* actl) {  // @region setup_loads
+  B2_PH_BEGIN()
   const int nv = m.nv, nb = m.nbody, nq = m.nq, nu = m.nu, njmax = d.njmax, nconmax = d.nconmax;
   real* H = sm + L.H; real* cdof = sm + L.cdof;
   real* qvel = sm + L.qvel; real* qacc = sm + L.qacc; real* Ma = sm + L.Ma; real* grad = sm + L.grad;
@@ -318,15 +330,28 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
   }
   int aoff = 0;
 #ifndef B2_HOSTEMU
-  if (B2_LANE == 0) {
-    aoff = atomicAdd(&actl[0], need);
-    if (aoff + need > L.arena_cap) {
-      // no room next to the CTA's other world: wait until it is done, then use the arena from its start
-      while (atomicAdd(&actl[1], 0) == 0) __nanosleep(200);
-      aoff = 0;
+  {
+    // The CTA's two warps each hold one world at a time and share the arena: warp 0's block grows from the bottom, warp
+    // 1's hangs from the top.  actl[0] packs both sizes (units of 4 floats, 16 bits each); a world whose block does not fit
+    // next to the other warp's current one waits until that warp releases it (k_solve clears the field after each world).
+    const int me = (threadIdx.x >> 5) & 1;
+    const int need4 = (need + 3) >> 2, cap4 = L.arena_cap >> 2;
+    if (B2_LANE == 0) {
+      unsigned* u = reinterpret_cast<unsigned*>(actl);
+      for (;;) {
+        unsigned old = *reinterpret_cast<volatile unsigned*>(u);
+        int other = (int)(me ? (old & 0xffffu) : (old >> 16));
+        if (need4 + other <= cap4) {
+          unsigned nw = me ? ((old & 0xffffu) | ((unsigned)need4 << 16)) : ((old & 0xffff0000u) | (unsigned)need4);
+          if (atomicCAS(u, old, nw) == old) break;
+        } else {
+          __nanosleep(200);
+        }
+      }
     }
+    __syncwarp();
+    aoff = me ? (cap4 - need4) * 4 : 0;
   }
-  aoff = __shfl_sync(0xffffffffu, aoff, 0);
 #endif
   real* D; real* aref; real* jar; real* jv; int* rowinfo; int* runinfo; unsigned char* rundofs; int* cinfo; real* jpool;
   {
@@ -595,6 +620,7 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
   }
 
   // ---- solve ------------------------------------------------------------------------------------------  // @region solve_init
+  B2_PH(0)
   int niter = 0;
   real* g_qacc = d.df[B2_DF_QACC] + (size_t)w * nv;
   real* g_qfc = d.df[B2_DF_QFRC_CONSTRAINT] + (size_t)w * nv;
@@ -638,6 +664,7 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
     real cost = 0, gauss = 0;
     // rounding floor of the cost difference in this arithmetic: below it "improvement" is noise
     const real eps_real = sizeof(real) == 4 ? (real)1.1920929e-7 : (real)2.220446e-16;
+    B2_PH(1)
     B2_UNROLL1
     for (int it = 0;; ++it) {
       // -- constraint update, part 1: row weights, cost, qfrc_constraint, gradient  // @region newton_update
@@ -719,6 +746,7 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
         cost = newcost;
       }
       if (it >= m.iterations) break;
+      B2_PH(2)
       // -- part 2: H = M + J^T diag(w) J, only when another Newton step will be taken  // @region hessian
       if (same_set) {
         chol_forwardsolve(H, nv, ld, invd, tmp);
@@ -765,8 +793,10 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
         }
         B2_WSYNC();
       }
+      B2_PH(3)
       spd_factor_solve(H, nv, ld, tmp, invd);  // @region factor_call
       }
+      B2_PH(4)
       B2_UNROLL1
       for (int i = B2_LANE; i < nv; i += B2_NLANE) search[i] = -tmp[i];
       B2_WSYNC();
@@ -781,7 +811,9 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
       }
       sn = sqrt(b2_wsum(sn)); q1 = b2_wsum(q1); q2 = b2_wsum(q2);
       rows_dot(jpool, rowinfo, runinfo, rundofs, nefc, search, jv, nullptr);
+      B2_PH(5)
       real alpha = linesearch(gauss, q1, q2, sn, tolerance, ls_tolerance, m.ls_iterations, scale, jar, jv, D, nefc);
+      B2_PH(6)
       if (alpha == 0) break;
       B2_UNROLL1
       for (int i = B2_LANE; i < nv; i += B2_NLANE) { qacc[i] += alpha * search[i]; Ma[i] += alpha * Mv[i]; }
@@ -799,7 +831,8 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
   for (int i = B2_LANE; i < nv; i += B2_NLANE) { g_qacc[i] = qacc[i]; g_qfc[i] = qfc[i]; }
   if (B2_LANE == 0) d.di[B2_DI_SOLVER_NITER][w] = niter;
   B2_WSYNC();
-
+  B2_PH(7)
+  B2_PH_END()
 }
 
 // Shared-memory layout of the post stage (sensors + integration): the integrator's matrix and a few vectors.

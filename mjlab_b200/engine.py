@@ -156,6 +156,7 @@ DATA_INT_FIELDS = [
   ("NCON_DROPPED", "ncon_dropped", lambda m, c, j: ()),
   ("NEFC_DROPPED", "nefc_dropped", lambda m, c, j: ()),
   ("SOLVE_ORDER", "solve_order", lambda m, c, j: ()),
+  ("SOLVE_NEXT", "solve_next", lambda m, c, j: ()),
 ]
 
 def leading_dim(n: int) -> int:
@@ -321,6 +322,8 @@ def load_library() -> C.CDLL:
   for name in ("b2_step", "b2_forward"):
     getattr(lib, name).argtypes = [C.POINTER(B2Model), C.POINTER(B2Data), C.c_void_p]
     getattr(lib, name).restype = C.c_int
+  lib.b2_substeps.argtypes = [C.POINTER(B2Model), C.POINTER(B2Data), C.c_int, C.c_void_p]
+  lib.b2_substeps.restype = C.c_int
   lib.b2_stage.argtypes = [C.POINTER(B2Model), C.POINTER(B2Data), C.c_int, C.c_int, C.c_void_p]
   lib.b2_stage.restype = C.c_int
   lib.b2_reset.argtypes = [C.POINTER(B2Model), C.POINTER(B2Data), C.c_void_p, C.c_void_p]

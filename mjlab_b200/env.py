@@ -322,9 +322,7 @@ class ManagerBasedRlEnv:
     lib, m, d, e, chk = self._lib, C.byref(self.sim._cm), C.byref(self.sim._cd), C.byref(self._ce), E.check_call
     st = self._stream()
     chk(lib, lib.b2_env_action(m, d, e, st))
-    for _ in range(self.cfg.decimation):
-      chk(lib, lib.b2_step(m, d, st))
-      chk(lib, lib.b2_env_airtime(m, d, e, st))
+    chk(lib, lib.b2_env_substeps(m, d, e, self.cfg.decimation, st))   # decimation x (physics step + air-time update)
     chk(lib, lib.b2_env_post(m, d, e, st))
     mask = self._buf["reset_buf"].data_ptr() if self.cfg.forward_mode == "masked" else None
     chk(lib, lib.b2_forward_masked(m, d, mask, self._buf["any_reset"].data_ptr(), st))
@@ -339,15 +337,18 @@ class ManagerBasedRlEnv:
     torch.cuda.synchronize(self._dev)
     side = torch.cuda.Stream(self._dev)
     g = torch.cuda.CUDAGraph()
+    n0 = self._lib.b2_launch_count()
     with torch.cuda.stream(side):
       with torch.cuda.graph(g, stream=side):
         self._enqueue_step()
+    self._launches_per_step = int(self._lib.b2_launch_count() - n0)
     torch.cuda.current_stream(self._dev).wait_stream(side)
     self._graph = g
     self._capture_epoch = getattr(self, "_capture_epoch", 0) + 1   # callers that captured _enqueue_step themselves must re-capture
 
-  #: kernels enqueued per env step: action, decimation x (smooth, order, solve, post, airtime), env_post + gate, forward (4), obs, log
-  launches_per_step = property(lambda self: 1 + 5 * self.cfg.decimation + 2 + 4 + 1 + 1)
+  #: kernels enqueued per env step, counted by the library while the step was captured: action, per chunk decimation x
+  #: (smooth, order, solve, post, airtime), env_post + gate, per chunk forward (4), obs, log
+  launches_per_step = property(lambda self: getattr(self, "_launches_per_step", 1 + 5 * self.cfg.decimation + 2 + 4 + 1 + 1))
 
   # ---- API ------------------------------------------------------------------------------------------
   def seed(self, seed: int = -1) -> int:

@@ -64,6 +64,8 @@ def load_library() -> C.CDLL:
   for name in ("b2_env_action", "b2_env_airtime", "b2_env_post"):
     getattr(lib, name).argtypes = [pm, pd, pe, vp]
   lib.b2_env_obs.argtypes = [pm, pd, pe, C.c_int, vp]
+  lib.b2_env_substeps.argtypes = [pm, pd, pe, C.c_int, vp]
+  lib.b2_env_substeps.restype = C.c_int
   lib.b2_env_reset.argtypes = [pm, pd, pe, vp, vp]
   lib.b2_env_log.argtypes = [pd, pe, vp]
   lib.b2_forward_masked.argtypes = [pm, pd, vp, vp, vp]

@@ -128,7 +128,7 @@ class TrackingRlEnv:
   max_episode_length_s = property(lambda self: self.vcfg.max_episode_length_s)
   max_episode_length = property(lambda self: self.vcfg.max_episode_length)
   unwrapped = property(lambda self: self)
-  launches_per_step = property(lambda self: 1 + 4 * self.cfg.decimation + 2 + 4 + 1 + 1)
+  launches_per_step = property(lambda self: getattr(self, "_launches_per_step", 1 + 4 * self.cfg.decimation + 2 + 4 + 1 + 1))
 
   @property
   def episode_length_buf(self) -> torch.Tensor:
@@ -201,8 +201,7 @@ class TrackingRlEnv:
     lib, m, d, e, chk = self._lib, C.byref(self.sim._cm), C.byref(self.sim._cd), C.byref(self._ce), E.check_call
     st = self._stream()
     chk(lib, lib.b2_trk_action(m, d, e, st))
-    for _ in range(self.cfg.decimation):
-      chk(lib, lib.b2_step(m, d, st))
+    chk(lib, lib.b2_substeps(m, d, self.cfg.decimation, st))
     chk(lib, lib.b2_trk_post(m, d, e, st))
     mask = self._buf["reset_buf"].data_ptr() if self.cfg.forward_mode == "masked" else None
     chk(lib, lib.b2_forward_masked(m, d, mask, self._buf["any_reset"].data_ptr(), st))
@@ -216,9 +215,11 @@ class TrackingRlEnv:
     torch.cuda.synchronize(self._dev)
     side = torch.cuda.Stream(self._dev)
     g = torch.cuda.CUDAGraph()
+    n0 = self._lib.b2_launch_count()
     with torch.cuda.stream(side):
       with torch.cuda.graph(g, stream=side):
         self._enqueue_step()
+    self._launches_per_step = int(self._lib.b2_launch_count() - n0)
     torch.cuda.current_stream(self._dev).wait_stream(side)
     self._graph = g
     self._capture_epoch = getattr(self, "_capture_epoch", 0) + 1   # callers that captured _enqueue_step themselves must re-capture

@@ -340,3 +340,34 @@ def test_play_zero_agent():
     else:
       assert bool(fell.all())                                    # open-loop G1 tips over ...
       assert int(env.episode_length_buf.max()) < 150             # ... every episode ends and restarts
+
+
+def test_chunked_streams_do_not_change_results():
+  """b2_env_substeps cuts the batch into chunks on side streams (graph edges): the env must produce bit-identical
+  trajectories with 1, 2 and 4 chunks, resets and the gated forward pass included."""
+  import os
+  from mjlab_b200.env import ManagerBasedRlEnv, VelocityEnvCfg
+  outs = []
+  old = {k: os.environ.get(k) for k in ("B200SIM_CHUNKS", "B200SIM_CHUNK_MIN")}
+  try:
+    for chunks in (1, 2, 4):
+      os.environ["B200SIM_CHUNKS"], os.environ["B200SIM_CHUNK_MIN"] = str(chunks), "8"
+      env = ManagerBasedRlEnv(VelocityEnvCfg(robot="g1", num_envs=100, seed=5), DEV)   # 100: a ragged last chunk
+      env.reset()
+      gen = torch.Generator(device=DEV).manual_seed(3)
+      env.episode_length_buf = torch.randint(0, 1000, (100,), device=DEV, generator=gen)
+      n0 = env._lib.b2_launch_count()
+      for _ in range(25):
+        obs, rew, term, trunc, _ = env.step(torch.rand(100, env.vcfg.nj, device=DEV, generator=gen) * 2 - 1)
+      assert env.launches_per_step == 1 + chunks * 5 * 4 + 2 + chunks * 4 + 1 + 1
+      outs.append((obs["critic"].clone(), rew.clone(), env.sim.data.qpos.clone(), env.sim.data.qvel.clone(), env.sim.data.ncon.clone(),
+                   env.episode_length_buf.clone()))
+  finally:
+    for k, v in old.items():
+      if v is None:
+        os.environ.pop(k, None)
+      else:
+        os.environ[k] = v
+  for o in outs[1:]:
+    for a, b in zip(outs[0], o):
+      assert torch.equal(a, b)
