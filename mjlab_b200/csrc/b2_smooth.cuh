@@ -24,18 +24,30 @@ static inline SmoothSmem smooth_smem_layout(int nq, int nv, int nu, int nbody, i
   SmoothSmem s;
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
+  // Buffers of the position stage that are dead once the kinematic Jacobian (cdof) exists are reused by the velocity /
+  // force stage: shared memory per world sets how many worlds an SM holds (latency-bound kernel, occupancy pays).
+  //   [xquat | xanchor | xaxis]  (last read: cdof)            -> [cdofdot | f | aforce]
+  //   xmat                       (last read: cinert)          -> cvel
+  //   cand                       (collision candidates)       -> cfrc (RNE, after collision)
   s.qpos = take(nq); s.qvel = take(nv);
-  s.xpos = take(3 * nbody); s.xquat = take(4 * nbody); s.xmat = take(9 * nbody); s.xipos = take(3 * nbody);
-  s.xanchor = take(3 * njnt); s.xaxis = take(3 * njnt);
+  s.xpos = take(3 * nbody); s.xipos = take(3 * nbody);
+  {
+    int a0 = o;
+    s.xquat = take(4 * nbody); s.xanchor = take(3 * njnt); s.xaxis = take(3 * njnt);
+    int a1 = o;
+    o = a0;
+    s.cdofdot = take(6 * nv); s.f = take(nv); s.aforce = take(nu);
+    if (o < a1) o = a1;
+  }
+  s.xmat = take(9 * nbody);
+  s.cvel = s.xmat;           // 6*nbody <= 9*nbody
   s.scom = take(3 * nbody); s.smass = take(nbody);
   s.cinert = take(10 * nbody); s.crb = take(10 * nbody);
-  s.cdof = take(6 * nv); s.cdofdot = take(6 * nv);
-  s.cvel = take(6 * nbody);
+  s.cdof = take(6 * nv);
   s.cacc = s.crb;            // crb is dead once qM is assembled; cacc (6*nbody) fits in 10*nbody
-  s.cfrc = take(6 * nbody);
-  s.M = take(nv * b2_ld(nv)); s.f = take(nv);
-  s.aforce = take(nu);
-  s.cand = take(ncand);      // candidate pair ids (ints stored in real-sized slots)
+  s.M = take(nv * b2_ld(nv));
+  s.cand = take(ncand > 6 * nbody ? ncand : 6 * nbody);   // candidate pair ids (ints stored in real-sized slots)
+  s.cfrc = s.cand;
   s.invd = take(64);  // 1 / diag(L)
   s.total = o;
   return s;
