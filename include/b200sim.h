@@ -124,6 +124,8 @@ enum b2_mi {
   B2_MI_SENSOR_DIM,        /* nsensor */
   B2_MI_SENSOR_ADR,        /* nsensor */
   B2_MI_DOF_ACTID,         /* nv: the actuator driving this dof, -1 none, -2 several (kernels then scan) */
+  B2_MI_BODY_ANCMASK,      /* nbody*2: 64-bit mask (lo, hi) of the body itself and its ancestors; valid when nbody <= 64
+                              (subtree tests of the contact sensors become one load instead of a walk up the tree) */
   B2_MI_DYN_GEOM,          /* ndyn: geoms that move (forward kinematics runs for these only) */
   B2_MI_FIELD_GEOM,        /* nfield: geom id of each field geom (static terrain boxes, see b2_model.nfield) */
   B2_MI_FIELD_CELL0,       /* nfield*2: lowest grid cell (ix, iy) the geom's AABB touches */

@@ -148,7 +148,12 @@ __global__ void __launch_bounds__(1024) k_order(const KData d, int w0, int w1) {
 }
 
 #define B2_POST_WPB 4
-__global__ void __launch_bounds__(B2_POST_WPB * 32) k_post(const KModel m, const KData d, const PostSmem L, int do_integrate, const unsigned char* mask, const int* gate, int w0, int w1) {
+// resident CTAs per SM the compiler must allow for (register cap 65536 / (B2_POST_MINB * 128)): the 1024 CTAs of a
+// 4096-world launch have to fit in ONE round (148 * 7 = 1036); left alone the compiler used 96 registers -> 5 per SM, two rounds
+#ifndef B2_POST_MINB
+#define B2_POST_MINB 7
+#endif
+__global__ void __launch_bounds__(B2_POST_WPB * 32, B2_POST_MINB) k_post(const KModel m, const KData d, const PostSmem L, int do_integrate, const unsigned char* mask, const int* gate, int w0, int w1) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   real* smem = reinterpret_cast<real*>(smem_raw);
   int warp = threadIdx.x >> 5;

@@ -345,6 +345,14 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
   for (int i = B2_LANE; i < nq; i += B2_NLANE) qpos[i] = g_qpos[i];
   B2_UNROLL1
   for (int i = B2_LANE; i < nv; i += B2_NLANE) qvel[i] = g_qvel[i];
+  // xfrc_applied is almost always all zero; its 6*nbody loads join the state loads here so that their HBM latency is
+  // paid once, instead of stalling the force stage later (it was 2.6 % of the kernel's stall samples there)
+  int anyx_lane = 0;
+  {
+    const real* xf = d.df[B2_DF_XFRC_APPLIED] + (size_t)w * nb * 6;
+    B2_UNROLL1
+    for (int i = B2_LANE; i < 6 * nb; i += B2_NLANE) anyx_lane |= (xf[i] != 0);
+  }
   B2_WSYNC();
 
   // ---- kinematics, level by level ------------------------------------------  // @region kinematics
@@ -956,11 +964,8 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
     const real* qfrc_applied = d.df[B2_DF_QFRC_APPLIED] + (size_t)w * nv;
     const real* xfrc = d.df[B2_DF_XFRC_APPLIED] + (size_t)w * nb * 6;
     const int* dofmask = MI(B2_MI_BODY_DOFMASK);
-    // any external wrench at all? (common case: none)
-    int anyx = 0;
-    B2_UNROLL1
-    for (int i = B2_LANE; i < 6 * nb; i += B2_NLANE) anyx |= (xfrc[i] != 0);
-    anyx = b2_wor_i(anyx);
+    // any external wrench at all? (common case: none; the loads were issued at the top of the kernel)
+    const int anyx = b2_wor_i(anyx_lane);
     real* g_bias = d.df[B2_DF_QFRC_BIAS] + (size_t)w * nv;
     real* g_pas = d.df[B2_DF_QFRC_PASSIVE] + (size_t)w * nv;
     real* g_act = d.df[B2_DF_QFRC_ACTUATOR] + (size_t)w * nv;

@@ -242,19 +242,20 @@ B2_DEV void contact_force(real* out, int adr, int dim, const real* fri, const re
   }
 }
 
-B2_DEV bool in_subtree(const int* body_parent, int body, int root) {
-  B2_UNROLL1
+// is `root` the body itself or one of its ancestors?  ancmask != NULL (nbody <= 64): one table lookup; else walk up.
+B2_DEV bool in_subtree(const int* body_parent, const int* ancmask, int body, int root) {
+  if (ancmask) return ((unsigned)ancmask[2 * body + (root >> 5)] >> (root & 31)) & 1u;
   for (int b = body;; b = body_parent[b]) {
     if (b == root) return true;
     if (b == 0) return false;
   }
 }
-B2_DEV bool match_side(const int* geom_body, const int* body_parent, int objtype, int objid, int geom) {
+B2_DEV bool match_side(const int* geom_body, const int* body_parent, const int* ancmask, int objtype, int objid, int geom) {
   if (objid < 0) return true;
   if (objtype == B2_OBJ_GEOM) return geom == objid;
   int body = geom_body[geom];
   if (objtype == B2_OBJ_BODY) return body == objid;
-  if (objtype == B2_OBJ_XBODY) return in_subtree(body_parent, body, objid);
+  if (objtype == B2_OBJ_XBODY) return in_subtree(body_parent, ancmask, body, objid);
   return false;
 }
 
@@ -946,6 +947,7 @@ B2_DEV void post_world(const KModel& m, const KData& d, const PostSmem& L, int w
 
   // ---- sensors -------------------------------------------------------------------------  // @region sensors
   if (m.nsensor > 0) {
+    const int* ancmask = m.nbody <= 64 ? MI(B2_MI_BODY_ANCMASK) : nullptr;
     const int* s_type = MI(B2_MI_SENSOR_TYPE);
     const int* s_objtype = MI(B2_MI_SENSOR_OBJTYPE);
     const int* s_objid = MI(B2_MI_SENSOR_OBJID);
@@ -1128,8 +1130,8 @@ B2_DEV void post_world(const KModel& m, const KData& d, const PostSmem& L, int w
         for (int c = 0; c < ncon; ++c) {
           int g1 = c_geom[2 * c], g2 = c_geom[2 * c + 1];
           real sgn = 0;
-          if (match_side(geom_body, body_parent, ot, oid, g1) && match_side(geom_body, body_parent, rt, rid, g2)) sgn = 1;
-          else if (match_side(geom_body, body_parent, ot, oid, g2) && match_side(geom_body, body_parent, rt, rid, g1)) sgn = -1;
+          if (match_side(geom_body, body_parent, ancmask, ot, oid, g1) && match_side(geom_body, body_parent, ancmask, rt, rid, g2)) sgn = 1;
+          else if (match_side(geom_body, body_parent, ancmask, ot, oid, g2) && match_side(geom_body, body_parent, ancmask, rt, rid, g1)) sgn = -1;
           if (sgn == 0) continue;
           ++nfound;
           if (reduce == 3 && (bits & 2)) {
@@ -1155,8 +1157,8 @@ B2_DEV void post_world(const KModel& m, const KData& d, const PostSmem& L, int w
               for (int c = 0; c < ncon; ++c) {
                 int g1 = c_geom[2 * c], g2 = c_geom[2 * c + 1];
                 real sgn = 0;
-                if (match_side(geom_body, body_parent, ot, oid, g1) && match_side(geom_body, body_parent, rt, rid, g2)) sgn = 1;
-                else if (match_side(geom_body, body_parent, ot, oid, g2) && match_side(geom_body, body_parent, rt, rid, g1)) sgn = -1;
+                if (match_side(geom_body, body_parent, ancmask, ot, oid, g1) && match_side(geom_body, body_parent, ancmask, rt, rid, g2)) sgn = 1;
+                else if (match_side(geom_body, body_parent, ancmask, ot, oid, g2) && match_side(geom_body, body_parent, ancmask, rt, rid, g1)) sgn = -1;
                 if (sgn == 0) continue;
                 real key;
                 if (reduce == 0) key = (real)c;

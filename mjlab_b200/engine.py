@@ -84,7 +84,7 @@ MODEL_INT_FIELDS = [
   ("SENSOR_TYPE", "sensor_type"), ("SENSOR_OBJTYPE", "sensor_objtype"), ("SENSOR_OBJID", "sensor_objid"),
   ("SENSOR_REFTYPE", "sensor_reftype"), ("SENSOR_REFID", "sensor_refid"), ("SENSOR_INTPRM", "sensor_intprm"),
   ("SENSOR_DIM", "sensor_dim"), ("SENSOR_ADR", "sensor_adr"), ("DOF_ACTID", "dof_actid"),
-  ("DYN_GEOM", "dyn_geom"), ("FIELD_GEOM", "field_geom"), ("FIELD_CELL0", "field_cell0"),
+  ("BODY_ANCMASK", "body_ancmask"), ("DYN_GEOM", "dyn_geom"), ("FIELD_GEOM", "field_geom"), ("FIELD_CELL0", "field_cell0"),
   ("FIELD_CELL_ADR", "field_cell_adr"), ("FIELD_CELL_ITEM", "field_cell_item"), ("FQ_GEOM", "fq_geom"),
 ]
 
@@ -218,13 +218,20 @@ def derived_int_tables(m) -> dict[str, np.ndarray]:
   for a in range(m.nu):
     dof = int(m.jnt_dofadr[m.actuator_trnid[a, 0]])
     dof_actid[dof] = a if dof_actid[dof] == -1 else -2
+  anc = np.zeros(nb, np.uint64)
+  if nb <= 64:
+    for i in range(nb):
+      anc[i] = (anc[m.body_parentid[i]] if i > 0 else np.uint64(0)) | (np.uint64(1) << np.uint64(i))
+  ancmask = np.zeros((nb, 2), np.uint32)
+  ancmask[:, 0] = (anc & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+  ancmask[:, 1] = (anc >> np.uint64(32)).astype(np.uint32)
   dofmask = np.zeros((nb, 2), np.uint32)
   dofmask[:, 0] = (mask & np.uint64(0xFFFFFFFF)).astype(np.uint32)
   dofmask[:, 1] = (mask >> np.uint64(32)).astype(np.uint32)
   return dict(
     nlevel=nlevel, level_adr=level_adr, level_body=order, child_adr=child_adr,
     child_body=np.array(flat if flat else [0], np.int32), body_lastdof=lastdof, body_dofmask=dofmask.view(np.int32),
-    dof_actid=dof_actid,
+    dof_actid=dof_actid, body_ancmask=ancmask.view(np.int32),
   )
 
 

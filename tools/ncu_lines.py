@@ -24,7 +24,7 @@ def line_table(so: str, kernel: str):
   out, cur, inside = [], ("?", 0), False
   for ln in txt.splitlines():
     if ln.startswith("\t.section"):
-      inside = (".text." in ln) and (kernel in ln)
+      inside = (".text." in ln) and (f"_Z{len(kernel)}{kernel}" in ln)   # exact (Itanium-mangled) function name
       continue
     if not inside:
       continue
