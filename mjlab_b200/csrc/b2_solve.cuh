@@ -104,6 +104,9 @@ B2_DEVN void rows_dot(const real* jpool, const int* rowinfo, const int* runinfo,
 }
 
 struct LsPnt { real alpha, cost, d1, d2; };
+#ifndef B2_FLOOR_MULT
+#define B2_FLOOR_MULT 8   // rounding floor of the convergence test, in units of eps * |cost| (experiments: tools/floor_experiment.py)
+#endif
 
 B2_DEVN LsPnt ls_eval(real alpha, real q0g, real q1g, real q2g, const real* jar, const real* jv, const real* D, int nefc) {  // @region linesearch
   real q0 = 0, q1 = 0, q2 = 0;
@@ -789,7 +792,7 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
       if (it > 0) {
         gn = sqrt(b2_wsum(gn));
         real improvement = scale * (cost - newcost);
-        real floor_ = fmax(tolerance, 8 * eps_real * scale * fabs(newcost));
+        real floor_ = fmax(tolerance, B2_FLOOR_MULT * eps_real * scale * fabs(newcost));
 #ifdef B2_TRACE
         printf("w%d it%d cost %.9g new %.9g impr %.3g floor %.3g gn*scale %.3g same %d nefc %d\n", w, it, (double)cost, (double)newcost, (double)improvement, (double)floor_, (double)(scale * gn), (int)same_set, nefc);
 #endif

@@ -1,0 +1,54 @@
+"""CPU experiment: how does the rounding floor of the Newton convergence test (B2_FLOOR_MULT x eps x |cost|, float32 builds
+only) trade iterations against accuracy?  Realistic heavy states (fallen G1 robots under random controls, produced by the
+float64 host build), one forward pass per variant, error of qacc against the float64 solution."""
+import ctypes as C
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+import mjlab_b200  # noqa: E402
+from oracle.cport import CpuSim  # noqa: E402
+from tests.hostemu import harness as H  # noqa: E402
+
+m = mjlab_b200.load_model("g1_flat")
+nw = 256
+rng = np.random.default_rng(0)
+sim = CpuSim(m, nw, 35, 300)
+sim.qpos[:] = m.key_qpos[0]
+sim.qpos[:, 2] += 0.02
+for k in range(30):
+  sim.ctrl[:] = m.key_ctrl[0] + rng.uniform(-1, 1, (nw, m.nu)) * 1.0
+  sim.step(4, 8)
+state = {f: getattr(sim, f).copy() for f in ("qpos", "qvel", "ctrl", "qacc_warmstart")}
+print("states: ncon mean %.1f max %d, nefc mean %.1f max %d" % (sim.ncon.mean(), sim.ncon.max(), sim.nefc.mean(), sim.nefc.max()))
+
+
+def run(real, mult):
+  out = ROOT / "build" / f"hostemu_{real}_{mult}.so"
+  out.parent.mkdir(exist_ok=True)
+  subprocess.run(["g++", "-O2", "-std=c++17", "-DB2_HOSTEMU", f"-DB2_REAL={real}", f"-DB2_FLOOR_MULT={mult}", "-shared", "-fPIC", "-ffp-contract=off",
+                  "-Wno-unused-variable", "-o", str(out), str(ROOT / "tests" / "hostemu" / "hostemu.cpp")], check=True)
+  orig = H.build
+  H.build = lambda r="float": out
+  try:
+    hs = H.HostSim(m, nw, 35, 300, real=real)
+  finally:
+    H.build = orig
+  for f, v in state.items():
+    getattr(hs, f)[:] = v
+  hs.forward()
+  return hs.qacc.astype(np.float64).copy(), hs.solver_niter.copy(), hs.nefc.copy()
+
+
+ref, nit64, nefc = run("double", 8)
+print("float64: niter mean %.2f max %d" % (nit64.mean(), nit64.max()))
+heavy = nefc > 60
+for mult in (8, 32, 128, 512, 2048):
+  q, nit, _ = run("float", mult)
+  err = np.abs(q - ref).max(1) / np.maximum(np.abs(ref).max(1), 1.0)
+  print(f"float32 floor x{mult:5d}: niter mean {nit.mean():.2f} (heavy worlds {nit[heavy].mean():.2f}, n={heavy.sum()}), max {nit.max()}; "
+        f"qacc rel err median {np.median(err):.2e} p90 {np.quantile(err, .9):.2e} max {err.max():.2e}")
