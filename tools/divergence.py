@@ -2,6 +2,7 @@
 (oracle/cport, which reproduces the numpy oracle to 1e-9): the statistic BASELINE.json's north_star asks for.
 
   python tools/divergence.py [robot] [nworld] > gpurun_out/divergence.json       # on the GPU box
+  python tools/divergence.py g1_rough 128                                        # robots spread over the terrain tiles
 
 Seeded states around the init keyframe (tests/util.random_states: some worlds standing, some falling), constant
 controls, `nconmax=35, njmax=300, dt=0.005`.  Reported at N = 1, 2, 5, 10, 20, 50, 100, 200 steps: per-world max-norm
@@ -24,9 +25,16 @@ from tests.util import random_states  # noqa: E402
 
 robot = sys.argv[1] if len(sys.argv) > 1 else "g1"
 nworld = int(sys.argv[2]) if len(sys.argv) > 2 else 128
-m = mjlab_b200.load_model(f"{robot}_flat")
+m = mjlab_b200.load_model(robot if robot.endswith("_rough") else f"{robot}_flat")
 sim = Simulation(nworld, SimulationCfg(nconmax=35, njmax=300, mujoco=MujocoCfg(timestep=0.005, iterations=10, ls_iterations=20)), m, "cuda:0")
 qpos, qvel, ctrl, _ = random_states(m, nworld, seed=123, vel=0.2)
+if robot.endswith("_rough"):   # one robot per sub-terrain origin (rows = difficulty), shifted onto the steps
+  rng = np.random.default_rng(7)
+  R, C = m.terrain_origins.shape[:2]
+  for w in range(nworld):
+    o = m.terrain_origins[rng.integers(0, R), rng.integers(0, C)]
+    qpos[w, :2] += o[:2] + rng.uniform(-2.5, 2.5, 2)
+    qpos[w, 2] += o[2] + 0.05
 cpu = CpuSim(m, nworld, 35, 300)
 cpu.qpos[:], cpu.qvel[:], cpu.ctrl[:] = qpos, qvel, ctrl
 f32 = lambda a: torch.as_tensor(a, dtype=torch.float32, device="cuda:0")  # noqa: E731
