@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(B2_SMOOTH_WPB * 32) k_smooth(const KModel m, c
 #ifdef B2_TIMING
 // diagnostics build only (tools/solve_timeline.py): per-world start / end of the solver in globaltimer ns + the SM id
 __device__ unsigned long long g_tim[3 * 16384];
+extern "C" int b2_debug_lsstat(unsigned long long* out) { return (int)cudaMemcpyFromSymbol(out, g_lsstat, sizeof(unsigned long long) * 8); }
 extern "C" int b2_debug_phases(unsigned long long* out, int n) { return (int)cudaMemcpyFromSymbol(out, g_phase, sizeof(unsigned long long) * 8 * n); }
 __device__ __forceinline__ unsigned long long b2_gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ unsigned b2_smid() { unsigned s; asm volatile("mov.u32 %0, %%smid;" : "=r"(s)); return s; }

@@ -104,11 +104,31 @@ B2_DEVN void rows_dot(const real* jpool, const int* rowinfo, const int* runinfo,
 }
 
 struct LsPnt { real alpha, cost, d1, d2; };
+#if defined(B2_TIMING) && !defined(B2_HOSTEMU)
+__device__ unsigned long long g_lsstat[8];   // [heavy?0:4] + {line searches, single evaluations, 3-point rounds, searches that reached refinement}
+#define B2_LSSTAT(k) { if (B2_LANE == 0) atomicAdd(&g_lsstat[(nefc > 60 ? 0 : 4) + (k)], 1ull); }
+#else
+#define B2_LSSTAT(k)
+#endif
+#ifdef B2_HOSTEMU
+static long long b2h_ls_passes = 0;   // test harness statistic: row passes of the line search (single or three-point)
+#define B2_LS_COUNT() (++b2h_ls_passes)
+#else
+#define B2_LS_COUNT()
+#endif
+// float32 only: treat |d1| below B2_LS_FLOOR_MULT * eps * (|alpha| d2 + |q1|) - the rounding noise of the derivative itself - as
+// converged.  MuJoCo's gradient tolerance (tolerance * ls_tolerance * |search| / scale ~ 1e-10) is below that noise in
+// float32, so without the floor the search keeps refining digits that do not exist (measured on the G1 batch: 11.5 row
+// passes per line search without it, 3.9 with it, same Newton iteration counts, same error against the float64 solution).  0 = off.
+#ifndef B2_LS_FLOOR_MULT
+#define B2_LS_FLOOR_MULT 16
+#endif
 #ifndef B2_FLOOR_MULT
 #define B2_FLOOR_MULT 8   // rounding floor of the convergence test, in units of eps * |cost| (experiments: tools/floor_experiment.py)
 #endif
 
 B2_DEVN LsPnt ls_eval(real alpha, real q0g, real q1g, real q2g, const real* jar, const real* jv, const real* D, int nefc) {  // @region linesearch
+  B2_LS_COUNT();
   real q0 = 0, q1 = 0, q2 = 0;
   B2_UNROLL1   // (unrolling by 2 / 4 to overlap the passes' loads was measured: +2 % kernel time, code size again)
   for (int r = B2_LANE; r < nefc; r += B2_NLANE) {
@@ -137,6 +157,7 @@ B2_DEVN LsPnt ls_eval(real alpha, real q0g, real q1g, real q2g, const real* jar,
 // is a chain of dependent reductions, and on the heaviest worlds (which set the kernel's duration) it is a third of the time.
 // Each point's sums are accumulated in the same order as ls_eval does, so the values are bit-identical to three calls.
 B2_DEVN void ls_eval3(const real* alpha, LsPnt* out, real q0g, real q1g, real q2g, const real* jar, const real* jv, const real* D, int nefc) {
+  B2_LS_COUNT();
   real a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0, c0 = 0, c1 = 0, c2 = 0;
   const real al0 = alpha[0], al1 = alpha[1], al2 = alpha[2];
   B2_UNROLL1
@@ -164,6 +185,16 @@ B2_DEVN void ls_eval3(const real* alpha, LsPnt* out, real q0g, real q1g, real q2
   }
 }
 
+// derivative tolerance at point p: MuJoCo's gtol, or the rounding noise of d1 in float32 when that is larger (see B2_LS_FLOOR_MULT)
+B2_DEV real ls_gtol(const LsPnt& p, real gtol) {
+  if (sizeof(real) == 4 && B2_LS_FLOOR_MULT > 0) {
+    const real q1 = p.d1 - p.alpha * p.d2;
+    const real noise = (real)B2_LS_FLOOR_MULT * (real)1.1920929e-7 * (fabs(p.alpha) * p.d2 + fabs(q1));
+    return noise > gtol ? noise : gtol;
+  }
+  return gtol;
+}
+
 // Bracket update of MuJoCo's line search: move end point p to the best candidate on its side of the minimum.
 B2_DEV bool ls_move_bracket(LsPnt& p, const LsPnt* cand) {
   bool flag = false;
@@ -181,17 +212,19 @@ B2_DEVN real linesearch(real q0g, real q1g, real q2g, real snorm, real tolerance
   if (snorm < B2_MINVAL) return 0;
   real gtol = tolerance * ls_tolerance * snorm / scale;
   int nev = 0;
+  B2_LSSTAT(0) B2_LSSTAT(1) B2_LSSTAT(1)
   LsPnt p0 = ls_eval(0, q0g, q1g, q2g, jar, jv, D, nefc);
   LsPnt p1 = ls_eval(p0.alpha - p0.d1 / p0.d2, q0g, q1g, q2g, jar, jv, D, nefc); ++nev;
   if (p0.cost < p1.cost) p1 = p0;
-  if (fabs(p1.d1) < gtol) return p1.alpha;
+  if (fabs(p1.d1) < ls_gtol(p1, gtol)) return p1.alpha;
   real dir = p1.d1 < 0 ? (real)1 : (real)-1;
   LsPnt p2 = p1;
   bool p2set = false;
-  while (p1.d1 * dir <= -gtol && nev < ls_iterations) {
+  while (p1.d1 * dir <= -ls_gtol(p1, gtol) && nev < ls_iterations) {
     p2 = p1; p2set = true;
+    B2_LSSTAT(1)
     p1 = ls_eval(p1.alpha - p1.d1 / p1.d2, q0g, q1g, q2g, jar, jv, D, nefc); ++nev;
-    if (fabs(p1.d1) < gtol) return p1.alpha;
+    if (fabs(p1.d1) < ls_gtol(p1, gtol)) return p1.alpha;
   }
   if (nev >= ls_iterations || !p2set) return p1.alpha;
   // Refinement.  The reference sequence is: evaluate p1next; loop { evaluate pmid; test; move the bracket ends, evaluating
@@ -199,7 +232,9 @@ B2_DEVN real linesearch(real q0g, real q1g, real q2g, real snorm, real tolerance
   // the midpoint of the NEXT iteration (needed iff the evaluation budget allows another iteration) - is known at the
   // same time, so each round is one ls_eval3 pass; `nev` advances exactly as in the one-at-a-time sequence.
   LsPnt p2next = p1, p1next, pmid;
+  B2_LSSTAT(3)
   {
+    B2_LSSTAT(2)
     ++nev;                                              // p1next
     const bool want_mid = nev < ls_iterations;
     real al[3] = {p1.alpha - p1.d1 / p1.d2, want_mid ? (real)0.5 * (p1.alpha + p2.alpha) : (real)0, 0};
@@ -212,7 +247,7 @@ B2_DEVN real linesearch(real q0g, real q1g, real q2g, real snorm, real tolerance
     LsPnt cand[3] = {p1next, p2next, pmid};
     int best = -1;
     for (int i = 0; i < 3; ++i)
-      if (fabs(cand[i].d1) < gtol && (best < 0 || cand[i].cost < cand[best].cost)) best = i;
+      if (fabs(cand[i].d1) < ls_gtol(cand[i], gtol) && (best < 0 || cand[i].cost < cand[best].cost)) best = i;
     if (best >= 0) return cand[best].alpha;
     const bool b1 = ls_move_bracket(p1, cand);
     const bool b2 = ls_move_bracket(p2, cand);
@@ -222,6 +257,7 @@ B2_DEVN real linesearch(real q0g, real q1g, real q2g, real snorm, real tolerance
     real al[3] = {b1 ? p1.alpha - p1.d1 / p1.d2 : (real)0, b2 ? p2.alpha - p2.d1 / p2.d2 : (real)0,
                   want_mid ? (real)0.5 * (p1.alpha + p2.alpha) : (real)0};
     LsPnt out[3];
+    B2_LSSTAT(2)
     ls_eval3(al, out, q0g, q1g, q2g, jar, jv, D, nefc);
     if (b1) p1next = out[0];
     if (b2) p2next = out[1];

@@ -18,6 +18,7 @@
 extern "C" {
 
 int b2h_sizeof_real(void) { return (int)sizeof(real); }
+long long b2h_ls_pass_count(void) { return b2h_ls_passes; }
 int b2h_sizeof_model(void) { return (int)sizeof(KModel); }
 int b2h_sizeof_data(void) { return (int)sizeof(KData); }
 

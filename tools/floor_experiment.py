@@ -27,10 +27,10 @@ state = {f: getattr(sim, f).copy() for f in ("qpos", "qvel", "ctrl", "qacc_warms
 print("states: ncon mean %.1f max %d, nefc mean %.1f max %d" % (sim.ncon.mean(), sim.ncon.max(), sim.nefc.mean(), sim.nefc.max()))
 
 
-def run(real, mult):
-  out = ROOT / "build" / f"hostemu_{real}_{mult}.so"
+def run(real, mult, ls_mult=0, nstep=0):
+  out = ROOT / "build" / f"hostemu_{real}_{mult}_{ls_mult}.so"
   out.parent.mkdir(exist_ok=True)
-  subprocess.run(["g++", "-O2", "-std=c++17", "-DB2_HOSTEMU", f"-DB2_REAL={real}", f"-DB2_FLOOR_MULT={mult}", "-shared", "-fPIC", "-ffp-contract=off",
+  subprocess.run(["g++", "-O2", "-std=c++17", "-DB2_HOSTEMU", f"-DB2_REAL={real}", f"-DB2_FLOOR_MULT={mult}", f"-DB2_LS_FLOOR_MULT={ls_mult}", "-shared", "-fPIC", "-ffp-contract=off",
                   "-Wno-unused-variable", "-o", str(out), str(ROOT / "tests" / "hostemu" / "hostemu.cpp")], check=True)
   orig = H.build
   H.build = lambda r="float": out
@@ -40,8 +40,15 @@ def run(real, mult):
     H.build = orig
   for f, v in state.items():
     getattr(hs, f)[:] = v
+  hs.lib.b2h_ls_pass_count.restype = C.c_longlong
+  n0 = hs.lib.b2h_ls_pass_count()
   hs.forward()
-  return hs.qacc.astype(np.float64).copy(), hs.solver_niter.copy(), hs.nefc.copy()
+  run.passes = hs.lib.b2h_ls_pass_count() - n0
+  qacc = hs.qacc.astype(np.float64).copy()
+  for _ in range(nstep):
+    hs.step()
+  run.qpos = hs.qpos.astype(np.float64).copy()
+  return qacc, hs.solver_niter.copy(), hs.nefc.copy()
 
 
 ref, nit64, nefc = run("double", 8)
@@ -52,3 +59,14 @@ for mult in (8, 32, 128, 512, 2048):
   err = np.abs(q - ref).max(1) / np.maximum(np.abs(ref).max(1), 1.0)
   print(f"float32 floor x{mult:5d}: niter mean {nit.mean():.2f} (heavy worlds {nit[heavy].mean():.2f}, n={heavy.sum()}), max {nit.max()}; "
         f"qacc rel err median {np.median(err):.2e} p90 {np.quantile(err, .9):.2e} max {err.max():.2e}")
+
+print("--- line-search derivative floor (float32), Newton floor x8")
+ref, nit64, nefc = run("double", 8, 0, nstep=20)
+qpos64 = run.qpos
+print("float64: line-search row passes %d" % run.passes)
+for ls_mult in (0, 4, 16, 64, 256):
+  q, nit, _ = run("float", 8, ls_mult, nstep=20)
+  err = np.abs(q - ref).max(1) / np.maximum(np.abs(ref).max(1), 1.0)
+  eq = np.abs(run.qpos - qpos64).max(1)
+  print(f"float32 ls floor x{ls_mult:4d}: row passes {run.passes} (forward pass), niter mean {nit.mean():.2f}; qacc rel err median {np.median(err):.2e} "
+        f"p90 {np.quantile(err, .9):.2e} max {err.max():.2e}; qpos err after 20 steps median {np.median(eq):.2e} p90 {np.quantile(eq, .9):.2e}")

@@ -63,4 +63,12 @@ for rep in range(3):
       tot = ph[sel].sum()
       print(f"   phase shares, {label}: " + ", ".join(f"{n} {100 * ph[sel, k].sum() / tot:.0f}%" for k, n in enumerate(names)),
             f"| cycles/world {ph[sel].sum(1).mean():.0f}")
+  if hasattr(lib, "b2_debug_lsstat") and rep == 2:
+    ls = np.zeros(8, np.uint64)
+    lib.b2_debug_lsstat.argtypes = [C.c_void_p]
+    lib.b2_debug_lsstat(ls.ctypes.data)
+    for label, o in (("worlds with > 60 rows", 0), ("other worlds", 4)):
+      n = max(int(ls[o]), 1)
+      print(f"   line searches ({label}, all launches so far): {int(ls[o])}; per search: {ls[o + 1] / n:.2f} single evaluations, "
+            f"{ls[o + 2] / n:.2f} three-point rounds; {100 * ls[o + 3] / n:.0f} % reach the refinement phase")
   E.check_call(lib, lib.b2_stage(pm, pd, 2, 1, st))
