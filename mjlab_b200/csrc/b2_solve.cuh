@@ -123,6 +123,9 @@ static long long b2h_ls_passes = 0;   // test harness statistic: row passes of t
 #ifndef B2_LS_FLOOR_MULT
 #define B2_LS_FLOOR_MULT 16
 #endif
+#ifndef B2_GRAD_FLOOR_MULT
+#define B2_GRAD_FLOOR_MULT 4   // float32 only: |gradient| < mult * eps * |(M a, qfrc_smooth, qfrc_constraint)| counts as converged; 0 = off
+#endif
 #ifndef B2_FLOOR_MULT
 #define B2_FLOOR_MULT 8   // rounding floor of the convergence test, in units of eps * |cost| (experiments: tools/floor_experiment.py)
 #endif
@@ -821,19 +824,27 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
         }
         B2_WSYNC();
       }
-      real gn = 0;
+      real gn = 0, gref = 0;
       B2_UNROLL1
-      for (int i = B2_LANE; i < nv; i += B2_NLANE) { real g = Ma[i] - qfs[i] - qfc[i]; grad[i] = g; tmp[i] = g; gn += g * g; }
+      for (int i = B2_LANE; i < nv; i += B2_NLANE) {
+        real g = Ma[i] - qfs[i] - qfc[i];
+        grad[i] = g; tmp[i] = g; gn += g * g;
+        if (sizeof(real) == 4 && B2_GRAD_FLOOR_MULT > 0) gref += Ma[i] * Ma[i] + qfs[i] * qfs[i] + qfc[i] * qfc[i];
+      }
       B2_WSYNC();
       if (it > 0) {
         gn = sqrt(b2_wsum(gn));
+        // float32: a gradient below the rounding noise of its own three terms is zero for all practical purposes
+        bool grad_is_noise = false;
+        if (sizeof(real) == 4 && B2_GRAD_FLOOR_MULT > 0)
+          grad_is_noise = gn < (real)B2_GRAD_FLOOR_MULT * eps_real * sqrt(b2_wsum(gref));
         real improvement = scale * (cost - newcost);
         real floor_ = fmax(tolerance, B2_FLOOR_MULT * eps_real * scale * fabs(newcost));
 #ifdef B2_TRACE
         printf("w%d it%d cost %.9g new %.9g impr %.3g floor %.3g gn*scale %.3g same %d nefc %d\n", w, it, (double)cost, (double)newcost, (double)improvement, (double)floor_, (double)(scale * gn), (int)same_set, nefc);
 #endif
         cost = newcost;
-        if (improvement < floor_ || scale * gn < tolerance) break;
+        if (improvement < floor_ || scale * gn < tolerance || grad_is_noise) break;
       } else {
         cost = newcost;
       }

@@ -27,10 +27,10 @@ state = {f: getattr(sim, f).copy() for f in ("qpos", "qvel", "ctrl", "qacc_warms
 print("states: ncon mean %.1f max %d, nefc mean %.1f max %d" % (sim.ncon.mean(), sim.ncon.max(), sim.nefc.mean(), sim.nefc.max()))
 
 
-def run(real, mult, ls_mult=0, nstep=0):
-  out = ROOT / "build" / f"hostemu_{real}_{mult}_{ls_mult}.so"
+def run(real, mult, ls_mult=16, nstep=0, grad_mult=0):
+  out = ROOT / "build" / f"hostemu_{real}_{mult}_{ls_mult}_{grad_mult}.so"
   out.parent.mkdir(exist_ok=True)
-  subprocess.run(["g++", "-O2", "-std=c++17", "-DB2_HOSTEMU", f"-DB2_REAL={real}", f"-DB2_FLOOR_MULT={mult}", f"-DB2_LS_FLOOR_MULT={ls_mult}", "-shared", "-fPIC", "-ffp-contract=off",
+  subprocess.run(["g++", "-O2", "-std=c++17", "-DB2_HOSTEMU", f"-DB2_REAL={real}", f"-DB2_FLOOR_MULT={mult}", f"-DB2_LS_FLOOR_MULT={ls_mult}", f"-DB2_GRAD_FLOOR_MULT={grad_mult}", "-shared", "-fPIC", "-ffp-contract=off",
                   "-Wno-unused-variable", "-o", str(out), str(ROOT / "tests" / "hostemu" / "hostemu.cpp")], check=True)
   orig = H.build
   H.build = lambda r="float": out
@@ -69,4 +69,12 @@ for ls_mult in (0, 4, 16, 64, 256):
   err = np.abs(q - ref).max(1) / np.maximum(np.abs(ref).max(1), 1.0)
   eq = np.abs(run.qpos - qpos64).max(1)
   print(f"float32 ls floor x{ls_mult:4d}: row passes {run.passes} (forward pass), niter mean {nit.mean():.2f}; qacc rel err median {np.median(err):.2e} "
+        f"p90 {np.quantile(err, .9):.2e} max {err.max():.2e}; qpos err after 20 steps median {np.median(eq):.2e} p90 {np.quantile(eq, .9):.2e}")
+
+print("--- gradient-noise floor of the Newton convergence test (float32), line-search floor x16")
+for gm in (0, 2, 8, 32, 128):
+  q, nit, _ = run("float", 8, 16, nstep=20, grad_mult=gm)
+  err = np.abs(q - ref).max(1) / np.maximum(np.abs(ref).max(1), 1.0)
+  eq = np.abs(run.qpos - qpos64).max(1)
+  print(f"float32 grad floor x{gm:4d}: niter mean {nit.mean():.2f} (heavy {nit[heavy].mean():.2f}); qacc rel err median {np.median(err):.2e} "
         f"p90 {np.quantile(err, .9):.2e} max {err.max():.2e}; qpos err after 20 steps median {np.median(eq):.2e} p90 {np.quantile(eq, .9):.2e}")
