@@ -229,6 +229,7 @@ static int make_plan(const b2_model* m, const b2_data* d, Plan* p) {
     if (arena > budget) arena = (int)budget & ~3;
   }
   if (const char* e = getenv("B200SIM_ARENA")) arena = atoi(e);  // experiments
+  arena = (arena + 3) & ~3;   // the two-ended allocator of k_solve works in units of 4 floats
   p->lv = solve_smem_layout(m->nv, rows_max, m->maxchain, arena);
   p->lp = post_smem_layout(m->nv);
   p->smem_smooth = (size_t)p->ls.total * sizeof(real) * B2_SMOOTH_WPB;
