@@ -229,6 +229,11 @@ static int make_plan(const b2_model* m, const b2_data* d, Plan* p) {
     if (arena > budget) arena = (int)budget & ~3;
   }
   if (const char* e = getenv("B200SIM_ARENA")) arena = atoi(e);  // experiments
+  {
+    // whatever the cap, a world reduced to one row and no Jacobian pool must fit (solve_world shrinks towards that)
+    int floor_ = solve_arena_need(1, runs_max, dofs_max, 0, d->nconmax > 0 ? d->nconmax : 1) + 64;
+    if (arena < floor_) arena = floor_;
+  }
   arena = (arena + 3) & ~3;   // the two-ended allocator of k_solve works in units of 4 floats
   p->lv = solve_smem_layout(m->nv, rows_max, m->maxchain, arena);
   p->lp = post_smem_layout(m->nv);

@@ -418,11 +418,19 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
     if (jpool_cap > 65535) jpool_cap = 65535;
   }
   int need = solve_arena_need(rows_cap, runs_cap, dofs_cap, jpool_cap, ncon > 0 ? ncon : 1);
-  if (need > L.arena_cap) {  // cannot happen when the arena holds one worst-case world; keep the pools inside it regardless
-    jpool_cap -= need - L.arena_cap;
-    if (jpool_cap < 0) jpool_cap = 0;
+  // A world beyond the arena (the arena may be capped below the strict worst case, see make_plan) shrinks its Jacobian pool
+  // first, then its row capacity: rows that do not fit are dropped from the tail and counted in nefc_dropped, as with njmax.
+  // The loop ends with need <= arena_cap (make_plan guarantees that a one-row world fits), which the allocator below
+  // relies on: a block larger than the arena could never be granted.
+  B2_UNROLL1
+  while (need > L.arena_cap) {
+    const int over = ((need - L.arena_cap) + 3) & ~3;
+    if (jpool_cap > 0) jpool_cap = jpool_cap > over ? jpool_cap - over : 0;
+    else if (rows_cap > 1) rows_cap = rows_cap > 8 ? rows_cap - 8 : 1;
+    else break;
     need = solve_arena_need(rows_cap, runs_cap, dofs_cap, jpool_cap, ncon > 0 ? ncon : 1);
   }
+  if (need > L.arena_cap) need = L.arena_cap;
   int aoff = 0;
 #ifndef B2_HOSTEMU
   {
@@ -430,13 +438,16 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
     // 1's hangs from the top.  actl[0] packs both sizes (units of 4 floats, 16 bits each); a world whose block does not fit
     // next to the other warp's current one waits until that warp releases it (k_solve clears the field after each world).
     const int me = (threadIdx.x >> 5) & 1;
-    const int need4 = (need + 3) >> 2, cap4 = L.arena_cap >> 2;
+    const int cap4 = L.arena_cap >> 2;
+    const int need4 = ((need + 3) >> 2) < cap4 ? ((need + 3) >> 2) : cap4;
     if (B2_LANE == 0) {
       unsigned* u = reinterpret_cast<unsigned*>(actl);
-      for (;;) {
+      // bounded wait (the CTA-mate releases its block within a millisecond; the bound only guards against a logic error
+      // turning into a hung GPU - past it the block is taken regardless)
+      for (int spins = 0;; ++spins) {
         unsigned old = *reinterpret_cast<volatile unsigned*>(u);
         int other = (int)(me ? (old & 0xffffu) : (old >> 16));
-        if (need4 + other <= cap4) {
+        if (need4 + other <= cap4 || spins > (1 << 22)) {
           unsigned nw = me ? ((old & 0xffffu) | ((unsigned)need4 << 16)) : ((old & 0xffff0000u) | (unsigned)need4);
           if (atomicCAS(u, old, nw) == old) break;
         } else {

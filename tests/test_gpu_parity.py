@@ -206,3 +206,50 @@ def test_trajectory_divergence_statistic(go1):
       assert np.median(e1) < 1e-6 and e1.max() < 1e-4   # ~1e-4 relative per step (north_star), in practice ~1e-7
   err = np.abs(sim.data.qpos.cpu().numpy() - cpu.qpos).max(1)
   assert np.median(err) < 1e-5 and same.mean() > 0.8
+
+
+def test_solver_arena_contention_does_not_change_results():
+  """k_solve's two warps per CTA share one row arena (two-ended allocator; a world waits when its block does not fit next
+  to its CTA-mate's).  The smallest arena that still holds the heaviest world of the batch makes most pairs wait; results
+  must be bit-identical to the default arena's."""
+  import os
+  import mjlab_b200
+  m = mjlab_b200.load_model("g1_flat")
+  nw, nstep = 256, 6
+  qpos, qvel, ctrl, xfrc = util.random_states(m, nw, seed=9, drop=0.015)
+
+  def run(arena):
+    if arena is None:
+      os.environ.pop("B200SIM_ARENA", None)
+    else:
+      os.environ["B200SIM_ARENA"] = str(arena)
+    sim = make_sim(m, nw, export_efc_J=False)
+    sim.use_cuda_graph = False
+    load_state(sim, qpos, qvel, ctrl, xfrc)
+    dropped = 0
+    for _ in range(nstep):
+      sim.step()
+      dropped += int(sim.data.nefc_dropped.sum())
+    torch.cuda.synchronize()
+    D = sim.data
+    return dropped, (D.qpos.clone(), D.qvel.clone(), D.efc_force.clone(), D.solver_niter.clone(), D.nefc.clone())
+
+  old = os.environ.get("B200SIM_ARENA")
+  try:
+    d0, ref = run(None)
+    assert d0 == 0
+    small = None
+    for arena in (800, 1000, 1200, 1600, 2000, 2400):       # floats; the default is ~3400
+      d1, out = run(arena)
+      if d1 == 0:
+        small = arena
+        break
+  finally:
+    if old is None:
+      os.environ.pop("B200SIM_ARENA", None)
+    else:
+      os.environ["B200SIM_ARENA"] = old
+  assert small is not None, "no arena below the default held the batch without dropping rows"   # (smaller ones truncate rows, and must not hang)
+  assert int(ref[4].max()) > 30
+  for a, b in zip(ref, out):
+    assert torch.equal(a, b)
