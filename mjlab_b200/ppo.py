@@ -16,6 +16,8 @@ and so that the env can be validated by actually learning on it.
 
 from __future__ import annotations
 
+import math
+
 from dataclasses import dataclass, field
 
 import torch
@@ -158,7 +160,8 @@ class OnPolicyRunner:
     # the learning rate lives on the device (KL-adaptive rule without a host round trip per mini-batch)
     cuda = self.device.type == "cuda"
     self._lr = torch.tensor(float(self.cfg.learning_rate), device=self.device)
-    self.optimizer = torch.optim.Adam(self.policy.parameters(), lr=self._lr, capturable=cuda, foreach=cuda)
+    # fused: one multi-tensor kernel per step (capturable in a CUDA graph, learning rate read from the device tensor)
+    self.optimizer = torch.optim.Adam(self.policy.parameters(), lr=self._lr, **(dict(capturable=True, fused=True) if cuda else dict(foreach=False)))
     self._update_graph, self._update_warm = None, 0
     T, B = self.cfg.num_steps_per_env, venv.num_envs
     z = lambda *s: torch.zeros(T, B, *s, device=self.device)  # noqa: E731
@@ -266,26 +269,46 @@ class OnPolicyRunner:
     return float(self._lr)
 
   def _update_body(self) -> None:
-    """All epochs x mini-batches of one PPO update; reads `self._perm`, writes `self._stats` (device tensors)."""
+    """All epochs x mini-batches of one PPO update; reads `self._perm`, writes `self._stats` (device tensors).
+
+    The step is bound by the number of small kernels, not by arithmetic, so a mini-batch is ONE row gather from a packed
+    copy of the roll-out ([N, obs | critic | actions | mu | sigma | logp, value, return, advantage]) and the Gaussian terms
+    are written out (log-prob, entropy and KL of a diagonal Normal with a state-independent std; the entropy is the same
+    for every row) instead of going through torch.distributions - same formulas as rsl_rl's PPO.update."""
     cfg, st, ro = self.cfg, self.st, self.ro
     N = cfg.num_steps_per_env * self.env.num_envs
-    flat = {k: v.reshape(N, *v.shape[2:]) for k, v in st.items()}
-    ret, adv = ro["returns"].reshape(N), ro["advantages"].reshape(N)
+    no, nc, na = self.n_obs, self.n_critic, self.n_act
+    cols = [("obs", no), ("critic", nc), ("actions", na), ("mu", na), ("sigma", na), ("logp", 1), ("values", 1)]
+    width = sum(w for _, w in cols) + 2
+    if getattr(self, "_pack", None) is None or self._pack.shape != (N, width):
+      self._pack = torch.zeros(N, width, device=self.device)
+    off, o = {}, 0
+    for k, w in cols:
+      self._pack[:, o:o + w] = st[k].reshape(N, w)
+      off[k] = (o, o + w)
+      o += w
+    self._pack[:, o] = ro["returns"].reshape(N)
+    self._pack[:, o + 1] = ro["advantages"].reshape(N)
+    off["ret"], off["adv"] = o, o + 1
     mb = N // cfg.num_mini_batches
     params = list(self.policy.parameters())
     stats = self._stats
     stats.zero_()
     self.policy.train()
+    half_log_2pi = 0.5 * math.log(2.0 * math.pi)
     for e in range(cfg.num_learning_epochs):
       for i in range(cfg.num_mini_batches):
-        idx = self._perm[e, i * mb:(i + 1) * mb]
-        dist_ = self.policy.distribution(flat["obs"][idx])
-        logp = dist_.log_prob(flat["actions"][idx]).sum(-1)
-        value = self.policy.evaluate(flat["critic"][idx]).squeeze(-1)
-        mu, sigma, entropy = dist_.mean, dist_.stddev, dist_.entropy().sum(-1)
+        b = self._pack[self._perm[e, i * mb:(i + 1) * mb]]
+        col = lambda k: b[:, off[k][0]:off[k][1]]  # noqa: E731
+        mu = self.policy.actor(self.policy.actor_norm(col("obs")))
+        value = self.policy.evaluate(col("critic")).squeeze(-1)
+        std = self.policy.std
+        log_std = std.log()
+        logp = (-0.5 * ((col("actions") - mu) / std).square() - log_std).sum(-1) - na * half_log_2pi
+        entropy = (0.5 + half_log_2pi + log_std).sum()            # per-row entropy of the diagonal Normal; identical rows
         with torch.no_grad():
-          old_mu, old_sigma = flat["mu"][idx], flat["sigma"][idx]
-          kl = torch.sum(torch.log(sigma / old_sigma + 1e-5) + (old_sigma.square() + (old_mu - mu).square()) / (2.0 * sigma.square()) - 0.5, -1).mean()
+          old_mu, old_sigma = col("mu"), col("sigma")
+          kl = torch.sum(torch.log(std / old_sigma + 1e-5) + (old_sigma.square() + (old_mu - mu).square()) / (2.0 * std.square()) - 0.5, -1).mean()
           if self.distributed:
             dist.all_reduce(kl, op=dist.ReduceOp.SUM)
             kl /= self.world_size
@@ -294,16 +317,16 @@ class OnPolicyRunner:
             down = torch.clamp(lr / 1.5, min=1e-5)
             up = torch.clamp(lr * 1.5, max=1e-2)
             lr.copy_(torch.where(kl > cfg.desired_kl * 2.0, down, torch.where((kl > 0.0) & (kl < cfg.desired_kl / 2.0), up, lr)))
-        ratio = torch.exp(logp - flat["logp"][idx])
-        a = adv[idx]
+        ratio = torch.exp(logp - b[:, off["logp"][0]])
+        a, ret = b[:, off["adv"]], b[:, off["ret"]]
         surrogate = torch.max(-a * ratio, -a * torch.clamp(ratio, 1.0 - cfg.clip_param, 1.0 + cfg.clip_param)).mean()
         if cfg.use_clipped_value_loss:
-          old_v = flat["values"][idx]
+          old_v = b[:, off["values"][0]]
           v_clip = old_v + (value - old_v).clamp(-cfg.clip_param, cfg.clip_param)
-          v_loss = torch.max((value - ret[idx]).square(), (v_clip - ret[idx]).square()).mean()
+          v_loss = torch.max((value - ret).square(), (v_clip - ret).square()).mean()
         else:
-          v_loss = (ret[idx] - value).square().mean()
-        loss = surrogate + cfg.value_loss_coef * v_loss - cfg.entropy_coef * entropy.mean()
+          v_loss = (ret - value).square().mean()
+        loss = surrogate + cfg.value_loss_coef * v_loss - cfg.entropy_coef * entropy
         self.optimizer.zero_grad(set_to_none=False)
         loss.backward()
         if self.distributed:
@@ -311,7 +334,7 @@ class OnPolicyRunner:
         nn.utils.clip_grad_norm_(params, cfg.max_grad_norm, foreach=self.device.type == "cuda")
         self.optimizer.step()
         with torch.no_grad():
-          stats += torch.stack((v_loss.detach(), surrogate.detach(), entropy.mean().detach(), kl))
+          stats += torch.stack((v_loss.detach(), surrogate.detach(), entropy.detach(), kl))
     stats /= cfg.num_learning_epochs * cfg.num_mini_batches
 
   def update(self, ro: dict) -> dict:
