@@ -123,6 +123,9 @@ static long long b2h_ls_passes = 0;   // test harness statistic: row passes of t
 #ifndef B2_LS_FLOOR_MULT
 #define B2_LS_FLOOR_MULT 16
 #endif
+#ifndef B2_LS_SKIP_P0
+#define B2_LS_SKIP_P0 1     // float32 only: take the line search's alpha = 0 point from the Newton update instead of a row pass
+#endif
 #ifndef B2_GRAD_FLOOR_MULT
 #define B2_GRAD_FLOOR_MULT 4   // float32 only: |gradient| < mult * eps * |(M a, qfrc_smooth, qfrc_constraint)| counts as converged; 0 = off
 #endif
@@ -210,13 +213,24 @@ B2_DEV bool ls_move_bracket(LsPnt& p, const LsPnt* cand) {
 
 // Exact 1-D minimisation along `search` (MuJoCo's iterative primal line search:
 // Newton steps until the derivative changes sign, then bracket refinement).
+// `cost0` / `slope0`: cost and directional derivative grad.search at alpha = 0, known from the Newton update.
 B2_DEVN real linesearch(real q0g, real q1g, real q2g, real snorm, real tolerance, real ls_tolerance, int ls_iterations,
-                       real scale, const real* jar, const real* jv, const real* D, int nefc) {
+                       real scale, const real* jar, const real* jv, const real* D, int nefc, real cost0, real slope0) {
   if (snorm < B2_MINVAL) return 0;
   real gtol = tolerance * ls_tolerance * snorm / scale;
   int nev = 0;
-  B2_LSSTAT(0) B2_LSSTAT(1) B2_LSSTAT(1)
-  LsPnt p0 = ls_eval(0, q0g, q1g, q2g, jar, jv, D, nefc);
+  B2_LSSTAT(0) B2_LSSTAT(1)
+  LsPnt p0;
+  if (sizeof(real) == 4 && B2_LS_SKIP_P0 && slope0 < 0) {
+    // float32 builds: the point alpha = 0 needs no pass over the rows.  Its cost is the cost the Newton update just
+    // computed, its slope is grad.search, and because search solves H search = -grad its curvature search.H.search equals
+    // -slope: the first trial point is the full Newton step alpha = 1.  (The float64 builds keep MuJoCo's evaluation so
+    // that they reproduce the oracle digit for digit.)
+    p0.alpha = 0; p0.cost = cost0; p0.d1 = slope0; p0.d2 = -slope0;
+  } else {
+    B2_LSSTAT(1)
+    p0 = ls_eval(0, q0g, q1g, q2g, jar, jv, D, nefc);
+  }
   LsPnt p1 = ls_eval(p0.alpha - p0.d1 / p0.d2, q0g, q1g, q2g, jar, jv, D, nefc); ++nev;
   if (p0.cost < p1.cost) p1 = p0;
   if (fabs(p1.d1) < ls_gtol(p1, gtol)) return p1.alpha;
@@ -915,18 +929,20 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
       for (int i = B2_LANE; i < nv; i += B2_NLANE) search[i] = -tmp[i];
       B2_WSYNC();
       // -- line search  // @region ls_setup
-      real sn = 0, q1 = 0, q2 = 0;
+      real sn = 0, q1 = 0, q2 = 0, gs = 0;
       symv_global(M, nv, ld, search, Mv);
       B2_UNROLL1
       for (int i = B2_LANE; i < nv; i += B2_NLANE) {
         sn += search[i] * search[i];
         q1 += search[i] * (Ma[i] - qfs[i]);
         q2 += (real)0.5 * search[i] * Mv[i];
+        gs += search[i] * grad[i];
       }
-      sn = sqrt(b2_wsum(sn)); q1 = b2_wsum(q1); q2 = b2_wsum(q2);
+      sn = sqrt(b2_wsum(sn));
+      b2_wsum3(q1, q2, gs);
       rows_dot(jpool, rowinfo, runinfo, rundofs, nefc, search, jv, nullptr);
       B2_PH(5)
-      real alpha = linesearch(gauss, q1, q2, sn, tolerance, ls_tolerance, m.ls_iterations, scale, jar, jv, D, nefc);
+      real alpha = linesearch(gauss, q1, q2, sn, tolerance, ls_tolerance, m.ls_iterations, scale, jar, jv, D, nefc, cost, gs);
       B2_PH(6)
       if (alpha == 0) break;
       B2_UNROLL1
