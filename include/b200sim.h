@@ -241,6 +241,9 @@ const char* b2_last_error(void);
 /* sizeof checks for the FFI side */
 int b2_sizeof_model(void);
 int b2_sizeof_data(void);
+/* solver slot of the world with heaviest-first rank `rank` in a launch over `nworld` worlds (diagnostic: the scheduling
+ * map of k_order, exposed so that it can be checked on a machine without a GPU) */
+int b2_debug_solver_slot(int rank, int nworld);
 /* number of kernel launches enqueued by this library since load (diagnostic) */
 long long b2_launch_count(void);
 

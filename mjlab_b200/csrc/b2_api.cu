@@ -68,6 +68,16 @@ static __host__ __device__ inline int solve_grid(int n) {
   return g < B2_SOLVE_MAX_CTAS ? g : B2_SOLVE_MAX_CTAS;
 }
 
+// Rank p in the heaviest-first order -> solver slot (a permutation of [0, n) for every n; tests/test_abi.py checks it
+// through b2_debug_solver_slot).  Light ranks start at L0 = max(G, n - G): with n < 2G (small or odd batches) every rank past
+// the G heavy ones is "light".  The lightest world of all sits next to rank G-1, not next to rank 0: the first warps to come
+// free then have a small CTA-mate, and the medium-heavy world they pull fits beside it.
+static __host__ __device__ inline int solve_slot(int p, int n) {
+  const int G = solve_grid(n);
+  const int L0 = G > n - G ? G : n - G;
+  return p < G ? 2 * p : (p >= L0 ? 2 * (p - L0) + 1 : 2 * G + (p - G));
+}
+
 // Persistent warps: warp (CTA c, index i) starts on solver slot B2_WPB*c + i, then pulls the next unclaimed slot from the
 // launch's work counter until the list is empty, so a warp-slot never idles while worlds are waiting (with one world per
 // warp and two per CTA, the slot of a light world stayed blocked until its heavy CTA-mate was done).
@@ -140,10 +150,7 @@ __global__ void __launch_bounds__(1024) k_order(const KData d, int w0, int w1) {
     // heaviest worlds was that wait while they were paired with each other), so the first wave pairs the c-th heaviest
     // world with the c-th lightest; the warps of the light worlds are free within microseconds and take the remaining
     // worlds longest-first, which keeps the tail of the launch short.
-    int p = atomicAdd(&base[k], 1), n = w1 - w0, G = solve_grid(n);
-    // (the lightest world of all sits next to rank G-1, not next to rank 0: the first warps to come free then have a
-    // small CTA-mate, and the medium-heavy world they pull fits beside it)
-    int slot = p < G ? 2 * p : (p >= n - G ? 2 * (p - (n - G)) + 1 : 2 * G + (p - G));
+    int slot = solve_slot(atomicAdd(&base[k], 1), w1 - w0);
     order[w0 + slot] = w;   // slots [w0, w1) hold a permutation of the worlds [w0, w1)
   }
 }
@@ -248,6 +255,7 @@ extern "C" {
 
 int b2_abi_version(void) { return 1; }
 const char* b2_last_error(void) { return g_err; }
+int b2_debug_solver_slot(int rank, int nworld) { return solve_slot(rank, nworld); }
 int b2_sizeof_model(void) { return (int)sizeof(b2_model); }
 int b2_sizeof_data(void) { return (int)sizeof(b2_data); }
 long long b2_launch_count(void) { return g_launches; }

@@ -95,3 +95,19 @@ def test_env_requires_cuda():
   from mjlab_b200.actuators import IdealPdActuator
   with pytest.raises(RuntimeError):
     IdealPdActuator(2, 3, 1.0, 0.1, device="cpu")
+
+
+def test_solver_slot_map_is_a_permutation():
+  """k_order scatters the worlds (heaviest-first rank) onto solver slots; for EVERY batch size - odd, tiny, larger than
+  the resident grid - the map must be a permutation of [0, n), else a world is solved twice and another not at all."""
+  import ctypes
+  lib = E.load_library()
+  lib.b2_debug_solver_slot.argtypes = [ctypes.c_int, ctypes.c_int]
+  lib.b2_debug_solver_slot.restype = ctypes.c_int
+  for n in list(range(1, 130)) + [255, 256, 257, 2367, 2368, 2369, 2370, 4095, 4096, 4097, 8191, 8192]:
+    slots = sorted(lib.b2_debug_solver_slot(p, n) for p in range(n))
+    assert slots == list(range(n)), n
+  # first wave: the c-th heaviest world shares CTA c (slots 2c, 2c+1) with a light one
+  n = 4096
+  assert [lib.b2_debug_solver_slot(p, n) for p in (0, 1, 2)] == [0, 2, 4]
+  assert lib.b2_debug_solver_slot(n - 1, n) % 2 == 1 and lib.b2_debug_solver_slot(n - 1184, n) == 1

@@ -253,3 +253,21 @@ def test_solver_arena_contention_does_not_change_results():
   assert int(ref[4].max()) > 30
   for a, b in zip(ref, out):
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("nw", [1, 7, 33])
+def test_odd_world_counts(nw):
+  """Batch sizes that are odd / smaller than a CTA pair: every world is solved exactly once (scheduling map of k_order)."""
+  import mjlab_b200
+  m = mjlab_b200.load_model("go1_flat")
+  qpos, qvel, ctrl, xfrc = util.random_states(m, nw, seed=4)
+  sim = make_sim(m, nw)
+  load_state(sim, qpos, qvel, ctrl, xfrc)
+  for _ in range(3):
+    sim.step()
+  torch.cuda.synchronize()
+  ds = util.oracle_rollout(m, qpos, qvel, ctrl, xfrc, 3, 35, 300)
+  for w, d in enumerate(ds):
+    assert int(sim.data.ncon[w]) == len(d.contacts) and int(sim.data.nefc[w]) == d.nefc
+    assert relerr(sim.data.qpos[w].cpu().numpy(), d.qpos) < 3e-4
+    assert relerr(sim.data.qvel[w].cpu().numpy(), d.qvel) < 5e-3
