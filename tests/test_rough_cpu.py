@@ -168,3 +168,19 @@ def test_float_host_build_on_the_terrain_grid_stays_close():
       h.step()
   assert a.ncon.tolist() == b.ncon.tolist()
   assert np.abs(a.qpos - b.qpos).max() < 5e-5
+
+
+def test_rough_task_configs():
+  """Train: curriculum on the 10 x 20 grid; play: 5 x 5 random grid with the terrain-randomisation reset event as well."""
+  from mjlab_b200 import envcfg
+  from mjlab_b200.env import VelocityEnvCfg
+  train = envcfg.velocity_cfg(mjlab_b200.load_model("g1_rough"), "g1", play=False)
+  assert train.terrain_mode == 1 and train.terrain_origins.shape == (10, 20, 3) and train.terrain_half_size == 4.0
+  play = envcfg.velocity_cfg(mjlab_b200.load_model("g1_rough_play"), "g1", play=True)
+  assert play.terrain_mode == 3 and play.terrain_origins.shape == (5, 5, 3) and not play.push_enabled
+  flat = envcfg.velocity_cfg(mjlab_b200.load_model("g1_flat"), "g1")
+  assert flat.terrain_mode == 0 and flat.terrain_rows == 0
+  c = VelocityEnvCfg.from_task("Mjlab-Velocity-Rough-Unitree-G1", num_envs=8)
+  assert (c.robot, c.terrain) == ("g1", "rough")
+  with pytest.raises(ValueError):
+    VelocityEnvCfg.from_task("Mjlab-Velocity-Rough-Unitree-H1")
