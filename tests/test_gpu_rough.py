@@ -123,3 +123,27 @@ def test_rough_env_full_size_properties():
   g1 = D.contact_geom[w, : int(ncon[w]), 0].cpu().numpy()
   assert np.isin(g1, m.dyn_geom).all()
   assert torch.isfinite(D.qpos).all() and torch.isfinite(D.qvel).all()
+
+
+def test_rough_play_mode_randomizes_terrain():
+  """`play` on the rough task: 5 x 5 random grid, no pushes / noise, and the `randomize_terrain` reset event moves every
+  reset env to a uniformly drawn sub-terrain (taking effect at its next reset, as in the reference's event order)."""
+  from mjlab_b200.env import ManagerBasedRlEnv, VelocityEnvCfg
+  B = 64
+  env = ManagerBasedRlEnv(VelocityEnvCfg.from_task("Mjlab-Velocity-Rough-Unitree-G1", play=True, num_envs=B, seed=1), DEV)
+  cfg = env.vcfg
+  assert cfg.terrain_mode == 3 and cfg.terrain_origins.shape == (5, 5, 3) and not cfg.push_enabled and not cfg.enable_corruption
+  env.reset()
+  org = torch.as_tensor(cfg.terrain_origins, dtype=torch.float32, device=DEV)
+  ty0 = env._buf["terrain_type"].clone()
+  zero = torch.zeros(B, cfg.nj, device=DEV)
+  resets = 0
+  for _ in range(200):
+    obs, rew, term, trunc, extras = env.step(zero)
+    resets += int((term | trunc).sum())
+    lv, ty = env._buf["terrain_level"].long(), env._buf["terrain_type"].long()
+    assert torch.equal(env._buf["env_origins"], org[lv, ty])
+    assert torch.isfinite(obs["critic"]).all() and torch.isfinite(rew).all()
+  assert resets > 0                                   # the open-loop G1 tips over (see test_play_zero_agent)
+  assert int((env._buf["terrain_type"] != ty0).sum()) > 0
+  assert 0.0 <= extras["log"]["Curriculum/terrain_levels"] <= 4.0
