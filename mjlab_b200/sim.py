@@ -29,6 +29,7 @@ import torch
 
 from . import engine as E
 from . import mjcf
+from .nan_guard import NanGuard, NanGuardCfg
 
 _INTEGRATOR_MAP = {"euler": mjcf.INT_EULER, "implicitfast": mjcf.INT_IMPLICITFAST}
 _CONE_MAP = {"pyramidal": mjcf.CONE_PYRAMIDAL, "elliptic": mjcf.CONE_ELLIPTIC}
@@ -75,6 +76,7 @@ class SimulationCfg:
   export_efc_J: bool = False  # also write the dense constraint Jacobian to HBM every step (off on the hot path)
   contact_sensor_maxmatch: int = 64
   mujoco: MujocoCfg = field(default_factory=MujocoCfg)
+  nan_guard: NanGuardCfg = field(default_factory=NanGuardCfg)   # sim.py:97; off by default
 
 
 class TensorBridge:
@@ -246,6 +248,7 @@ class Simulation:
 
     self._model_bridge = TensorBridge(_ModelFields(self))
     self._data_bridge = TensorBridge(self._data_fields)
+    self.nan_guard = NanGuard(cfg.nan_guard, num_envs, model)   # sim.py:162
 
     self.use_cuda_graph = True
     self.step_graph = None
@@ -366,10 +369,11 @@ class Simulation:
       self._launch_forward()
 
   def step(self) -> None:
-    if self.use_cuda_graph and self.step_graph is not None:
-      self.step_graph.replay()
-    else:
-      self._launch_step()
+    with self.nan_guard.watch(self.data):      # sim.py:267-273; a no-op unless cfg.nan_guard.enabled
+      if self.use_cuda_graph and self.step_graph is not None:
+        self.step_graph.replay()
+      else:
+        self._launch_step()
 
   def reset(self, env_ids: torch.Tensor | None = None) -> None:
     if env_ids is None:

@@ -271,3 +271,28 @@ def test_odd_world_counts(nw):
     assert int(sim.data.ncon[w]) == len(d.contacts) and int(sim.data.nefc[w]) == d.nefc
     assert relerr(sim.data.qpos[w].cpu().numpy(), d.qpos) < 3e-4
     assert relerr(sim.data.qvel[w].cpu().numpy(), d.qvel) < 5e-3
+
+
+def test_nan_guard_dumps_on_device_nan(tmp_path):
+  """`SimulationCfg.nan_guard.enabled`: a NaN that enters one world's state is detected after the step, that world's
+  history is dumped, the other worlds carry on (NaN / Inf propagate, they are detected, not prevented: sim.py:267-273)."""
+  import mjlab_b200
+  from mjlab_b200.nan_guard import NanGuardCfg
+  from mjlab_b200.sim import MujocoCfg, Simulation, SimulationCfg
+  m = mjlab_b200.load_model("go1_flat")
+  cfg = SimulationCfg(nconmax=35, njmax=300, mujoco=MujocoCfg(timestep=0.005, iterations=10, ls_iterations=20),
+                      nan_guard=NanGuardCfg(enabled=True, buffer_size=4, output_dir=str(tmp_path), max_envs_to_dump=3))
+  sim = Simulation(8, cfg, m, "cuda:0")
+  qpos, qvel, ctrl, xfrc = util.random_states(m, 8, seed=2)
+  load_state(sim, qpos, qvel, ctrl, xfrc)
+  for _ in range(3):
+    sim.step()
+  assert not list(tmp_path.iterdir())
+  sim.data.qvel[5, 7] = float("nan")
+  sim.step()
+  dump = np.load(tmp_path / "nan_dump_latest.npz", allow_pickle=True)
+  meta = dump["_metadata"].item()
+  assert meta["nan_env_ids"] == [5] and meta["buffer_size"] == 4 and meta["detection_step"] == 4
+  assert np.isnan(dump["states_step_000003"][0]).any() and np.isfinite(dump["states_step_000002"]).all()
+  ok = [w for w in range(8) if w != 5]
+  assert torch.isfinite(sim.data.qpos[ok]).all() and torch.isfinite(sim.data.qvel[ok]).all()
