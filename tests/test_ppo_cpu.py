@@ -100,3 +100,33 @@ def test_gradient_all_reduce_averages_over_ranks():
   for g0, g1, r0, r1 in zip(l0, l1, a0, a1):
     np.testing.assert_allclose(r0, (g0 + g1) / 2, rtol=1e-6)
     np.testing.assert_allclose(r1, r0, rtol=0, atol=0)
+
+
+def test_policy_export_roundtrip(tmp_path):
+  """TorchScript export of actor(normalizer(obs)) reproduces the live policy; the metadata side-car carries the reference's
+  keys (rl/exporter_utils.py:23-62).  The env is a stand-in with the attributes the exporter reads."""
+  import json
+  from types import SimpleNamespace as NS
+  import mjlab_b200
+  from mjlab_b200 import envcfg, exporter
+  m = mjlab_b200.load_model("go1_flat")
+  cfg = envcfg.velocity_cfg(m, "go1")
+  env = NS(scene={"robot": NS(joint_names=[n.removeprefix("robot/") for n in cfg.joint_names])}, sim=NS(mj_model=m), vcfg=cfg,
+           command_manager=NS(active_terms=["twist"]), observation_manager=NS(active_terms={"policy": ["base_lin_vel", "actions"]}))
+  torch.manual_seed(0)
+  ac = ppo.ActorCritic(cfg.n_obs_policy, cfg.n_obs_critic, cfg.nj, ppo.PpoCfg())
+  ac.update_normalization(torch.randn(256, cfg.n_obs_policy) * 2 + 1, torch.randn(256, cfg.n_obs_critic))
+  out = exporter.export_policy_as_jit(ac, env, str(tmp_path), run_path="local/test")
+  loaded = torch.jit.load(out)
+  x = torch.randn(5, cfg.n_obs_policy)
+  ac.eval()
+  with torch.no_grad():
+    np.testing.assert_allclose(loaded(x).numpy(), ac.act_inference(x).numpy(), rtol=1e-5, atol=1e-6)
+  meta = json.load(open(out.replace(".pt", ".json")))
+  assert set(meta) == {"run_path", "joint_names", "joint_stiffness", "joint_damping", "default_joint_pos", "command_names",
+                       "observation_names", "action_scale"}
+  assert len(meta["joint_names"].split(",")) == cfg.nj == len(meta["joint_stiffness"].split(","))
+  kp = np.asarray(m.actuator_gainprm)[cfg.ctrl_ids, 0]
+  np.testing.assert_allclose([float(v) for v in meta["joint_stiffness"].split(",")], kp, atol=1e-3)
+  with pytest.raises(RuntimeError):
+    exporter.export_policy_as_onnx(ac, env, str(tmp_path))
