@@ -41,23 +41,22 @@ def get_base_metadata(env, run_path: str) -> dict:
 
 
 class _PolicyModule(nn.Module):
-  """actor(normalizer(obs)): what `_OnnxPolicyExporter` traces."""
+  """obs -> actions = actor(normalizer(obs)): what `_OnnxPolicyExporter` traces (the network's internal padding of the
+  observation / action widths stays inside)."""
 
   def __init__(self, actor_critic):
     super().__init__()
     import copy
-    self.normalizer = copy.deepcopy(actor_critic.actor_norm)
-    self.actor = copy.deepcopy(actor_critic.actor)
+    self.ac = copy.deepcopy(actor_critic)
 
   def forward(self, obs: torch.Tensor) -> torch.Tensor:
-    return self.actor(self.normalizer(obs))
+    return self.ac.act_inference(obs)
 
 
 def export_policy_as_jit(actor_critic, env, path: str, run_path: str = "", filename: str = "policy.pt") -> str:
   os.makedirs(path, exist_ok=True)
   mod = _PolicyModule(actor_critic).to("cpu").eval()
-  n_obs = mod.actor[0].in_features
-  traced = torch.jit.trace(mod, torch.zeros(1, n_obs))
+  traced = torch.jit.trace(mod, torch.zeros(1, actor_critic.n_actor_obs))
   out = os.path.join(path, filename)
   traced.save(out)
   meta = get_base_metadata(env, run_path)
@@ -75,7 +74,7 @@ def export_policy_as_onnx(actor_critic, env, path: str, run_path: str = "", file
   os.makedirs(path, exist_ok=True)
   mod = _PolicyModule(actor_critic).to("cpu").eval()
   out = os.path.join(path, filename)
-  torch.onnx.export(mod, torch.zeros(1, mod.actor[0].in_features), out, input_names=["obs"], output_names=["actions"], dynamo=False)
+  torch.onnx.export(mod, torch.zeros(1, actor_critic.n_actor_obs), out, input_names=["obs"], output_names=["actions"], dynamo=False)
   model = onnx.load(out)
   for k, v in get_base_metadata(env, run_path).items():
     entry = onnx.StringStringEntryProto()

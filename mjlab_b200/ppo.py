@@ -98,31 +98,52 @@ def _mlp(n_in: int, hidden: tuple, n_out: int) -> nn.Sequential:
   return nn.Sequential(*layers)
 
 
+def _pad4(n: int) -> int:
+  return (n + 3) & ~3
+
+
 class ActorCritic(nn.Module):
+  """rsl_rl's ActorCritic (MLP actor + MLP critic, state-independent action std, empirical observation normalisation).
+
+  The first and last layers are built on feature counts rounded up to a multiple of 4 (99 -> 100 observations, 29 -> 32
+  actions): cuBLAS only takes its TMA / vectorised kernels when the leading dimensions are 16-byte aligned, and the
+  `align1` fallbacks were 8 of the 31 ms of a PPO update.  The extra inputs are always zero and the extra outputs are never
+  read, so the function computed (and every gradient that matters) is that of the unpadded network."""
+
   def __init__(self, n_actor_obs: int, n_critic_obs: int, n_actions: int, cfg: PpoCfg):
     super().__init__()
-    self.actor = _mlp(n_actor_obs, cfg.actor_hidden_dims, n_actions)
-    self.critic = _mlp(n_critic_obs, cfg.critic_hidden_dims, 1)
-    self.actor_norm = EmpiricalNormalization(n_actor_obs) if cfg.actor_obs_normalization else nn.Identity()
-    self.critic_norm = EmpiricalNormalization(n_critic_obs) if cfg.critic_obs_normalization else nn.Identity()
+    self.n_actor_obs, self.n_critic_obs, self.n_actions = n_actor_obs, n_critic_obs, n_actions
+    self.w_actor_obs, self.w_critic_obs, self.w_actions = _pad4(n_actor_obs), _pad4(n_critic_obs), _pad4(n_actions)
+    self.actor = _mlp(self.w_actor_obs, cfg.actor_hidden_dims, self.w_actions)
+    self.critic = _mlp(self.w_critic_obs, cfg.critic_hidden_dims, 4)
+    self.actor_norm = EmpiricalNormalization(self.w_actor_obs) if cfg.actor_obs_normalization else nn.Identity()
+    self.critic_norm = EmpiricalNormalization(self.w_critic_obs) if cfg.critic_obs_normalization else nn.Identity()
     self.std = nn.Parameter(cfg.init_noise_std * torch.ones(n_actions))
 
+  @staticmethod
+  def _fit(x: torch.Tensor, width: int) -> torch.Tensor:
+    return x if x.shape[-1] == width else nn.functional.pad(x, (0, width - x.shape[-1]))
+
+  def actor_mean(self, obs: torch.Tensor) -> torch.Tensor:
+    """obs: [.., n_actor_obs] or already padded to w_actor_obs."""
+    return self.actor(self.actor_norm(self._fit(obs, self.w_actor_obs)))[..., : self.n_actions]
+
   def distribution(self, obs: torch.Tensor) -> torch.distributions.Normal:
-    mean = self.actor(self.actor_norm(obs))
+    mean = self.actor_mean(obs)
     return torch.distributions.Normal(mean, self.std.expand_as(mean))
 
   def act_inference(self, obs: torch.Tensor) -> torch.Tensor:
-    return self.actor(self.actor_norm(obs))
+    return self.actor_mean(obs)
 
   def evaluate(self, critic_obs: torch.Tensor) -> torch.Tensor:
-    return self.critic(self.critic_norm(critic_obs))
+    return self.critic(self.critic_norm(self._fit(critic_obs, self.w_critic_obs)))[..., :1]
 
   @torch.no_grad()
   def update_normalization(self, obs: torch.Tensor, critic_obs: torch.Tensor) -> None:
     if isinstance(self.actor_norm, EmpiricalNormalization):
-      self.actor_norm.update(obs)
+      self.actor_norm.update(self._fit(obs, self.w_actor_obs))
     if isinstance(self.critic_norm, EmpiricalNormalization):
-      self.critic_norm.update(critic_obs)
+      self.critic_norm.update(self._fit(critic_obs, self.w_critic_obs))
 
 
 def reduce_gradients(params, world_size: int) -> None:
@@ -278,14 +299,19 @@ class OnPolicyRunner:
     cfg, st, ro = self.cfg, self.st, self.ro
     N = cfg.num_steps_per_env * self.env.num_envs
     no, nc, na = self.n_obs, self.n_critic, self.n_act
-    cols = [("obs", no), ("critic", nc), ("actions", na), ("mu", na), ("sigma", na), ("logp", 1), ("values", 1)]
-    width = sum(w for _, w in cols) + 2
+    pol = self.policy
+    # column blocks start on multiples of 4 floats and the observation blocks have the networks' padded widths (their
+    # padding columns stay zero): every view handed to a GEMM is 16-byte aligned
+    cols = [("obs", no, pol.w_actor_obs), ("critic", nc, pol.w_critic_obs), ("actions", na, pol.w_actions), ("mu", na, pol.w_actions),
+            ("sigma", na, pol.w_actions), ("logp", 1, 1), ("values", 1, 1)]
+    width = sum(w for _, _, w in cols) + 2
     if getattr(self, "_pack", None) is None or self._pack.shape != (N, width):
       self._pack = torch.zeros(N, width, device=self.device)
     off, o = {}, 0
-    for k, w in cols:
-      self._pack[:, o:o + w] = st[k].reshape(N, w)
-      off[k] = (o, o + w)
+    for k, n_real, w in cols:
+      self._pack[:, o:o + n_real] = st[k].reshape(N, n_real)
+      off[k] = (o, o + n_real)
+      off[k + "_padded"] = (o, o + w)
       o += w
     self._pack[:, o] = ro["returns"].reshape(N)
     self._pack[:, o + 1] = ro["advantages"].reshape(N)
@@ -300,8 +326,8 @@ class OnPolicyRunner:
       for i in range(cfg.num_mini_batches):
         b = self._pack[self._perm[e, i * mb:(i + 1) * mb]]
         col = lambda k: b[:, off[k][0]:off[k][1]]  # noqa: E731
-        mu = self.policy.actor(self.policy.actor_norm(col("obs")))
-        value = self.policy.evaluate(col("critic")).squeeze(-1)
+        mu = pol.actor_mean(col("obs_padded"))
+        value = pol.evaluate(col("critic_padded")).squeeze(-1)
         std = self.policy.std
         log_std = std.log()
         logp = (-0.5 * ((col("actions") - mu) / std).square() - log_std).sum(-1) - na * half_log_2pi
