@@ -1,5 +1,10 @@
-import sys, torch
-sys.path.insert(0, '/root/repo')
+"""Kernel-level profile of one PPO update (torch.profiler, eager launches) on the GPU box:  python tools/profile_ppo_update.py"""
+import sys
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 from mjlab_b200.env import ManagerBasedRlEnv, VelocityEnvCfg
 from mjlab_b200.ppo import OnPolicyRunner, PpoCfg
 from mjlab_b200.vecenv import RslRlVecEnvWrapper
