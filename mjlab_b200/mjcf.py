@@ -846,6 +846,68 @@ def _infer_inertial(b: SBody):
 # ---------------------------------------------------------------------------
 # Compile: Spec -> ModelDesc.
 # ---------------------------------------------------------------------------
+def collision_tables(m: "ModelDesc", excl: set) -> None:
+  """Static-geom poses, the geom field and the candidate pair list of a model whose body / geom arrays are filled in
+  (`excl`: set of excluded (body, body) pairs, lower id first).  Shared by `_compile` and `tools/export_mjmodel.py`."""
+  nbody, ngeom = m.nbody, m.ngeom
+  body_weldid, body_mocapid, body_parentid = np.asarray(m.body_weldid), np.asarray(m.body_mocapid), np.asarray(m.body_parentid)
+  body_pos, body_quat = np.asarray(m.body_pos, float), np.asarray(m.body_quat, float)
+  # static geometry: geoms of bodies welded to the world never move, so their world pose is a model constant
+  # (`sgeom_xpos/xmat`) and the kernels only run forward kinematics for `dyn_geom`
+  gb, gw = m.geom_bodyid, body_weldid
+  sxpos, sxquat = np.zeros((nbody, 3)), np.tile([1.0, 0, 0, 0], (nbody, 1))
+  for b in range(1, nbody):
+    if gw[b] == 0 and body_mocapid[b] < 0:
+      pb = body_parentid[b]
+      sxpos[b] = sxpos[pb] + quat_to_mat(sxquat[pb]) @ body_pos[b]
+      sxquat[b] = quat_mul(sxquat[pb], body_quat[b])
+  static = np.array([gw[gb[g]] == 0 and body_mocapid[gb[g]] < 0 for g in range(ngeom)], bool) if ngeom else np.zeros(0, bool)
+  m.dyn_geom = np.flatnonzero(~static).astype(np.int32)
+  m.ndyn = len(m.dyn_geom)
+  m.sgeom_xpos, m.sgeom_xmat = np.zeros((ngeom, 3)), np.zeros((ngeom, 9))
+  for g in np.flatnonzero(static):
+    Rb = quat_to_mat(sxquat[gb[g]])
+    m.sgeom_xpos[g] = sxpos[gb[g]] + Rb @ m.geom_pos[g]
+    m.sgeom_xmat[g] = quat_to_mat(quat_mul(sxquat[gb[g]], m.geom_quat[g])).reshape(9)
+
+  # geom field: many static, bounded, collidable geoms (terrain boxes) are not enumerated pair by pair; they go into a
+  # uniform xy grid (cell -> field geoms whose AABB overlaps it) that each moving "query" geom looks up at run time
+  collidable = (m.geom_contype != 0) | (m.geom_conaffinity != 0)
+  bounded = np.isin(m.geom_type, (GEOM_SPHERE, GEOM_CAPSULE, GEOM_BOX))
+  fld = np.flatnonzero(static & collidable & bounded)
+  if len(fld) < FIELD_MIN_GEOMS:
+    fld = fld[:0]
+  in_field = np.zeros(ngeom, bool)
+  in_field[fld] = True
+  _build_geom_field(m, fld, body_parentid, excl)
+
+  pairs = []
+  active = [g for g in range(ngeom) if collidable[g] and not in_field[g]]
+  for ia, g1 in enumerate(active):
+    for g2 in active[ia + 1:]:
+      b1, b2 = gb[g1], gb[g2]
+      ct1, ca1, ct2, ca2 = m.geom_contype[g1], m.geom_conaffinity[g1], m.geom_contype[g2], m.geom_conaffinity[g2]
+      if not ((ct1 & ca2) or (ct2 & ca1)):
+        continue
+      w1, w2 = gw[b1], gw[b2]
+      if w1 == w2:
+        continue
+      wp1, wp2 = gw[body_parentid[w1]], gw[body_parentid[w2]]
+      if w1 != 0 and w2 != 0 and (w1 == wp2 or w2 == wp1):
+        continue
+      if (min(b1, b2), max(b1, b2)) in excl:
+        continue
+      t1, t2 = m.geom_type[g1], m.geom_type[g2]
+      if t1 in (GEOM_MESH, GEOM_HFIELD) or t2 in (GEOM_MESH, GEOM_HFIELD):
+        continue
+      if t1 == GEOM_PLANE and t2 == GEOM_PLANE:
+        continue
+      # contact.geom1 carries the lower geom-type enum (MuJoCo convention)
+      pairs.append((g1, g2) if t1 <= t2 else (g2, g1))
+  m.pair_geom = np.array(pairs, np.int32).reshape(-1, 2)
+  m.npair = len(pairs)
+
+
 FIELD_MIN_GEOMS = 16     # fewer static geoms than this stay ordinary candidate pairs
 FIELD_CELL = 1.0         # grid cell edge [m]
 
@@ -1207,60 +1269,7 @@ def _compile(spec: Spec) -> ModelDesc:
     ia, ib = body_names.index(a), body_names.index(b)
     excl.add((min(ia, ib), max(ia, ib)))
   m.exclude_pairs = np.array(sorted(excl), np.int32).reshape(-1, 2)
-  # static geometry: geoms of bodies welded to the world never move, so their world pose is a model constant
-  # (`sgeom_xpos/xmat`) and the kernels only run forward kinematics for `dyn_geom`
-  gb, gw = m.geom_bodyid, body_weldid
-  sxpos, sxquat = np.zeros((nbody, 3)), np.tile([1.0, 0, 0, 0], (nbody, 1))
-  for b in range(1, nbody):
-    if gw[b] == 0 and body_mocapid[b] < 0:
-      pb = body_parentid[b]
-      sxpos[b] = sxpos[pb] + quat_to_mat(sxquat[pb]) @ body_pos[b]
-      sxquat[b] = quat_mul(sxquat[pb], body_quat[b])
-  static = np.array([gw[gb[g]] == 0 and body_mocapid[gb[g]] < 0 for g in range(ngeom)], bool) if ngeom else np.zeros(0, bool)
-  m.dyn_geom = np.flatnonzero(~static).astype(np.int32)
-  m.ndyn = len(m.dyn_geom)
-  m.sgeom_xpos, m.sgeom_xmat = np.zeros((ngeom, 3)), np.zeros((ngeom, 9))
-  for g in np.flatnonzero(static):
-    Rb = quat_to_mat(sxquat[gb[g]])
-    m.sgeom_xpos[g] = sxpos[gb[g]] + Rb @ m.geom_pos[g]
-    m.sgeom_xmat[g] = quat_to_mat(quat_mul(sxquat[gb[g]], m.geom_quat[g])).reshape(9)
-
-  # geom field: many static, bounded, collidable geoms (terrain boxes) are not enumerated pair by pair; they go into a
-  # uniform xy grid (cell -> field geoms whose AABB overlaps it) that each moving "query" geom looks up at run time
-  collidable = (m.geom_contype != 0) | (m.geom_conaffinity != 0)
-  bounded = np.isin(m.geom_type, (GEOM_SPHERE, GEOM_CAPSULE, GEOM_BOX))
-  fld = np.flatnonzero(static & collidable & bounded)
-  if len(fld) < FIELD_MIN_GEOMS:
-    fld = fld[:0]
-  in_field = np.zeros(ngeom, bool)
-  in_field[fld] = True
-  _build_geom_field(m, fld, body_parentid, excl)
-
-  pairs = []
-  active = [g for g in range(ngeom) if collidable[g] and not in_field[g]]
-  for ia, g1 in enumerate(active):
-    for g2 in active[ia + 1:]:
-      b1, b2 = gb[g1], gb[g2]
-      ct1, ca1, ct2, ca2 = m.geom_contype[g1], m.geom_conaffinity[g1], m.geom_contype[g2], m.geom_conaffinity[g2]
-      if not ((ct1 & ca2) or (ct2 & ca1)):
-        continue
-      w1, w2 = gw[b1], gw[b2]
-      if w1 == w2:
-        continue
-      wp1, wp2 = gw[body_parentid[w1]], gw[body_parentid[w2]]
-      if w1 != 0 and w2 != 0 and (w1 == wp2 or w2 == wp1):
-        continue
-      if (min(b1, b2), max(b1, b2)) in excl:
-        continue
-      t1, t2 = m.geom_type[g1], m.geom_type[g2]
-      if t1 in (GEOM_MESH, GEOM_HFIELD) or t2 in (GEOM_MESH, GEOM_HFIELD):
-        continue
-      if t1 == GEOM_PLANE and t2 == GEOM_PLANE:
-        continue
-      # contact.geom1 carries the lower geom-type enum (MuJoCo convention)
-      pairs.append((g1, g2) if t1 <= t2 else (g2, g1))
-  m.pair_geom = np.array(pairs, np.int32).reshape(-1, 2)
-  m.npair = len(pairs)
+  collision_tables(m, excl)
   _setconst(m)
   return m
 

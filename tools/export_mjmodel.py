@@ -1,6 +1,10 @@
 """Box-side helper (needs `mujoco`, which this image does not have): dump a compiled mujoco.MjModel into the
 array container `mjlab_b200.mjcf.ModelDesc` uses, so models compiled by MuJoCo itself can be fed to the
-engine and cross-checked against `mjlab_b200.mjcf`'s own compiler.  UNTESTED here (no mujoco wheel)."""
+engine and cross-checked against `mjlab_b200.mjcf`'s own compiler.  The array copy is UNTESTED here (no mujoco wheel); the
+collision tables (static-geom poses, geom field, candidate pairs) come from the same `collision_tables` the compiler uses.
+
+    python tools/export_mjmodel.py scene.xml out.npz        # on a box with MuJoCo
+"""
 import sys
 
 import numpy as np
@@ -8,7 +12,7 @@ import numpy as np
 
 def export(mj_model, path):
   import mujoco  # noqa: F401  (only available where MuJoCo is installed)
-  from mjlab_b200.mjcf import ModelDesc, _setconst
+  from mjlab_b200.mjcf import ModelDesc, collision_tables
 
   m = ModelDesc()
   ints = ["nq", "nv", "nu", "nbody", "njnt", "ngeom", "nsite", "nsensor", "nsensordata", "nmocap", "nkey"]
@@ -40,10 +44,20 @@ def export(mj_model, path):
   m.opt_tolerance, m.opt_ls_tolerance, m.opt_impratio = float(o.tolerance), float(o.ls_tolerance), float(o.impratio)
   m.opt_disableflags = int(o.disableflags)
   m.stat_meaninertia = float(mj_model.stat.meaninertia)
-  m.exclude_pairs = np.zeros((0, 2), np.int32)
-  raise NotImplementedError("pair_geom: run mjlab_b200.mjcf's pair filter on the exported arrays (TODO on the box)")
+  # <exclude> body pairs: MuJoCo stores them as signatures (body1 << 16) + body2
+  sig = np.asarray(getattr(mj_model, "exclude_signature", np.zeros(0, np.int64))).astype(np.int64)
+  excl = {(int(min(x >> 16, x & 0xFFFF)), int(max(x >> 16, x & 0xFFFF))) for x in sig}
+  m.exclude_pairs = np.array(sorted(excl), np.int32).reshape(-1, 2)
+  collision_tables(m, excl)
+  m.save(path)
+  return m
 
 
 if __name__ == "__main__":
-  print(__doc__)
-  sys.exit(0)
+  if len(sys.argv) != 3:
+    print(__doc__)
+    sys.exit(0)
+  import mujoco
+  from pathlib import Path
+  sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+  export(mujoco.MjModel.from_xml_path(sys.argv[1]), sys.argv[2])
