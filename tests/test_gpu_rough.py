@@ -147,3 +147,75 @@ def test_rough_play_mode_randomizes_terrain():
   assert resets > 0                                   # the open-loop G1 tips over (see test_play_zero_agent)
   assert int((env._buf["terrain_type"] != ty0).sum()) > 0
   assert 0.0 <= extras["log"]["Curriculum/terrain_levels"] <= 4.0
+
+
+def test_rough_env_step_closed_loop_matches_oracles():
+  """env.step() on the terrain (graph replay, resets with the terrain-level curriculum, forward after resets) against
+  oracle physics (numpy, float64, incl. the geom field and box contacts) + oracle env, step by step."""
+  from mjlab_b200 import envabi as A
+  from oracle import envstep as OE
+  from tests.test_gpu_env import _batch, _scatter, make_env
+  B, T = 4, 4
+  env = make_env("g1", B, terrain="rough", seed=11)
+  m, cfg = env.sim.mj_model, env.vcfg
+  cfg.max_episode_length = 3
+  A.fill_params(env._ce, cfg)
+  env._capture()
+  s = OE.make_state(cfg, B, env._buf["env_origins"].cpu().numpy())
+  s.terrain_level[:] = env._buf["terrain_level"].cpu().numpy()
+  s.terrain_type[:] = env._buf["terrain_type"].cpu().numpy()
+  s.push_time_left[:] = env._buf["push_time_left"].cpu().numpy()
+  ds = [O.Data(m) for _ in range(B)]
+  for x in ds:
+    O.forward(m, x, 35, 300)
+  obs, _ = env.reset()
+  d = _batch(ds, m)
+  s.reset_buf[:] = True
+  s.log_env[:] = 0
+  u = OE.draws(cfg.seed, B, 0)
+  OE.reset_idx(cfg, m, s, d, np.arange(B), u)
+  _scatter(ds, d)
+  for x in ds:
+    O.forward(m, x, 35, 300)
+  d = _batch(ds, m)
+  OE.observations(cfg, s, d, OE.root_kinematics(cfg, d), u)
+  torch.cuda.synchronize()
+  # the first reset ran the curriculum against the construction pose (reference behaviour): levels and origins agree
+  np.testing.assert_array_equal(env._buf["terrain_level"].cpu().numpy(), s.terrain_level)
+  np.testing.assert_allclose(env._buf["env_origins"].cpu().numpy(), s.env_origins, rtol=0, atol=1e-6)
+  np.testing.assert_allclose(env.sim.data.qpos.cpu().numpy(), d.qpos, rtol=1e-5, atol=2e-5)
+  np.testing.assert_allclose(obs["critic"].cpu().numpy(), s.obs_critic, rtol=2e-3, atol=2e-3)
+  rng = np.random.default_rng(5)
+  resets = 0
+  for t in range(T):
+    a = rng.uniform(-1, 1, (B, cfg.nj)).astype(np.float32)
+    obs, rew, term, trunc, extras = env.step(torch.as_tensor(a, device=DEV))
+    u = OE.draws(cfg.seed, B, s.step_counter)
+    d = _batch(ds, m)
+    OE.apply_action(cfg, s, d, a)
+    _scatter(ds, d)
+    for k in range(4):
+      for x in ds:
+        O.step(m, x, 35, 300)
+      d = _batch(ds, m)
+      OE.update_air_time(cfg, s, d.sensordata.astype(np.float32), d.time)
+    OE.post(cfg, m, s, d, u=u)
+    _scatter(ds, d)
+    if s.reset_buf.any():
+      for x in ds:
+        O.forward(m, x, 35, 300)
+      d = _batch(ds, m)
+    OE.obs_stage(cfg, m, s, d, u=u)
+    _scatter(ds, d)
+    torch.cuda.synchronize()
+    resets += int(s.reset_buf.sum())
+    np.testing.assert_array_equal(term.cpu().numpy(), s.terminated)
+    np.testing.assert_array_equal(trunc.cpu().numpy(), s.time_outs)
+    np.testing.assert_array_equal(env._buf["terrain_level"].cpu().numpy(), s.terrain_level)
+    np.testing.assert_allclose(env._buf["env_origins"].cpu().numpy(), s.env_origins, rtol=0, atol=1e-6)
+    np.testing.assert_allclose(rew.cpu().numpy(), s.reward, rtol=5e-3, atol=3e-4)
+    np.testing.assert_allclose(env.sim.data.qpos.cpu().numpy(), d.qpos, rtol=1e-3, atol=2e-4)
+    np.testing.assert_allclose(obs["critic"].cpu().numpy(), s.obs_critic, rtol=2e-2, atol=1e-2)
+    assert extras["log"]["Episode/num_resets"] == float(s.reset_buf.sum())
+    assert abs(extras["log"]["Curriculum/terrain_levels"] - float(s.terrain_level.mean())) < 1e-5
+  assert resets >= B           # max_episode_length 3: every env timed out once and went through the curriculum
