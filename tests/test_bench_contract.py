@@ -1,0 +1,24 @@
+"""bench.py's reference (CPU) arm runs without a GPU: check the JSON contract of the line it prints."""
+import json
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_reference_arm_prints_one_contract_line():
+  out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+  assert out.returncode == 0, out.stderr[-2000:]
+  lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+  assert len(lines) == 1
+  j = json.loads(lines[0])
+  assert j["impl"] == "reference" and j["metric"] == "env-steps/s" and j["unit"] == "env-steps/s"
+  assert j["n_gpus"] == 1 and j["steps"] == 1 and j["warmup"] == 1 and j["higher_is_better"] is True
+  assert j["scaling"] == "weak" and j["vs_baseline"] is None and j["data"] == "synthetic" and j["dtype"] == "f64"
+  assert j["value"] > 0 and j["ms_per_step"] > 0 and "workload" in j["config"] and "model" not in j["config"]
+  cb = j["cpu_baseline"]
+  assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == j["value"] and cb["sample"]
+  e = j["e2e"]
+  assert e["value"] == j["value"] and e["unit"] == j["unit"] and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
