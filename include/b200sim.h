@@ -208,6 +208,10 @@ enum b2_di {
                               long-running worlds start at once and do not stretch the kernel's tail); internal */
   B2_DI_SOLVE_NEXT,        /* 1: element [w0] is the work counter of the solver launch over worlds [w0, w1): its warps pull
                               solver slots from it until the list is empty (set by the ordering kernel); internal */
+  B2_DI_SOLVE_RING,        /* 1: elements [w0, w1): the worlds of that launch in the order their solve finished (-1 = not yet);
+                              warps that find the solver queue empty take the sensor / integration stage of finished worlds
+                              from here instead of idling through the launch's tail; internal */
+  B2_DI_SOLVE_CTR,         /* 4: row w0 = {worlds solved, next ring entry to post-process, -, -} of that launch; internal */
   B2_DI_COUNT
 };
 

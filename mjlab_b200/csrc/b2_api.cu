@@ -28,9 +28,14 @@ static_assert(sizeof(KEnv) == sizeof(b2_env), "KEnv must mirror b2_env");
 #ifndef B2_SOLVE_MINB
 #define B2_SOLVE_MINB 8
 #endif
+#ifndef B2_ORDER_MODE_DEFAULT
+#define B2_ORDER_MODE_DEFAULT 0
+#endif
 
-static char g_err[512] = "";
-static long long g_launches = 0;
+// Error text and the launch counter are per host thread (one host thread drives one GPU, sim.py one process per GPU; a
+// process that drives several devices from several threads keeps their errors apart).
+static thread_local char g_err[512] = "";
+static thread_local long long g_launches = 0;
 
 static int fail(const char* fmt, ...) {
   va_list ap;
@@ -56,24 +61,26 @@ __global__ void __launch_bounds__(B2_SMOOTH_WPB * 32) k_smooth(const KModel m, c
 __device__ unsigned long long g_tim[3 * 16384];
 extern "C" int b2_debug_lsstat(unsigned long long* out) { return (int)cudaMemcpyFromSymbol(out, g_lsstat, sizeof(unsigned long long) * 8); }
 extern "C" int b2_debug_phases(unsigned long long* out, int n) { return (int)cudaMemcpyFromSymbol(out, g_phase, sizeof(unsigned long long) * 8 * n); }
+extern "C" int b2_debug_smooth_phases(unsigned long long* out, int n) { return (int)cudaMemcpyFromSymbol(out, g_sphase, sizeof(unsigned long long) * 8 * n); }
 __device__ __forceinline__ unsigned long long b2_gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ unsigned b2_smid() { unsigned s; asm volatile("mov.u32 %0, %%smid;" : "=r"(s)); return s; }
 extern "C" int b2_debug_timing(unsigned long long* out, int n) { return (int)cudaMemcpyFromSymbol(out, g_tim, sizeof(unsigned long long) * 3 * n); }
 #endif
 
-// Number of solver CTAs for n worlds: all resident at once (B2_SOLVE_MINB per SM), each warp then pulls further worlds.
-#define B2_SOLVE_MAX_CTAS (148 * B2_SOLVE_MINB)
-static __host__ __device__ inline int solve_grid(int n) {
+// Number of solver CTAs for n worlds: all resident at once (the CTAs per SM the occupancy calculator grants, times the
+// device's SM count - both queried in b2_check), each warp then pulls further worlds.  `cap` = that product.
+#define B2_SOLVE_DEFAULT_CTAS (148 * B2_SOLVE_MINB)   // B200: 148 SMs; used until b2_check has queried the device
+static __host__ __device__ inline int solve_grid(int n, int cap) {
   int g = (n + B2_WPB - 1) / B2_WPB;
-  return g < B2_SOLVE_MAX_CTAS ? g : B2_SOLVE_MAX_CTAS;
+  return g < cap ? g : cap;
 }
 
 // Rank p in the heaviest-first order -> solver slot (a permutation of [0, n) for every n; tests/test_abi.py checks it
 // through b2_debug_solver_slot).  Light ranks start at L0 = max(G, n - G): with n < 2G (small or odd batches) every rank past
 // the G heavy ones is "light".  The lightest world of all sits next to rank G-1, not next to rank 0: the first warps to come
 // free then have a small CTA-mate, and the medium-heavy world they pull fits beside it.
-static __host__ __device__ inline int solve_slot(int p, int n) {
-  const int G = solve_grid(n);
+static __host__ __device__ inline int solve_slot(int p, int n, int cap) {
+  const int G = solve_grid(n, cap);
   const int L0 = G > n - G ? G : n - G;
   return p < G ? 2 * p : (p >= L0 ? 2 * (p - L0) + 1 : 2 * G + (p - G));
 }
@@ -81,7 +88,19 @@ static __host__ __device__ inline int solve_slot(int p, int n) {
 // Persistent warps: warp (CTA c, index i) starts on solver slot B2_WPB*c + i, then pulls the next unclaimed slot from the
 // launch's work counter until the list is empty, so a warp-slot never idles while worlds are waiting (with one world per
 // warp and two per CTA, the slot of a light world stayed blocked until its heavy CTA-mate was done).
-__global__ void __launch_bounds__(B2_WPB * 32, B2_SOLVE_MINB) k_solve(const KModel m, const KData d, const SolveSmem L, const unsigned char* mask, const int* gate, int w0, int w1) {
+//
+// post_mode != 0 (1: forward, 2: step with integration; EXPERIMENT, B200SIM_FUSE_POST=1, measured slower - 0.67 ms against
+// 0.42 + 0.10 ms for the two launches, profiles/r02_fused_post_experiment.txt: the sensor code evicts the Newton loop from
+// the instruction caches of exactly the warps that set the launch's duration): the sensor / integration stage runs INSIDE
+// this launch.  The span of
+// the solver is the latency of its heaviest worlds and for its last ~40 % most warp slots are empty (per-world timeline,
+// profiles/r02_timeline.txt), while the old separate k_post launch was one latency-bound wave of its own.  Every solved world
+// is published in a ring (B2_DI_SOLVE_RING, release / acquire through __threadfence); a warp that finds the solver queue
+// empty claims ring entries in order and runs post_world for them - on worlds that finished long ago while the heavy ones
+// are still iterating - so the sensor stage fills the solver's tail instead of following it.  A claimed entry is waited
+// for only when all earlier-finished worlds are already taken, i.e. at the very end of the launch.  All CTAs are resident
+// (grid <= SMs x occupancy), so every claimed entry is eventually produced.
+__global__ void __launch_bounds__(B2_WPB * 32, B2_SOLVE_MINB) k_solve(const KModel m, const KData d, const SolveSmem L, const PostSmem LP, int post_mode, const unsigned char* mask, const int* gate, int w0, int w1) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   real* smem = reinterpret_cast<real*>(smem_raw);
   // [fixed part of world 0 | ... | fixed part of world B2_WPB-1 | row arena | arena control word]
@@ -93,6 +112,8 @@ __global__ void __launch_bounds__(B2_WPB * 32, B2_SOLVE_MINB) k_solve(const KMod
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = w1 - w0;
   int* next = d.di[B2_DI_SOLVE_NEXT] + w0;
+  int* ring = d.di[B2_DI_SOLVE_RING] + w0;
+  int* ctr = d.di[B2_DI_SOLVE_CTR] + 4 * (size_t)w0;
   int slot = blockIdx.x * B2_WPB + warp;
   while (slot < n) {
     int w = d.di[B2_DI_SOLVE_ORDER][w0 + slot];
@@ -110,31 +131,66 @@ __global__ void __launch_bounds__(B2_WPB * 32, B2_SOLVE_MINB) k_solve(const KMod
         atomicAnd(reinterpret_cast<unsigned*>(actl), (warp & 1) ? 0x0000ffffu : 0xffff0000u);
       }
     }
+    if (post_mode) {  // publish: every lane's results visible device-wide, then the ring entry
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) {
+        int pos = atomicAdd(&ctr[0], 1);
+        *reinterpret_cast<volatile int*>(ring + pos) = w;
+      }
+    }
     if (lane == 0) slot = atomicAdd(next, 1);
     slot = __shfl_sync(0xffffffffu, slot, 0);
   }
+  if (!post_mode) return;
+  real* psm = smem + (size_t)warp * L.fixed_total;   // the warp's solver scratch, free now (post layout <= fixed part, make_plan)
+  for (;;) {
+    int w = -1;
+    if (lane == 0) {
+      int idx = atomicAdd(&ctr[1], 1);
+      if (idx < n) {
+        // bounded like the arena wait: the bound only keeps a logic error from hanging the GPU
+        for (int spins = 0; (w = *reinterpret_cast<volatile int*>(ring + idx)) < 0 && spins < (1 << 24); ++spins) __nanosleep(256);
+        __threadfence();
+      }
+    }
+    w = __shfl_sync(0xffffffffu, w, 0);
+    if (w < 0) break;
+    if (mask && !mask[w]) continue;
+    post_world(m, d, LP, w, psm, post_mode == 2);
+    __syncwarp();
+  }
 }
 
-// Counting sort of the worlds by contact count, heaviest first (one CTA).  Which solver slot a world lands in has no
+// Counting sort of the worlds by predicted solver cost, heaviest first (one CTA).  Which solver slot a world lands in has no
 // effect on its results; the atomics only make the order inside a bucket arbitrary.
 #define B2_ORDER_BINS 64
-// Sort key = contact count.  (Weighting it with the Newton iteration count of the world's previous solve was tried: the
-// iteration count is too noisy from step to step - a 92-row world predicted "light" started late and became the tail.)
-static __device__ __forceinline__ int order_key(int ncon, int niter_prev) {
-  (void)niter_prev;
-  return ncon < B2_ORDER_BINS ? ncon : B2_ORDER_BINS - 1;
+// Sort key.  Per-world timers (tools/solve_timeline.py): the latency of a world is ~42 us per Newton iteration almost
+// regardless of its row count, so contacts alone (mode 0, round 1) leave 8-iteration worlds with 8 contacts in the middle
+// of the order, where they become the launch's tail.  The iteration count of the world's previous solve predicts the next
+// one well enough when it is ADDED to the contact count (a world with many contacts is never sorted as light, which is what
+// went wrong when the product of the two was tried in round 1).  `mode`: 0 = contacts, k > 0 = contacts + k * previous iterations.
+static __device__ __forceinline__ int order_key(int ncon, int niter_prev, int mode) {
+  int k = ncon + mode * niter_prev;
+  return k < B2_ORDER_BINS ? k : B2_ORDER_BINS - 1;
 }
-__global__ void __launch_bounds__(1024) k_order(const KData d, int w0, int w1) {
+__global__ void __launch_bounds__(1024) k_order(const KData d, int w0, int w1, int cap, int mode) {
   __shared__ int hist[B2_ORDER_BINS], base[B2_ORDER_BINS];
   const int* ncon = d.di[B2_DI_NCON];
-  const int* niter = d.di[B2_DI_SOLVER_NITER];   // of the world's previous solve: the best cheap predictor of this one
+  const int* niter = d.di[B2_DI_SOLVER_NITER];   // of the world's previous solve
   int* order = d.di[B2_DI_SOLVE_ORDER];
+  int* ring = d.di[B2_DI_SOLVE_RING];
   if (threadIdx.x < B2_ORDER_BINS) hist[threadIdx.x] = 0;
-  if (threadIdx.x == 0) d.di[B2_DI_SOLVE_NEXT][w0] = solve_grid(w1 - w0) * B2_WPB;   // first slot no warp starts on
+  if (threadIdx.x == 0) {
+    d.di[B2_DI_SOLVE_NEXT][w0] = solve_grid(w1 - w0, cap) * B2_WPB;   // first slot no warp starts on
+    d.di[B2_DI_SOLVE_CTR][4 * (size_t)w0] = 0;
+    d.di[B2_DI_SOLVE_CTR][4 * (size_t)w0 + 1] = 0;
+  }
   __syncthreads();
   for (int w = w0 + threadIdx.x; w < w1; w += blockDim.x) {
-    int k = order_key(ncon[w], niter[w]);
+    int k = order_key(ncon[w], niter[w], mode);
     atomicAdd(&hist[k], 1);
+    ring[w] = -1;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -143,14 +199,14 @@ __global__ void __launch_bounds__(1024) k_order(const KData d, int w0, int w1) {
   }
   __syncthreads();
   for (int w = w0 + threadIdx.x; w < w1; w += blockDim.x) {
-    int k = order_key(ncon[w], niter[w]);
+    int k = order_key(ncon[w], niter[w], mode);
     // Rank p in the heaviest-first order -> solver slot.  G CTAs of two warps are resident; warp (c, i) starts on slot
     // 2c + i and then pulls slots 2G, 2G+1, ... in order.  The two worlds of a CTA share one row arena and a world that
     // does not fit next to its CTA-mate waits for the mate to finish (per-world timers: 55 % of the latency of the
     // heaviest worlds was that wait while they were paired with each other), so the first wave pairs the c-th heaviest
     // world with the c-th lightest; the warps of the light worlds are free within microseconds and take the remaining
     // worlds longest-first, which keeps the tail of the launch short.
-    int slot = solve_slot(atomicAdd(&base[k], 1), w1 - w0);
+    int slot = solve_slot(atomicAdd(&base[k], 1), w1 - w0, cap);
     order[w0 + slot] = w;   // slots [w0, w1) hold a permutation of the worlds [w0, w1)
   }
 }
@@ -208,9 +264,20 @@ struct Plan {
   SolveSmem lv;
   PostSmem lp;
   size_t smem_smooth, smem_solve, smem_post;
+  int solve_cap;    // resident solver CTAs on this device: SMs x CTAs per SM granted by the occupancy calculator
+  int order_mode;   // sort key of k_order (see order_key)
+  int fuse_post;    // run the sensor / integration stage inside k_solve's tail (experiment, default off: see k_solve)
+  int chunks, chunk_min;
 };
 
 static_assert(B2_WPB <= 2, "the arena hand-over in k_solve assumes at most two worlds per CTA");
+
+// Experiment knobs (tests flip them in-process) are read when a plan is BUILT, not on every enqueue: a plan is cached per
+// (model sizes, data sizes, device) and rebuilt by b2_check, which Simulation calls at construction.
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e && *e ? atoi(e) : dflt;
+}
 
 static int make_plan(const b2_model* m, const b2_data* d, Plan* p) {
   p->ls = smooth_smem_layout(m->nq, m->nv, m->nu, m->nbody, m->njnt, B2_NCAND_MAX);
@@ -229,38 +296,72 @@ static int make_plan(const b2_model* m, const b2_data* d, Plan* p) {
   // order of magnitude below it (G1, random actions: median 30 rows, max 116 of 198).  Cap the arena so that
   // B2_SOLVE_MINB CTAs stay resident per SM, but never below half the strict bound.  A world beyond the cap loses rows
   // from the tail of its contact list exactly like njmax truncation does (counted in nefc_dropped).
+  p->lp = post_smem_layout(m->nv);
   {
-    SolveSmem probe = solve_smem_layout(m->nv, rows_max, m->maxchain, 0);
+    SolveSmem probe = solve_smem_layout(m->nv, rows_max, m->maxchain, 0, p->lp.total);
     long budget = (233472 / B2_SOLVE_MINB - 1024 - 16 - (long)probe.fixed_total * B2_WPB * (long)sizeof(real)) / (long)sizeof(real);
     if (budget < arena / 2) budget = arena / 2;
     if (arena > budget) arena = (int)budget & ~3;
   }
-  if (const char* e = getenv("B200SIM_ARENA")) arena = atoi(e);  // experiments
+  arena = env_int("B200SIM_ARENA", arena);  // experiments
   {
     // whatever the cap, a world reduced to one row and no Jacobian pool must fit (solve_world shrinks towards that)
     int floor_ = solve_arena_need(1, runs_max, dofs_max, 0, d->nconmax > 0 ? d->nconmax : 1) + 64;
     if (arena < floor_) arena = floor_;
   }
   arena = (arena + 3) & ~3;   // the two-ended allocator of k_solve works in units of 4 floats
-  p->lv = solve_smem_layout(m->nv, rows_max, m->maxchain, arena);
-  p->lp = post_smem_layout(m->nv);
+  p->lv = solve_smem_layout(m->nv, rows_max, m->maxchain, arena, p->lp.total);
   p->smem_smooth = (size_t)p->ls.total * sizeof(real) * B2_SMOOTH_WPB;
   p->smem_solve = ((size_t)p->lv.fixed_total * B2_WPB + p->lv.arena_cap) * sizeof(real) + 16;
   p->smem_post = (size_t)p->lp.total * sizeof(real) * B2_POST_WPB;
-  if (const char* e = getenv("B200SIM_SMEM_PAD")) p->smem_solve += (size_t)atoi(e);  // occupancy experiments only
+  p->smem_solve += (size_t)env_int("B200SIM_SMEM_PAD", 0);  // occupancy experiments only
+  p->solve_cap = B2_SOLVE_DEFAULT_CTAS;
+  p->order_mode = env_int("B200SIM_ORDER_MODE", B2_ORDER_MODE_DEFAULT);
+  p->fuse_post = env_int("B200SIM_FUSE_POST", 0);
+  p->chunks = env_int("B200SIM_CHUNKS", 1);
+  p->chunk_min = env_int("B200SIM_CHUNK_MIN", 512);
   return 0;
+}
+
+// Plan cache: one entry per (sizes the layouts depend on, device).  b2_check builds / refreshes the entry (and is the only
+// place that touches the device attributes); the enqueue paths only look it up.
+struct PlanKey { int v[12]; };
+struct PlanEntry { PlanKey key; Plan plan; bool checked; };
+static PlanEntry g_plans[32];
+static int g_nplans = 0;
+
+static PlanKey plan_key(const b2_model* m, const b2_data* d) {
+  int dev = -1;
+  cudaGetDevice(&dev);
+  PlanKey k = {{m->nq, m->nv, m->nu, m->nbody, m->njnt, m->nlimited, m->maxchain, d->nconmax, d->njmax, dev, 0, 0}};
+  return k;
+}
+
+static PlanEntry* plan_lookup(const b2_model* m, const b2_data* d, bool rebuild) {
+  PlanKey k = plan_key(m, d);
+  PlanEntry* e = nullptr;
+  for (int i = 0; i < g_nplans; ++i)
+    if (memcmp(&g_plans[i].key, &k, sizeof(k)) == 0) { e = &g_plans[i]; break; }
+  if (e && !rebuild) return e;
+  if (!e) {
+    e = &g_plans[g_nplans < 32 ? g_nplans++ : 31];
+    e->key = k;
+    e->checked = false;
+  }
+  make_plan(m, d, &e->plan);
+  return e;
 }
 
 extern "C" {
 
 int b2_abi_version(void) { return 1; }
 const char* b2_last_error(void) { return g_err; }
-int b2_debug_solver_slot(int rank, int nworld) { return solve_slot(rank, nworld); }
+int b2_debug_solver_slot(int rank, int nworld) { return solve_slot(rank, nworld, B2_SOLVE_DEFAULT_CTAS); }
 int b2_sizeof_model(void) { return (int)sizeof(b2_model); }
 int b2_sizeof_data(void) { return (int)sizeof(b2_data); }
 long long b2_launch_count(void) { return g_launches; }
 
-int b2_check(const b2_model* m, const b2_data* d) {
+static int check_sizes(const b2_model* m, const b2_data* d) {
   if (!m || !d) return fail("null model/data");
   if (m->nv > 64) return fail("nv=%d exceeds the 64-dof limit of the per-world dof masks", m->nv);
   if (m->nv < 1) return fail("nv must be >= 1");
@@ -268,11 +369,17 @@ int b2_check(const b2_model* m, const b2_data* d) {
   if (m->solver != 2) return fail("only the Newton solver is supported");
   if (m->integrator != B2_INT_EULER && m->integrator != B2_INT_IMPLICITFAST) return fail("unsupported integrator %d", m->integrator);
   if (d->nworld < 1 || d->nconmax < 0 || d->njmax < 1) return fail("bad nworld/nconmax/njmax");
-  Plan p;
-  make_plan(m, d, &p);
-  int dev = 0, maxsmem = 0;
+  return 0;
+}
+
+int b2_check(const b2_model* m, const b2_data* d) {
+  if (check_sizes(m, d)) return 1;
+  int dev = 0, maxsmem = 0, nsm = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return fail("no CUDA device: %s", cudaGetErrorString(cudaGetLastError()));
+  PlanEntry* pe = plan_lookup(m, d, true);
+  Plan& p = pe->plan;
   cudaDeviceGetAttribute(&maxsmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
   if ((int)p.smem_smooth > maxsmem || (int)p.smem_solve > maxsmem || (int)p.smem_post > maxsmem)
     return fail("shared memory per CTA (%zu / %zu B) exceeds the device limit %d B; lower njmax or model size",
                 p.smem_smooth, p.smem_solve, maxsmem);
@@ -283,24 +390,46 @@ int b2_check(const b2_model* m, const b2_data* d) {
   if (e != cudaSuccess) return fail("cudaFuncSetAttribute(k_solve): %s", cudaGetErrorString(e));
   e = cudaFuncSetAttribute(k_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_post);
   if (e != cudaSuccess) return fail("cudaFuncSetAttribute(k_post): %s", cudaGetErrorString(e));
+  // The solver grid must be fully resident (its warps wait on each other's results in the fused sensor stage): size it
+  // from what the occupancy calculator grants on THIS device, not from a compiled-in SM count.
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve, B2_WPB * 32, p.smem_solve);
+  if (e != cudaSuccess || per_sm < 1 || nsm < 1) return fail("k_solve does not fit on an SM (%s)", cudaGetErrorString(e));
+  p.solve_cap = per_sm * nsm;
+  pe->checked = true;
   return 0;
 }
 
-// One physics step (do_integrate) or forward pass for the worlds [w0, w1) on stream st: four launches.
+static const Plan* get_plan(const b2_model* m, const b2_data* d) {
+  PlanEntry* pe = plan_lookup(m, d, false);
+  if (!pe->checked) {   // a caller that skipped b2_check: do it now (first enqueue only)
+    if (b2_check(m, d)) return nullptr;
+    pe = plan_lookup(m, d, false);
+  }
+  return &pe->plan;
+}
+
+// One physics step (do_integrate) or forward pass for the worlds [w0, w1) on stream st: four launches (kinematics ...
+// qacc_smooth; the solver order; constraint rows + Newton solver; sensors + integration).
 static void launch_range(const Plan& p, const KModel& km, const KData& kd, cudaStream_t st, int do_integrate, const unsigned char* mask,
                          const int* gate, int w0, int w1) {
   int n = w1 - w0;
   k_smooth<<<(n + B2_SMOOTH_WPB - 1) / B2_SMOOTH_WPB, B2_SMOOTH_WPB * 32, p.smem_smooth, st>>>(km, kd, p.ls, B2_NCAND_MAX, mask, gate, w0, w1);
-  k_order<<<1, 1024, 0, st>>>(kd, w0, w1);
-  k_solve<<<solve_grid(n), B2_WPB * 32, p.smem_solve, st>>>(km, kd, p.lv, mask, gate, w0, w1);
-  k_post<<<(n + B2_POST_WPB - 1) / B2_POST_WPB, B2_POST_WPB * 32, p.smem_post, st>>>(km, kd, p.lp, do_integrate, mask, gate, w0, w1);
-  g_launches += 4;
+  k_order<<<1, 1024, 0, st>>>(kd, w0, w1, p.solve_cap, p.order_mode);
+  if (p.fuse_post) {
+    k_solve<<<solve_grid(n, p.solve_cap), B2_WPB * 32, p.smem_solve, st>>>(km, kd, p.lv, p.lp, do_integrate ? 2 : 1, mask, gate, w0, w1);
+    g_launches += 3;
+  } else {
+    k_solve<<<solve_grid(n, p.solve_cap), B2_WPB * 32, p.smem_solve, st>>>(km, kd, p.lv, p.lp, 0, mask, gate, w0, w1);
+    k_post<<<(n + B2_POST_WPB - 1) / B2_POST_WPB, B2_POST_WPB * 32, p.smem_post, st>>>(km, kd, p.lp, do_integrate, mask, gate, w0, w1);
+    g_launches += 4;
+  }
 }
 
 static int run(const b2_model* m, b2_data* d, void* stream, int do_integrate, const unsigned char* mask = nullptr, const int* gate = nullptr) {
-  Plan p;
-  make_plan(m, d, &p);
-  launch_range(p, *reinterpret_cast<const KModel*>(m), *reinterpret_cast<const KData*>(d), (cudaStream_t)stream, do_integrate, mask, gate, 0, d->nworld);
+  const Plan* p = get_plan(m, d);
+  if (!p) return 1;
+  launch_range(*p, *reinterpret_cast<const KModel*>(m), *reinterpret_cast<const KData*>(d), (cudaStream_t)stream, do_integrate, mask, gate, 0, d->nworld);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail("launch failed: %s", cudaGetErrorString(e));
   return 0;
@@ -321,12 +450,9 @@ struct ChunkStreams {
 };
 static ChunkStreams g_cs[16];
 
-static int chunk_count(int nworld) {
-  // read on every call (a getenv per enqueue is nothing next to a launch): tests flip these in-process
-  const char* e = getenv("B200SIM_CHUNKS");
-  const char* emin = getenv("B200SIM_CHUNK_MIN");
-  int c = e && atoi(e) > 0 ? atoi(e) : 1;   // default: one chunk (see the note above run_chunked)
-  int min_worlds = emin && atoi(emin) > 0 ? atoi(emin) : 512;   // below this many worlds per chunk the launches only add overhead
+static int chunk_count(const Plan& p, int nworld) {
+  int c = p.chunks > 0 ? p.chunks : 1;   // default: one chunk (see the note above run_chunked)
+  int min_worlds = p.chunk_min > 0 ? p.chunk_min : 512;   // below this many worlds per chunk the launches only add overhead
   if (c > B2_MAX_CHUNKS) c = B2_MAX_CHUNKS;
   while (c > 1 && nworld / c < min_worlds) c >>= 1;
   return c < 1 ? 1 : c;
@@ -354,12 +480,13 @@ typedef void (*chunk_hook)(const void* ctx, cudaStream_t st, int w0, int w1);
 // nsub x [physics step or forward; hook] for every world, chunk chains on side streams forked from / joined to `stream`.
 static int run_chunked(const b2_model* m, b2_data* d, void* stream, int nsub, int do_integrate, const unsigned char* mask, const int* gate,
                        chunk_hook hook, const void* hook_ctx) {
-  Plan p;
-  make_plan(m, d, &p);
+  const Plan* pp = get_plan(m, d);
+  if (!pp) return 1;
+  const Plan& p = *pp;
   const KModel& km = *reinterpret_cast<const KModel*>(m);
   const KData& kd = *reinterpret_cast<const KData*>(d);
   cudaStream_t main_st = (cudaStream_t)stream;
-  int nc = chunk_count(d->nworld);
+  int nc = chunk_count(p, d->nworld);
   ChunkStreams* cs = nc > 1 ? chunk_streams(nc) : nullptr;
   if (!cs) {
     for (int s = 0; s < nsub; ++s) {
@@ -367,7 +494,7 @@ static int run_chunked(const b2_model* m, b2_data* d, void* stream, int nsub, in
       if (hook) hook(hook_ctx, main_st, 0, d->nworld);
     }
   } else {
-    // chunk boundaries on multiples of 4 worlds (k_post packs 4 worlds per CTA, the env kernels too)
+    // chunk boundaries on multiples of 4 worlds (the env kernels pack 4 worlds per CTA)
     int per = ((d->nworld + nc - 1) / nc + 3) & ~3;
     if (cudaEventRecord(cs->fork, main_st) != cudaSuccess) return fail("event record: %s", cudaGetErrorString(cudaGetLastError()));
     for (int c = 0; c < nc; ++c) {
@@ -388,20 +515,24 @@ static int run_chunked(const b2_model* m, b2_data* d, void* stream, int nsub, in
   return 0;
 }
 
+// Stages on their own (bench.py brackets each with CUDA events, stage-wise tests): 0 = k_smooth + k_order, 1 = k_solve
+// WITHOUT the fused sensor stage, 2 = k_post (the same post_world as a kernel of its own), 3 = k_solve with the fused
+// sensor / integration stage, i.e. what b2_step launches after stage 0.
 int b2_stage(const b2_model* m, b2_data* d, int stage, int do_integrate, void* stream) {
-  Plan p;
-  make_plan(m, d, &p);
+  const Plan* pp = get_plan(m, d);
+  if (!pp) return 1;
+  const Plan& p = *pp;
   cudaStream_t st = (cudaStream_t)stream;
   const KModel& km = *reinterpret_cast<const KModel*>(m);
   const KData& kd = *reinterpret_cast<const KData*>(d);
-  int grid = (d->nworld + B2_WPB - 1) / B2_WPB;
   if (stage == 0) {
     k_smooth<<<(d->nworld + B2_SMOOTH_WPB - 1) / B2_SMOOTH_WPB, B2_SMOOTH_WPB * 32, p.smem_smooth, st>>>(km, kd, p.ls, B2_NCAND_MAX, nullptr, nullptr, 0, d->nworld);
-    k_order<<<1, 1024, 0, st>>>(kd, 0, d->nworld);
+    k_order<<<1, 1024, 0, st>>>(kd, 0, d->nworld, p.solve_cap, p.order_mode);
     g_launches += 1;
   }
-  else if (stage == 1) k_solve<<<solve_grid(d->nworld), B2_WPB * 32, p.smem_solve, st>>>(km, kd, p.lv, nullptr, nullptr, 0, d->nworld);
+  else if (stage == 1) k_solve<<<solve_grid(d->nworld, p.solve_cap), B2_WPB * 32, p.smem_solve, st>>>(km, kd, p.lv, p.lp, 0, nullptr, nullptr, 0, d->nworld);
   else if (stage == 2) k_post<<<(d->nworld + B2_POST_WPB - 1) / B2_POST_WPB, B2_POST_WPB * 32, p.smem_post, st>>>(km, kd, p.lp, do_integrate, nullptr, nullptr, 0, d->nworld);
+  else if (stage == 3) k_solve<<<solve_grid(d->nworld, p.solve_cap), B2_WPB * 32, p.smem_solve, st>>>(km, kd, p.lv, p.lp, do_integrate ? 2 : 1, nullptr, nullptr, 0, d->nworld);
   else return fail("unknown stage %d", stage);
   g_launches += 1;
   cudaError_t e = cudaGetLastError();

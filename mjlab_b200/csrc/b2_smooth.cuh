@@ -305,10 +305,23 @@ B2_DEV void make_frame(real* F, const real* normal, const real* tangent) {
   cross3(F + 6, n, t);
 }
 
+#if defined(B2_TIMING) && !defined(B2_HOSTEMU)
+// diagnostics build only (tools/solve_timeline.py): clock64 per phase of smooth_world
+__device__ unsigned long long g_sphase[8 * 16384];
+#define B2_SPH_BEGIN() long long sph_t = clock64(); unsigned long long sph_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define B2_SPH(k) { long long sph_n = clock64(); sph_acc[k] += (unsigned long long)(sph_n - sph_t); sph_t = sph_n; }
+#define B2_SPH_END() if (B2_LANE == 0 && w < 16384) { for (int k = 0; k < 8; ++k) g_sphase[8 * w + k] = sph_acc[k]; }
+#else
+#define B2_SPH_BEGIN()
+#define B2_SPH(k)
+#define B2_SPH_END()
+#endif
+
 // ---------------------------------------------------------------------------
 // Stage 1 for world w.  sm: this warp's shared-memory slab.
 // ---------------------------------------------------------------------------
 B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, int ncand_max, int w, real* sm) {  // @region setup
+  B2_SPH_BEGIN()
   const int nq = m.nq, nv = m.nv, nu = m.nu, nb = m.nbody, nj = m.njnt;
   real* qpos = sm + L.qpos; real* qvel = sm + L.qvel;
   real* xpos = sm + L.xpos; real* xquat = sm + L.xquat; real* xmat = sm + L.xmat; real* xipos = sm + L.xipos;
@@ -487,6 +500,7 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
     }
   }
 
+  B2_SPH(0)
   // ---- subtree com (backward gather over levels) ----------------------------  // @region subtree_com
   const real* body_mass = MF(B2_MF_BODY_MASS);
   const real* body_inertia = MF(B2_MF_BODY_INERTIA);
@@ -576,6 +590,7 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
     B2_UNROLL1
     for (int i = B2_LANE; i < 6 * nv; i += B2_NLANE) g[i] = cdof[i];
   }
+  B2_SPH(1)
   // ---- composite rigid body inertias, dense qM --------------------------------  // @region crb_qM
   B2_UNROLL1
   for (int lev = m.nlevel - 1; lev >= 1; --lev) {
@@ -616,6 +631,7 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
     for (int i = B2_LANE; i < nv * ld; i += B2_NLANE) g[i] = M[i];
   }
 
+  B2_SPH(2)
   // ---- collision ---------------------------------------------------------------  // @region collision
   {
     const int* pair_geom = MI(B2_MI_PAIR_GEOM);
@@ -838,6 +854,7 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
     }
   }
 
+  B2_SPH(3)
   // ---- com_vel: cvel, cdof_dot (forward over levels) ----------------------------  // @region com_vel
   B2_UNROLL1
   for (int lev = 0; lev < m.nlevel; ++lev) {
@@ -909,6 +926,7 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
     B2_WSYNC();
   }
 
+  B2_SPH(4)
   // ---- RNE bias (cacc aliases crb) -----------------------------------------------------  // @region rne
   const real* grav = MF(B2_MF_OPT_GRAVITY);
   B2_UNROLL1
@@ -952,6 +970,7 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
     B2_WSYNC();
   }
 
+  B2_SPH(5)
   // ---- passive + actuator + applied forces -> qfrc_smooth ------------------------------  // @region qfrc_smooth
   {
     const real* damping = MF(B2_MF_DOF_DAMPING);
@@ -1012,6 +1031,7 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
     }
     B2_WSYNC();
   }
+  B2_SPH(6)
   // ---- qacc_smooth = M^-1 qfrc_smooth (M already copied to HBM; factor in place) ---------  // @region factor_solve
   spd_factor_solve(M, nv, ld, f, sm + L.invd);
   {
@@ -1019,4 +1039,6 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
     B2_UNROLL1
     for (int i = B2_LANE; i < nv; i += B2_NLANE) g[i] = f[i];
   }
+  B2_SPH(7)
+  B2_SPH_END()
 }

@@ -37,7 +37,7 @@ int solve_arena_need(int rows, int runs, int dofs, int pool, int ncon) {
   return cd + 3 * r4(rows) + r4(2 * runs) + r4((dofs + 3) / 4) + r4(4 * ncon) + r4(pool);
 }
 
-static inline SolveSmem solve_smem_layout(int nv, int rows_max, int maxchain, int arena_cap) {
+static inline SolveSmem solve_smem_layout(int nv, int rows_max, int maxchain, int arena_cap, int min_fixed = 0) {
   SolveSmem s;
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
@@ -48,7 +48,7 @@ static inline SolveSmem solve_smem_layout(int nv, int rows_max, int maxchain, in
   s.qfs = take(nv); s.qas = take(nv); s.qfc = take(nv); s.tmp = take(nv); s.invd = take(64);  // 1 / diag(L)
   s.pairtab = take((maxchain * (maxchain + 1) / 2 + 1) / 2);  // ushort (a << 8 | b) per lower-triangle pair index
   s.actmask = take((rows_max + 31) / 32);  // bit r: row r was active at the last Hessian factorisation
-  s.fixed_total = o;
+  s.fixed_total = o > min_fixed ? o : ((min_fixed + 3) & ~3);  // the fused sensor stage reuses the warp's fixed part as its scratch
   s.arena_cap = arena_cap;
   s.rows_max = rows_max;
   return s;
@@ -112,6 +112,7 @@ __device__ unsigned long long g_lsstat[8];   // [heavy?0:4] + {line searches, si
 #endif
 #ifdef B2_HOSTEMU
 static long long b2h_ls_passes = 0;   // test harness statistic: row passes of the line search (single or three-point)
+static long long b2h_flip_hist[66] = {0};   // [k < 64]: Newton iterations (it > 0) whose active set differs in k rows from the last factorised one; [64]: >= 64; [65]: first iterations
 #define B2_LS_COUNT() (++b2h_ls_passes)
 #else
 #define B2_LS_COUNT()
@@ -792,6 +793,9 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
       // of the last factorisation, the factor still in H is reused (same result, no copy / J^T D J / Cholesky).
       real c1 = 0;
       bool same_set = it > 0;
+#ifdef B2_HOSTEMU
+      int nflip_stat = 0;
+#endif
       B2_UNROLL1
       for (int base = 0; base < nefc; base += B2_NLANE) {
         int r = base + B2_LANE;
@@ -808,6 +812,7 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
 #ifdef B2_HOSTEMU
         unsigned* slot = actmask + (base >> 5);
         unsigned prev = (*slot >> (base & 31)) & 1u;
+        if (it > 0 && prev != bal) ++nflip_stat;
         if (it == 0 || prev != bal) same_set = false;
         *slot = (*slot & ~(1u << (base & 31))) | (bal << (base & 31));
 #else
@@ -874,6 +879,9 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
         cost = newcost;
       }
       if (it >= m.iterations) break;
+#ifdef B2_HOSTEMU
+      b2h_flip_hist[it == 0 ? 65 : (nflip_stat < 64 ? nflip_stat : 64)] += 1;
+#endif
       B2_PH(2)
       // -- part 2: H = M + J^T diag(w) J, only when another Newton step will be taken  // @region hessian
       if (same_set) {

@@ -157,6 +157,8 @@ DATA_INT_FIELDS = [
   ("NEFC_DROPPED", "nefc_dropped", lambda m, c, j: ()),
   ("SOLVE_ORDER", "solve_order", lambda m, c, j: ()),
   ("SOLVE_NEXT", "solve_next", lambda m, c, j: ()),
+  ("SOLVE_RING", "solve_ring", lambda m, c, j: ()),
+  ("SOLVE_CTR", "solve_ctr", lambda m, c, j: (4,)),
 ]
 
 def leading_dim(n: int) -> int:
@@ -256,6 +258,16 @@ def check_supported(m) -> None:
     raise ValueError("supported integrators: euler, implicitfast")
   if m.nu and np.any(m.actuator_trnid[:, 0] < 0):
     raise ValueError("only joint transmissions are supported")
+  # parsed-but-unimplemented physics is an error, never a silent no-op: friction-loss constraint rows
+  fl = np.asarray(getattr(m, "dof_frictionloss", 0.0))
+  if np.any(fl != 0):
+    raise ValueError("dof_frictionloss != 0: friction-loss constraint rows are outside the supported subset "
+                     "(the shipped tasks use frictionloss = 0, src/mjlab/actuator/actuator.py:28)")
+
+
+# model fields that exist on the compiled model and have physical meaning, but that no kernel reads: making them
+# per-world / randomising them would silently do nothing, so `expand_model_fields` and `randomize_field` refuse them
+UNCONSUMED_PHYSICS_FIELDS = frozenset({"dof_frictionloss"})
 
 
 def model_scalars(m, tables) -> dict[str, int]:

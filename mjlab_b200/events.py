@@ -39,6 +39,9 @@ def randomize_field(env, env_ids, field: str, ranges, distribution: str = "unifo
   if field not in FIELD_SPECS:
     raise ValueError(f"Unknown field '{field}'. Supported fields: {list(FIELD_SPECS)}")
   kind, default_axes = FIELD_SPECS[field]
+  from . import engine as _E
+  if field in _E.UNCONSUMED_PHYSICS_FIELDS:
+    raise ValueError(f"'{field}' is not consumed by the engine (unsupported feature): randomising it would silently do nothing")
   robot, dev = env.scene["robot"], env.device
   ix = robot.indexing
   if kind == "geom":

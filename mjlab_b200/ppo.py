@@ -178,6 +178,11 @@ class OnPolicyRunner:
     if self.distributed:
       for t in list(self.policy.parameters()) + list(self.policy.buffers()):
         dist.broadcast(t.data, src=0)
+    # Exploration noise and mini-batch permutations must differ per process (the reference seeds the whole agent with
+    # seed + local_rank, scripts/train.py:58-63); the parameters above stay identical on every rank.
+    torch.manual_seed(self.cfg.seed + self.rank)
+    if torch.cuda.is_available():
+      torch.cuda.manual_seed(self.cfg.seed + self.rank)
     # the learning rate lives on the device (KL-adaptive rule without a host round trip per mini-batch)
     cuda = self.device.type == "cuda"
     self._lr = torch.tensor(float(self.cfg.learning_rate), device=self.device)

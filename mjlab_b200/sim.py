@@ -332,6 +332,9 @@ class Simulation:
     invalid = [f for f in fields if not hasattr(self._mj_model, f)]
     if invalid:
       raise ValueError(f"Fields not found in model: {invalid}")
+    dead = [f for f in fields if f in E.UNCONSUMED_PHYSICS_FIELDS]
+    if dead:
+      raise ValueError(f"Fields {dead} are not consumed by the engine (friction-loss rows are unsupported); randomising them would have no effect")
     if self.num_envs == 1:
       return
     for f in fields:

@@ -19,6 +19,7 @@ extern "C" {
 
 int b2h_sizeof_real(void) { return (int)sizeof(real); }
 long long b2h_ls_pass_count(void) { return b2h_ls_passes; }
+void b2h_flip_histogram(long long* out) { for (int i = 0; i < 66; ++i) out[i] = b2h_flip_hist[i]; }
 int b2h_sizeof_model(void) { return (int)sizeof(KModel); }
 int b2h_sizeof_data(void) { return (int)sizeof(KData); }
 

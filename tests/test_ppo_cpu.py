@@ -102,6 +102,38 @@ def test_gradient_all_reduce_averages_over_ranks():
     np.testing.assert_allclose(r1, r0, rtol=0, atol=0)
 
 
+def _seed_worker(rank, world, port, q):
+  os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  env = ToyEnv(n=16, horizon=10)
+  cfg = ppo.PpoCfg(num_steps_per_env=4, actor_hidden_dims=(16,), critic_hidden_dims=(16,), num_learning_epochs=1, num_mini_batches=2, seed=7)
+  r = ppo.OnPolicyRunner(env, cfg, device="cpu")
+  params = torch.cat([p.detach().view(-1) for p in r.policy.parameters()]).numpy().copy()
+  r.collect()
+  # the toy env's observations are identical on both ranks (same generator seed), so any difference in the sampled
+  # actions comes from the exploration noise alone
+  q.put((rank, params, r.st["actions"].numpy().copy()))
+  dist.barrier()
+  dist.destroy_process_group()
+
+
+def test_ranks_share_parameters_but_not_exploration_noise():
+  """every rank seeded torch with cfg.seed, so all replicas drew the same action noise.  The reference seeds the
+  agent with seed + local_rank (scripts/train.py:58-63): parameters equal (rank-0 broadcast), noise different."""
+  ctx = mp.get_context("spawn")
+  q = ctx.Queue()
+  port = 29850 + os.getpid() % 100
+  procs = [ctx.Process(target=_seed_worker, args=(r, 2, port, q)) for r in range(2)]
+  for p in procs:
+    p.start()
+  out = sorted((q.get(timeout=120) for _ in range(2)), key=lambda t: t[0])
+  for p in procs:
+    p.join(timeout=60)
+  (_, p0, a0), (_, p1, a1) = out
+  np.testing.assert_array_equal(p0, p1)
+  assert np.abs(a0 - a1).max() > 1e-3, "both ranks sampled identical actions: exploration noise is not rank-specific"
+
+
 def test_policy_export_roundtrip(tmp_path):
   """TorchScript export of actor(normalizer(obs)) reproduces the live policy; the metadata side-car carries the reference's
   keys (rl/exporter_utils.py:23-62).  The env is a stand-in with the attributes the exporter reads."""

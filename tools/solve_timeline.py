@@ -17,6 +17,7 @@ from mjlab_b200 import engine as E  # noqa: E402
 from mjlab_b200.env import ManagerBasedRlEnv, VelocityEnvCfg  # noqa: E402
 
 nw = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+FUSED = len(sys.argv) > 2 and sys.argv[2] == "fused"   # time k_solve with the sensor / integration stage in its tail
 env = ManagerBasedRlEnv(VelocityEnvCfg(robot="g1", num_envs=nw, seed=42), "cuda:0")
 gen = torch.Generator(device="cuda:0").manual_seed(0)
 env.reset()
@@ -27,10 +28,22 @@ lib, pm, pd = env._lib, C.byref(env.sim._cm), C.byref(env.sim._cd)
 lib.b2_debug_timing.argtypes = [C.c_void_p, C.c_int]
 st = torch.cuda.current_stream().cuda_stream
 for rep in range(3):
+  e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+  e0.record()
   E.check_call(lib, lib.b2_stage(pm, pd, 0, 1, st))
+  e1.record()
   torch.cuda.synchronize()
-  E.check_call(lib, lib.b2_stage(pm, pd, 1, 1, st))
+  E.check_call(lib, lib.b2_stage(pm, pd, 3 if FUSED else 1, 1, st))
+  e2.record()
   torch.cuda.synchronize()
+  print(f"rep {rep}: CUDA events: k_smooth+k_order {e0.elapsed_time(e1) * 1e3:.0f} us, k_solve{' (+fused sensor/integration stage)' if FUSED else ''} {e1.elapsed_time(e2) * 1e3:.0f} us")
+  if hasattr(lib, "b2_debug_smooth_phases"):
+    ph = np.zeros(8 * nw, np.uint64)
+    lib.b2_debug_smooth_phases.argtypes = [C.c_void_p, C.c_int]
+    lib.b2_debug_smooth_phases(ph.ctypes.data, nw)
+    ph = ph.reshape(nw, 8).astype(np.float64)
+    names = ["setup+kinematics", "subtree_com+cinert+cdof", "crb+qM", "collision", "com_vel+actuation", "rne", "qfrc_smooth", "factor+solve"]
+    print("   k_smooth phase shares: " + ", ".join(f"{n} {100 * ph[:, k].sum() / ph.sum():.0f}%" for k, n in enumerate(names)), f"| cycles/world {ph.sum(1).mean():.0f}")
   out = np.zeros(3 * nw, np.uint64)
   assert lib.b2_debug_timing(out.ctypes.data, nw) == 0
   t = out.reshape(nw, 3)
@@ -71,4 +84,5 @@ for rep in range(3):
       n = max(int(ls[o]), 1)
       print(f"   line searches ({label}, all launches so far): {int(ls[o])}; per search: {ls[o + 1] / n:.2f} single evaluations, "
             f"{ls[o + 2] / n:.2f} three-point rounds; {100 * ls[o + 3] / n:.0f} % reach the refinement phase")
-  E.check_call(lib, lib.b2_stage(pm, pd, 2, 1, st))
+  if not FUSED:
+    E.check_call(lib, lib.b2_stage(pm, pd, 2, 1, st))
