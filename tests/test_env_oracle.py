@@ -12,11 +12,12 @@ from tests.envutil import init_state_from_golden, load_golden, snapshot
 TOL = dict(rtol=2e-5, atol=2e-6)
 
 
-@pytest.mark.parametrize("robot", ["g1", "go1"])
-def test_oracle_matches_reference_functions(robot):
+@pytest.mark.parametrize("fixture", ["g1", "go1", "g1_fallen", "go1_fallen"])
+def test_oracle_matches_reference_functions(fixture):
+  robot = fixture.split("_")[0]
   m = mjlab_b200.load_model(f"{robot}_flat")
   cfg = envcfg.velocity_cfg(m, robot)
-  g = load_golden(robot)
+  g = load_golden(fixture)
   T, B = g["actions"].shape[:2]
   s = OE.make_state(cfg, B)
   init_state_from_golden(s, g)
@@ -48,6 +49,9 @@ def test_oracle_matches_reference_functions(robot):
     np.testing.assert_allclose(s.obs_policy, g["ref_obs_policy"][t], **TOL)
     np.testing.assert_allclose(s.obs_critic, g["ref_obs_critic"][t], **TOL)
   assert nterm_checked > 0  # the fixture exercises at least one termination flag
+  if fixture.endswith("fallen"):   # ... and these make the reference's own bad_orientation / illegal_contact return True
+    assert g["ref_fell_over"].any() and not g["ref_fell_over"].all()
+    assert robot != "go1" or (g["ref_illegal"].any() and not g["ref_illegal"].all())
 
 
 def test_philox_known_answer():

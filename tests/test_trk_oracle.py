@@ -52,6 +52,8 @@ def test_oracle_matches_reference_functions():
     np.testing.assert_allclose(s.obs_policy, g["ref_obs_policy"][t], **TOL)
     np.testing.assert_allclose(s.obs_critic, g["ref_obs_critic"][t], **TOL)
   assert nterm > 0
+  # every motion termination is True somewhere in the reference's own output
+  assert g["ref_term_anchor_pos"].any() and g["ref_term_anchor_ori"].any() and g["ref_term_ee"].any()
 
 
 def test_adaptive_sampling_probabilities():
