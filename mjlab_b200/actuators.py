@@ -49,6 +49,17 @@ def _stream(dev) -> int:
   return torch.cuda.current_stream(dev).cuda_stream
 
 
+# Every random draw of this module goes through these two hooks, in the same order and with the same shapes as the
+# reference's DelayBuffer (utils/buffers/delay_buffer.py:158-166,213-222,276-301).  tests/test_gpu_actuators.py replaces them
+# to replay the draws recorded from the reference's own class (tools/make_actuator_golden.py).
+def _randint(low: int, high: int, shape, device, generator=None) -> torch.Tensor:
+  return torch.randint(low, high, shape, dtype=torch.long, device=device, generator=generator)
+
+
+def _rand(shape, device, generator=None) -> torch.Tensor:
+  return torch.rand(shape, dtype=torch.float32, device=device, generator=generator)
+
+
 class IdealPdActuator:
   """tau = clamp(kp (q* - q) + kd (qd* - qd) + tau_ff, +-effort_limit), per-env gains (pd_actuator.py:94-131)."""
 
@@ -77,13 +88,15 @@ class IdealPdActuator:
     return self._effort
 
   def set_gains(self, env_ids, kp: torch.Tensor | None = None, kd: torch.Tensor | None = None) -> None:
+    """kp / kd: (num_env_ids, num_joints), or (num_env_ids,) = one gain per env (pd_actuator.py:111-135)."""
     if kp is not None:
-      self.stiffness[env_ids] = kp
+      self.stiffness[env_ids] = kp.unsqueeze(-1) if kp.ndim == 1 else kp
     if kd is not None:
-      self.damping[env_ids] = kd
+      self.damping[env_ids] = kd.unsqueeze(-1) if kd.ndim == 1 else kd
 
   def set_effort_limit(self, env_ids, effort_limit: torch.Tensor) -> None:
-    self.force_limit[env_ids] = effort_limit
+    """effort_limit: (num_env_ids, num_joints) or (num_env_ids,) (pd_actuator.py:137-151)."""
+    self.force_limit[env_ids] = effort_limit.unsqueeze(-1) if effort_limit.ndim == 1 else effort_limit
 
   def reset(self, env_ids=None) -> None:
     pass
@@ -124,7 +137,7 @@ class DelayBuffer:
     self._pending: torch.Tensor | None = None
 
   def _rand_phase(self) -> torch.Tensor:
-    return torch.randint(0, self.update_period, (self.batch_size,), dtype=torch.long, device=self.device, generator=self.generator)
+    return _randint(0, self.update_period, (self.batch_size,), self.device, self.generator)
 
   @property
   def is_initialized(self) -> bool:
@@ -163,11 +176,11 @@ class DelayBuffer:
     else:
       should = torch.ones(self.batch_size, dtype=torch.bool, device=self.device)
     if self.per_env:
-      cand = torch.randint(self.min_lag, self.max_lag + 1, (self.batch_size,), dtype=torch.long, device=self.device, generator=self.generator)
+      cand = _randint(self.min_lag, self.max_lag + 1, (self.batch_size,), self.device, self.generator)
     else:
-      cand = torch.randint(self.min_lag, self.max_lag + 1, (1,), dtype=torch.long, device=self.device, generator=self.generator).expand(self.batch_size)
+      cand = _randint(self.min_lag, self.max_lag + 1, (1,), self.device, self.generator).expand(self.batch_size)
     if self.hold_prob > 0.0:
-      should = should & (torch.rand(self.batch_size, dtype=torch.float32, device=self.device, generator=self.generator) >= self.hold_prob)
+      should = should & (_rand((self.batch_size,), self.device, self.generator) >= self.hold_prob)
     self._current_lags = torch.where(should, cand, self._current_lags)
     self._step_count += 1
 

@@ -21,7 +21,8 @@ def test_ideal_pd_matches_formula():
   from mjlab_b200.actuators import IdealPdActuator
   n, nj = 257, 29
   act = IdealPdActuator(n, nj, stiffness=80.0, damping=2.5, effort_limit=20.0, device=DEV)
-  act.set_gains(torch.arange(0, n, 2, device=DEV), kp=torch.full((nj,), 40.0, device=DEV), kd=torch.full((nj,), 1.0, device=DEV))
+  ids = torch.arange(0, n, 2, device=DEV)
+  act.set_gains(ids, kp=torch.full((len(ids), nj), 40.0, device=DEV), kd=torch.full((len(ids),), 1.0, device=DEV))   # (ids, nj) / one per env
   c = _cmd(n, nj)
   got = act.compute(c).clone()
   want = torch.clamp(act.stiffness * (c.position_target - c.joint_pos) + act.damping * (c.velocity_target - c.joint_vel) + c.effort_target,
@@ -117,6 +118,130 @@ def test_learned_mlp_matches_torch(order):
     vc = torch.clamp(c.joint_vel, -corner, corner)
     want = torch.clamp(tau, min=torch.clamp(35.0 * (-1 - vc / 30.0), min=-23.7), max=torch.clamp(35.0 * (1 - vc / 30.0), max=23.7))
     torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-4)
+
+
+# ---- the same classes against the REFERENCE'S OWN classes (tests/golden/actuators.npz, tools/make_actuator_golden.py) ----------
+def _golden():
+  from pathlib import Path
+  return np.load(Path(__file__).resolve().parent / "golden" / "actuators.npz")
+
+
+def _gcmd(g, prefix, t):
+  from mjlab_b200.actuators import ActuatorCmd
+  return ActuatorCmd(**{k: torch.as_tensor(g[f"{prefix}_{k}"][t], device=DEV) for k in
+                        ("position_target", "velocity_target", "effort_target", "joint_pos", "joint_vel")})
+
+
+class _Replay:
+  """Feeds the draws recorded from the reference's DelayBuffer into mjlab_b200.actuators' `_randint` / `_rand` hooks."""
+
+  def __init__(self, g, prefix, monkeypatch):
+    from mjlab_b200 import actuators as ACT
+    self.draws = [g[f"{prefix}_draw{i}"] for i in range(int(g[f"{prefix}_ndraws"]))]
+    self.i = 0
+    monkeypatch.setattr(ACT, "_randint", lambda lo, hi, shape, device, generator=None: self._next(shape, device, torch.long, lo, hi))
+    monkeypatch.setattr(ACT, "_rand", lambda shape, device, generator=None: self._next(shape, device, torch.float32, 0, 1))
+
+  def _next(self, shape, device, dtype, lo, hi):
+    v = self.draws[self.i]
+    self.i += 1
+    assert tuple(v.shape) == tuple(shape), (self.i, v.shape, shape)     # same call sequence as the reference
+    assert v.min() >= lo and v.max() < hi
+    return torch.as_tensor(v, device=device).to(dtype)
+
+
+def test_ideal_pd_and_dc_motor_match_reference_classes():
+  from mjlab_b200.actuators import DcMotorActuator, IdealPdActuator
+  g = _golden()
+  T, B, NJ = g["pd_out"].shape
+  act = IdealPdActuator(B, NJ, stiffness=80.0, damping=2.5, effort_limit=20.0, device=DEV)
+  for t in range(T):
+    if t == 4:
+      act.set_gains(torch.tensor([0, 2, 4], device=DEV), kp=torch.full((3, NJ), 40.0, device=DEV), kd=torch.tensor([1.0, 1.5, 2.0], device=DEV))
+    if t == 8:
+      act.set_effort_limit(torch.tensor([1], device=DEV), torch.full((1, NJ), 5.0, device=DEV))
+    np.testing.assert_allclose(act.compute(_gcmd(g, "pd", t)).cpu().numpy(), g["pd_out"][t], rtol=1e-6, atol=1e-5)
+  dc = DcMotorActuator(B, NJ, stiffness=50.0, damping=1.0, effort_limit=23.7, saturation_effort=35.0, velocity_limit=30.0, device=DEV)
+  for t in range(T):
+    np.testing.assert_allclose(dc.compute(_gcmd(g, "dc", t)).cpu().numpy(), g["dc_out"][t], rtol=1e-6, atol=1e-5)
+  assert (np.abs(g["dc_out"]) < 23.7 - 1e-3).any() and (np.abs(np.abs(g["dc_out"]) - 23.7) < 1e-5).any()   # both clips occur
+
+
+def test_delay_buffer_matches_reference_class(monkeypatch):
+  """Lag policy (period 3, per-env phase, hold probability 0.3, reset of two rows at t = 7) and the lagged reads, with the
+  reference's own random draws replayed: current_lags and outputs equal the reference's at every step."""
+  from mjlab_b200.actuators import DelayBuffer
+  g = _golden()
+  x = torch.as_tensor(g["delay_in"], device=DEV)
+  T, B = x.shape[:2]
+  rp = _Replay(g, "delay", monkeypatch)
+  buf = DelayBuffer(min_lag=1, max_lag=4, batch_size=B, device=DEV, update_period=3, per_env_phase=True, hold_prob=0.3)
+  for t in range(T):
+    if t == 7:
+      buf.reset(torch.tensor([1, 4], device=DEV))
+    buf.append(x[t])
+    y = buf.compute()
+    np.testing.assert_array_equal(buf.current_lags.cpu().numpy(), g["delay_lags"][t])
+    np.testing.assert_array_equal(y.cpu().numpy(), g["delay_out"][t])
+  assert rp.i == len(rp.draws)
+  rp = _Replay(g, "delay2", monkeypatch)
+  buf = DelayBuffer(min_lag=0, max_lag=3, batch_size=B, device=DEV, per_env=False)
+  for t in range(T):
+    buf.append(x[t])
+    y = buf.compute()
+    np.testing.assert_array_equal(buf.current_lags.cpu().numpy(), g["delay2_lags"][t])
+    np.testing.assert_array_equal(y.cpu().numpy(), g["delay2_out"][t])
+  assert rp.i == len(rp.draws)
+
+
+def test_delayed_actuator_matches_reference_class(monkeypatch):
+  from mjlab_b200.actuators import DelayedActuator, IdealPdActuator
+  g = _golden()
+  T, B, NJ = g["dly_out"].shape
+  rp = _Replay(g, "dly", monkeypatch)
+  act = DelayedActuator(IdealPdActuator(B, NJ, stiffness=10.0, damping=0.5, effort_limit=50.0, device=DEV),
+                        delay_target=("position", "effort"), delay_min_lag=0, delay_max_lag=3, delay_update_period=4,
+                        delay_hold_prob=0.0, delay_per_env_phase=True)
+  for t in range(T):
+    if t == 5:
+      act.set_lags(torch.tensor([3, 0], device=DEV), torch.tensor([0, 5], device=DEV))
+    if t == 9:
+      act.reset(torch.tensor([2], device=DEV))
+    np.testing.assert_allclose(act.compute(_gcmd(g, "dly", t)).cpu().numpy(), g["dly_out"][t], rtol=1e-6, atol=1e-5)
+  assert rp.i == len(rp.draws)
+
+
+@pytest.mark.parametrize("order", ["pos_vel", "vel_pos"])
+def test_learned_mlp_matches_reference_class(order):
+  from mjlab_b200.actuators import LearnedMlpActuator
+  g = _golden()
+  T, B, NJ = g[f"mlp_out_{order}"].shape
+  H = 3
+  net = torch.nn.Sequential(torch.nn.Linear(2 * H, 16), torch.nn.Softsign(), torch.nn.Linear(16, 16), torch.nn.Softsign(), torch.nn.Linear(16, 1))
+  with torch.no_grad():
+    for i, lyr in enumerate(l for l in net if isinstance(l, torch.nn.Linear)):
+      lyr.weight.copy_(torch.as_tensor(g[f"mlp_w{i}"])); lyr.bias.copy_(torch.as_tensor(g[f"mlp_b{i}"]))
+  act = LearnedMlpActuator(B, NJ, net, pos_scale=-1.0, vel_scale=0.05, torque_scale=8.0, effort_limit=23.7, saturation_effort=35.0,
+                           velocity_limit=30.0, input_order=order, history_length=H, activation="softsign", device=DEV)
+  for t in range(T):
+    if t == 6:
+      act.reset(torch.tensor([1, 3], device=DEV))
+    np.testing.assert_allclose(act.compute(_gcmd(g, "mlp", t)).cpu().numpy(), g[f"mlp_out_{order}"][t], rtol=2e-5, atol=2e-5)
+
+
+def test_circular_buffer_on_device_matches_reference_class():
+  from mjlab_b200.buffers import CircularBuffer
+  g = _golden()
+  x = torch.as_tensor(g["delay_in"], device=DEV)
+  B = x.shape[1]
+  cb = CircularBuffer(max_len=4, batch_size=B, device=DEV)
+  for t in range(8):
+    if t == 5:
+      cb.reset([0, 3])
+    cb.append(x[t])
+    for lag in range(6):
+      np.testing.assert_array_equal(cb[lag].cpu().numpy(), g["circ_out"][t, lag])
+    np.testing.assert_array_equal(cb.buffer.cpu().numpy(), g["circ_buffer"][t])
 
 
 def _sim(robot="g1", n=16):
