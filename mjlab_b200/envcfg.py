@@ -114,6 +114,11 @@ class VelocityCfg:
   push_interval: tuple = (1.0, 3.0)
   push_x: tuple = (-0.5, 0.5)
   push_y: tuple = (-0.5, 0.5)
+  # full six-axis ranges {"x" | "y" | "z" | "roll" | "pitch" | "yaw": (lo, hi)} as the reference's event params spell them
+  # (envs/mdp/events.py:104-107,141-146,217-221); when given they replace the x / y / yaw shorthands above
+  reset_pose_range: dict = None
+  reset_velocity_range: dict = None
+  push_velocity_range: dict = None
   enable_corruption: bool = True
   push_enabled: bool = True
   heading_command: bool = True
@@ -141,14 +146,18 @@ class VelocityCfg:
 
   @property
   def reset_pose(self) -> np.ndarray:
+    if self.reset_pose_range is not None:
+      return self._ranges6(self.reset_pose_range)
     return self._ranges6({"x": self.reset_x, "y": self.reset_y, "yaw": self.reset_yaw})
 
   @property
   def reset_vel(self) -> np.ndarray:
-    return self._ranges6({})
+    return self._ranges6(self.reset_velocity_range or {})
 
   @property
   def push_vel(self) -> np.ndarray:
+    if self.push_velocity_range is not None:
+      return self._ranges6(self.push_velocity_range)
     return self._ranges6({"x": self.push_x, "y": self.push_y})
 
 
