@@ -195,6 +195,170 @@ B2_DEV void capsule_box(LaneContacts& lc, const real* cp, const real* cR, const 
   }
 }
 
+// Box against box (oracle/mjstep.py `_box_box`, statement by statement): separating-axis test over 3 + 3 face normals and 9
+// edge cross products; a face axis clips the other box's incident face against the side planes of the reference face
+// (Sutherland-Hodgman, <= 8 points), keeps the points at most `margin` above the reference face and reduces them to <= 4
+// (deepest, farthest from it, farthest from that line on either side); an edge axis gives one contact between the closest
+// points of the two supporting edges.  All contacts of the pair share one normal (box 1 -> box 2).
+#define B2_BOXBOX_PARALLEL ((real)1e-10)
+#define B2_BOXBOX_FACE_BIAS ((real)0.05)
+B2_DEV real boxbox_radius(const real* R, const real* s, const real* L) {
+  return s[0] * fabs(R[0] * L[0] + R[3] * L[1] + R[6] * L[2]) + s[1] * fabs(R[1] * L[0] + R[4] * L[1] + R[7] * L[2]) +
+         s[2] * fabs(R[2] * L[0] + R[5] * L[1] + R[8] * L[2]);
+}
+B2_DEVN void box_box(LaneContacts& lc, const real* p1, const real* R1, const real* s1, const real* p2, const real* R2,
+                     const real* s2, real margin) {
+  const real d[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+  real best_s = -INFINITY, best_sign = 1;
+  int best_code = 0;
+  B2_UNROLL1
+  for (int code = 0; code < 6; ++code) {
+    const real* R = code < 3 ? R1 : R2;
+    const int k = code < 3 ? code : code - 3;
+    real L[3] = {R[k], R[3 + k], R[6 + k]};
+    real dl = dot3(d, L);
+    real sep = fabs(dl) - boxbox_radius(R1, s1, L) - boxbox_radius(R2, s2, L);
+    if (sep > margin) return;
+    if (sep > best_s) { best_s = sep; best_code = code; best_sign = dl >= 0 ? (real)1 : (real)-1; }
+  }
+  real edge_s = -INFINITY, en[3] = {0, 0, 0};
+  int ei = 0, ej = 0;
+  bool have_edge = false;
+  B2_UNROLL1
+  for (int i = 0; i < 3; ++i) {
+    B2_UNROLL1
+    for (int j = 0; j < 3; ++j) {
+      real a[3] = {R1[i], R1[3 + i], R1[6 + i]}, b[3] = {R2[j], R2[3 + j], R2[6 + j]}, L[3];
+      cross3(L, a, b);
+      real n2 = dot3(L, L);
+      if (n2 < B2_BOXBOX_PARALLEL) continue;
+      real inv = (real)1 / sqrt(n2);
+      L[0] *= inv; L[1] *= inv; L[2] *= inv;
+      real dl = dot3(d, L);
+      real sep = fabs(dl) - boxbox_radius(R1, s1, L) - boxbox_radius(R2, s2, L);
+      if (sep > margin) return;
+      if (sep > edge_s) {
+        edge_s = sep; ei = i; ej = j; have_edge = true;
+        real sg = dl >= 0 ? (real)1 : (real)-1;
+        en[0] = L[0] * sg; en[1] = L[1] * sg; en[2] = L[2] * sg;
+      }
+    }
+  }
+  if (have_edge && edge_s > best_s + B2_BOXBOX_FACE_BIAS * fabs(best_s) + (real)1e-9) {
+    real pa[3] = {p1[0], p1[1], p1[2]}, pb[3] = {p2[0], p2[1], p2[2]};
+    for (int k = 0; k < 3; ++k) {
+      if (k != ei) {
+        real ax[3] = {R1[k], R1[3 + k], R1[6 + k]};
+        real sg = (dot3(ax, en) >= 0 ? (real)1 : (real)-1) * s1[k];
+        pa[0] += sg * ax[0]; pa[1] += sg * ax[1]; pa[2] += sg * ax[2];
+      }
+      if (k != ej) {
+        real ax[3] = {R2[k], R2[3 + k], R2[6 + k]};
+        real sg = (dot3(ax, en) >= 0 ? (real)1 : (real)-1) * s2[k];
+        pb[0] -= sg * ax[0]; pb[1] -= sg * ax[1]; pb[2] -= sg * ax[2];
+      }
+    }
+    real a[3] = {R1[ei], R1[3 + ei], R1[6 + ei]}, b[3] = {R2[ej], R2[3 + ej], R2[6 + ej]};
+    real w[3] = {pa[0] - pb[0], pa[1] - pb[1], pa[2] - pb[2]};
+    real bb = dot3(a, b), dd = dot3(a, w), e = dot3(b, w);
+    real den = (real)1 - bb * bb;
+    real t = clampr((bb * e - dd) / den, -s1[ei], s1[ei]);
+    real u = clampr((e - bb * dd) / den, -s2[ej], s2[ej]);
+    real qa[3] = {pa[0] + t * a[0], pa[1] + t * a[1], pa[2] + t * a[2]};
+    real qb[3] = {pb[0] + u * b[0], pb[1] + u * b[1], pb[2] + u * b[2]};
+    real df[3] = {qb[0] - qa[0], qb[1] - qa[1], qb[2] - qa[2]};
+    real dist = dot3(df, en);
+    if (dist > margin) return;
+    lc.dist[0] = dist;
+    lc.pos[0][0] = (real)0.5 * (qa[0] + qb[0]); lc.pos[0][1] = (real)0.5 * (qa[1] + qb[1]); lc.pos[0][2] = (real)0.5 * (qa[2] + qb[2]);
+    lc.normal[0] = en[0]; lc.normal[1] = en[1]; lc.normal[2] = en[2];
+    lc.n = 1;
+    return;
+  }
+  // face contact: reference box r, incident box i
+  const bool flip = best_code >= 3;
+  const real *pr = flip ? p2 : p1, *Rr = flip ? R2 : R1, *sr = flip ? s2 : s1;
+  const real *pi = flip ? p1 : p2, *Ri = flip ? R1 : R2, *si = flip ? s1 : s2;
+  const int axis = flip ? best_code - 3 : best_code;
+  const real nsg = flip ? -best_sign : best_sign;
+  const real nref[3] = {Rr[axis] * nsg, Rr[3 + axis] * nsg, Rr[6 + axis] * nsg};
+  int ks = 0;
+  real kbest = -1;
+  for (int k = 0; k < 3; ++k) {
+    real v = fabs(Ri[k] * nref[0] + Ri[3 + k] * nref[1] + Ri[6 + k] * nref[2]);
+    if (v > kbest) { ks = k; kbest = v; }
+  }
+  const real sgi = (Ri[ks] * nref[0] + Ri[3 + ks] * nref[1] + Ri[6 + ks] * nref[2]) > 0 ? (real)-1 : (real)1;
+  const int iu = (ks + 1) % 3, iv = (ks + 2) % 3, ru = (axis + 1) % 3, rv = (axis + 2) % 3;
+  const real ci[3] = {pi[0] + sgi * si[ks] * Ri[ks], pi[1] + sgi * si[ks] * Ri[3 + ks], pi[2] + sgi * si[ks] * Ri[6 + ks]};
+  real poly[8][3], nxt[8][3];
+  int np_ = 4;
+  for (int v = 0; v < 4; ++v) {
+    const real a = (v == 1 || v == 2) ? (real)1 : (real)-1, b = v >= 2 ? (real)1 : (real)-1;
+    real q[3];
+    for (int c = 0; c < 3; ++c) q[c] = ci[c] + a * si[iu] * Ri[3 * c + iu] + b * si[iv] * Ri[3 * c + iv] - pr[c];
+    poly[v][0] = q[0] * Rr[ru] + q[1] * Rr[3 + ru] + q[2] * Rr[6 + ru];
+    poly[v][1] = q[0] * Rr[rv] + q[1] * Rr[3 + rv] + q[2] * Rr[6 + rv];
+    poly[v][2] = dot3(q, nref) - sr[axis];
+  }
+  B2_UNROLL1
+  for (int pl = 0; pl < 4; ++pl) {
+    const int c = pl >> 1;
+    const real lim = c == 0 ? sr[ru] : sr[rv], sgn = (pl & 1) ? (real)-1 : (real)1;
+    int nn = 0;
+    B2_UNROLL1
+    for (int k = 0; k < np_; ++k) {
+      const real* cur = poly[k];
+      const real* prv = poly[k == 0 ? np_ - 1 : k - 1];
+      const real fc = sgn * cur[c] - lim, fp = sgn * prv[c] - lim;
+      if ((fc <= 0) != (fp <= 0)) {
+        const real tt = fp / (fp - fc);
+        if (nn < 8) { for (int e = 0; e < 3; ++e) nxt[nn][e] = prv[e] + tt * (cur[e] - prv[e]); ++nn; }
+      }
+      if (fc <= 0 && nn < 8) { for (int e = 0; e < 3; ++e) nxt[nn][e] = cur[e]; ++nn; }
+    }
+    np_ = nn;
+    for (int k = 0; k < nn; ++k) for (int e = 0; e < 3; ++e) poly[k][e] = nxt[k][e];
+    if (np_ == 0) return;
+  }
+  int nc = 0;
+  for (int k = 0; k < np_; ++k)
+    if (poly[k][2] <= margin) { for (int e = 0; e < 3; ++e) nxt[nc][e] = poly[k][e]; ++nc; }
+  int sel[4] = {0, 1, 2, 3}, nsel = nc < 4 ? nc : 4;
+  if (nc > B2_MAXCON_PER_PAIR) {
+    int i0 = 0;
+    for (int k = 1; k < nc; ++k) if (nxt[k][2] < nxt[i0][2]) i0 = k;
+    int i1 = 0; real dbest = -1;
+    for (int k = 0; k < nc; ++k) {
+      real dx = nxt[k][0] - nxt[i0][0], dy = nxt[k][1] - nxt[i0][1], d2 = dx * dx + dy * dy;
+      if (d2 > dbest) { dbest = d2; i1 = k; }
+    }
+    const real ex = nxt[i1][0] - nxt[i0][0], ey = nxt[i1][1] - nxt[i0][1];
+    int i2 = 0; real cbest = -1, cr2 = 0;
+    for (int k = 0; k < nc; ++k) {
+      real cr = ex * (nxt[k][1] - nxt[i0][1]) - ey * (nxt[k][0] - nxt[i0][0]);
+      if (fabs(cr) > cbest) { cbest = fabs(cr); i2 = k; cr2 = cr; }
+    }
+    int i3 = 0; real obest = -INFINITY;
+    for (int k = 0; k < nc; ++k) {
+      real cr = ex * (nxt[k][1] - nxt[i0][1]) - ey * (nxt[k][0] - nxt[i0][0]);
+      real o = cr2 > 0 ? -cr : cr;
+      if (o > obest) { obest = o; i3 = k; }
+    }
+    sel[0] = i0; sel[1] = i1; sel[2] = i2; nsel = 3;
+    if (obest > 0 && i3 != i0 && i3 != i1 && i3 != i2) { sel[3] = i3; nsel = 4; }
+  }
+  for (int q = 0; q < nsel; ++q) {
+    const real* pt = nxt[sel[q]];
+    const real cu = pt[0], cv = pt[1], cn = pt[2], hn = sr[axis] + (real)0.5 * cn;
+    lc.dist[q] = cn;
+    for (int c = 0; c < 3; ++c) lc.pos[q][c] = pr[c] + cu * Rr[3 * c + ru] + cv * Rr[3 * c + rv] + hn * nref[c];
+  }
+  const real fs = flip ? (real)-1 : (real)1;
+  lc.normal[0] = fs * nref[0]; lc.normal[1] = fs * nref[1]; lc.normal[2] = fs * nref[2];
+  lc.n = nsel;
+}
+
 // Narrowphase for one geom pair (types t1 <= t2). Normal points from geom1 to geom2.
 B2_DEV void narrowphase(LaneContacts& lc, int t1, int t2, const real* p1, const real* R1, const real* s1, const real* p2,
                         const real* R2, const real* s2, real margin) {
@@ -283,8 +447,10 @@ B2_DEV void narrowphase(LaneContacts& lc, int t1, int t2, const real* p1, const 
     sphere_box(lc, p1, s1[0], p2, R2, s2, margin);
   } else if (t1 == B2_GEOM_CAPSULE && t2 == B2_GEOM_BOX) {
     capsule_box(lc, p1, R1, s1, p2, R2, s2, margin);
+  } else if (t1 == B2_GEOM_BOX && t2 == B2_GEOM_BOX) {
+    box_box(lc, p1, R1, s1, p2, R2, s2, margin);
   }
-  // unsupported pairs (box-box, meshes, ...) are rejected on the host (engine.check_supported)
+  // unsupported pairs (meshes, height fields, ...) are rejected on the host (engine.check_supported)
 }
 
 // Contact frame rows [normal; t1; t2] from a normal and an optional tangent hint.

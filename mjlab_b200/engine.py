@@ -237,7 +237,7 @@ def derived_int_tables(m) -> dict[str, np.ndarray]:
   )
 
 
-SUPPORTED_PAIRS = {(0, 2), (0, 3), (0, 6), (2, 2), (2, 3), (3, 3), (2, 6), (3, 6)}  # (plane|sphere|capsule|box) subset
+SUPPORTED_PAIRS = {(0, 2), (0, 3), (0, 6), (2, 2), (2, 3), (3, 3), (2, 6), (3, 6), (6, 6)}  # (plane|sphere|capsule|box) subset
 
 
 def check_supported(m) -> None:

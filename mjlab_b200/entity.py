@@ -405,6 +405,18 @@ class Entity:
   def num_bodies(self) -> int:
     return len(self.body_names)
 
+  @property
+  def num_geoms(self) -> int:
+    return len(self.geom_names)
+
+  @property
+  def num_sites(self) -> int:
+    return len(self.site_names)
+
+  @property
+  def num_actuators(self) -> int:
+    return len(self.actuator_names)
+
   def find_bodies(self, keys, preserve_order=False):
     return _resolve(keys, self.body_names, preserve_order)
 

@@ -34,7 +34,7 @@ from .sim import MujocoCfg, Simulation, SimulationCfg
 
 _TORCH = {"f4": torch.float32, "i4": torch.int32, "i8": torch.int64, "u1": torch.uint8}
 _TASK_ROBOT = {"Mjlab-Velocity-Flat-Unitree-G1": ("g1", "flat"), "Mjlab-Velocity-Flat-Unitree-Go1": ("go1", "flat"),
-               "Mjlab-Velocity-Rough-Unitree-G1": ("g1", "rough")}
+               "Mjlab-Velocity-Rough-Unitree-G1": ("g1", "rough"), "Mjlab-Velocity-Rough-Unitree-Go1": ("go1", "rough")}
 
 
 def _default_sim_cfg() -> SimulationCfg:
@@ -216,9 +216,7 @@ class ManagerBasedRlEnv:
     self.device = device
     self.render_mode = render_mode
     self._lib = A.load_library()
-    if cfg.terrain == "rough" and cfg.robot != "g1":
-      raise ValueError("the rough-terrain scene is built for the G1 (box-box contacts of the Go1 trunk are not implemented)")
-    model = load_model(f"{cfg.robot}_flat" if cfg.terrain == "flat" else ("g1_rough_play" if cfg.play else "g1_rough"))
+    model = load_model(f"{cfg.robot}_flat" if cfg.terrain == "flat" else (f"{cfg.robot}_rough_play" if cfg.play else f"{cfg.robot}_rough"))
     self.sim = Simulation(cfg.num_envs, cfg.sim, model, device)
     dev = torch.device(device)
     self._dev = dev

@@ -309,11 +309,112 @@ class SOption:
   disableflags: int = 0
 
 
+class _OptView:
+  """`model.opt` of a `ModelDesc`: MuJoCo's nested option struct as a live view of the flat `opt_*` attributes, so code written
+  against `mujoco.MjModel` (`m.opt.timestep = 0.005`, tests/test_sim.py:62-72 of the reference) works unchanged."""
+
+  _NAMES = ("timestep", "gravity", "integrator", "cone", "solver", "iterations", "tolerance", "ls_iterations", "ls_tolerance",
+            "impratio", "disableflags", "ccd_iterations")
+
+  def __init__(self, model):
+    object.__setattr__(self, "_m", model)
+
+  def __getattr__(self, name):
+    if name in _OptView._NAMES:
+      m = object.__getattribute__(self, "_m")
+      if name == "ccd_iterations":
+        return getattr(m, "opt_ccd_iterations", 50)
+      return getattr(m, f"opt_{name}")
+    raise AttributeError(name)
+
+  def __setattr__(self, name, value):
+    if name not in _OptView._NAMES:
+      raise AttributeError(f"unknown option '{name}'")
+    setattr(object.__getattribute__(self, "_m"), f"opt_{name}", np.asarray(value, float) if name == "gravity" else value)
+
+
+class _Named:
+  """`model.body(i)` / `model.geom("name")` style accessor result: id and name."""
+
+  def __init__(self, kind, i, name):
+    self.kind, self.id, self.name = kind, i, name
+
+
 class ModelDesc:
   """Attribute bag of numpy arrays named after MjModel fields."""
 
   def __init__(self, **kw):
     self.__dict__.update(kw)
+
+  # ---- the parts of mujoco.MjModel's object API that mjlab-side code touches ------------------------------------------
+  @property
+  def opt(self) -> _OptView:
+    return _OptView(self)
+
+  @property
+  def stat(self):
+    from types import SimpleNamespace
+    return SimpleNamespace(meaninertia=getattr(self, "stat_meaninertia", 1.0))
+
+  def _named(self, kind: str, names_attr: str, key):
+    names = getattr(self, names_attr)
+    i = names.index(key) if isinstance(key, str) else int(key)
+    return _Named(kind, i, names[i])
+
+  def body(self, key): return self._named("body", "body_names", key)          # noqa: E704
+  def geom(self, key): return self._named("geom", "geom_names", key)          # noqa: E704
+  def joint(self, key): return self._named("joint", "jnt_names", key)         # noqa: E704
+  def jnt(self, key): return self._named("joint", "jnt_names", key)           # noqa: E704
+  def site(self, key): return self._named("site", "site_names", key)          # noqa: E704
+  def actuator(self, key): return self._named("actuator", "actuator_names", key)  # noqa: E704
+  def sensor(self, key): return self._named("sensor", "sensor_names", key)    # noqa: E704
+
+  # arrays copied verbatim from a mujoco.MjModel (same names, same layout)
+  _MJ_INTS = ("nq", "nv", "nu", "nbody", "njnt", "ngeom", "nsite", "nsensor", "nsensordata", "nmocap", "nkey")
+  _MJ_ARRAYS = (
+    "body_parentid", "body_rootid", "body_weldid", "body_mocapid", "body_jntnum", "body_jntadr", "body_dofnum",
+    "body_dofadr", "body_pos", "body_quat", "body_ipos", "body_iquat", "body_mass", "body_inertia", "body_subtreemass",
+    "body_invweight0", "jnt_type", "jnt_qposadr", "jnt_dofadr", "jnt_bodyid", "jnt_pos", "jnt_axis", "jnt_range",
+    "jnt_limited", "jnt_solref", "jnt_solimp", "jnt_margin", "jnt_stiffness", "dof_bodyid", "dof_jntid", "dof_parentid",
+    "dof_armature", "dof_damping", "dof_frictionloss", "dof_invweight0", "qpos0", "qpos_spring", "geom_type",
+    "geom_bodyid", "geom_pos", "geom_quat", "geom_size", "geom_contype", "geom_conaffinity", "geom_condim",
+    "geom_priority", "geom_friction", "geom_solref", "geom_solimp", "geom_solmix", "geom_margin", "geom_gap",
+    "geom_rbound", "geom_group", "geom_rgba", "site_bodyid", "site_pos", "site_quat", "actuator_trnid",
+    "actuator_gaintype", "actuator_biastype", "actuator_gainprm", "actuator_biasprm", "actuator_gear",
+    "actuator_forcelimited", "actuator_forcerange", "actuator_ctrllimited", "actuator_ctrlrange", "sensor_type",
+    "sensor_objtype", "sensor_objid", "sensor_reftype", "sensor_refid", "sensor_intprm", "sensor_dim", "sensor_adr",
+    "sensor_cutoff", "key_qpos", "key_qvel", "key_ctrl",
+  )
+
+  @staticmethod
+  def from_mjmodel(mj_model) -> "ModelDesc":
+    """In-process conversion of a compiled `mujoco.MjModel` (or any object with the same attribute surface) into the array
+    container the engine uploads - the `mjwarp.put_model(mjm)` half of sim/sim.py:139.  Arrays keep MuJoCo's names and layout;
+    names come from the `model.body(i).name` accessors; `<exclude>` pairs from `exclude_signature`; the derived collision tables
+    (candidate pairs, static-geom poses, geom field) are rebuilt by the same `collision_tables` the MJCF compiler uses."""
+    m = ModelDesc()
+    for k in ModelDesc._MJ_INTS:
+      setattr(m, k, int(getattr(mj_model, k)))
+    for k in ModelDesc._MJ_ARRAYS:
+      if hasattr(mj_model, k):
+        setattr(m, k, np.array(getattr(mj_model, k)))
+    for kind, n in (("body", m.nbody), ("jnt", m.njnt), ("geom", m.ngeom), ("site", m.nsite), ("actuator", m.nu), ("sensor", m.nsensor)):
+      acc = getattr(mj_model, {"jnt": "joint"}.get(kind, kind))
+      setattr(m, f"{kind}_names", [acc(i).name for i in range(n)])
+    o = mj_model.opt
+    m.opt_timestep, m.opt_gravity = float(o.timestep), np.array(o.gravity, float)
+    m.opt_integrator, m.opt_cone, m.opt_solver = int(o.integrator), int(o.cone), int(o.solver)
+    m.opt_iterations, m.opt_ls_iterations = int(o.iterations), int(o.ls_iterations)
+    m.opt_tolerance, m.opt_ls_tolerance, m.opt_impratio = float(o.tolerance), float(o.ls_tolerance), float(o.impratio)
+    m.opt_disableflags = int(o.disableflags)
+    m.opt_ccd_iterations = int(getattr(o, "ccd_iterations", 50))
+    m.stat_meaninertia = float(mj_model.stat.meaninertia)
+    # <exclude> body pairs: MuJoCo stores them as signatures (body1 << 16) + body2
+    sig = np.asarray(getattr(mj_model, "exclude_signature", np.zeros(0, np.int64))).astype(np.int64).reshape(-1)
+    excl = {(int(min(x >> 16, x & 0xFFFF)), int(max(x >> 16, x & 0xFFFF))) for x in sig}
+    m.exclude_pairs = np.array(sorted(excl), np.int32).reshape(-1, 2)
+    collision_tables(m, excl)
+    return m
 
   def fields(self):
     return {k: v for k, v in self.__dict__.items() if isinstance(v, np.ndarray)}
@@ -980,9 +1081,9 @@ def _build_geom_field(m: "ModelDesc", fld: np.ndarray, body_parentid, excl) -> N
     b = m.geom_bodyid[g]
     if any((min(b, fb), max(b, fb)) in excl for fb in fbody):
       raise NotImplementedError("<exclude> between a moving body and a field body")
-    if m.geom_type[g] not in (GEOM_SPHERE, GEOM_CAPSULE):
-      raise NotImplementedError(f"geom '{m.geom_names[g]}': only spheres and capsules collide with a geom field "
-                                "(box-box / mesh narrowphase is not implemented)")
+    if m.geom_type[g] not in (GEOM_SPHERE, GEOM_CAPSULE, GEOM_BOX):
+      raise NotImplementedError(f"geom '{m.geom_names[g]}': only spheres, capsules and boxes collide with a geom field "
+                                "(mesh / ellipsoid / cylinder narrowphase is not implemented)")
     if m.geom_type[g] > GEOM_BOX or np.any(m.geom_type[fld] != GEOM_BOX):
       raise NotImplementedError("geom fields hold boxes only")
     q.append(g)

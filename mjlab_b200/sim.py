@@ -64,6 +64,7 @@ class MujocoCfg:
     model.opt_tolerance = float(self.tolerance)
     model.opt_ls_iterations = int(self.ls_iterations)
     model.opt_ls_tolerance = float(self.ls_tolerance)
+    model.opt_ccd_iterations = int(self.ccd_iterations)   # piped like the reference (sim.py:66-79); no CCD in the supported subset
 
 
 @dataclass(kw_only=True)
@@ -79,8 +80,10 @@ class SimulationCfg:
   nan_guard: NanGuardCfg = field(default_factory=NanGuardCfg)   # sim.py:97; off by default
 
 
-class TensorBridge:
-  """Read-only attribute bag of torch tensors (WarpBridge analogue)."""
+class WarpBridge:
+  """Read-only attribute bag of torch tensors: the reference's `WarpBridge` (sim/sim_data.py:177-240) without Warp underneath.
+  Attributes are the engine's own device buffers as `torch.Tensor`s (stable addresses for the process lifetime); assigning an
+  attribute raises, in-place writes (`bridge.qpos[:] = x`, index assignment) go straight to the buffer the kernels read."""
 
   def __init__(self, fields: dict[str, Any]) -> None:
     object.__setattr__(self, "_fields", fields)
@@ -93,7 +96,7 @@ class TensorBridge:
 
   def __setattr__(self, name: str, value: Any) -> None:
     raise AttributeError(
-      f"Cannot set attribute '{name}' on TensorBridge. This wrapper is read-only to preserve memory addresses "
+      f"Cannot set attribute '{name}' on WarpBridge. This wrapper is read-only to preserve memory addresses "
       f"for CUDA graphs. Use in-place operations instead: obj.{name}[:] = value"
     )
 
@@ -105,6 +108,9 @@ class TensorBridge:
 
   def clear_cache(self) -> None:  # API parity; tensors are not cached wrappers here
     pass
+
+
+TensorBridge = WarpBridge   # round-1 name
 
 
 class _Opt:
@@ -164,7 +170,11 @@ def _natural_shape(m: mjcf.ModelDesc, attr: str) -> tuple[int, ...]:
 class Simulation:
   """World-batched physics on one B200 (one process per GPU)."""
 
-  def __init__(self, num_envs: int, cfg: SimulationCfg, model: mjcf.ModelDesc, device: str):
+  def __init__(self, num_envs: int, cfg: SimulationCfg, model, device: str):
+    """`model`: a `mjcf.ModelDesc`, or a compiled `mujoco.MjModel` (any object with MjModel's attribute surface), which is
+    converted in-process (`ModelDesc.from_mjmodel`, the put_model half of sim/sim.py:139)."""
+    if not isinstance(model, mjcf.ModelDesc):
+      model = mjcf.ModelDesc.from_mjmodel(model)
     if not str(device).startswith("cuda"):
       raise RuntimeError("mjlab_b200.Simulation requires a CUDA device (there is no CPU fallback)")
     if not torch.cuda.is_available():
@@ -313,11 +323,20 @@ class Simulation:
     return self._mj_model
 
   @property
-  def data(self) -> TensorBridge:
+  def data(self) -> WarpBridge:
     return self._data_bridge
 
   @property
-  def model(self) -> TensorBridge:
+  def model(self) -> WarpBridge:
+    return self._model_bridge
+
+  # the reference exposes the raw mjwarp structs next to the torch bridges (sim.py:193-207); here they are the same objects
+  @property
+  def wp_data(self) -> WarpBridge:
+    return self._data_bridge
+
+  @property
+  def wp_model(self) -> WarpBridge:
     return self._model_bridge
 
   @property

@@ -5,7 +5,7 @@ input data, not code):
 
     python tools/make_models.py
 
-Writes mjlab_b200/assets/{g1_flat,go1_flat,g1_rough,g1_rough_play}.npz (rough: the ROUGH_TERRAINS_CFG box grid with the
+Writes mjlab_b200/assets/{g1,go1}_{flat,rough,rough_play}.npz (rough: the ROUGH_TERRAINS_CFG box grid with the
 fixed terrain seed 0 of SURVEY.md section 8(d), config 4).  Nothing at run time reads
 /root/reference; the GPU box only sees the .npz files.
 """
@@ -33,9 +33,10 @@ if __name__ == "__main__":
     m.save(out / f"{which}_flat.npz")
     print(which, dict(nq=m.nq, nv=m.nv, nu=m.nu, nbody=m.nbody, ngeom=m.ngeom, nsite=m.nsite,
                       nsensordata=m.nsensordata, npair=m.npair, meaninertia=round(m.stat_meaninertia, 5)))
-  for name, play in (("g1_rough", False), ("g1_rough_play", True)):
+  for name, play in (("g1_rough", False), ("g1_rough_play", True), ("go1_rough", False), ("go1_rough_play", True)):
+    which = name.split("_")[0]
     ter = terrains.generate(terrains.rough_terrains_cfg(play=play, seed=0))
-    m = robots.build_scene(SRC["g1"].read_text(), "g1", terrain=ter).compile()
+    m = robots.build_scene(SRC[which].read_text(), which, terrain=ter).compile()
     m.terrain_origins = np.asarray(ter.origins, float)
     m.terrain_size = np.asarray(ter.cfg.size, float)
     m.save(out / f"{name}.npz")
