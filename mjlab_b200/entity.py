@@ -353,7 +353,7 @@ class Entity:
     pre = f"{name}/" if prefix is None else prefix
     self.name, self._sim = name, sim
     sel = lambda names: [i for i, n in enumerate(names) if n.startswith(pre)]  # noqa: E731
-    body_ids, geom_ids, site_ids = sel(m.body_names), sel(m.geom_names), sel(m.site_names)
+    body_ids, geom_ids, site_ids = [i for i in sel(m.body_names) if i != 0], sel(m.geom_names), sel(m.site_names)   # never the world body
     jall = [j for j in range(m.njnt) if m.jnt_names[j].startswith(pre)]
     free = [j for j in jall if m.jnt_type[j] == 0]
     joints = [j for j in jall if m.jnt_type[j] != 0]

@@ -87,6 +87,40 @@ def env_origins_grid(num_envs: int, spacing: float) -> np.ndarray:
   return o
 
 
+class _Scene(dict):
+  """`env.scene`: entities and sensors by name (scene/scene.py:97-130).  Sensor views are built on first access from the compiled
+  model's sensors (scene/scene.py:196-198 auto-discovers the XML sensors the same way): contact sensors by their cfg name,
+  builtin sensors by their full name; `feet_ground_contact` shares the air-time state the fused env kernels advance."""
+
+  def __init__(self, env: "ManagerBasedRlEnv", entities: dict):
+    super().__init__(entities)
+    self._env = env
+
+  @property
+  def env_origins(self) -> torch.Tensor:
+    return self._env._buf["env_origins"]
+
+  @property
+  def num_envs(self) -> int:
+    return self._env.num_envs
+
+  def __missing__(self, name: str):
+    from .sensors import SENS_CONTACT, BuiltinSensor, ContactSensor
+    sim = self._env.sim
+    m = sim.mj_model
+    names = list(m.sensor_names)
+    if name in names:
+      s = BuiltinSensor(name, sim)
+    elif any(n.startswith(name + "_") and int(m.sensor_type[i]) == SENS_CONTACT for i, n in enumerate(names)):
+      fused = name == "feet_ground_contact"
+      s = ContactSensor(name, sim, air_state=self._env._buf["air_state"] if fused else None,
+                        air_last_time=self._env._buf["air_last_time"] if fused else None)
+    else:
+      raise KeyError(f"'{name}' is neither an entity nor a sensor of the scene; sensors: {names}")
+    self[name] = s
+    return s
+
+
 class _LogView(Mapping):
   """`extras["log"]`: the reference's per-step log entries computed lazily from a snapshot of the device log sums."""
 
@@ -261,7 +295,7 @@ class ManagerBasedRlEnv:
 
     # ---- scene / managers (facades over the same buffers) --------------------------------------------
     self.robot = Entity("robot", self.sim, joint_pos_target=self._buf["joint_pos_target"], encoder_bias=self._buf["encoder_bias"])
-    self.scene = {"robot": self.robot}
+    self.scene = _Scene(self, {"robot": self.robot})
     self.action_manager = _ActionManager(self)
     self.command_manager = _CommandManager(self)
     self.reward_manager = _RewardManager(self)

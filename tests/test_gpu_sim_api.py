@@ -291,3 +291,33 @@ def test_go1_rough_env_steps():
     obs, rew, term, trunc, _ = env.step(torch.rand(64, env.vcfg.nj, device=DEV, generator=g) * 2 - 1)
   assert torch.isfinite(obs["policy"]).all() and torch.isfinite(rew).all()
   assert int(env.sim.data.ncon.sum()) > 0 and int(env.sim.data.ncon_dropped.sum()) == 0
+
+
+def test_env_scene_sensor_views():
+  """`env.scene[...]` hands out the reference's sensor objects (contact_sensor.py:231-281, builtin_sensor.py:327-340) over the
+  buffers the fused kernels write: feet air-time state, contact found / force slices, IMU slices."""
+  from mjlab_b200.env import ManagerBasedRlEnv, VelocityEnvCfg
+  env = ManagerBasedRlEnv(VelocityEnvCfg(robot="go1", num_envs=32, seed=2), DEV)
+  env.reset()
+  feet = env.scene["feet_ground_contact"]
+  assert env.scene["feet_ground_contact"] is feet
+  saw_first = False
+  for _ in range(40):
+    env.step(torch.zeros(32, env.vcfg.nj, device=DEV))
+    d = feet.data
+    assert d.found.shape == (32, 4) and d.force.shape == (32, 4, 3)
+    assert torch.equal(d.current_air_time, env._buf["air_state"][:, 0]) and torch.equal(d.current_contact_time, env._buf["air_state"][:, 2])
+    fc = feet.compute_first_contact(env.step_dt)
+    assert torch.equal(fc, (d.current_contact_time > 0) & (d.current_contact_time < env.step_dt + 1e-8))
+    saw_first |= bool(fc.any())
+    in_contact = d.found > 0
+    assert torch.all(d.current_contact_time[in_contact] > 0) and torch.all(d.current_air_time[in_contact] == 0)
+  assert saw_first and bool((feet.data.found > 0).any())
+  imu = env.scene["robot/imu_ang_vel"]
+  i = env.sim.mj_model.sensor_names.index("robot/imu_ang_vel")
+  a = int(env.sim.mj_model.sensor_adr[i])
+  assert torch.equal(imu.data, env.sim.data.sensordata[:, a: a + 3])
+  assert env.scene["nonfoot_ground_touch"].data.found.shape[0] == 32
+  with pytest.raises(KeyError):
+    env.scene["no_such_thing"]
+  assert env.scene.env_origins.shape == (32, 3)
