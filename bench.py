@@ -47,8 +47,15 @@ def parse():
   ap.add_argument("--warmup", type=int, default=20)
   ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
   ap.add_argument("--model", default="g1_flat")
-  ap.add_argument("--task", default="velocity", choices=["velocity", "tracking", "rough"],
-                  help="velocity (BASELINE configs 2/3, the headline) or tracking (config 5: synthetic clip, domain randomisation on)")
+  ap.add_argument("--task", default="velocity", choices=["velocity", "tracking", "rough", "train"],
+                  help="velocity (the headline: full env step), rough (BASELINE config 4), tracking (config 5: synthetic clip, domain "
+                       "randomisation on), train (config 3: full PPO iteration = 24 env steps + 5 x 4 mini-batch updates with the gradient all-reduce)")
+  ap.add_argument("--mode", default="env", choices=["env", "physics"],
+                  help="env: ManagerBasedRlEnv.step (measure_env_sps); physics: the decimation x sim.step() loop alone "
+                       "(scripts/benchmarks/measure_throughput.py:82-101, BASELINE config 2 with --model go1_flat)")
+  ap.add_argument("--prewarm-s", type=float, default=1.5, help="untimed env steps for this many seconds before the warm-up steps "
+                       "(clocks and caches reach steady state; declared in config.prewarm_s)")
+  ap.add_argument("--matmul-precision", default="highest", choices=["highest", "high"], help="--task train: fp32 (default) or TF32 GEMMs")
   ap.add_argument("--num-envs", type=int, default=None, help="envs per GPU (default 4096; 8192 for --task rough, BASELINE config 4)")
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-roofline-pass", action="store_true")
@@ -56,7 +63,7 @@ def parse():
                   help="forward pass after resets: all envs when any env reset (the reference's behaviour) or only the reset envs")
   args = ap.parse_args()
   if args.task == "rough":
-    args.model = "g1_rough"
+    args.model = args.model.split("_")[0] + "_rough"
   if args.num_envs is None:
     args.num_envs = 8192 if args.task == "rough" else NUM_ENVS
   return args
@@ -198,51 +205,70 @@ def cpu_env_steps_per_s(name: str, cores: int, worlds_per_core: int, nsteps: int
   return cores * worlds_per_core * nsteps / dt, dt
 
 
-def cpu_compiled_env_steps_per_s(name: str, cores: int, target_s: float = 12.0):
-  """env-steps/s of the compiled CPU build (oracle/cport: the same algorithm, float64, one thread per core) on a bounded sample:
-  per env step one action -> ctrl write, `decimation` physics steps and the numpy env stage (oracle/envstep.py) on the batch."""
-  from types import SimpleNamespace as NS
+class CpuEnv:
+  """The SAME env step on the host cores: compiled all-cores CPU build of the physics (oracle/cport, float64) + the numpy env
+  stage (oracle/envstep.py), `nworld` worlds, random actions, staggered episode lengths, resets and the forward pass after
+  resets included - the workload of the own arm, measured on the CPU."""
 
-  import mjlab_b200
-  from mjlab_b200 import envcfg
-  from oracle import envstep as OE
-  from oracle.cport import CpuSim
-  m = mjlab_b200.load_model(name)
-  m.opt_timestep, m.opt_iterations, m.opt_ls_iterations = 0.005, 10, 20
-  cfg = envcfg.velocity_cfg(m, name.split("_")[0])
-  nworld = 64 * cores
-  sim = CpuSim(m, nworld, 35, 300)
-  sim.qpos[:] = m.key_qpos[0]
-  rng = np.random.default_rng(7)
-  s = OE.make_state(cfg, nworld)
-  fields = ("qpos", "qvel", "ctrl", "xpos", "xquat", "subtree_com", "cvel", "site_xpos", "sensordata", "qacc_warmstart", "qacc")
+  def __init__(self, name: str, nworld: int, cores: int, forward: bool = True):
+    from types import SimpleNamespace as NS
 
-  def view():
-    d = NS(**{f: getattr(sim, f) for f in fields})
-    d.time = sim.time.reshape(-1)
+    import mjlab_b200
+    from mjlab_b200 import envcfg
+    from oracle import envstep as OE
+    from oracle.cport import CpuSim
+    self.OE, self.NS = OE, NS
+    m = mjlab_b200.load_model(name)
+    m.opt_timestep, m.opt_iterations, m.opt_ls_iterations = 0.005, 10, 20
+    self.m, self.cfg = m, envcfg.velocity_cfg(m, name.split("_")[0])
+    self.nworld, self.cores, self.forward = nworld, cores, forward
+    self.sim = CpuSim(m, nworld, 35, 300)
+    self.sim.qpos[:] = m.key_qpos[0]
+    self.rng = np.random.default_rng(7)
+    self.s = OE.make_state(self.cfg, nworld)
+    self.s.episode_length[:] = self.rng.integers(0, self.cfg.max_episode_length, nworld)   # rsl_rl's init_at_random_ep_len
+    self.fields = ("qpos", "qvel", "ctrl", "xpos", "xquat", "subtree_com", "cvel", "site_xpos", "sensordata", "qacc_warmstart", "qacc")
+    self.nreset = 0
+
+  def view(self):
+    d = self.NS(**{f: getattr(self.sim, f) for f in self.fields})
+    d.time = self.sim.time.reshape(-1)
     return d
 
-  def env_step():
-    d = view()
-    OE.apply_action(cfg, s, d, rng.uniform(-1, 1, (nworld, cfg.nj)))
+  def step(self):
+    OE, cfg, s, sim = self.OE, self.cfg, self.s, self.sim
+    d = self.view()
+    OE.apply_action(cfg, s, d, self.rng.uniform(-1, 1, (self.nworld, cfg.nj)))
     for _ in range(DECIMATION):
-      sim.step(1, cores)
+      sim.step(1, self.cores)
       OE.update_air_time(cfg, s, sim.sensordata.astype(np.float32), d.time)
-    OE.post(cfg, m, s, d)
-    OE.obs_stage(cfg, m, s, d)
+    OE.post(cfg, self.m, s, d)
+    self.nreset += int(s.reset_buf.sum())
+    if self.forward and s.reset_buf.any():
+      sim.forward(self.cores)       # sim.forward() over all envs when any env was reset (manager_based_rl_env.py:295-298)
+    OE.obs_stage(cfg, self.m, s, d)
 
-  env_step()  # page in the buffers
+
+def cpu_compiled_env_steps_per_s(name: str, cores: int, nworld: int, target_s: float = 12.0, steps: int | None = None, warmup: int = 1):
+  """env-steps/s of the CPU arm on `nworld` worlds.  `steps` given: exactly that many timed env steps after `warmup`; else a
+  bounded sample of about `target_s` seconds."""
+  env = CpuEnv(name, nworld, cores)
+  env.step()  # page in the buffers
   t0 = time.perf_counter()
-  env_step()
+  env.step()
   one = time.perf_counter() - t0
-  nsteps = int(max(3, min(200, target_s / max(one, 1e-3))))
+  for _ in range(max(0, warmup - 2)):
+    env.step()
+  nsteps = int(steps) if steps is not None else int(max(3, min(200, target_s / max(one, 1e-3))))
+  env.nreset = 0
   t0 = time.perf_counter()
   for _ in range(nsteps):
-    env_step()
+    env.step()
   secs = time.perf_counter() - t0
-  desc = (f"{nworld} worlds x {nsteps} env steps (x{DECIMATION} physics steps + numpy env stage; the forward pass after resets is not "
-          f"included), compiled CPU build of the same algorithm (oracle/cport, g++ -O3, float64), {cores} threads, {secs:.1f} s")
-  return nworld * nsteps / secs, secs, desc
+  desc = (f"{nworld} worlds x {nsteps} env steps (each: action -> ctrl, {DECIMATION} physics steps + air-time update, terminations, rewards, "
+          f"resets, forward pass after resets, commands, pushes, observations; {env.nreset / nsteps:.1f} resets per step), compiled CPU build "
+          f"of the same algorithm (oracle/cport, g++ -O3, float64) + numpy env stage, {cores} threads, {secs:.1f} s")
+  return nworld * nsteps / secs, secs, desc, nsteps
 
 
 def run_reference(args):
@@ -250,18 +276,20 @@ def run_reference(args):
   if rank != 0:
     return
   cores = os.cpu_count() or 1
-  k, w = args.steps, args.warmup
-  value, secs, desc = cpu_compiled_env_steps_per_s(args.model, cores, target_s=20.0)
-  ms = 1e3 * 64 * cores / value   # one "step" of this arm = one env step of its 64 x cores worlds
+  k, w = args.steps, max(args.warmup, 1)
+  value, secs, desc, nsteps = cpu_compiled_env_steps_per_s(args.model, cores, args.num_envs, steps=k, warmup=w)
   line = {
     "impl": "reference", "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
-    "steps": k, "warmup": w, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-    "dtype": "f64", "data": "synthetic",
+    "steps": k, "warmup": w, "ms_per_step": 1e3 * secs / nsteps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    "dtype": "f64", "data": "synthetic", "same_config": True,
     "config": {"workload": workload_name(args.model, args.num_envs, args.forward_mode), "num_envs_per_gpu": args.num_envs,
-               "decimation": DECIMATION, "timestep": 0.005},
+               "decimation": DECIMATION, "timestep": 0.005, "nconmax": 35, "njmax": 300,
+               "actions": "U(-1,1) redrawn every env step (random policy)", "forward_mode": "reference"},
     "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": desc},
     "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    "note": "mujoco / mujoco_warp are not installable on this image: the CPU arm is a compiled all-cores CPU build of the same algorithm",
+    "note": "mujoco / mujoco_warp cannot be installed on this image or on the GPU box (profiles/r02_reference_install_attempt.log): the CPU "
+            "arm is a compiled all-cores CPU build of the same algorithm on the same workload (one step = one env step of all "
+            f"{args.num_envs} worlds), not MuJoCo C",
   }
   print(json.dumps(line))
 
@@ -332,10 +360,42 @@ def run_b200(args):
       dist.barrier()
     torch.cuda.synchronize()
 
+  physics = args.mode == "physics"
+  if physics:
+    # scripts/benchmarks/measure_throughput.py:82-101 (`measure_physics_sps`): the decimation x sim.step() loop alone, counted in
+    # env steps.  The controls are redrawn every env step through the action path (process_action + ctrl write, SURVEY 8(d)
+    # config 2), so the robots keep moving; no managers, no resets.
+    lib_, pm_, pd_, pe_ = env._lib, C.byref(sim._cm), C.byref(sim._cd), C.byref(env._ce)
+    gph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream(dev)
+    torch.cuda.synchronize()
+    with torch.cuda.stream(side):
+      with torch.cuda.graph(gph, stream=side):
+        E.check_call(lib_, lib_.b2_env_action(pm_, pd_, pe_, side.cuda_stream))
+        E.check_call(lib_, lib_.b2_substeps(pm_, pd_, DECIMATION, side.cuda_stream))
+    torch.cuda.current_stream().wait_stream(side)
+
+    def do_step(a):
+      env._buf["action_in"].copy_(a, non_blocking=True)
+      gph.replay()
+  else:
+    def do_step(a):
+      return env.step(a)
+
+  # declared pre-warm: untimed steps for `prewarm_s` seconds so that clocks, instruction caches and the L2-resident model
+  # tables are in steady state before the W warm-up steps (r01: with 5 warm-up steps alone the first timed steps ran 10 % slow)
+  t_pre = time.perf_counter()
+  npre = 0
+  pw = rand_actions(16)
+  while time.perf_counter() - t_pre < args.prewarm_s:
+    for k in range(16):
+      do_step(pw[k])
+    torch.cuda.synchronize()
+    npre += 16
   warm = max(args.warmup, 3)
   wa = rand_actions(warm)
   for k in range(warm):
-    env.step(wa[k])
+    do_step(wa[k])
   barrier()
 
   # ---- timed region: device-resident inputs ----------------------------------------------------
@@ -349,7 +409,7 @@ def run_b200(args):
   for k in range(args.steps):
     flush.zero_()
     ev[k][0].record()
-    env.step(acts[k])
+    do_step(acts[k])
     ev[k][1].record()
     resets += env._buf["any_reset"][0]
   barrier()
@@ -365,12 +425,18 @@ def run_b200(args):
     host_actions.copy_(host_all[k])
     flush.zero_()
     ev2[k][0].record()
-    obs, rew, term, trunc, _ = env.step(host_actions)      # the H2D copy of the action batch is inside step()
-    dev_result[:, : cfg.n_obs_policy] = obs["policy"]
-    dev_result[:, cfg.n_obs_policy: cfg.n_obs_policy + cfg.n_obs_critic] = obs["critic"]
-    dev_result[:, -3] = rew
-    dev_result[:, -2] = term
-    dev_result[:, -1] = trunc
+    if physics:
+      do_step(host_actions)                                  # H2D copy of the action batch, then the physics loop
+      dev_result.zero_()
+      dev_result[:, : m.nq] = sim.data.qpos                  # the state a caller of sim.step() reads back
+      dev_result[:, m.nq: m.nq + m.nv] = sim.data.qvel
+    else:
+      obs, rew, term, trunc, _ = env.step(host_actions)      # the H2D copy of the action batch is inside step()
+      dev_result[:, : cfg.n_obs_policy] = obs["policy"]
+      dev_result[:, cfg.n_obs_policy: cfg.n_obs_policy + cfg.n_obs_critic] = obs["critic"]
+      dev_result[:, -3] = rew
+      dev_result[:, -2] = term
+      dev_result[:, -1] = trunc
     host_result.copy_(dev_result, non_blocking=True)
     ev2[k][1].record()
     ev2[k][1].synchronize()  # the policy consumes the observations before it can produce the next action
@@ -403,11 +469,14 @@ def run_b200(args):
       trk = args.task == "tracking"
       timed("k_env_action", lambda st: (lib.b2_trk_action if trk else lib.b2_env_action)(pm, pd, pe, st))
       for _ in range(DECIMATION):
-        timed("k_smooth", lambda st: lib.b2_stage(pm, pd, 0, 1, st))
+        timed("k_smooth", lambda st: lib.b2_stage(pm, pd, 4, 1, st))
+        timed("k_order", lambda st: lib.b2_stage(pm, pd, 5, 1, st))
         timed("k_solve", lambda st: lib.b2_stage(pm, pd, 1, 1, st))
         timed("k_post", lambda st: lib.b2_stage(pm, pd, 2, 1, st))
-        if not trk:
+        if not trk and not physics:
           timed("k_env_airtime", lambda st: lib.b2_env_airtime(pm, pd, pe, st))
+      if physics:
+        continue
       timed("k_env_post", lambda st: (lib.b2_trk_post if trk else lib.b2_env_post)(pm, pd, pe, st))
       timed("forward_after_reset", lambda st: lib.b2_forward_masked(pm, pd, mask, gate, st))
       timed("k_env_obs", lambda st: (lib.b2_trk_obs if trk else lib.b2_env_obs)(pm, pd, pe, 1, st))
@@ -415,8 +484,11 @@ def run_b200(args):
     barrier()
     avg = {k: statistics.mean(a.elapsed_time(b) for a, b in v) for k, v in times.items()}
     per_step = {k: avg[k] * len(v) / nroof for k, v in times.items()}
+    # the graph replay's own time against the sum of its kernels timed one by one (eager launches): what is left is launch
+    # gaps inside the graph and the action copy; negative = the graph packs the kernels tighter than eager launches do
+    per_step["graph_step_minus_kernel_sum"] = elapsed_ms / args.steps - sum(per_step.values())
     b_smooth, b_solve = algorithmic_bytes(m)
-    b_env = DECIMATION * (b_smooth + b_solve) + 4 * (cfg.n_obs_policy + cfg.n_obs_critic + nj + 3)   # B_env
+    b_env = DECIMATION * (b_smooth + b_solve) + (0 if physics else 4 * (cfg.n_obs_policy + cfg.n_obs_critic + nj + 3))   # B_env
     peaks = {}
     try:
       peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
@@ -440,7 +512,7 @@ def run_b200(args):
 
   # ---- secondary number: forward pass restricted to the reset envs (not the reference's behaviour; reported, not the headline)
   alt = None
-  if args.forward_mode == "reference" and not args.no_roofline_pass:
+  if args.forward_mode == "reference" and not args.no_roofline_pass and not physics:
     env2 = make_env("masked")
     env2.reset()
     env2.episode_length_buf = env.episode_length_buf.clone()
@@ -477,13 +549,16 @@ def run_b200(args):
       "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
       "warmup": warm, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
       "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-      "config": {"workload": workload_name(args.model, nw, args.forward_mode, args.task), "num_envs_per_gpu": nw, "decimation": DECIMATION,
+      "config": {"workload": (f"{args.model}: process_action + ctrl write, then {DECIMATION} x sim.step() (measure_physics_sps: physics only, "
+                              f"no managers, no resets), {nw} envs/GPU - one CUDA graph" if physics else
+                              workload_name(args.model, nw, args.forward_mode, args.task)), "mode": args.mode, "num_envs_per_gpu": nw, "decimation": DECIMATION,
+                 "prewarm_s": args.prewarm_s, "prewarm_steps": npre,
                  "timestep": 0.005, "nconmax": 35, "njmax": 300, "parallelism": f"replicas x{world} (no physics collective)",
                  "l2": "256 MiB flush between timed steps", "actions": "U(-1,1) redrawn every env step (random policy)",
                  "forward_mode": args.forward_mode, "mean_resets_per_step": mean_resets,
                  "mean_solver_niter": niter, "mean_nefc": nefc, "mean_ncon": ncon},
       "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": nw * nj * 4, "d2h_bytes_per_step": nw * nout * 4},
-      "gpu_launches": args.steps * env.launches_per_step,
+      "gpu_launches": args.steps * ((1 + 4 * DECIMATION) if physics else env.launches_per_step),
       "clocks": clk,
       "wall_s": t_wall,
     }
@@ -491,12 +566,109 @@ def run_b200(args):
       line["roofline"] = roof
     if alt is not None:
       line["config"]["alt_masked_forward"] = alt
-    if world == 1 and not args.no_cpu_baseline and args.task in ("velocity", "rough"):
+    if world == 1 and not args.no_cpu_baseline and args.task in ("velocity", "rough") and not physics:
       cores = os.cpu_count() or 1
-      v, secs, desc = cpu_compiled_env_steps_per_s(args.model, cores, target_s=12.0)
+      v, secs, desc, _ = cpu_compiled_env_steps_per_s(args.model, cores, nw, target_s=12.0)
       line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": desc}
       v1, secs1 = cpu_env_steps_per_s(args.model, 1, 4, 2)
       line["cpu_baseline"]["numpy_oracle_1core"] = {"value": v1, "sample": f"4 worlds x 2 env steps, oracle/mjstep.py + oracle/envstep.py (the independent checker), {secs1:.1f} s"}
+    print(json.dumps(line))
+  if world > 1:
+    dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------
+# --task train: BASELINE config 3, the full PPO iteration (the one path of the reference with a collective)
+# ---------------------------------------------------------------------------------------------
+def run_train(args):
+  """One step = one PPO iteration of the reference's training loop (rsl_rl OnPolicyRunner.learn with config/g1/rl_cfg.py:10-39):
+  24 env steps x num_envs envs with policy inference (roll-out), GAE, then 5 epochs x 4 mini-batches of forward / backward /
+  gradient all-reduce over the ranks / clip / Adam with the KL-adaptive learning rate.  value = 24 x num_envs x n_gpus / iteration
+  time; fp32 GEMMs unless --matmul-precision high."""
+  import torch
+  import torch.distributed as dist
+
+  from mjlab_b200.env import ManagerBasedRlEnv, VelocityEnvCfg
+  from mjlab_b200.ppo import OnPolicyRunner, PpoCfg
+  from mjlab_b200.vecenv import RslRlVecEnvWrapper
+
+  world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+  torch.cuda.set_device(local)
+  dev = f"cuda:{local}"
+  if world > 1:
+    dist.init_process_group("nccl", device_id=torch.device(dev))
+  nw = args.num_envs
+  robot = args.model.split("_")[0]
+  env = ManagerBasedRlEnv(VelocityEnvCfg(robot=robot, num_envs=nw, seed=42 + rank, forward_mode=args.forward_mode), dev)
+  pcfg = PpoCfg(matmul_precision=args.matmul_precision)
+  runner = OnPolicyRunner(RslRlVecEnvWrapper(env), pcfg)
+  T = pcfg.num_steps_per_env
+
+  def barrier():
+    torch.cuda.synchronize()
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  # graph captures (roll-out graph on iteration 1, update graphs after two eager updates) + steady state, then W warm-ups
+  runner.learn(4)
+  t_pre = time.perf_counter()
+  while time.perf_counter() - t_pre < args.prewarm_s:
+    runner.learn(1)
+    torch.cuda.synchronize()
+  warm = max(args.warmup, 3)
+  runner.learn(warm)
+  barrier()
+  clocks = Clocks(local)
+  clocks.start()
+  ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * args.steps)]
+  barrier()
+  t_wall0 = time.perf_counter()
+  for k in range(args.steps):
+    ev[3 * k].record()
+    ro = runner.collect()
+    ev[3 * k + 1].record()
+    runner.update(ro)
+    ev[3 * k + 2].record()
+    runner.iteration += 1
+  barrier()
+  t_wall = time.perf_counter() - t_wall0
+  ro_ms = sum(ev[3 * k].elapsed_time(ev[3 * k + 1]) for k in range(args.steps))
+  up_ms = sum(ev[3 * k + 1].elapsed_time(ev[3 * k + 2]) for k in range(args.steps))
+  # e2e: the public API (learn), whose iteration reads its metrics back to the host (reward, episode statistics, KL, lr)
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  barrier()
+  e0.record()
+  hist = runner.learn(args.steps)
+  e1.record()
+  barrier()
+  e2e_ms = e0.elapsed_time(e1)
+  clk = clocks.stop()
+  t = torch.tensor([ro_ms + up_ms, e2e_ms, ro_ms, up_ms], dtype=torch.float64, device=dev)
+  if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  elapsed_ms, e2e_ms, ro_ms, up_ms = t.tolist()
+  total = args.steps * T * nw * world
+  if rank == 0:
+    nparam = sum(p.numel() for p in runner.policy.parameters())
+    nmb = pcfg.num_learning_epochs * pcfg.num_mini_batches
+    line = {
+      "metric": "env-steps/s", "value": total / (elapsed_ms * 1e-3), "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
+      "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+      "dtype": "f32" if args.matmul_precision == "highest" else "tf32 GEMMs (physics f32)", "data": "synthetic",
+      "config": {"workload": f"{args.model} velocity task, full PPO train iteration (BASELINE config 3): {T} env steps x {nw} envs/GPU with policy "
+                             f"inference, GAE, {pcfg.num_learning_epochs} epochs x {pcfg.num_mini_batches} mini-batches (MLP 512-256-128 ELU, obs normalisation, "
+                             "adaptive learning rate), gradient all-reduce over the ranks", "task": "train", "num_envs_per_gpu": nw,
+                 "decimation": DECIMATION, "timestep": 0.005, "parallelism": f"dp{world}: one world batch per rank, {nmb} all-reduces of {4 * (nparam + 1)} B per iteration",
+                 "matmul_precision": args.matmul_precision, "prewarm_s": args.prewarm_s, "l2": "inputs larger than L2: the roll-out storage of one iteration is "
+                 f"{4 * T * nw * (env.vcfg.n_obs_policy + env.vcfg.n_obs_critic + 3 * env.vcfg.nj + 5) / 2**20:.0f} MiB",
+                 "iteration_split_ms": {"rollout": ro_ms / args.steps, "update": up_ms / args.steps},
+                 "update_path": ("per mini-batch: graph (forward + backward) -> NCCL all-reduce -> graph (clip + Adam)" if world > 1 else "one CUDA graph")},
+      "e2e": {"value": total / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 4 * 11},
+      "gpu_launches": args.steps * (T * env.launches_per_step),
+      "clocks": clk, "wall_s": t_wall,
+      "last_iteration": {k: hist[-1][k] for k in ("mean_step_reward", "kl", "lr", "mean_episode_length")},
+    }
     print(json.dumps(line))
   if world > 1:
     dist.destroy_process_group()
@@ -506,5 +678,7 @@ if __name__ == "__main__":
   a = parse()
   if a.impl == "reference":
     run_reference(a)
+  elif a.task == "train":
+    run_train(a)
   else:
     run_b200(a)

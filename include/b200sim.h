@@ -267,10 +267,11 @@ int b2_forward(const b2_model* m, b2_data* d, void* stream);
  * edges under stream capture); results are identical for any N. */
 int b2_substeps(const b2_model* m, b2_data* d, int nsub, void* stream);
 
-/* One stage of b2_step on its own: 0 = k_smooth (position / velocity stage), 1 = k_solve (constraint rows + Newton
- * solver), 2 = k_post (sensors, and integration when do_integrate != 0).  b2_step == stages 0, 1, 2 with
- * do_integrate = 1; b2_forward the same with do_integrate = 0.  Used by bench.py to bracket each kernel with CUDA events
- * and by stage-wise tests. */
+/* One stage of b2_step on its own: 0 = k_smooth (position / velocity stage) + k_order (solver schedule), 1 = k_solve
+ * (constraint rows + Newton solver), 2 = k_post (sensors, and integration when do_integrate != 0).  b2_step == stages 0, 1, 2
+ * with do_integrate = 1; b2_forward the same with do_integrate = 0.  4 = k_smooth alone, 5 = k_order alone (0 == 4 then 5);
+ * 3 = k_solve with the sensor stage fused into its tail (experiment).  Used by bench.py to bracket each kernel with CUDA
+ * events and by stage-wise tests. */
 int b2_stage(const b2_model* m, b2_data* d, int stage, int do_integrate, void* stream);
 
 /* mjwarp.reset_data(m, d, reset=mask): worlds with mask[w] != 0 (bool bytes)

@@ -515,9 +515,8 @@ static int run_chunked(const b2_model* m, b2_data* d, void* stream, int nsub, in
   return 0;
 }
 
-// Stages on their own (bench.py brackets each with CUDA events, stage-wise tests): 0 = k_smooth + k_order, 1 = k_solve
-// WITHOUT the fused sensor stage, 2 = k_post (the same post_world as a kernel of its own), 3 = k_solve with the fused
-// sensor / integration stage, i.e. what b2_step launches after stage 0.
+// Stages on their own (bench.py brackets each with CUDA events, stage-wise tests): 0 = k_smooth + k_order, 1 = k_solve,
+// 2 = k_post, 3 = k_solve with the fused sensor / integration stage (experiment), 4 = k_smooth alone, 5 = k_order alone.
 int b2_stage(const b2_model* m, b2_data* d, int stage, int do_integrate, void* stream) {
   const Plan* pp = get_plan(m, d);
   if (!pp) return 1;
@@ -533,6 +532,8 @@ int b2_stage(const b2_model* m, b2_data* d, int stage, int do_integrate, void* s
   else if (stage == 1) k_solve<<<solve_grid(d->nworld, p.solve_cap), B2_WPB * 32, p.smem_solve, st>>>(km, kd, p.lv, p.lp, 0, nullptr, nullptr, 0, d->nworld);
   else if (stage == 2) k_post<<<(d->nworld + B2_POST_WPB - 1) / B2_POST_WPB, B2_POST_WPB * 32, p.smem_post, st>>>(km, kd, p.lp, do_integrate, nullptr, nullptr, 0, d->nworld);
   else if (stage == 3) k_solve<<<solve_grid(d->nworld, p.solve_cap), B2_WPB * 32, p.smem_solve, st>>>(km, kd, p.lv, p.lp, do_integrate ? 2 : 1, nullptr, nullptr, 0, d->nworld);
+  else if (stage == 4) k_smooth<<<(d->nworld + B2_SMOOTH_WPB - 1) / B2_SMOOTH_WPB, B2_SMOOTH_WPB * 32, p.smem_smooth, st>>>(km, kd, p.ls, B2_NCAND_MAX, nullptr, nullptr, 0, d->nworld);
+  else if (stage == 5) k_order<<<1, 1024, 0, st>>>(kd, 0, d->nworld, p.solve_cap, p.order_mode);
   else return fail("unknown stage %d", stage);
   g_launches += 1;
   cudaError_t e = cudaGetLastError();

@@ -407,6 +407,10 @@ class ManagerBasedRlEnv:
     E.check_call(lib, lib.b2_env_reset(m, d, e, mask, st))
     E.check_call(lib, lib.b2_forward(m, d, st))
     E.check_call(lib, lib.b2_env_obs(m, d, e, 0, st))
+    # advance the draw counter: the Philox draws are indexed by (seed, env, counter, slot), so without this reset() and the
+    # first step() would share their draws (identical observation noise; an env timing out on step 0 would be reset to exactly
+    # its initial state), and repeated reset() calls would reproduce the same state
+    self._buf["step_counter"].add_(1)
     self._publish_log()
     return self.obs_buf, self.extras
 
@@ -415,10 +419,11 @@ class ManagerBasedRlEnv:
     if action.shape[-1] != self.vcfg.nj:
       raise ValueError(f"Invalid action shape, expected: {self.vcfg.nj}, received: {action.shape[-1]}.")
     self._buf["action_in"].copy_(action, non_blocking=True)
-    if self._graph is not None:
-      self._graph.replay()
-    else:
-      self._enqueue_step()
+    with self.sim.nan_guard.watch(self.sim.data):   # a no-op unless cfg.sim.nan_guard.enabled: the env's fused step bypasses
+      if self._graph is not None:                   # Simulation.step(), so the guard brackets the whole env step here
+        self._graph.replay()
+      else:
+        self._enqueue_step()
     self.common_step_counter += 1
     self._sim_step_counter += self.cfg.decimation
     if self._next_stage < len(self.cfg.velocity_stages) and self.common_step_counter > self.cfg.velocity_stages[self._next_stage]["step"]:

@@ -48,9 +48,9 @@ class PpoCfg:
   use_clipped_value_loss: bool = True
   clip_param: float = 0.2
   clip_actions: float | None = None
-  # "high": TF32 tensor-core GEMMs for the actor / critic (the one place of the training loop where tensor cores apply;
-  # mini-batches of 24 576 x 512); "highest" = rsl_rl's plain fp32
-  matmul_precision: str = "high"
+  # "highest" = rsl_rl's plain fp32 (the default: numbers quoted against the reference use it); "high": TF32 tensor-core GEMMs
+  # for the actor / critic (mini-batches of 24 576 x 512), reported separately
+  matmul_precision: str = "highest"
   # capture the whole 24-step roll-out (policy inference + the env's kernels + GAE) in ONE CUDA graph: removes ~2000 eager
   # launches per iteration; needs the env's raw enqueue API, falls back to eager otherwise
   rollout_cuda_graph: bool = True
@@ -206,6 +206,8 @@ class OnPolicyRunner:
   # ---- roll-out -------------------------------------------------------------------------------------
   def _raw_env(self):
     e = getattr(self.env, "env", None)
+    if e is not None and getattr(getattr(getattr(e, "sim", None), "nan_guard", None), "enabled", False):
+      return None   # NanGuard watches env.step(); the captured roll-out graph bypasses it, so fall back to stepping the env
     return e if (e is not None and hasattr(e, "_enqueue_step") and str(self.device).startswith("cuda")) else None
 
   def _step_env(self, a: torch.Tensor, raw):
@@ -294,19 +296,14 @@ class OnPolicyRunner:
   def learning_rate(self) -> float:
     return float(self._lr)
 
-  def _update_body(self) -> None:
-    """All epochs x mini-batches of one PPO update; reads `self._perm`, writes `self._stats` (device tensors).
-
-    The step is bound by the number of small kernels, not by arithmetic, so a mini-batch is ONE row gather from a packed
-    copy of the roll-out ([N, obs | critic | actions | mu | sigma | logp, value, return, advantage]) and the Gaussian terms
-    are written out (log-prob, entropy and KL of a diagonal Normal with a state-independent std; the entropy is the same
-    for every row) instead of going through torch.distributions - same formulas as rsl_rl's PPO.update."""
+  def _pack_rollout(self) -> None:
+    """One packed copy of the roll-out, [N, obs | critic | actions | mu | sigma | logp | value | return | advantage]: a mini-batch
+    is then ONE row gather.  Column blocks start on multiples of 4 floats and the observation blocks have the networks' padded
+    widths (their padding columns stay zero): every view handed to a GEMM is 16-byte aligned."""
     cfg, st, ro = self.cfg, self.st, self.ro
     N = cfg.num_steps_per_env * self.env.num_envs
     no, nc, na = self.n_obs, self.n_critic, self.n_act
     pol = self.policy
-    # column blocks start on multiples of 4 floats and the observation blocks have the networks' padded widths (their
-    # padding columns stay zero): every view handed to a GEMM is 16-byte aligned
     cols = [("obs", no, pol.w_actor_obs), ("critic", nc, pol.w_critic_obs), ("actions", na, pol.w_actions), ("mu", na, pol.w_actions),
             ("sigma", na, pol.w_actions), ("logp", 1, 1), ("values", 1, 1)]
     width = sum(w for _, _, w in cols) + 2
@@ -321,65 +318,146 @@ class OnPolicyRunner:
     self._pack[:, o] = ro["returns"].reshape(N)
     self._pack[:, o + 1] = ro["advantages"].reshape(N)
     off["ret"], off["adv"] = o, o + 1
-    mb = N // cfg.num_mini_batches
-    params = list(self.policy.parameters())
-    stats = self._stats
-    stats.zero_()
-    self.policy.train()
+    self._off = off
+
+  def _mb_backward(self, idx: torch.Tensor) -> None:
+    """Forward, losses and backward of one mini-batch (rows `idx` of the packed roll-out).  Leaves the gradients in the
+    parameters' .grad (views of `self._flat` in distributed runs), this rank's KL in `self._kl` and the loss terms in
+    `self._mb_stats`.  The Gaussian terms are written out (log-prob, entropy and KL of a diagonal Normal with a state-independent
+    std) instead of going through torch.distributions - same formulas as rsl_rl's PPO.update."""
+    cfg, off, pol, na = self.cfg, self._off, self.policy, self.n_act
     half_log_2pi = 0.5 * math.log(2.0 * math.pi)
+    b = self._pack[idx]
+    col = lambda k: b[:, off[k][0]:off[k][1]]  # noqa: E731
+    mu = pol.actor_mean(col("obs_padded"))
+    value = pol.evaluate(col("critic_padded")).squeeze(-1)
+    std = pol.std
+    log_std = std.log()
+    logp = (-0.5 * ((col("actions") - mu) / std).square() - log_std).sum(-1) - na * half_log_2pi
+    entropy = (0.5 + half_log_2pi + log_std).sum()            # per-row entropy of the diagonal Normal; identical rows
+    with torch.no_grad():
+      old_mu, old_sigma = col("mu"), col("sigma")
+      kl = torch.sum(torch.log(std / old_sigma + 1e-5) + (old_sigma.square() + (old_mu - mu).square()) / (2.0 * std.square()) - 0.5, -1).mean()
+    ratio = torch.exp(logp - b[:, off["logp"][0]])
+    a, ret = b[:, off["adv"]], b[:, off["ret"]]
+    surrogate = torch.max(-a * ratio, -a * torch.clamp(ratio, 1.0 - cfg.clip_param, 1.0 + cfg.clip_param)).mean()
+    if cfg.use_clipped_value_loss:
+      old_v = b[:, off["values"][0]]
+      v_clip = old_v + (value - old_v).clamp(-cfg.clip_param, cfg.clip_param)
+      v_loss = torch.max((value - ret).square(), (v_clip - ret).square()).mean()
+    else:
+      v_loss = (ret - value).square().mean()
+    loss = surrogate + cfg.value_loss_coef * v_loss - cfg.entropy_coef * entropy
+    if self._flat is not None:
+      self._flat.zero_()
+    else:
+      self.optimizer.zero_grad(set_to_none=False)
+    loss.backward()
+    with torch.no_grad():
+      self._kl.copy_(kl)
+      self._mb_stats.copy_(torch.stack((v_loss.detach(), surrogate.detach(), entropy.detach())))
+
+  def _mb_step(self) -> None:
+    """After the gradients (and the KL) have been averaged over the ranks: KL-adaptive learning rate (on the device), gradient
+    clipping, Adam.  The learning rate only enters the optimiser step, so adapting it here equals rsl_rl's order."""
+    cfg = self.cfg
+    with torch.no_grad():
+      if self._flat is not None:
+        self._flat /= self.world_size          # [gradients | KL], summed over the ranks by ONE all-reduce
+      kl = self._kl
+      if cfg.schedule == "adaptive" and cfg.desired_kl is not None:
+        lr = self._lr
+        down = torch.clamp(lr / 1.5, min=1e-5)
+        up = torch.clamp(lr * 1.5, max=1e-2)
+        lr.copy_(torch.where(kl > cfg.desired_kl * 2.0, down, torch.where((kl > 0.0) & (kl < cfg.desired_kl / 2.0), up, lr)))
+    nn.utils.clip_grad_norm_(self._params, cfg.max_grad_norm, foreach=self.device.type == "cuda")
+    self.optimizer.step()
+    with torch.no_grad():
+      self._stats[:3] += self._mb_stats
+      self._stats[3] += kl
+
+  def _setup_update(self) -> None:
+    cfg = self.cfg
+    N = cfg.num_steps_per_env * self.env.num_envs
+    self._perm = torch.zeros(cfg.num_learning_epochs, N, dtype=torch.long, device=self.device)
+    self._stats = torch.zeros(4, device=self.device)
+    self._mb_stats = torch.zeros(3, device=self.device)
+    self._params = [p for p in self.policy.parameters() if p.requires_grad]
+    self._cur_idx = torch.zeros(N // cfg.num_mini_batches, dtype=torch.long, device=self.device)
+    self._flat = None
+    if self.distributed:
+      # every gradient is a view of ONE flat buffer whose last element carries the mini-batch KL: the ranks exchange both
+      # with a single all-reduce per mini-batch (1.76 MB for the G1 networks), no flatten / unflatten copies
+      n = sum(p.numel() for p in self._params)
+      self._flat = torch.zeros(n + 1, device=self.device)
+      o = 0
+      for p in self._params:
+        p.grad = self._flat[o:o + p.numel()].view_as(p)
+        o += p.numel()
+      self._kl = self._flat[n:n + 1].view(())
+    else:
+      self._kl = torch.zeros((), device=self.device)
+    self._graph_a = self._graph_b = None
+
+  def _update_body(self) -> None:
+    """All epochs x mini-batches of one PPO update; reads `self._perm`, writes `self._stats` (device tensors)."""
+    cfg = self.cfg
+    self._pack_rollout()
+    N = cfg.num_steps_per_env * self.env.num_envs
+    mb = N // cfg.num_mini_batches
+    self._stats.zero_()
+    self.policy.train()
     for e in range(cfg.num_learning_epochs):
       for i in range(cfg.num_mini_batches):
-        b = self._pack[self._perm[e, i * mb:(i + 1) * mb]]
-        col = lambda k: b[:, off[k][0]:off[k][1]]  # noqa: E731
-        mu = pol.actor_mean(col("obs_padded"))
-        value = pol.evaluate(col("critic_padded")).squeeze(-1)
-        std = self.policy.std
-        log_std = std.log()
-        logp = (-0.5 * ((col("actions") - mu) / std).square() - log_std).sum(-1) - na * half_log_2pi
-        entropy = (0.5 + half_log_2pi + log_std).sum()            # per-row entropy of the diagonal Normal; identical rows
-        with torch.no_grad():
-          old_mu, old_sigma = col("mu"), col("sigma")
-          kl = torch.sum(torch.log(std / old_sigma + 1e-5) + (old_sigma.square() + (old_mu - mu).square()) / (2.0 * std.square()) - 0.5, -1).mean()
-          if self.distributed:
-            dist.all_reduce(kl, op=dist.ReduceOp.SUM)
-            kl /= self.world_size
-          if cfg.schedule == "adaptive" and cfg.desired_kl is not None:
-            lr = self._lr
-            down = torch.clamp(lr / 1.5, min=1e-5)
-            up = torch.clamp(lr * 1.5, max=1e-2)
-            lr.copy_(torch.where(kl > cfg.desired_kl * 2.0, down, torch.where((kl > 0.0) & (kl < cfg.desired_kl / 2.0), up, lr)))
-        ratio = torch.exp(logp - b[:, off["logp"][0]])
-        a, ret = b[:, off["adv"]], b[:, off["ret"]]
-        surrogate = torch.max(-a * ratio, -a * torch.clamp(ratio, 1.0 - cfg.clip_param, 1.0 + cfg.clip_param)).mean()
-        if cfg.use_clipped_value_loss:
-          old_v = b[:, off["values"][0]]
-          v_clip = old_v + (value - old_v).clamp(-cfg.clip_param, cfg.clip_param)
-          v_loss = torch.max((value - ret).square(), (v_clip - ret).square()).mean()
-        else:
-          v_loss = (ret - value).square().mean()
-        loss = surrogate + cfg.value_loss_coef * v_loss - cfg.entropy_coef * entropy
-        self.optimizer.zero_grad(set_to_none=False)
-        loss.backward()
+        self._mb_backward(self._perm[e, i * mb:(i + 1) * mb])
         if self.distributed:
-          reduce_gradients(params, self.world_size)
-        nn.utils.clip_grad_norm_(params, cfg.max_grad_norm, foreach=self.device.type == "cuda")
-        self.optimizer.step()
-        with torch.no_grad():
-          stats += torch.stack((v_loss.detach(), surrogate.detach(), entropy.detach(), kl))
-    stats /= cfg.num_learning_epochs * cfg.num_mini_batches
+          dist.all_reduce(self._flat, op=dist.ReduceOp.SUM)
+        self._mb_step()
+    self._stats /= cfg.num_learning_epochs * cfg.num_mini_batches
+
+  def _update_distributed_graphs(self) -> None:
+    """Distributed update without eager kernel launches: per mini-batch ONE graph replay for forward + backward, ONE NCCL
+    all-reduce of the flat [gradients | KL] buffer, ONE graph replay for clip + Adam.  (Capturing the NCCL call itself inside a
+    CUDA graph hung with this torch / NCCL pair in round 1; keeping the collective outside the two graphs needs no such support
+    and costs 3 launches per mini-batch instead of ~75.)"""
+    cfg = self.cfg
+    N = cfg.num_steps_per_env * self.env.num_envs
+    mb = N // cfg.num_mini_batches
+    self._pack_rollout()
+    self._stats.zero_()
+    self.policy.train()
+    if self._graph_a is None:
+      torch.cuda.synchronize(self.device)
+      side = torch.cuda.Stream(self.device)
+      ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+      with torch.cuda.stream(side):
+        with torch.cuda.graph(ga, stream=side):
+          self._mb_backward(self._cur_idx)
+        with torch.cuda.graph(gb, stream=side):
+          self._mb_step()
+      torch.cuda.current_stream(self.device).wait_stream(side)
+      self._graph_a, self._graph_b = ga, gb
+    for e in range(cfg.num_learning_epochs):
+      for i in range(cfg.num_mini_batches):
+        self._cur_idx.copy_(self._perm[e, i * mb:(i + 1) * mb])
+        self._graph_a.replay()
+        dist.all_reduce(self._flat, op=dist.ReduceOp.SUM)
+        self._graph_b.replay()
+    self._stats /= cfg.num_learning_epochs * cfg.num_mini_batches
 
   def update(self, ro: dict) -> dict:
     cfg = self.cfg
     N = cfg.num_steps_per_env * self.env.num_envs
     if not hasattr(self, "_perm"):
-      self._perm = torch.zeros(cfg.num_learning_epochs, N, dtype=torch.long, device=self.device)
-      self._stats = torch.zeros(4, device=self.device)
+      self._setup_update()
     for e in range(cfg.num_learning_epochs):
       self._perm[e].copy_(torch.randperm(N, device=self.device))
-    use_graph = cfg.update_cuda_graph and self.device.type == "cuda" and not self.distributed
+    use_graph = cfg.update_cuda_graph and self.device.type == "cuda"
     if not use_graph or self._update_warm < 2:
       self._update_body()               # eager: also the warm-up that creates Adam's state and the .grad tensors
       self._update_warm += 1
+    elif self.distributed:
+      self._update_distributed_graphs()
     else:
       if self._update_graph is None:
         torch.cuda.synchronize(self.device)

@@ -247,6 +247,7 @@ class TrackingRlEnv:
     E.check_call(lib, lib.b2_trk_reset(m, d, e, mask, st))
     E.check_call(lib, lib.b2_forward(m, d, st))
     E.check_call(lib, lib.b2_trk_obs(m, d, e, 0, st))
+    self._buf["step_counter"].add_(1)   # reset() consumes one draw-counter value (see env.ManagerBasedRlEnv.reset)
     self._publish_log()
     return self.obs_buf, self.extras
 
@@ -254,10 +255,11 @@ class TrackingRlEnv:
     if action.shape[-1] != self.vcfg.nj:
       raise ValueError(f"Invalid action shape, expected: {self.vcfg.nj}, received: {action.shape[-1]}.")
     self._buf["action_in"].copy_(action, non_blocking=True)
-    if self._graph is not None:
-      self._graph.replay()
-    else:
-      self._enqueue_step()
+    with self.sim.nan_guard.watch(self.sim.data):   # no-op unless enabled; brackets the fused env step (see env.ManagerBasedRlEnv.step)
+      if self._graph is not None:
+        self._graph.replay()
+      else:
+        self._enqueue_step()
     self.common_step_counter += 1
     self._publish_log()
     return self.obs_buf, self.reward_buf, self.reset_terminated, self.reset_time_outs, self.extras

@@ -65,3 +65,6 @@ class CpuSim:
 
   def step(self, nstep: int = 1, nthread: int = 1) -> None:
     self.lib.cport_steps(C.byref(self.cm), C.byref(self.cd), int(nstep), int(nthread))
+
+  def forward(self, nthread: int = 1) -> None:
+    self.lib.cport_forward(C.byref(self.cm), C.byref(self.cd), int(nthread))

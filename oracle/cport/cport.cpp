@@ -21,8 +21,12 @@ extern "C" {
 
 int cport_sizeof_real(void) { return (int)sizeof(real); }
 
+static int cport_run(const KModel* m, KData* d, int nstep, int nthread, int do_integrate);
 // nstep physics steps for every world, worlds distributed over nthread threads (dynamic chunks of 1 world).
-int cport_steps(const KModel* m, KData* d, int nstep, int nthread) {
+int cport_steps(const KModel* m, KData* d, int nstep, int nthread) { return cport_run(m, d, nstep, nthread, 1); }
+// one forward pass (no integration) for every world: sim.forward() after resets (manager_based_rl_env.py:295-298)
+int cport_forward(const KModel* m, KData* d, int nthread) { return cport_run(m, d, 1, nthread, 0); }
+static int cport_run(const KModel* m, KData* d, int nstep, int nthread, int do_integrate) {
   SmoothSmem ls = smooth_smem_layout(m->nq, m->nv, m->nu, m->nbody, m->njnt, 256);
   int rows_max = 4 * d->nconmax + 2 * m->nlimited;
   if (rows_max > d->njmax) rows_max = d->njmax;
@@ -41,7 +45,7 @@ int cport_steps(const KModel* m, KData* d, int nstep, int nthread) {
       for (int s = 0; s < nstep; ++s) {
         smooth_world(*m, *d, ls, 256, w, a.data());
         solve_world(*m, *d, lv, w, b.data(), ar.data(), actl);
-        post_world(*m, *d, lp, w, c.data(), 1);
+        post_world(*m, *d, lp, w, c.data(), do_integrate);
       }
     }
   };

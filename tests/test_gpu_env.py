@@ -233,6 +233,7 @@ def test_env_step_closed_loop_matches_oracle(robot, mode):
   d = _batch(ds, m)
   R = OE.root_kinematics(cfg, d)
   OE.observations(cfg, s, d, R, u)
+  s.step_counter += 1       # reset() consumes one draw counter value: the first step() must not reuse its draws
   torch.cuda.synchronize()
   np.testing.assert_allclose(obs["critic"].cpu().numpy(), s.obs_critic, rtol=2e-3, atol=2e-3)
   np.testing.assert_allclose(env.sim.data.qpos.cpu().numpy(), d.qpos, rtol=1e-5, atol=1e-6)
@@ -269,7 +270,8 @@ def test_env_step_closed_loop_matches_oracle(robot, mode):
     np.testing.assert_allclose(pol, spol, rtol=2e-2, atol=1e-2)
     log = extras["log"]
     assert log["Episode/num_resets"] == float(s.reset_buf.sum())
-  assert s.step_counter == T + 0 and env.common_step_counter == T
+  assert s.step_counter == T + 1 and env.common_step_counter == T
+  assert int(env._buf["step_counter"][0]) == T + 1
 
 
 @pytest.mark.parametrize("robot", ["g1"])

@@ -179,6 +179,7 @@ def test_rough_env_step_closed_loop_matches_oracles():
     O.forward(m, x, 35, 300)
   d = _batch(ds, m)
   OE.observations(cfg, s, d, OE.root_kinematics(cfg, d), u)
+  s.step_counter += 1       # reset() consumes one draw counter value
   torch.cuda.synchronize()
   # the first reset ran the curriculum against the construction pose (reference behaviour): levels and origins agree
   np.testing.assert_array_equal(env._buf["terrain_level"].cpu().numpy(), s.terrain_level)

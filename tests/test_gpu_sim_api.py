@@ -321,3 +321,38 @@ def test_env_scene_sensor_views():
   with pytest.raises(KeyError):
     env.scene["no_such_thing"]
   assert env.scene.env_origins.shape == (32, 3)
+
+
+def test_reset_consumes_its_own_draws():
+  """reset() and the first step() shared draw counter 0.  Repeated reset() calls must give different states, and the
+  noise of the first step's observations must differ from reset()'s."""
+  from mjlab_b200.env import ManagerBasedRlEnv, VelocityEnvCfg
+  env = ManagerBasedRlEnv(VelocityEnvCfg(robot="go1", num_envs=16, seed=11), DEV)
+  env.reset()
+  q1 = env.sim.data.qpos.clone()
+  c1 = int(env._buf["step_counter"][0])
+  env.reset()
+  q2 = env.sim.data.qpos.clone()
+  assert int(env._buf["step_counter"][0]) == c1 + 1
+  assert not torch.equal(q1[:, :2], q2[:, :2])                     # a fresh x / y / yaw draw on every reset()
+  env.step(torch.zeros(16, env.vcfg.nj, device=DEV))
+  assert int(env._buf["step_counter"][0]) == c1 + 2
+
+
+def test_nan_guard_covers_the_fused_env_step(tmp_path):
+  """NanGuard was only wired into Simulation.step(); the env's fused step bypasses it."""
+  from mjlab_b200.env import ManagerBasedRlEnv, VelocityEnvCfg, _default_sim_cfg
+  from mjlab_b200.nan_guard import NanGuardCfg
+  sc = _default_sim_cfg()
+  sc.nan_guard = NanGuardCfg(enabled=True, buffer_size=4, output_dir=str(tmp_path), max_envs_to_dump=2)
+  env = ManagerBasedRlEnv(VelocityEnvCfg(robot="go1", num_envs=8, seed=1, sim=sc), DEV)
+  env.reset()
+  z = torch.zeros(8, env.vcfg.nj, device=DEV)
+  for _ in range(3):
+    env.step(z)
+  assert not list(tmp_path.glob("nan_dump_*.npz"))
+  env.sim.data.qvel[5, 7] = float("nan")
+  env.step(z)
+  dump = np.load(tmp_path / "nan_dump_latest.npz", allow_pickle=True)
+  meta = dump["_metadata"].item()
+  assert 5 in meta["nan_env_ids"] and meta["buffer_size"] == 4

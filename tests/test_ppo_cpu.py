@@ -109,10 +109,15 @@ def _seed_worker(rank, world, port, q):
   cfg = ppo.PpoCfg(num_steps_per_env=4, actor_hidden_dims=(16,), critic_hidden_dims=(16,), num_learning_epochs=1, num_mini_batches=2, seed=7)
   r = ppo.OnPolicyRunner(env, cfg, device="cpu")
   params = torch.cat([p.detach().view(-1) for p in r.policy.parameters()]).numpy().copy()
-  r.collect()
+  ro = r.collect()
+  actions = r.st["actions"].numpy().copy()
+  # the distributed update: gradients are views of one flat buffer, [gradients | KL] all-reduced once per mini-batch
+  stats = r.update(ro)
+  after = torch.cat([p.detach().view(-1) for p in r.policy.parameters()]).numpy().copy()
+  assert r._flat is not None and all(p.grad.data_ptr() >= r._flat.data_ptr() for p in r._params)
   # the toy env's observations are identical on both ranks (same generator seed), so any difference in the sampled
   # actions comes from the exploration noise alone
-  q.put((rank, params, r.st["actions"].numpy().copy()))
+  q.put((rank, params, actions, after, float(stats["kl"]), float(r._lr)))
   dist.barrier()
   dist.destroy_process_group()
 
@@ -129,9 +134,12 @@ def test_ranks_share_parameters_but_not_exploration_noise():
   out = sorted((q.get(timeout=120) for _ in range(2)), key=lambda t: t[0])
   for p in procs:
     p.join(timeout=60)
-  (_, p0, a0), (_, p1, a1) = out
+  (_, p0, a0, f0, kl0, lr0), (_, p1, a1, f1, kl1, lr1) = out
   np.testing.assert_array_equal(p0, p1)
   assert np.abs(a0 - a1).max() > 1e-3, "both ranks sampled identical actions: exploration noise is not rank-specific"
+  # after the update the replicas still hold identical parameters (averaged gradients, the same KL -> the same learning rate)
+  np.testing.assert_array_equal(f0, f1)
+  assert np.abs(f0 - p0).max() > 1e-5 and kl0 == kl1 and lr0 == lr1
 
 
 def test_policy_export_roundtrip(tmp_path):
