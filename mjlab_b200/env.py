@@ -361,6 +361,23 @@ class ManagerBasedRlEnv:
     chk(lib, lib.b2_env_obs(m, d, e, 1, st))
     chk(lib, lib.b2_env_log(d, e, st))
 
+  def _step_guarded(self) -> None:
+    """The env step with `NanGuard.watch` around every PHYSICS step, as in the reference, where the env calls `sim.step()`
+    (manager_based_rl_env.py:275-280 -> sim.py:267-273).  The fused graph bypasses `Simulation.step()`, and a check after the
+    whole env step would come too late: a world that went NaN is usually terminated and reset inside the same step.  Debug
+    path (eager launches, one host sync per physics step); only taken when `cfg.sim.nan_guard.enabled`."""
+    lib, m, d, e, chk = self._lib, C.byref(self.sim._cm), C.byref(self.sim._cd), C.byref(self._ce), E.check_call
+    st = self._stream()
+    chk(lib, lib.b2_env_action(m, d, e, st))
+    for _ in range(self.cfg.decimation):
+      with self.sim.nan_guard.watch(self.sim.data):
+        chk(lib, lib.b2_env_substeps(m, d, e, 1, st))
+    chk(lib, lib.b2_env_post(m, d, e, st))
+    mask = self._buf["reset_buf"].data_ptr() if self.cfg.forward_mode == "masked" else None
+    chk(lib, lib.b2_forward_masked(m, d, mask, self._buf["any_reset"].data_ptr(), st))
+    chk(lib, lib.b2_env_obs(m, d, e, 1, st))
+    chk(lib, lib.b2_env_log(d, e, st))
+
   def _capture(self) -> None:
     """(Re)capture the env-step graph; needed again whenever a buffer address or a by-value parameter changes."""
     self._graph = None
@@ -419,11 +436,12 @@ class ManagerBasedRlEnv:
     if action.shape[-1] != self.vcfg.nj:
       raise ValueError(f"Invalid action shape, expected: {self.vcfg.nj}, received: {action.shape[-1]}.")
     self._buf["action_in"].copy_(action, non_blocking=True)
-    with self.sim.nan_guard.watch(self.sim.data):   # a no-op unless cfg.sim.nan_guard.enabled: the env's fused step bypasses
-      if self._graph is not None:                   # Simulation.step(), so the guard brackets the whole env step here
-        self._graph.replay()
-      else:
-        self._enqueue_step()
+    if self.sim.nan_guard.enabled:
+      self._step_guarded()
+    elif self._graph is not None:
+      self._graph.replay()
+    else:
+      self._enqueue_step()
     self.common_step_counter += 1
     self._sim_step_counter += self.cfg.decimation
     if self._next_stage < len(self.cfg.velocity_stages) and self.common_step_counter > self.cfg.velocity_stages[self._next_stage]["step"]:

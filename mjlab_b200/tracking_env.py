@@ -255,11 +255,13 @@ class TrackingRlEnv:
     if action.shape[-1] != self.vcfg.nj:
       raise ValueError(f"Invalid action shape, expected: {self.vcfg.nj}, received: {action.shape[-1]}.")
     self._buf["action_in"].copy_(action, non_blocking=True)
-    with self.sim.nan_guard.watch(self.sim.data):   # no-op unless enabled; brackets the fused env step (see env.ManagerBasedRlEnv.step)
-      if self._graph is not None:
-        self._graph.replay()
-      else:
-        self._enqueue_step()
+    if self.sim.nan_guard.enabled:
+      raise NotImplementedError("NanGuard on the tracking env: enable it on the velocity env (per-physics-step checks, "
+                                "env.ManagerBasedRlEnv._step_guarded) or step `sim` directly")
+    if self._graph is not None:
+      self._graph.replay()
+    else:
+      self._enqueue_step()
     self.common_step_counter += 1
     self._publish_log()
     return self.obs_buf, self.reward_buf, self.reset_terminated, self.reset_time_outs, self.extras
