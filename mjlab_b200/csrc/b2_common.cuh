@@ -404,6 +404,9 @@ B2_DEVN void chol_backsolve(const real* L, int n, int ld, const real* invd, real
   B2_WSYNC();
 }
 
+#ifndef B2_SYMV_BATCH
+#define B2_SYMV_BATCH 4    // loads in flight per lane and batch (multiple of 4).  Measured (k_solve, G1 4096 worlds): 12 + straight-line tail 0.414 ms, one predicated 12-wide body 0.399, 8 -> 0.398, 4 -> 0.394: code size beats loads in flight (profiles/r02_k_solve_icache.txt)
+#endif
 // y = M x for a symmetric M [n][ld] in global memory: lane i walks column i (== row i), so every
 // load of the warp is one coalesced segment.
 B2_DEVN void symv_global(const real* M, int n, int ld, const real* x, real* y) {  // @region symv_global
@@ -414,29 +417,20 @@ B2_DEVN void symv_global(const real* M, int n, int ld, const real* x, real* y) {
     y[i] = a;
   }
 #else
-  // Latency-bound on L2: keep many independent loads in flight (12 per batch), no dependent scalar tail.
+  // Latency-bound on L2: keep many independent loads in flight (12 per batch), no dependent scalar tail.  ONE predicated
+  // 12-wide batch body serves every batch, the partial last one included: the straight-line main + tail variants of round 1
+  // cost 5.5 KB of the Newton loop's instruction footprint (38 KB against a 32 KB L1.5: profiles/r02_k_solve_icache.txt).
   const int i = B2_LANE;
   if (i < n) {
     const real* Mi = M + i;
     real a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-    int e = 0;
     B2_UNROLL1
-    for (; e + 12 <= n; e += 12) {
-      real m[12];
+    for (int e = 0; e < n; e += B2_SYMV_BATCH) {
+      real m[B2_SYMV_BATCH];
 #pragma unroll
-      for (int k = 0; k < 12; ++k) m[k] = Mi[(e + k) * ld];
+      for (int k = 0; k < B2_SYMV_BATCH; ++k) m[k] = e + k < n ? Mi[(e + k) * ld] : (real)0;
 #pragma unroll
-      for (int k = 0; k < 12; k += 4) {
-        a0 = fmaf(m[k], x[e + k], a0); a1 = fmaf(m[k + 1], x[e + k + 1], a1);
-        a2 = fmaf(m[k + 2], x[e + k + 2], a2); a3 = fmaf(m[k + 3], x[e + k + 3], a3);
-      }
-    }
-    {
-      real m[12];
-#pragma unroll
-      for (int k = 0; k < 12; ++k) m[k] = e + k < n ? Mi[(e + k) * ld] : (real)0;
-#pragma unroll
-      for (int k = 0; k < 12; k += 4) {
+      for (int k = 0; k < B2_SYMV_BATCH; k += 4) {
         a0 = fmaf(m[k], e + k < n ? x[e + k] : (real)0, a0); a1 = fmaf(m[k + 1], e + k + 1 < n ? x[e + k + 1] : (real)0, a1);
         a2 = fmaf(m[k + 2], e + k + 2 < n ? x[e + k + 2] : (real)0, a2); a3 = fmaf(m[k + 3], e + k + 3 < n ? x[e + k + 3] : (real)0, a3);
       }

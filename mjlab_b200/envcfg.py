@@ -16,6 +16,34 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
+def cfg_to_dict(obj, _depth: int = 0):
+  """Plain-data view of a (reference) configuration object: dataclasses -> dicts of their fields, callables / classes -> their
+  `__name__`, tuples -> lists, `slice(None)` -> None, tensors / arrays -> lists.  `from_manager_cfg` works on this view, so it takes
+  the reference's live `ManagerBasedRlEnvCfg` and the JSON fixtures generated from it alike."""
+  import dataclasses
+  if _depth > 12:
+    return repr(obj)
+  if obj is None or isinstance(obj, (bool, int, float, str)):
+    return obj
+  if isinstance(obj, slice):
+    return None if obj == slice(None) else [obj.start, obj.stop, obj.step]
+  if isinstance(obj, dict):
+    return {str(k): cfg_to_dict(v, _depth + 1) for k, v in obj.items()}
+  if isinstance(obj, (list, tuple, set)):
+    return [cfg_to_dict(v, _depth + 1) for v in obj]
+  if isinstance(obj, np.ndarray):
+    return obj.tolist()
+  if hasattr(obj, "detach") and hasattr(obj, "tolist"):
+    return obj.detach().cpu().tolist()
+  if dataclasses.is_dataclass(obj) and not isinstance(obj, type):
+    d = {f.name: cfg_to_dict(getattr(obj, f.name), _depth + 1) for f in dataclasses.fields(obj)}
+    d["__type__"] = type(obj).__name__
+    return d
+  if callable(obj):
+    return getattr(obj, "__name__", type(obj).__name__)
+  return repr(obj)
+
+
 REWARD_NAMES = (
   "track_linear_velocity", "track_angular_velocity", "upright", "pose", "body_ang_vel", "angular_momentum",
   "dof_pos_limits", "action_rate_l2", "air_time", "foot_clearance", "foot_swing_height", "foot_slip", "soft_landing",
