@@ -67,6 +67,27 @@ class VelocityEnvCfg:
     {"step": 10000 * 24, "lin_vel_x": (-2.0, 3.0)},
   )
   sim: SimulationCfg = field(default_factory=_default_sim_cfg)
+  # a reference `ManagerBasedRlEnvCfg` (the live dataclass, or its `envcfg.cfg_to_dict` view) whose reward / termination /
+  # observation / event / command / curriculum terms replace the built-in task tables (see `from_manager_cfg`)
+  manager_cfg: Any = None
+
+  @classmethod
+  def from_manager_cfg(cls, cfg, robot: str, terrain: str = "flat", **kw) -> "VelocityEnvCfg":
+    """Consume the reference's `ManagerBasedRlEnvCfg` (envs/manager_based_rl_env.py:59-129, e.g. `load_env_cfg(task)` edited by
+    the user: re-weighted / removed reward terms, other noise or command ranges, no push event, ...).  The SCENE is not rebuilt
+    from the cfg's `spec_fn`s (that needs MuJoCo's compiler): `robot` / `terrain` name one of the compiled scenes; every term is
+    taken from the cfg and must be one the kernels implement (`envcfg.UnsupportedTermError` otherwise)."""
+    d = cfg if isinstance(cfg, dict) else envcfg.cfg_to_dict(cfg)
+    mj, sc = d["sim"]["mujoco"], d["sim"]
+    sim = SimulationCfg(nconmax=sc["nconmax"], njmax=sc["njmax"], ls_parallel=sc.get("ls_parallel", True),
+                        contact_sensor_maxmatch=sc.get("contact_sensor_maxmatch", 64),
+                        mujoco=MujocoCfg(timestep=mj["timestep"], integrator=mj["integrator"], impratio=mj["impratio"], cone=mj["cone"],
+                                         solver=mj["solver"], iterations=mj["iterations"], tolerance=mj["tolerance"],
+                                         ls_iterations=mj["ls_iterations"], ls_tolerance=mj["ls_tolerance"], gravity=tuple(mj["gravity"])))
+    play = float(d["episode_length_s"]) > 1e6      # which compiled rough scene (5 x 5 play grid or 10 x 20 curriculum grid)
+    kw.setdefault("num_envs", int(d["scene"]["num_envs"]))
+    kw.setdefault("seed", d.get("seed") if d.get("seed") is not None else 42)
+    return cls(robot=robot, terrain=terrain, play=play, decimation=int(d["decimation"]), sim=sim, manager_cfg=d, **kw)
 
   @classmethod
   def from_task(cls, task: str, play: bool = False, **kw) -> "VelocityEnvCfg":
@@ -255,6 +276,14 @@ class ManagerBasedRlEnv:
     dev = torch.device(device)
     self._dev = dev
     self.vcfg = envcfg.velocity_cfg(model, cfg.robot, play=cfg.play)
+    if cfg.manager_cfg is not None:
+      self.vcfg = envcfg.from_manager_cfg(cfg.manager_cfg, model, cfg.robot)
+      ex = self.vcfg.extra
+      cfg.foot_friction_range = tuple(ex["foot_friction"]["ranges"]) if ex["foot_friction"] else None
+      cfg.velocity_stages = tuple(ex["velocity_stages"])
+      post = [t for g in ex["obs_post"].values() for t in g]
+      if any(t["clip"] or t["scale"] is not None or t["delay_max_lag"] > 0 or t["history_length"] > 0 for t in post):
+        self._want_obs_pipeline = ex["obs_post"]
     self.vcfg.seed = int(cfg.seed)
     self.vcfg.decimation = cfg.decimation
     self.vcfg.step_dt = cfg.decimation * cfg.sim.mujoco.timestep
@@ -305,6 +334,15 @@ class ManagerBasedRlEnv:
     self.common_step_counter = 0
     self._sim_step_counter = 0
     self.obs_buf = {"policy": self._buf["obs_policy"], "critic": self._buf["obs_critic"]}
+    self._raw_obs = self.obs_buf
+    self._obs_pipeline = None
+    if getattr(self, "_want_obs_pipeline", None) is not None:
+      # clip / scale / delay / history asked for by some observation term: post-processing outside the step graph
+      from .obs_pipeline import ObservationPipeline
+      nj, nf = self.vcfg.nj, self.vcfg.nfeet
+      pol = [("base_lin_vel", 3), ("base_ang_vel", 3), ("projected_gravity", 3), ("joint_pos", nj), ("joint_vel", nj), ("actions", nj), ("command", 3)]
+      cri = pol + [("foot_height", nf), ("foot_air_time", nf), ("foot_contact", nf), ("foot_contact_forces", 3 * nf)]
+      self._obs_pipeline = ObservationPipeline({"policy": pol, "critic": cri}, self._want_obs_pipeline, n, device)
     self.reward_buf = self._buf["reward"]
     self.reset_buf = self._buf["reset_buf"].view(torch.bool)
     self.reset_terminated = self._buf["terminated"].view(torch.bool)
@@ -317,7 +355,7 @@ class ManagerBasedRlEnv:
       names = self._foot_geom_names()
       randomize_field(self, None, "geom_friction", cfg.foot_friction_range, operation="abs", geom_names=names)
 
-    if cfg.play and cfg.robot == "g1":  # config/g1/env_cfgs.py:167-173
+    if cfg.manager_cfg is None and cfg.play and cfg.robot == "g1" and cfg.terrain == "flat":  # config/g1/env_cfgs.py:167-173: the FLAT play cfg only (pinned by tests/test_task_cfg.py)
       self.vcfg.cmd_lin_x, self.vcfg.cmd_ang_z = (-1.5, 2.0), (-0.7, 0.7)
       A.fill_params(self._ce, self.vcfg)
     self._next_stage = 0
@@ -428,6 +466,9 @@ class ManagerBasedRlEnv:
     # first step() would share their draws (identical observation noise; an env timing out on step 0 would be reset to exactly
     # its initial state), and repeated reset() calls would reproduce the same state
     self._buf["step_counter"].add_(1)
+    if self._obs_pipeline is not None:
+      self._obs_pipeline.reset(env_ids)
+      self.obs_buf = self._obs_pipeline.compute(self._raw_obs, update_history=True)
     self._publish_log()
     return self.obs_buf, self.extras
 
@@ -446,6 +487,13 @@ class ManagerBasedRlEnv:
     self._sim_step_counter += self.cfg.decimation
     if self._next_stage < len(self.cfg.velocity_stages) and self.common_step_counter > self.cfg.velocity_stages[self._next_stage]["step"]:
       self._apply_velocity_stages()
+    if self._obs_pipeline is not None:
+      # _reset_idx resets the observation manager's buffers of the envs that were reset (manager_based_rl_env.py:392-416) before the
+      # observations of this step are pushed; one host sync for the ids - this optional path is outside the fused graph anyway
+      ids = self._buf["reset_buf"].nonzero().flatten()
+      if ids.numel():
+        self._obs_pipeline.reset(ids)
+      self.obs_buf = self._obs_pipeline.compute(self._raw_obs, update_history=True)
     self._publish_log()
     return self.obs_buf, self.reward_buf, self.reset_terminated, self.reset_time_outs, self.extras
 

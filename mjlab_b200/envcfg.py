@@ -279,7 +279,7 @@ def velocity_cfg(m, robot: str, play: bool = False) -> VelocityCfg:
     max_episode_length=math.ceil(int(1e9) / 0.02) if play else 1000, max_episode_length_s=float(int(1e9)) if play else 20.0,
     enable_corruption=not play, push_enabled=not play,
     foot_site_body=np.asarray(m.site_bodyid)[site_ids[list(foot_local)]].astype(int),
-    **_terrain_fields(m, play),
+    **_terrain_fields(m, play and robot == "g1"),   # only the G1 play cfg adds the randomize_terrain reset event (config/g1/env_cfgs.py:136-140; go1: none)
   )
 
 
@@ -385,3 +385,208 @@ def tracking_cfg(m, time_step_total: int, robot: str = "g1", play: bool = False,
     velocity_range=r6({} if play else _TRACKING_VELOCITY_RANGE), push_vel=r6(_TRACKING_VELOCITY_RANGE),
     enable_corruption=not play, push_enabled=not play,
   )
+
+
+# ---------------------------------------------------------------------------------------------------------
+# consuming a reference ManagerBasedRlEnvCfg (envs/manager_based_rl_env.py:59-129)
+# ---------------------------------------------------------------------------------------------------------
+# kernel reward slot -> the reference term FUNCTION it implements (tasks/velocity/mdp/rewards.py, envs/mdp/rewards.py)
+REWARD_FUNCS = {
+  "track_linear_velocity": "track_linear_velocity", "track_angular_velocity": "track_angular_velocity", "upright": "flat_orientation",
+  "pose": "variable_posture", "body_ang_vel": "body_angular_velocity_penalty", "angular_momentum": "angular_momentum_penalty",
+  "dof_pos_limits": "joint_pos_limits", "action_rate_l2": "action_rate_l2", "air_time": "feet_air_time", "foot_clearance": "feet_clearance",
+  "foot_swing_height": "feet_swing_height", "foot_slip": "feet_slip", "soft_landing": "soft_landing", "self_collisions": "self_collision_cost",
+}
+# observation terms the fused kernel writes, in its fixed order: (term function, sensor_name param or None)
+POLICY_OBS_TERMS = (("builtin_sensor", "robot/imu_lin_vel"), ("builtin_sensor", "robot/imu_ang_vel"), ("projected_gravity", None),
+                    ("joint_pos_rel", None), ("joint_vel_rel", None), ("last_action", None), ("generated_commands", None))
+CRITIC_EXTRA_OBS_TERMS = (("foot_height", None), ("foot_air_time", None), ("foot_contact", None), ("foot_contact_forces", None))
+_POST_KEYS = ("clip", "scale", "delay_min_lag", "delay_max_lag", "delay_per_env", "delay_hold_prob", "delay_update_period",
+              "delay_per_env_phase", "history_length", "flatten_history_dim")
+
+
+class UnsupportedTermError(NotImplementedError):
+  """A term / option of the configuration that the fused env kernels do not implement (never silently ignored)."""
+
+
+def _range6(d) -> dict:
+  return {k: (float(v[0]), float(v[1])) for k, v in (d or {}).items()}
+
+
+def from_manager_cfg(cfg, m, robot: str) -> VelocityCfg:
+  """Resolve a reference `ManagerBasedRlEnvCfg` of the velocity task (the live dataclass or its `cfg_to_dict` view) into the
+  kernels' `VelocityCfg`: reward weights and parameters by term FUNCTION, termination set, observation noise / corruption flags,
+  action scale, reset / push / friction events, command ranges, curricula, episode length, decimation.  The kernels implement the
+  shipped term functions in a fixed observation layout; anything else raises `UnsupportedTermError` naming the term.  Per-term
+  clip / scale / delay / history settings are returned in `extra["obs_post"]` for `obs_pipeline.ObservationPipeline`."""
+  d = cfg if isinstance(cfg, dict) else cfg_to_dict(cfg)
+  c = velocity_cfg(m, robot, play=False)
+  pre = "robot/"
+  local_names = [n.removeprefix(pre) for n in c.joint_names]
+  # ---- timing ---------------------------------------------------------------------------------------------------------
+  mj = d["sim"]["mujoco"]
+  if mj["solver"] != "newton" or mj["cone"] != "pyramidal" or mj["integrator"] not in ("implicitfast", "euler"):
+    raise UnsupportedTermError(f"sim options {mj['solver']} / {mj['cone']} / {mj['integrator']} are outside the supported subset")
+  c.decimation = int(d["decimation"])
+  c.step_dt = float(mj["timestep"]) * c.decimation
+  c.max_episode_length_s = float(d["episode_length_s"])
+  c.max_episode_length = math.ceil(c.max_episode_length_s / c.step_dt)
+  c.extra["sim"] = dict(timestep=float(mj["timestep"]), iterations=int(mj["iterations"]), ls_iterations=int(mj["ls_iterations"]),
+                        integrator=mj["integrator"], nconmax=d["sim"]["nconmax"], njmax=d["sim"]["njmax"])
+  # ---- rewards --------------------------------------------------------------------------------------------------------
+  by_func = {}
+  for name, t in d["rewards"].items():
+    if t is None:
+      continue
+    if t["func"] in by_func:
+      raise UnsupportedTermError(f"reward function '{t['func']}' appears twice ('{by_func[t['func']][0]}', '{name}')")
+    by_func[t["func"]] = (name, t)
+  unknown = set(by_func) - set(REWARD_FUNCS.values())
+  if unknown:
+    raise UnsupportedTermError(f"reward terms {sorted(by_func[f][0] for f in unknown)} ({sorted(unknown)}) are not implemented by the env kernels")
+  w = np.zeros(len(REWARD_NAMES))
+  P = {}
+  for k, slot in enumerate(REWARD_NAMES):
+    if REWARD_FUNCS[slot] in by_func:
+      _, t = by_func[REWARD_FUNCS[slot]]
+      w[k] = float(t["weight"])
+      P[slot] = t["params"]
+  c.reward_weights = w
+  if "track_linear_velocity" in P: c.std_lin = float(P["track_linear_velocity"]["std"])        # noqa: E701
+  if "track_angular_velocity" in P: c.std_ang = float(P["track_angular_velocity"]["std"])      # noqa: E701
+  if "upright" in P:
+    c.std_upright = float(P["upright"]["std"])
+    bn = P["upright"]["asset_cfg"].get("body_names")
+    if bn:
+      body_local = [m.body_names[i].removeprefix(pre) for i in c.body_ids]
+      hit = [i for i, n in enumerate(body_local) if any(re.fullmatch(k, n) for k in bn)]
+      if len(hit) != 1:
+        raise UnsupportedTermError(f"flat_orientation: body_names {bn} must select exactly one body")
+      c.upright_body_local, c.upright_body = hit[0], int(c.body_ids[hit[0]])
+  if "pose" in P:
+    p = P["pose"]
+    c.walking_threshold, c.running_threshold = float(p["walking_threshold"]), float(p["running_threshold"])
+    for key in ("standing", "walking", "running"):
+      mp = {k: float(v) for k, v in p[f"std_{key}"].items()}
+      setattr(c, f"std_{key}_map", mp)
+      setattr(c, f"std_{key}", _resolve_values(mp, local_names))
+  if "air_time" in P:
+    p = P["air_time"]
+    c.air_thr_min, c.air_thr_max, c.air_cmd_threshold = float(p["threshold_min"]), float(p["threshold_max"]), float(p["command_threshold"])
+  th = {float(P[s]["command_threshold"]) for s in ("foot_clearance", "foot_swing_height", "foot_slip", "soft_landing") if s in P}
+  hs = {float(P[s]["target_height"]) for s in ("foot_clearance", "foot_swing_height") if s in P}
+  if len(th) > 1 or len(hs) > 1:
+    raise UnsupportedTermError(f"the foot terms share one command_threshold / target_height in the kernels, got {sorted(th)} / {sorted(hs)}")
+  if th: c.cmd_threshold = th.pop()          # noqa: E701
+  if hs: c.target_height = hs.pop()          # noqa: E701
+  # ---- terminations -----------------------------------------------------------------------------------------------------
+  tf = {t["func"]: t for t in d["terminations"].values() if t is not None}
+  bad = set(tf) - {"time_out", "bad_orientation", "illegal_contact"}
+  if bad:
+    raise UnsupportedTermError(f"termination functions {sorted(bad)} are not implemented by the env kernels")
+  if "time_out" not in tf or not tf["time_out"]["time_out"]:
+    raise UnsupportedTermError("the kernels always apply the time_out truncation")
+  if "bad_orientation" in tf:
+    c.limit_angle = float(tf["bad_orientation"]["params"]["limit_angle"])
+  else:
+    c.limit_angle = 4.0          # never reached: projected gravity angle <= pi
+  if ("illegal_contact" in tf) != (c.illegal_count > 0):
+    raise UnsupportedTermError("illegal_contact needs the scene's nonfoot_ground_touch sensor (and the compiled Go1 scene always has it)")
+  # ---- observations -------------------------------------------------------------------------------------------------------
+  obs = d["observations"]
+  if set(obs) != {"policy", "critic"}:
+    raise UnsupportedTermError(f"observation groups {sorted(obs)}: the kernels write 'policy' and 'critic'")
+  post = {}
+  for group, want in (("policy", POLICY_OBS_TERMS), ("critic", POLICY_OBS_TERMS + CRITIC_EXTRA_OBS_TERMS)):
+    g = obs[group]
+    terms = [(n, t) for n, t in g["terms"].items() if t is not None]
+    got = tuple((t["func"], t["params"].get("sensor_name") if t["func"] == "builtin_sensor" else None) for _, t in terms)
+    if got != want:
+      raise UnsupportedTermError(f"observation group '{group}': terms {got} differ from the kernel's layout {want}")
+    if not g["concatenate_terms"]:
+      raise UnsupportedTermError("concatenate_terms=False")
+    post[group] = []
+    for n, t in terms:
+      e = {k: t[k] for k in _POST_KEYS}
+      if g.get("history_length") is not None:
+        e["history_length"], e["flatten_history_dim"] = g["history_length"], g["flatten_history_dim"]
+      e["name"] = n
+      post[group].append(e)
+  if obs["critic"]["enable_corruption"]:
+    raise UnsupportedTermError("critic.enable_corruption=True: the kernels only corrupt the policy group")
+  c.enable_corruption = bool(obs["policy"]["enable_corruption"])
+  nj = c.nj
+  seg = [(0, 3), (3, 6), (6, 9), (9, 9 + nj), (9 + nj, 9 + 2 * nj), (9 + 2 * nj, 9 + 3 * nj), (9 + 3 * nj, 12 + 3 * nj)]
+  lo, hi = np.zeros(c.n_obs_policy), np.zeros(c.n_obs_policy)
+  for (a, b), (n, t) in zip(seg, [(n, t) for n, t in obs["policy"]["terms"].items() if t is not None]):
+    nz = t["noise"]
+    if nz is None:
+      continue
+    if nz.get("__type__") != "UniformNoiseCfg" or nz.get("operation") != "add":
+      raise UnsupportedTermError(f"observation term '{n}': noise {nz} (only additive UniformNoiseCfg is implemented)")
+    lo[a:b], hi[a:b] = float(nz["n_min"]), float(nz["n_max"])
+  c.noise_lo, c.noise_hi = lo, hi
+  c.extra["obs_post"] = post
+  # ---- actions ----------------------------------------------------------------------------------------------------------------
+  acts = [a for a in d["actions"].values() if a is not None]
+  if len(acts) != 1 or acts[0]["class_type"] != "JointPositionAction" or not acts[0]["use_default_offset"] or acts[0]["clip"]:
+    raise UnsupportedTermError("actions: one JointPositionAction with use_default_offset=True and no clip is implemented")
+  sc = acts[0]["scale"]
+  c.action_scale = _resolve_values({k: float(v) for k, v in sc.items()}, local_names) if isinstance(sc, dict) else np.full(nj, float(sc))
+  # ---- events -------------------------------------------------------------------------------------------------------------------
+  c.push_enabled = False
+  c.extra["foot_friction"] = None
+  terrain_mode = 0
+  for name, e in d["events"].items():
+    if e is None:
+      continue
+    f, p = e["func"], e["params"]
+    if f == "reset_root_state_uniform" and e["mode"] == "reset":
+      c.reset_pose_range, c.reset_velocity_range = _range6(p.get("pose_range")), _range6(p.get("velocity_range"))
+    elif f == "reset_joints_by_offset" and e["mode"] == "reset":
+      c.reset_joint_pos, c.reset_joint_vel = tuple(map(float, p["position_range"])), tuple(map(float, p["velocity_range"]))
+    elif f == "push_by_setting_velocity" and e["mode"] == "interval":
+      c.push_enabled, c.push_interval = True, tuple(map(float, e["interval_range_s"]))
+      c.push_velocity_range = _range6(p["velocity_range"])
+    elif f == "randomize_field" and e["mode"] == "startup":
+      if p["field"] != "geom_friction" or p["operation"] != "abs":
+        raise UnsupportedTermError(f"startup event '{name}': randomize_field({p['field']}, {p['operation']}) - call events.randomize_field yourself")
+      c.extra["foot_friction"] = dict(ranges=tuple(map(float, p["ranges"])), geom_names=tuple(p["asset_cfg"]["geom_names"]))
+    elif f == "randomize_terrain" and e["mode"] == "reset":
+      terrain_mode |= 2
+    else:
+      raise UnsupportedTermError(f"event '{name}' ({f}, mode {e['mode']}) is not implemented by the env kernels")
+  # ---- commands -------------------------------------------------------------------------------------------------------------------
+  cmds = [t for t in d["commands"].values() if t is not None]
+  if len(cmds) != 1 or cmds[0]["class_type"] != "UniformVelocityCommand":
+    raise UnsupportedTermError("commands: one UniformVelocityCommand is implemented")
+  t = cmds[0]
+  if t["init_velocity_prob"] != 0.0:
+    raise UnsupportedTermError("UniformVelocityCommand.init_velocity_prob > 0")
+  r = t["ranges"]
+  c.cmd_resample = tuple(map(float, t["resampling_time_range"]))
+  c.cmd_lin_x, c.cmd_lin_y, c.cmd_ang_z = tuple(map(float, r["lin_vel_x"])), tuple(map(float, r["lin_vel_y"])), tuple(map(float, r["ang_vel_z"]))
+  c.heading_command = bool(t["heading_command"])
+  if c.heading_command:
+    c.cmd_heading = tuple(map(float, r["heading"]))
+  c.rel_standing, c.rel_heading, c.heading_stiffness = float(t["rel_standing_envs"]), float(t["rel_heading_envs"]), float(t["heading_control_stiffness"])
+  # ---- curriculum -------------------------------------------------------------------------------------------------------------------
+  c.extra["velocity_stages"] = ()
+  for name, t in d["curriculum"].items():
+    if t is None:
+      continue
+    if t["func"] == "commands_vel":
+      c.extra["velocity_stages"] = tuple({k: (tuple(v) if isinstance(v, list) else v) for k, v in st.items()} for st in t["params"]["velocity_stages"])
+    elif t["func"] == "terrain_levels_vel":
+      terrain_mode |= 1
+    else:
+      raise UnsupportedTermError(f"curriculum term '{name}' ({t['func']})")
+  has_terrain = c.terrain_origins is not None
+  gen = d["scene"]["terrain"].get("terrain_generator") if d["scene"].get("terrain") else None
+  if (gen is not None) != has_terrain:
+    raise UnsupportedTermError("the configuration's terrain (plane / generator) does not match the compiled scene")
+  c.terrain_mode = terrain_mode if has_terrain else 0
+  if gen is not None:
+    c.terrain_half_size = float(gen["size"][0]) / 2.0
+    c.max_init_terrain_level = int(d["scene"]["terrain"]["max_init_terrain_level"])
+  return c

@@ -335,3 +335,48 @@ def test_vecenv_wrapper_contract():
   assert float(env.action_manager.action.abs().max()) <= 0.5 + 1e-6     # clipped before the env sees it
   o2 = venv.get_observations()
   assert torch.equal(o2["policy"], obs["policy"])
+
+
+def test_observation_pipeline_matches_reference_manager(monkeypatch):
+  """clip -> scale -> delay -> history -> concatenate of `obs_pipeline.ObservationPipeline` against the reference's own
+  ObservationManager (tests/golden/obs_pipeline.npz, tools/make_obs_pipeline_golden.py) on the same term inputs and the same
+  recorded lag draws: per-env stochastic delay with an update period and hold probability, per-term and group-level history
+  (term-major, oldest first), partial reset at step 5 (back-fill on the next push), cached compute() without a second push."""
+  from pathlib import Path
+  from mjlab_b200.obs_pipeline import ObservationPipeline
+  g = np.load(Path(__file__).resolve().parent / "golden" / "obs_pipeline.npz")
+  seq = {k: torch.as_tensor(g[f"seq_{k}"], device=DEV) for k in ("a", "b", "c")}
+  T, B = g["ref_policy"].shape[:2]
+  post = {
+    "policy": [
+      dict(name="a", clip=(-1.0, 1.5), scale=None, delay_min_lag=0, delay_max_lag=0, history_length=0),
+      dict(name="b", clip=None, scale=(0.5, 2.0, 1.0, -1.0), delay_min_lag=1, delay_max_lag=3, delay_update_period=2, delay_hold_prob=0.25, history_length=0),
+      dict(name="c", clip=(-2.0, 2.0), scale=0.1, delay_min_lag=0, delay_max_lag=2, history_length=3),
+    ],
+    "critic": [dict(name="a", history_length=2, flatten_history_dim=True), dict(name="c", history_length=2, flatten_history_dim=True)],
+  }
+  # replay the reference's draws (same hooks as the DelayBuffer tests; the fixture stores them as draw0 .. drawN)
+  from mjlab_b200 import actuators as ACT
+  draws, pos = [g[f"draw{i}"] for i in range(int(g["ndraws"]))], [0]
+
+  def nxt(shape, device, dtype):
+    v = draws[pos[0]]
+    pos[0] += 1
+    assert tuple(v.shape) == tuple(shape), (pos[0], v.shape, shape)
+    return torch.as_tensor(v, device=device).to(dtype)
+
+  monkeypatch.setattr(ACT, "_randint", lambda lo, hi, shape, device, generator=None: nxt(shape, device, torch.long))
+  monkeypatch.setattr(ACT, "_rand", lambda shape, device, generator=None: nxt(shape, device, torch.float32))
+  pipe = ObservationPipeline({"policy": [("a", 3), ("b", 4), ("c", 2)], "critic": [("a", 3), ("c", 2)]}, post, B, DEV)
+  assert [int(np.prod(d)) for d in pipe.term_dims("policy")] == g["term_dims_policy"].tolist()
+  assert [int(np.prod(d)) for d in pipe.term_dims("critic")] == g["term_dims_critic"].tolist()
+  for t in range(T):
+    raw = {"policy": torch.cat([seq["a"][t], seq["b"][t], seq["c"][t]], 1), "critic": torch.cat([seq["a"][t], seq["c"][t]], 1)}
+    if t == 5:
+      pipe.reset(torch.tensor([1, 3], device=DEV))
+    o = pipe.compute(raw, update_history=True)
+    again = pipe.compute(raw)
+    for grp in ("policy", "critic"):
+      np.testing.assert_allclose(o[grp].cpu().numpy(), g[f"ref_{grp}"][t], rtol=1e-6, atol=1e-6, err_msg=f"{grp} t={t}")
+      assert again[grp] is o[grp]
+  assert pos[0] == len(draws)

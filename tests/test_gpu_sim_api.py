@@ -356,3 +356,75 @@ def test_nan_guard_covers_the_fused_env_step(tmp_path):
   dump = np.load(tmp_path / "nan_dump_latest.npz", allow_pickle=True)
   meta = dump["_metadata"].item()
   assert 5 in meta["nan_env_ids"] and meta["buffer_size"] == 4
+
+
+def _task_cfg(task, play=False):
+  import json
+  from pathlib import Path
+  return json.loads((Path(__file__).resolve().parent / "golden" / "task_cfg" / f"{task}{'-play' if play else ''}.json").read_text())
+
+
+def test_env_from_the_reference_manager_cfg_equals_the_builtin_task():
+  """`VelocityEnvCfg.from_manager_cfg(load_env_cfg(task))`: the env built from the reference's own configuration object (its JSON
+  dump, tests/golden/task_cfg) steps bit-identically to the built-in task of the same name."""
+  from mjlab_b200.env import ManagerBasedRlEnv, VelocityEnvCfg
+  d = _task_cfg("Mjlab-Velocity-Flat-Unitree-Go1")
+  a = ManagerBasedRlEnv(VelocityEnvCfg.from_task("Mjlab-Velocity-Flat-Unitree-Go1", num_envs=64, seed=5), DEV)
+  torch.manual_seed(123)
+  b = ManagerBasedRlEnv(VelocityEnvCfg.from_manager_cfg(d, "go1", "flat", num_envs=64, seed=5), DEV)
+  assert b.max_episode_length == a.max_episode_length == 1000 and b.step_dt == a.step_dt
+  outs = []
+  for env in (a, b):
+    torch.manual_seed(9)       # the startup foot-friction event draws from torch's generator
+    env2 = env
+    g = torch.Generator(device=DEV).manual_seed(1)
+    env2.sim.model.geom_friction[:] = a.sim.model.geom_friction      # same startup DR on both
+    env2.reset()
+    env2.episode_length_buf = torch.randint(0, 1000, (64,), device=DEV, generator=g)
+    for _ in range(12):
+      obs, rew, term, trunc, _ = env2.step(torch.rand(64, env2.vcfg.nj, device=DEV, generator=g) * 2 - 1)
+    outs.append((obs["policy"].clone(), obs["critic"].clone(), rew.clone(), term.clone(), env2.sim.data.qpos.clone()))
+  for x, y in zip(*outs):
+    assert torch.equal(x, y)
+
+
+def test_env_consumes_edited_manager_cfg_with_history_and_delay():
+  """A user-edited reference cfg: a reward re-weighted and one removed, no push event, 3-step history on the critic group and a
+  delayed, clipped policy term -> consumed (weights, flags) and post-processed (observation shapes, delay, history back-fill)."""
+  from mjlab_b200 import envcfg
+  from mjlab_b200.env import ManagerBasedRlEnv, VelocityEnvCfg
+  d = _task_cfg("Mjlab-Velocity-Flat-Unitree-Go1")
+  d["rewards"]["foot_slip"]["weight"] = -0.7
+  d["rewards"].pop("soft_landing")
+  d["events"].pop("push_robot")
+  d["observations"]["critic"]["history_length"] = 3
+  d["observations"]["policy"]["enable_corruption"] = False
+  d["observations"]["policy"]["terms"]["base_ang_vel"].update(delay_min_lag=2, delay_max_lag=2)
+  d["observations"]["policy"]["terms"]["joint_vel"].update(clip=[-1.0, 1.0], scale=0.5)
+  env = ManagerBasedRlEnv(VelocityEnvCfg.from_manager_cfg(d, "go1", "flat", num_envs=32, seed=2), DEV)
+  k = envcfg.REWARD_NAMES.index
+  assert env.vcfg.reward_weights[k("foot_slip")] == -0.7 and env.vcfg.reward_weights[k("soft_landing")] == 0 and not env.vcfg.push_enabled
+  obs, _ = env.reset()
+  nj = env.vcfg.nj
+  assert obs["policy"].shape == (32, 48) and obs["critic"].shape == (32, 3 * 72)
+  raw_hist = []
+  z = torch.zeros(32, nj, device=DEV)
+  for t in range(6):
+    obs, rew, term, trunc, _ = env.step(z)
+    raw = env._raw_obs["policy"].clone()
+    raw_hist.append(raw)
+    alive = ~(term | trunc)
+    # clipped + scaled term
+    jv = obs["policy"][:, 9 + nj: 9 + 2 * nj]
+    torch.testing.assert_close(jv, raw[:, 9 + nj: 9 + 2 * nj].clip(-1, 1) * 0.5)
+    # delayed term: the value of two control steps ago (envs that have not been reset since)
+    if t >= 2:
+      keep = alive & alive_prev & alive_prev2
+      torch.testing.assert_close(obs["policy"][keep, 3:6], raw_hist[t - 2][keep, 3:6])
+    alive_prev2 = alive_prev if t >= 1 else alive
+    alive_prev = alive
+    # critic history, term-major, oldest first: the newest slot of the first term is this step's raw critic term
+    torch.testing.assert_close(obs["critic"][:, 6:9], env._raw_obs["critic"][:, 0:3])
+  with pytest.raises(envcfg.UnsupportedTermError):
+    d["rewards"]["x"] = dict(func="electrical_power_cost", weight=-1.0, params={})
+    ManagerBasedRlEnv(VelocityEnvCfg.from_manager_cfg(d, "go1", "flat", num_envs=8), DEV)

@@ -1,0 +1,107 @@
+"""The kernels' built-in task tables (`envcfg.velocity_cfg`, `env.VelocityEnvCfg`) against THE REFERENCE'S OWN configuration
+objects: tests/golden/task_cfg/*.json are dumps of `load_env_cfg(task, play)` (tools/make_cfg_golden.py runs the reference's
+tasks/registry.py under tools/refstub.py).  `envcfg.from_manager_cfg` - the path a user's ManagerBasedRlEnvCfg takes - must
+resolve each dump to exactly the built-in configuration: every reward weight and parameter, noise range, termination, reset /
+push / command range, curriculum stage, episode length.  Also: unsupported terms raise instead of being ignored."""
+import copy
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import mjlab_b200
+from mjlab_b200 import envcfg
+
+CFG = Path(__file__).resolve().parent / "golden" / "task_cfg"
+CASES = [("Mjlab-Velocity-Flat-Unitree-G1", "g1", "flat"), ("Mjlab-Velocity-Flat-Unitree-Go1", "go1", "flat"),
+         ("Mjlab-Velocity-Rough-Unitree-G1", "g1", "rough"), ("Mjlab-Velocity-Rough-Unitree-Go1", "go1", "rough")]
+SCALARS = ("decimation", "step_dt", "max_episode_length", "max_episode_length_s", "limit_angle", "std_lin", "std_ang", "std_upright",
+           "walking_threshold", "running_threshold", "air_thr_min", "air_thr_max", "air_cmd_threshold", "target_height", "cmd_threshold",
+           "cmd_resample", "cmd_lin_x", "cmd_lin_y", "cmd_ang_z", "cmd_heading", "rel_standing", "rel_heading", "heading_stiffness",
+           "reset_joint_pos", "reset_joint_vel", "enable_corruption", "push_enabled", "heading_command", "terrain_mode",
+           "upright_body", "upright_body_local")
+ARRAYS = ("reward_weights", "std_standing", "std_walking", "std_running", "noise_lo", "noise_hi", "action_scale", "reset_pose", "reset_vel")
+
+
+def _load(task, play):
+  return json.loads((CFG / f"{task}{'-play' if play else ''}.json").read_text())
+
+
+@pytest.mark.parametrize("task,robot,terrain", CASES)
+@pytest.mark.parametrize("play", [False, True])
+def test_builtin_task_tables_equal_the_reference_cfg(task, robot, terrain, play):
+  d = _load(task, play)
+  m = mjlab_b200.load_model(f"{robot}_{terrain}" + ("_play" if (play and terrain == "rough") else ""))
+  got = envcfg.from_manager_cfg(d, m, robot)
+  want = envcfg.velocity_cfg(m, robot, play=play)
+  if play and robot == "g1" and terrain == "flat":        # env.ManagerBasedRlEnv applies the G1 play override of the command ranges (config/g1/env_cfgs.py:167-173)
+    want.cmd_lin_x, want.cmd_ang_z = (-1.5, 2.0), (-0.7, 0.7)
+  for k in SCALARS:
+    a, b = getattr(got, k), getattr(want, k)
+    if isinstance(b, tuple):
+      np.testing.assert_allclose(a, b, rtol=1e-12, err_msg=k)
+    else:
+      assert a == pytest.approx(b, rel=1e-12), k
+  for k in ARRAYS:
+    np.testing.assert_allclose(getattr(got, k), getattr(want, k), rtol=1e-12, atol=0, err_msg=k)
+  if want.push_enabled:
+    np.testing.assert_allclose(got.push_vel, want.push_vel)
+    np.testing.assert_allclose(got.push_interval, want.push_interval)
+  if terrain == "rough":
+    assert got.terrain_half_size == want.terrain_half_size and got.max_init_terrain_level == want.max_init_terrain_level
+  # env-level settings: foot friction DR, velocity curriculum stages, sim options
+  from mjlab_b200.env import VelocityEnvCfg, _default_sim_cfg
+  ecfg = VelocityEnvCfg(robot=robot, terrain=terrain, play=play)
+  ff = got.extra["foot_friction"]
+  assert ff is not None and tuple(ff["ranges"]) == tuple(ecfg.foot_friction_range)
+  prims = [f"{s}_foot{i}_collision" for s in ("left", "right") for i in range(1, 8)] if robot == "g1" else [f"{leg}_foot_collision" for leg in ("FR", "FL", "RR", "RL")]
+  assert sorted(ff["geom_names"]) == sorted(prims)
+  stages = got.extra["velocity_stages"]
+  assert len(stages) == len(ecfg.velocity_stages)
+  for s, w in zip(stages, ecfg.velocity_stages):
+    assert s["step"] == w["step"] and all(tuple(s[k]) == tuple(w[k]) for k in w if k != "step") and set(s) == set(w)
+  sc = _default_sim_cfg()
+  assert got.extra["sim"] == dict(timestep=sc.mujoco.timestep, iterations=sc.mujoco.iterations, ls_iterations=sc.mujoco.ls_iterations,
+                                  integrator=sc.mujoco.integrator, nconmax=sc.nconmax, njmax=sc.njmax)
+  # no term asks for clip / scale / delay / history in the shipped tasks: the post-processing pipeline is the identity
+  for group in ("policy", "critic"):
+    assert all(t["clip"] is None and t["scale"] is None and t["delay_max_lag"] == 0 and t["history_length"] == 0 for t in got.extra["obs_post"][group])
+
+
+def test_unsupported_terms_raise():
+  m = mjlab_b200.load_model("g1_flat")
+  base = _load("Mjlab-Velocity-Flat-Unitree-G1", False)
+
+  def bad(edit, match):
+    d = copy.deepcopy(base)
+    edit(d)
+    with pytest.raises(envcfg.UnsupportedTermError, match=match):
+      envcfg.from_manager_cfg(d, m, "g1")
+
+  bad(lambda d: d["rewards"].update(my_term=dict(func="my_reward", weight=1.0, params={})), "my_term")
+  bad(lambda d: d["terminations"].update(x=dict(func="root_height_below_minimum", time_out=False, params={})), "root_height_below_minimum")
+  bad(lambda d: d["observations"]["policy"]["terms"].pop("joint_vel"), "differ from the kernel's layout")
+  bad(lambda d: d["observations"]["critic"].update(enable_corruption=True), "critic.enable_corruption")
+  bad(lambda d: d["events"].update(x=dict(func="apply_external_force_torque", mode="reset", params={}, interval_range_s=None)), "apply_external_force_torque")
+  bad(lambda d: d["commands"]["twist"].update(init_velocity_prob=0.5), "init_velocity_prob")
+  bad(lambda d: d["sim"]["mujoco"].update(solver="cg"), "supported subset")
+  bad(lambda d: d["observations"]["policy"]["terms"]["joint_pos"].update(noise=dict(__type__="GaussianNoiseCfg", operation="add", mean=0, std=1)), "UniformNoiseCfg")
+
+
+def test_reweighted_and_removed_terms_are_consumed():
+  m = mjlab_b200.load_model("go1_flat")
+  d = _load("Mjlab-Velocity-Flat-Unitree-Go1", False)
+  d["rewards"]["foot_slip"]["weight"] = -0.7
+  d["rewards"].pop("soft_landing")
+  d["rewards"]["track_linear_velocity"]["params"]["std"] = 0.3
+  d["events"].pop("push_robot")
+  d["observations"]["policy"]["terms"]["joint_vel"]["noise"]["n_max"] = 2.5
+  d["observations"]["policy"]["terms"]["base_ang_vel"]["delay_max_lag"] = 2
+  d["observations"]["critic"]["history_length"] = 3
+  c = envcfg.from_manager_cfg(d, m, "go1")
+  k = envcfg.REWARD_NAMES.index
+  assert c.reward_weights[k("foot_slip")] == -0.7 and c.reward_weights[k("soft_landing")] == 0.0 and c.std_lin == 0.3
+  assert not c.push_enabled and c.noise_hi[9 + c.nj] == 2.5 and c.noise_lo[9 + c.nj] == -1.5
+  post = c.extra["obs_post"]
+  assert post["policy"][1]["delay_max_lag"] == 2 and all(t["history_length"] == 3 for t in post["critic"])

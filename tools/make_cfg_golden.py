@@ -37,5 +37,5 @@ if __name__ == "__main__":
       d = cfg_to_dict(cfg)
       d["__task__"], d["__play__"] = task, play
       path = out / f"{task}{'-play' if play else ''}.json"
-      path.write_text(json.dumps(d, indent=1, sort_keys=True))
+      path.write_text(json.dumps(d, indent=1))   # key order kept: the order of observation terms IS the observation layout
       print(path.name, len(path.read_text()) // 1024, "KB", "rewards:", len(d["rewards"]), "obs:", {g: len(v["terms"]) for g, v in d["observations"].items()})
