@@ -130,6 +130,9 @@ static long long b2h_flip_hist[66] = {0};   // [k < 64]: Newton iterations (it >
 #ifndef B2_GRAD_FLOOR_MULT
 #define B2_GRAD_FLOOR_MULT 4   // float32 only: |gradient| < mult * eps * |(M a, qfrc_smooth, qfrc_constraint)| counts as converged; 0 = off
 #endif
+#ifndef B2_GRAD_KEEP_MULT
+#define B2_GRAD_KEEP_MULT 100   // float32 only: do not stop on "no cost improvement" while |gradient| > mult * its rounding noise; 0 = off
+#endif
 #ifndef B2_FLOOR_MULT
 #define B2_FLOOR_MULT 8   // rounding floor of the convergence test, in units of eps * |cost| (experiments: tools/floor_experiment.py)
 #endif
@@ -865,16 +868,24 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
       if (it > 0) {
         gn = sqrt(b2_wsum(gn));
         // float32: a gradient below the rounding noise of its own three terms is zero for all practical purposes
-        bool grad_is_noise = false;
-        if (sizeof(real) == 4 && B2_GRAD_FLOOR_MULT > 0)
-          grad_is_noise = gn < (real)B2_GRAD_FLOOR_MULT * eps_real * sqrt(b2_wsum(gref));
+        bool grad_is_noise = false, grad_is_large = false;
+        if (sizeof(real) == 4 && B2_GRAD_FLOOR_MULT > 0) {
+          const real gnoise = eps_real * sqrt(b2_wsum(gref));
+          grad_is_noise = gn < (real)B2_GRAD_FLOOR_MULT * gnoise;
+          // float32 cannot resolve cost differences below ~eps |cost|, so "no improvement" is not evidence of convergence while
+          // the gradient still stands far above ITS rounding noise: keep iterating then (the Newton direction and the line
+          // search work from derivatives, not from cost differences).  Without this a world could stop one iteration early with
+          // a residual that the implicit integrator turns into a 1e-2 rad/s velocity error on a light ankle dof
+          // (profiles/r02_divergence.txt).  0 = off.
+          grad_is_large = B2_GRAD_KEEP_MULT > 0 && gn > (real)B2_GRAD_KEEP_MULT * gnoise;
+        }
         real improvement = scale * (cost - newcost);
         real floor_ = fmax(tolerance, B2_FLOOR_MULT * eps_real * scale * fabs(newcost));
 #ifdef B2_TRACE
         printf("w%d it%d cost %.9g new %.9g impr %.3g floor %.3g gn*scale %.3g same %d nefc %d\n", w, it, (double)cost, (double)newcost, (double)improvement, (double)floor_, (double)(scale * gn), (int)same_set, nefc);
 #endif
         cost = newcost;
-        if (improvement < floor_ || scale * gn < tolerance || grad_is_noise) break;
+        if ((improvement < floor_ && !grad_is_large) || scale * gn < tolerance || grad_is_noise) break;
       } else {
         cost = newcost;
       }

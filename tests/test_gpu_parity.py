@@ -1,8 +1,11 @@
 """GPU parity: CUDA path (through the C ABI via Simulation) vs the float64 oracle.
 
 Bit-exact: contact counts, contact geom-pair lists, efc row counts.
-Tolerance (stated per assertion): fp32 device arithmetic vs fp64 oracle,
-1e-4 relative per step on qpos/qvel (north_star), looser where noted.
+Tolerance (stated per assertion): fp32 device arithmetic vs fp64 oracle, north_star's 1e-4 relative per step on qpos, qvel,
+qacc, efc_force and sensordata.  Measured on these states (float32 host build of the kernel source vs float64, round 2): qvel
+1e-6 after 5 steps, efc_force 2e-5, qacc 5e-6, sensordata 8e-6, efc_aref 5e-6, efc_D 1e-4 (G1) - the bounds below leave 4-10 x room
+for the CUDA build's different summation order.  `relerr` normalises by the field's max-norm per world: components near zero have
+no relative error of their own.  The population statistic (128 worlds, N steps, worst world) is profiles/r02_divergence.txt.
 """
 import numpy as np
 import pytest
@@ -53,16 +56,16 @@ def test_forward_stagewise(name):
     assert int(D.nefc[w]) == d.nefc
     for fld, tol in [("xpos", 1e-6), ("xquat", 1e-6), ("geom_xpos", 1e-6), ("subtree_com", 1e-6), ("cdof", 2e-6),
                      ("qM", 1e-5), ("cvel", 1e-5), ("qfrc_bias", 1e-4), ("qfrc_actuator", 1e-5), ("qfrc_smooth", 1e-4),
-                     ("qacc_smooth", 1e-3)]:
+                     ("qacc_smooth", 1e-4)]:
       assert relerr(getattr(D, fld)[w].cpu().numpy(), getattr(d, fld)) < tol, (w, fld)
     n = d.nefc
     if n:
       assert relerr(D.efc_J[w, :n].cpu().numpy(), d.efc_J) < 1e-5
-      assert relerr(D.efc_D[w, :n].cpu().numpy(), d.efc_D) < 1e-4
-      assert relerr(D.efc_aref[w, :n].cpu().numpy(), d.efc_aref) < 1e-3
-      assert relerr(D.efc_force[w, :n].cpu().numpy(), d.efc_force) < 5e-3
-    assert relerr(D.qacc[w].cpu().numpy(), d.qacc) < 1e-3
-    assert relerr(D.sensordata[w].cpu().numpy(), d.sensordata) < 1e-3
+      assert relerr(D.efc_D[w, :n].cpu().numpy(), d.efc_D) < 5e-4
+      assert relerr(D.efc_aref[w, :n].cpu().numpy(), d.efc_aref) < 1e-4
+      assert relerr(D.efc_force[w, :n].cpu().numpy(), d.efc_force) < 2e-4
+    assert relerr(D.qacc[w].cpu().numpy(), d.qacc) < 1e-4
+    assert relerr(D.sensordata[w].cpu().numpy(), d.sensordata) < 1e-4
 
 
 @pytest.mark.parametrize("name,integrator", [("go1_flat", "implicitfast"), ("g1_flat", "implicitfast"), ("go1_flat", "euler")])
@@ -86,7 +89,7 @@ def test_step_trajectory(name, integrator):
     assert abs(float(sim.data.time[w]) - d.time) < 1e-6
   # 1e-4 relative per step (north_star), accumulated over nstep steps
   assert worst_q < 1e-4 * nstep, worst_q
-  assert worst_v < 1e-3 * nstep, worst_v
+  assert worst_v < 1e-4 * nstep, worst_v
 
 
 def test_reset_and_graph_replay(go1):
@@ -150,7 +153,7 @@ def test_gpu_matches_committed_golden(name):
   # fp32 vs fp64: 1e-4 relative per step on qpos / qvel (north_star), nstep steps
   nstep = int(g["nstep"])
   assert relerr(sim.data.qpos.cpu().numpy(), g["qpos"]) < 1e-4 * nstep
-  assert relerr(sim.data.qvel.cpu().numpy(), g["qvel"]) < 1e-3 * nstep
+  assert relerr(sim.data.qvel.cpu().numpy(), g["qvel"]) < 1e-4 * nstep
   assert relerr(sim.data.xpos.cpu().numpy(), g["xpos"]) < 1e-4 * nstep
 
 
