@@ -366,7 +366,7 @@ static int check_sizes(const b2_model* m, const b2_data* d) {
   if (m->nv > 64) return fail("nv=%d exceeds the 64-dof limit of the per-world dof masks", m->nv);
   if (m->nv < 1) return fail("nv must be >= 1");
   if (m->cone != 0) return fail("only the pyramidal cone is supported");
-  if (m->solver != 2) return fail("only the Newton solver is supported");
+  if (m->solver != 2 && m->solver != 1) return fail("supported solvers: Newton, CG (PGS is not implemented)");
   if (m->integrator != B2_INT_EULER && m->integrator != B2_INT_IMPLICITFAST) return fail("unsupported integrator %d", m->integrator);
   if (d->nworld < 1 || d->nconmax < 0 || d->njmax < 1) return fail("bad nworld/nconmax/njmax");
   return 0;

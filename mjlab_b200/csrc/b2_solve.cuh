@@ -18,7 +18,7 @@
 // J^T D J is accumulated run by run over w*(w+1)/2 dof pairs instead of nv*(nv+1)/2
 // (G1 foot-ground contact: w = 12 of nv = 35).
 struct SolveSmem {
-  int H, cdof, qvel, qacc, Ma, grad, search, Mv, qfs, qas, qfc, tmp, invd, pairtab, actmask;  // fixed part, per world
+  int H, cdof, qvel, qacc, Ma, grad, search, Mv, qfs, qas, qfc, tmp, invd, pairtab, actmask, gold, mgold;  // fixed part, per world
   int fixed_total;  // reals per world
   int arena_cap;    // reals of the row arena shared by the worlds of one CTA (>= the demand of one worst-case world)
   int rows_max;     // bound on constraint rows per world
@@ -48,6 +48,7 @@ static inline SolveSmem solve_smem_layout(int nv, int rows_max, int maxchain, in
   s.qfs = take(nv); s.qas = take(nv); s.qfc = take(nv); s.tmp = take(nv); s.invd = take(64);  // 1 / diag(L)
   s.pairtab = take((maxchain * (maxchain + 1) / 2 + 1) / 2);  // ushort (a << 8 | b) per lower-triangle pair index
   s.actmask = take((rows_max + 31) / 32);  // bit r: row r was active at the last Hessian factorisation
+  s.gold = take(nv); s.mgold = take(nv);   // CG solver: previous gradient and previous M^-1 gradient (Polak-Ribiere)
   s.fixed_total = o > min_fixed ? o : ((min_fixed + 3) & ~3);  // the fused sensor stage reuses the warp's fixed part as its scratch
   s.arena_cap = arena_cap;
   s.rows_max = rows_max;
@@ -362,6 +363,8 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
   real* qfc = sm + L.qfc; real* tmp = sm + L.tmp; real* invd = sm + L.invd;
   unsigned short* pairtab = (unsigned short*)(sm + L.pairtab);
   unsigned* actmask = (unsigned*)(sm + L.actmask);
+  real* gold = sm + L.gold; real* mgold = sm + L.mgold;
+  const bool cg = m.solver == 1;   // mjSOL_CG: M is the preconditioner, Polak-Ribiere directions (mj_solCG); 2 = Newton
   const int ld = b2_ld(nv);
   const int* body_parent = MI(B2_MI_BODY_PARENTID);
   const int* body_root = MI(B2_MI_BODY_ROOTID);
@@ -895,7 +898,16 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
 #endif
       B2_PH(2)
       // -- part 2: H = M + J^T diag(w) J, only when another Newton step will be taken  // @region hessian
-      if (same_set) {
+      if (cg) {
+        // CG: precondition with M alone - factorised once per solve - instead of the Hessian of the active set
+        if (it == 0) {
+          copy_g2s(H, M, nv * ld);
+          spd_factor_solve(H, nv, ld, tmp, invd);
+        } else {
+          chol_forwardsolve(H, nv, ld, invd, tmp);
+          chol_backsolve(H, nv, ld, invd, tmp);
+        }
+      } else if (same_set) {
         chol_forwardsolve(H, nv, ld, invd, tmp);
         chol_backsolve(H, nv, ld, invd, tmp);
       } else {
@@ -944,8 +956,24 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
       spd_factor_solve(H, nv, ld, tmp, invd);  // @region factor_call
       }
       B2_PH(4)
-      B2_UNROLL1
-      for (int i = B2_LANE; i < nv; i += B2_NLANE) search[i] = -tmp[i];
+      if (cg && it > 0) {
+        // Polak-Ribiere: beta = grad . (Mgrad - Mgrad_old) / (grad_old . Mgrad_old), restarted (beta = 0) when negative
+        real num = 0, den = 0;
+        B2_UNROLL1
+        for (int i = B2_LANE; i < nv; i += B2_NLANE) { num += grad[i] * (tmp[i] - mgold[i]); den += gold[i] * mgold[i]; }
+        num = b2_wsum(num); den = b2_wsum(den);
+        real beta = num / (den > B2_MINVAL ? den : B2_MINVAL);
+        if (beta < 0) beta = 0;
+        B2_UNROLL1
+        for (int i = B2_LANE; i < nv; i += B2_NLANE) search[i] = -tmp[i] + beta * search[i];
+      } else {
+        B2_UNROLL1
+        for (int i = B2_LANE; i < nv; i += B2_NLANE) search[i] = -tmp[i];
+      }
+      if (cg) {
+        B2_UNROLL1
+        for (int i = B2_LANE; i < nv; i += B2_NLANE) { gold[i] = grad[i]; mgold[i] = tmp[i]; }
+      }
       B2_WSYNC();
       // -- line search  // @region ls_setup
       real sn = 0, q1 = 0, q2 = 0, gs = 0;
@@ -961,7 +989,7 @@ B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int
       b2_wsum3(q1, q2, gs);
       rows_dot(jpool, rowinfo, runinfo, rundofs, nefc, search, jv, nullptr);
       B2_PH(5)
-      real alpha = linesearch(gauss, q1, q2, sn, tolerance, ls_tolerance, m.ls_iterations, scale, jar, jv, D, nefc, cost, gs);
+      real alpha = linesearch(gauss, q1, q2, sn, tolerance, ls_tolerance, m.ls_iterations, scale, jar, jv, D, nefc, cost, cg ? (real)0 : gs);   // the alpha = 0 shortcut needs H search = -grad: Newton only
       B2_PH(6)
       if (alpha == 0) break;
       B2_UNROLL1

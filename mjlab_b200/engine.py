@@ -252,8 +252,8 @@ def check_supported(m) -> None:
       raise ValueError(f"collision between geom types {t} ({m.geom_names[g1]}, {m.geom_names[g2]}) is not supported")
   if m.opt_cone != 0:
     raise ValueError("only the pyramidal friction cone is supported")
-  if m.opt_solver != 2:
-    raise ValueError("only the Newton solver is supported")
+  if m.opt_solver not in (1, 2):
+    raise ValueError("supported solvers: Newton, CG (PGS is not implemented)")
   if m.opt_integrator not in (0, 3):
     raise ValueError("supported integrators: euler, implicitfast")
   if m.nu and np.any(m.actuator_trnid[:, 0] < 0):

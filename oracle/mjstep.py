@@ -43,6 +43,7 @@ SENS_JOINTPOS, SENS_JOINTVEL = 8, 9
 SENS_FRAMEPOS, SENS_FRAMEQUAT, SENS_FRAMELINVEL, SENS_FRAMEANGVEL = 25, 26, 30, 31
 SENS_SUBTREECOM, SENS_SUBTREELINVEL, SENS_SUBTREEANGMOM = 34, 35, 36
 SENS_CONTACT = 42
+SOL_PGS, SOL_CG, SOL_NEWTON = range(3)
 MINVAL = 1e-15
 MINIMP, MAXIMP = 0.0001, 0.9999
 
@@ -1064,13 +1065,17 @@ def solve(m, d):
     st["cost"] = 0.5 * np.sum(D[act] * jar[act] ** 2) + st["gauss"]
     st["qfrc_constraint"] = J.T @ force
     st["grad"] = st["Ma"] - d.qfrc_smooth - st["qfrc_constraint"]
-    H = M + (J[act].T * D[act]) @ J[act]
-    st["Mgrad"] = np.linalg.solve(H, st["grad"])
+    if cg:
+      st["Mgrad"] = np.linalg.solve(M, st["grad"])      # CG: the mass matrix is the preconditioner (mj_solCG)
+    else:
+      H = M + (J[act].T * D[act]) @ J[act]
+      st["Mgrad"] = np.linalg.solve(H, st["grad"])
 
+  cg = int(getattr(m, "opt_solver", SOL_NEWTON)) == SOL_CG
   update(st, qacc)
   niter = 0
+  search = -st["Mgrad"]
   while niter < m.opt_iterations:
-    search = -st["Mgrad"]
     alpha = _linesearch(m, d, st, search, m.opt_tolerance, m.opt_ls_tolerance, m.opt_ls_iterations, scale)
     if alpha == 0.0:
       break
@@ -1078,7 +1083,13 @@ def solve(m, d):
     st["Ma"] = st["Ma"] + alpha * st["Mv"]
     st["jar"] = st["jar"] + alpha * st["jv"]
     oldcost = st["cost"]
+    gradold, Mgradold = st["grad"], st["Mgrad"]
     update(st, qacc)
+    if cg:   # Polak-Ribiere with the M^-1 preconditioner, restarted when negative (MuJoCo's mj_solCG / mj_solPrimal)
+      beta = np.dot(st["grad"], st["Mgrad"] - Mgradold) / max(MINVAL, np.dot(gradold, Mgradold))
+      search = -st["Mgrad"] + max(0.0, beta) * search
+    else:
+      search = -st["Mgrad"]
     niter += 1
     improvement = scale * (oldcost - st["cost"])
     gradient = scale * np.linalg.norm(st["grad"])

@@ -35,12 +35,12 @@ def test_simulation_config_is_piped():
   from mjlab_b200 import mjcf
   from mjlab_b200.sim import MujocoCfg, SimulationCfg
   cfg = SimulationCfg(contact_sensor_maxmatch=128, ls_parallel=False,
-                      mujoco=MujocoCfg(timestep=0.02, integrator="euler", solver="newton", iterations=7, ls_iterations=14,
+                      mujoco=MujocoCfg(timestep=0.02, integrator="euler", solver="cg", iterations=7, ls_iterations=14,
                                        ccd_iterations=20, gravity=(0, 0, 7.5)))
   sim = _sim(1, cfg)
   assert sim.mj_model.opt.timestep == cfg.mujoco.timestep
   assert sim.mj_model.opt.integrator == mjcf.INT_EULER
-  assert sim.mj_model.opt.solver == mjcf.SOL_NEWTON
+  assert sim.mj_model.opt.solver == mjcf.SOL_CG
   assert sim.mj_model.opt.iterations == cfg.mujoco.iterations
   assert sim.mj_model.opt.ls_iterations == cfg.mujoco.ls_iterations
   assert sim.mj_model.opt.ccd_iterations == cfg.mujoco.ccd_iterations
@@ -48,7 +48,7 @@ def test_simulation_config_is_piped():
   np.testing.assert_almost_equal(sim.model.opt.timestep[0].cpu().numpy(), cfg.mujoco.timestep)
   np.testing.assert_almost_equal(sim.model.opt.gravity[0].cpu().numpy(), cfg.mujoco.gravity)
   assert sim.model.opt.integrator == mjcf.INT_EULER
-  assert sim.model.opt.solver == mjcf.SOL_NEWTON
+  assert sim.model.opt.solver == mjcf.SOL_CG
   assert sim.model.opt.iterations == cfg.mujoco.iterations
   assert sim.wp_model.opt.contact_sensor_maxmatch == cfg.contact_sensor_maxmatch
   assert sim.wp_model.opt.ls_parallel == cfg.ls_parallel
@@ -57,9 +57,32 @@ def test_simulation_config_is_piped():
   # gravity (0, 0, +7.5) really reaches the kernels: the free body accelerates upwards
   sim.step()
   assert float(sim.data.qvel[0, 2]) == pytest.approx(7.5 * 0.02, rel=1e-5)
-  # the reference's test asks for solver="cg"; CG / PGS are outside the supported subset and refused at setup, not ignored
-  with pytest.raises(ValueError, match="Newton"):
-    _sim(1, SimulationCfg(mujoco=MujocoCfg(solver="cg")))
+  # PGS and the elliptic cone are outside the supported subset: refused at setup, not ignored
+  with pytest.raises(ValueError, match="PGS"):
+    _sim(1, SimulationCfg(mujoco=MujocoCfg(solver="pgs")))
+  with pytest.raises(ValueError, match="pyramidal"):
+    _sim(1, SimulationCfg(mujoco=MujocoCfg(cone="elliptic")))
+
+
+def test_cg_solver_on_the_gpu_matches_oracle():
+  import copy
+  import mjlab_b200
+  from mjlab_b200.sim import MujocoCfg, SimulationCfg
+  from tests import util
+  m = copy.deepcopy(mjlab_b200.load_model("go1_flat"))
+  nw = 8
+  qpos, qvel, ctrl, xfrc = util.random_states(m, nw, seed=5)
+  sim = _sim(nw, SimulationCfg(nconmax=35, njmax=300, mujoco=MujocoCfg(timestep=0.005, solver="cg", iterations=100, ls_iterations=50)), m)
+  f = lambda a: torch.as_tensor(a, dtype=torch.float32, device=DEV)  # noqa: E731
+  sim.data.qpos[:], sim.data.qvel[:], sim.data.ctrl[:] = f(qpos), f(qvel), f(ctrl)
+  sim.forward()
+  ds = util.oracle_rollout(sim.mj_model, qpos, qvel, ctrl, xfrc, 1, 35, 300, integrate_last=False)
+  assert sim.mj_model.opt_solver == 1
+  for w, d in enumerate(ds):
+    assert int(sim.data.nefc[w]) == d.nefc
+    q = sim.data.qacc[w].cpu().numpy()
+    assert np.abs(q - d.qacc).max() < 2e-3 * max(1.0, np.abs(d.qacc).max()), w
+  assert int(sim.data.solver_niter.max()) > 3
 
 
 def test_sim_reset_restores_initial_state():
