@@ -100,7 +100,8 @@ static __host__ __device__ inline int solve_slot(int p, int n, int cap) {
 // are still iterating - so the sensor stage fills the solver's tail instead of following it.  A claimed entry is waited
 // for only when all earlier-finished worlds are already taken, i.e. at the very end of the launch.  All CTAs are resident
 // (grid <= SMs x occupancy), so every claimed entry is eventually produced.
-__global__ void __launch_bounds__(B2_WPB * 32, B2_SOLVE_MINB) k_solve(const KModel m, const KData d, const SolveSmem L, const PostSmem LP, int post_mode, const unsigned char* mask, const int* gate, int w0, int w1) {
+template <bool CG>
+__global__ void __launch_bounds__(B2_WPB * 32, B2_SOLVE_MINB) k_solve_t(const KModel m, const KData d, const SolveSmem L, const PostSmem LP, int post_mode, const unsigned char* mask, const int* gate, int w0, int w1) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   real* smem = reinterpret_cast<real*>(smem_raw);
   // [fixed part of world 0 | ... | fixed part of world B2_WPB-1 | row arena | arena control word]
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(B2_WPB * 32, B2_SOLVE_MINB) k_solve(const KMod
 #ifdef B2_TIMING
       unsigned long long t0 = b2_gtime();
 #endif
-      solve_world(m, d, L, w, smem + (size_t)warp * L.fixed_total, arena, actl);
+      solve_world_t<CG>(m, d, L, w, smem + (size_t)warp * L.fixed_total, arena, actl);
       __syncwarp();
 #ifdef B2_TIMING
       if (lane == 0 && w < 16384) { g_tim[3 * w] = t0; g_tim[3 * w + 1] = b2_gtime(); g_tim[3 * w + 2] = b2_smid(); }
@@ -160,6 +161,15 @@ __global__ void __launch_bounds__(B2_WPB * 32, B2_SOLVE_MINB) k_solve(const KMod
     post_world(m, d, LP, w, psm, post_mode == 2);
     __syncwarp();
   }
+}
+
+// the two instantiations under the names the profiles use: k_solve (Newton, the shipped configuration) and k_solve_cg
+#define k_solve k_solve_t<false>
+#define k_solve_cg k_solve_t<true>
+static void launch_solve(bool cg, int grid, size_t smem, cudaStream_t st, const KModel& km, const KData& kd, const SolveSmem& lv, const PostSmem& lp,
+                         int post_mode, const unsigned char* mask, const int* gate, int w0, int w1) {
+  if (cg) k_solve_cg<<<grid, B2_WPB * 32, smem, st>>>(km, kd, lv, lp, post_mode, mask, gate, w0, w1);
+  else k_solve<<<grid, B2_WPB * 32, smem, st>>>(km, kd, lv, lp, post_mode, mask, gate, w0, w1);
 }
 
 // Counting sort of the worlds by predicted solver cost, heaviest first (one CTA).  Which solver slot a world lands in has no
@@ -333,7 +343,7 @@ static int g_nplans = 0;
 static PlanKey plan_key(const b2_model* m, const b2_data* d) {
   int dev = -1;
   cudaGetDevice(&dev);
-  PlanKey k = {{m->nq, m->nv, m->nu, m->nbody, m->njnt, m->nlimited, m->maxchain, d->nconmax, d->njmax, dev, 0, 0}};
+  PlanKey k = {{m->nq, m->nv, m->nu, m->nbody, m->njnt, m->nlimited, m->maxchain, d->nconmax, d->njmax, dev, m->solver, 0}};
   return k;
 }
 
@@ -388,12 +398,15 @@ int b2_check(const b2_model* m, const b2_data* d) {
   if (e != cudaSuccess) return fail("cudaFuncSetAttribute(k_smooth): %s", cudaGetErrorString(e));
   e = cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_solve);
   if (e != cudaSuccess) return fail("cudaFuncSetAttribute(k_solve): %s", cudaGetErrorString(e));
+  e = cudaFuncSetAttribute(k_solve_cg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_solve);
+  if (e != cudaSuccess) return fail("cudaFuncSetAttribute(k_solve_cg): %s", cudaGetErrorString(e));
   e = cudaFuncSetAttribute(k_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_post);
   if (e != cudaSuccess) return fail("cudaFuncSetAttribute(k_post): %s", cudaGetErrorString(e));
   // The solver grid must be fully resident (its warps wait on each other's results in the fused sensor stage): size it
   // from what the occupancy calculator grants on THIS device, not from a compiled-in SM count.
   int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve, B2_WPB * 32, p.smem_solve);
+  e = m->solver == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_cg, B2_WPB * 32, p.smem_solve)
+                     : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve, B2_WPB * 32, p.smem_solve);
   if (e != cudaSuccess || per_sm < 1 || nsm < 1) return fail("k_solve does not fit on an SM (%s)", cudaGetErrorString(e));
   p.solve_cap = per_sm * nsm;
   pe->checked = true;
@@ -416,11 +429,12 @@ static void launch_range(const Plan& p, const KModel& km, const KData& kd, cudaS
   int n = w1 - w0;
   k_smooth<<<(n + B2_SMOOTH_WPB - 1) / B2_SMOOTH_WPB, B2_SMOOTH_WPB * 32, p.smem_smooth, st>>>(km, kd, p.ls, B2_NCAND_MAX, mask, gate, w0, w1);
   k_order<<<1, 1024, 0, st>>>(kd, w0, w1, p.solve_cap, p.order_mode);
+  const bool cg = km.solver == 1;
   if (p.fuse_post) {
-    k_solve<<<solve_grid(n, p.solve_cap), B2_WPB * 32, p.smem_solve, st>>>(km, kd, p.lv, p.lp, do_integrate ? 2 : 1, mask, gate, w0, w1);
+    launch_solve(cg, solve_grid(n, p.solve_cap), p.smem_solve, st, km, kd, p.lv, p.lp, do_integrate ? 2 : 1, mask, gate, w0, w1);
     g_launches += 3;
   } else {
-    k_solve<<<solve_grid(n, p.solve_cap), B2_WPB * 32, p.smem_solve, st>>>(km, kd, p.lv, p.lp, 0, mask, gate, w0, w1);
+    launch_solve(cg, solve_grid(n, p.solve_cap), p.smem_solve, st, km, kd, p.lv, p.lp, 0, mask, gate, w0, w1);
     k_post<<<(n + B2_POST_WPB - 1) / B2_POST_WPB, B2_POST_WPB * 32, p.smem_post, st>>>(km, kd, p.lp, do_integrate, mask, gate, w0, w1);
     g_launches += 4;
   }
@@ -529,9 +543,9 @@ int b2_stage(const b2_model* m, b2_data* d, int stage, int do_integrate, void* s
     k_order<<<1, 1024, 0, st>>>(kd, 0, d->nworld, p.solve_cap, p.order_mode);
     g_launches += 1;
   }
-  else if (stage == 1) k_solve<<<solve_grid(d->nworld, p.solve_cap), B2_WPB * 32, p.smem_solve, st>>>(km, kd, p.lv, p.lp, 0, nullptr, nullptr, 0, d->nworld);
+  else if (stage == 1) launch_solve(km.solver == 1, solve_grid(d->nworld, p.solve_cap), p.smem_solve, st, km, kd, p.lv, p.lp, 0, nullptr, nullptr, 0, d->nworld);
   else if (stage == 2) k_post<<<(d->nworld + B2_POST_WPB - 1) / B2_POST_WPB, B2_POST_WPB * 32, p.smem_post, st>>>(km, kd, p.lp, do_integrate, nullptr, nullptr, 0, d->nworld);
-  else if (stage == 3) k_solve<<<solve_grid(d->nworld, p.solve_cap), B2_WPB * 32, p.smem_solve, st>>>(km, kd, p.lv, p.lp, do_integrate ? 2 : 1, nullptr, nullptr, 0, d->nworld);
+  else if (stage == 3) launch_solve(km.solver == 1, solve_grid(d->nworld, p.solve_cap), p.smem_solve, st, km, kd, p.lv, p.lp, do_integrate ? 2 : 1, nullptr, nullptr, 0, d->nworld);
   else if (stage == 4) k_smooth<<<(d->nworld + B2_SMOOTH_WPB - 1) / B2_SMOOTH_WPB, B2_SMOOTH_WPB * 32, p.smem_smooth, st>>>(km, kd, p.ls, B2_NCAND_MAX, nullptr, nullptr, 0, d->nworld);
   else if (stage == 5) k_order<<<1, 1024, 0, st>>>(kd, 0, d->nworld, p.solve_cap, p.order_mode);
   else return fail("unknown stage %d", stage);

@@ -16,6 +16,10 @@ from collections import defaultdict
 from pathlib import Path
 
 
+# template instantiations known under a plain name (b2_api.cu: k_solve = k_solve_t<false>, k_solve_cg = k_solve_t<true>)
+MANGLED = {"k_solve": "_Z9k_solve_tILb0EE", "k_solve_cg": "_Z9k_solve_tILb1EE"}
+
+
 def line_table(so: str, kernel: str):
   with tempfile.TemporaryDirectory() as td:
     subprocess.run(["cuobjdump", "-xelf", "all", str(Path(so).resolve())], cwd=td, check=True, capture_output=True)
@@ -24,7 +28,7 @@ def line_table(so: str, kernel: str):
   out, cur, inside = [], ("?", 0), False
   for ln in txt.splitlines():
     if ln.startswith("\t.section"):
-      inside = (".text." in ln) and (f"_Z{len(kernel)}{kernel}" in ln)   # exact (Itanium-mangled) function name
+      inside = (".text." in ln) and (MANGLED.get(kernel, f"_Z{len(kernel)}{kernel}") in ln)   # exact (Itanium-mangled) function name
       continue
     if not inside:
       continue
