@@ -35,9 +35,9 @@ sys.path.insert(0, str(ROOT))
 
 DECIMATION = 4
 NUM_ENVS = 4096
-# DRAM bytes per launch from the committed ncu captures of this workload (profiles/r01z_k_solve_final.txt,
-# r01e_k_smooth.txt, r01e_k_post.txt)
-NCU_TRAFFIC_BYTES = {"k_solve": 38_369_280 + 515_584, "k_smooth": 12_324_096 + 32_529_664, "k_post": 52_356_608 + 761_600}
+# DRAM bytes per launch from the committed ncu captures of this workload (profiles/r02_final_k_solve.txt,
+# r02_final_k_smooth.txt, r02_final_k_post.txt)
+NCU_TRAFFIC_BYTES = {"k_solve": 38_247_168 + 627_200, "k_smooth": 11_950_848 + 29_646_336, "k_post": 52_210_944 + 724_992}
 
 
 def parse():
@@ -502,7 +502,7 @@ def run_b200(args):
     roof = {
       "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
       "traffic": NCU_TRAFFIC_BYTES.get(dom) if (args.model == "g1_flat" and nw == NUM_ENVS) else None,
-      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, profiles/r01z_k_solve_final.txt",
+      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, profiles/r02_final_k_{solve,smooth,post}.txt",
       "peak_source": "measured burst (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback (B200_PROFILING.md)",
       "algorithmic_bytes_per_world": {"k_smooth": b_smooth, "k_solve": b_solve, "env_step": b_env},
       "avg_launch_ms": avg, "ms_per_env_step_by_kernel": per_step,
