@@ -194,7 +194,8 @@ int b2_env_action(const b2_model* m, b2_data* d, const b2_env* e, void* stream);
 int b2_env_airtime(const b2_model* m, b2_data* d, const b2_env* e, void* stream);
 
 /* decimation x [sim.step(); scene.update(dt)] (manager_based_rl_env.py:276-283): nsub physics steps, each followed by the
- * air-time update, chunked over side streams like b2_substeps. */
+ * air-time update, chunked over side streams like b2_substeps.  The first sub-step reuses the preceding forward pass's
+ * position / velocity stage per world where the state is untouched (b2_substeps_after_forward, b200sim.h). */
 int b2_env_substeps(const b2_model* m, b2_data* d, const b2_env* e, int nsub, void* stream);
 
 /* episode counters, terminations, rewards, then the reset of every done env (sim reset, reset events, manager

@@ -190,6 +190,8 @@ enum b2_df {
   B2_DF_EFC_POS,         /* njmax */
   B2_DF_EFC_MARGIN,      /* njmax */
   B2_DF_EFC_FORCE,       /* njmax */
+  B2_DF_MEMO_QPOS,       /* nq: the qpos the position / velocity stage outputs of this world were computed from; internal */
+  B2_DF_MEMO_QVEL,       /* nv: likewise for qvel; internal */
   B2_DF_COUNT
 };
 
@@ -212,6 +214,7 @@ enum b2_di {
                               warps that find the solver queue empty take the sensor / integration stage of finished worlds
                               from here instead of idling through the launch's tail; internal */
   B2_DI_SOLVE_CTR,         /* 4: row w0 = {worlds solved, next ring entry to post-process, -, -} of that launch; internal */
+  B2_DI_SMOOTH_MEMO,       /* 1: 1 = MEMO_QPOS / MEMO_QVEL describe the stage outputs in HBM; write 0 after changing MODEL fields; internal */
   B2_DI_COUNT
 };
 
@@ -267,10 +270,20 @@ int b2_forward(const b2_model* m, b2_data* d, void* stream);
  * edges under stream capture); results are identical for any N. */
 int b2_substeps(const b2_model* m, b2_data* d, int nsub, void* stream);
 
+/* b2_substeps for the caller that knows a b2_forward came last (ManagerBasedRlEnv.step: the forward pass after the resets,
+ * manager_based_rl_env.py:306-311, then the next step's decimation loop, :275-280).  Each world whose qpos / qvel are still
+ * bit for bit those of that pass (B2_DF_MEMO_QPOS / _QVEL; B2_DI_SMOOTH_MEMO == 1; no external wrench, no mocap body) skips
+ * the position / velocity stage of the FIRST sub-step - kinematics, mass matrix, collision, bias forces are in HBM already -
+ * and only redoes what depends on ctrl (actuator forces, qfrc_smooth, qacc_smooth) through the same instructions, so results
+ * are bit-identical to b2_substeps.  MODEL fields edited in between are not seen by that comparison: zero
+ * B2_DI_SMOOTH_MEMO after such an edit (Simulation.invalidate_memo()).  B200SIM_MEMO=0 turns the reuse off. */
+int b2_substeps_after_forward(const b2_model* m, b2_data* d, int nsub, void* stream);
+
 /* One stage of b2_step on its own: 0 = k_smooth (position / velocity stage) + k_order (solver schedule), 1 = k_solve
  * (constraint rows + Newton solver), 2 = k_post (sensors, and integration when do_integrate != 0).  b2_step == stages 0, 1, 2
  * with do_integrate = 1; b2_forward the same with do_integrate = 0.  4 = k_smooth alone, 5 = k_order alone (0 == 4 then 5);
- * 3 = k_solve with the sensor stage fused into its tail (experiment).  Used by bench.py to bracket each kernel with CUDA
+ * 3 = k_solve with the sensor stage fused into its tail (experiment); 6 = k_smooth the way b2_substeps_after_forward launches
+ * its first sub-step.  Used by bench.py to bracket each kernel with CUDA
  * events and by stage-wise tests. */
 int b2_stage(const b2_model* m, b2_data* d, int stage, int do_integrate, void* stream);
 

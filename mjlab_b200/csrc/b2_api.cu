@@ -45,7 +45,7 @@ static int fail(const char* fmt, ...) {
   return 1;
 }
 
-__global__ void __launch_bounds__(B2_SMOOTH_WPB * 32) k_smooth(const KModel m, const KData d, const SmoothSmem L, int ncand_max, const unsigned char* mask, const int* gate, int w0, int w1) {
+__global__ void __launch_bounds__(B2_SMOOTH_WPB * 32) k_smooth(const KModel m, const KData d, const SmoothSmem L, int ncand_max, int memo_consume, const unsigned char* mask, const int* gate, int w0, int w1) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   real* smem = reinterpret_cast<real*>(smem_raw);
   int warp = threadIdx.x >> 5;
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(B2_SMOOTH_WPB * 32) k_smooth(const KModel m, c
   if (w >= w1) return;
   if (gate && *gate == 0) return;
   if (mask && !mask[w]) return;
-  smooth_world(m, d, L, ncand_max, w, smem + (size_t)warp * L.total);
+  smooth_world(m, d, L, ncand_max, w, smem + (size_t)warp * L.total, memo_consume);
 }
 
 #ifdef B2_TIMING
@@ -276,6 +276,7 @@ struct Plan {
   size_t smem_smooth, smem_solve, smem_post;
   int solve_cap;    // resident solver CTAs on this device: SMs x CTAs per SM granted by the occupancy calculator
   int order_mode;   // sort key of k_order (see order_key)
+  int memo;         // the env step's first sub-step reuses the preceding forward pass's position / velocity stage (B200SIM_MEMO, default on)
   int fuse_post;    // run the sensor / integration stage inside k_solve's tail (experiment, default off: see k_solve)
   int chunks, chunk_min;
 };
@@ -328,6 +329,7 @@ static int make_plan(const b2_model* m, const b2_data* d, Plan* p) {
   p->solve_cap = B2_SOLVE_DEFAULT_CTAS;
   p->order_mode = env_int("B200SIM_ORDER_MODE", B2_ORDER_MODE_DEFAULT);
   p->fuse_post = env_int("B200SIM_FUSE_POST", 0);
+  p->memo = env_int("B200SIM_MEMO", 1);
   p->chunks = env_int("B200SIM_CHUNKS", 1);
   p->chunk_min = env_int("B200SIM_CHUNK_MIN", 512);
   return 0;
@@ -425,9 +427,9 @@ static const Plan* get_plan(const b2_model* m, const b2_data* d) {
 // One physics step (do_integrate) or forward pass for the worlds [w0, w1) on stream st: four launches (kinematics ...
 // qacc_smooth; the solver order; constraint rows + Newton solver; sensors + integration).
 static void launch_range(const Plan& p, const KModel& km, const KData& kd, cudaStream_t st, int do_integrate, const unsigned char* mask,
-                         const int* gate, int w0, int w1) {
+                         const int* gate, int w0, int w1, int memo_consume = 0) {
   int n = w1 - w0;
-  k_smooth<<<(n + B2_SMOOTH_WPB - 1) / B2_SMOOTH_WPB, B2_SMOOTH_WPB * 32, p.smem_smooth, st>>>(km, kd, p.ls, B2_NCAND_MAX, mask, gate, w0, w1);
+  k_smooth<<<(n + B2_SMOOTH_WPB - 1) / B2_SMOOTH_WPB, B2_SMOOTH_WPB * 32, p.smem_smooth, st>>>(km, kd, p.ls, B2_NCAND_MAX, memo_consume, mask, gate, w0, w1);
   k_order<<<1, 1024, 0, st>>>(kd, w0, w1, p.solve_cap, p.order_mode);
   const bool cg = km.solver == 1;
   if (p.fuse_post) {
@@ -492,8 +494,9 @@ static ChunkStreams* chunk_streams(int want) {
 typedef void (*chunk_hook)(const void* ctx, cudaStream_t st, int w0, int w1);
 
 // nsub x [physics step or forward; hook] for every world, chunk chains on side streams forked from / joined to `stream`.
+// memo_first: the first of the nsub passes may reuse the stage outputs a preceding pass left in HBM (see smooth_world).
 static int run_chunked(const b2_model* m, b2_data* d, void* stream, int nsub, int do_integrate, const unsigned char* mask, const int* gate,
-                       chunk_hook hook, const void* hook_ctx) {
+                       chunk_hook hook, const void* hook_ctx, int memo_first = 0) {
   const Plan* pp = get_plan(m, d);
   if (!pp) return 1;
   const Plan& p = *pp;
@@ -504,7 +507,7 @@ static int run_chunked(const b2_model* m, b2_data* d, void* stream, int nsub, in
   ChunkStreams* cs = nc > 1 ? chunk_streams(nc) : nullptr;
   if (!cs) {
     for (int s = 0; s < nsub; ++s) {
-      launch_range(p, km, kd, main_st, do_integrate, mask, gate, 0, d->nworld);
+      launch_range(p, km, kd, main_st, do_integrate, mask, gate, 0, d->nworld, memo_first && p.memo && s == 0);
       if (hook) hook(hook_ctx, main_st, 0, d->nworld);
     }
   } else {
@@ -517,7 +520,7 @@ static int run_chunked(const b2_model* m, b2_data* d, void* stream, int nsub, in
       cudaStream_t st = cs->side[c];
       if (cudaStreamWaitEvent(st, cs->fork, 0) != cudaSuccess) return fail("stream wait: %s", cudaGetErrorString(cudaGetLastError()));
       for (int s = 0; s < nsub; ++s) {
-        launch_range(p, km, kd, st, do_integrate, mask, gate, w0, w1);
+        launch_range(p, km, kd, st, do_integrate, mask, gate, w0, w1, memo_first && p.memo && s == 0);
         if (hook) hook(hook_ctx, st, w0, w1);
       }
       if (cudaEventRecord(cs->join[c], st) != cudaSuccess) return fail("event record: %s", cudaGetErrorString(cudaGetLastError()));
@@ -530,7 +533,8 @@ static int run_chunked(const b2_model* m, b2_data* d, void* stream, int nsub, in
 }
 
 // Stages on their own (bench.py brackets each with CUDA events, stage-wise tests): 0 = k_smooth + k_order, 1 = k_solve,
-// 2 = k_post, 3 = k_solve with the fused sensor / integration stage (experiment), 4 = k_smooth alone, 5 = k_order alone.
+// 2 = k_post, 3 = k_solve with the fused sensor / integration stage (experiment), 4 = k_smooth alone, 5 = k_order alone,
+// 6 = k_smooth as the first sub-step after a forward pass launches it (b2_substeps_after_forward).
 int b2_stage(const b2_model* m, b2_data* d, int stage, int do_integrate, void* stream) {
   const Plan* pp = get_plan(m, d);
   if (!pp) return 1;
@@ -539,14 +543,15 @@ int b2_stage(const b2_model* m, b2_data* d, int stage, int do_integrate, void* s
   const KModel& km = *reinterpret_cast<const KModel*>(m);
   const KData& kd = *reinterpret_cast<const KData*>(d);
   if (stage == 0) {
-    k_smooth<<<(d->nworld + B2_SMOOTH_WPB - 1) / B2_SMOOTH_WPB, B2_SMOOTH_WPB * 32, p.smem_smooth, st>>>(km, kd, p.ls, B2_NCAND_MAX, nullptr, nullptr, 0, d->nworld);
+    k_smooth<<<(d->nworld + B2_SMOOTH_WPB - 1) / B2_SMOOTH_WPB, B2_SMOOTH_WPB * 32, p.smem_smooth, st>>>(km, kd, p.ls, B2_NCAND_MAX, 0, nullptr, nullptr, 0, d->nworld);
     k_order<<<1, 1024, 0, st>>>(kd, 0, d->nworld, p.solve_cap, p.order_mode);
     g_launches += 1;
   }
   else if (stage == 1) launch_solve(km.solver == 1, solve_grid(d->nworld, p.solve_cap), p.smem_solve, st, km, kd, p.lv, p.lp, 0, nullptr, nullptr, 0, d->nworld);
   else if (stage == 2) k_post<<<(d->nworld + B2_POST_WPB - 1) / B2_POST_WPB, B2_POST_WPB * 32, p.smem_post, st>>>(km, kd, p.lp, do_integrate, nullptr, nullptr, 0, d->nworld);
   else if (stage == 3) launch_solve(km.solver == 1, solve_grid(d->nworld, p.solve_cap), p.smem_solve, st, km, kd, p.lv, p.lp, do_integrate ? 2 : 1, nullptr, nullptr, 0, d->nworld);
-  else if (stage == 4) k_smooth<<<(d->nworld + B2_SMOOTH_WPB - 1) / B2_SMOOTH_WPB, B2_SMOOTH_WPB * 32, p.smem_smooth, st>>>(km, kd, p.ls, B2_NCAND_MAX, nullptr, nullptr, 0, d->nworld);
+  else if (stage == 4) k_smooth<<<(d->nworld + B2_SMOOTH_WPB - 1) / B2_SMOOTH_WPB, B2_SMOOTH_WPB * 32, p.smem_smooth, st>>>(km, kd, p.ls, B2_NCAND_MAX, 0, nullptr, nullptr, 0, d->nworld);
+  else if (stage == 6) k_smooth<<<(d->nworld + B2_SMOOTH_WPB - 1) / B2_SMOOTH_WPB, B2_SMOOTH_WPB * 32, p.smem_smooth, st>>>(km, kd, p.ls, B2_NCAND_MAX, p.memo, nullptr, nullptr, 0, d->nworld);
   else if (stage == 5) k_order<<<1, 1024, 0, st>>>(kd, 0, d->nworld, p.solve_cap, p.order_mode);
   else return fail("unknown stage %d", stage);
   g_launches += 1;
@@ -599,6 +604,11 @@ int b2_forward_masked(const b2_model* m, b2_data* d, const unsigned char* mask, 
 int b2_substeps(const b2_model* m, b2_data* d, int nsub, void* stream) {
   if (nsub < 0) return fail("nsub must be >= 0");
   return run_chunked(m, d, stream, nsub, 1, nullptr, nullptr, nullptr, nullptr);
+}
+
+int b2_substeps_after_forward(const b2_model* m, b2_data* d, int nsub, void* stream) {
+  if (nsub < 0) return fail("nsub must be >= 0");
+  return run_chunked(m, d, stream, nsub, 1, nullptr, nullptr, nullptr, nullptr, 1);
 }
 
 }  // extern "C"

@@ -15,6 +15,7 @@
 
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #ifndef B2_REAL
 #define B2_REAL float
@@ -103,6 +104,7 @@ B2_DEV real b2_rsqrt(real x) { return rsqrtf(x); }
 #endif
 
 #define B2_MINVAL ((real)1e-15)
+#define B2_QUAT_UNIT_TOL ((real)(sizeof(real) == 4 ? 9.5e-7 : 1.8e-15))   // 8 ulp of 1: a normalised quaternion's computed norm is within ~3
 #define B2_MINIMP ((real)0.0001)
 #define B2_MAXIMP ((real)0.9999)
 
@@ -144,6 +146,11 @@ struct KData {
 // ---------------------------------------------------------------------------
 // small vector / quaternion math (row-major 3x3)
 // ---------------------------------------------------------------------------
+// bit-for-bit equality (a copied NaN equals itself, -0 and +0 differ)
+B2_DEV bool b2_same_bits(real a, real b) {
+  if (sizeof(real) == 4) { unsigned x, y; memcpy(&x, &a, 4); memcpy(&y, &b, 4); return x == y; }
+  unsigned long long x = 0, y = 0; memcpy(&x, &a, sizeof(real)); memcpy(&y, &b, sizeof(real)); return x == y;
+}
 B2_DEV real dot3(const real* a, const real* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }  // @region vecmath
 B2_DEV void cross3(real* r, const real* a, const real* b) {
   real x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
@@ -159,6 +166,10 @@ B2_DEV void quat_mul(real* r, const real* a, const real* b) {
 B2_DEV void quat_normalize(real* q) {
   real n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
   if (n < B2_MINVAL) { q[0] = 1; q[1] = q[2] = q[3] = 0; return; }
+  // MuJoCo rescales only when the norm is off by more than its rounding noise (mju_normalize4: |norm - 1| > mjMINVAL in
+  // double).  The float analogue matters here: an unconditional rescale is NOT idempotent in float (about one unit
+  // quaternion in six flips between two neighbours for ever), which would change qpos on every pass over an unchanged state.
+  if (fabs(n - (real)1) <= B2_QUAT_UNIT_TOL) return;
   real s = (real)1 / n;
   q[0] *= s; q[1] *= s; q[2] *= s; q[3] *= s;
 }

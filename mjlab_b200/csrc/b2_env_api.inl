@@ -189,7 +189,7 @@ static void airtime_hook(const void* ctx, cudaStream_t st, int w0, int w1) {
 int b2_env_substeps(const b2_model* m, b2_data* d, const b2_env* e, int nsub, void* stream) {
   if (nsub < 0) return fail("nsub must be >= 0");
   AirtimeCtx c{reinterpret_cast<const KModel*>(m), reinterpret_cast<const KData*>(d), reinterpret_cast<const KEnv*>(e)};
-  return run_chunked(m, d, stream, nsub, 1, nullptr, nullptr, airtime_hook, &c);
+  return run_chunked(m, d, stream, nsub, 1, nullptr, nullptr, airtime_hook, &c, 1);
 }
 
 int b2_env_obs(const b2_model* m, b2_data* d, const b2_env* e, int with_update, void* stream) {

@@ -486,7 +486,13 @@ __device__ unsigned long long g_sphase[8 * 16384];
 // ---------------------------------------------------------------------------
 // Stage 1 for world w.  sm: this warp's shared-memory slab.
 // ---------------------------------------------------------------------------
-B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, int ncand_max, int w, real* sm) {  // @region setup
+#ifdef B2_HOSTEMU
+static long long b2h_memo_hits = 0;
+#endif
+// memo_consume: reuse this world's position / velocity stage outputs in HBM when its state is bit for bit the one they were
+// computed from (the env step's first sub-step after the forward pass that follows the resets): only the ctrl-dependent
+// tail (actuator forces, qfrc_smooth, qacc_smooth) is redone, through the very same instructions as in the full pass.
+B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, int ncand_max, int w, real* sm, int memo_consume = 0) {  // @region setup
   B2_SPH_BEGIN()
   const int nq = m.nq, nv = m.nv, nu = m.nu, nb = m.nbody, nj = m.njnt;
   real* qpos = sm + L.qpos; real* qvel = sm + L.qvel;
@@ -533,7 +539,35 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
     for (int i = B2_LANE; i < 6 * nb; i += B2_NLANE) anyx_lane |= (xf[i] != 0);
   }
   B2_WSYNC();
+  const int ld = b2_ld(nv);
+  bool light = false;
+  {
+    real* memo_q = d.df[B2_DF_MEMO_QPOS] + (size_t)w * nq;
+    real* memo_v = d.df[B2_DF_MEMO_QVEL] + (size_t)w * nv;
+    const int* memo_ok = d.di[B2_DI_SMOOTH_MEMO] + w;
+    if (memo_consume && m.nmocap == 0 && *memo_ok == 1) {
+      int diff = anyx_lane;   // an external wrench needs the kinematic quantities: full pass
+      B2_UNROLL1
+      for (int i = B2_LANE; i < nq; i += B2_NLANE) diff |= !b2_same_bits(qpos[i], memo_q[i]);
+      B2_UNROLL1
+      for (int i = B2_LANE; i < nv; i += B2_NLANE) diff |= !b2_same_bits(qvel[i], memo_v[i]);
+      // the plain pass would normalise the free joints' quaternions inside qpos again: only a fixed point may skip it
+      B2_UNROLL1
+      for (int j = B2_LANE; j < nj; j += B2_NLANE) {
+        if (jnt_type[j] != B2_JNT_FREE) continue;
+        const real* q0 = qpos + jnt_qposadr[j] + 3;
+        real q[4] = {q0[0], q0[1], q0[2], q0[3]};
+        quat_normalize(q);
+        diff |= !(b2_same_bits(q[0], q0[0]) && b2_same_bits(q[1], q0[1]) && b2_same_bits(q[2], q0[2]) && b2_same_bits(q[3], q0[3]));
+      }
+      light = !b2_wor_i(diff);
+#ifdef B2_HOSTEMU
+      b2h_memo_hits += light;   // test harness statistic
+#endif
+    }
+  }
 
+  if (!light) {   // ======== position / velocity stage (skipped when the memo holds) ========
   // ---- kinematics, level by level ------------------------------------------  // @region kinematics
   const real* qpos0 = MF(B2_MF_QPOS0);
   const real* body_pos = MF(B2_MF_BODY_POS);
@@ -628,6 +662,16 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
     g = d.df[B2_DF_XIPOS] + (size_t)w * nb * 3;  for (int i = B2_LANE; i < 3 * nb; i += B2_NLANE) g[i] = xipos[i];
     g = d.df[B2_DF_XANCHOR] + (size_t)w * nj * 3; for (int i = B2_LANE; i < 3 * nj; i += B2_NLANE) g[i] = xanchor[i];
     g = d.df[B2_DF_XAXIS] + (size_t)w * nj * 3;  for (int i = B2_LANE; i < 3 * nj; i += B2_NLANE) g[i] = xaxis[i];
+  }
+  // the state this pass describes (after the in-place quaternion normalisation above): key of the memo
+  {
+    real* memo_q = d.df[B2_DF_MEMO_QPOS] + (size_t)w * nq;
+    real* memo_v = d.df[B2_DF_MEMO_QVEL] + (size_t)w * nv;
+    B2_UNROLL1
+    for (int i = B2_LANE; i < nq; i += B2_NLANE) memo_q[i] = qpos[i];
+    B2_UNROLL1
+    for (int i = B2_LANE; i < nv; i += B2_NLANE) memo_v[i] = qvel[i];
+    if (B2_LANE == 0) d.di[B2_DI_SMOOTH_MEMO][w] = 1;
   }
   // geom and site poses straight to HBM
   {
@@ -771,7 +815,6 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
     }
     B2_WSYNC();
   }
-  const int ld = b2_ld(nv);
   B2_UNROLL1
   for (int i = B2_LANE; i < nv * ld; i += B2_NLANE) M[i] = 0;
   B2_WSYNC();
@@ -1060,6 +1103,7 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
     for (int i = B2_LANE; i < 6 * nv; i += B2_NLANE) g[i] = cdofdot[i];
   }
 
+  }   // !light
   // ---- actuation ------------------------------------------------------------------  // @region actuation
   {
     const int* trnid = MI(B2_MI_ACTUATOR_TRNID);
@@ -1094,6 +1138,7 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
 
   B2_SPH(4)
   // ---- RNE bias (cacc aliases crb) -----------------------------------------------------  // @region rne
+  if (!light) {
   const real* grav = MF(B2_MF_OPT_GRAVITY);
   B2_UNROLL1
   for (int lev = 0; lev < m.nlevel; ++lev) {
@@ -1135,6 +1180,12 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
     }
     B2_WSYNC();
   }
+  } else {   // memo: the mass matrix of this state is in HBM
+    const real* g = d.df[B2_DF_QM] + (size_t)w * nv * ld;
+    B2_UNROLL1
+    for (int i = B2_LANE; i < nv * ld; i += B2_NLANE) M[i] = g[i];
+    B2_WSYNC();
+  }
 
   B2_SPH(5)
   // ---- passive + actuator + applied forces -> qfrc_smooth ------------------------------  // @region qfrc_smooth
@@ -1159,7 +1210,9 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
     for (int i = B2_LANE; i < nv; i += B2_NLANE) {
       const real* ci = cdof + 6 * i;
       const real* cf = cfrc + 6 * dof_bodyid[i];
-      real bias = ci[0] * cf[0] + ci[1] * cf[1] + ci[2] * cf[2] + ci[3] * cf[3] + ci[4] * cf[4] + ci[5] * cf[5];
+      real bias;
+      if (light) bias = g_bias[i];
+      else bias = ci[0] * cf[0] + ci[1] * cf[1] + ci[2] * cf[2] + ci[3] * cf[3] + ci[4] * cf[4] + ci[5] * cf[5];
       real pas = -damping[i] * qvel[i];
       int j = dof_jntid[i];
       int jt = jnt_type[j];

@@ -143,6 +143,8 @@ DATA_FLOAT_FIELDS = [
   ("EFC_POS", "efc_pos", lambda m, c, j: (j,)),
   ("EFC_MARGIN", "efc_margin", lambda m, c, j: (j,)),
   ("EFC_FORCE", "efc_force", lambda m, c, j: (j,)),
+  ("MEMO_QPOS", "memo_qpos", lambda m, c, j: (m.nq,)),
+  ("MEMO_QVEL", "memo_qvel", lambda m, c, j: (m.nv,)),
 ]
 
 DATA_INT_FIELDS = [
@@ -159,6 +161,7 @@ DATA_INT_FIELDS = [
   ("SOLVE_NEXT", "solve_next", lambda m, c, j: ()),
   ("SOLVE_RING", "solve_ring", lambda m, c, j: ()),
   ("SOLVE_CTR", "solve_ctr", lambda m, c, j: (4,)),
+  ("SMOOTH_MEMO", "smooth_memo", lambda m, c, j: ()),
 ]
 
 def leading_dim(n: int) -> int:
@@ -343,6 +346,8 @@ def load_library() -> C.CDLL:
     getattr(lib, name).restype = C.c_int
   lib.b2_substeps.argtypes = [C.POINTER(B2Model), C.POINTER(B2Data), C.c_int, C.c_void_p]
   lib.b2_substeps.restype = C.c_int
+  lib.b2_substeps_after_forward.argtypes = [C.POINTER(B2Model), C.POINTER(B2Data), C.c_int, C.c_void_p]
+  lib.b2_substeps_after_forward.restype = C.c_int
   lib.b2_stage.argtypes = [C.POINTER(B2Model), C.POINTER(B2Data), C.c_int, C.c_int, C.c_void_p]
   lib.b2_stage.restype = C.c_int
   lib.b2_reset.argtypes = [C.POINTER(B2Model), C.POINTER(B2Data), C.c_void_p, C.c_void_p]

@@ -477,6 +477,7 @@ class ManagerBasedRlEnv:
     if action.shape[-1] != self.vcfg.nj:
       raise ValueError(f"Invalid action shape, expected: {self.vcfg.nj}, received: {action.shape[-1]}.")
     self._buf["action_in"].copy_(action, non_blocking=True)
+    self.sim.flush_memo()
     if self.sim.nan_guard.enabled:
       self._step_guarded()
     elif self._graph is not None:

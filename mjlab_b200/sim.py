@@ -85,11 +85,15 @@ class WarpBridge:
   Attributes are the engine's own device buffers as `torch.Tensor`s (stable addresses for the process lifetime); assigning an
   attribute raises, in-place writes (`bridge.qpos[:] = x`, index assignment) go straight to the buffer the kernels read."""
 
-  def __init__(self, fields: dict[str, Any]) -> None:
+  def __init__(self, fields: dict[str, Any], on_access: Any = None) -> None:
     object.__setattr__(self, "_fields", fields)
+    object.__setattr__(self, "_on_access", on_access)
 
   def __getattr__(self, name: str) -> Any:
     try:
+      cb = object.__getattribute__(self, "_on_access")
+      if cb is not None:
+        cb()
       return object.__getattribute__(self, "_fields")[name]
     except KeyError:
       raise AttributeError(name) from None
@@ -256,7 +260,8 @@ class Simulation:
     # static geoms (terrain): their world pose is written once; the step kernels only update moving geoms
     E.check_call(self._lib, self._lib.b2_init_static(C.byref(self._cm), C.byref(self._cd), self._stream()))
 
-    self._model_bridge = TensorBridge(_ModelFields(self))
+    self._memo_dirty = True
+    self._model_bridge = TensorBridge(_ModelFields(self), on_access=self.invalidate_memo)
     self._data_bridge = TensorBridge(self._data_fields)
     self.nan_guard = NanGuard(cfg.nan_guard, num_envs, model)   # sim.py:162
 
@@ -328,7 +333,21 @@ class Simulation:
 
   @property
   def model(self) -> WarpBridge:
+    # Handing out a model tensor (any attribute access on this bridge) may be followed by an in-place edit the engine cannot
+    # see; the env step's reuse of the forward pass (b2_substeps_after_forward) compares qpos / qvel only, so the bridge
+    # calls invalidate_memo() on every access.
     return self._model_bridge
+
+  def invalidate_memo(self) -> None:
+    """Forget the position / velocity stage a forward pass left behind (needed after MODEL fields were edited through a tensor
+    obtained earlier than the previous env step; `sim.model.<field>` accesses do it by themselves)."""
+    self._memo_dirty = True
+
+  def flush_memo(self) -> None:
+    """Called by the envs before they replay their step graph."""
+    if self._memo_dirty:
+      self._data_fields["smooth_memo"].zero_()
+      self._memo_dirty = False
 
   # the reference exposes the raw mjwarp structs next to the torch bridges (sim.py:193-207); here they are the same objects
   @property

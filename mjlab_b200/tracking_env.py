@@ -201,7 +201,7 @@ class TrackingRlEnv:
     lib, m, d, e, chk = self._lib, C.byref(self.sim._cm), C.byref(self.sim._cd), C.byref(self._ce), E.check_call
     st = self._stream()
     chk(lib, lib.b2_trk_action(m, d, e, st))
-    chk(lib, lib.b2_substeps(m, d, self.cfg.decimation, st))
+    chk(lib, lib.b2_substeps_after_forward(m, d, self.cfg.decimation, st))
     chk(lib, lib.b2_trk_post(m, d, e, st))
     mask = self._buf["reset_buf"].data_ptr() if self.cfg.forward_mode == "masked" else None
     chk(lib, lib.b2_forward_masked(m, d, mask, self._buf["any_reset"].data_ptr(), st))
@@ -255,6 +255,7 @@ class TrackingRlEnv:
     if action.shape[-1] != self.vcfg.nj:
       raise ValueError(f"Invalid action shape, expected: {self.vcfg.nj}, received: {action.shape[-1]}.")
     self._buf["action_in"].copy_(action, non_blocking=True)
+    self.sim.flush_memo()
     if self.sim.nan_guard.enabled:
       raise NotImplementedError("NanGuard on the tracking env: enable it on the velocity env (per-physics-step checks, "
                                 "env.ManagerBasedRlEnv._step_guarded) or step `sim` directly")

@@ -89,8 +89,15 @@ class HostSim:
     self.cm.mf_stride[idx] = row.size
     return big
 
-  def step(self):
+  def step(self, after_forward: bool = False):
+    """after_forward: let the position / velocity stage reuse what the preceding pass left (b2_substeps_after_forward)."""
+    self.lib.b2h_set_memo_consume(int(after_forward))
     self.lib.b2h_run(C.byref(self.cm), C.byref(self.cd), 1, 0, self.nworld)
+    self.lib.b2h_set_memo_consume(0)
+
+  def memo_hits(self) -> int:
+    self.lib.b2h_memo_hit_count.restype = C.c_longlong
+    return int(self.lib.b2h_memo_hit_count())
 
   def forward(self):
     self.lib.b2h_run(C.byref(self.cm), C.byref(self.cd), 0, 0, self.nworld)

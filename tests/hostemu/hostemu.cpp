@@ -26,6 +26,11 @@ int b2h_sizeof_data(void) { return (int)sizeof(KData); }
 static int jpool_budget = 0;
 void b2h_set_jpool_budget(int b) { jpool_budget = b; }
 
+static int memo_consume = 0;
+// 1: b2h_run lets the position / velocity stage reuse what a preceding pass left in the data arrays (smooth_world's memo)
+void b2h_set_memo_consume(int v) { memo_consume = v; }
+long long b2h_memo_hit_count(void) { return b2h_memo_hits; }
+
 int b2h_run(const KModel* m, KData* d, int do_integrate, int world_lo, int world_hi) {
   SmoothSmem ls = smooth_smem_layout(m->nq, m->nv, m->nu, m->nbody, m->njnt, 256);
   int rows_max = 4 * d->nconmax + 2 * m->nlimited;
@@ -40,7 +45,7 @@ int b2h_run(const KModel* m, KData* d, int do_integrate, int world_lo, int world
   std::vector<real> a(ls.total), b(lv.fixed_total), ar(arena + 4), c(lp.total);
   int actl[2] = {0, 0};
   for (int w = world_lo; w < world_hi && w < d->nworld; ++w) {
-    smooth_world(*m, *d, ls, 256, w, a.data());
+    smooth_world(*m, *d, ls, 256, w, a.data(), memo_consume);
     solve_world(*m, *d, lv, w, b.data(), ar.data(), actl);
     post_world(*m, *d, lp, w, c.data(), do_integrate);
   }

@@ -380,3 +380,49 @@ def test_chunked_streams_do_not_change_results():
   for o in outs[1:]:
     for a, b in zip(outs[0], o):
       assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("task", ["velocity", "tracking"])
+def test_forward_pass_reuse_is_bit_identical(task):
+  """The first sub-step of an env step reuses the position / velocity stage of the forward pass that ended the previous step
+  (b2_substeps_after_forward): trajectories with the reuse on (default) and off (B200SIM_MEMO=0) are bit-identical - resets,
+  interval pushes (which touch qvel AFTER the forward pass), domain randomisation at reset and a model edit in between
+  included - and the reuse really is taken."""
+  import os
+  from mjlab_b200.env import ManagerBasedRlEnv, VelocityEnvCfg
+  from mjlab_b200.tracking_env import TrackingEnvCfg, TrackingRlEnv
+  old = os.environ.get("B200SIM_MEMO")
+  outs = []
+  try:
+    for memo in ("0", "1"):
+      os.environ["B200SIM_MEMO"] = memo
+      if task == "velocity":
+        env = ManagerBasedRlEnv(VelocityEnvCfg(robot="g1", num_envs=256, seed=5), DEV)
+      else:
+        env = TrackingRlEnv(TrackingEnvCfg(num_envs=256, seed=5), DEV)
+      env.reset()
+      gen = torch.Generator(device=DEV).manual_seed(3)
+      env.episode_length_buf = torch.randint(0, env.max_episode_length, (256,), device=DEV, generator=gen)
+      trace = []
+      for k in range(40):
+        if k == 20:   # an edit of model fields between two steps: the bridge access drops the memo
+          env.sim.model.geom_friction[:, :, 0] *= 1.0
+        if k % 2:     # every other step ends with a time-out, so with the forward pass (it only runs when some env was reset)
+          env.episode_length_buf[k % 256] = env.max_episode_length
+        obs, rew, term, trunc, _ = env.step(torch.rand(256, env.vcfg.nj, device=DEV, generator=gen) * 2 - 1)
+        trace.append((obs["critic"].clone(), rew.clone(), term.clone(), trunc.clone(), env.sim.data.qpos.clone(), env.sim.data.qvel.clone(),
+                      env.sim.data.qacc.clone(), env.sim.data.ncon.clone(), env.sim.data.sensordata.clone()))
+      outs.append(trace)
+      # the flag / snapshot left behind: after a step every world's stage outputs belong to the state in HBM (forward pass over all
+      # worlds in the reference mode), unless an interval push changed qvel afterwards
+      d = env.sim.data
+      same = (d.memo_qpos == d.qpos).all(1) & (d.memo_qvel == d.qvel).all(1) & (d.smooth_memo == 1)
+      assert float(same.float().mean()) > 0.9
+  finally:
+    if old is None:
+      os.environ.pop("B200SIM_MEMO", None)
+    else:
+      os.environ["B200SIM_MEMO"] = old
+  for k, (a, b) in enumerate(zip(*outs)):
+    for x, y in zip(a, b):
+      assert torch.equal(x, y), (k, float((x.float() - y.float()).abs().max()))
