@@ -45,7 +45,10 @@ static int fail(const char* fmt, ...) {
   return 1;
 }
 
-__global__ void __launch_bounds__(B2_SMOOTH_WPB * 32) k_smooth(const KModel m, const KData d, const SmoothSmem L, int ncand_max, int memo_consume, const unsigned char* mask, const int* gate, int w0, int w1) {
+#ifndef B2_SMOOTH_MINB
+#define B2_SMOOTH_MINB 28   // worlds resident per SM the compiler must allow for (register cap 65536 / (MINB * 32))
+#endif
+__global__ void __launch_bounds__(B2_SMOOTH_WPB * 32, B2_SMOOTH_MINB) k_smooth(const KModel m, const KData d, const SmoothSmem L, int ncand_max, int memo_consume, const unsigned char* mask, const int* gate, int w0, int w1) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   real* smem = reinterpret_cast<real*>(smem_raw);
   int warp = threadIdx.x >> 5;

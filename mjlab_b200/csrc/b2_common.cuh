@@ -251,17 +251,28 @@ B2_DEV real b2_shfl(real x, int src) { return __shfl_sync(0xffffffffu, x, src); 
 // invd[j] <- 1 / L[j][j].  Left-looking over PANELS OF TWO COLUMNS: one pass over a lane's row serves both columns
 // (3 instead of 4 128-bit loads per 8 FMAs, half the per-column overhead); the pivot rows are read in place (their
 // entries k < j are final).  j is even inside the panel loop, so the unaligned tail of the k range is 0 or 2 elements.
-B2_DEVN void chol_factor(real* A, int n, int ld, real* invd, real* x) {  // @region chol_factor
+// Row i of a lower-triangular matrix stored PACKED: rows padded to a multiple of four entries (128-bit row loads stay
+// aligned), row i = 4k + r starts at 4 (k + 1) (2k + r).  k_smooth keeps the mass matrix this way: 684 instead of 1260 words
+// for the G1's 35 dofs, which is what lets an SM hold every world of a 4096-world batch at once (b2_smooth.cuh, layout).
+static inline
+#ifndef B2_HOSTEMU
+__host__ __device__
+#endif
+int b2_poff(int i) { const int k = i >> 2, r = i & 3; return 4 * (k + 1) * (2 * k + r); }
+#define B2_MROW(A, i) (PACKED ? (A) + b2_poff(i) : (A) + (i) * ld)
+
+template <bool PACKED>
+B2_DEVN void chol_factor_t(real* A, int n, int ld, real* invd, real* x) {  // @region chol_factor
   const int nrows = x ? n + 1 : n;
 #ifdef B2_HOSTEMU
   for (int j = 0; j < n; ++j) {
-    const real* rj = A + j * ld;
+    const real* rj = B2_MROW(A, j);
     real piv = rj[j];
     for (int k = 0; k < j; ++k) piv -= rj[k] * rj[k];
     real inv = b2_rsqrt(piv > B2_MINVAL ? piv : B2_MINVAL);
     invd[j] = inv;
     for (int i = j; i < nrows; ++i) {
-      real* ri = i < n ? A + i * ld : x;
+      real* ri = i < n ? B2_MROW(A, i) : x;
       real s = ri[j];
       for (int k = 0; k < j; ++k) s -= ri[k] * rj[k];
       ri[j] = s * inv;
@@ -272,15 +283,15 @@ B2_DEVN void chol_factor(real* A, int n, int ld, real* invd, real* x) {  // @reg
   B2_UNROLL1
   for (; j + 1 < n; j += 2) {
     B2_WSYNC();
-    const real* r0 = A + j * ld;
-    const real* r1 = r0 + ld;
+    const real* r0 = B2_MROW(A, j);
+    const real* r1 = B2_MROW(A, j + 1);
     const int j0 = j & ~3;
     real inv0 = 0, inv1 = 0, l10 = 0;
     B2_UNROLL1
     for (int base = j; base < nrows; base += B2_NLANE) {
       const int i = base + B2_LANE;
       real s0 = 0, s1 = 0;
-      real* ri = i < n ? A + i * ld : x;
+      real* ri = i < n ? B2_MROW(A, i) : x;
       if (i < nrows) {
         s0 = ri[j]; s1 = ri[j + 1];
         real t0 = 0, t1 = 0;
@@ -319,14 +330,14 @@ B2_DEVN void chol_factor(real* A, int n, int ld, real* invd, real* x) {  // @reg
   }
   if (j < n) {  // n odd: last column on its own
     B2_WSYNC();
-    const real* rj = A + j * ld;
+    const real* rj = B2_MROW(A, j);
     const int j0 = j & ~3;
     real inv = 0;
     B2_UNROLL1
     for (int base = j; base < nrows; base += B2_NLANE) {
       const int i = base + B2_LANE;
       real s = 0;
-      real* ri = i < n ? A + i * ld : x;
+      real* ri = i < n ? B2_MROW(A, i) : x;
       if (i < nrows) {
         s = ri[j];
         real s2 = 0;
@@ -352,6 +363,8 @@ B2_DEVN void chol_factor(real* A, int n, int ld, real* invd, real* x) {  // @reg
 #endif
   B2_WSYNC();
 }
+
+B2_DEV void chol_factor(real* A, int n, int ld, real* invd, real* x) { chol_factor_t<false>(A, n, ld, invd, x); }
 
 // x <- L^-1 x (forward substitution) for a factor that is already in place.
 B2_DEVN void chol_forwardsolve(const real* L, int n, int ld, const real* invd, real* x) {
@@ -381,12 +394,13 @@ B2_DEVN void chol_forwardsolve(const real* L, int n, int ld, const real* invd, r
 }
 
 // x <- L^-T x (backward substitution), x in shared memory.
-B2_DEVN void chol_backsolve(const real* L, int n, int ld, const real* invd, real* x) {  // @region chol_solve
+template <bool PACKED>
+B2_DEVN void chol_backsolve_t(const real* L, int n, int ld, const real* invd, real* x) {  // @region chol_solve
 #ifdef B2_HOSTEMU
   for (int k = n - 1; k >= 0; --k) {
     real xk = x[k] * invd[k];
     x[k] = xk;
-    for (int i = 0; i < k; ++i) x[i] -= L[k * ld + i] * xk;
+    for (int i = 0; i < k; ++i) x[i] -= B2_MROW(L, k)[i] * xk;
   }
 #else
   // lane i keeps x[i] and x[i+32] in registers; x_k is broadcast with a dynamic-lane shuffle
@@ -396,7 +410,7 @@ B2_DEVN void chol_backsolve(const real* L, int n, int ld, const real* invd, real
   real x1 = row1 < n ? x[row1] : (real)0;
   B2_UNROLL1
   for (int k = n - 1; k >= 32; --k) {
-    const real* Lk = L + k * ld;
+    const real* Lk = B2_MROW(L, k);
     real l0 = Lk[row0];
     real l1 = row1 < k ? Lk[row1] : (real)0;
     real xk = b2_shfl(x1, k & 31) * invd[k];
@@ -405,7 +419,7 @@ B2_DEVN void chol_backsolve(const real* L, int n, int ld, const real* invd, real
   }
   B2_UNROLL1
   for (int k = (n < 32 ? n : 32) - 1; k >= 0; --k) {
-    real l0 = row0 < k ? L[k * ld + row0] : (real)0;
+    real l0 = row0 < k ? B2_MROW(L, k)[row0] : (real)0;
     real xk = b2_shfl(x0, k) * invd[k];
     if (row0 == k) x0 = xk; else x0 = fmaf(-l0, xk, x0);
   }
@@ -414,6 +428,8 @@ B2_DEVN void chol_backsolve(const real* L, int n, int ld, const real* invd, real
 #endif
   B2_WSYNC();
 }
+
+B2_DEV void chol_backsolve(const real* L, int n, int ld, const real* invd, real* x) { chol_backsolve_t<false>(L, n, ld, invd, x); }
 
 #ifndef B2_SYMV_BATCH
 #define B2_SYMV_BATCH 4    // loads in flight per lane and batch (multiple of 4).  Measured (k_solve, G1 4096 worlds): 12 + straight-line tail 0.414 ms, one predicated 12-wide body 0.399, 8 -> 0.398, 4 -> 0.394: code size beats loads in flight (profiles/r02_k_solve_icache.txt)
@@ -487,4 +503,9 @@ B2_DEVN void copy_g2s(real* dst, const real* src, int count) {  // @region copy_
 B2_DEV void spd_factor_solve(real* A, int n, int ld, real* x, real* invd) {
   chol_factor(A, n, ld, invd, x);
   chol_backsolve(A, n, ld, invd, x);
+}
+// the same for a PACKED lower triangle (b2_poff)
+B2_DEV void spd_factor_solve_packed(real* A, int n, real* x, real* invd) {
+  chol_factor_t<true>(A, n, 0, invd, x);
+  chol_backsolve_t<true>(A, n, 0, invd, x);
 }

@@ -24,32 +24,31 @@ static inline SmoothSmem smooth_smem_layout(int nq, int nv, int nu, int nbody, i
   SmoothSmem s;
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
-  // Buffers of the position stage that are dead once the kinematic Jacobian (cdof) exists are reused by the velocity /
-  // force stage: shared memory per world sets how many worlds an SM holds (latency-bound kernel, occupancy pays).
-  //   [xquat | xanchor | xaxis]  (last read: cdof)            -> [cdofdot | f | aforce]
-  //   xmat                       (last read: cinert)          -> cvel
-  //   cand                       (collision candidates)       -> cfrc (RNE, after collision)
+  // Shared memory per world sets how many worlds an SM holds, and this kernel is latency-bound: occupancy pays.  Only what
+  // lives through the whole pass has its own slot; everything else time-shares ONE region whose largest tenant is the dense
+  // mass matrix, which is why smooth_world assembles M last (after the bias forces), straight before its factorisation:
+  //   position stage   : xpos | xquat | xanchor | xaxis | xmat      (last read: cdof)
+  //   velocity / force : cand (collision) = cfrc (RNE) | cvel | cdofdot | cacc     (last read: qfrc_smooth)
+  //   mass matrix      : M, packed lower triangle                     (crb is accumulated in place in cinert)
   s.qpos = take(nq); s.qvel = take(nv);
-  s.xpos = take(3 * nbody); s.xipos = take(3 * nbody);
-  {
-    int a0 = o;
-    s.xquat = take(4 * nbody); s.xanchor = take(3 * njnt); s.xaxis = take(3 * njnt);
-    int a1 = o;
-    o = a0;
-    s.cdofdot = take(6 * nv); s.f = take(nv); s.aforce = take(nu);
-    if (o < a1) o = a1;
-  }
-  s.xmat = take(9 * nbody);
-  s.cvel = s.xmat;           // 6*nbody <= 9*nbody
+  s.xipos = take(3 * nbody);
   s.scom = take(3 * nbody); s.smass = take(nbody);
-  s.cinert = take(10 * nbody); s.crb = take(10 * nbody);
+  s.cinert = take(10 * nbody); s.crb = s.cinert;
   s.cdof = take(6 * nv);
-  s.cacc = s.crb;            // crb is dead once qM is assembled; cacc (6*nbody) fits in 10*nbody
-  s.M = take(nv * b2_ld(nv));
+  s.f = take(nv); s.aforce = take(nu);
+  s.invd = take(64);  // 1 / diag(L)
+  const int r0 = o;
+  s.xpos = take(3 * nbody); s.xquat = take(4 * nbody); s.xanchor = take(3 * njnt); s.xaxis = take(3 * njnt); s.xmat = take(9 * nbody);
+  int end = o;
+  o = r0;
   s.cand = take(ncand > 6 * nbody ? ncand : 6 * nbody);   // candidate pair ids (ints stored in real-sized slots)
   s.cfrc = s.cand;
-  s.invd = take(64);  // 1 / diag(L)
-  s.total = o;
+  s.cvel = take(6 * nbody); s.cdofdot = take(6 * nv); s.cacc = take(6 * nbody);
+  if (o > end) end = o;
+  o = r0;
+  s.M = take(b2_poff(nv));   // packed lower triangle
+  if (o > end) end = o;
+  s.total = end;
   return s;
 }
 
@@ -766,7 +765,6 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
     ci[4] = Ri[0] * Ri[6] * I0 + Ri[1] * Ri[7] * I1 + Ri[2] * Ri[8] * I2 - ms * o[0] * o[2];
     ci[5] = Ri[3] * Ri[6] * I0 + Ri[4] * Ri[7] * I1 + Ri[5] * Ri[8] * I2 - ms * o[1] * o[2];
     ci[6] = ms * o[0]; ci[7] = ms * o[1]; ci[8] = ms * o[2]; ci[9] = ms;
-    for (int c = 0; c < 10; ++c) crb[10 * b + c] = ci[c];
   }
   B2_UNROLL1
   for (int j = B2_LANE; j < nj; j += B2_NLANE) {
@@ -801,46 +799,6 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
     for (int i = B2_LANE; i < 6 * nv; i += B2_NLANE) g[i] = cdof[i];
   }
   B2_SPH(1)
-  // ---- composite rigid body inertias, dense qM --------------------------------  // @region crb_qM
-  B2_UNROLL1
-  for (int lev = m.nlevel - 1; lev >= 1; --lev) {
-    B2_UNROLL1
-    for (int k = level_adr[lev] + B2_LANE; k < level_adr[lev + 1]; k += B2_NLANE) {
-      int b = level_body[k];
-      B2_UNROLL1
-      for (int c = child_adr[b]; c < child_adr[b + 1]; ++c) {
-        int ch = child_body[c];
-        for (int e = 0; e < 10; ++e) crb[10 * b + e] += crb[10 * ch + e];
-      }
-    }
-    B2_WSYNC();
-  }
-  B2_UNROLL1
-  for (int i = B2_LANE; i < nv * ld; i += B2_NLANE) M[i] = 0;
-  B2_WSYNC();
-  const real* armature = MF(B2_MF_DOF_ARMATURE);
-  B2_UNROLL1
-  for (int i = B2_LANE; i < nv; i += B2_NLANE) {
-    real buf[6];
-    inert_mul(buf, crb + 10 * dof_bodyid[i], cdof + 6 * i);
-    const real* ci = cdof + 6 * i;
-    M[i * ld + i] = armature[i] + ci[0] * buf[0] + ci[1] * buf[1] + ci[2] * buf[2] + ci[3] * buf[3] + ci[4] * buf[4] + ci[5] * buf[5];
-    B2_UNROLL1
-    for (int j = dof_parentid[i]; j >= 0; j = dof_parentid[j]) {
-      const real* cj = cdof + 6 * j;
-      real v = cj[0] * buf[0] + cj[1] * buf[1] + cj[2] * buf[2] + cj[3] * buf[3] + cj[4] * buf[4] + cj[5] * buf[5];
-      M[i * ld + j] = v;
-      M[j * ld + i] = v;
-    }
-  }
-  B2_WSYNC();
-  {
-    real* g = d.df[B2_DF_QM] + (size_t)w * nv * ld;
-    B2_UNROLL1
-    for (int i = B2_LANE; i < nv * ld; i += B2_NLANE) g[i] = M[i];
-  }
-
-  B2_SPH(2)
   // ---- collision ---------------------------------------------------------------  // @region collision
   {
     const int* pair_geom = MI(B2_MI_PAIR_GEOM);
@@ -1137,7 +1095,7 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
   }
 
   B2_SPH(4)
-  // ---- RNE bias (cacc aliases crb) -----------------------------------------------------  // @region rne
+  // ---- RNE bias ------------------------------------------------------------------------  // @region rne
   if (!light) {
   const real* grav = MF(B2_MF_OPT_GRAVITY);
   B2_UNROLL1
@@ -1180,11 +1138,6 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
     }
     B2_WSYNC();
   }
-  } else {   // memo: the mass matrix of this state is in HBM
-    const real* g = d.df[B2_DF_QM] + (size_t)w * nv * ld;
-    B2_UNROLL1
-    for (int i = B2_LANE; i < nv * ld; i += B2_NLANE) M[i] = g[i];
-    B2_WSYNC();
   }
 
   B2_SPH(5)
@@ -1250,9 +1203,72 @@ B2_DEV void smooth_world(const KModel& m, const KData& d, const SmoothSmem& L, i
     }
     B2_WSYNC();
   }
+  if (!light) {
+  // ---- composite rigid body inertias (accumulated in place: cinert is in HBM and dead here), dense qM ----  // @region crb_qM
+  B2_UNROLL1
+  for (int lev = m.nlevel - 1; lev >= 1; --lev) {
+    B2_UNROLL1
+    for (int k = level_adr[lev] + B2_LANE; k < level_adr[lev + 1]; k += B2_NLANE) {
+      int b = level_body[k];
+      B2_UNROLL1
+      for (int c = child_adr[b]; c < child_adr[b + 1]; ++c) {
+        int ch = child_body[c];
+        for (int e = 0; e < 10; ++e) crb[10 * b + e] += crb[10 * ch + e];
+      }
+    }
+    B2_WSYNC();
+  }
+  const int npack = b2_poff(nv);   // M is kept as a packed lower triangle (b2_common.cuh, b2_poff)
+  B2_UNROLL1
+  for (int i = B2_LANE; i < npack; i += B2_NLANE) M[i] = 0;
+  B2_WSYNC();
+  const real* armature = MF(B2_MF_DOF_ARMATURE);
+  B2_UNROLL1
+  for (int i = B2_LANE; i < nv; i += B2_NLANE) {
+    real buf[6];
+    inert_mul(buf, crb + 10 * dof_bodyid[i], cdof + 6 * i);
+    const real* ci = cdof + 6 * i;
+    real* Mi = M + b2_poff(i);
+    Mi[i] = armature[i] + ci[0] * buf[0] + ci[1] * buf[1] + ci[2] * buf[2] + ci[3] * buf[3] + ci[4] * buf[4] + ci[5] * buf[5];
+    B2_UNROLL1
+    for (int j = dof_parentid[i]; j >= 0; j = dof_parentid[j]) {   // ancestors: j < i
+      const real* cj = cdof + 6 * j;
+      Mi[j] = cj[0] * buf[0] + cj[1] * buf[1] + cj[2] * buf[2] + cj[3] * buf[3] + cj[4] * buf[4] + cj[5] * buf[5];
+    }
+  }
+  B2_WSYNC();
+  {  // dense symmetric copy for the solver and the integrator
+    real* g = d.df[B2_DF_QM] + (size_t)w * nv * ld;
+    int i = B2_LANE / ld, j = B2_LANE - i * ld;   // (row, column) of idx, advanced without a division per element
+    B2_UNROLL1
+    for (int idx = B2_LANE; idx < nv * ld; idx += B2_NLANE) {
+      g[idx] = j >= nv ? (real)0 : (j <= i ? M[b2_poff(i) + j] : M[b2_poff(j) + i]);
+      j += B2_NLANE;
+      while (j >= ld) { j -= ld; ++i; }
+    }
+    B2_WSYNC();   // the factorisation below overwrites M in place
+  }
+
+  B2_SPH(2)
+  } else {   // memo: the mass matrix of this state is in HBM
+    const real* g = d.df[B2_DF_QM] + (size_t)w * nv * ld;
+    const int npack = b2_poff(nv);
+    B2_UNROLL1
+    for (int i = B2_LANE; i < npack; i += B2_NLANE) M[i] = 0;
+    B2_WSYNC();
+    int i = B2_LANE / ld, j = B2_LANE - i * ld;
+    B2_UNROLL1
+    for (int idx = B2_LANE; idx < nv * ld; idx += B2_NLANE) {
+      if (j <= i) M[b2_poff(i) + j] = g[idx];
+      j += B2_NLANE;
+      while (j >= ld) { j -= ld; ++i; }
+    }
+    B2_WSYNC();
+  }
+
   B2_SPH(6)
-  // ---- qacc_smooth = M^-1 qfrc_smooth (M already copied to HBM; factor in place) ---------  // @region factor_solve
-  spd_factor_solve(M, nv, ld, f, sm + L.invd);
+  // ---- qacc_smooth = M^-1 qfrc_smooth (M is in HBM; factor in place) ---------------------  // @region factor_solve
+  spd_factor_solve_packed(M, nv, f, sm + L.invd);
   {
     real* g = d.df[B2_DF_QACC_SMOOTH] + (size_t)w * nv;
     B2_UNROLL1
