@@ -36,8 +36,8 @@ sys.path.insert(0, str(ROOT))
 DECIMATION = 4
 NUM_ENVS = 4096
 # DRAM bytes per launch from the committed ncu captures of this workload (profiles/r02_final_k_solve.txt,
-# r02_final_k_smooth.txt, r02_final_k_post.txt)
-NCU_TRAFFIC_BYTES = {"k_solve": 38_247_168 + 627_200, "k_smooth": 11_950_848 + 29_646_336, "k_post": 52_210_944 + 724_992}
+# r02b_k_smooth.txt, r02_final_k_post.txt)
+NCU_TRAFFIC_BYTES = {"k_solve": 38_247_168 + 627_200, "k_smooth": 14_992_128 + 38_866_688, "k_post": 52_210_944 + 724_992}
 
 
 def parse():
@@ -505,7 +505,7 @@ def run_b200(args):
     roof = {
       "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
       "traffic": NCU_TRAFFIC_BYTES.get(dom) if (args.model == "g1_flat" and nw == NUM_ENVS) else None,
-      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, profiles/r02_final_k_{solve,smooth,post}.txt",
+      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, profiles/r02_final_k_{solve,post}.txt, r02b_k_smooth.txt",
       "peak_source": "measured burst (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback (B200_PROFILING.md)",
       "algorithmic_bytes_per_world": {"k_smooth": b_smooth, "k_solve": b_solve, "env_step": b_env},
       "avg_launch_ms": avg, "ms_per_env_step_by_kernel": per_step,
@@ -519,6 +519,8 @@ def run_b200(args):
     env2 = make_env("masked")
     env2.reset()
     env2.episode_length_buf = env.episode_length_buf.clone()
+    for k in range(npre):           # the same pre-warm as the main arm: the state mix (fallen / standing worlds) sets the solver's load
+      env2.step(pw[k % 16])
     for k in range(warm):
       env2.step(wa[k])
     ev3 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
