@@ -35,17 +35,20 @@ extern "C" {
 #endif
 
 #define B2E_MAXFEET 4
-#define B2E_NREW 14
-#define B2E_NTERM 3
+#define B2E_NREW 21
+#define B2E_NTERM 5
 
 /* reward term order (tasks/velocity/velocity_env_cfg.py:183-278 + config/g1/env_cfgs.py:122-126) */
 enum b2e_rew {
   B2E_REW_TRACK_LIN = 0, B2E_REW_TRACK_ANG, B2E_REW_UPRIGHT, B2E_REW_POSE, B2E_REW_BODY_ANG_VEL, B2E_REW_ANGMOM,
   B2E_REW_DOF_POS_LIMITS, B2E_REW_ACTION_RATE, B2E_REW_AIR_TIME, B2E_REW_FOOT_CLEARANCE, B2E_REW_FOOT_SWING,
-  B2E_REW_FOOT_SLIP, B2E_REW_SOFT_LANDING, B2E_REW_SELF_COLLISIONS
+  B2E_REW_FOOT_SLIP, B2E_REW_SOFT_LANDING, B2E_REW_SELF_COLLISIONS,
+  /* the generic term library (envs/mdp/rewards.py:22-70,149-155), weight 0 in the shipped velocity tasks */
+  B2E_REW_IS_ALIVE, B2E_REW_IS_TERMINATED, B2E_REW_JOINT_TORQUES_L2, B2E_REW_JOINT_VEL_L2, B2E_REW_JOINT_ACC_L2,
+  B2E_REW_ACTION_ACC_L2, B2E_REW_FLAT_ORIENTATION_L2
 };
-/* termination term order */
-enum b2e_term { B2E_TERM_TIME_OUT = 0, B2E_TERM_FELL_OVER, B2E_TERM_ILLEGAL_CONTACT };
+/* termination term order; the last two (envs/mdp/terminations.py:35-47) are off unless B2E_IP_TERM_FLAGS enables them */
+enum b2e_term { B2E_TERM_TIME_OUT = 0, B2E_TERM_FELL_OVER, B2E_TERM_ILLEGAL_CONTACT, B2E_TERM_ROOT_HEIGHT, B2E_TERM_NAN };
 
 /* ---- int parameters ----------------------------------------------------- */
 enum b2e_ip {
@@ -65,6 +68,7 @@ enum b2e_ip {
   B2E_IP_TERRAIN_MODE,      /* bit 0: terrain_levels_vel curriculum at reset (tasks/velocity/mdp/curriculums.py:30-64);
                                bit 1: randomize_terrain reset event of play mode (envs/mdp/events.py:26-37); 0: flat plane */
   B2E_IP_TERRAIN_ROWS, B2E_IP_TERRAIN_COLS,
+  B2E_IP_TERM_FLAGS,        /* bit 0: root_height_below_minimum (B2E_FP_MIN_ROOT_HEIGHT), bit 1: nan_detection */
   B2E_IP_FOOT_SITE,         /* [B2E_MAXFEET] global site ids */
   B2E_IP_FOOT_SITE_BODY = B2E_IP_FOOT_SITE + B2E_MAXFEET,    /* [B2E_MAXFEET] body of each foot site */
   B2E_IP_FOOT_FOUND_ADR = B2E_IP_FOOT_SITE_BODY + B2E_MAXFEET,
@@ -81,6 +85,7 @@ enum b2e_fp {
   B2E_FP_WALKING_THRESHOLD, B2E_FP_RUNNING_THRESHOLD,
   B2E_FP_AIR_THR_MIN, B2E_FP_AIR_THR_MAX, B2E_FP_AIR_CMD_THRESHOLD,
   B2E_FP_TARGET_HEIGHT, B2E_FP_CMD_THRESHOLD,
+  B2E_FP_MIN_ROOT_HEIGHT,   /* root_height_below_minimum(minimum_height) */
   B2E_FP_TERRAIN_HALF_SIZE, /* terrain_generator.size[0] / 2: an env that walked farther than this moves up a level */
   B2E_FP_CMD_RESAMPLE,      /* [2] */
   B2E_FP_CMD_LIN_X = B2E_FP_CMD_RESAMPLE + 2,

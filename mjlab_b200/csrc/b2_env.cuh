@@ -88,6 +88,7 @@ B2_DEV real env_wrap_to_pi(real a) {
   if (r < 0) r += TWO_PI;
   return (r == 0 && a > 0) ? PI : r - PI;
 }
+B2_DEV bool env_finite(real x) { return x == x && x - x == 0; }   // neither NaN nor +-Inf
 B2_DEV real env_nan_to_num(real v) { return (v == v && v - v == 0) ? v : (real)0; }
 
 // DcMotorActuator._clip_effort (actuator/dc_actuator.py:136-162): torque-speed line, then the continuous limit
@@ -231,13 +232,31 @@ B2_DEV void env_post_world(const KModel& m, const KData& d, const KEnv& e, int w
   for (int k = B2_LANE; k < EI(B2E_IP_ILLEGAL_COUNT); k += B2_NLANE) ill |= sd[EI(B2E_IP_ILLEGAL_ADR) + k] != 0;
   bool illegal = b2_wor_i(ill) != 0;
   const bool has_illegal = EI(B2E_IP_ILLEGAL_COUNT) > 0;
-  bool terminated = fell || (has_illegal && illegal);
+  // generic terminations (envs/mdp/terminations.py:35-47), off unless the configuration lists them
+  const int tflags = EI(B2E_IP_TERM_FLAGS);
+  const bool root_low = (tflags & 1) && R.pos[2] < EF(B2E_FP_MIN_ROOT_HEIGHT);
+  bool has_nan = false;
+  if (tflags & 2) {   // NanGuard.detect_nans: qpos, qvel, qacc, qacc_warmstart
+    int bad = 0;
+    const real* qv = d.df[B2_DF_QVEL] + (size_t)w * m.nv;
+    const real* qa = d.df[B2_DF_QACC] + (size_t)w * m.nv;
+    const real* qw = d.df[B2_DF_QACC_WARMSTART] + (size_t)w * m.nv;
+    for (int i = B2_LANE; i < m.nq; i += B2_NLANE) bad |= !env_finite(qpos[i]);
+    for (int i = B2_LANE; i < m.nv; i += B2_NLANE) bad |= !(env_finite(qv[i]) && env_finite(qa[i]) && env_finite(qw[i]));
+    has_nan = b2_wor_i(bad) != 0;
+  }
+  bool terminated = fell || (has_illegal && illegal) || root_low || has_nan;
   bool reset = terminated || time_out;
 
   // ---- per-joint reward sums ------------------------------------------------------------
   const int* jq = EBI(B2E_B_JOINT_Q_ADR);
-  real pose_acc = 0, lim_acc = 0, rate_acc = 0;
+  real pose_acc = 0, lim_acc = 0, rate_acc = 0, tau_acc = 0, vel_acc = 0, acc_acc = 0, aacc_acc = 0;
   {
+    const int* jv = EBI(B2E_B_JOINT_V_ADR);
+    const int* cid = EBI(B2E_B_CTRL_IDS);
+    const real* g_qvel = d.df[B2_DF_QVEL] + (size_t)w * m.nv;
+    const real* g_qacc = d.df[B2_DF_QACC] + (size_t)w * m.nv;
+    const real* g_af = d.df[B2_DF_ACTUATOR_FORCE] + (size_t)w * m.nu;
     const real wt = EF(B2E_FP_WALKING_THRESHOLD), rt = EF(B2E_FP_RUNNING_THRESHOLD);
     const real ms = total_cmd < wt ? 1 : 0, mw = (total_cmd >= wt && total_cmd < rt) ? 1 : 0, mr = total_cmd >= rt ? 1 : 0;
     for (int j = B2_LANE; j < nj; j += B2_NLANE) {
@@ -250,8 +269,14 @@ B2_DEV void env_post_world(const KModel& m, const KData& d, const KEnv& e, int w
       lim_acc += -(lo < 0 ? lo : (real)0) + (hi > 0 ? hi : (real)0);
       real da = EBR(B2E_B_ACTION)[o] - EBR(B2E_B_PREV_ACTION)[o];
       rate_acc += da * da;
+      // generic library: joint_torques_l2, joint_vel_l2, joint_acc_l2, action_acc_l2 (envs/mdp/rewards.py:32-70)
+      real tau = g_af[cid[j]], qd = g_qvel[jv[j]], qdd = g_qacc[jv[j]];
+      tau_acc += tau * tau; vel_acc += qd * qd; acc_acc += qdd * qdd;
+      real dda = EBR(B2E_B_ACTION)[o] - 2 * EBR(B2E_B_PREV_ACTION)[o] + EBR(B2E_B_PREV_PREV_ACTION)[o];
+      aacc_acc += dda * dda;
     }
     pose_acc = b2_wsum(pose_acc); lim_acc = b2_wsum(lim_acc); rate_acc = b2_wsum(rate_acc);
+    tau_acc = b2_wsum(tau_acc); vel_acc = b2_wsum(vel_acc); acc_acc = b2_wsum(acc_acc); aacc_acc = b2_wsum(aacc_acc);
   }
 
   // ---- per-foot quantities (lane f < nfeet) ------------------------------------------------
@@ -340,6 +365,13 @@ B2_DEV void env_post_world(const KModel& m, const KData& d, const KEnv& e, int w
     term[B2E_REW_FOOT_SLIP] = slip_cost * active;
     term[B2E_REW_SOFT_LANDING] = land_cost * active;
     term[B2E_REW_SELF_COLLISIONS] = EI(B2E_IP_SELFCOL_ADR) >= 0 ? sd[EI(B2E_IP_SELFCOL_ADR)] : (real)0;
+    term[B2E_REW_IS_ALIVE] = terminated ? 0 : 1;
+    term[B2E_REW_IS_TERMINATED] = terminated ? 1 : 0;
+    term[B2E_REW_JOINT_TORQUES_L2] = tau_acc;
+    term[B2E_REW_JOINT_VEL_L2] = vel_acc;
+    term[B2E_REW_JOINT_ACC_L2] = acc_acc;
+    term[B2E_REW_ACTION_ACC_L2] = aacc_acc;
+    term[B2E_REW_FLAT_ORIENTATION_L2] = R.pg[0] * R.pg[0] + R.pg[1] * R.pg[1];
     if (EF(B2E_FP_REWARD_WEIGHT + B2E_REW_AIR_TIME) != 0) { logv[B2E_LOG_AIR_TIME_SUM] = m_air_sum; logv[B2E_LOG_AIR_COUNT] = m_air_cnt; }
     if (EF(B2E_FP_REWARD_WEIGHT + B2E_REW_FOOT_SWING) != 0) logv[B2E_LOG_PEAK_SUM] = m_peak;
     logv[B2E_LOG_LANDINGS] = m_land;
@@ -361,6 +393,7 @@ B2_DEV void env_post_world(const KModel& m, const KData& d, const KEnv& e, int w
     EBR(B2E_B_REWARD)[w] = total;
     unsigned char* td = EBU(B2E_B_TERM_DONES) + (size_t)w * B2E_NTERM;
     td[B2E_TERM_TIME_OUT] = time_out; td[B2E_TERM_FELL_OVER] = fell; td[B2E_TERM_ILLEGAL_CONTACT] = has_illegal && illegal;
+    td[B2E_TERM_ROOT_HEIGHT] = root_low; td[B2E_TERM_NAN] = has_nan;
     EBU(B2E_B_TERMINATED)[w] = terminated; EBU(B2E_B_TIME_OUTS)[w] = time_out; EBU(B2E_B_RESET_BUF)[w] = reset;
     EBL(B2E_B_EPISODE_LENGTH)[w] = ep;
   }

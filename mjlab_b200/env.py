@@ -154,9 +154,9 @@ class _LogView(Mapping):
       K, cfg = A.K, self._env.vcfg
       n = max(v[K["B2E_LOG_NRESET"]], 1.0)
       out: dict[str, float] = {}
-      for k, name in enumerate(self._env.reward_manager.active_terms):
+      for name, k in self._env.reward_manager.slots.items():
         out["Episode_Reward/" + name] = v[K["B2E_LOG_EPISODE_SUM"] + k] / n / cfg.max_episode_length_s
-      for k, name in enumerate(self._env.termination_manager.active_terms):
+      for name, k in self._env.termination_manager.slots.items():
         out["Episode_Termination/" + name] = v[K["B2E_LOG_TERM_COUNT"] + k]
       out["Metrics/twist/error_vel_xy"] = v[K["B2E_LOG_CMD_ERR_XY"]] / n
       out["Metrics/twist/error_vel_yaw"] = v[K["B2E_LOG_CMD_ERR_YAW"]] / n
@@ -219,28 +219,36 @@ class _CommandManager:
 class _RewardManager:
   def __init__(self, env):
     self._env = env
-    self.active_terms = list(envcfg.REWARD_NAMES) if env.vcfg.selfcol_adr >= 0 else list(envcfg.REWARD_NAMES[:-1])
+    # term name -> kernel slot: the shipped task's 13 / 14 terms always, the generic library (envs/mdp/rewards.py) when weighted
+    core = envcfg.REWARD_NAMES.index("self_collisions")
+    w = env.vcfg.reward_weights
+    self.slots = {n: k for k, n in enumerate(envcfg.REWARD_NAMES)
+                  if k < core or (k == core and env.vcfg.selfcol_adr >= 0) or (k > core and w[k] != 0)}
+    self.active_terms = list(self.slots)
 
   _step_reward = property(lambda self: self._env._buf["step_reward"])
   _reward_buf = property(lambda self: self._env._buf["reward"])
-  _episode_sums = property(lambda self: {n: self._env._buf["episode_sums"][:, k] for k, n in enumerate(self.active_terms)})
+  _episode_sums = property(lambda self: {n: self._env._buf["episode_sums"][:, k] for n, k in self.slots.items()})
 
   def get_active_iterable_terms(self, env_idx: int):
     row = self._env._buf["step_reward"][env_idx].tolist()
-    return [(n, [row[k]]) for k, n in enumerate(self.active_terms)]
+    return [(n, [row[k]]) for n, k in self.slots.items()]
 
 
 class _TerminationManager:
   def __init__(self, env):
     self._env = env
-    self.active_terms = ["time_out", "fell_over"] + (["illegal_contact"] if env.vcfg.illegal_count > 0 else [])
+    on = {"time_out": True, "fell_over": True, "illegal_contact": env.vcfg.illegal_count > 0,
+          "root_height_below_minimum": env.vcfg.min_root_height is not None, "nan_detection": env.vcfg.nan_termination}
+    self.slots = {n: k for k, n in enumerate(envcfg.TERMINATION_NAMES) if on[n]}
+    self.active_terms = list(self.slots)
 
   terminated = property(lambda self: self._env._buf["terminated"].view(torch.bool))
   time_outs = property(lambda self: self._env._buf["time_outs"].view(torch.bool))
   dones = property(lambda self: self._env._buf["reset_buf"].view(torch.bool))
 
   def get_term(self, name: str) -> torch.Tensor:
-    return self._env._buf["term_dones"][:, self.active_terms.index(name)].view(torch.bool)
+    return self._env._buf["term_dones"][:, self.slots[name]].view(torch.bool)
 
 
 class _ObservationManager:

@@ -165,7 +165,8 @@ def fill_params(ce: B2Env, cfg) -> None:
                   ("ILLEGAL_ADR", max(cfg.illegal_adr, 0)), ("ILLEGAL_COUNT", cfg.illegal_count),
                   ("MAX_EPISODE_LENGTH", min(int(cfg.max_episode_length), 2**31 - 1)), ("ENABLE_CORRUPTION", int(cfg.enable_corruption)),
                   ("PUSH_ENABLED", int(cfg.push_enabled)), ("HEADING_COMMAND", int(cfg.heading_command)),
-                  ("TERRAIN_MODE", int(cfg.terrain_mode)), ("TERRAIN_ROWS", int(cfg.terrain_rows)), ("TERRAIN_COLS", int(cfg.terrain_cols))):
+                  ("TERRAIN_MODE", int(cfg.terrain_mode)), ("TERRAIN_ROWS", int(cfg.terrain_rows)), ("TERRAIN_COLS", int(cfg.terrain_cols)),
+                  ("TERM_FLAGS", (1 if cfg.min_root_height is not None else 0) | (2 if cfg.nan_termination else 0))):
     ip[K["B2E_IP_" + name]] = int(v)
   for f in range(cfg.nfeet):
     ip[K["B2E_IP_FOOT_SITE"] + f] = int(cfg.foot_site_ids[f])
@@ -177,7 +178,7 @@ def fill_params(ce: B2Env, cfg) -> None:
                   ("WALKING_THRESHOLD", cfg.walking_threshold), ("RUNNING_THRESHOLD", cfg.running_threshold),
                   ("AIR_THR_MIN", cfg.air_thr_min), ("AIR_THR_MAX", cfg.air_thr_max), ("AIR_CMD_THRESHOLD", cfg.air_cmd_threshold),
                   ("TARGET_HEIGHT", cfg.target_height), ("CMD_THRESHOLD", cfg.cmd_threshold), ("REL_STANDING", cfg.rel_standing),
-                  ("TERRAIN_HALF_SIZE", cfg.terrain_half_size),
+                  ("TERRAIN_HALF_SIZE", cfg.terrain_half_size), ("MIN_ROOT_HEIGHT", cfg.min_root_height if cfg.min_root_height is not None else 0.0),
                   ("REL_HEADING", cfg.rel_heading), ("HEADING_STIFFNESS", cfg.heading_stiffness)):
     fp[K["B2E_FP_" + name]] = float(v)
   for name, pair in (("CMD_RESAMPLE", cfg.cmd_resample), ("CMD_LIN_X", cfg.cmd_lin_x), ("CMD_LIN_Y", cfg.cmd_lin_y),

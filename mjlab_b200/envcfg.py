@@ -48,8 +48,10 @@ REWARD_NAMES = (
   "track_linear_velocity", "track_angular_velocity", "upright", "pose", "body_ang_vel", "angular_momentum",
   "dof_pos_limits", "action_rate_l2", "air_time", "foot_clearance", "foot_swing_height", "foot_slip", "soft_landing",
   "self_collisions",
+  # the generic library of envs/mdp/rewards.py (weight 0 in the shipped tasks; a consumed ManagerBasedRlEnvCfg may use them)
+  "is_alive", "is_terminated", "joint_torques_l2", "joint_vel_l2", "joint_acc_l2", "action_acc_l2", "flat_orientation_l2",
 )
-TERMINATION_NAMES = ("time_out", "fell_over", "illegal_contact")
+TERMINATION_NAMES = ("time_out", "fell_over", "illegal_contact", "root_height_below_minimum", "nan_detection")
 
 _G1_STD_WALK = {
   r".*hip_pitch.*": 0.3, r".*hip_roll.*": 0.15, r".*hip_yaw.*": 0.15, r".*knee.*": 0.35, r".*ankle_pitch.*": 0.25,
@@ -113,6 +115,8 @@ class VelocityCfg:
   max_episode_length: int = 1000
   max_episode_length_s: float = 20.0
   limit_angle: float = math.radians(70.0)
+  min_root_height: float | None = None     # root_height_below_minimum termination (envs/mdp/terminations.py:35-42); None = off
+  nan_termination: bool = False            # nan_detection termination (envs/mdp/terminations.py:45-47)
   # reward parameters (velocity_env_cfg.py:183-278)
   std_lin: float = math.sqrt(0.25)
   std_ang: float = math.sqrt(0.5)
@@ -272,7 +276,7 @@ def velocity_cfg(m, robot: str, play: bool = False) -> VelocityCfg:
     linvel_adr=sadr("robot/imu_lin_vel"), angvel_adr=sadr("robot/imu_ang_vel"), angmom_adr=sadr("robot/root_angmom"),
     selfcol_adr=selfcol, illegal_adr=illegal_adr, illegal_count=illegal_count,
     upright_body=int(body_ids[body_local.index(upright)]), upright_body_local=body_local.index(upright),
-    reward_weights=np.array([weights[n] for n in REWARD_NAMES]),
+    reward_weights=np.array([weights.get(n, 0.0) for n in REWARD_NAMES]),
     std_standing=_resolve_values(std_stand, local_names), std_walking=_resolve_values(std_walk, local_names),
     std_running=_resolve_values(std_run, local_names), std_standing_map=std_stand, std_walking_map=std_walk,
     std_running_map=std_run, noise_lo=lo, noise_hi=hi, n_obs_policy=n_pol, n_obs_critic=n_cri,
@@ -396,6 +400,8 @@ REWARD_FUNCS = {
   "pose": "variable_posture", "body_ang_vel": "body_angular_velocity_penalty", "angular_momentum": "angular_momentum_penalty",
   "dof_pos_limits": "joint_pos_limits", "action_rate_l2": "action_rate_l2", "air_time": "feet_air_time", "foot_clearance": "feet_clearance",
   "foot_swing_height": "feet_swing_height", "foot_slip": "feet_slip", "soft_landing": "soft_landing", "self_collisions": "self_collision_cost",
+  "is_alive": "is_alive", "is_terminated": "is_terminated", "joint_torques_l2": "joint_torques_l2", "joint_vel_l2": "joint_vel_l2",
+  "joint_acc_l2": "joint_acc_l2", "action_acc_l2": "action_acc_l2", "flat_orientation_l2": "flat_orientation_l2",
 }
 # observation terms the fused kernel writes, in its fixed order: (term function, sensor_name param or None)
 POLICY_OBS_TERMS = (("builtin_sensor", "robot/imu_lin_vel"), ("builtin_sensor", "robot/imu_ang_vel"), ("projected_gravity", None),
@@ -452,6 +458,10 @@ def from_manager_cfg(cfg, m, robot: str) -> VelocityCfg:
       w[k] = float(t["weight"])
       P[slot] = t["params"]
   c.reward_weights = w
+  for slot in ("joint_torques_l2", "joint_vel_l2", "joint_acc_l2", "flat_orientation_l2"):
+    ac = (P.get(slot) or {}).get("asset_cfg") or {}
+    if any(ac.get(k) not in (None, (".*",), [".*"], ".*") for k in ("joint_names", "body_names")) or ac.get("name", "robot") != "robot":
+      raise UnsupportedTermError(f"reward '{slot}': the kernel term covers all actuated joints of 'robot' (asset_cfg {ac})")
   if "track_linear_velocity" in P: c.std_lin = float(P["track_linear_velocity"]["std"])        # noqa: E701
   if "track_angular_velocity" in P: c.std_ang = float(P["track_angular_velocity"]["std"])      # noqa: E701
   if "upright" in P:
@@ -481,7 +491,7 @@ def from_manager_cfg(cfg, m, robot: str) -> VelocityCfg:
   if hs: c.target_height = hs.pop()          # noqa: E701
   # ---- terminations -----------------------------------------------------------------------------------------------------
   tf = {t["func"]: t for t in d["terminations"].values() if t is not None}
-  bad = set(tf) - {"time_out", "bad_orientation", "illegal_contact"}
+  bad = set(tf) - {"time_out", "bad_orientation", "illegal_contact", "root_height_below_minimum", "nan_detection"}
   if bad:
     raise UnsupportedTermError(f"termination functions {sorted(bad)} are not implemented by the env kernels")
   if "time_out" not in tf or not tf["time_out"]["time_out"]:
@@ -490,6 +500,11 @@ def from_manager_cfg(cfg, m, robot: str) -> VelocityCfg:
     c.limit_angle = float(tf["bad_orientation"]["params"]["limit_angle"])
   else:
     c.limit_angle = 4.0          # never reached: projected gravity angle <= pi
+  c.min_root_height = float(tf["root_height_below_minimum"]["params"]["minimum_height"]) if "root_height_below_minimum" in tf else None
+  c.nan_termination = "nan_detection" in tf
+  for f in ("bad_orientation", "root_height_below_minimum", "nan_detection", "illegal_contact"):
+    if f in tf and tf[f]["time_out"]:
+      raise UnsupportedTermError(f"termination '{f}' with time_out=True: the kernels count it as a failure termination")
   if ("illegal_contact" in tf) != (c.illegal_count > 0):
     raise UnsupportedTermError("illegal_contact needs the scene's nonfoot_ground_touch sensor (and the compiled Go1 scene always has it)")
   # ---- observations -------------------------------------------------------------------------------------------------------

@@ -175,13 +175,24 @@ def terminations(cfg, s, d, R):
     illegal = np.any(d.sensordata[:, cfg.illegal_adr: cfg.illegal_adr + cfg.illegal_count] != 0, axis=1)
   else:
     illegal = np.zeros_like(fell)
-  return time_out, fell, illegal
+  # generic library (envs/mdp/terminations.py:35-47), off unless configured
+  if getattr(cfg, "min_root_height", None) is not None:
+    root_low = d.xpos[:, cfg.root_body, 2].astype(F) < F(cfg.min_root_height)
+  else:
+    root_low = np.zeros_like(fell)
+  if getattr(cfg, "nan_termination", False):
+    has_nan = np.zeros_like(fell)
+    for a in (d.qpos, d.qvel, d.qacc, d.qacc_warmstart):
+      has_nan |= ~np.all(np.isfinite(a), axis=1)
+  else:
+    has_nan = np.zeros_like(fell)
+  return time_out, fell, illegal, root_low, has_nan
 
 
 # ---------------------------------------------------------------------------------------------------------
 # rewards (tasks/velocity/mdp/rewards.py:23-359, envs/mdp/rewards.py:56-88); returns [B, NREW] raw term values
 # ---------------------------------------------------------------------------------------------------------
-def reward_terms(cfg, s, d, R, log=None):
+def reward_terms(cfg, s, d, R, log=None, terminated=None):
   B = s.command.shape[0]
   w = cfg.reward_weights
   cmd = s.command
@@ -239,6 +250,17 @@ def reward_terms(cfg, s, d, R, log=None):
   out[:, K["B2E_REW_SOFT_LANDING"]] = np.sum(fmag * fc.astype(F), 1) * active  # :262-288
   if cfg.selfcol_adr >= 0:
     out[:, K["B2E_REW_SELF_COLLISIONS"]] = sd[:, cfg.selfcol_adr]  # :88-95
+  # generic library, envs/mdp/rewards.py:22-70,149-155
+  if terminated is not None:
+    out[:, K["B2E_REW_IS_ALIVE"]] = (~terminated).astype(F)
+    out[:, K["B2E_REW_IS_TERMINATED"]] = terminated.astype(F)
+  if getattr(d, "actuator_force", None) is not None:   # (data views of callers that never weight these terms may lack the arrays)
+    out[:, K["B2E_REW_JOINT_TORQUES_L2"]] = np.sum(np.square(d.actuator_force[:, cfg.ctrl_ids].astype(F)), 1)
+  out[:, K["B2E_REW_JOINT_VEL_L2"]] = np.sum(np.square(d.qvel[:, cfg.joint_v_adr].astype(F)), 1)
+  if getattr(d, "qacc", None) is not None:
+    out[:, K["B2E_REW_JOINT_ACC_L2"]] = np.sum(np.square(d.qacc[:, cfg.joint_v_adr].astype(F)), 1)
+  out[:, K["B2E_REW_ACTION_ACC_L2"]] = np.sum(np.square(s.action - F(2) * s.prev_action + s.prev_prev_action), 1)
+  out[:, K["B2E_REW_FLAT_ORIENTATION_L2"]] = np.sum(np.square(R.pg[:, :2]), 1)
   if log is not None:
     if w[K["B2E_REW_ANGMOM"]] != 0:
       log[:, K["B2E_LOG_ANGMOM"]] = np.sqrt(am_sq)
@@ -324,12 +346,12 @@ def post(cfg, m, s, d, u=None, do_reset=True) -> None:
   s.log_env[:] = 0
   R = root_kinematics(cfg, d)
   s.episode_length += 1
-  time_out, fell, illegal = terminations(cfg, s, d, R)
-  terms = reward_terms(cfg, s, d, R, log=s.log_env)
+  time_out, fell, illegal, root_low, has_nan = terminations(cfg, s, d, R)
+  s.terminated[:] = fell | illegal | root_low | has_nan
+  terms = reward_terms(cfg, s, d, R, log=s.log_env, terminated=s.terminated)
   s.last_terms = terms
   reward_total(cfg, s, terms)
-  s.term_dones[:, 0], s.term_dones[:, 1], s.term_dones[:, 2] = time_out, fell, illegal
-  s.terminated[:] = fell | illegal
+  s.term_dones[:, 0], s.term_dones[:, 1], s.term_dones[:, 2], s.term_dones[:, 3], s.term_dones[:, 4] = time_out, fell, illegal, root_low, has_nan
   s.time_outs[:] = time_out
   s.reset_buf[:] = s.terminated | s.time_outs
   if not do_reset:

@@ -32,6 +32,35 @@ def compare_state(env, s, names=STATE):
       np.testing.assert_array_equal(a.astype(np.int64), np.asarray(b).astype(np.int64).reshape(a.shape), err_msg=n)
 
 
+GENERIC_WEIGHTS = [0.5, -2.0, -1e-4, -1e-3, -1e-6, -0.01, -1.0]   # is_alive, is_terminated, joint_torques_l2, joint_vel_l2, joint_acc_l2, action_acc_l2, flat_orientation_l2
+
+
+@pytest.mark.parametrize("fixture", ["g1", "go1_fallen"])
+def test_generic_terminations_match_reference(fixture):
+  """root_height_below_minimum / nan_detection (envs/mdp/terminations.py:35-47) against the reference's functions: both depend on
+  the current state only, so every env is compared at every step."""
+  robot = fixture.split("_")[0]
+  m = mjlab_b200.load_model(f"{robot}_flat")
+  cfg = envcfg.velocity_cfg(m, robot)
+  g = load_golden(fixture)
+  cfg.min_root_height, cfg.nan_termination = float(g["min_root_height"]), True
+  T, B = g["actions"].shape[:2]
+  sim = HostSim(m, B, nconmax=35, njmax=300)
+  env = HostEnv(sim, cfg)
+  init_state_from_golden(env, g)
+  for t in range(T):
+    upload(sim, snapshot(g, t, m))
+    if t == 3:
+      sim.qacc[1, 2] = np.inf     # a world going bad: nan_detection fires for it alone
+    env.stage(2)
+    np.testing.assert_array_equal(env.term_dones[:, 3], g["ref_root_low"][t])
+    want_nan = g["ref_nan"][t].copy()
+    want_nan[1] |= t == 3
+    np.testing.assert_array_equal(env.term_dones[:, 4], want_nan)
+    assert np.array_equal(env.terminated.astype(bool), env.term_dones[:, 1:].any(1))
+  assert g["ref_root_low"].any() and not g["ref_root_low"].all()
+
+
 @pytest.mark.parametrize("fixture", ["g1", "go1", "g1_fallen", "go1_fallen"])
 def test_kernels_match_reference_golden(fixture):
   """Before an env's first reset the kernels must reproduce the reference's reward terms / observations / flags.  The
@@ -42,6 +71,7 @@ def test_kernels_match_reference_golden(fixture):
   cfg = envcfg.velocity_cfg(m, robot)
   cfg.enable_corruption = False
   cfg.push_enabled = False
+  cfg.reward_weights[14:] = GENERIC_WEIGHTS   # the generic term library is off (weight 0) in the shipped tasks: switch it on
   g = load_golden(fixture)
   T, B = g["actions"].shape[:2]
   sim = HostSim(m, B, nconmax=35, njmax=300)
@@ -67,7 +97,7 @@ def test_kernels_match_reference_golden(fixture):
     ntrue += int(env.term_dones[:, 1:].sum())
     w = cfg.reward_weights.astype(np.float32)
     np.testing.assert_allclose(env.step_reward[alive], (g["ref_rew_terms"][t] * w)[alive], **TOL)
-    np.testing.assert_allclose(env.reward[alive], g["ref_reward"][t][alive], **TOL)
+    np.testing.assert_allclose(env.reward[alive], (g["ref_rew_terms"][t] * w * np.float32(cfg.step_dt)).sum(1)[alive], rtol=1e-4, atol=1e-5)
     alive &= ~env.reset_buf.astype(bool)
     np.testing.assert_allclose(env.peak_heights[alive], g["ref_peak"][t][alive], **TOL)
     upload(sim, d)  # the reset rewrote qpos/qvel of done envs; the golden observations come from the un-reset snapshot

@@ -48,6 +48,15 @@ def test_oracle_matches_reference_functions(fixture):
     OE.observations(cfg_nonoise, s, d, R, u=None)
     np.testing.assert_allclose(s.obs_policy, g["ref_obs_policy"][t], **TOL)
     np.testing.assert_allclose(s.obs_critic, g["ref_obs_critic"][t], **TOL)
+  # generic terminations: state-only flags, compared on every snapshot
+  cfg2 = envcfg.velocity_cfg(m, robot)
+  cfg2.min_root_height, cfg2.nan_termination = float(g["min_root_height"]), True
+  for t in range(T):
+    d = snapshot(g, t, m)
+    flags = OE.terminations(cfg2, s, d, OE.root_kinematics(cfg2, d))
+    np.testing.assert_array_equal(flags[3], g["ref_root_low"][t])
+    np.testing.assert_array_equal(flags[4], g["ref_nan"][t])
+  assert g["ref_root_low"].any() and not g["ref_root_low"].all()
   assert nterm_checked > 0  # the fixture exercises at least one termination flag
   if fixture.endswith("fallen"):   # ... and these make the reference's own bad_orientation / illegal_contact return True
     assert g["ref_fell_over"].any() and not g["ref_fell_over"].all()

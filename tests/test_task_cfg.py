@@ -80,7 +80,10 @@ def test_unsupported_terms_raise():
       envcfg.from_manager_cfg(d, m, "g1")
 
   bad(lambda d: d["rewards"].update(my_term=dict(func="my_reward", weight=1.0, params={})), "my_term")
-  bad(lambda d: d["terminations"].update(x=dict(func="root_height_below_minimum", time_out=False, params={})), "root_height_below_minimum")
+  bad(lambda d: d["terminations"].update(x=dict(func="my_termination", time_out=False, params={})), "my_termination")
+  bad(lambda d: d["terminations"].update(x=dict(func="nan_detection", time_out=True, params={})), "time_out=True")
+  bad(lambda d: d["rewards"].update(jv=dict(func="joint_vel_l2", weight=-1.0, params={"asset_cfg": {"name": "robot", "joint_names": (".*_knee_joint",)}})),
+      "all actuated joints")
   bad(lambda d: d["observations"]["policy"]["terms"].pop("joint_vel"), "differ from the kernel's layout")
   bad(lambda d: d["observations"]["critic"].update(enable_corruption=True), "critic.enable_corruption")
   bad(lambda d: d["events"].update(x=dict(func="apply_external_force_torque", mode="reset", params={}, interval_range_s=None)), "apply_external_force_torque")
@@ -99,8 +102,16 @@ def test_reweighted_and_removed_terms_are_consumed():
   d["observations"]["policy"]["terms"]["joint_vel"]["noise"]["n_max"] = 2.5
   d["observations"]["policy"]["terms"]["base_ang_vel"]["delay_max_lag"] = 2
   d["observations"]["critic"]["history_length"] = 3
+  # terms of the generic library (envs/mdp/rewards.py, terminations.py) that the shipped tasks do not use
+  d["rewards"]["alive"] = dict(func="is_alive", weight=0.25, params={})
+  d["rewards"]["torques"] = dict(func="joint_torques_l2", weight=-2e-4, params={"asset_cfg": {"name": "robot", "joint_names": None, "body_names": None}})
+  d["rewards"]["act_acc"] = dict(func="action_acc_l2", weight=-0.01, params={})
+  d["terminations"]["too_low"] = dict(func="root_height_below_minimum", time_out=False, params={"minimum_height": 0.17})
+  d["terminations"]["nans"] = dict(func="nan_detection", time_out=False, params={})
   c = envcfg.from_manager_cfg(d, m, "go1")
   k = envcfg.REWARD_NAMES.index
+  assert c.reward_weights[k("is_alive")] == 0.25 and c.reward_weights[k("joint_torques_l2")] == -2e-4 and c.reward_weights[k("action_acc_l2")] == -0.01
+  assert c.reward_weights[k("joint_acc_l2")] == 0.0 and c.min_root_height == 0.17 and c.nan_termination
   assert c.reward_weights[k("foot_slip")] == -0.7 and c.reward_weights[k("soft_landing")] == 0.0 and c.std_lin == 0.3
   assert not c.push_enabled and c.noise_hi[9 + c.nj] == 2.5 and c.noise_lo[9 + c.nj] == -1.5
   post = c.extra["obs_post"]
