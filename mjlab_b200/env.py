@@ -257,10 +257,30 @@ class _ObservationManager:
     nj, nf = env.vcfg.nj, env.vcfg.nfeet
     pol = [("base_lin_vel", 3), ("base_ang_vel", 3), ("projected_gravity", 3), ("joint_pos", nj), ("joint_vel", nj), ("actions", nj), ("command", 3)]
     cri = pol + [("foot_height", nf), ("foot_air_time", nf), ("foot_contact", nf), ("foot_contact_forces", 3 * nf)]
-    self.active_terms = {"policy": [n for n, _ in pol], "critic": [n for n, _ in cri]}
-    self.group_obs_term_dim = {"policy": [(d,) for _, d in pol], "critic": [(d,) for _, d in cri]}
-    self.group_obs_dim = {"policy": (env.vcfg.n_obs_policy,), "critic": (env.vcfg.n_obs_critic,)}
-    self.group_obs_concatenate = {"policy": True, "critic": True}
+    self._fixed = {"policy": pol, "critic": cri}
+
+  # group / term tables: the kernel's two groups, or - with a post-processing / gathering pipeline (a consumed cfg with its own
+  # groups, history, ...) - what the pipeline emits (observation_manager.py `active_terms`, `group_obs_term_dim`, `group_obs_dim`)
+  @property
+  def active_terms(self) -> dict[str, list[str]]:
+    p = self._env._obs_pipeline
+    return {g: [t["name"] for t in ts] for g, ts in p.groups.items()} if p is not None else {g: [n for n, _ in ts] for g, ts in self._fixed.items()}
+
+  @property
+  def group_obs_term_dim(self) -> dict[str, list[tuple]]:
+    p = self._env._obs_pipeline
+    return {g: p.term_dims(g) for g in p.groups} if p is not None else {g: [(d,) for _, d in ts] for g, ts in self._fixed.items()}
+
+  @property
+  def group_obs_dim(self) -> dict[str, tuple]:
+    out = {}
+    for g, dims in self.group_obs_term_dim.items():
+      out[g] = (sum(int(torch.tensor(d).prod()) for d in dims),) if all(len(d) == 1 for d in dims) else tuple(dims)
+    return out
+
+  @property
+  def group_obs_concatenate(self) -> dict[str, bool]:
+    return {g: True for g in self.active_terms}
 
   def compute(self, update_history: bool = False) -> dict[str, torch.Tensor]:
     """The buffers of the last `step` / `reset` (the reference returns its cached dict unless update_history is set, :160-161)."""
@@ -287,11 +307,12 @@ class ManagerBasedRlEnv:
     if cfg.manager_cfg is not None:
       self.vcfg = envcfg.from_manager_cfg(cfg.manager_cfg, model, cfg.robot)
       ex = self.vcfg.extra
-      cfg.foot_friction_range = tuple(ex["foot_friction"]["ranges"]) if ex["foot_friction"] else None
+      cfg.foot_friction_range = None          # the cfg's own startup events are applied below, whatever field they randomise
       cfg.velocity_stages = tuple(ex["velocity_stages"])
       post = [t for g in ex["obs_post"].values() for t in g]
-      if any(t["clip"] or t["scale"] is not None or t["delay_max_lag"] > 0 or t["history_length"] > 0 for t in post):
+      if ex["obs_custom"] or any(t["clip"] or t["scale"] is not None or t["delay_max_lag"] > 0 or t["history_length"] > 0 for t in post):
         self._want_obs_pipeline = ex["obs_post"]
+        self._obs_layout = ex["obs_layout"]
     self.vcfg.seed = int(cfg.seed)
     self.vcfg.decimation = cfg.decimation
     self.vcfg.step_dt = cfg.decimation * cfg.sim.mujoco.timestep
@@ -350,7 +371,8 @@ class ManagerBasedRlEnv:
       nj, nf = self.vcfg.nj, self.vcfg.nfeet
       pol = [("base_lin_vel", 3), ("base_ang_vel", 3), ("projected_gravity", 3), ("joint_pos", nj), ("joint_vel", nj), ("actions", nj), ("command", 3)]
       cri = pol + [("foot_height", nf), ("foot_air_time", nf), ("foot_contact", nf), ("foot_contact_forces", 3 * nf)]
-      self._obs_pipeline = ObservationPipeline({"policy": pol, "critic": cri}, self._want_obs_pipeline, n, device)
+      layout = getattr(self, "_obs_layout", None) or {"policy": pol, "critic": cri}   # a consumed cfg: its own groups, gathered from the bank
+      self._obs_pipeline = ObservationPipeline(layout, self._want_obs_pipeline, n, device)
     self.reward_buf = self._buf["reward"]
     self.reset_buf = self._buf["reset_buf"].view(torch.bool)
     self.reset_terminated = self._buf["terminated"].view(torch.bool)
@@ -362,6 +384,16 @@ class ManagerBasedRlEnv:
       self.sim.expand_model_fields(("geom_friction",))
       names = self._foot_geom_names()
       randomize_field(self, None, "geom_friction", cfg.foot_friction_range, operation="abs", geom_names=names)
+
+    for ev in self.vcfg.extra.get("startup_dr", []):   # a consumed ManagerBasedRlEnvCfg: its startup randomize_field events, in order
+      from .events import FIELD_SPECS, randomize_field
+      from .managers import SceneEntityCfg
+      if ev["field"] not in FIELD_SPECS:
+        raise envcfg.UnsupportedTermError(f"startup event '{ev['name']}': randomize_field does not know the field '{ev['field']}'")
+      ac = SceneEntityCfg(**{k: v for k, v in ev["asset_cfg"].items() if v is not None})
+      ac.resolve(self.scene)
+      self.sim.expand_model_fields((ev["field"],))
+      randomize_field(self, None, ev["field"], ev["ranges"], ev["distribution"], ev["operation"], asset_cfg=ac, axes=ev["axes"])
 
     if cfg.manager_cfg is None and cfg.play and cfg.robot == "g1" and cfg.terrain == "flat":  # config/g1/env_cfgs.py:167-173: the FLAT play cfg only (pinned by tests/test_task_cfg.py)
       self.vcfg.cmd_lin_x, self.vcfg.cmd_ang_z = (-1.5, 2.0), (-0.7, 0.7)

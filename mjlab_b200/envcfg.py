@@ -508,40 +508,72 @@ def from_manager_cfg(cfg, m, robot: str) -> VelocityCfg:
   if ("illegal_contact" in tf) != (c.illegal_count > 0):
     raise UnsupportedTermError("illegal_contact needs the scene's nonfoot_ground_touch sensor (and the compiled Go1 scene always has it)")
   # ---- observations -------------------------------------------------------------------------------------------------------
+  # The kernel writes a fixed term bank: the seven policy terms (with the policy group's noise) and a clean copy of them followed
+  # by the four foot terms (the critic group).  Any group of the cfg - any name, any subset, any order - is a gather of bank
+  # segments (`extra["obs_layout"]`, applied by obs_pipeline.ObservationPipeline together with clip / scale / delay / history);
+  # a term with noise comes from the noisy copy, one without from the clean copy.
   obs = d["observations"]
-  if set(obs) != {"policy", "critic"}:
-    raise UnsupportedTermError(f"observation groups {sorted(obs)}: the kernels write 'policy' and 'critic'")
-  post = {}
-  for group, want in (("policy", POLICY_OBS_TERMS), ("critic", POLICY_OBS_TERMS + CRITIC_EXTRA_OBS_TERMS)):
-    g = obs[group]
-    terms = [(n, t) for n, t in g["terms"].items() if t is not None]
-    got = tuple((t["func"], t["params"].get("sensor_name") if t["func"] == "builtin_sensor" else None) for _, t in terms)
-    if got != want:
-      raise UnsupportedTermError(f"observation group '{group}': terms {got} differ from the kernel's layout {want}")
+  nj, nf = c.nj, c.nfeet
+  bank_p = {f: (o, w) for f, o, w in zip(POLICY_OBS_TERMS, (0, 3, 6, 9, 9 + nj, 9 + 2 * nj, 9 + 3 * nj), (3, 3, 3, nj, nj, nj, 3))}
+  bank_e = {f: (o, w) for f, o, w in zip(CRITIC_EXTRA_OBS_TERMS, (12 + 3 * nj, 12 + 3 * nj + nf, 12 + 3 * nj + 2 * nf, 12 + 3 * nj + 3 * nf),
+                                         (nf, nf, nf, 3 * nf))}
+  lo, hi = np.zeros(c.n_obs_policy), np.zeros(c.n_obs_policy)
+  noise_of: dict = {}
+  ranges_of: dict = {}
+  post, layout = {}, {}
+  for group, g in obs.items():
+    if g is None:
+      continue
     if not g["concatenate_terms"]:
       raise UnsupportedTermError("concatenate_terms=False")
-    post[group] = []
-    for n, t in terms:
+    post[group], layout[group] = [], []
+    for n, t in g["terms"].items():
+      if t is None:
+        continue
+      key = (t["func"], t["params"].get("sensor_name") if t["func"] == "builtin_sensor" else None)
+      if key not in bank_p and key not in bank_e:
+        raise UnsupportedTermError(f"observation term '{n}' ({key[0]}{', ' + str(key[1]) if key[1] else ''}) is not in the env kernels' term bank "
+                                   f"{[k[1] or k[0] for k in POLICY_OBS_TERMS + CRITIC_EXTRA_OBS_TERMS]}")
+      nz = t["noise"]
+      if nz is not None:
+        if nz.get("__type__") != "UniformNoiseCfg" or nz.get("operation") != "add":
+          raise UnsupportedTermError(f"observation term '{n}': noise {nz} (only additive UniformNoiseCfg is implemented)")
+        if key not in bank_p:
+          raise UnsupportedTermError(f"observation term '{n}': the foot terms of the kernels' bank carry no noise")
+        rng = (float(nz["n_min"]), float(nz["n_max"]))
+        if g["enable_corruption"]:
+          if noise_of.setdefault(key, rng) != rng:
+            raise UnsupportedTermError(f"observation term '{n}': one noise range per term function ({noise_of[key]} vs {rng})")
+          ranges_of[key] = rng
+        else:
+          ranges_of.setdefault(key, rng)     # kept in the table while no corrupted group says otherwise (the reference keeps the term's cfg too)
+      if nz is not None and g["enable_corruption"]:
+        o, w = bank_p[key]
+        src = ("policy", o, w)
+      else:
+        o, w = bank_p[key] if key in bank_p else bank_e[key]
+        src = ("critic", o, w)
+      layout[group].append((n, w, src[0], src[1]))
       e = {k: t[k] for k in _POST_KEYS}
       if g.get("history_length") is not None:
         e["history_length"], e["flatten_history_dim"] = g["history_length"], g["flatten_history_dim"]
       e["name"] = n
       post[group].append(e)
-  if obs["critic"]["enable_corruption"]:
-    raise UnsupportedTermError("critic.enable_corruption=True: the kernels only corrupt the policy group")
-  c.enable_corruption = bool(obs["policy"]["enable_corruption"])
-  nj = c.nj
-  seg = [(0, 3), (3, 6), (6, 9), (9, 9 + nj), (9 + nj, 9 + 2 * nj), (9 + 2 * nj, 9 + 3 * nj), (9 + 3 * nj, 12 + 3 * nj)]
-  lo, hi = np.zeros(c.n_obs_policy), np.zeros(c.n_obs_policy)
-  for (a, b), (n, t) in zip(seg, [(n, t) for n, t in obs["policy"]["terms"].items() if t is not None]):
-    nz = t["noise"]
-    if nz is None:
-      continue
-    if nz.get("__type__") != "UniformNoiseCfg" or nz.get("operation") != "add":
-      raise UnsupportedTermError(f"observation term '{n}': noise {nz} (only additive UniformNoiseCfg is implemented)")
-    lo[a:b], hi[a:b] = float(nz["n_min"]), float(nz["n_max"])
+  for key, rng in ranges_of.items():
+    o, w = bank_p[key]
+    lo[o:o + w], hi[o:o + w] = noise_of.get(key, rng)
+  if "policy" not in layout or "critic" not in layout:
+    raise UnsupportedTermError(f"observation groups {sorted(layout)}: 'policy' and 'critic' are required (rsl_rl's actor / critic inputs)")
+  c.enable_corruption = bool(noise_of)
   c.noise_lo, c.noise_hi = lo, hi
   c.extra["obs_post"] = post
+  c.extra["obs_layout"] = layout
+  default = {"policy": [(o, w, "policy") for o, w in bank_p.values()],
+             "critic": [(o, w, "critic") for o, w in list(bank_p.values()) + list(bank_e.values())]}
+  got = {g: [(o, w, sg) for _, w, sg, o in terms] for g, terms in layout.items()}
+  # the kernel's own two groups, as they are: nothing to gather (a clean-copy source is the same data when the term has no noise)
+  c.extra["obs_custom"] = set(got) != {"policy", "critic"} or any(
+    [(o, w) for o, w, _ in got[g]] != [(o, w) for o, w, _ in default[g]] for g in ("policy", "critic"))
   # ---- actions ----------------------------------------------------------------------------------------------------------------
   acts = [a for a in d["actions"].values() if a is not None]
   if len(acts) != 1 or acts[0]["class_type"] != "JointPositionAction" or not acts[0]["use_default_offset"] or acts[0]["clip"]:
@@ -564,9 +596,16 @@ def from_manager_cfg(cfg, m, robot: str) -> VelocityCfg:
       c.push_enabled, c.push_interval = True, tuple(map(float, e["interval_range_s"]))
       c.push_velocity_range = _range6(p["velocity_range"])
     elif f == "randomize_field" and e["mode"] == "startup":
-      if p["field"] != "geom_friction" or p["operation"] != "abs":
-        raise UnsupportedTermError(f"startup event '{name}': randomize_field({p['field']}, {p['operation']}) - call events.randomize_field yourself")
-      c.extra["foot_friction"] = dict(ranges=tuple(map(float, p["ranges"])), geom_names=tuple(p["asset_cfg"]["geom_names"]))
+      # applied once by the env after construction through events.randomize_field (any field of its FIELD_SPECS), in cfg order
+      rg = p["ranges"]
+      rg = {int(k): tuple(map(float, v)) for k, v in rg.items()} if isinstance(rg, dict) else tuple(map(float, rg))
+      ac = p.get("asset_cfg") or {"name": "robot"}
+      c.extra.setdefault("startup_dr", []).append(dict(
+        name=name, field=p["field"], ranges=rg, distribution=p.get("distribution", "uniform"), operation=p.get("operation", "abs"),
+        axes=list(p["axes"]) if p.get("axes") is not None else None,
+        asset_cfg={k: (tuple(ac[k]) if isinstance(ac.get(k), (list, tuple)) else ac.get(k)) for k in ("name", "geom_names", "body_names", "joint_names", "site_names")}))
+      if p["field"] == "geom_friction" and p.get("operation", "abs") == "abs" and not isinstance(rg, dict):
+        c.extra["foot_friction"] = dict(ranges=rg, geom_names=tuple(ac["geom_names"]))   # (kept for the task-table tests)
     elif f == "randomize_terrain" and e["mode"] == "reset":
       terrain_mode |= 2
     else:

@@ -18,7 +18,7 @@ from .buffers import CircularBuffer
 
 class ObservationPipeline:
   def __init__(self, layout: dict[str, list[tuple[str, int]]], post: dict[str, list[dict]], num_envs: int, device: str):
-    """layout: group -> [(term name, width)] in the kernel's order; post: group -> per-term settings (`envcfg.from_manager_cfg`
+    """layout: group -> [(term name, width)] in the kernel's order, or [(term name, width, source group, offset)]; post: group -> per-term settings (`envcfg.from_manager_cfg`
     `extra["obs_post"]`: clip, scale, delay_*, history_length, flatten_history_dim)."""
     from .actuators import DelayBuffer
     self.num_envs, self.device = num_envs, device
@@ -26,8 +26,12 @@ class ObservationPipeline:
     for g, terms in layout.items():
       o, out = 0, []
       assert len(terms) == len(post[g]), (g, len(terms), len(post[g]))
-      for (name, dim), p in zip(terms, post[g]):
-        t = dict(name=name, sl=slice(o, o + dim), dim=dim, clip=tuple(p["clip"]) if p.get("clip") else None, scale=None, delay=None,
+      for entry, p in zip(terms, post[g]):
+        # (name, width): the next `width` columns of the kernel's group g; (name, width, source group, offset): a gather from the
+        # kernel's term bank (envcfg.from_manager_cfg `extra["obs_layout"]`: any subset / order / group name)
+        name, dim = entry[0], entry[1]
+        src, off = (entry[2], entry[3]) if len(entry) == 4 else (g, o)
+        t = dict(name=name, src=src, sl=slice(off, off + dim), dim=dim, clip=tuple(p["clip"]) if p.get("clip") else None, scale=None, delay=None,
                  history=None, flatten=bool(p.get("flatten_history_dim", True)))
         if p.get("scale") is not None:
           t["scale"] = torch.as_tensor(p["scale"], dtype=torch.float32, device=device)
@@ -68,7 +72,7 @@ class ObservationPipeline:
     for g, terms in self.groups.items():
       parts = []
       for t in terms:
-        obs = raw[g][:, t["sl"]].clone()
+        obs = raw[t["src"]][:, t["sl"]].clone()
         if t["clip"] is not None:
           obs = obs.clip_(min=t["clip"][0], max=t["clip"][1])
         if t["scale"] is not None:

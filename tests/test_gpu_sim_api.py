@@ -424,7 +424,21 @@ def test_env_consumes_edited_manager_cfg_with_history_and_delay():
   d["observations"]["policy"]["enable_corruption"] = False
   d["observations"]["policy"]["terms"]["base_ang_vel"].update(delay_min_lag=2, delay_max_lag=2)
   d["observations"]["policy"]["terms"]["joint_vel"].update(clip=[-1.0, 1.0], scale=0.5)
+  # two more startup domain-randomisation events (any field of randomize_field, events.py:292-354): trunk mass scaled, hip damping set
+  ev = lambda field, ranges, op, **names: dict(func="randomize_field", mode="startup", interval_range_s=None, params=dict(  # noqa: E731
+    field=field, ranges=ranges, operation=op, asset_cfg=dict(name="robot", **names)))
+  d["events"]["trunk_mass"] = ev("body_mass", [0.8, 1.2], "scale", body_names=["trunk"])
+  d["events"]["hip_damping"] = ev("dof_damping", [0.5, 1.5], "abs", joint_names=[".*_hip_joint"])
   env = ManagerBasedRlEnv(VelocityEnvCfg.from_manager_cfg(d, "go1", "flat", num_envs=32, seed=2), DEV)
+  mj = env.sim.mj_model
+  trunk = [i for i, n in enumerate(mj.body_names) if n.endswith("trunk")][0]
+  ratio = env.sim.model.body_mass[:, trunk] / float(mj.body_mass[trunk])
+  assert ratio.shape == (32,) and float(ratio.min()) >= 0.8 and float(ratio.max()) <= 1.2 and float(ratio.std()) > 0.02
+  hips = [int(mj.jnt_dofadr[i]) for i, n in enumerate(mj.jnt_names) if n.endswith("_hip_joint")]
+  dmp = env.sim.model.dof_damping[:, hips]
+  assert dmp.shape == (32, 4) and float(dmp.min()) >= 0.5 and float(dmp.max()) <= 1.5 and float(dmp.std()) > 0.05
+  fr = env.sim.model.geom_friction[:, [i for i, n in enumerate(mj.geom_names) if n.endswith("_foot_collision")], 0]
+  assert float(fr.min()) >= 0.3 and float(fr.max()) <= 1.2 and float(fr.std()) > 0.05        # the cfg's own foot_friction event
   k = envcfg.REWARD_NAMES.index
   assert env.vcfg.reward_weights[k("foot_slip")] == -0.7 and env.vcfg.reward_weights[k("soft_landing")] == 0 and not env.vcfg.push_enabled
   obs, _ = env.reset()
@@ -451,3 +465,31 @@ def test_env_consumes_edited_manager_cfg_with_history_and_delay():
   with pytest.raises(envcfg.UnsupportedTermError):
     d["rewards"]["x"] = dict(func="electrical_power_cost", weight=-1.0, params={})
     ManagerBasedRlEnv(VelocityEnvCfg.from_manager_cfg(d, "go1", "flat", num_envs=8), DEV)
+
+
+def test_env_consumes_custom_observation_groups():
+  """Observation groups of a consumed cfg are gathers from the kernels' term bank: the usual sim-to-real edit (no base linear
+  velocity for the policy), a reordered group and an extra group; noisy terms come from the corrupted copy, the others clean."""
+  from mjlab_b200.env import ManagerBasedRlEnv, VelocityEnvCfg
+  d = _task_cfg("Mjlab-Velocity-Flat-Unitree-Go1")
+  pt = d["observations"]["policy"]["terms"]
+  pt.pop("base_lin_vel")
+  d["observations"]["policy"]["terms"] = {"command": pt["command"], **{k: v for k, v in pt.items() if k != "command"}}
+  d["observations"]["feet"] = dict(d["observations"]["critic"], terms={k: d["observations"]["critic"]["terms"][k] for k in ("foot_contact", "foot_height")})
+  env = ManagerBasedRlEnv(VelocityEnvCfg.from_manager_cfg(d, "go1", "flat", num_envs=48, seed=4), DEV)
+  nj, nf = env.vcfg.nj, env.vcfg.nfeet
+  om = env.observation_manager
+  assert om.active_terms["policy"] == ["command", "base_ang_vel", "projected_gravity", "joint_pos", "joint_vel", "actions"]
+  assert om.group_obs_dim == {"policy": (9 + 3 * nj,), "critic": (12 + 3 * nj + 6 * nf,), "feet": (2 * nf,)}
+  obs, _ = env.reset()
+  g = torch.Generator(device=DEV).manual_seed(0)
+  for _ in range(5):
+    obs, rew, term, trunc, _ = env.step(torch.rand(48, nj, device=DEV, generator=g) * 2 - 1)
+    raw_p, raw_c = env._raw_obs["policy"], env._raw_obs["critic"]
+    assert obs["policy"].shape == (48, 9 + 3 * nj) and obs["feet"].shape == (48, 2 * nf) and obs["critic"].shape == raw_c.shape
+    torch.testing.assert_close(obs["policy"][:, 0:3], raw_c[:, 9 + 3 * nj: 12 + 3 * nj])           # command: no noise, clean copy
+    torch.testing.assert_close(obs["policy"][:, 3:6], raw_p[:, 3:6])                               # noisy imu angular velocity
+    torch.testing.assert_close(obs["policy"][:, 9: 9 + nj], raw_p[:, 9: 9 + nj])                   # noisy joint positions
+    assert float((raw_p[:, 3:6] - raw_c[:, 3:6]).abs().max()) > 1e-3                               # (the two copies do differ)
+    torch.testing.assert_close(obs["feet"], torch.cat([raw_c[:, 12 + 3 * nj + 2 * nf: 12 + 3 * nj + 3 * nf], raw_c[:, 12 + 3 * nj: 12 + 3 * nj + nf]], 1))
+    torch.testing.assert_close(obs["critic"], raw_c)

@@ -84,8 +84,13 @@ def test_unsupported_terms_raise():
   bad(lambda d: d["terminations"].update(x=dict(func="nan_detection", time_out=True, params={})), "time_out=True")
   bad(lambda d: d["rewards"].update(jv=dict(func="joint_vel_l2", weight=-1.0, params={"asset_cfg": {"name": "robot", "joint_names": (".*_knee_joint",)}})),
       "all actuated joints")
-  bad(lambda d: d["observations"]["policy"]["terms"].pop("joint_vel"), "differ from the kernel's layout")
-  bad(lambda d: d["observations"]["critic"].update(enable_corruption=True), "critic.enable_corruption")
+  bad(lambda d: d["observations"]["policy"]["terms"].update(h=dict(d["observations"]["policy"]["terms"]["joint_vel"], func="base_lin_vel", params={})),
+      "term bank")
+  bad(lambda d: d["observations"].pop("critic"), "'policy' and 'critic' are required")
+  bad(lambda d: (d["observations"]["critic"].update(enable_corruption=True),
+                 d["observations"]["critic"]["terms"]["joint_vel"]["noise"].update(n_max=9.0)), "one noise range per term function")
+  bad(lambda d: d["observations"]["critic"]["terms"]["foot_height"].update(noise=dict(__type__="UniformNoiseCfg", operation="add", n_min=-1, n_max=1)),
+      "carry no noise")
   bad(lambda d: d["events"].update(x=dict(func="apply_external_force_torque", mode="reset", params={}, interval_range_s=None)), "apply_external_force_torque")
   bad(lambda d: d["commands"]["twist"].update(init_velocity_prob=0.5), "init_velocity_prob")
   bad(lambda d: d["sim"]["mujoco"].update(solver="cg"), "supported subset")
@@ -108,11 +113,21 @@ def test_reweighted_and_removed_terms_are_consumed():
   d["rewards"]["act_acc"] = dict(func="action_acc_l2", weight=-0.01, params={})
   d["terminations"]["too_low"] = dict(func="root_height_below_minimum", time_out=False, params={"minimum_height": 0.17})
   d["terminations"]["nans"] = dict(func="nan_detection", time_out=False, params={})
+  # observation groups are gathers from the kernels' term bank: drop a policy term (the usual sim-to-real edit), reorder, add a group
+  pt = d["observations"]["policy"]["terms"]
+  pt.pop("base_lin_vel")
+  d["observations"]["policy"]["terms"] = {"command": pt["command"], **{k2: v for k2, v in pt.items() if k2 != "command"}}
+  d["observations"]["feet"] = dict(d["observations"]["critic"], terms={k2: d["observations"]["critic"]["terms"][k2] for k2 in ("foot_contact", "foot_height")})
   c = envcfg.from_manager_cfg(d, m, "go1")
   k = envcfg.REWARD_NAMES.index
+  lay = c.extra["obs_layout"]
+  assert c.extra["obs_custom"] and [t[0] for t in lay["policy"]] == ["command", "base_ang_vel", "projected_gravity", "joint_pos", "joint_vel", "actions"]
+  assert lay["policy"][0][1:] == (3, "critic", 9 + 3 * c.nj)          # no noise on the command: the clean copy
+  assert lay["policy"][1][1:] == (3, "policy", 3)                     # noisy imu_ang_vel
+  assert [t[0] for t in lay["feet"]] == ["foot_contact", "foot_height"] and lay["feet"][0][2:] == ("critic", 12 + 3 * c.nj + 2 * c.nfeet)
   assert c.reward_weights[k("is_alive")] == 0.25 and c.reward_weights[k("joint_torques_l2")] == -2e-4 and c.reward_weights[k("action_acc_l2")] == -0.01
   assert c.reward_weights[k("joint_acc_l2")] == 0.0 and c.min_root_height == 0.17 and c.nan_termination
   assert c.reward_weights[k("foot_slip")] == -0.7 and c.reward_weights[k("soft_landing")] == 0.0 and c.std_lin == 0.3
   assert not c.push_enabled and c.noise_hi[9 + c.nj] == 2.5 and c.noise_lo[9 + c.nj] == -1.5
   post = c.extra["obs_post"]
-  assert post["policy"][1]["delay_max_lag"] == 2 and all(t["history_length"] == 3 for t in post["critic"])
+  assert {t["name"]: t for t in post["policy"]}["base_ang_vel"]["delay_max_lag"] == 2 and all(t["history_length"] == 3 for t in post["critic"])
