@@ -360,6 +360,7 @@ class TrackingCfg:
   enable_corruption: bool = True
   push_enabled: bool = True
   seed: int = 0
+  extra: dict = field(default_factory=dict)   # what the kernels do not consume themselves (startup events, sim options)
 
 
 def tracking_cfg(m, time_step_total: int, robot: str = "g1", play: bool = False, tracked=G1_TRACKED_BODIES, anchor="torso_link", ee=G1_EE_BODIES) -> TrackingCfg:
@@ -643,4 +644,147 @@ def from_manager_cfg(cfg, m, robot: str) -> VelocityCfg:
   if gen is not None:
     c.terrain_half_size = float(gen["size"][0]) / 2.0
     c.max_init_terrain_level = int(d["scene"]["terrain"]["max_init_terrain_level"])
+  return c
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the tracking task from a reference ManagerBasedRlEnvCfg (tasks/tracking/tracking_env_cfg.py)
+# ---------------------------------------------------------------------------------------------------------
+TRACKING_REWARD_FUNCS = {
+  "motion_global_root_pos": "motion_global_anchor_position_error_exp", "motion_global_root_ori": "motion_global_anchor_orientation_error_exp",
+  "motion_body_pos": "motion_relative_body_position_error_exp", "motion_body_ori": "motion_relative_body_orientation_error_exp",
+  "motion_body_lin_vel": "motion_global_body_linear_velocity_error_exp", "motion_body_ang_vel": "motion_global_body_angular_velocity_error_exp",
+  "action_rate_l2": "action_rate_l2", "joint_limit": "joint_pos_limits", "self_collisions": "self_collision_cost",
+}
+_TRACKING_STD = {"motion_global_root_pos": "std_anchor_pos", "motion_global_root_ori": "std_anchor_ori", "motion_body_pos": "std_body_pos",
+                 "motion_body_ori": "std_body_ori", "motion_body_lin_vel": "std_body_lin_vel", "motion_body_ang_vel": "std_body_ang_vel"}
+_TRACKING_POLICY_OBS = (("generated_commands", None), ("motion_anchor_pos_b", None), ("motion_anchor_ori_b", None), ("builtin_sensor", "robot/imu_lin_vel"),
+                        ("builtin_sensor", "robot/imu_ang_vel"), ("joint_pos_rel", None), ("joint_vel_rel", None), ("last_action", None))
+_TRACKING_CRITIC_OBS = _TRACKING_POLICY_OBS[:3] + (("robot_body_pos_b", None), ("robot_body_ori_b", None)) + _TRACKING_POLICY_OBS[3:]
+
+
+def tracking_from_manager_cfg(cfg, m, time_step_total: int, robot: str = "g1") -> TrackingCfg:
+  """Resolve a reference `ManagerBasedRlEnvCfg` of the tracking task (live dataclass or `cfg_to_dict` view) into the tracking
+  kernels' `TrackingCfg`: reward weights / stds by term FUNCTION, termination thresholds and end-effector bodies, the
+  MotionCommand's bodies, anchor, reset ranges and sampling parameters, observation noise, action scale, push event, episode
+  length.  Startup events come back in `extra["startup_dr"]` / `extra["encoder_bias_range"]` for the env to apply.  The
+  observation layout is the kernel's fixed one; anything the kernels do not implement raises `UnsupportedTermError`."""
+  d = cfg if isinstance(cfg, dict) else cfg_to_dict(cfg)
+  cmds = [t for t in d["commands"].values() if t is not None]
+  if len(cmds) != 1 or cmds[0]["class_type"] != "MotionCommand":
+    raise UnsupportedTermError("commands: one MotionCommand is implemented")
+  mc = cmds[0]
+  ee_t = [t for t in d["terminations"].values() if t is not None and t["func"] == "bad_motion_body_pos_z_only"]
+  ee = tuple(ee_t[0]["params"]["body_names"]) if ee_t else G1_EE_BODIES
+  c = tracking_cfg(m, time_step_total, robot, play=False, tracked=tuple(mc["body_names"]), anchor=mc["anchor_body_name"], ee=ee)
+  pre = "robot/"
+  local_names = [n.removeprefix(pre) for n in velocity_cfg(m, robot).joint_names]
+  mj = d["sim"]["mujoco"]
+  if mj["solver"] != "newton" or mj["cone"] != "pyramidal" or mj["integrator"] not in ("implicitfast", "euler"):
+    raise UnsupportedTermError(f"sim options {mj['solver']} / {mj['cone']} / {mj['integrator']} are outside the supported subset")
+  c.step_dt = float(mj["timestep"]) * int(d["decimation"])
+  c.max_episode_length_s = float(d["episode_length_s"])
+  c.max_episode_length = math.ceil(c.max_episode_length_s / c.step_dt)
+  c.bin_count = int(time_step_total // (1 / c.step_dt)) + 1
+  c.extra = {"decimation": int(d["decimation"]),
+             "sim": dict(timestep=float(mj["timestep"]), iterations=int(mj["iterations"]), ls_iterations=int(mj["ls_iterations"]),
+                         integrator=mj["integrator"], nconmax=d["sim"]["nconmax"], njmax=d["sim"]["njmax"])}
+  # ---- rewards ----
+  by_func = {}
+  for name, t in d["rewards"].items():
+    if t is None:
+      continue
+    if t["func"] in by_func:
+      raise UnsupportedTermError(f"reward function '{t['func']}' appears twice")
+    by_func[t["func"]] = (name, t)
+  unknown = set(by_func) - set(TRACKING_REWARD_FUNCS.values())
+  if unknown:
+    raise UnsupportedTermError(f"reward terms {sorted(by_func[f][0] for f in unknown)} ({sorted(unknown)}) are not implemented by the tracking kernels")
+  w = np.zeros(len(TRACKING_REWARD_NAMES))
+  for k, slot in enumerate(TRACKING_REWARD_NAMES):
+    if TRACKING_REWARD_FUNCS[slot] in by_func:
+      _, t = by_func[TRACKING_REWARD_FUNCS[slot]]
+      w[k] = float(t["weight"])
+      if slot in _TRACKING_STD:
+        setattr(c, _TRACKING_STD[slot], float(t["params"]["std"]))
+  if w[TRACKING_REWARD_NAMES.index("self_collisions")] != 0 and c.selfcol_adr < 0:
+    raise UnsupportedTermError("self_collision_cost needs the scene's self_collision sensor")
+  c.reward_weights = w
+  # ---- terminations ----
+  tf = {t["func"]: t for t in d["terminations"].values() if t is not None}
+  bad = set(tf) - {"time_out", "bad_anchor_pos_z_only", "bad_anchor_ori", "bad_motion_body_pos_z_only"}
+  if bad:
+    raise UnsupportedTermError(f"termination functions {sorted(bad)} are not implemented by the tracking kernels")
+  if "time_out" not in tf or not tf["time_out"]["time_out"]:
+    raise UnsupportedTermError("the kernels always apply the time_out truncation")
+  BIG = 1e9   # a threshold no error reaches = term absent
+  c.anchor_pos_threshold = float(tf["bad_anchor_pos_z_only"]["params"]["threshold"]) if "bad_anchor_pos_z_only" in tf else BIG
+  c.anchor_ori_threshold = float(tf["bad_anchor_ori"]["params"]["threshold"]) if "bad_anchor_ori" in tf else BIG
+  c.ee_pos_threshold = float(tf["bad_motion_body_pos_z_only"]["params"]["threshold"]) if "bad_motion_body_pos_z_only" in tf else BIG
+  # ---- command ----
+  r6 = VelocityCfg._ranges6
+  c.pose_range, c.velocity_range = r6(_range6(mc.get("pose_range"))), r6(_range6(mc.get("velocity_range")))
+  c.joint_position_range = tuple(map(float, mc["joint_position_range"]))
+  c.sampling_mode = mc["sampling_mode"]
+  c.adaptive_kernel_size, c.adaptive_lambda = int(mc["adaptive_kernel_size"]), float(mc["adaptive_lambda"])
+  c.adaptive_uniform_ratio, c.adaptive_alpha = float(mc["adaptive_uniform_ratio"]), float(mc["adaptive_alpha"])
+  # ---- observations: the kernel's fixed layout, noise per policy term ----
+  obs = d["observations"]
+  if set(k for k, g in obs.items() if g is not None) != {"policy", "critic"}:
+    raise UnsupportedTermError("tracking observation groups: the kernels write 'policy' and 'critic'")
+  nj = c.nj
+  seg = [(0, 2 * nj), (2 * nj, 2 * nj + 3), (2 * nj + 3, 2 * nj + 9), (2 * nj + 9, 2 * nj + 12), (2 * nj + 12, 2 * nj + 15),
+         (2 * nj + 15, 3 * nj + 15), (3 * nj + 15, 4 * nj + 15), (4 * nj + 15, 5 * nj + 15)]
+  lo, hi = np.zeros(c.n_obs_policy), np.zeros(c.n_obs_policy)
+  for group, want in (("policy", _TRACKING_POLICY_OBS), ("critic", _TRACKING_CRITIC_OBS)):
+    g = obs[group]
+    terms = [(n, t) for n, t in g["terms"].items() if t is not None]
+    got = tuple((t["func"], t["params"].get("sensor_name") if t["func"] == "builtin_sensor" else None) for _, t in terms)
+    if got != want:
+      raise UnsupportedTermError(f"tracking observation group '{group}': terms {got} differ from the kernel's layout {want}")
+    for n, t in terms:
+      if t["clip"] or t["scale"] is not None or t["delay_max_lag"] > 0 or t["history_length"] > 0 or g.get("history_length"):
+        raise UnsupportedTermError(f"tracking observation term '{n}': clip / scale / delay / history are not wired for the tracking env")
+    if group == "policy":
+      for (a, b), (n, t) in zip(seg, terms):
+        nz = t["noise"]
+        if nz is None:
+          continue
+        if nz.get("__type__") != "UniformNoiseCfg" or nz.get("operation") != "add":
+          raise UnsupportedTermError(f"observation term '{n}': noise {nz} (only additive UniformNoiseCfg is implemented)")
+        lo[a:b], hi[a:b] = float(nz["n_min"]), float(nz["n_max"])
+  if obs["critic"]["enable_corruption"]:
+    raise UnsupportedTermError("critic.enable_corruption=True: the tracking kernels only corrupt the policy group")
+  c.enable_corruption = bool(obs["policy"]["enable_corruption"])
+  c.noise_lo, c.noise_hi = lo, hi
+  # ---- actions ----
+  acts = [a for a in d["actions"].values() if a is not None]
+  if len(acts) != 1 or acts[0]["class_type"] != "JointPositionAction" or not acts[0]["use_default_offset"] or acts[0]["clip"]:
+    raise UnsupportedTermError("actions: one JointPositionAction with use_default_offset=True and no clip is implemented")
+  sc = acts[0]["scale"]
+  c.action_scale = _resolve_values({k: float(v) for k, v in sc.items()}, local_names) if isinstance(sc, dict) else np.full(nj, float(sc))
+  # ---- events ----
+  c.push_enabled = False
+  c.extra["startup_dr"], c.extra["encoder_bias_range"] = [], None
+  for name, e in d["events"].items():
+    if e is None:
+      continue
+    f, p = e["func"], e["params"]
+    if f == "push_by_setting_velocity" and e["mode"] == "interval":
+      c.push_enabled, c.push_interval = True, tuple(map(float, e["interval_range_s"]))
+      c.push_vel = r6(_range6(p["velocity_range"]))
+    elif f == "randomize_field" and e["mode"] == "startup":
+      rg = p["ranges"]
+      rg = {int(k): tuple(map(float, v)) for k, v in rg.items()} if isinstance(rg, dict) else tuple(map(float, rg))
+      ac = p.get("asset_cfg") or {"name": "robot"}
+      c.extra["startup_dr"].append(dict(
+        name=name, field=p["field"], ranges=rg, distribution=p.get("distribution", "uniform"), operation=p.get("operation", "abs"),
+        axes=list(p["axes"]) if p.get("axes") is not None else None,
+        asset_cfg={k: (tuple(ac[k]) if isinstance(ac.get(k), (list, tuple)) else ac.get(k)) for k in ("name", "geom_names", "body_names", "joint_names", "site_names")}))
+    elif f == "randomize_encoder_bias" and e["mode"] == "startup":
+      c.extra["encoder_bias_range"] = tuple(map(float, p["bias_range"]))
+    else:
+      raise UnsupportedTermError(f"event '{name}' ({f}, mode {e['mode']}) is not implemented by the tracking kernels")
+  if any(t is not None for t in (d.get("curriculum") or {}).values()):
+    raise UnsupportedTermError("tracking curriculum terms are not implemented")
   return c

@@ -50,6 +50,25 @@ class TrackingEnvCfg:
   forward_mode: Literal["reference", "masked"] = "reference"
   log_metrics: bool = True
   sim: SimulationCfg = field(default_factory=_default_sim_cfg)
+  manager_cfg: Any = None   # a reference ManagerBasedRlEnvCfg of the tracking task (or its cfg_to_dict view): see from_manager_cfg
+
+  @classmethod
+  def from_manager_cfg(cls, cfg, **kw) -> "TrackingEnvCfg":
+    """The tracking env driven by the reference's own configuration object (`load_env_cfg("Mjlab-Tracking-Flat-Unitree-G1")`,
+    edited as usual): reward weights / stds, termination thresholds, MotionCommand bodies and ranges, noise, events, episode
+    length are resolved by `envcfg.tracking_from_manager_cfg`; unsupported terms raise `envcfg.UnsupportedTermError`."""
+    d = cfg if isinstance(cfg, dict) else envcfg.cfg_to_dict(cfg)
+    mj = d["sim"]["mujoco"]
+    sim = _default_sim_cfg()
+    sim.mujoco.timestep, sim.mujoco.iterations, sim.mujoco.ls_iterations = float(mj["timestep"]), int(mj["iterations"]), int(mj["ls_iterations"])
+    sim.mujoco.integrator = mj["integrator"]
+    if d["sim"].get("nconmax"):
+      sim.nconmax = int(d["sim"]["nconmax"])
+    if d["sim"].get("njmax"):
+      sim.njmax = int(d["sim"]["njmax"])
+    mf = [t for t in d["commands"].values() if t is not None][0].get("motion_file") or None
+    kw.setdefault("motion_file", mf)
+    return cls(decimation=int(d["decimation"]), sim=sim, manager_cfg=d, **kw)
 
 
 class TrackingRlEnv:
@@ -68,7 +87,10 @@ class TrackingRlEnv:
     else:
       motion = synthetic_motion(model, cfg.synthetic_frames, device=device)
     self.sim = Simulation(cfg.num_envs, cfg.sim, model, device)
-    self.vcfg = envcfg.tracking_cfg(model, motion["joint_pos"].shape[0], play=cfg.play)
+    if cfg.manager_cfg is not None:
+      self.vcfg = envcfg.tracking_from_manager_cfg(cfg.manager_cfg, model, motion["joint_pos"].shape[0])
+    else:
+      self.vcfg = envcfg.tracking_cfg(model, motion["joint_pos"].shape[0], play=cfg.play)
     self.vcfg.seed = int(cfg.seed)
     if cfg.sampling_mode is not None:
       self.vcfg.sampling_mode = cfg.sampling_mode
@@ -111,7 +133,20 @@ class TrackingRlEnv:
     self.reset_terminated = self._buf["terminated"].view(torch.bool)
     self.reset_time_outs = self._buf["time_outs"].view(torch.bool)
 
-    if cfg.domain_randomization:   # startup events (tracking_env_cfg.py:179-208)
+    if cfg.manager_cfg is not None:   # the cfg's own startup events, in order (any field events.randomize_field knows)
+      from .events import FIELD_SPECS, randomize_field
+      from .managers import SceneEntityCfg
+      for ev in self.vcfg.extra["startup_dr"]:
+        if ev["field"] not in FIELD_SPECS:
+          raise envcfg.UnsupportedTermError(f"startup event '{ev['name']}': randomize_field does not know the field '{ev['field']}'")
+        ac = SceneEntityCfg(**{k: v for k, v in ev["asset_cfg"].items() if v is not None})
+        ac.resolve(self.scene)
+        self.sim.expand_model_fields((ev["field"],))
+        randomize_field(self, None, ev["field"], ev["ranges"], ev["distribution"], ev["operation"], asset_cfg=ac, axes=ev["axes"])
+      br = self.vcfg.extra["encoder_bias_range"]
+      if br is not None:   # randomize_encoder_bias, events.py:709-744
+        self._buf["encoder_bias"][:] = torch.rand(n, self.vcfg.nj, device=dev) * (br[1] - br[0]) + br[0]
+    elif cfg.domain_randomization:   # startup events (tracking_env_cfg.py:179-208)
       from .events import randomize_field
       self.sim.expand_model_fields(("body_ipos", "geom_friction"))
       randomize_field(self, None, "body_ipos", {0: (-0.025, 0.025), 1: (-0.05, 0.05), 2: (-0.05, 0.05)}, operation="add", body_names=("torso_link",))

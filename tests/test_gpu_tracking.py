@@ -180,3 +180,33 @@ def test_tracking_env_full_size():
   ipos = env.sim.model.body_ipos
   tid = env.robot.indexing.body_ids[env.robot.find_bodies("torso_link")[0]]
   assert float(ipos[:, tid, 0].std()) > 0.005 and float(env._buf["encoder_bias"].abs().max()) <= 0.01 + 1e-6
+
+
+def test_tracking_env_from_the_reference_manager_cfg_equals_the_builtin_task():
+  """`TrackingEnvCfg.from_manager_cfg(load_env_cfg("Mjlab-Tracking-Flat-Unitree-G1"))` (the JSON dump of the reference's own cfg
+  object, tests/golden/task_cfg) steps bit-identically to the built-in tracking task, startup events included (same torch seed)."""
+  import json
+  from pathlib import Path
+  from mjlab_b200.tracking_env import TrackingEnvCfg, TrackingRlEnv
+  d = json.loads((Path(__file__).resolve().parent / "golden" / "task_cfg" / "Mjlab-Tracking-Flat-Unitree-G1.json").read_text())
+  B = 48
+  outs = []
+  for cfg in (TrackingEnvCfg(num_envs=B, seed=3), TrackingEnvCfg.from_manager_cfg(d, num_envs=B, seed=3)):
+    torch.manual_seed(11)
+    env = TrackingRlEnv(cfg, DEV)
+    g = torch.Generator(device=DEV).manual_seed(2)
+    env.reset()
+    for _ in range(12):
+      obs, rew, term, trunc, _ = env.step(torch.rand(B, env.vcfg.nj, device=DEV, generator=g) * 2 - 1)
+    outs.append((obs["policy"].clone(), obs["critic"].clone(), rew.clone(), term.clone(), trunc.clone(), env.sim.data.qpos.clone(),
+                 env.sim.model.body_ipos.clone(), env.sim.model.geom_friction.clone(), env._buf["encoder_bias"].clone()))
+    assert env.max_episode_length == 500
+  for x, y in zip(*outs):
+    assert torch.equal(x, y)
+  # an edited cfg: one termination removed, a reward re-weighted
+  d["terminations"].pop("anchor_ori")
+  d["rewards"]["motion_body_pos"]["weight"] = 2.0
+  env = TrackingRlEnv(TrackingEnvCfg.from_manager_cfg(d, num_envs=8, seed=3), DEV)
+  assert env.vcfg.anchor_ori_threshold > 1e8 and env.vcfg.reward_weights[2] == 2.0
+  env.reset()
+  env.step(torch.zeros(8, env.vcfg.nj, device=DEV))

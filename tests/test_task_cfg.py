@@ -131,3 +131,54 @@ def test_reweighted_and_removed_terms_are_consumed():
   assert not c.push_enabled and c.noise_hi[9 + c.nj] == 2.5 and c.noise_lo[9 + c.nj] == -1.5
   post = c.extra["obs_post"]
   assert {t["name"]: t for t in post["policy"]}["base_ang_vel"]["delay_max_lag"] == 2 and all(t["history_length"] == 3 for t in post["critic"])
+
+
+@pytest.mark.parametrize("play", [False, True])
+def test_tracking_cfg_from_the_reference_cfg_equals_the_builtin_table(play):
+  """`envcfg.tracking_from_manager_cfg(load_env_cfg("Mjlab-Tracking-Flat-Unitree-G1", play))` (its JSON dump) resolves to the very
+  table the built-in tracking task uses: weights, stds, thresholds, bodies, ranges, sampling, noise, action scale, push event."""
+  import dataclasses
+  m = mjlab_b200.load_model("g1_flat")
+  d = _load("Mjlab-Tracking-Flat-Unitree-G1", play)
+  got = envcfg.tracking_from_manager_cfg(d, m, 500)
+  want = envcfg.tracking_cfg(m, 500, play=play)
+  for f in dataclasses.fields(want):
+    if f.name == "extra":
+      continue
+    x, y = getattr(want, f.name), getattr(got, f.name)
+    if isinstance(x, (str, type(None))):
+      assert x == y, f.name
+    else:
+      np.testing.assert_array_equal(np.asarray(x), np.asarray(y), err_msg=f.name)
+  assert got.extra["encoder_bias_range"] == (-0.01, 0.01)
+  assert [(e["field"], e["operation"]) for e in got.extra["startup_dr"]] == [("body_ipos", "add"), ("geom_friction", "abs")]
+
+
+def test_tracking_cfg_edits_and_unsupported_terms():
+  m = mjlab_b200.load_model("g1_flat")
+  base = _load("Mjlab-Tracking-Flat-Unitree-G1", False)
+  d = copy.deepcopy(base)
+  d["rewards"]["motion_body_pos"].update(weight=2.0)
+  d["rewards"]["motion_body_pos"]["params"]["std"] = 0.2
+  d["rewards"].pop("self_collisions")
+  d["terminations"].pop("anchor_ori")
+  d["terminations"]["ee_body_pos"]["params"].update(threshold=0.4, body_names=["left_ankle_roll_link", "right_ankle_roll_link"])
+  d["commands"]["motion"].update(sampling_mode="uniform", joint_position_range=[-0.2, 0.2])
+  d["events"].pop("push_robot")
+  d["episode_length_s"] = 6.0
+  c = envcfg.tracking_from_manager_cfg(d, m, 500)
+  k = envcfg.TRACKING_REWARD_NAMES.index
+  assert c.reward_weights[k("motion_body_pos")] == 2.0 and c.std_body_pos == 0.2 and c.reward_weights[k("self_collisions")] == 0.0
+  assert c.anchor_ori_threshold > 1e8 and c.ee_pos_threshold == 0.4 and len(c.ee_sel) == 2
+  assert c.sampling_mode == "uniform" and c.joint_position_range == (-0.2, 0.2) and not c.push_enabled and c.max_episode_length == 300
+
+  def bad(edit, match):
+    x = copy.deepcopy(base)
+    edit(x)
+    with pytest.raises(envcfg.UnsupportedTermError, match=match):
+      envcfg.tracking_from_manager_cfg(x, m, 500)
+
+  bad(lambda x: x["rewards"].update(my=dict(func="my_reward", weight=1.0, params={})), "my")
+  bad(lambda x: x["terminations"].update(t=dict(func="bad_orientation", time_out=False, params={"limit_angle": 1.0})), "bad_orientation")
+  bad(lambda x: x["observations"]["policy"]["terms"].pop("base_lin_vel"), "differ from the kernel's layout")
+  bad(lambda x: x["events"].update(e=dict(func="reset_joints_by_offset", mode="reset", params={}, interval_range_s=None)), "reset_joints_by_offset")
