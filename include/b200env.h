@@ -141,6 +141,7 @@ enum b2e_buf {
   B2E_B_TERMINATED, B2E_B_TIME_OUTS, B2E_B_RESET_BUF,               /* uint8 [1] */
   B2E_B_OBS_POLICY,         /* [n_obs_policy] */
   B2E_B_OBS_CRITIC,         /* [n_obs_critic] */
+  B2E_B_OBS_EXTRA,          /* [6] terms outside the shipped groups, for cfg-built groups: base_lin_vel, base_ang_vel (envs/mdp/observations.py:24-35) */
   B2E_B_LOG_ENV,            /* [B2E_NLOG] per-env contributions to the log means */
   /* scalars on the device */
   B2E_B_LOG,                /* [B2E_NLOG] reduced over envs by b2_env_log */

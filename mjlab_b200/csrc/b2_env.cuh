@@ -601,5 +601,6 @@ B2_DEV void env_obs_world(const KModel& m, const KData& d, const KEnv& e, int w,
       op[i] = v;
     }
   }
+  for (int i = B2_LANE; i < 6; i += B2_NLANE) EBR(B2E_B_OBS_EXTRA)[(size_t)w * 6 + i] = i < 3 ? R.lin_b[i] : R.ang_b[i - 3];   // base_lin_vel, base_ang_vel
   B2_WSYNC();
 }

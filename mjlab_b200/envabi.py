@@ -136,6 +136,7 @@ BUFFERS = [
   ("RESET_BUF", "reset_buf", "state", "u1", lambda c: ()),
   ("OBS_POLICY", "obs_policy", "state", "f4", lambda c: (c.n_obs_policy,)),
   ("OBS_CRITIC", "obs_critic", "state", "f4", lambda c: (c.n_obs_critic,)),
+  ("OBS_EXTRA", "obs_extra", "state", "f4", lambda c: (6,)),
   ("LOG_ENV", "log_env", "state", "f4", lambda c: (NLOG,)),
   ("LOG", "log", "scalar", "f4", lambda c: (NLOG,)),
   ("STEP_COUNTER", "step_counter", "scalar", "i8", lambda c: (1,)),

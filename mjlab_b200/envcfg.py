@@ -518,6 +518,7 @@ def from_manager_cfg(cfg, m, robot: str) -> VelocityCfg:
   bank_p = {f: (o, w) for f, o, w in zip(POLICY_OBS_TERMS, (0, 3, 6, 9, 9 + nj, 9 + 2 * nj, 9 + 3 * nj), (3, 3, 3, nj, nj, nj, 3))}
   bank_e = {f: (o, w) for f, o, w in zip(CRITIC_EXTRA_OBS_TERMS, (12 + 3 * nj, 12 + 3 * nj + nf, 12 + 3 * nj + 2 * nf, 12 + 3 * nj + 3 * nf),
                                          (nf, nf, nf, 3 * nf))}
+  bank_x = {("base_lin_vel", None): (0, 3), ("base_ang_vel", None): (3, 3)}
   lo, hi = np.zeros(c.n_obs_policy), np.zeros(c.n_obs_policy)
   noise_of: dict = {}
   ranges_of: dict = {}
@@ -532,9 +533,20 @@ def from_manager_cfg(cfg, m, robot: str) -> VelocityCfg:
       if t is None:
         continue
       key = (t["func"], t["params"].get("sensor_name") if t["func"] == "builtin_sensor" else None)
+      if key in bank_x:   # outside the shipped groups: the kernel writes them to a side buffer, clean only
+        if t["noise"] is not None and g["enable_corruption"]:
+          raise UnsupportedTermError(f"observation term '{n}': {key[0]} carries no noise in the kernels (use the imu sensors' terms)")
+        o, w = bank_x[key]
+        layout[group].append((n, w, "extra", o))
+        e = {k: t[k] for k in _POST_KEYS}
+        if g.get("history_length") is not None:
+          e["history_length"], e["flatten_history_dim"] = g["history_length"], g["flatten_history_dim"]
+        e["name"] = n
+        post[group].append(e)
+        continue
       if key not in bank_p and key not in bank_e:
         raise UnsupportedTermError(f"observation term '{n}' ({key[0]}{', ' + str(key[1]) if key[1] else ''}) is not in the env kernels' term bank "
-                                   f"{[k[1] or k[0] for k in POLICY_OBS_TERMS + CRITIC_EXTRA_OBS_TERMS]}")
+                                   f"{[k[1] or k[0] for k in POLICY_OBS_TERMS + CRITIC_EXTRA_OBS_TERMS] + ['base_lin_vel', 'base_ang_vel']}")
       nz = t["noise"]
       if nz is not None:
         if nz.get("__type__") != "UniformNoiseCfg" or nz.get("operation") != "add":
@@ -574,7 +586,7 @@ def from_manager_cfg(cfg, m, robot: str) -> VelocityCfg:
   got = {g: [(o, w, sg) for _, w, sg, o in terms] for g, terms in layout.items()}
   # the kernel's own two groups, as they are: nothing to gather (a clean-copy source is the same data when the term has no noise)
   c.extra["obs_custom"] = set(got) != {"policy", "critic"} or any(
-    [(o, w) for o, w, _ in got[g]] != [(o, w) for o, w, _ in default[g]] for g in ("policy", "critic"))
+    [(o, w, sg == "extra") for o, w, sg in got[g]] != [(o, w, False) for o, w, _ in default[g]] for g in ("policy", "critic"))
   # ---- actions ----------------------------------------------------------------------------------------------------------------
   acts = [a for a in d["actions"].values() if a is not None]
   if len(acts) != 1 or acts[0]["class_type"] != "JointPositionAction" or not acts[0]["use_default_offset"] or acts[0]["clip"]:

@@ -107,7 +107,7 @@ def make_state(cfg, nworld: int, env_origins=None) -> NS:
     air_state=z(4, nf), air_last_time=z(), peak_heights=z(nf), push_time_left=z(), episode_length=np.zeros(nworld, np.int64),
     reward=z(), step_reward=z(A.NREW), episode_sums=z(A.NREW), term_dones=np.zeros((nworld, A.NTERM), bool),
     terminated=np.zeros(nworld, bool), time_outs=np.zeros(nworld, bool), reset_buf=np.zeros(nworld, bool),
-    obs_policy=z(cfg.n_obs_policy), obs_critic=z(cfg.n_obs_critic), log_env=z(A.NLOG), log=np.zeros(A.NLOG, F), step_counter=0,
+    obs_policy=z(cfg.n_obs_policy), obs_critic=z(cfg.n_obs_critic), obs_extra=z(6), log_env=z(A.NLOG), log=np.zeros(A.NLOG, F), step_counter=0,
   )
 
 
@@ -334,6 +334,7 @@ def observations(cfg, s, d, R, u=None):
     pol = np.where(lo != hi, pol + n, pol).astype(F)
   s.obs_policy[:] = pol
   s.obs_critic[:] = cri
+  s.obs_extra[:] = np.concatenate([R.lin_b, R.ang_b], 1)   # base_lin_vel, base_ang_vel (envs/mdp/observations.py:24-35)
 
 
 # ---------------------------------------------------------------------------------------------------------

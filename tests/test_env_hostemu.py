@@ -106,6 +106,8 @@ def test_kernels_match_reference_golden(fixture):
     np.testing.assert_allclose(env.heading_error[alive], g["ref_heading_error"][t][alive], rtol=3e-5, atol=5e-6)
     np.testing.assert_allclose(env.obs_policy[alive], g["ref_obs_policy"][t][alive], **TOL)
     np.testing.assert_allclose(env.obs_critic[alive], g["ref_obs_critic"][t][alive], **TOL)
+    # base_lin_vel / base_ang_vel (envs/mdp/observations.py:24-35) = the reference EntityData's root_link_*_vel_b
+    np.testing.assert_allclose(env.obs_extra[alive], np.concatenate([g["ref_root_lin_vel_b"][t], g["ref_root_ang_vel_b"][t]], 1)[alive], **TOL)
     checked += int(alive.sum())
   if fixture.endswith("fallen"):
     assert ntrue >= 20 and checked >= 2 * T   # True flags seen; the two upright envs stay comparable throughout

@@ -140,6 +140,8 @@ def test_env_kernels_match_reference_golden(fixture):
     np.testing.assert_allclose(S.get("heading_error")[alive], g["ref_heading_error"][t][alive], rtol=3e-5, atol=5e-6)
     np.testing.assert_allclose(S.get("obs_policy")[alive], g["ref_obs_policy"][t][alive], **TOL)
     np.testing.assert_allclose(S.get("obs_critic")[alive], g["ref_obs_critic"][t][alive], **TOL)
+    # base_lin_vel / base_ang_vel (envs/mdp/observations.py:24-35) = the reference EntityData's root_link_*_vel_b
+    np.testing.assert_allclose(S.get("obs_extra")[alive], np.concatenate([g["ref_root_lin_vel_b"][t], g["ref_root_ang_vel_b"][t]], 1)[alive], **TOL)
     checked += int(alive.sum())
   if fixture.endswith("fallen"):
     assert ntrue >= 20 and checked >= 2 * T
@@ -150,7 +152,7 @@ def test_env_kernels_match_reference_golden(fixture):
 STATE = ["action", "prev_action", "prev_prev_action", "raw_action", "joint_pos_target", "command", "heading_target", "cmd_time_left",
          "cmd_metrics", "cmd_counter", "is_heading", "is_standing", "air_state", "air_last_time", "peak_heights", "push_time_left",
          "episode_length", "reward", "step_reward", "episode_sums", "term_dones", "terminated", "time_outs", "reset_buf", "obs_policy",
-         "obs_critic", "log_env"]
+         "obs_critic", "obs_extra", "log_env"]
 
 
 def _compare(S, s, names):

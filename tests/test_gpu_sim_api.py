@@ -476,20 +476,23 @@ def test_env_consumes_custom_observation_groups():
   pt.pop("base_lin_vel")
   d["observations"]["policy"]["terms"] = {"command": pt["command"], **{k: v for k, v in pt.items() if k != "command"}}
   d["observations"]["feet"] = dict(d["observations"]["critic"], terms={k: d["observations"]["critic"]["terms"][k] for k in ("foot_contact", "foot_height")})
+  d["observations"]["feet"]["terms"]["root_ang_vel"] = dict(d["observations"]["critic"]["terms"]["foot_height"], func="base_ang_vel", params={})
   env = ManagerBasedRlEnv(VelocityEnvCfg.from_manager_cfg(d, "go1", "flat", num_envs=48, seed=4), DEV)
   nj, nf = env.vcfg.nj, env.vcfg.nfeet
   om = env.observation_manager
   assert om.active_terms["policy"] == ["command", "base_ang_vel", "projected_gravity", "joint_pos", "joint_vel", "actions"]
-  assert om.group_obs_dim == {"policy": (9 + 3 * nj,), "critic": (12 + 3 * nj + 6 * nf,), "feet": (2 * nf,)}
+  assert om.group_obs_dim == {"policy": (9 + 3 * nj,), "critic": (12 + 3 * nj + 6 * nf,), "feet": (2 * nf + 3,)}
   obs, _ = env.reset()
   g = torch.Generator(device=DEV).manual_seed(0)
   for _ in range(5):
     obs, rew, term, trunc, _ = env.step(torch.rand(48, nj, device=DEV, generator=g) * 2 - 1)
     raw_p, raw_c = env._raw_obs["policy"], env._raw_obs["critic"]
-    assert obs["policy"].shape == (48, 9 + 3 * nj) and obs["feet"].shape == (48, 2 * nf) and obs["critic"].shape == raw_c.shape
+    assert obs["policy"].shape == (48, 9 + 3 * nj) and obs["feet"].shape == (48, 2 * nf + 3) and obs["critic"].shape == raw_c.shape
     torch.testing.assert_close(obs["policy"][:, 0:3], raw_c[:, 9 + 3 * nj: 12 + 3 * nj])           # command: no noise, clean copy
     torch.testing.assert_close(obs["policy"][:, 3:6], raw_p[:, 3:6])                               # noisy imu angular velocity
     torch.testing.assert_close(obs["policy"][:, 9: 9 + nj], raw_p[:, 9: 9 + nj])                   # noisy joint positions
     assert float((raw_p[:, 3:6] - raw_c[:, 3:6]).abs().max()) > 1e-3                               # (the two copies do differ)
-    torch.testing.assert_close(obs["feet"], torch.cat([raw_c[:, 12 + 3 * nj + 2 * nf: 12 + 3 * nj + 3 * nf], raw_c[:, 12 + 3 * nj: 12 + 3 * nj + nf]], 1))
+    torch.testing.assert_close(obs["feet"][:, : 2 * nf], torch.cat([raw_c[:, 12 + 3 * nj + 2 * nf: 12 + 3 * nj + 3 * nf], raw_c[:, 12 + 3 * nj: 12 + 3 * nj + nf]], 1))
+    # base_ang_vel (envs/mdp/observations.py:31-35) = EntityData.root_link_ang_vel_b, the same quantity through the entity view
+    torch.testing.assert_close(obs["feet"][:, 2 * nf:], env.robot.data.root_link_ang_vel_b, rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(obs["critic"], raw_c)

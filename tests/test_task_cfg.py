@@ -84,8 +84,10 @@ def test_unsupported_terms_raise():
   bad(lambda d: d["terminations"].update(x=dict(func="nan_detection", time_out=True, params={})), "time_out=True")
   bad(lambda d: d["rewards"].update(jv=dict(func="joint_vel_l2", weight=-1.0, params={"asset_cfg": {"name": "robot", "joint_names": (".*_knee_joint",)}})),
       "all actuated joints")
-  bad(lambda d: d["observations"]["policy"]["terms"].update(h=dict(d["observations"]["policy"]["terms"]["joint_vel"], func="base_lin_vel", params={})),
+  bad(lambda d: d["observations"]["policy"]["terms"].update(h=dict(d["observations"]["policy"]["terms"]["joint_vel"], func="body_height", params={})),
       "term bank")
+  bad(lambda d: d["observations"]["policy"]["terms"].update(h=dict(d["observations"]["policy"]["terms"]["joint_vel"], func="base_lin_vel", params={})),
+      "carries no noise")
   bad(lambda d: d["observations"].pop("critic"), "'policy' and 'critic' are required")
   bad(lambda d: (d["observations"]["critic"].update(enable_corruption=True),
                  d["observations"]["critic"]["terms"]["joint_vel"]["noise"].update(n_max=9.0)), "one noise range per term function")
@@ -118,9 +120,11 @@ def test_reweighted_and_removed_terms_are_consumed():
   pt.pop("base_lin_vel")
   d["observations"]["policy"]["terms"] = {"command": pt["command"], **{k2: v for k2, v in pt.items() if k2 != "command"}}
   d["observations"]["feet"] = dict(d["observations"]["critic"], terms={k2: d["observations"]["critic"]["terms"][k2] for k2 in ("foot_contact", "foot_height")})
+  d["observations"]["critic"]["terms"]["root_lin_vel"] = dict(d["observations"]["critic"]["terms"]["foot_height"], func="base_lin_vel", params={})
   c = envcfg.from_manager_cfg(d, m, "go1")
   k = envcfg.REWARD_NAMES.index
   lay = c.extra["obs_layout"]
+  assert lay["critic"][-1] == ("root_lin_vel", 3, "extra", 0)        # envs/mdp/observations.py base_lin_vel: the kernels' side buffer
   assert c.extra["obs_custom"] and [t[0] for t in lay["policy"]] == ["command", "base_ang_vel", "projected_gravity", "joint_pos", "joint_vel", "actions"]
   assert lay["policy"][0][1:] == (3, "critic", 9 + 3 * c.nj)          # no noise on the command: the clean copy
   assert lay["policy"][1][1:] == (3, "policy", 3)                     # noisy imu_ang_vel
