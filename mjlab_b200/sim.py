@@ -127,22 +127,27 @@ class _Opt:
 
   @property
   def timestep(self) -> torch.Tensor:
+    self._sim.invalidate_memo()   # the tensor may be edited in place (see Simulation.model)
     return self._sim._model_views["opt_timestep"].reshape(-1)
 
   @property
   def gravity(self) -> torch.Tensor:
+    self._sim.invalidate_memo()   # the tensor may be edited in place (see Simulation.model)
     return self._sim._model_views["opt_gravity"]
 
   @property
   def tolerance(self) -> torch.Tensor:
+    self._sim.invalidate_memo()   # the tensor may be edited in place (see Simulation.model)
     return self._sim._model_views["opt_tolerance"].reshape(-1)
 
   @property
   def ls_tolerance(self) -> torch.Tensor:
+    self._sim.invalidate_memo()   # the tensor may be edited in place (see Simulation.model)
     return self._sim._model_views["opt_ls_tolerance"].reshape(-1)
 
   @property
   def impratio(self) -> torch.Tensor:
+    self._sim.invalidate_memo()   # the tensor may be edited in place (see Simulation.model)
     return self._sim._model_views["opt_impratio"].reshape(-1)
 
   @property

@@ -445,7 +445,14 @@ def test_forward_pass_reuse_is_bit_identical(task):
       trace = []
       for k in range(40):
         if k == 20:   # an edit of model fields between two steps: the bridge access drops the memo
+          assert not env.sim._memo_dirty
           env.sim.model.geom_friction[:, :, 0] *= 1.0
+          assert env.sim._memo_dirty
+        if k == 30:   # ... and so does handing out an option tensor through a cached `opt` object
+          opt = env.sim.model.opt
+          env.sim._memo_dirty = False
+          _ = opt.gravity
+          assert env.sim._memo_dirty
         if k % 2:     # every other step ends with a time-out, so with the forward pass (it only runs when some env was reset)
           env.episode_length_buf[k % 256] = env.max_episode_length
         obs, rew, term, trunc, _ = env.step(torch.rand(256, env.vcfg.nj, device=DEV, generator=gen) * 2 - 1)
