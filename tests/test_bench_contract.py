@@ -49,3 +49,20 @@ def test_own_arm_prints_the_full_contract_line():
   assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
   assert set(j["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
   assert "workload" in j["config"] and "model" not in j["config"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flags,metric_min", [
+  (["--mode", "physics", "--model", "go1_flat", "--steps", "4", "--warmup", "3", "--no-roofline-pass", "--prewarm-s", "0.2"], 1e5),
+  (["--task", "train", "--steps", "1", "--warmup", "3", "--prewarm-s", "0.2"], 1e4),
+  (["--task", "tracking", "--steps", "4", "--warmup", "3", "--no-roofline-pass", "--prewarm-s", "0.2"], 1e5),
+])
+def test_other_bench_modes_print_one_line(flags, metric_min):
+  """BASELINE configs 2 (physics-only stepping), 3 (PPO train iteration) and 5 (tracking) stay driver-runnable."""
+  out = subprocess.run([sys.executable, str(ROOT / "bench.py"), *flags], capture_output=True, text=True, timeout=900, cwd=ROOT)
+  assert out.returncode == 0, out.stderr[-2000:]
+  lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+  assert len(lines) == 1
+  j = json.loads(lines[0])
+  assert j["value"] > metric_min and j["n_gpus"] == 1 and j["gpu_launches"] > 0 and "workload" in j["config"]
+  assert j["e2e"]["value"] > 0 and set(j["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
