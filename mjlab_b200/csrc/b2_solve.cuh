@@ -311,12 +311,20 @@ B2_DEV bool in_subtree(const int* body_parent, const int* ancmask, int body, int
     if (b == 0) return false;
   }
 }
-B2_DEV bool match_side(const int* geom_body, const int* body_parent, const int* ancmask, int objtype, int objid, int geom) {
+B2_DEV bool match_side(const int* body_parent, const int* ancmask, int objtype, int objid, int geom, int body) {
   if (objid < 0) return true;
   if (objtype == B2_OBJ_GEOM) return geom == objid;
-  int body = geom_body[geom];
   if (objtype == B2_OBJ_BODY) return body == objid;
   if (objtype == B2_OBJ_XBODY) return in_subtree(body_parent, ancmask, body, objid);
+  return false;
+}
+
+// the same with the body's ancestor mask in hand (lo: bodies 0..31, hi: 32..63)
+B2_DEV bool match_side_m(int objtype, int objid, int geom, int body, unsigned lo, unsigned hi) {
+  if (objid < 0) return true;
+  if (objtype == B2_OBJ_GEOM) return geom == objid;
+  if (objtype == B2_OBJ_BODY) return body == objid;
+  if (objtype == B2_OBJ_XBODY) return ((objid < 32 ? lo : hi) >> (objid & 31)) & 1u;
   return false;
 }
 
@@ -1197,6 +1205,26 @@ B2_DEV void post_world(const KModel& m, const KData& d, const PostSmem& L, int w
       B2_WSYNC();
     }
     B2_WSYNC();
+    // Per-contact quantities every contact sensor needs - the two bodies, the contact-frame force, the world-frame force -
+    // once per contact (lanes over contacts) instead of once per (sensor, contact) inside the sensor loops below: those run one
+    // lane per sensor, so their length is the latency of this stage.  Scratch: the integrator's matrix, not built yet.
+    const int cpre = ancmask ? (ncon < (nv * ld) / 12 ? ncon : (nv * ld) / 12) : 0;
+    int* cbody = (int*)H;                  // [2 cpre] bodies of the two geoms
+    unsigned* canc = (unsigned*)H + 2 * cpre;   // [4 cpre] their ancestor masks
+    real* cfc = H + 6 * cpre;
+    real* cfg = cfc + 3 * cpre;
+    B2_UNROLL1
+    for (int c = B2_LANE; c < cpre; c += B2_NLANE) {
+      const int b1 = geom_body[c_geom[2 * c]], b2 = geom_body[c_geom[2 * c + 1]];
+      cbody[2 * c] = b1; cbody[2 * c + 1] = b2;
+      canc[4 * c] = (unsigned)ancmask[2 * b1]; canc[4 * c + 1] = (unsigned)ancmask[2 * b1 + 1];
+      canc[4 * c + 2] = (unsigned)ancmask[2 * b2]; canc[4 * c + 3] = (unsigned)ancmask[2 * b2 + 1];
+      real fc[3], fg[3];
+      contact_force(fc, nefc > 0 ? c_adr[c] : -1, c_dim[c], c_fri + 5 * c, efc_force);
+      mulmTv3(fg, c_frame + 9 * c, fc);
+      for (int e = 0; e < 3; ++e) { cfc[3 * c + e] = fc[e]; cfg[3 * c + e] = fg[e]; }
+    }
+    B2_WSYNC();
     B2_UNROLL1
     for (int s = B2_LANE; s < m.nsensor; s += B2_NLANE) {
       int t = s_type[s], oid = s_objid[s], adr = s_adr[s], dim = s_dim[s];
@@ -1264,14 +1292,26 @@ B2_DEV void post_world(const KModel& m, const KData& d, const PostSmem& L, int w
         for (int c = 0; c < ncon; ++c) {
           int g1 = c_geom[2 * c], g2 = c_geom[2 * c + 1];
           real sgn = 0;
-          if (match_side(geom_body, body_parent, ancmask, ot, oid, g1) && match_side(geom_body, body_parent, ancmask, rt, rid, g2)) sgn = 1;
-          else if (match_side(geom_body, body_parent, ancmask, ot, oid, g2) && match_side(geom_body, body_parent, ancmask, rt, rid, g1)) sgn = -1;
+          if (c < cpre) {
+            const int b1 = cbody[2 * c], b2 = cbody[2 * c + 1];
+            const unsigned l1 = canc[4 * c], h1 = canc[4 * c + 1], l2 = canc[4 * c + 2], h2 = canc[4 * c + 3];
+            if (match_side_m(ot, oid, g1, b1, l1, h1) && match_side_m(rt, rid, g2, b2, l2, h2)) sgn = 1;
+            else if (match_side_m(ot, oid, g2, b2, l2, h2) && match_side_m(rt, rid, g1, b1, l1, h1)) sgn = -1;
+          } else {
+            const int b1 = geom_body[g1], b2 = geom_body[g2];
+            if (match_side(body_parent, ancmask, ot, oid, g1, b1) && match_side(body_parent, ancmask, rt, rid, g2, b2)) sgn = 1;
+            else if (match_side(body_parent, ancmask, ot, oid, g2, b2) && match_side(body_parent, ancmask, rt, rid, g1, b1)) sgn = -1;
+          }
           if (sgn == 0) continue;
           ++nfound;
           if (reduce == 3 && (bits & 2)) {
-            real fc[3], fg[3];
-            contact_force(fc, nefc > 0 ? c_adr[c] : -1, c_dim[c], c_fri + 5 * c, efc_force);
-            mulmTv3(fg, c_frame + 9 * c, fc);
+            real fg[3];
+            if (c < cpre) { fg[0] = cfg[3 * c]; fg[1] = cfg[3 * c + 1]; fg[2] = cfg[3 * c + 2]; }
+            else {
+              real fc[3];
+              contact_force(fc, nefc > 0 ? c_adr[c] : -1, c_dim[c], c_fri + 5 * c, efc_force);
+              mulmTv3(fg, c_frame + 9 * c, fc);
+            }
             net[0] += sgn * fg[0]; net[1] += sgn * fg[1]; net[2] += sgn * fg[2];
           }
         }
@@ -1291,15 +1331,24 @@ B2_DEV void post_world(const KModel& m, const KData& d, const PostSmem& L, int w
               for (int c = 0; c < ncon; ++c) {
                 int g1 = c_geom[2 * c], g2 = c_geom[2 * c + 1];
                 real sgn = 0;
-                if (match_side(geom_body, body_parent, ancmask, ot, oid, g1) && match_side(geom_body, body_parent, ancmask, rt, rid, g2)) sgn = 1;
-                else if (match_side(geom_body, body_parent, ancmask, ot, oid, g2) && match_side(geom_body, body_parent, ancmask, rt, rid, g1)) sgn = -1;
+                if (c < cpre) {
+                  const int b1 = cbody[2 * c], b2 = cbody[2 * c + 1];
+                  const unsigned l1 = canc[4 * c], h1 = canc[4 * c + 1], l2 = canc[4 * c + 2], h2 = canc[4 * c + 3];
+                  if (match_side_m(ot, oid, g1, b1, l1, h1) && match_side_m(rt, rid, g2, b2, l2, h2)) sgn = 1;
+                  else if (match_side_m(ot, oid, g2, b2, l2, h2) && match_side_m(rt, rid, g1, b1, l1, h1)) sgn = -1;
+                } else {
+                  const int b1 = geom_body[g1], b2 = geom_body[g2];
+                  if (match_side(body_parent, ancmask, ot, oid, g1, b1) && match_side(body_parent, ancmask, rt, rid, g2, b2)) sgn = 1;
+                  else if (match_side(body_parent, ancmask, ot, oid, g2, b2) && match_side(body_parent, ancmask, rt, rid, g1, b1)) sgn = -1;
+                }
                 if (sgn == 0) continue;
                 real key;
                 if (reduce == 0) key = (real)c;
                 else if (reduce == 1) key = c_dist[c];
                 else {
                   real fc[3];
-                  contact_force(fc, nefc > 0 ? c_adr[c] : -1, c_dim[c], c_fri + 5 * c, efc_force);
+                  if (c < cpre) { fc[0] = cfc[3 * c]; fc[1] = cfc[3 * c + 1]; fc[2] = cfc[3 * c + 2]; }
+                  else contact_force(fc, nefc > 0 ? c_adr[c] : -1, c_dim[c], c_fri + 5 * c, efc_force);
                   key = -sqrt(dot3(fc, fc));
                 }
                 // strict ordering by (key, c) to enumerate matches in sorted order
@@ -1314,7 +1363,8 @@ B2_DEV void post_world(const KModel& m, const KData& d, const PostSmem& L, int w
               if (bits & 1) out[p++] = (real)nfound;
               if (bits & 2) {
                 real fc[3];
-                contact_force(fc, nefc > 0 ? c_adr[c] : -1, c_dim[c], c_fri + 5 * c, efc_force);
+                if (c < cpre) { fc[0] = cfc[3 * c]; fc[1] = cfc[3 * c + 1]; fc[2] = cfc[3 * c + 2]; }
+                else contact_force(fc, nefc > 0 ? c_adr[c] : -1, c_dim[c], c_fri + 5 * c, efc_force);
                 out[p] = picksgn * fc[0]; out[p + 1] = picksgn * fc[1]; out[p + 2] = picksgn * fc[2]; p += 3;
               }
               if (bits & 4) p += 3;
