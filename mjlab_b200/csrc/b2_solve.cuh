@@ -1119,6 +1119,15 @@ B2_DEV void post_world(const KModel& m, const KData& d, const PostSmem& L, int w
     const real* body_mass = MF(B2_MF_BODY_MASS);
     const real* body_inertia = MF(B2_MF_BODY_INERTIA);
 
+    // The level sweeps below pass their results from level to level; through global memory every level costs a store -> load
+    // round trip to L2, so they run on shared-memory copies (the integrator's matrix is not built yet: its space is free) and
+    // the finished arrays go to HBM in one coalesced pass.
+    real* s_cacc = H;                       // [6 nb]
+    real* s_slin = H;                       // [3 nb]   (the cacc sweep is over by then)
+    real* s_sang = H + 3 * nb;              // [3 nb]
+    real* s_scom = H + 6 * nb;              // [3 nb]
+    const bool sweeps_in_smem = 9 * nb <= nv * ld;
+    if (!sweeps_in_smem) { s_cacc = g_cacc; s_slin = g_slin; s_sang = g_sang; s_scom = const_cast<real*>(g_scom); }
     if (m.has_accelerometer) {
       // cacc including qacc (rne_postconstraint, acceleration part), forward over levels
       const real* grav = MF(B2_MF_OPT_GRAVITY);
@@ -1132,17 +1141,22 @@ B2_DEV void post_world(const KModel& m, const KData& d, const PostSmem& L, int w
             a[0] = a[1] = a[2] = 0; a[3] = -grav[0]; a[4] = -grav[1]; a[5] = -grav[2];
           } else {
             int p = body_parent[b];
-            for (int c = 0; c < 6; ++c) a[c] = g_cacc[6 * p + c];
+            for (int c = 0; c < 6; ++c) a[c] = s_cacc[6 * p + c];
             B2_UNROLL1
             for (int e = 0; e < body_dofnum[b]; ++e) {
               int dd = body_dofadr[b] + e;
               for (int c = 0; c < 6; ++c) a[c] += g_cdofdot[6 * dd + c] * qvel[dd] + g_cdof[6 * dd + c] * qacc[dd];
             }
           }
-          for (int c = 0; c < 6; ++c) g_cacc[6 * b + c] = a[c];
+          for (int c = 0; c < 6; ++c) s_cacc[6 * b + c] = a[c];
         }
         B2_WSYNC();
       }
+      if (s_cacc != g_cacc) {
+        B2_UNROLL1
+        for (int i = B2_LANE; i < 6 * nb; i += B2_NLANE) g_cacc[i] = s_cacc[i];
+      }
+      B2_WSYNC();
     }
     if (m.has_subtreevel) {
       // subtree linear velocity: backward gather of body momenta
@@ -1155,13 +1169,14 @@ B2_DEV void post_world(const KModel& m, const KData& d, const PostSmem& L, int w
         real t[3];
         cross3(t, v, off);
         real ms = body_mass[b];
-        g_slin[3 * b] = ms * (v[3] + t[0]); g_slin[3 * b + 1] = ms * (v[4] + t[1]); g_slin[3 * b + 2] = ms * (v[5] + t[2]);
+        s_slin[3 * b] = ms * (v[3] + t[0]); s_slin[3 * b + 1] = ms * (v[4] + t[1]); s_slin[3 * b + 2] = ms * (v[5] + t[2]);
+        if (sweeps_in_smem) { s_scom[3 * b] = g_scom[3 * b]; s_scom[3 * b + 1] = g_scom[3 * b + 1]; s_scom[3 * b + 2] = g_scom[3 * b + 2]; }
         const real* Ri = g_ximat + 9 * b;
         real wl[3], Iw[3];
         mulmTv3(wl, Ri, v);
         wl[0] *= body_inertia[3 * b]; wl[1] *= body_inertia[3 * b + 1]; wl[2] *= body_inertia[3 * b + 2];
         mulmv3(Iw, Ri, wl);
-        g_sang[3 * b] = Iw[0]; g_sang[3 * b + 1] = Iw[1]; g_sang[3 * b + 2] = Iw[2];
+        s_sang[3 * b] = Iw[0]; s_sang[3 * b + 1] = Iw[1]; s_sang[3 * b + 2] = Iw[2];
       }
       B2_WSYNC();
       // angular momentum about each subtree's com: gather children bottom-up.  Keep momentum P, mass m and
@@ -1175,32 +1190,37 @@ B2_DEV void post_world(const KModel& m, const KData& d, const PostSmem& L, int w
         B2_UNROLL1
         for (int k = level_adr[lev] + B2_LANE; k < level_adr[lev + 1]; k += B2_NLANE) {
           int b = level_body[k];
-          real P[3] = {g_slin[3 * b], g_slin[3 * b + 1], g_slin[3 * b + 2]};
-          real Lb[3] = {g_sang[3 * b], g_sang[3 * b + 1], g_sang[3 * b + 2]};
-          real dx[3] = {g_xipos[3 * b] - g_scom[3 * b], g_xipos[3 * b + 1] - g_scom[3 * b + 1], g_xipos[3 * b + 2] - g_scom[3 * b + 2]};
+          real P[3] = {s_slin[3 * b], s_slin[3 * b + 1], s_slin[3 * b + 2]};
+          real Lb[3] = {s_sang[3 * b], s_sang[3 * b + 1], s_sang[3 * b + 2]};
+          real dx[3] = {g_xipos[3 * b] - s_scom[3 * b], g_xipos[3 * b + 1] - s_scom[3 * b + 1], g_xipos[3 * b + 2] - s_scom[3 * b + 2]};
           real t[3];
           cross3(t, dx, P);
           Lb[0] += t[0]; Lb[1] += t[1]; Lb[2] += t[2];
           B2_UNROLL1
           for (int c = child_adr[b]; c < child_adr[b + 1]; ++c) {
             int ch = child_body[c];
-            real Pc[3] = {g_slin[3 * ch], g_slin[3 * ch + 1], g_slin[3 * ch + 2]};
-            real dc[3] = {g_scom[3 * ch] - g_scom[3 * b], g_scom[3 * ch + 1] - g_scom[3 * b + 1], g_scom[3 * ch + 2] - g_scom[3 * b + 2]};
+            real Pc[3] = {s_slin[3 * ch], s_slin[3 * ch + 1], s_slin[3 * ch + 2]};
+            real dc[3] = {s_scom[3 * ch] - s_scom[3 * b], s_scom[3 * ch + 1] - s_scom[3 * b + 1], s_scom[3 * ch + 2] - s_scom[3 * b + 2]};
             cross3(t, dc, Pc);
-            Lb[0] += g_sang[3 * ch] + t[0]; Lb[1] += g_sang[3 * ch + 1] + t[1]; Lb[2] += g_sang[3 * ch + 2] + t[2];
+            Lb[0] += s_sang[3 * ch] + t[0]; Lb[1] += s_sang[3 * ch + 1] + t[1]; Lb[2] += s_sang[3 * ch + 2] + t[2];
             P[0] += Pc[0]; P[1] += Pc[1]; P[2] += Pc[2];
           }
-          g_slin[3 * b] = P[0]; g_slin[3 * b + 1] = P[1]; g_slin[3 * b + 2] = P[2];
-          g_sang[3 * b] = Lb[0]; g_sang[3 * b + 1] = Lb[1]; g_sang[3 * b + 2] = Lb[2];
+          s_slin[3 * b] = P[0]; s_slin[3 * b + 1] = P[1]; s_slin[3 * b + 2] = P[2];
+          s_sang[3 * b] = Lb[0]; s_sang[3 * b + 1] = Lb[1]; s_sang[3 * b + 2] = Lb[2];
         }
         B2_WSYNC();
       }
-      // momentum -> velocity
+      // momentum -> velocity, and out to HBM
       const real* stm = MF(B2_MF_BODY_SUBTREEMASS);
       B2_UNROLL1
       for (int b = B2_LANE; b < nb; b += B2_NLANE) {
         real inv = stm[b] > B2_MINVAL ? (real)1 / stm[b] : (real)0;
-        g_slin[3 * b] *= inv; g_slin[3 * b + 1] *= inv; g_slin[3 * b + 2] *= inv;
+        s_slin[3 * b] *= inv; s_slin[3 * b + 1] *= inv; s_slin[3 * b + 2] *= inv;
+      }
+      B2_WSYNC();
+      if (s_slin != g_slin) {
+        B2_UNROLL1
+        for (int i = B2_LANE; i < 3 * nb; i += B2_NLANE) { g_slin[i] = s_slin[i]; g_sang[i] = s_sang[i]; }
       }
       B2_WSYNC();
     }
