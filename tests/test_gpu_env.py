@@ -421,7 +421,7 @@ def test_chunked_streams_do_not_change_results():
       assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize("task", ["velocity", "tracking"])
+@pytest.mark.parametrize("task", ["velocity", "tracking", "rough_go1"])
 def test_forward_pass_reuse_is_bit_identical(task):
   """The first sub-step of an env step reuses the position / velocity stage of the forward pass that ended the previous step
   (b2_substeps_after_forward): trajectories with the reuse on (default) and off (B200SIM_MEMO=0) are bit-identical - resets,
@@ -437,6 +437,8 @@ def test_forward_pass_reuse_is_bit_identical(task):
       os.environ["B200SIM_MEMO"] = memo
       if task == "velocity":
         env = ManagerBasedRlEnv(VelocityEnvCfg(robot="g1", num_envs=256, seed=5), DEV)
+      elif task == "rough_go1":   # geom field, box-box narrowphase, terrain curriculum at reset
+        env = ManagerBasedRlEnv(VelocityEnvCfg(robot="go1", terrain="rough", num_envs=256, seed=5), DEV)
       else:
         env = TrackingRlEnv(TrackingEnvCfg(num_envs=256, seed=5), DEV)
       env.reset()
@@ -472,3 +474,29 @@ def test_forward_pass_reuse_is_bit_identical(task):
   for k, (a, b) in enumerate(zip(*outs)):
     for x, y in zip(a, b):
       assert torch.equal(x, y), (k, float((x.float() - y.float()).abs().max()))
+
+
+def test_fused_post_experiment_knob_still_gives_identical_results():
+  """B200SIM_FUSE_POST=1 (sensors + integration inside the solver's tail, measured slower and off by default,
+  profiles/r02_fused_post_experiment.txt) must keep producing the default path's trajectories bit for bit."""
+  import os
+  from mjlab_b200.env import ManagerBasedRlEnv, VelocityEnvCfg
+  old = os.environ.get("B200SIM_FUSE_POST")
+  outs = []
+  try:
+    for knob in ("0", "1"):
+      os.environ["B200SIM_FUSE_POST"] = knob
+      env = ManagerBasedRlEnv(VelocityEnvCfg(robot="go1", num_envs=96, seed=5), DEV)
+      env.reset()
+      gen = torch.Generator(device=DEV).manual_seed(3)
+      env.episode_length_buf = torch.randint(0, 1000, (96,), device=DEV, generator=gen)
+      for _ in range(15):
+        obs, rew, term, trunc, _ = env.step(torch.rand(96, env.vcfg.nj, device=DEV, generator=gen) * 2 - 1)
+      outs.append((obs["critic"].clone(), rew.clone(), env.sim.data.qpos.clone(), env.sim.data.qvel.clone(), env.sim.data.sensordata.clone()))
+  finally:
+    if old is None:
+      os.environ.pop("B200SIM_FUSE_POST", None)
+    else:
+      os.environ["B200SIM_FUSE_POST"] = old
+  for a, b in zip(*outs):
+    assert torch.equal(a, b)
