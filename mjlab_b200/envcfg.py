@@ -533,6 +533,8 @@ def from_manager_cfg(cfg, m, robot: str) -> VelocityCfg:
       if t is None:
         continue
       key = (t["func"], t["params"].get("sensor_name") if t["func"] == "builtin_sensor" else None)
+      if t["func"] == "joint_pos_rel" and t["params"].get("biased"):
+        raise UnsupportedTermError(f"observation term '{n}': joint_pos_rel(biased=True) is implemented by the tracking kernels only")
       if key in bank_x:   # outside the shipped groups: the kernel writes them to a side buffer, clean only
         if t["noise"] is not None and g["enable_corruption"]:
           raise UnsupportedTermError(f"observation term '{n}': {key[0]} carries no noise in the kernels (use the imu sensors' terms)")

@@ -89,6 +89,7 @@ def test_unsupported_terms_raise():
   bad(lambda d: d["observations"]["policy"]["terms"].update(h=dict(d["observations"]["policy"]["terms"]["joint_vel"], func="base_lin_vel", params={})),
       "carries no noise")
   bad(lambda d: d["observations"].pop("critic"), "'policy' and 'critic' are required")
+  bad(lambda d: d["observations"]["policy"]["terms"]["joint_pos"]["params"].update(biased=True), "biased=True")
   bad(lambda d: (d["observations"]["critic"].update(enable_corruption=True),
                  d["observations"]["critic"]["terms"]["joint_vel"]["noise"].update(n_max=9.0)), "one noise range per term function")
   bad(lambda d: d["observations"]["critic"]["terms"]["foot_height"].update(noise=dict(__type__="UniformNoiseCfg", operation="add", n_min=-1, n_max=1)),
