@@ -420,6 +420,38 @@ def _range6(d) -> dict:
   return {k: (float(v[0]), float(v[1])) for k, v in (d or {}).items()}
 
 
+
+# ---- parameters of a consumed term: every one is either read into the kernels' table, or a selector that must name what the
+# kernels are wired to (the feet sites, the contact sensors, the "twist" command, all actuated joints); anything else raises
+def _ac(v) -> dict:
+  """The non-default selectors of a SceneEntityCfg dump."""
+  v = v or {}
+  out = {k: (tuple(x) if isinstance(x, (list, tuple)) else x) for k, x in v.items()
+         if k.endswith(("_names", "_ids")) and x not in (None, False) and not (isinstance(x, dict))}
+  if v.get("name", "robot") != "robot":
+    out["name"] = v["name"]
+  if v.get("preserve_order"):
+    out["preserve_order"] = True
+  return out
+
+
+def _all_joints(v) -> bool:
+  a = _ac(v)
+  return a == {} or a == {"joint_names": (".*",)}
+
+
+def _check_params(kind: str, name: str, func: str, params: dict, consumed: tuple, fixed: dict) -> None:
+  for k, v in params.items():
+    if k in consumed:
+      continue
+    if k not in fixed:
+      raise UnsupportedTermError(f"{kind} '{name}' ({func}): parameter '{k}' is not consumed by the env kernels")
+    want = fixed[k]
+    ok = want(v) if callable(want) else v == want
+    if not ok:
+      raise UnsupportedTermError(f"{kind} '{name}' ({func}): {k}={v!r} - the env kernels are wired to "
+                                 f"{want.__doc__ if callable(want) else repr(want)}")
+
 def from_manager_cfg(cfg, m, robot: str) -> VelocityCfg:
   """Resolve a reference `ManagerBasedRlEnvCfg` of the velocity task (the live dataclass or its `cfg_to_dict` view) into the
   kernels' `VelocityCfg`: reward weights and parameters by term FUNCTION, termination set, observation noise / corruption flags,
@@ -459,6 +491,39 @@ def from_manager_cfg(cfg, m, robot: str) -> VelocityCfg:
       w[k] = float(t["weight"])
       P[slot] = t["params"]
   c.reward_weights = w
+  feet = tuple(c.foot_site_names)
+
+  def foot_sites(v):
+    return _ac(v) == {"site_names": feet}
+  foot_sites.__doc__ = f"the foot sites {feet}"
+
+  def all_joints(v):
+    return _all_joints(v)
+  all_joints.__doc__ = "all actuated joints of 'robot'"
+
+  def upright_body(v):
+    return _ac(v) == _ac((P.get("upright") or {}).get("asset_cfg")) if "upright" in P else len(_ac(v).get("body_names", ())) == 1
+  upright_body.__doc__ = "the body of the flat_orientation term (one body serves both)"
+  twist, fgc = {"command_name": "twist"}, {"sensor_name": "feet_ground_contact"}
+  rules = {
+    "track_linear_velocity": (("std",), twist), "track_angular_velocity": (("std",), twist),
+    "upright": (("std", "asset_cfg"), {}),
+    "pose": (("std_standing", "std_walking", "std_running", "walking_threshold", "running_threshold"), {**twist, "asset_cfg": all_joints}),
+    "body_ang_vel": ((), {"asset_cfg": upright_body}),
+    "angular_momentum": ((), {"sensor_name": "robot/root_angmom"}),
+    "dof_pos_limits": ((), {"asset_cfg": all_joints}), "action_rate_l2": ((), {}),
+    "air_time": (("threshold_min", "threshold_max", "command_threshold"), {**twist, **fgc}),
+    "foot_clearance": (("target_height", "command_threshold"), {**twist, "asset_cfg": foot_sites}),
+    "foot_swing_height": (("target_height", "command_threshold"), {**twist, **fgc, "asset_cfg": foot_sites}),
+    "foot_slip": (("command_threshold",), {**twist, **fgc, "asset_cfg": foot_sites}),
+    "soft_landing": (("command_threshold",), {**twist, **fgc}),
+    "self_collisions": ((), {"sensor_name": "self_collision"}),
+    "is_alive": ((), {}), "is_terminated": ((), {}), "action_acc_l2": ((), {}),
+    "joint_torques_l2": ((), {"asset_cfg": all_joints}), "joint_vel_l2": ((), {"asset_cfg": all_joints}),
+    "joint_acc_l2": ((), {"asset_cfg": all_joints}), "flat_orientation_l2": ((), {"asset_cfg": all_joints}),
+  }
+  for slot, params in P.items():
+    _check_params("reward", by_func[REWARD_FUNCS[slot]][0], REWARD_FUNCS[slot], params, *rules[slot])
   for slot in ("joint_torques_l2", "joint_vel_l2", "joint_acc_l2", "flat_orientation_l2"):
     ac = (P.get(slot) or {}).get("asset_cfg") or {}
     if any(ac.get(k) not in (None, (".*",), [".*"], ".*") for k in ("joint_names", "body_names")) or ac.get("name", "robot") != "robot":
@@ -497,6 +562,11 @@ def from_manager_cfg(cfg, m, robot: str) -> VelocityCfg:
     raise UnsupportedTermError(f"termination functions {sorted(bad)} are not implemented by the env kernels")
   if "time_out" not in tf or not tf["time_out"]["time_out"]:
     raise UnsupportedTermError("the kernels always apply the time_out truncation")
+  trules = {"time_out": ((), {}), "bad_orientation": (("limit_angle",), {"asset_cfg": all_joints}),
+            "illegal_contact": ((), {"sensor_name": "nonfoot_ground_touch"}),
+            "root_height_below_minimum": (("minimum_height",), {"asset_cfg": all_joints}), "nan_detection": ((), {})}
+  for f, t in tf.items():
+    _check_params("termination", f, f, t["params"], *trules[f])
   if "bad_orientation" in tf:
     c.limit_angle = float(tf["bad_orientation"]["params"]["limit_angle"])
   else:
@@ -533,6 +603,13 @@ def from_manager_cfg(cfg, m, robot: str) -> VelocityCfg:
       if t is None:
         continue
       key = (t["func"], t["params"].get("sensor_name") if t["func"] == "builtin_sensor" else None)
+      orules = {"builtin_sensor": (("sensor_name",), {}), "projected_gravity": ((), {"asset_cfg": all_joints}),
+                "joint_pos_rel": (("biased",), {"asset_cfg": all_joints}), "joint_vel_rel": ((), {"asset_cfg": all_joints}),
+                "last_action": ((), {"action_name": lambda v: v in (None, "joint_pos")}), "generated_commands": ((), twist),
+                "foot_height": ((), {"asset_cfg": foot_sites}), "foot_air_time": ((), fgc), "foot_contact": ((), fgc),
+                "foot_contact_forces": ((), fgc), "base_lin_vel": ((), {"asset_cfg": all_joints}), "base_ang_vel": ((), {"asset_cfg": all_joints})}
+      if t["func"] in orules:
+        _check_params("observation term", n, t["func"], t["params"], *orules[t["func"]])
       if t["func"] == "joint_pos_rel" and t["params"].get("biased"):
         raise UnsupportedTermError(f"observation term '{n}': joint_pos_rel(biased=True) is implemented by the tracking kernels only")
       if key in bank_x:   # outside the shipped groups: the kernel writes them to a side buffer, clean only
@@ -603,6 +680,8 @@ def from_manager_cfg(cfg, m, robot: str) -> VelocityCfg:
     if e is None:
       continue
     f, p = e["func"], e["params"]
+    if f in ("reset_root_state_uniform", "reset_joints_by_offset", "push_by_setting_velocity"):
+      _check_params("event", name, f, p, ("pose_range", "velocity_range", "position_range"), {"asset_cfg": all_joints})
     if f == "reset_root_state_uniform" and e["mode"] == "reset":
       c.reset_pose_range, c.reset_velocity_range = _range6(p.get("pose_range")), _range6(p.get("velocity_range"))
     elif f == "reset_joints_by_offset" and e["mode"] == "reset":

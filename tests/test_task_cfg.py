@@ -88,6 +88,15 @@ def test_unsupported_terms_raise():
       "term bank")
   bad(lambda d: d["observations"]["policy"]["terms"].update(h=dict(d["observations"]["policy"]["terms"]["joint_vel"], func="base_lin_vel", params={})),
       "carries no noise")
+  # parameters are either consumed or must name what the kernels are wired to: never silently ignored
+  bad(lambda d: d["rewards"]["foot_slip"]["params"]["asset_cfg"].update(site_names=["left_foot"]), "foot sites")
+  bad(lambda d: d["rewards"]["body_ang_vel"]["params"]["asset_cfg"].update(body_names=["pelvis"]), "flat_orientation term")
+  bad(lambda d: d["rewards"]["track_linear_velocity"]["params"].update(command_name="other"), "command_name")
+  bad(lambda d: d["rewards"]["air_time"]["params"].update(sensor_name="hands_contact"), "sensor_name")
+  bad(lambda d: d["rewards"]["action_rate_l2"]["params"].update(gain=2.0), "parameter 'gain' is not consumed")
+  bad(lambda d: d["terminations"]["fell_over"]["params"].update(asset_cfg=dict(name="robot", body_names=["torso_link"])), "all actuated joints")
+  bad(lambda d: d["observations"]["critic"]["terms"]["foot_height"]["params"]["asset_cfg"].update(site_names=["right_foot"]), "foot sites")
+  bad(lambda d: d["events"]["reset_robot_joints"]["params"]["asset_cfg"].update(joint_names=[".*_knee_joint"]), "all actuated joints")
   bad(lambda d: d["observations"].pop("critic"), "'policy' and 'critic' are required")
   bad(lambda d: d["observations"]["policy"]["terms"]["joint_pos"]["params"].update(biased=True), "biased=True")
   bad(lambda d: (d["observations"]["critic"].update(enable_corruption=True),
