@@ -794,9 +794,15 @@ def tracking_from_manager_cfg(cfg, m, time_step_total: int, robot: str = "g1") -
   if unknown:
     raise UnsupportedTermError(f"reward terms {sorted(by_func[f][0] for f in unknown)} ({sorted(unknown)}) are not implemented by the tracking kernels")
   w = np.zeros(len(TRACKING_REWARD_NAMES))
+
+  def all_joints(v):
+    return _all_joints(v)
+  all_joints.__doc__ = "all actuated joints of 'robot'"
+  motion = {"command_name": "motion"}
   for k, slot in enumerate(TRACKING_REWARD_NAMES):
     if TRACKING_REWARD_FUNCS[slot] in by_func:
-      _, t = by_func[TRACKING_REWARD_FUNCS[slot]]
+      rname, t = by_func[TRACKING_REWARD_FUNCS[slot]]
+      _check_params("reward", rname, t["func"], t["params"], ("std",), {**motion, "asset_cfg": all_joints, "sensor_name": "self_collision"})
       w[k] = float(t["weight"])
       if slot in _TRACKING_STD:
         setattr(c, _TRACKING_STD[slot], float(t["params"]["std"]))
@@ -810,6 +816,8 @@ def tracking_from_manager_cfg(cfg, m, time_step_total: int, robot: str = "g1") -
     raise UnsupportedTermError(f"termination functions {sorted(bad)} are not implemented by the tracking kernels")
   if "time_out" not in tf or not tf["time_out"]["time_out"]:
     raise UnsupportedTermError("the kernels always apply the time_out truncation")
+  for f, t in tf.items():
+    _check_params("termination", f, f, t["params"], ("threshold", "body_names"), {**motion, "asset_cfg": all_joints})
   BIG = 1e9   # a threshold no error reaches = term absent
   c.anchor_pos_threshold = float(tf["bad_anchor_pos_z_only"]["params"]["threshold"]) if "bad_anchor_pos_z_only" in tf else BIG
   c.anchor_ori_threshold = float(tf["bad_anchor_ori"]["params"]["threshold"]) if "bad_anchor_ori" in tf else BIG
@@ -836,6 +844,11 @@ def tracking_from_manager_cfg(cfg, m, time_step_total: int, robot: str = "g1") -
     if got != want:
       raise UnsupportedTermError(f"tracking observation group '{group}': terms {got} differ from the kernel's layout {want}")
     for n, t in terms:
+      want_biased = group == "policy" and t["func"] == "joint_pos_rel"     # the kernels' layout: biased encoder reading for the policy only
+      _check_params("observation term", n, t["func"], t["params"], ("sensor_name",),
+                    {**motion, "asset_cfg": all_joints, "biased": (lambda v, wb=want_biased: bool(v) == wb)})
+      if want_biased and not t["params"].get("biased"):
+        raise UnsupportedTermError(f"tracking observation term '{n}': the kernels write joint_pos_rel(biased=True) into the policy group")
       if t["clip"] or t["scale"] is not None or t["delay_max_lag"] > 0 or t["history_length"] > 0 or g.get("history_length"):
         raise UnsupportedTermError(f"tracking observation term '{n}': clip / scale / delay / history are not wired for the tracking env")
     if group == "policy":

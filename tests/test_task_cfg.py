@@ -196,3 +196,7 @@ def test_tracking_cfg_edits_and_unsupported_terms():
   bad(lambda x: x["terminations"].update(t=dict(func="bad_orientation", time_out=False, params={"limit_angle": 1.0})), "bad_orientation")
   bad(lambda x: x["observations"]["policy"]["terms"].pop("base_lin_vel"), "differ from the kernel's layout")
   bad(lambda x: x["events"].update(e=dict(func="reset_joints_by_offset", mode="reset", params={}, interval_range_s=None)), "reset_joints_by_offset")
+  bad(lambda x: x["observations"]["policy"]["terms"]["joint_pos"]["params"].update(biased=False), "biased")
+  bad(lambda x: x["observations"]["critic"]["terms"]["joint_pos"]["params"].update(biased=True), "biased")
+  bad(lambda x: x["rewards"]["motion_body_pos"]["params"].update(command_name="other"), "command_name")
+  bad(lambda x: x["rewards"]["motion_body_pos"]["params"].update(body_names=["pelvis"]), "parameter 'body_names' is not consumed")
