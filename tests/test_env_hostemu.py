@@ -221,3 +221,36 @@ def test_terrain_curriculum_matches_oracle(mode):
   assert moved > B // 2 and (mode == 3 or wrapped > 0)
   # reset poses sit on the (possibly updated) origins
   assert np.all((s.terrain_level >= 0) & (s.terrain_level < rows)) and np.all((s.terrain_type >= 0) & (s.terrain_type < cols))
+
+
+def test_reward_manager_zeroes_nan_and_inf_terms():
+  """RewardManager.compute turns a NaN / +-Inf term VALUE into 0 for that env and term, the other terms still count
+  (managers/reward_manager.py:77-91; the reference's tests/test_rewards.py:235-273)."""
+  m = mjlab_b200.load_model("g1_flat")
+  cfg = envcfg.velocity_cfg(m, "g1")
+  cfg.push_enabled = False
+  g = load_golden("g1")
+  B = g["actions"].shape[1]
+  k = envcfg.REWARD_NAMES.index("angular_momentum")
+  rew, step = [], []
+  for poison in (False, True):
+    sim = HostSim(m, B, nconmax=35, njmax=300)
+    env = HostEnv(sim, cfg)
+    init_state_from_golden(env, g)
+    env.action_in[:] = g["actions"][0]
+    env.stage(0)
+    upload(sim, snapshot(g, 0, m))
+    if poison:
+      sim.sensordata[1, cfg.angmom_adr] = np.nan
+      sim.sensordata[3, cfg.angmom_adr] = np.inf
+      sim.sensordata[4, cfg.angmom_adr] = -np.inf     # squared: +inf
+    env.stage(2)
+    rew.append(env.reward.copy()); step.append(env.step_reward.copy())
+  clean_r, bad_r = rew
+  clean_s, bad_s = step
+  assert np.all(np.isfinite(bad_r)) and np.all(np.isfinite(bad_s))
+  for w in (1, 3, 4):
+    assert bad_s[w, k] == 0.0 and clean_s[w, k] != 0.0
+    np.testing.assert_allclose(bad_r[w], clean_r[w] - clean_s[w, k] * np.float32(cfg.step_dt), rtol=1e-5, atol=1e-7)
+  others = [w for w in range(B) if w not in (1, 3, 4)]
+  np.testing.assert_array_equal(bad_r[others], clean_r[others])
