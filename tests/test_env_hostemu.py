@@ -254,3 +254,35 @@ def test_reward_manager_zeroes_nan_and_inf_terms():
     np.testing.assert_allclose(bad_r[w], clean_r[w] - clean_s[w, k] * np.float32(cfg.step_dt), rtol=1e-5, atol=1e-7)
   others = [w for w in range(B) if w not in (1, 3, 4)]
   np.testing.assert_array_equal(bad_r[others], clean_r[others])
+
+
+def test_action_history_tracking_and_reset():
+  """ActionManager: action / prev_action / prev_prev_action shift on every process_action and are zeroed for the envs that reset
+  (managers/action_manager.py:100-120; the reference's tests/test_action_manager.py:51-118), here in k_env_action / the reset inside
+  k_env_post."""
+  m = mjlab_b200.load_model("go1_flat")
+  cfg = envcfg.velocity_cfg(m, "go1")
+  cfg.push_enabled = False
+  B = 4
+  sim = HostSim(m, B, nconmax=35, njmax=300)
+  env = HostEnv(sim, cfg)
+  sim.forward()
+  assert not env.action.any() and not env.prev_action.any() and not env.prev_prev_action.any()
+  acts = [np.full((B, cfg.nj), 0.1 * i, np.float32) for i in range(1, 5)]
+  for t, a in enumerate(acts):
+    env.action_in[:] = a
+    env.stage(0)
+    np.testing.assert_array_equal(env.action, a)
+    np.testing.assert_array_equal(env.prev_action, acts[t - 1] if t >= 1 else 0 * a)
+    np.testing.assert_array_equal(env.prev_prev_action, acts[t - 2] if t >= 2 else 0 * a)
+  # envs 0 and 2 time out in this step's post stage -> their history is cleared, the others keep theirs
+  env.episode_length[:] = 0
+  env.episode_length[[0, 2]] = cfg.max_episode_length
+  env.stage(2)
+  assert env.reset_buf[[0, 2]].all() and not env.reset_buf[[1, 3]].any()
+  for w in (0, 2):
+    assert not env.action[w].any() and not env.prev_action[w].any() and not env.prev_prev_action[w].any()
+  for w in (1, 3):
+    np.testing.assert_array_equal(env.action[w], acts[3][w])
+    np.testing.assert_array_equal(env.prev_action[w], acts[2][w])
+    np.testing.assert_array_equal(env.prev_prev_action[w], acts[1][w])
