@@ -79,6 +79,9 @@ enum b2_mf {
   B2_MF_SGEOM_XMAT,       /* ngeom*9 */
   B2_MF_FIELD_AABB,       /* nfield*6: world AABB (centre, half extents) of each field geom */
   B2_MF_FIELD_GRID,       /* 4: x0, y0, cell edge, 1 / cell edge of the uniform xy grid over the field */
+  B2_MF_DOF_FRICTIONLOSS, /* nv: dry-friction force bound per dof (> 0 gives the dof a friction-loss constraint row) */
+  B2_MF_DOF_SOLREF,       /* nv*2: solref of the friction-loss row (MuJoCo's dof_solref, <joint solreffriction>) */
+  B2_MF_DOF_SOLIMP,       /* nv*5: solimp of the friction-loss row (dof_solimp, <joint solimpfriction>) */
   B2_MF_COUNT
 };
 
@@ -199,7 +202,7 @@ enum b2_df {
 enum b2_di {
   B2_DI_NCON = 0,          /* 1 */
   B2_DI_NEFC,              /* 1 */
-  B2_DI_NL,                /* 1: number of joint-limit rows (efc rows 0..nl-1) */
+  B2_DI_NL,                /* 1: number of joint-limit rows (efc rows nf..nf+nl-1, after the friction-loss rows) */
   B2_DI_SOLVER_NITER,      /* 1 */
   B2_DI_CONTACT_GEOM,      /* nconmax*2 */
   B2_DI_CONTACT_DIM,       /* nconmax */
@@ -215,6 +218,7 @@ enum b2_di {
                               from here instead of idling through the launch's tail; internal */
   B2_DI_SOLVE_CTR,         /* 4: row w0 = {worlds solved, next ring entry to post-process, -, -} of that launch; internal */
   B2_DI_SMOOTH_MEMO,       /* 1: 1 = MEMO_QPOS / MEMO_QVEL describe the stage outputs in HBM; write 0 after changing MODEL fields; internal */
+  B2_DI_NF,                /* 1: number of friction-loss rows (efc rows 0..nf-1; MuJoCo's order: friction, limits, contacts) */
   B2_DI_COUNT
 };
 
@@ -227,6 +231,8 @@ typedef struct b2_model {
   int has_accelerometer, has_subtreevel;
   int nlimited;      /* number of limited hinge/slide joints (bounds the joint-limit rows) */
   int maxchain;      /* max over candidate pairs of |dofs(body1) U dofs(body2)| (compact row width bound) */
+  int nfriction;     /* capacity for friction-loss rows: 0 = the model has none (the solver kernels without the friction
+                      * code are launched), else an upper bound on the dofs with dof_frictionloss > 0 in any world */
   /* geom field: a large set of static boxes (the rough-terrain grid, terrains/terrain_generator.py) is not enumerated as
    * candidate pairs; moving "query" geoms look the boxes up in a uniform xy grid.  nfield == 0: no field. */
   int nfield, nfq, ndyn, field_nx, field_ny;

@@ -103,7 +103,7 @@ static __host__ __device__ inline int solve_slot(int p, int n, int cap) {
 // are still iterating - so the sensor stage fills the solver's tail instead of following it.  A claimed entry is waited
 // for only when all earlier-finished worlds are already taken, i.e. at the very end of the launch.  All CTAs are resident
 // (grid <= SMs x occupancy), so every claimed entry is eventually produced.
-template <bool CG>
+template <bool CG, bool FR>
 __global__ void __launch_bounds__(B2_WPB * 32, B2_SOLVE_MINB) k_solve_t(const KModel m, const KData d, const SolveSmem L, const PostSmem LP, int post_mode, const unsigned char* mask, const int* gate, int w0, int w1) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   real* smem = reinterpret_cast<real*>(smem_raw);
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(B2_WPB * 32, B2_SOLVE_MINB) k_solve_t(const KM
 #ifdef B2_TIMING
       unsigned long long t0 = b2_gtime();
 #endif
-      solve_world_t<CG>(m, d, L, w, smem + (size_t)warp * L.fixed_total, arena, actl);
+      solve_world_t<CG, FR>(m, d, L, w, smem + (size_t)warp * L.fixed_total, arena, actl);
       __syncwarp();
 #ifdef B2_TIMING
       if (lane == 0 && w < 16384) { g_tim[3 * w] = t0; g_tim[3 * w + 1] = b2_gtime(); g_tim[3 * w + 2] = b2_smid(); }
@@ -166,13 +166,20 @@ __global__ void __launch_bounds__(B2_WPB * 32, B2_SOLVE_MINB) k_solve_t(const KM
   }
 }
 
-// the two instantiations under the names the profiles use: k_solve (Newton, the shipped configuration) and k_solve_cg
-#define k_solve k_solve_t<false>
-#define k_solve_cg k_solve_t<true>
-static void launch_solve(bool cg, int grid, size_t smem, cudaStream_t st, const KModel& km, const KData& kd, const SolveSmem& lv, const PostSmem& lp,
+// the instantiations under the names the profiles use: k_solve (Newton, no friction-loss rows: the shipped configuration),
+// k_solve_cg, and the two that carry the friction-loss row code (models with dof_frictionloss > 0)
+#define k_solve k_solve_t<false, false>
+#define k_solve_cg k_solve_t<true, false>
+#define k_solve_fr k_solve_t<false, true>
+#define k_solve_cg_fr k_solve_t<true, true>
+typedef void (*solve_kernel_t)(const KModel, const KData, const SolveSmem, const PostSmem, int, const unsigned char*, const int*, int, int);
+static solve_kernel_t solve_kernel(const KModel& km) {
+  const bool cg = km.solver == 1, fr = km.nfriction > 0;
+  return fr ? (cg ? (solve_kernel_t)k_solve_cg_fr : (solve_kernel_t)k_solve_fr) : (cg ? (solve_kernel_t)k_solve_cg : (solve_kernel_t)k_solve);
+}
+static void launch_solve(int grid, size_t smem, cudaStream_t st, const KModel& km, const KData& kd, const SolveSmem& lv, const PostSmem& lp,
                          int post_mode, const unsigned char* mask, const int* gate, int w0, int w1) {
-  if (cg) k_solve_cg<<<grid, B2_WPB * 32, smem, st>>>(km, kd, lv, lp, post_mode, mask, gate, w0, w1);
-  else k_solve<<<grid, B2_WPB * 32, smem, st>>>(km, kd, lv, lp, post_mode, mask, gate, w0, w1);
+  solve_kernel(km)<<<grid, B2_WPB * 32, smem, st>>>(km, kd, lv, lp, post_mode, mask, gate, w0, w1);
 }
 
 // Counting sort of the worlds by predicted solver cost, heaviest first (one CTA).  Which solver slot a world lands in has no
@@ -297,14 +304,8 @@ static int make_plan(const b2_model* m, const b2_data* d, Plan* p) {
   p->ls = smooth_smem_layout(m->nq, m->nv, m->nu, m->nbody, m->njnt, B2_NCAND_MAX);
   // true upper bounds on rows / runs / pools of ONE world; the arena of a CTA holds one such world, and two worlds
   // whenever their actual demand fits (the common case: demand is an order of magnitude below the bound)
-  int rows_max = 4 * d->nconmax + 2 * m->nlimited;
-  if (rows_max > d->njmax) rows_max = d->njmax;
-  if (rows_max < 1) rows_max = 1;
-  int runs_max = 2 * m->nlimited + d->nconmax + 1;
-  int wpad = m->maxchain | 1;
-  int pool_max = 2 * m->nlimited + 4 * d->nconmax * wpad;
-  if (pool_max > 65535) pool_max = 65535;
-  int dofs_max = 2 * m->nlimited + d->nconmax * m->maxchain;
+  const SolveCaps caps = solve_caps(m->nlimited, m->nfriction, d->nconmax, d->njmax, m->maxchain);
+  const int rows_max = caps.rows, runs_max = caps.runs, pool_max = caps.pool, dofs_max = caps.dofs;
   int arena = solve_arena_need(rows_max, runs_max, dofs_max, pool_max, d->nconmax > 0 ? d->nconmax : 1);
   // The strict bound assumes every contact couples the two longest kinematic chains (maxchain); real worlds stay an
   // order of magnitude below it (G1, random actions: median 30 rows, max 116 of 198).  Cap the arena so that
@@ -312,7 +313,7 @@ static int make_plan(const b2_model* m, const b2_data* d, Plan* p) {
   // from the tail of its contact list exactly like njmax truncation does (counted in nefc_dropped).
   p->lp = post_smem_layout(m->nv);
   {
-    SolveSmem probe = solve_smem_layout(m->nv, rows_max, m->maxchain, 0, p->lp.total);
+    SolveSmem probe = solve_smem_layout(m->nv, rows_max, m->maxchain, 0, p->lp.total, m->nfriction);
     long budget = (233472 / B2_SOLVE_MINB - 1024 - 16 - (long)probe.fixed_total * B2_WPB * (long)sizeof(real)) / (long)sizeof(real);
     if (budget < arena / 2) budget = arena / 2;
     if (arena > budget) arena = (int)budget & ~3;
@@ -324,7 +325,7 @@ static int make_plan(const b2_model* m, const b2_data* d, Plan* p) {
     if (arena < floor_) arena = floor_;
   }
   arena = (arena + 3) & ~3;   // the two-ended allocator of k_solve works in units of 4 floats
-  p->lv = solve_smem_layout(m->nv, rows_max, m->maxchain, arena, p->lp.total);
+  p->lv = solve_smem_layout(m->nv, rows_max, m->maxchain, arena, p->lp.total, m->nfriction);
   p->smem_smooth = (size_t)p->ls.total * sizeof(real) * B2_SMOOTH_WPB;
   p->smem_solve = ((size_t)p->lv.fixed_total * B2_WPB + p->lv.arena_cap) * sizeof(real) + 16;
   p->smem_post = (size_t)p->lp.total * sizeof(real) * B2_POST_WPB;
@@ -348,7 +349,7 @@ static int g_nplans = 0;
 static PlanKey plan_key(const b2_model* m, const b2_data* d) {
   int dev = -1;
   cudaGetDevice(&dev);
-  PlanKey k = {{m->nq, m->nv, m->nu, m->nbody, m->njnt, m->nlimited, m->maxchain, d->nconmax, d->njmax, dev, m->solver, 0}};
+  PlanKey k = {{m->nq, m->nv, m->nu, m->nbody, m->njnt, m->nlimited, m->maxchain, d->nconmax, d->njmax, dev, m->solver, m->nfriction}};
   return k;
 }
 
@@ -369,7 +370,7 @@ static PlanEntry* plan_lookup(const b2_model* m, const b2_data* d, bool rebuild)
 
 extern "C" {
 
-int b2_abi_version(void) { return 1; }
+int b2_abi_version(void) { return 2; }
 const char* b2_last_error(void) { return g_err; }
 int b2_debug_solver_slot(int rank, int nworld) { return solve_slot(rank, nworld, B2_SOLVE_DEFAULT_CTAS); }
 int b2_sizeof_model(void) { return (int)sizeof(b2_model); }
@@ -401,17 +402,15 @@ int b2_check(const b2_model* m, const b2_data* d) {
   cudaError_t e;
   e = cudaFuncSetAttribute(k_smooth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_smooth);
   if (e != cudaSuccess) return fail("cudaFuncSetAttribute(k_smooth): %s", cudaGetErrorString(e));
-  e = cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_solve);
+  const solve_kernel_t ksolve = solve_kernel(*reinterpret_cast<const KModel*>(m));
+  e = cudaFuncSetAttribute(ksolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_solve);
   if (e != cudaSuccess) return fail("cudaFuncSetAttribute(k_solve): %s", cudaGetErrorString(e));
-  e = cudaFuncSetAttribute(k_solve_cg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_solve);
-  if (e != cudaSuccess) return fail("cudaFuncSetAttribute(k_solve_cg): %s", cudaGetErrorString(e));
   e = cudaFuncSetAttribute(k_post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_post);
   if (e != cudaSuccess) return fail("cudaFuncSetAttribute(k_post): %s", cudaGetErrorString(e));
   // The solver grid must be fully resident (its warps wait on each other's results in the fused sensor stage): size it
   // from what the occupancy calculator grants on THIS device, not from a compiled-in SM count.
   int per_sm = 0;
-  e = m->solver == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_cg, B2_WPB * 32, p.smem_solve)
-                     : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve, B2_WPB * 32, p.smem_solve);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ksolve, B2_WPB * 32, p.smem_solve);
   if (e != cudaSuccess || per_sm < 1 || nsm < 1) return fail("k_solve does not fit on an SM (%s)", cudaGetErrorString(e));
   p.solve_cap = per_sm * nsm;
   pe->checked = true;
@@ -434,12 +433,11 @@ static void launch_range(const Plan& p, const KModel& km, const KData& kd, cudaS
   int n = w1 - w0;
   k_smooth<<<(n + B2_SMOOTH_WPB - 1) / B2_SMOOTH_WPB, B2_SMOOTH_WPB * 32, p.smem_smooth, st>>>(km, kd, p.ls, B2_NCAND_MAX, memo_consume, mask, gate, w0, w1);
   k_order<<<1, 1024, 0, st>>>(kd, w0, w1, p.solve_cap, p.order_mode);
-  const bool cg = km.solver == 1;
   if (p.fuse_post) {
-    launch_solve(cg, solve_grid(n, p.solve_cap), p.smem_solve, st, km, kd, p.lv, p.lp, do_integrate ? 2 : 1, mask, gate, w0, w1);
+    launch_solve(solve_grid(n, p.solve_cap), p.smem_solve, st, km, kd, p.lv, p.lp, do_integrate ? 2 : 1, mask, gate, w0, w1);
     g_launches += 3;
   } else {
-    launch_solve(cg, solve_grid(n, p.solve_cap), p.smem_solve, st, km, kd, p.lv, p.lp, 0, mask, gate, w0, w1);
+    launch_solve(solve_grid(n, p.solve_cap), p.smem_solve, st, km, kd, p.lv, p.lp, 0, mask, gate, w0, w1);
     k_post<<<(n + B2_POST_WPB - 1) / B2_POST_WPB, B2_POST_WPB * 32, p.smem_post, st>>>(km, kd, p.lp, do_integrate, mask, gate, w0, w1);
     g_launches += 4;
   }
@@ -550,9 +548,9 @@ int b2_stage(const b2_model* m, b2_data* d, int stage, int do_integrate, void* s
     k_order<<<1, 1024, 0, st>>>(kd, 0, d->nworld, p.solve_cap, p.order_mode);
     g_launches += 1;
   }
-  else if (stage == 1) launch_solve(km.solver == 1, solve_grid(d->nworld, p.solve_cap), p.smem_solve, st, km, kd, p.lv, p.lp, 0, nullptr, nullptr, 0, d->nworld);
+  else if (stage == 1) launch_solve(solve_grid(d->nworld, p.solve_cap), p.smem_solve, st, km, kd, p.lv, p.lp, 0, nullptr, nullptr, 0, d->nworld);
   else if (stage == 2) k_post<<<(d->nworld + B2_POST_WPB - 1) / B2_POST_WPB, B2_POST_WPB * 32, p.smem_post, st>>>(km, kd, p.lp, do_integrate, nullptr, nullptr, 0, d->nworld);
-  else if (stage == 3) launch_solve(km.solver == 1, solve_grid(d->nworld, p.solve_cap), p.smem_solve, st, km, kd, p.lv, p.lp, do_integrate ? 2 : 1, nullptr, nullptr, 0, d->nworld);
+  else if (stage == 3) launch_solve(solve_grid(d->nworld, p.solve_cap), p.smem_solve, st, km, kd, p.lv, p.lp, do_integrate ? 2 : 1, nullptr, nullptr, 0, d->nworld);
   else if (stage == 4) k_smooth<<<(d->nworld + B2_SMOOTH_WPB - 1) / B2_SMOOTH_WPB, B2_SMOOTH_WPB * 32, p.smem_smooth, st>>>(km, kd, p.ls, B2_NCAND_MAX, 0, nullptr, nullptr, 0, d->nworld);
   else if (stage == 6) k_smooth<<<(d->nworld + B2_SMOOTH_WPB - 1) / B2_SMOOTH_WPB, B2_SMOOTH_WPB * 32, p.smem_smooth, st>>>(km, kd, p.ls, B2_NCAND_MAX, p.memo, nullptr, nullptr, 0, d->nworld);
   else if (stage == 5) k_order<<<1, 1024, 0, st>>>(kd, 0, d->nworld, p.solve_cap, p.order_mode);

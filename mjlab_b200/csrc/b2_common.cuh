@@ -129,7 +129,7 @@ struct KModel {
   int nq, nv, nu, nbody, njnt, ngeom, nsite, nsensor, nsensordata, npair, nmocap, nlevel;
   int integrator, cone, solver, iterations, ls_iterations, disableflags;
   int has_accelerometer, has_subtreevel;
-  int nlimited, maxchain;
+  int nlimited, maxchain, nfriction;
   int nfield, nfq, ndyn, field_nx, field_ny;
   const real* mf[B2_MF_COUNT];
   int mf_stride[B2_MF_COUNT];

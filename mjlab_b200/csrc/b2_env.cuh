@@ -198,7 +198,7 @@ B2_DEV void reset_world(const KModel& m, const KData& d, int w) {
   }
   if (B2_LANE == 0) {
     d.df[B2_DF_TIME][w] = 0;
-    d.di[B2_DI_NCON][w] = 0; d.di[B2_DI_NEFC][w] = 0; d.di[B2_DI_NL][w] = 0; d.di[B2_DI_SOLVER_NITER][w] = 0;
+    d.di[B2_DI_NCON][w] = 0; d.di[B2_DI_NEFC][w] = 0; d.di[B2_DI_NL][w] = 0; d.di[B2_DI_NF][w] = 0; d.di[B2_DI_SOLVER_NITER][w] = 0;
   }
   B2_WSYNC();
 }

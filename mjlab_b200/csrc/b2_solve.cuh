@@ -1,5 +1,5 @@
 // b2_solve.cuh - stage 2 of the physics step, one warp per world:
-//   constraint rows (joint limits, pyramidal contacts) -> efc_J / efc_D / efc_aref
+//   constraint rows (friction loss, joint limits, pyramidal contacts) -> efc_J / efc_D / efc_aref
 //   -> primal Newton solver with exact line search -> qacc, efc_force, qfrc_constraint
 //   -> sensors (IMU trio, subtree angular momentum, contact sensors, ...)
 //   -> integration (implicitfast | Euler), time, warm start
@@ -18,7 +18,7 @@
 // J^T D J is accumulated run by run over w*(w+1)/2 dof pairs instead of nv*(nv+1)/2
 // (G1 foot-ground contact: w = 12 of nv = 35).
 struct SolveSmem {
-  int H, cdof, qvel, qacc, Ma, grad, search, Mv, qfs, qas, qfc, tmp, invd, pairtab, actmask, gold, mgold;  // fixed part, per world
+  int H, cdof, qvel, qacc, Ma, grad, search, Mv, qfs, qas, qfc, tmp, invd, pairtab, actmask, gold, mgold, floss;  // fixed part, per world
   int fixed_total;  // reals per world
   int arena_cap;    // reals of the row arena shared by the worlds of one CTA (>= the demand of one worst-case world)
   int rows_max;     // bound on constraint rows per world
@@ -37,7 +37,22 @@ int solve_arena_need(int rows, int runs, int dofs, int pool, int ncon) {
   return cd + 3 * r4(rows) + r4(2 * runs) + r4((dofs + 3) / 4) + r4(4 * ncon) + r4(pool);
 }
 
-static inline SolveSmem solve_smem_layout(int nv, int rows_max, int maxchain, int arena_cap, int min_fixed = 0) {
+// True upper bounds on the rows / runs / dof-list entries / Jacobian pool of ONE world (the arena of a CTA holds one such world).
+struct SolveCaps { int rows, runs, dofs, pool; };
+static inline SolveCaps solve_caps(int nlimited, int nfriction, int nconmax, int njmax, int maxchain) {
+  SolveCaps c;
+  const int single = 2 * nlimited + nfriction;   // rows of width 1: friction loss, joint limits
+  c.rows = 4 * nconmax + single;
+  if (c.rows > njmax) c.rows = njmax;
+  if (c.rows < 1) c.rows = 1;
+  c.runs = single + nconmax + 1;
+  c.pool = single + 4 * nconmax * (maxchain | 1);
+  if (c.pool > 65535) c.pool = 65535;
+  c.dofs = single + nconmax * maxchain;
+  return c;
+}
+
+static inline SolveSmem solve_smem_layout(int nv, int rows_max, int maxchain, int arena_cap, int min_fixed = 0, int nfriction = 0) {
   SolveSmem s;
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
@@ -49,6 +64,7 @@ static inline SolveSmem solve_smem_layout(int nv, int rows_max, int maxchain, in
   s.pairtab = take((maxchain * (maxchain + 1) / 2 + 1) / 2);  // ushort (a << 8 | b) per lower-triangle pair index
   s.actmask = take((rows_max + 31) / 32);  // bit r: row r was active at the last Hessian factorisation
   s.gold = take(nv); s.mgold = take(nv);   // CG solver: previous gradient and previous M^-1 gradient (Polak-Ribiere)
+  s.floss = take(nfriction > 0 ? nv : 0);  // friction-loss rows (rows 0..nf-1, nf <= nv): the row's force bound
   s.fixed_total = o > min_fixed ? o : ((min_fixed + 3) & ~3);  // the fused sensor stage reuses the warp's fixed part as its scratch
   s.arena_cap = arena_cap;
   s.rows_max = rows_max;
@@ -138,13 +154,36 @@ static long long b2h_flip_hist[66] = {0};   // [k < 64]: Newton iterations (it >
 #define B2_FLOOR_MULT 8   // rounding floor of the convergence test, in units of eps * |cost| (experiments: tools/floor_experiment.py)
 #endif
 
-B2_DEVN LsPnt ls_eval(real alpha, real q0g, real q1g, real q2g, const real* jar, const real* jv, const real* D, int nefc) {  // @region linesearch
+// Friction-loss row (mj_constraintUpdate, mjCNSTR_FRICTION_DOF): Huber cost of the row's residual x with force bound f and
+// R = 1 / D - quadratic inside |x| < R f, linear outside, where the force saturates at -/+ f.  Returns the cost; `force` is
+// the row's efc_force, `wgt` its Hessian weight (D in the quadratic zone, else 0).
+B2_DEV real fric_row(real x, real D, real f, real& force, real& wgt) {
+  const real Rf = f / D;
+  if (x <= -Rf) { force = f; wgt = 0; return f * (-(real)0.5 * Rf - x); }
+  if (x >= Rf) { force = -f; wgt = 0; return f * (-(real)0.5 * Rf + x); }
+  force = -D * x; wgt = D;
+  return (real)0.5 * D * x * x;
+}
+// its contribution to the line search's quadratic q0 + alpha q1 + alpha^2 q2 at the trial point x = jar + alpha jv (mj PrimalEval)
+B2_DEV void fric_quad(real x, real ja, real v, real D, real f, real& q0, real& q1, real& q2) {
+  const real Rf = f / D;
+  if (x <= -Rf) { q0 += f * (-(real)0.5 * Rf - ja); q1 -= f * v; }
+  else if (x >= Rf) { q0 += f * (-(real)0.5 * Rf + ja); q1 += f * v; }
+  else { const real dj = D * ja; q0 += (real)0.5 * dj * ja; q1 += dj * v; q2 += (real)0.5 * D * v * v; }
+}
+
+// FR: the world may hold friction-loss rows (rows 0..nf-1, bounds in floss).  A template parameter like CG below: models
+// without friction loss run instantiations that carry none of this code.
+template <bool FR>
+B2_DEVN LsPnt ls_eval(real alpha, real q0g, real q1g, real q2g, const real* jar, const real* jv, const real* D, int nefc, int nf, const real* floss) {  // @region linesearch
   B2_LS_COUNT();
   real q0 = 0, q1 = 0, q2 = 0;
   B2_UNROLL1   // (unrolling by 2 / 4 to overlap the passes' loads was measured: +2 % kernel time, code size again)
   for (int r = B2_LANE; r < nefc; r += B2_NLANE) {
     real x = jar[r] + alpha * jv[r];
-    if (x < 0) {
+    if (FR && r < nf) {
+      fric_quad(x, jar[r], jv[r], D[r], floss[r], q0, q1, q2);
+    } else if (x < 0) {
       real dj = D[r] * jar[r];
       q0 += (real)0.5 * dj * jar[r];
       q1 += dj * jv[r];
@@ -167,13 +206,21 @@ B2_DEVN LsPnt ls_eval(real alpha, real q0g, real q1g, real q2g, const real* jar,
 // together reads each row once and lets the three warp reductions overlap instead of running back to back - the line search
 // is a chain of dependent reductions, and on the heaviest worlds (which set the kernel's duration) it is a third of the time.
 // Each point's sums are accumulated in the same order as ls_eval does, so the values are bit-identical to three calls.
-B2_DEVN void ls_eval3(const real* alpha, LsPnt* out, real q0g, real q1g, real q2g, const real* jar, const real* jv, const real* D, int nefc) {
+template <bool FR>
+B2_DEVN void ls_eval3(const real* alpha, LsPnt* out, real q0g, real q1g, real q2g, const real* jar, const real* jv, const real* D, int nefc, int nf, const real* floss) {
   B2_LS_COUNT();
   real a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0, c0 = 0, c1 = 0, c2 = 0;
   const real al0 = alpha[0], al1 = alpha[1], al2 = alpha[2];
   B2_UNROLL1
   for (int r = B2_LANE; r < nefc; r += B2_NLANE) {
     const real ja = jar[r], v = jv[r], Dr = D[r];
+    if (FR && r < nf) {
+      const real f = floss[r];
+      fric_quad(ja + al0 * v, ja, v, Dr, f, a0, a1, a2);
+      fric_quad(ja + al1 * v, ja, v, Dr, f, b0, b1, b2);
+      fric_quad(ja + al2 * v, ja, v, Dr, f, c0, c1, c2);
+      continue;
+    }
     const real dj = Dr * ja;
     const real t0 = (real)0.5 * dj * ja, t1 = dj * v, t2 = (real)0.5 * Dr * v * v;
     if (ja + al0 * v < 0) { a0 += t0; a1 += t1; a2 += t2; }
@@ -219,8 +266,9 @@ B2_DEV bool ls_move_bracket(LsPnt& p, const LsPnt* cand) {
 // Exact 1-D minimisation along `search` (MuJoCo's iterative primal line search:
 // Newton steps until the derivative changes sign, then bracket refinement).
 // `cost0` / `slope0`: cost and directional derivative grad.search at alpha = 0, known from the Newton update.
+template <bool FR>
 B2_DEVN real linesearch(real q0g, real q1g, real q2g, real snorm, real tolerance, real ls_tolerance, int ls_iterations,
-                       real scale, const real* jar, const real* jv, const real* D, int nefc, real cost0, real slope0) {
+                       real scale, const real* jar, const real* jv, const real* D, int nefc, real cost0, real slope0, int nf, const real* floss) {
   if (snorm < B2_MINVAL) return 0;
   real gtol = tolerance * ls_tolerance * snorm / scale;
   int nev = 0;
@@ -234,9 +282,9 @@ B2_DEVN real linesearch(real q0g, real q1g, real q2g, real snorm, real tolerance
     p0.alpha = 0; p0.cost = cost0; p0.d1 = slope0; p0.d2 = -slope0;
   } else {
     B2_LSSTAT(1)
-    p0 = ls_eval(0, q0g, q1g, q2g, jar, jv, D, nefc);
+    p0 = ls_eval<FR>(0, q0g, q1g, q2g, jar, jv, D, nefc, nf, floss);
   }
-  LsPnt p1 = ls_eval(p0.alpha - p0.d1 / p0.d2, q0g, q1g, q2g, jar, jv, D, nefc); ++nev;
+  LsPnt p1 = ls_eval<FR>(p0.alpha - p0.d1 / p0.d2, q0g, q1g, q2g, jar, jv, D, nefc, nf, floss); ++nev;
   if (p0.cost < p1.cost) p1 = p0;
   if (fabs(p1.d1) < ls_gtol(p1, gtol)) return p1.alpha;
   real dir = p1.d1 < 0 ? (real)1 : (real)-1;
@@ -245,7 +293,7 @@ B2_DEVN real linesearch(real q0g, real q1g, real q2g, real snorm, real tolerance
   while (p1.d1 * dir <= -ls_gtol(p1, gtol) && nev < ls_iterations) {
     p2 = p1; p2set = true;
     B2_LSSTAT(1)
-    p1 = ls_eval(p1.alpha - p1.d1 / p1.d2, q0g, q1g, q2g, jar, jv, D, nefc); ++nev;
+    p1 = ls_eval<FR>(p1.alpha - p1.d1 / p1.d2, q0g, q1g, q2g, jar, jv, D, nefc, nf, floss); ++nev;
     if (fabs(p1.d1) < ls_gtol(p1, gtol)) return p1.alpha;
   }
   if (nev >= ls_iterations || !p2set) return p1.alpha;
@@ -261,7 +309,7 @@ B2_DEVN real linesearch(real q0g, real q1g, real q2g, real snorm, real tolerance
     const bool want_mid = nev < ls_iterations;
     real al[3] = {p1.alpha - p1.d1 / p1.d2, want_mid ? (real)0.5 * (p1.alpha + p2.alpha) : (real)0, 0};
     LsPnt out[3];
-    ls_eval3(al, out, q0g, q1g, q2g, jar, jv, D, nefc);
+    ls_eval3<FR>(al, out, q0g, q1g, q2g, jar, jv, D, nefc, nf, floss);
     p1next = out[0]; pmid = out[1];
   }
   while (nev < ls_iterations) {
@@ -280,7 +328,7 @@ B2_DEVN real linesearch(real q0g, real q1g, real q2g, real snorm, real tolerance
                   want_mid ? (real)0.5 * (p1.alpha + p2.alpha) : (real)0};
     LsPnt out[3];
     B2_LSSTAT(2)
-    ls_eval3(al, out, q0g, q1g, q2g, jar, jv, D, nefc);
+    ls_eval3<FR>(al, out, q0g, q1g, q2g, jar, jv, D, nefc, nf, floss);
     if (b1) p1next = out[0];
     if (b2) p2next = out[1];
     pmid = out[2];
@@ -365,7 +413,7 @@ __device__ unsigned long long g_phase[8 * 16384];
 // CG: compile-time choice of the search direction (true = mjSOL_CG: M-preconditioned Polak-Ribiere; false = Newton).  A template
 // and not a run-time branch: the Newton kernel's loop is instruction-fetch bound, and the CG code inside it cost 5 % (0.394 ->
 // 0.414 ms per launch) even though it never ran.
-template <bool CG>
+template <bool CG, bool FR>
 B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, int w, real* sm, real* arena, int* actl) {  // @region setup_loads
   B2_PH_BEGIN()
   const int nv = m.nv, nb = m.nbody, nq = m.nq, nu = m.nu, njmax = d.njmax, nconmax = d.nconmax;
@@ -376,6 +424,7 @@ B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, i
   unsigned short* pairtab = (unsigned short*)(sm + L.pairtab);
   unsigned* actmask = (unsigned*)(sm + L.actmask);
   real* gold = sm + L.gold; real* mgold = sm + L.mgold;
+  real* floss = sm + L.floss;   // FR only
   constexpr bool cg = CG;   // mjSOL_CG: M is the preconditioner, Polak-Ribiere directions (mj_solCG)
   const int ld = b2_ld(nv);
   const int* body_parent = MI(B2_MI_BODY_PARENTID);
@@ -419,6 +468,14 @@ B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, i
   int rows_cap, runs_cap, dofs_cap, jpool_cap;
   {
     int nlim = 0, crow = 0, ckept = 0, cdofs = 0, cpool = 0;
+    if (FR) {   // friction-loss rows are rows of width 1 like the limit rows: counted with them
+      const real* dfl = MF(B2_MF_DOF_FRICTIONLOSS);
+      B2_UNROLL1
+      for (int base = 0; base < nv; base += B2_NLANE) {
+        int e = base + B2_LANE;
+        nlim += b2_popc(b2_ballot(e < nv && dfl[e] > 0));
+      }
+    }
     B2_UNROLL1
     for (int base = 0; base < 2 * m.njnt; base += B2_NLANE) {
       int s = base + B2_LANE;
@@ -509,6 +566,40 @@ B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, i
 
   // ---- joint-limit rows (ordered: joint, lower then upper); each is its own run of width 1 ----  // @region limit_rows
   int nefc = 0;
+  if (FR) {
+    // ---- friction-loss rows first (MuJoCo's row order: friction, limits, contacts), one per dof with frictionloss > 0
+    const real* dfl = MF(B2_MF_DOF_FRICTIONLOSS);
+    B2_UNROLL1
+    for (int base = 0; base < nv; base += B2_NLANE) {
+      int e = base + B2_LANE;
+      const real fl = e < nv ? dfl[e] : (real)0;
+      const bool on = fl > 0;
+      unsigned bal = b2_ballot(on);
+      if (on) {
+        int row = nefc + b2_popc(bal & b2_lanemask_lt());
+        if (row < rows_cap) {
+          jpool[row] = 1;
+          rundofs[row] = (unsigned char)e;
+          rowinfo[row] = row | (row << 16);
+          runinfo[2 * row] = row | (1 << 16);
+          runinfo[2 * row + 1] = row | (1 << 16);
+          rowsrc[row] = -(0x10000 + e);
+          floss[row] = fl;
+          g_pos[row] = 0;
+          g_mar[row] = 0;
+          if (export_J) {
+            real* Jr = gJ + (size_t)row * nv;
+            B2_UNROLL1
+            for (int k = 0; k < nv; ++k) Jr[k] = 0;
+            Jr[e] = 1;
+          }
+        }
+      }
+      nefc += b2_popc(bal);
+    }
+    if (nefc > rows_cap) nefc = rows_cap;
+  }
+  const int nf = nefc;
   {
     B2_UNROLL1
     for (int base = 0; base < 2 * m.njnt; base += B2_NLANE) {
@@ -547,7 +638,7 @@ B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, i
     }
     if (nefc > rows_cap) nefc = rows_cap;
   }
-  const int nl = nefc;
+  const int nl = nefc;   // rows of width 1: nf friction-loss rows, then nl - nf joint-limit rows
 
   // ---- contact rows ---------------------------------------------------------------------------  // @region contact_rows
   const real* c_pos = d.df[B2_DF_CONTACT_POS] + (size_t)w * nconmax * 3;
@@ -687,7 +778,8 @@ B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, i
     for (int c = B2_LANE; c < ncon; c += B2_NLANE) c_adr[c] = cinfo[4 * c];
     if (B2_LANE == 0) {
       d.di[B2_DI_NEFC][w] = nefc;
-      d.di[B2_DI_NL][w] = nl;
+      d.di[B2_DI_NL][w] = nl - nf;
+      d.di[B2_DI_NF][w] = nf;
       d.di[B2_DI_NEFC_DROPPED][w] = ndrop;
     }
     // dense export for tests / API consumers that ask for efc_J
@@ -736,7 +828,11 @@ B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, i
       int src = rowsrc[r];
       real invw, k, b, imp;
       real pos = g_pos[r] - g_mar[r];
-      if (src < 0) {
+      if (FR && src <= -0x10000) {
+        int e = -src - 0x10000;
+        invw = diw[e];
+        kbi(timestep, MF(B2_MF_DOF_SOLREF) + 2 * e, MF(B2_MF_DOF_SOLIMP) + 5 * e, pos, k, b, imp);
+      } else if (src < 0) {
         int j = -src - 1;
         invw = diw[jnt_dofadr[j]];
         kbi(timestep, jnt_solref + 2 * j, jnt_solimp + 5 * j, pos, k, b, imp);
@@ -777,7 +873,11 @@ B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, i
     rows_dot(jpool, rowinfo, runinfo, rundofs, nefc, qas, jar, aref);
     real cs = 0;
     B2_UNROLL1
-    for (int r = B2_LANE; r < nefc; r += B2_NLANE) { real x = jar[r]; if (x < 0) cs += (real)0.5 * D[r] * x * x; }
+    for (int r = B2_LANE; r < nefc; r += B2_NLANE) {
+      real x = jar[r];
+      if (FR && r < nf) { real f_, w_; cs += fric_row(x, D[r], floss[r], f_, w_); }
+      else if (x < 0) cs += (real)0.5 * D[r] * x * x;
+    }
     cs = b2_wsum(cs);
     // cost at the warm start
     B2_UNROLL1
@@ -786,7 +886,11 @@ B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, i
     rows_dot(jpool, rowinfo, runinfo, rundofs, nefc, qacc, jar, aref);
     real cw = 0;
     B2_UNROLL1
-    for (int r = B2_LANE; r < nefc; r += B2_NLANE) { real x = jar[r]; if (x < 0) cw += (real)0.5 * D[r] * x * x; }
+    for (int r = B2_LANE; r < nefc; r += B2_NLANE) {
+      real x = jar[r];
+      if (FR && r < nf) { real f_, w_; cw += fric_row(x, D[r], floss[r], f_, w_); }
+      else if (x < 0) cw += (real)0.5 * D[r] * x * x;
+    }
     real gw = 0;
     symv_global(M, nv, ld, qacc, Ma);
     B2_UNROLL1
@@ -820,11 +924,18 @@ B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, i
         bool act = false;
         if (r < nefc) {
           real x = jar[r];
+          if (FR && r < nf) {   // friction loss: "active" = in the quadratic zone (the only state that enters the Hessian)
+            real f_, w_;
+            c1 += fric_row(x, D[r], floss[r], f_, w_);
+            wgt[r] = w_; frc[r] = f_;
+            act = w_ != 0;
+          } else {
           act = x < 0;
           real wr = act ? D[r] : (real)0;
           wgt[r] = wr;
           frc[r] = -wr * x;
           c1 += (real)0.5 * wr * x * x;
+          }
         }
         unsigned bal = b2_ballot(act);
 #ifdef B2_HOSTEMU
@@ -1001,7 +1112,7 @@ B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, i
       b2_wsum3(q1, q2, gs);
       rows_dot(jpool, rowinfo, runinfo, rundofs, nefc, search, jv, nullptr);
       B2_PH(5)
-      real alpha = linesearch(gauss, q1, q2, sn, tolerance, ls_tolerance, m.ls_iterations, scale, jar, jv, D, nefc, cost, cg ? (real)0 : gs);   // the alpha = 0 shortcut needs H search = -grad: Newton only
+      real alpha = linesearch<FR>(gauss, q1, q2, sn, tolerance, ls_tolerance, m.ls_iterations, scale, jar, jv, D, nefc, cost, cg ? (real)0 : gs, nf, floss);   // the alpha = 0 shortcut needs H search = -grad: Newton only
       B2_PH(6)
       if (alpha == 0) break;
       B2_UNROLL1
@@ -1014,7 +1125,11 @@ B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, i
     // qfc / efc_force at the final point: the loop exits right after a constraint update
     // (break at the convergence test or iteration cap) or with alpha == 0 (state unchanged).
     B2_UNROLL1
-    for (int r = B2_LANE; r < nefc; r += B2_NLANE) { real x = jar[r]; g_force[r] = x < 0 ? -D[r] * x : 0; }
+    for (int r = B2_LANE; r < nefc; r += B2_NLANE) {
+      real x = jar[r];
+      if (FR && r < nf) { real f_, w_; fric_row(x, D[r], floss[r], f_, w_); g_force[r] = f_; }
+      else g_force[r] = x < 0 ? -D[r] * x : 0;
+    }
   }
   B2_UNROLL1
   for (int i = B2_LANE; i < nv; i += B2_NLANE) { g_qacc[i] = qacc[i]; g_qfc[i] = qfc[i]; }
@@ -1026,8 +1141,11 @@ B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, i
 
 // run-time dispatch for callers that are not templated themselves (the host builds: tests/hostemu, oracle/cport)
 B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int w, real* sm, real* arena, int* actl) {
-  if (m.solver == 1) solve_world_t<true>(m, d, L, w, sm, arena, actl);
-  else solve_world_t<false>(m, d, L, w, sm, arena, actl);
+  if (m.nfriction > 0) {
+    if (m.solver == 1) solve_world_t<true, true>(m, d, L, w, sm, arena, actl);
+    else solve_world_t<false, true>(m, d, L, w, sm, arena, actl);
+  } else if (m.solver == 1) solve_world_t<true, false>(m, d, L, w, sm, arena, actl);
+  else solve_world_t<false, false>(m, d, L, w, sm, arena, actl);
 }
 
 // Shared-memory layout of the post stage (sensors + integration): the integrator's matrix and a few vectors.

@@ -68,6 +68,9 @@ MODEL_FLOAT_FIELDS = [
   ("SGEOM_XMAT", "sgeom_xmat", lambda m: m.ngeom * 9),
   ("FIELD_AABB", "field_aabb", lambda m: m.nfield * 6),
   ("FIELD_GRID", "field_grid", lambda m: 4),
+  ("DOF_FRICTIONLOSS", "dof_frictionloss", lambda m: m.nv),
+  ("DOF_SOLREF", "dof_solref", lambda m: m.nv * 2),
+  ("DOF_SOLIMP", "dof_solimp", lambda m: m.nv * 5),
 ]
 
 MODEL_INT_FIELDS = [
@@ -162,6 +165,7 @@ DATA_INT_FIELDS = [
   ("SOLVE_RING", "solve_ring", lambda m, c, j: ()),
   ("SOLVE_CTR", "solve_ctr", lambda m, c, j: (4,)),
   ("SMOOTH_MEMO", "smooth_memo", lambda m, c, j: ()),
+  ("NF", "nf", lambda m, c, j: ()),
 ]
 
 def leading_dim(n: int) -> int:
@@ -179,7 +183,7 @@ class B2Model(C.Structure):
   _fields_ = (
     [(n, C.c_int) for n in ("nq", "nv", "nu", "nbody", "njnt", "ngeom", "nsite", "nsensor", "nsensordata", "npair",
                             "nmocap", "nlevel", "integrator", "cone", "solver", "iterations", "ls_iterations",
-                            "disableflags", "has_accelerometer", "has_subtreevel", "nlimited", "maxchain",
+                            "disableflags", "has_accelerometer", "has_subtreevel", "nlimited", "maxchain", "nfriction",
                             "nfield", "nfq", "ndyn", "field_nx", "field_ny")]
     + [("mf", C.c_void_p * NMF), ("mf_stride", C.c_int * NMF), ("mi", C.c_void_p * NMI)]
   )
@@ -261,16 +265,20 @@ def check_supported(m) -> None:
     raise ValueError("supported integrators: euler, implicitfast")
   if m.nu and np.any(m.actuator_trnid[:, 0] < 0):
     raise ValueError("only joint transmissions are supported")
-  # parsed-but-unimplemented physics is an error, never a silent no-op: friction-loss constraint rows
   fl = np.asarray(getattr(m, "dof_frictionloss", 0.0))
-  if np.any(fl != 0):
-    raise ValueError("dof_frictionloss != 0: friction-loss constraint rows are outside the supported subset "
-                     "(the shipped tasks use frictionloss = 0, src/mjlab/actuator/actuator.py:28)")
+  if np.any(fl < 0):
+    raise ValueError("dof_frictionloss must be >= 0")
 
 
 # model fields that exist on the compiled model and have physical meaning, but that no kernel reads: making them
 # per-world / randomising them would silently do nothing, so `expand_model_fields` and `randomize_field` refuse them
-UNCONSUMED_PHYSICS_FIELDS = frozenset({"dof_frictionloss"})
+# (ADVICE r01).  Empty since the friction-loss rows were built (dof_frictionloss is consumed by k_solve).
+UNCONSUMED_PHYSICS_FIELDS: frozenset = frozenset()
+
+
+def count_friction_dofs(m) -> int:
+  """Dofs that get a friction-loss constraint row (mj_instantiateFriction: dof_frictionloss > 0)."""
+  return int(np.sum(np.asarray(getattr(m, "dof_frictionloss", 0.0)) > 0))
 
 
 def model_scalars(m, tables) -> dict[str, int]:
@@ -282,7 +290,7 @@ def model_scalars(m, tables) -> dict[str, int]:
     ls_iterations=int(m.opt_ls_iterations), disableflags=int(m.opt_disableflags),
     has_accelerometer=int(np.any(st == 1)), has_subtreevel=int(np.any((st == 35) | (st == 36))),
     nlimited=int(np.sum((np.asarray(m.jnt_limited) != 0) & (np.asarray(m.jnt_type) >= 2))) if m.njnt else 0,
-    maxchain=_max_chain(m, tables),
+    maxchain=_max_chain(m, tables), nfriction=count_friction_dofs(m),
     nfield=int(m.nfield), nfq=int(m.nfq), ndyn=int(m.ndyn), field_nx=int(m.field_nx), field_ny=int(m.field_ny),
   )
 

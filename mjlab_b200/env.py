@@ -402,6 +402,7 @@ class ManagerBasedRlEnv:
     self._graph: torch.cuda.CUDAGraph | None = None
     self.use_cuda_graph = os.environ.get("B200SIM_NO_GRAPH", "0") != "1"  # eager launches for profilers
     self._capture()
+    self.sim.add_graph_listener(self._capture)   # sim.expand_model_fields after construction: the step graph follows
 
   # ---- properties (manager_based_rl_env.py:171-203) --------------------------------------------------
   num_envs = property(lambda self: self.cfg.num_envs)

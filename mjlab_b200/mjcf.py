@@ -215,6 +215,8 @@ class SJoint:
   springref: float = 0.0
   solref: np.ndarray = field(default_factory=lambda: np.array([0.02, 1.0]))
   solimp: np.ndarray = field(default_factory=lambda: np.array([0.9, 0.95, 0.001, 0.5, 2.0]))
+  solreffriction: np.ndarray = field(default_factory=lambda: np.array([0.02, 1.0]))
+  solimpfriction: np.ndarray = field(default_factory=lambda: np.array([0.9, 0.95, 0.001, 0.5, 2.0]))
 
 
 @dataclass
@@ -376,7 +378,7 @@ class ModelDesc:
     "body_dofadr", "body_pos", "body_quat", "body_ipos", "body_iquat", "body_mass", "body_inertia", "body_subtreemass",
     "body_invweight0", "jnt_type", "jnt_qposadr", "jnt_dofadr", "jnt_bodyid", "jnt_pos", "jnt_axis", "jnt_range",
     "jnt_limited", "jnt_solref", "jnt_solimp", "jnt_margin", "jnt_stiffness", "dof_bodyid", "dof_jntid", "dof_parentid",
-    "dof_armature", "dof_damping", "dof_frictionloss", "dof_invweight0", "qpos0", "qpos_spring", "geom_type",
+    "dof_armature", "dof_damping", "dof_frictionloss", "dof_solref", "dof_solimp", "dof_invweight0", "qpos0", "qpos_spring", "geom_type",
     "geom_bodyid", "geom_pos", "geom_quat", "geom_size", "geom_contype", "geom_conaffinity", "geom_condim",
     "geom_priority", "geom_friction", "geom_solref", "geom_solimp", "geom_solmix", "geom_margin", "geom_gap",
     "geom_rbound", "geom_group", "geom_rgba", "site_bodyid", "site_pos", "site_quat", "actuator_trnid",
@@ -414,7 +416,18 @@ class ModelDesc:
     excl = {(int(min(x >> 16, x & 0xFFFF)), int(max(x >> 16, x & 0xFFFF))) for x in sig}
     m.exclude_pairs = np.array(sorted(excl), np.int32).reshape(-1, 2)
     collision_tables(m, excl)
-    return m
+    return m.fill_defaults()
+
+  def fill_defaults(self) -> "ModelDesc":
+    """Arrays a source may lack (model files written before the field existed, duck-typed MjModels): MuJoCo's defaults."""
+    nv = int(self.nv)
+    if not hasattr(self, "dof_frictionloss"):
+      self.dof_frictionloss = np.zeros(nv)
+    if not hasattr(self, "dof_solref"):
+      self.dof_solref = np.tile(np.array([0.02, 1.0]), (nv, 1))
+    if not hasattr(self, "dof_solimp"):
+      self.dof_solimp = np.tile(np.array([0.9, 0.95, 0.001, 0.5, 2.0]), (nv, 1))
+    return self
 
   def fields(self):
     return {k: v for k, v in self.__dict__.items() if isinstance(v, np.ndarray)}
@@ -445,7 +458,7 @@ class ModelDesc:
         m.__dict__.update(json.loads(bytes(z[k]).decode()))
       else:
         m.__dict__[k] = z[k]
-    return m
+    return m.fill_defaults()
 
   def name2id(self, kind: str, name: str) -> int:
     names = getattr(self, f"{kind}_names")
@@ -762,6 +775,10 @@ class _Parser:
           j.solref = _floats(a["solreflimit"], 2, [0.02, 1.0])
         if "solimplimit" in a:
           j.solimp = _floats(a["solimplimit"], 5, [0.9, 0.95, 0.001, 0.5, 2.0])
+        if "solreffriction" in a:
+          j.solreffriction = _floats(a["solreffriction"], 2, [0.02, 1.0])
+        if "solimpfriction" in a:
+          j.solimpfriction = _floats(a["solimpfriction"], 5, [0.9, 0.95, 0.001, 0.5, 2.0])
         body.joints.append(j)
       elif e.tag == "geom":
         body.geoms.append(self._parse_geom(self._attrs(e, "geom", childclass)))
@@ -1130,7 +1147,7 @@ def _compile(spec: Spec) -> ModelDesc:
   jnt_solref, jnt_solimp, jnt_margin, jnt_stiffness = [], [], [], []
   jnt_names: list[str] = []
   dof_bodyid, dof_jntid, dof_parentid = [], [], []
-  dof_armature, dof_damping, dof_frictionloss = [], [], []
+  dof_armature, dof_damping, dof_frictionloss, dof_solref, dof_solimp = [], [], [], [], []
   qpos0: list[float] = []
   qpos_spring: list[float] = []
   body_jntnum = np.zeros(nbody, np.int32)
@@ -1183,6 +1200,8 @@ def _compile(spec: Spec) -> ModelDesc:
         dof_armature.append(j.armature)
         dof_damping.append(j.damping)
         dof_frictionloss.append(j.frictionloss)
+        dof_solref.append(j.solreffriction)
+        dof_solimp.append(j.solimpfriction)
       body_jntnum[i] += 1
       body_dofnum[i] += ndof
     body_lastdof[i] = last
@@ -1261,6 +1280,8 @@ def _compile(spec: Spec) -> ModelDesc:
   m.dof_armature = arr(dof_armature, (nv,))
   m.dof_damping = arr(dof_damping, (nv,))
   m.dof_frictionloss = arr(dof_frictionloss, (nv,))
+  m.dof_solref = arr(dof_solref, (nv, 2))
+  m.dof_solimp = arr(dof_solimp, (nv, 5))
   m.qpos0 = arr(qpos0, (nq,))
   m.qpos_spring = arr(qpos_spring, (nq,))
   m.geom_type = arr([g.type for g in geoms], (ngeom,), np.int32)

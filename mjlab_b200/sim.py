@@ -200,7 +200,7 @@ class Simulation:
     self._tables = E.derived_int_tables(model)
 
     self.nconmax = int(cfg.nconmax) if cfg.nconmax is not None else max(16, 4 * model.ngeom // 3)
-    self.njmax = int(cfg.njmax) if cfg.njmax is not None else max(32, 4 * self.nconmax + 2 * model.njnt)
+    self.njmax = int(cfg.njmax) if cfg.njmax is not None else max(32, 4 * self.nconmax + 2 * model.njnt + E.count_friction_dofs(model))
 
     dev = torch.device(device)
     self._dev = dev
@@ -313,6 +313,7 @@ class Simulation:
     """
     self.step_graph = self.forward_graph = self.reset_graph = None
     if not self.use_cuda_graph:
+      self._notify_graph_listeners()
       return
     torch.cuda.synchronize(self._dev)
     side = torch.cuda.Stream(self._dev)
@@ -326,6 +327,19 @@ class Simulation:
         graphs.append(g)
     torch.cuda.current_stream(self._dev).wait_stream(side)
     self.step_graph, self.forward_graph, self.reset_graph = graphs
+    self._notify_graph_listeners()
+
+  def _notify_graph_listeners(self) -> None:
+    # graphs captured by others over this simulation's buffers (the env step graph) hold the same addresses / by-value
+    # parameters and must be re-captured with ours
+    for cb in list(getattr(self, "_graph_listeners", ())):
+      cb()
+
+  def add_graph_listener(self, cb) -> None:
+    """`cb()` runs after every `create_graph()` (i.e. after `expand_model_fields` replaced a model buffer)."""
+    if not hasattr(self, "_graph_listeners"):
+      self._graph_listeners = []
+    self._graph_listeners.append(cb)
 
   # -- properties -----------------------------------------------------------------------
   @property
@@ -377,7 +391,7 @@ class Simulation:
       raise ValueError(f"Fields not found in model: {invalid}")
     dead = [f for f in fields if f in E.UNCONSUMED_PHYSICS_FIELDS]
     if dead:
-      raise ValueError(f"Fields {dead} are not consumed by the engine (friction-loss rows are unsupported); randomising them would have no effect")
+      raise ValueError(f"Fields {dead} are not consumed by the engine; randomising them would have no effect")
     if self.num_envs == 1:
       return
     for f in fields:
@@ -394,6 +408,11 @@ class Simulation:
       else:
         self._model_store[f] = dst
         self._model_views[f] = dst
+    if "dof_frictionloss" in fields and self._cm.nfriction < self._mj_model.nv:
+      # per-world friction loss: any dof may get a row in some world, so the solver is planned for nv friction-loss rows
+      # (and the friction-aware kernel instantiation is launched even if the compiled model had frictionloss = 0)
+      self._cm.nfriction = int(self._mj_model.nv)
+      E.check_call(self._lib, self._lib.b2_check(C.byref(self._cm), C.byref(self._cd)))
     self._model_bridge.clear_cache()
     self.create_graph()
 

@@ -156,6 +156,7 @@ class TrackingRlEnv:
     self._graph: torch.cuda.CUDAGraph | None = None
     self.use_cuda_graph = os.environ.get("B200SIM_NO_GRAPH", "0") != "1"
     self._capture()
+    self.sim.add_graph_listener(self._capture)   # sim.expand_model_fields after construction: the step graph follows
 
   num_envs = property(lambda self: self.cfg.num_envs)
   physics_dt = property(lambda self: self.cfg.sim.mujoco.timestep)

@@ -28,12 +28,9 @@ int cport_steps(const KModel* m, KData* d, int nstep, int nthread) { return cpor
 int cport_forward(const KModel* m, KData* d, int nthread) { return cport_run(m, d, 1, nthread, 0); }
 static int cport_run(const KModel* m, KData* d, int nstep, int nthread, int do_integrate) {
   SmoothSmem ls = smooth_smem_layout(m->nq, m->nv, m->nu, m->nbody, m->njnt, 256);
-  int rows_max = 4 * d->nconmax + 2 * m->nlimited;
-  if (rows_max > d->njmax) rows_max = d->njmax;
-  int wpad = m->maxchain | 1;
-  int arena = solve_arena_need(rows_max, 2 * m->nlimited + d->nconmax + 1, 2 * m->nlimited + d->nconmax * m->maxchain,
-                               2 * m->nlimited + 4 * d->nconmax * wpad, d->nconmax > 0 ? d->nconmax : 1);
-  SolveSmem lv = solve_smem_layout(m->nv, rows_max, m->maxchain, arena);
+  const SolveCaps caps = solve_caps(m->nlimited, m->nfriction, d->nconmax, d->njmax, m->maxchain);
+  int arena = solve_arena_need(caps.rows, caps.runs, caps.dofs, caps.pool, d->nconmax > 0 ? d->nconmax : 1);
+  SolveSmem lv = solve_smem_layout(m->nv, caps.rows, m->maxchain, arena, 0, m->nfriction);
   PostSmem lp = post_smem_layout(m->nv);
   std::atomic<int> next(0);
   auto work = [&]() {

@@ -758,6 +758,28 @@ def _kbi(m, solref, solimp, pos):
 def make_constraint(m, d, njmax=None):
   nv = m.nv
   rows_J, rows_pos, rows_margin, rows_invw, rows_solref, rows_solimp, rows_type, rows_id = ([] for _ in range(8))
+  rows_floss = []
+  # friction loss (mj_instantiateFriction: one row per dof with frictionloss > 0; rows come first: friction, limits, contacts)
+  dfl = np.asarray(getattr(d, "dof_frictionloss", getattr(m, "dof_frictionloss", np.zeros(nv))), float)
+  dof_solref = np.asarray(getattr(m, "dof_solref", np.tile([0.02, 1.0], (nv, 1))), float).reshape(nv, 2)
+  dof_solimp = np.asarray(getattr(m, "dof_solimp", np.tile([0.9, 0.95, 0.001, 0.5, 2.0], (nv, 1))), float).reshape(nv, 5)
+  for i in range(nv):
+    if dfl[i] > 0:
+      J = np.zeros(nv)
+      J[i] = 1.0
+      rows_J.append(J)
+      rows_pos.append(0.0)
+      rows_margin.append(0.0)
+      rows_invw.append(getattr(d, "dof_invweight0", m.dof_invweight0)[i])
+      rows_solref.append(dof_solref[i])
+      rows_solimp.append(dof_solimp[i])
+      rows_type.append(2)
+      rows_id.append(i)
+      rows_floss.append(dfl[i])
+  if njmax is not None and len(rows_J) > njmax:
+    for lst in (rows_J, rows_pos, rows_margin, rows_invw, rows_solref, rows_solimp, rows_type, rows_id, rows_floss):
+      del lst[njmax:]
+  d.nf = len(rows_J)
   # joint limits
   for j in range(m.njnt):
     if not m.jnt_limited[j] or m.jnt_type[j] not in (JNT_HINGE, JNT_SLIDE):
@@ -824,11 +846,15 @@ def make_constraint(m, d, njmax=None):
   d.efc_type = np.array(rows_type, int)
   d.efc_id = np.array(rows_id, int)
   d.efc_D = np.zeros(n)
+  d.efc_R = np.zeros(n)
+  d.efc_frictionloss = np.zeros(n)
+  d.efc_frictionloss[: d.nf] = rows_floss
   d.efc_k, d.efc_b, d.efc_imp = np.zeros(n), np.zeros(n), np.zeros(n)
   for i in range(n):
     k, b, imp = _kbi(m, rows_solref[i], rows_solimp[i], rows_pos[i] - rows_margin[i])
     d.efc_k[i], d.efc_b[i], d.efc_imp[i] = k, b, imp
-    d.efc_D[i] = 1.0 / max(rows_invw[i] * (1 - imp) / imp, MINVAL)
+    d.efc_R[i] = max(rows_invw[i] * (1 - imp) / imp, MINVAL)
+    d.efc_D[i] = 1.0 / d.efc_R[i]
 
 
 def reference_constraint(m, d):
@@ -944,18 +970,48 @@ def smooth_acc(m, d):
 
 
 # ---------------------------------------------------------------------------
-# Newton solver (primal, pyramidal/limit rows only: every row is an inequality)
+# Newton / CG solver (primal; friction-loss rows are Huber-type, limit and pyramidal rows are inequalities)
 # ---------------------------------------------------------------------------
 class _Pnt:
   __slots__ = ("alpha", "cost", "d1", "d2")
 
 
-def _ls_eval(alpha, quad_gauss, jar, jv, D):
+def _row_update(jar, D, R, floss, nf):
+  """mj_constraintUpdate per row: (cost terms, force, rows that enter the Hessian).  Rows [0, nf) are friction-loss rows:
+  quadratic for |jar| < R f, linear beyond with the force saturated at -/+ f; the others are active iff jar < 0."""
+  act = jar < 0
+  force = np.where(act, -D * jar, 0.0)
+  cost = np.where(act, 0.5 * D * jar * jar, 0.0)
+  for i in range(nf):
+    f, rf = floss[i], R[i] * floss[i]
+    if jar[i] <= -rf:
+      force[i], cost[i], act[i] = f, -0.5 * rf * f - f * jar[i], False
+    elif jar[i] >= rf:
+      force[i], cost[i], act[i] = -f, -0.5 * rf * f + f * jar[i], False
+    else:
+      force[i], cost[i], act[i] = -D[i] * jar[i], 0.5 * D[i] * jar[i] * jar[i], True
+  return cost, force, act
+
+
+def _ls_eval(alpha, quad_gauss, jar, jv, D, R=None, floss=None, nf=0):
   x = jar + alpha * jv
   act = x < 0
+  act[:nf] = False
   q0 = quad_gauss[0] + 0.5 * np.sum(D[act] * jar[act] ** 2)
   q1 = quad_gauss[1] + np.sum(D[act] * jar[act] * jv[act])
   q2 = quad_gauss[2] + 0.5 * np.sum(D[act] * jv[act] ** 2)
+  for i in range(nf):   # mj PrimalEval, friction rows
+    f, rf = floss[i], R[i] * floss[i]
+    if -rf < x[i] < rf:
+      q0 += 0.5 * D[i] * jar[i] * jar[i]
+      q1 += D[i] * jar[i] * jv[i]
+      q2 += 0.5 * D[i] * jv[i] * jv[i]
+    elif x[i] <= -rf:
+      q0 += f * (-0.5 * rf - jar[i])
+      q1 += -f * jv[i]
+    else:
+      q0 += f * (-0.5 * rf + jar[i])
+      q1 += f * jv[i]
   p = _Pnt()
   p.alpha = alpha
   p.cost = alpha * alpha * q2 + alpha * q1 + q0
@@ -979,9 +1035,9 @@ def _linesearch(m, d, st, search, tolerance, ls_tolerance, ls_iterations, scale)
 
   def ev(a):
     nev[0] += 1
-    return _ls_eval(a, quad_gauss, st["jar"], jv, d.efc_D)
+    return _ls_eval(a, quad_gauss, st["jar"], jv, d.efc_D, d.efc_R, d.efc_frictionloss, d.nf)
 
-  p0 = _ls_eval(0.0, quad_gauss, st["jar"], jv, d.efc_D)
+  p0 = _ls_eval(0.0, quad_gauss, st["jar"], jv, d.efc_D, d.efc_R, d.efc_frictionloss, d.nf)
   p1 = ev(p0.alpha - p0.d1 / p0.d2)
   if p0.cost < p1.cost:
     p1 = p0
@@ -1044,11 +1100,12 @@ def solve(m, d):
   J, D, aref, M = d.efc_J, d.efc_D, d.efc_aref, d.qM
   scale = 1.0 / (m.stat_meaninertia * max(1, nv))
 
+  R, floss, nf = d.efc_R, d.efc_frictionloss, d.nf
+
   def cost_of(qacc):
     jar = J @ qacc - aref
-    act = jar < 0
     Ma = M @ qacc
-    return 0.5 * np.sum(D[act] * jar[act] ** 2) + 0.5 * np.dot(Ma - d.qfrc_smooth, qacc - d.qacc_smooth)
+    return np.sum(_row_update(jar, D, R, floss, nf)[0]) + 0.5 * np.dot(Ma - d.qfrc_smooth, qacc - d.qacc_smooth)
 
   # warm start: keep qacc_warmstart unless the unconstrained acceleration is cheaper
   qacc = d.qacc_warmstart.copy()
@@ -1058,11 +1115,10 @@ def solve(m, d):
 
   def update(st, qacc):
     jar = st["jar"]
-    act = jar < 0
-    force = np.where(act, -D * jar, 0.0)
+    rowcost, force, act = _row_update(jar, D, R, floss, nf)
     st["active"], st["force"] = act, force
     st["gauss"] = 0.5 * np.dot(st["Ma"] - d.qfrc_smooth, qacc - d.qacc_smooth)
-    st["cost"] = 0.5 * np.sum(D[act] * jar[act] ** 2) + st["gauss"]
+    st["cost"] = np.sum(rowcost) + st["gauss"]
     st["qfrc_constraint"] = J.T @ force
     st["grad"] = st["Ma"] - d.qfrc_smooth - st["qfrc_constraint"]
     if cg:

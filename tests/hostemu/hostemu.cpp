@@ -33,14 +33,10 @@ long long b2h_memo_hit_count(void) { return b2h_memo_hits; }
 
 int b2h_run(const KModel* m, KData* d, int do_integrate, int world_lo, int world_hi) {
   SmoothSmem ls = smooth_smem_layout(m->nq, m->nv, m->nu, m->nbody, m->njnt, 256);
-  int rows_max = 4 * d->nconmax + 2 * m->nlimited;
-  if (rows_max > d->njmax) rows_max = d->njmax;
-  int wpad = m->maxchain | 1;
-  int pool_max = 2 * m->nlimited + 4 * d->nconmax * wpad;
-  int arena = solve_arena_need(rows_max, 2 * m->nlimited + d->nconmax + 1, 2 * m->nlimited + d->nconmax * m->maxchain, pool_max,
-                               d->nconmax > 0 ? d->nconmax : 1);
+  const SolveCaps caps = solve_caps(m->nlimited, m->nfriction, d->nconmax, d->njmax, m->maxchain);
+  int arena = solve_arena_need(caps.rows, caps.runs, caps.dofs, caps.pool, d->nconmax > 0 ? d->nconmax : 1);
   if (jpool_budget > 0) arena = jpool_budget;  // tests of the overflow path: an arena smaller than the worst case
-  SolveSmem lv = solve_smem_layout(m->nv, rows_max, m->maxchain, arena);
+  SolveSmem lv = solve_smem_layout(m->nv, caps.rows, m->maxchain, arena, 0, m->nfriction);
   PostSmem lp = post_smem_layout(m->nv);
   std::vector<real> a(ls.total), b(lv.fixed_total), ar(arena + 4), c(lp.total);
   int actl[2] = {0, 0};

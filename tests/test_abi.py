@@ -38,7 +38,7 @@ def test_library_exports_declared_symbols():
   assert {"b2_step", "b2_forward", "b2_reset", "b2_repeat_rows", "b2_check", "b2_stage", "b2_last_error"} <= set(fns)
   for fn in fns:
     assert hasattr(lib, fn), fn
-  assert lib.b2_abi_version() == 1
+  assert lib.b2_abi_version() == 2
   assert lib.b2_sizeof_model() == ctypes.sizeof(E.B2Model)
   assert lib.b2_sizeof_data() == ctypes.sizeof(E.B2Data)
 

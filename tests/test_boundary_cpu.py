@@ -97,10 +97,20 @@ def test_scene_entity_cfg_resolve():
     SceneEntityCfg("nobody", joint_names="hip").resolve(scene)
 
 
-def test_frictionloss_is_rejected_at_setup():
+def test_frictionloss_is_consumed_not_rejected():
+  """Round-1 advice: parsed-but-unused physics must not be silent.  Friction loss was first rejected at setup; since the
+  friction-loss rows were built it is consumed (tests/test_frictionloss_cpu.py): positive values size the solver for the
+  rows, negative ones are an error, and no model field is left in the 'unconsumed' set."""
   m = mjlab_b200.load_model("go1_flat")
   E.check_supported(m)
+  tables = E.derived_int_tables(m)
+  assert E.model_scalars(m, tables)["nfriction"] == 0
   m.dof_frictionloss = np.asarray(m.dof_frictionloss, float).copy()
   m.dof_frictionloss[7] = 0.1
+  E.check_supported(m)
+  assert E.model_scalars(m, tables)["nfriction"] == 1
+  m.dof_frictionloss[7] = -0.1
   with pytest.raises(ValueError, match="frictionloss"):
     E.check_supported(m)
+  assert not E.UNCONSUMED_PHYSICS_FIELDS
+  assert "dof_frictionloss" in [a for _, a, _ in E.MODEL_FLOAT_FIELDS]
