@@ -120,7 +120,7 @@ def test_randomize_field_dof_frictionloss_in_env():
   from mjlab_b200 import events
   from mjlab_b200.env import ManagerBasedRlEnv, VelocityEnvCfg
   torch.manual_seed(0)
-  env = ManagerBasedRlEnv(VelocityEnvCfg(task="go1_flat", num_envs=64, seed=3), device="cuda:0")
+  env = ManagerBasedRlEnv(VelocityEnvCfg(robot="go1", num_envs=64, seed=3), "cuda:0")
   env.sim.expand_model_fields(("dof_frictionloss",))
   env.reset()
   events.randomize_field(env, None, "dof_frictionloss", (0.2, 0.6), operation="abs", joint_names=(".*",))
