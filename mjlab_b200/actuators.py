@@ -60,6 +60,19 @@ def _rand(shape, device, generator=None) -> torch.Tensor:
   return torch.rand(shape, dtype=torch.float32, device=device, generator=generator)
 
 
+class BuiltinPositionActuator:
+  """View of one group of MuJoCo-builtin position actuators (actuator/builtin_actuator.py:26-76): the torque law runs inside
+  the physics kernels (`ctrl` -> `actuator_gainprm` / `actuator_biasprm` / `actuator_forcerange`), so the object only names the
+  group - `ctrl_ids` (global actuator ids), `joint_ids` (entity-local), `joint_names` - for the event terms that edit its gains
+  and limits in the model (`events.randomize_pd_gains`, `events.randomize_effort_limits`)."""
+
+  def __init__(self, ctrl_ids: torch.Tensor, joint_ids: torch.Tensor, joint_names: Sequence[str]):
+    self.ctrl_ids, self.joint_ids, self.joint_names = ctrl_ids, joint_ids, list(joint_names)
+
+  def __repr__(self) -> str:
+    return f"BuiltinPositionActuator({self.joint_names})"
+
+
 class IdealPdActuator:
   """tau = clamp(kp (q* - q) + kd (qd* - qd) + tau_ff, +-effort_limit), per-env gains (pd_actuator.py:94-131)."""
 
@@ -75,6 +88,7 @@ class IdealPdActuator:
     self.default_force_limit = self.force_limit.clone()
     self._effort = torch.zeros((num_envs, num_joints), dtype=torch.float32, device=self.device)
     self.num_envs, self.num_joints = num_envs, num_joints
+    self.ctrl_ids = torch.arange(num_joints, device=self.device)   # overwritten by the owner when the group is a subset of an entity's actuators
 
   def _dc(self) -> tuple[torch.Tensor | None, torch.Tensor | None]:
     return None, None

@@ -347,7 +347,7 @@ class Entity:
   """One articulated robot inside the compiled scene: names, index maps, `data`, and the `write_*_to_sim` API."""
 
   def __init__(self, name: str, sim, cfg=None, prefix: str | None = None, device: str | None = None,
-               joint_pos_target=None, encoder_bias=None):
+               joint_pos_target=None, encoder_bias=None, actuator_groups=None):
     m = sim.mj_model
     device = device or sim.device
     pre = f"{name}/" if prefix is None else prefix
@@ -383,6 +383,18 @@ class Entity:
       default_joint_pos=T(kq[m.jnt_qposadr[joints]]).repeat(n, 1), default_joint_vel=torch.zeros(n, len(joints), device=device),
       joint_pos_limits=T(lim).repeat(n, 1, 1), soft_joint_pos_limits=T(soft).repeat(n, 1, 1), is_fixed_base=not free,
       is_articulated=bool(joints), is_actuated=bool(ctrl), joint_pos_target=joint_pos_target, encoder_bias=encoder_bias)
+    # `entity.actuators` (entity/entity.py:160-206): one object per actuator cfg.  `actuator_groups`: the joint-name patterns of
+    # every cfg, in cfg order (robots.g1_cfg / go1_cfg); None: all builtin actuators as one group.
+    from .actuators import BuiltinPositionActuator
+    from .robots import resolve_matching_names
+    local_of = {n: k for k, n in enumerate(self.joint_names)}
+    ctrl_of = {n: c for n, c in zip(self.actuator_names, ctrl)}
+    groups = [tuple(g) if not isinstance(g, str) else (g,) for g in actuator_groups] if actuator_groups else [(".*",)]
+    self.actuators = []
+    for g in groups:
+      _, names = resolve_matching_names(g, self.actuator_names)
+      if names:
+        self.actuators.append(BuiltinPositionActuator(L([ctrl_of[n] for n in names]), L([local_of[n] for n in names]), names))
 
   # properties (entity/entity.py:209-262)
   @property

@@ -352,7 +352,9 @@ class ManagerBasedRlEnv:
     E.check_call(self._lib, self._lib.b2_env_check(C.byref(self.sim._cm), C.byref(self.sim._cd), C.byref(self._ce)))
 
     # ---- scene / managers (facades over the same buffers) --------------------------------------------
-    self.robot = Entity("robot", self.sim, joint_pos_target=self._buf["joint_pos_target"], encoder_bias=self._buf["encoder_bias"])
+    from .robots import g1_cfg, go1_cfg
+    groups = [a.joint_names_expr for a in {"g1": g1_cfg, "go1": go1_cfg}[cfg.robot]()[0]]   # one actuator object per actuator cfg, as the reference entity
+    self.robot = Entity("robot", self.sim, joint_pos_target=self._buf["joint_pos_target"], encoder_bias=self._buf["encoder_bias"], actuator_groups=groups)
     self.scene = _Scene(self, {"robot": self.robot})
     self.action_manager = _ActionManager(self)
     self.command_manager = _CommandManager(self)
@@ -385,15 +387,9 @@ class ManagerBasedRlEnv:
       names = self._foot_geom_names()
       randomize_field(self, None, "geom_friction", cfg.foot_friction_range, operation="abs", geom_names=names)
 
-    for ev in self.vcfg.extra.get("startup_dr", []):   # a consumed ManagerBasedRlEnvCfg: its startup randomize_field events, in order
-      from .events import FIELD_SPECS, randomize_field
-      from .managers import SceneEntityCfg
-      if ev["field"] not in FIELD_SPECS:
-        raise envcfg.UnsupportedTermError(f"startup event '{ev['name']}': randomize_field does not know the field '{ev['field']}'")
-      ac = SceneEntityCfg(**{k: v for k, v in ev["asset_cfg"].items() if v is not None})
-      ac.resolve(self.scene)
-      self.sim.expand_model_fields((ev["field"],))
-      randomize_field(self, None, ev["field"], ev["ranges"], ev["distribution"], ev["operation"], asset_cfg=ac, axes=ev["axes"])
+    for ev in self.vcfg.extra.get("startup_dr", []):   # a consumed ManagerBasedRlEnvCfg: its startup events (randomize_field / pd gains / effort limits / encoder bias), in order
+      from .events import apply_startup_event
+      apply_startup_event(self, ev)
 
     if cfg.manager_cfg is None and cfg.play and cfg.robot == "g1" and cfg.terrain == "flat":  # config/g1/env_cfgs.py:167-173: the FLAT play cfg only (pinned by tests/test_task_cfg.py)
       self.vcfg.cmd_lin_x, self.vcfg.cmd_ang_z = (-1.5, 2.0), (-0.7, 0.7)

@@ -412,6 +412,16 @@ _POST_KEYS = ("clip", "scale", "delay_min_lag", "delay_max_lag", "delay_per_env"
               "delay_per_env_phase", "history_length", "flatten_history_dim")
 
 
+def _startup_actuator_event(name: str, f: str, p: dict) -> dict:
+  """randomize_pd_gains / randomize_effort_limits / randomize_encoder_bias as startup events (envs/mdp/events.py:519-744): applied
+  once by the env through `events.apply_startup_event` (model fields expanded per world first)."""
+  ac = p.get("asset_cfg") or {"name": "robot"}
+  keys = ("name", "joint_names", "actuator_names")
+  params = {k: (tuple(v) if isinstance(v, (list, tuple)) else v) for k, v in p.items() if k != "asset_cfg"}
+  return dict(name=name, kind=f, params=params,
+              asset_cfg={k: (tuple(ac[k]) if isinstance(ac.get(k), (list, tuple)) else ac.get(k)) for k in keys})
+
+
 class UnsupportedTermError(NotImplementedError):
   """A term / option of the configuration that the fused env kernels do not implement (never silently ignored)."""
 
@@ -700,6 +710,8 @@ def from_manager_cfg(cfg, m, robot: str) -> VelocityCfg:
         asset_cfg={k: (tuple(ac[k]) if isinstance(ac.get(k), (list, tuple)) else ac.get(k)) for k in ("name", "geom_names", "body_names", "joint_names", "site_names")}))
       if p["field"] == "geom_friction" and p.get("operation", "abs") == "abs" and not isinstance(rg, dict):
         c.extra["foot_friction"] = dict(ranges=rg, geom_names=tuple(ac["geom_names"]))   # (kept for the task-table tests)
+    elif f in ("randomize_pd_gains", "randomize_effort_limits", "randomize_encoder_bias") and e["mode"] == "startup":
+      c.extra.setdefault("startup_dr", []).append(_startup_actuator_event(name, f, p))
     elif f == "randomize_terrain" and e["mode"] == "reset":
       terrain_mode |= 2
     else:
@@ -889,6 +901,8 @@ def tracking_from_manager_cfg(cfg, m, time_step_total: int, robot: str = "g1") -
         asset_cfg={k: (tuple(ac[k]) if isinstance(ac.get(k), (list, tuple)) else ac.get(k)) for k in ("name", "geom_names", "body_names", "joint_names", "site_names")}))
     elif f == "randomize_encoder_bias" and e["mode"] == "startup":
       c.extra["encoder_bias_range"] = tuple(map(float, p["bias_range"]))
+    elif f in ("randomize_pd_gains", "randomize_effort_limits") and e["mode"] == "startup":
+      c.extra["startup_dr"].append(_startup_actuator_event(name, f, p))
     else:
       raise UnsupportedTermError(f"event '{name}' ({f}, mode {e['mode']}) is not implemented by the tracking kernels")
   if any(t is not None for t in (d.get("curriculum") or {}).values()):

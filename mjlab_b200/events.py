@@ -118,3 +118,149 @@ def randomize_field(env, env_ids, field: str, ranges, distribution: str = "unifo
     model_field[eg, ig] = base * rnd
   else:
     model_field[eg, ig] = rnd
+
+
+# ---- actuator / wrench / encoder events (envs/mdp/events.py:226-252, 519-790) -------------------------------------------------
+def _env_ids(env, env_ids) -> torch.Tensor:
+  if env_ids is None:
+    return torch.arange(env.num_envs, device=env.device, dtype=torch.long)
+  return torch.as_tensor(env_ids, device=env.device).long()
+
+
+def _selected_actuators(env, asset_cfg):
+  """events.py:556-567: the entity's actuator objects selected by `asset_cfg.actuator_ids`, DelayedActuators unwrapped."""
+  asset = env.scene[asset_cfg.name if asset_cfg is not None else "robot"]
+  ids = getattr(asset_cfg, "actuator_ids", slice(None)) if asset_cfg is not None else slice(None)
+  if isinstance(ids, list):
+    acts = [asset.actuators[i] for i in ids]
+  elif isinstance(ids, slice):
+    acts = list(asset.actuators[ids])
+  else:
+    acts = [asset.actuators[ids]]
+  return [getattr(a, "base_actuator", a) for a in acts]
+
+
+def _per_world(env, *fields: str) -> None:
+  for f in fields:
+    t = getattr(env.sim.model, f)
+    if t.shape[0] != env.num_envs or t.stride(0) == 0:
+      raise ValueError(f"'{f}' is shared by all worlds; call sim.expand_model_fields(('{f}',)) first")
+
+
+def randomize_pd_gains(env, env_ids, kp_range, kd_range, asset_cfg=None, distribution: str = "uniform", operation: str = "scale") -> None:
+  """Stiffness / damping randomisation (events.py:519-624).  Builtin position actuators live in the model: gainprm[0] = kp,
+  biasprm[1] = -kp, biasprm[2] = -kd per world (the physics kernels read them every step); objects with `set_gains`
+  (IdealPdActuator and its subclasses) keep per-env gain tensors.  "scale" always starts from the compiled / default gains, so
+  repeated calls do not accumulate.  Draw order as the reference: per actuator, kp then kd, one value per (env, ctrl)."""
+  if operation not in ("scale", "abs"):
+    raise ValueError(f"Unknown operation: {operation}")
+  ids = _env_ids(env, env_ids)
+  dev = env.device
+  for act in _selected_actuators(env, asset_cfg):
+    ctrl = act.ctrl_ids
+    kp = _sample(distribution, kp_range[0], kp_range[1], (len(ids), len(ctrl)), dev)
+    kd = _sample(distribution, kd_range[0], kd_range[1], (len(ids), len(ctrl)), dev)
+    if hasattr(act, "set_gains"):
+      if operation == "scale":
+        act.set_gains(ids, kp=act.default_stiffness[ids] * kp, kd=act.default_damping[ids] * kd)
+      else:
+        act.set_gains(ids, kp=kp, kd=kd)
+      continue
+    _per_world(env, "actuator_gainprm", "actuator_biasprm")
+    gain, bias = env.sim.model.actuator_gainprm, env.sim.model.actuator_biasprm
+    if operation == "scale":
+      g0, b0 = env.sim.get_default_field("actuator_gainprm"), env.sim.get_default_field("actuator_biasprm")
+      gain[ids[:, None], ctrl, 0] = g0[ctrl, 0] * kp
+      bias[ids[:, None], ctrl, 1] = b0[ctrl, 1] * kp
+      bias[ids[:, None], ctrl, 2] = b0[ctrl, 2] * kd
+    else:
+      gain[ids[:, None], ctrl, 0] = kp
+      bias[ids[:, None], ctrl, 1] = -kp
+      bias[ids[:, None], ctrl, 2] = -kd
+
+
+def randomize_effort_limits(env, env_ids, effort_limit_range, asset_cfg=None, distribution: str = "uniform", operation: str = "scale") -> None:
+  """Effort-limit randomisation (events.py:627-706): `actuator_forcerange` = -/+ limit for builtin actuators, `force_limit` for
+  the PD classes.  As in the reference, "scale" multiplies the CURRENT limits (it does accumulate over repeated calls)."""
+  if operation not in ("scale", "abs"):
+    raise ValueError(f"Unknown operation: {operation}")
+  ids = _env_ids(env, env_ids)
+  for act in _selected_actuators(env, asset_cfg):
+    ctrl = act.ctrl_ids
+    eff = _sample(distribution, effort_limit_range[0], effort_limit_range[1], (len(ids), len(ctrl)), env.device)
+    if hasattr(act, "set_effort_limit"):
+      act.set_effort_limit(ids, effort_limit=act.force_limit[ids].clone() * eff if operation == "scale" else eff)
+      continue
+    _per_world(env, "actuator_forcerange")
+    fr = env.sim.model.actuator_forcerange
+    if operation == "scale":
+      fr[ids[:, None], ctrl, 0] *= eff
+      fr[ids[:, None], ctrl, 1] *= eff
+    else:
+      fr[ids[:, None], ctrl, 0] = -eff
+      fr[ids[:, None], ctrl, 1] = eff
+
+
+def randomize_encoder_bias(env, env_ids, bias_range, asset_cfg=None) -> None:
+  """Joint-encoder calibration error (events.py:709-744): U(bias_range) per (env, joint) into `entity.data.encoder_bias`, which
+  the observation kernels add to `joint_pos_rel(biased=True)`."""
+  asset = env.scene[asset_cfg.name if asset_cfg is not None else "robot"]
+  ids = _env_ids(env, env_ids)
+  joint_ids = getattr(asset_cfg, "joint_ids", slice(None)) if asset_cfg is not None else slice(None)
+  n = asset.num_joints if isinstance(joint_ids, slice) else len(joint_ids)
+  bias = _sample("uniform", bias_range[0], bias_range[1], (len(ids), n), env.device)
+  if isinstance(joint_ids, slice):
+    asset.data.encoder_bias[ids] = bias
+  else:
+    asset.data.encoder_bias[ids[:, None], torch.as_tensor(joint_ids, device=env.device)] = bias
+
+
+def apply_external_force_torque(env, env_ids, force_range, torque_range, asset_cfg=None) -> None:
+  """U(force_range) / U(torque_range) per (env, body, axis) into `xfrc_applied` of the selected bodies (events.py:226-245);
+  the wrench stays until overwritten (the position / velocity-stage reuse of the env step sees a nonzero wrench and recomputes)."""
+  asset = env.scene[asset_cfg.name if asset_cfg is not None else "robot"]
+  ids = _env_ids(env, env_ids)
+  body_ids = getattr(asset_cfg, "body_ids", slice(None)) if asset_cfg is not None else slice(None)
+  nb = len(body_ids) if isinstance(body_ids, list) else asset.num_bodies
+  size = (len(ids), nb, 3)
+  forces = _sample("uniform", force_range[0], force_range[1], size, env.device)
+  torques = _sample("uniform", torque_range[0], torque_range[1], size, env.device)
+  asset.write_external_wrench_to_sim(forces, torques, env_ids=ids, body_ids=body_ids)
+
+
+def sync_actuator_delays(env, env_ids, lag_range, asset_cfg=None) -> None:
+  """One lag per env, applied to every delayed actuator of the entity (events.py:747-790)."""
+  asset = env.scene[asset_cfg.name if asset_cfg is not None else "robot"]
+  ids = _env_ids(env, env_ids)
+  sel = getattr(asset_cfg, "actuator_ids", slice(None)) if asset_cfg is not None else slice(None)
+  acts = [asset.actuators[i] for i in sel] if isinstance(sel, list) else list(asset.actuators[sel]) if isinstance(sel, slice) else [asset.actuators[sel]]
+  delayed = [a for a in acts if hasattr(a, "set_lags")]
+  if not delayed:
+    return
+  lags = torch.randint(int(lag_range[0]), int(lag_range[1]) + 1, (len(ids),), device=env.device)
+  for a in delayed:
+    a.set_lags(lags, ids)
+
+
+# ---- a consumed ManagerBasedRlEnvCfg's startup events (envcfg.from_manager_cfg -> extra["startup_dr"]) -------------------------
+STARTUP_ACTUATOR_EVENTS = {"randomize_pd_gains": ("actuator_gainprm", "actuator_biasprm"), "randomize_effort_limits": ("actuator_forcerange",),
+                           "randomize_encoder_bias": ()}
+
+
+def apply_startup_event(env, ev: dict) -> None:
+  """One startup event of the cfg, applied the way `ManagerBasedRlEnv.__init__` does (manager_based_rl_env.py:118-129, 219):
+  the model fields it writes get one row per world first, then the term function runs once over all envs."""
+  from .managers import SceneEntityCfg
+  ac = SceneEntityCfg(**{k: v for k, v in ev["asset_cfg"].items() if v is not None})
+  ac.resolve(env.scene)
+  kind = ev.get("kind", "randomize_field")
+  if kind == "randomize_field":
+    if ev["field"] not in FIELD_SPECS:
+      from .envcfg import UnsupportedTermError
+      raise UnsupportedTermError(f"startup event '{ev['name']}': randomize_field does not know the field '{ev['field']}'")
+    env.sim.expand_model_fields((ev["field"],))
+    randomize_field(env, None, ev["field"], ev["ranges"], ev["distribution"], ev["operation"], asset_cfg=ac, axes=ev["axes"])
+    return
+  env.sim.expand_model_fields(STARTUP_ACTUATOR_EVENTS[kind])
+  {"randomize_pd_gains": randomize_pd_gains, "randomize_effort_limits": randomize_effort_limits,
+   "randomize_encoder_bias": randomize_encoder_bias}[kind](env, None, asset_cfg=ac, **ev["params"])

@@ -123,7 +123,9 @@ class TrackingRlEnv:
       self._buf["push_time_left"][:] = torch.rand(n, device=dev) * (hi - lo) + lo
     E.check_call(self._lib, self._lib.b2_trk_check(C.byref(self.sim._cm), C.byref(self.sim._cd), C.byref(self._ce)))
 
-    self.robot = Entity("robot", self.sim, joint_pos_target=self._buf["joint_pos_target"], encoder_bias=self._buf["encoder_bias"])
+    from .robots import g1_cfg
+    self.robot = Entity("robot", self.sim, joint_pos_target=self._buf["joint_pos_target"], encoder_bias=self._buf["encoder_bias"],
+                        actuator_groups=[a.joint_names_expr for a in g1_cfg()[0]])
     self.scene = {"robot": self.robot}
     self.extras: dict[str, Any] = {"log": {}}
     self.common_step_counter = 0
@@ -134,15 +136,9 @@ class TrackingRlEnv:
     self.reset_time_outs = self._buf["time_outs"].view(torch.bool)
 
     if cfg.manager_cfg is not None:   # the cfg's own startup events, in order (any field events.randomize_field knows)
-      from .events import FIELD_SPECS, randomize_field
-      from .managers import SceneEntityCfg
+      from .events import apply_startup_event
       for ev in self.vcfg.extra["startup_dr"]:
-        if ev["field"] not in FIELD_SPECS:
-          raise envcfg.UnsupportedTermError(f"startup event '{ev['name']}': randomize_field does not know the field '{ev['field']}'")
-        ac = SceneEntityCfg(**{k: v for k, v in ev["asset_cfg"].items() if v is not None})
-        ac.resolve(self.scene)
-        self.sim.expand_model_fields((ev["field"],))
-        randomize_field(self, None, ev["field"], ev["ranges"], ev["distribution"], ev["operation"], asset_cfg=ac, axes=ev["axes"])
+        apply_startup_event(self, ev)
       br = self.vcfg.extra["encoder_bias_range"]
       if br is not None:   # randomize_encoder_bias, events.py:709-744
         self._buf["encoder_bias"][:] = torch.rand(n, self.vcfg.nj, device=dev) * (br[1] - br[0]) + br[0]

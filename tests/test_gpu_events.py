@@ -1,0 +1,85 @@
+"""Actuator domain-randomisation events on the GPU env (envs/mdp/events.py:519-744): a consumed cfg's startup
+`randomize_pd_gains` / `randomize_effort_limits` / `randomize_encoder_bias` give every world its own gains and limits, and the
+physics kernels use them (actuator_force per world = clamp(kp (ctrl - q) - kd qd, -/+ limit) with THAT world's numbers)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def test_startup_pd_gain_and_effort_limit_events_reach_the_physics():
+  from mjlab_b200 import events
+  from mjlab_b200.env import ManagerBasedRlEnv, VelocityEnvCfg
+  from tests.test_gpu_sim_api import _task_cfg
+  d = _task_cfg("Mjlab-Velocity-Flat-Unitree-Go1")
+  ac = dict(name="robot")   # all actuator objects (actuator_ids index `entity.actuators`, one object per actuator cfg)
+  d["events"]["gains"] = dict(func="randomize_pd_gains", mode="startup", interval_range_s=None,
+                              params=dict(kp_range=[0.5, 1.5], kd_range=[0.5, 2.0], operation="scale", distribution="log_uniform", asset_cfg=ac))
+  d["events"]["effort"] = dict(func="randomize_effort_limits", mode="startup", interval_range_s=None,
+                               params=dict(effort_limit_range=[0.2, 1.0], operation="scale", asset_cfg=ac))
+  d["events"]["enc"] = dict(func="randomize_encoder_bias", mode="startup", interval_range_s=None, params=dict(bias_range=[-0.01, 0.01]))
+  n = 64
+  env = ManagerBasedRlEnv(VelocityEnvCfg.from_manager_cfg(d, "go1", "flat", num_envs=n, seed=7), DEV)
+  sim, mj = env.sim, env.sim.mj_model
+  nu = mj.nu
+  assert len(env.robot.actuators) == len(__import__("mjlab_b200.robots", fromlist=["go1_cfg"]).go1_cfg()[0])
+  assert sorted(int(i) for a in env.robot.actuators for i in a.ctrl_ids) == list(range(nu))
+  g, b, fr = sim.model.actuator_gainprm, sim.model.actuator_biasprm, sim.model.actuator_forcerange
+  assert g.shape == (n, nu, 10) and g.stride(0) == nu * 10 and fr.stride(0) == nu * 2
+  g0 = torch.as_tensor(mj.actuator_gainprm, dtype=torch.float32, device=DEV)
+  b0 = torch.as_tensor(mj.actuator_biasprm, dtype=torch.float32, device=DEV)
+  f0 = torch.as_tensor(mj.actuator_forcerange, dtype=torch.float32, device=DEV)
+  kp, kd, el = g[:, :, 0] / g0[:, 0], b[:, :, 2] / b0[:, 2], fr[:, :, 1] / f0[:, 1]
+  assert 0.5 <= float(kp.min()) and float(kp.max()) <= 1.5 and float(kp.std()) > 0.1
+  assert 0.5 <= float(kd.min()) and float(kd.max()) <= 2.0 and float(kd.std()) > 0.1
+  assert 0.2 <= float(el.min()) and float(el.max()) <= 1.0 and float(el.std()) > 0.1
+  torch.testing.assert_close(b[:, :, 1], -g[:, :, 0])                       # bias[1] = -kp stays tied to the gain
+  torch.testing.assert_close(fr[:, :, 0], -fr[:, :, 1])
+  eb = env.robot.data.encoder_bias
+  assert float(eb.abs().max()) <= 0.01 and float(eb.std()) > 1e-3
+  env.reset()
+  gen = torch.Generator(device=DEV).manual_seed(1)
+  for _ in range(3):
+    env.step(torch.rand(n, nu, device=DEV, generator=gen) * 4 - 2)          # large actions: many joints saturate at their limit
+  sim.forward()
+  torch.cuda.synchronize()
+  D = sim.data
+  jq = torch.as_tensor(mj.jnt_qposadr[mj.actuator_trnid[:, 0]], device=DEV).long()
+  jv = torch.as_tensor(mj.jnt_dofadr[mj.actuator_trnid[:, 0]], device=DEV).long()
+  want = g[:, :, 0] * D.ctrl + b[:, :, 1] * D.qpos[:, jq] + b[:, :, 2] * D.qvel[:, jv]
+  want = torch.maximum(torch.minimum(want, fr[:, :, 1]), fr[:, :, 0])
+  torch.testing.assert_close(D.actuator_force, want, rtol=1e-5, atol=1e-4)
+  sat = (D.actuator_force.abs() == fr[:, :, 1])
+  assert 0.005 < float(sat.float().mean()) < 0.95                           # both branches of the clamp occur
+  # "scale" on the gains starts from the compiled values (no accumulation); on the limits it multiplies the current ones
+  before = fr.clone()
+  events.randomize_pd_gains(env, None, (2.0, 2.0), (1.0, 1.0), operation="scale")
+  torch.testing.assert_close(sim.model.actuator_gainprm[:, :, 0], (2.0 * g0[:, 0]).expand(n, nu))
+  events.randomize_effort_limits(env, torch.arange(8, device=DEV), (0.5, 0.5), operation="scale")
+  torch.testing.assert_close(sim.model.actuator_forcerange[:8], 0.5 * before[:8])
+  torch.testing.assert_close(sim.model.actuator_forcerange[8:], before[8:])
+
+
+def test_external_force_event_pushes_the_selected_body():
+  from mjlab_b200 import events
+  from mjlab_b200.env import ManagerBasedRlEnv, VelocityEnvCfg
+  from mjlab_b200.managers import SceneEntityCfg
+  n = 16
+  env = ManagerBasedRlEnv(VelocityEnvCfg(robot="go1", num_envs=n, seed=2), DEV)
+  env.reset()
+  ac = SceneEntityCfg("robot", body_names=["trunk"])
+  ac.resolve(env.scene)
+  ids = torch.arange(0, n, 2, device=DEV)
+  env.sim.forward()
+  acc0 = env.sim.data.qacc[:, :2].clone()
+  events.apply_external_force_torque(env, ids, force_range=(40.0, 40.0), torque_range=(0.0, 0.0), asset_cfg=ac)
+  trunk = int(env.robot.indexing.body_ids[ac.body_ids[0]])
+  x = env.sim.data.xfrc_applied
+  assert torch.all(x[ids, trunk, :3] == 40.0) and float(x[1::2].abs().max()) == 0.0 and float(x[ids][:, :, 3:].abs().max()) == 0.0
+  env.sim.forward()
+  torch.cuda.synchronize()
+  dacc = env.sim.data.qacc[:, :2] - acc0
+  # 40 N along +x and +y on the trunk of a 12.7 kg robot: the pushed worlds' base accelerates by m/s^2 more (same state, same
+  # controls: a paired comparison), the others are bit-identical
+  assert float(dacc[ids].min()) > 1.0 and float(dacc[1::2].abs().max()) == 0.0

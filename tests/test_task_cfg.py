@@ -200,3 +200,28 @@ def test_tracking_cfg_edits_and_unsupported_terms():
   bad(lambda x: x["observations"]["critic"]["terms"]["joint_pos"]["params"].update(biased=True), "biased")
   bad(lambda x: x["rewards"]["motion_body_pos"]["params"].update(command_name="other"), "command_name")
   bad(lambda x: x["rewards"]["motion_body_pos"]["params"].update(body_names=["pelvis"]), "parameter 'body_names' is not consumed")
+
+
+def test_startup_actuator_events_are_consumed():
+  """randomize_pd_gains / randomize_effort_limits / randomize_encoder_bias (envs/mdp/events.py:519-744) as STARTUP events of a
+  user's cfg come back in extra["startup_dr"] for `events.apply_startup_event`; the same functions in reset mode would need
+  per-reset host work outside the step graph and are refused by name."""
+  m = mjlab_b200.load_model("go1_flat")
+  d = _load("Mjlab-Velocity-Flat-Unitree-Go1", False)
+  ac = dict(name="robot")   # all actuator objects (actuator_ids index `entity.actuators`, one object per actuator cfg)
+  d["events"]["gains"] = dict(func="randomize_pd_gains", mode="startup", interval_range_s=None,
+                              params=dict(kp_range=[0.8, 1.2], kd_range=[0.9, 1.1], operation="scale", distribution="uniform", asset_cfg=ac))
+  d["events"]["effort"] = dict(func="randomize_effort_limits", mode="startup", interval_range_s=None,
+                               params=dict(effort_limit_range=[0.7, 1.0], asset_cfg=ac))
+  d["events"]["enc"] = dict(func="randomize_encoder_bias", mode="startup", interval_range_s=None, params=dict(bias_range=[-0.01, 0.01]))
+  c = envcfg.from_manager_cfg(d, m, "go1")
+  got = {e["name"]: e for e in c.extra["startup_dr"] if e.get("kind")}
+  assert set(got) == {"gains", "effort", "enc"}
+  assert got["gains"]["kind"] == "randomize_pd_gains" and got["gains"]["params"] == dict(kp_range=(0.8, 1.2), kd_range=(0.9, 1.1), operation="scale", distribution="uniform")
+  assert got["gains"]["asset_cfg"] == dict(name="robot", joint_names=None, actuator_names=None)
+  assert got["effort"]["params"] == dict(effort_limit_range=(0.7, 1.0)) and got["enc"]["params"] == dict(bias_range=(-0.01, 0.01))
+  names = [e["name"] for e in c.extra["startup_dr"]]
+  assert names.index("gains") < names.index("effort") < names.index("enc")     # cfg order is kept
+  d["events"]["gains"]["mode"] = "reset"
+  with pytest.raises(envcfg.UnsupportedTermError, match="randomize_pd_gains, mode reset"):
+    envcfg.from_manager_cfg(d, m, "go1")
