@@ -35,7 +35,7 @@ extern "C" {
 #endif
 
 #define B2E_MAXFEET 4
-#define B2E_NREW 21
+#define B2E_NREW 22
 #define B2E_NTERM 5
 
 /* reward term order (tasks/velocity/velocity_env_cfg.py:183-278 + config/g1/env_cfgs.py:122-126) */
@@ -43,9 +43,10 @@ enum b2e_rew {
   B2E_REW_TRACK_LIN = 0, B2E_REW_TRACK_ANG, B2E_REW_UPRIGHT, B2E_REW_POSE, B2E_REW_BODY_ANG_VEL, B2E_REW_ANGMOM,
   B2E_REW_DOF_POS_LIMITS, B2E_REW_ACTION_RATE, B2E_REW_AIR_TIME, B2E_REW_FOOT_CLEARANCE, B2E_REW_FOOT_SWING,
   B2E_REW_FOOT_SLIP, B2E_REW_SOFT_LANDING, B2E_REW_SELF_COLLISIONS,
-  /* the generic term library (envs/mdp/rewards.py:22-70,149-155), weight 0 in the shipped velocity tasks */
+  /* the generic term library (envs/mdp/rewards.py:22-70,125-155), weight 0 in the shipped velocity tasks */
   B2E_REW_IS_ALIVE, B2E_REW_IS_TERMINATED, B2E_REW_JOINT_TORQUES_L2, B2E_REW_JOINT_VEL_L2, B2E_REW_JOINT_ACC_L2,
-  B2E_REW_ACTION_ACC_L2, B2E_REW_FLAT_ORIENTATION_L2
+  B2E_REW_ACTION_ACC_L2, B2E_REW_FLAT_ORIENTATION_L2,
+  B2E_REW_ELECTRICAL_POWER   /* electrical_power_cost (envs/mdp/rewards.py:125-146): sum_j max(0, actuator_force_j * joint_vel_j) */
 };
 /* termination term order; the last two (envs/mdp/terminations.py:35-47) are off unless B2E_IP_TERM_FLAGS enables them */
 enum b2e_term { B2E_TERM_TIME_OUT = 0, B2E_TERM_FELL_OVER, B2E_TERM_ILLEGAL_CONTACT, B2E_TERM_ROOT_HEIGHT, B2E_TERM_NAN };

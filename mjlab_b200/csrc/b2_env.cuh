@@ -250,7 +250,7 @@ B2_DEV void env_post_world(const KModel& m, const KData& d, const KEnv& e, int w
 
   // ---- per-joint reward sums ------------------------------------------------------------
   const int* jq = EBI(B2E_B_JOINT_Q_ADR);
-  real pose_acc = 0, lim_acc = 0, rate_acc = 0, tau_acc = 0, vel_acc = 0, acc_acc = 0, aacc_acc = 0;
+  real pose_acc = 0, lim_acc = 0, rate_acc = 0, tau_acc = 0, vel_acc = 0, acc_acc = 0, aacc_acc = 0, pow_acc = 0;
   {
     const int* jv = EBI(B2E_B_JOINT_V_ADR);
     const int* cid = EBI(B2E_B_CTRL_IDS);
@@ -272,11 +272,13 @@ B2_DEV void env_post_world(const KModel& m, const KData& d, const KEnv& e, int w
       // generic library: joint_torques_l2, joint_vel_l2, joint_acc_l2, action_acc_l2 (envs/mdp/rewards.py:32-70)
       real tau = g_af[cid[j]], qd = g_qvel[jv[j]], qdd = g_qacc[jv[j]];
       tau_acc += tau * tau; vel_acc += qd * qd; acc_acc += qdd * qdd;
+      { const real mech = tau * qd; pow_acc += mech > 0 ? mech : (real)0; }   // electrical_power_cost: regeneration is not penalised
       real dda = EBR(B2E_B_ACTION)[o] - 2 * EBR(B2E_B_PREV_ACTION)[o] + EBR(B2E_B_PREV_PREV_ACTION)[o];
       aacc_acc += dda * dda;
     }
     pose_acc = b2_wsum(pose_acc); lim_acc = b2_wsum(lim_acc); rate_acc = b2_wsum(rate_acc);
     tau_acc = b2_wsum(tau_acc); vel_acc = b2_wsum(vel_acc); acc_acc = b2_wsum(acc_acc); aacc_acc = b2_wsum(aacc_acc);
+    pow_acc = b2_wsum(pow_acc);
   }
 
   // ---- per-foot quantities (lane f < nfeet) ------------------------------------------------
@@ -372,6 +374,7 @@ B2_DEV void env_post_world(const KModel& m, const KData& d, const KEnv& e, int w
     term[B2E_REW_JOINT_ACC_L2] = acc_acc;
     term[B2E_REW_ACTION_ACC_L2] = aacc_acc;
     term[B2E_REW_FLAT_ORIENTATION_L2] = R.pg[0] * R.pg[0] + R.pg[1] * R.pg[1];
+    term[B2E_REW_ELECTRICAL_POWER] = pow_acc;
     if (EF(B2E_FP_REWARD_WEIGHT + B2E_REW_AIR_TIME) != 0) { logv[B2E_LOG_AIR_TIME_SUM] = m_air_sum; logv[B2E_LOG_AIR_COUNT] = m_air_cnt; }
     if (EF(B2E_FP_REWARD_WEIGHT + B2E_REW_FOOT_SWING) != 0) logv[B2E_LOG_PEAK_SUM] = m_peak;
     logv[B2E_LOG_LANDINGS] = m_land;

@@ -222,8 +222,9 @@ class _RewardManager:
     # term name -> kernel slot: the shipped task's 13 / 14 terms always, the generic library (envs/mdp/rewards.py) when weighted
     core = envcfg.REWARD_NAMES.index("self_collisions")
     w = env.vcfg.reward_weights
+    staged = {k for k, _ in env.vcfg.extra.get("reward_weight_stages", ())}    # terms a reward_weight curriculum will switch on later
     self.slots = {n: k for k, n in enumerate(envcfg.REWARD_NAMES)
-                  if k < core or (k == core and env.vcfg.selfcol_adr >= 0) or (k > core and w[k] != 0)}
+                  if k < core or (k == core and env.vcfg.selfcol_adr >= 0) or (k > core and (w[k] != 0 or k in staged))}
     self.active_terms = list(self.slots)
 
   _step_reward = property(lambda self: self._env._buf["step_reward"])
@@ -395,6 +396,8 @@ class ManagerBasedRlEnv:
       self.vcfg.cmd_lin_x, self.vcfg.cmd_ang_z = (-1.5, 2.0), (-0.7, 0.7)
       A.fill_params(self._ce, self.vcfg)
     self._next_stage = 0
+    st = [s_[0] for _, stages in self.vcfg.extra.get("reward_weight_stages", ()) for s_ in stages]
+    self._next_reward_stage_step = min(st) if st else None
     self._graph: torch.cuda.CUDAGraph | None = None
     self.use_cuda_graph = os.environ.get("B200SIM_NO_GRAPH", "0") != "1"  # eager launches for profilers
     self._capture()
@@ -525,6 +528,8 @@ class ManagerBasedRlEnv:
     self._sim_step_counter += self.cfg.decimation
     if self._next_stage < len(self.cfg.velocity_stages) and self.common_step_counter > self.cfg.velocity_stages[self._next_stage]["step"]:
       self._apply_velocity_stages()
+    if self._next_reward_stage_step is not None and self.common_step_counter > self._next_reward_stage_step:
+      self._apply_reward_weight_stages()
     if self._obs_pipeline is not None:
       # _reset_idx resets the observation manager's buffers of the envs that were reset (manager_based_rl_env.py:392-416) before the
       # observations of this step are pushed; one host sync for the ids - this optional path is outside the fused graph anyway
@@ -541,6 +546,8 @@ class ManagerBasedRlEnv:
     self._sim_step_counter += n * self.cfg.decimation
     if self._next_stage < len(self.cfg.velocity_stages) and self.common_step_counter > self.cfg.velocity_stages[self._next_stage]["step"]:
       self._apply_velocity_stages()
+    if self._next_reward_stage_step is not None and self.common_step_counter > self._next_reward_stage_step:
+      self._apply_reward_weight_stages()
     self._publish_log()
 
   def _publish_log(self) -> None:
@@ -555,6 +562,29 @@ class ManagerBasedRlEnv:
 
   def close(self) -> None:
     self._graph = None
+
+  def update_reward_weight(self, term: str | int, weight: float) -> None:
+    """Reward-weight curriculum hook (tasks/velocity/mdp/curriculums.py:95-107 `reward_weight`): weights are by-value kernel
+    parameters, so a change re-captures the step graph (a handful of times in a training run)."""
+    k = term if isinstance(term, int) else envcfg.REWARD_NAMES.index(term)
+    if float(self.vcfg.reward_weights[k]) != float(weight):
+      self.vcfg.reward_weights[k] = float(weight)
+      A.fill_params(self._ce, self.vcfg)
+      self._capture()
+
+  def _apply_reward_weight_stages(self) -> None:
+    """every stage whose step has been passed applies, in order: the last one passed wins (as the reference's loop)"""
+    nxt = None
+    for slot, stages in self.vcfg.extra.get("reward_weight_stages", ()):
+      w = None
+      for step, weight in stages:
+        if self.common_step_counter > step:
+          w = weight
+        else:
+          nxt = step if nxt is None else min(nxt, step)
+      if w is not None:
+        self.update_reward_weight(slot, w)
+    self._next_reward_stage_step = nxt
 
   def _apply_velocity_stages(self) -> None:
     """commands_vel (tasks/velocity/mdp/curriculums.py:72-99): every stage whose step has been passed applies, in order."""

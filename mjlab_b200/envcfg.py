@@ -50,6 +50,7 @@ REWARD_NAMES = (
   "self_collisions",
   # the generic library of envs/mdp/rewards.py (weight 0 in the shipped tasks; a consumed ManagerBasedRlEnvCfg may use them)
   "is_alive", "is_terminated", "joint_torques_l2", "joint_vel_l2", "joint_acc_l2", "action_acc_l2", "flat_orientation_l2",
+  "electrical_power_cost",
 )
 TERMINATION_NAMES = ("time_out", "fell_over", "illegal_contact", "root_height_below_minimum", "nan_detection")
 
@@ -403,6 +404,7 @@ REWARD_FUNCS = {
   "foot_swing_height": "feet_swing_height", "foot_slip": "feet_slip", "soft_landing": "soft_landing", "self_collisions": "self_collision_cost",
   "is_alive": "is_alive", "is_terminated": "is_terminated", "joint_torques_l2": "joint_torques_l2", "joint_vel_l2": "joint_vel_l2",
   "joint_acc_l2": "joint_acc_l2", "action_acc_l2": "action_acc_l2", "flat_orientation_l2": "flat_orientation_l2",
+  "electrical_power_cost": "electrical_power_cost",
 }
 # observation terms the fused kernel writes, in its fixed order: (term function, sensor_name param or None)
 POLICY_OBS_TERMS = (("builtin_sensor", "robot/imu_lin_vel"), ("builtin_sensor", "robot/imu_ang_vel"), ("projected_gravity", None),
@@ -490,6 +492,16 @@ def from_manager_cfg(cfg, m, robot: str) -> VelocityCfg:
     if t["func"] in by_func:
       raise UnsupportedTermError(f"reward function '{t['func']}' appears twice ('{by_func[t['func']][0]}', '{name}')")
     by_func[t["func"]] = (name, t)
+  if "posture" in by_func:
+    # envs/mdp/rewards.py:91-122: exp(-mean((q - q0)^2 / std^2)) with ONE std table = variable_posture (tasks/velocity/mdp/
+    # rewards.py:291-359) whose three tables are equal (std s = s*1 + s*0 + s*0 whatever the commanded speed): same kernel slot
+    if "variable_posture" in by_func:
+      raise UnsupportedTermError(f"reward terms '{by_func['posture'][0]}' (posture) and '{by_func['variable_posture'][0]}' (variable_posture) share one kernel slot")
+    pname, pt = by_func.pop("posture")
+    pp = dict(pt["params"])
+    std = pp.pop("std")
+    by_func["variable_posture"] = (pname, dict(pt, func="variable_posture", params=dict(
+      pp, std_standing=std, std_walking=std, std_running=std, walking_threshold=0.5, running_threshold=1.5, command_name="twist")))
   unknown = set(by_func) - set(REWARD_FUNCS.values())
   if unknown:
     raise UnsupportedTermError(f"reward terms {sorted(by_func[f][0] for f in unknown)} ({sorted(unknown)}) are not implemented by the env kernels")
@@ -531,10 +543,11 @@ def from_manager_cfg(cfg, m, robot: str) -> VelocityCfg:
     "is_alive": ((), {}), "is_terminated": ((), {}), "action_acc_l2": ((), {}),
     "joint_torques_l2": ((), {"asset_cfg": all_joints}), "joint_vel_l2": ((), {"asset_cfg": all_joints}),
     "joint_acc_l2": ((), {"asset_cfg": all_joints}), "flat_orientation_l2": ((), {"asset_cfg": all_joints}),
+    "electrical_power_cost": ((), {"asset_cfg": all_joints}),
   }
   for slot, params in P.items():
     _check_params("reward", by_func[REWARD_FUNCS[slot]][0], REWARD_FUNCS[slot], params, *rules[slot])
-  for slot in ("joint_torques_l2", "joint_vel_l2", "joint_acc_l2", "flat_orientation_l2"):
+  for slot in ("joint_torques_l2", "joint_vel_l2", "joint_acc_l2", "flat_orientation_l2", "electrical_power_cost"):
     ac = (P.get(slot) or {}).get("asset_cfg") or {}
     if any(ac.get(k) not in (None, (".*",), [".*"], ".*") for k in ("joint_names", "body_names")) or ac.get("name", "robot") != "robot":
       raise UnsupportedTermError(f"reward '{slot}': the kernel term covers all actuated joints of 'robot' (asset_cfg {ac})")
@@ -732,6 +745,8 @@ def from_manager_cfg(cfg, m, robot: str) -> VelocityCfg:
   c.rel_standing, c.rel_heading, c.heading_stiffness = float(t["rel_standing_envs"]), float(t["rel_heading_envs"]), float(t["heading_control_stiffness"])
   # ---- curriculum -------------------------------------------------------------------------------------------------------------------
   c.extra["velocity_stages"] = ()
+  c.extra["reward_weight_stages"] = []   # [(kernel reward slot, ((step, weight), ...))], tasks/velocity/mdp/curriculums.py:95-107
+  slot_of_term = {by_func[f][0]: k for k, s_ in enumerate(REWARD_NAMES) for f in (REWARD_FUNCS[s_],) if f in by_func}
   for name, t in d["curriculum"].items():
     if t is None:
       continue
@@ -739,6 +754,11 @@ def from_manager_cfg(cfg, m, robot: str) -> VelocityCfg:
       c.extra["velocity_stages"] = tuple({k: (tuple(v) if isinstance(v, list) else v) for k, v in st.items()} for st in t["params"]["velocity_stages"])
     elif t["func"] == "terrain_levels_vel":
       terrain_mode |= 1
+    elif t["func"] == "reward_weight":
+      rn = t["params"]["reward_name"]
+      if rn not in slot_of_term:
+        raise UnsupportedTermError(f"curriculum term '{name}' (reward_weight): no reward term named '{rn}'")
+      c.extra["reward_weight_stages"].append((slot_of_term[rn], tuple((int(s_["step"]), float(s_["weight"])) for s_ in t["params"]["weight_stages"])))
     else:
       raise UnsupportedTermError(f"curriculum term '{name}' ({t['func']})")
   has_terrain = c.terrain_origins is not None

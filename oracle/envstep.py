@@ -256,6 +256,8 @@ def reward_terms(cfg, s, d, R, log=None, terminated=None):
     out[:, K["B2E_REW_IS_TERMINATED"]] = terminated.astype(F)
   if getattr(d, "actuator_force", None) is not None:   # (data views of callers that never weight these terms may lack the arrays)
     out[:, K["B2E_REW_JOINT_TORQUES_L2"]] = np.sum(np.square(d.actuator_force[:, cfg.ctrl_ids].astype(F)), 1)
+    mech = d.actuator_force[:, cfg.ctrl_ids].astype(F) * d.qvel[:, cfg.joint_v_adr].astype(F)       # electrical_power_cost, :125-146
+    out[:, K["B2E_REW_ELECTRICAL_POWER"]] = np.sum(np.maximum(mech, F(0)), 1)
   out[:, K["B2E_REW_JOINT_VEL_L2"]] = np.sum(np.square(d.qvel[:, cfg.joint_v_adr].astype(F)), 1)
   if getattr(d, "qacc", None) is not None:
     out[:, K["B2E_REW_JOINT_ACC_L2"]] = np.sum(np.square(d.qacc[:, cfg.joint_v_adr].astype(F)), 1)

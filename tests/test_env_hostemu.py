@@ -32,7 +32,7 @@ def compare_state(env, s, names=STATE):
       np.testing.assert_array_equal(a.astype(np.int64), np.asarray(b).astype(np.int64).reshape(a.shape), err_msg=n)
 
 
-GENERIC_WEIGHTS = [0.5, -2.0, -1e-4, -1e-3, -1e-6, -0.01, -1.0]   # is_alive, is_terminated, joint_torques_l2, joint_vel_l2, joint_acc_l2, action_acc_l2, flat_orientation_l2
+GENERIC_WEIGHTS = [0.5, -2.0, -1e-4, -1e-3, -1e-6, -0.01, -1.0, -2e-3]   # is_alive, is_terminated, joint_torques_l2, joint_vel_l2, joint_acc_l2, action_acc_l2, flat_orientation_l2, electrical_power_cost
 
 
 @pytest.mark.parametrize("fixture", ["g1", "go1_fallen"])

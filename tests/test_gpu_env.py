@@ -64,7 +64,7 @@ def _init_from_golden(S, g):
   S.put("is_standing", g["is_standing"]); S.put("episode_length", g["episode_len0"])
 
 
-GENERIC_WEIGHTS = [0.5, -2.0, -1e-4, -1e-3, -1e-6, -0.01, -1.0]   # is_alive, is_terminated, joint_torques_l2, joint_vel_l2, joint_acc_l2, action_acc_l2, flat_orientation_l2
+GENERIC_WEIGHTS = [0.5, -2.0, -1e-4, -1e-3, -1e-6, -0.01, -1.0, -2e-3]   # is_alive, is_terminated, joint_torques_l2, joint_vel_l2, joint_acc_l2, action_acc_l2, flat_orientation_l2, electrical_power_cost
 
 
 @pytest.mark.parametrize("fixture", ["g1", "go1_fallen"])
@@ -226,7 +226,7 @@ def _oracle_data(m, B):
 
 def _batch(ds, m):
   from types import SimpleNamespace as NS
-  fields = ["qpos", "qvel", "ctrl", "xpos", "xquat", "subtree_com", "cvel", "site_xpos", "sensordata", "qacc_warmstart", "qacc"]
+  fields = ["qpos", "qvel", "ctrl", "xpos", "xquat", "subtree_com", "cvel", "site_xpos", "sensordata", "qacc_warmstart", "qacc", "actuator_force"]
   d = NS(**{f: np.stack([np.asarray(getattr(x, f), np.float64) for x in ds]) for f in fields})
   d.time = np.array([x.time for x in ds])
   return d

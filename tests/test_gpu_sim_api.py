@@ -463,7 +463,7 @@ def test_env_consumes_edited_manager_cfg_with_history_and_delay():
     # critic history, term-major, oldest first: the newest slot of the first term is this step's raw critic term
     torch.testing.assert_close(obs["critic"][:, 6:9], env._raw_obs["critic"][:, 0:3])
   with pytest.raises(envcfg.UnsupportedTermError):
-    d["rewards"]["x"] = dict(func="electrical_power_cost", weight=-1.0, params={})
+    d["rewards"]["x"] = dict(func="my_power_cost", weight=-1.0, params={})
     ManagerBasedRlEnv(VelocityEnvCfg.from_manager_cfg(d, "go1", "flat", num_envs=8), DEV)
 
 

@@ -225,3 +225,48 @@ def test_startup_actuator_events_are_consumed():
   d["events"]["gains"]["mode"] = "reset"
   with pytest.raises(envcfg.UnsupportedTermError, match="randomize_pd_gains, mode reset"):
     envcfg.from_manager_cfg(d, m, "go1")
+
+
+def test_posture_and_electrical_power_cost_are_consumed():
+  """envs/mdp/rewards.py:91-146.  `posture` (one std table) lands in the pose slot with three equal tables - the same
+  arithmetic as `variable_posture` whatever the commanded speed; `electrical_power_cost` has a kernel slot of its own (pinned
+  by the reference's class in tests/golden/mdp_velocity_*.npz)."""
+  m = mjlab_b200.load_model("go1_flat")
+  d = _load("Mjlab-Velocity-Flat-Unitree-Go1", False)
+  all_j = dict(name="robot", joint_names=[".*"])
+  ref = envcfg.from_manager_cfg(copy.deepcopy(d), m, "go1")
+  d["rewards"]["power"] = dict(func="electrical_power_cost", weight=-2e-3, params=dict(asset_cfg=all_j))
+  both = copy.deepcopy(d)
+  both["rewards"]["posture2"] = dict(func="posture", weight=1.0, params=dict(std={".*": 0.3}, asset_cfg=all_j))
+  with pytest.raises(envcfg.UnsupportedTermError, match="share one kernel slot"):
+    envcfg.from_manager_cfg(both, m, "go1")
+  pose_w = d["rewards"]["pose"]["weight"]
+  d["rewards"].pop("pose")
+  d["rewards"]["posture"] = dict(func="posture", weight=pose_w, params=dict(std={".*_hip_joint": 0.1, ".*_(thigh|calf)_joint": 0.3}, asset_cfg=all_j))
+  c = envcfg.from_manager_cfg(d, m, "go1")
+  k = envcfg.REWARD_NAMES.index
+  assert c.reward_weights[k("electrical_power_cost")] == -2e-3 and ref.reward_weights[k("electrical_power_cost")] == 0
+  assert c.reward_weights[k("pose")] == pose_w
+  names = [n.removeprefix("robot/") for n in c.joint_names]
+  want = np.array([0.1 if n.endswith("_hip_joint") else 0.3 for n in names])
+  for key in ("standing", "walking", "running"):
+    np.testing.assert_array_equal(getattr(c, f"std_{key}"), want)
+  bad = copy.deepcopy(d)
+  bad["rewards"]["power"]["params"]["asset_cfg"] = dict(name="robot", joint_names=[".*_hip_joint"])
+  with pytest.raises(envcfg.UnsupportedTermError, match="all actuated joints"):
+    envcfg.from_manager_cfg(bad, m, "go1")
+
+
+def test_reward_weight_curriculum_is_consumed():
+  """tasks/velocity/mdp/curriculums.py:95-107: stages of (step, weight) for a reward term named as in the cfg."""
+  m = mjlab_b200.load_model("go1_flat")
+  d = _load("Mjlab-Velocity-Flat-Unitree-Go1", False)
+  d["rewards"]["torques"] = dict(func="joint_torques_l2", weight=0.0, params={})
+  d["curriculum"]["torque_ramp"] = dict(func="reward_weight", params=dict(reward_name="torques", weight_stages=[dict(step=2, weight=-1e-4), dict(step=5, weight=-2e-4)]))
+  d["curriculum"]["slip_ramp"] = dict(func="reward_weight", params=dict(reward_name="foot_slip", weight_stages=[dict(step=3, weight=-0.5)]))
+  c = envcfg.from_manager_cfg(d, m, "go1")
+  k = envcfg.REWARD_NAMES.index
+  assert c.extra["reward_weight_stages"] == [(k("joint_torques_l2"), ((2, -1e-4), (5, -2e-4))), (k("foot_slip"), ((3, -0.5),))]
+  d["curriculum"]["torque_ramp"]["params"]["reward_name"] = "nope"
+  with pytest.raises(envcfg.UnsupportedTermError, match="no reward term named 'nope'"):
+    envcfg.from_manager_cfg(d, m, "go1")
