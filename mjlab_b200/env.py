@@ -366,7 +366,8 @@ class ManagerBasedRlEnv:
     self.common_step_counter = 0
     self._sim_step_counter = 0
     self.obs_buf = {"policy": self._buf["obs_policy"], "critic": self._buf["obs_critic"]}
-    self._raw_obs = {**self.obs_buf, "extra": self._buf["obs_extra"]}   # the kernels' term bank (cfg-built groups gather from it)
+    self._raw_obs = {**self.obs_buf, "extra": self._buf["obs_extra"],   # the kernels' term bank (cfg-built groups gather from it)
+                     "sensordata": self.sim.data.sensordata}            # builtin_sensor terms outside the bank: slices of the physics kernels' sensordata
     self._obs_pipeline = None
     if getattr(self, "_want_obs_pipeline", None) is not None:
       # clip / scale / delay / history asked for by some observation term: post-processing outside the step graph

@@ -646,6 +646,23 @@ def from_manager_cfg(cfg, m, robot: str) -> VelocityCfg:
         e["name"] = n
         post[group].append(e)
         continue
+      if t["func"] == "builtin_sensor" and key not in bank_p:
+        # any other builtin sensor of the scene (envs/mdp/observations.py:102-108): its slice of sensordata, as the physics kernels
+        # wrote it (the accelerometer `robot/imu_lin_acc`, `robot/root_angmom`, ...); no kernel-side noise for these
+        sn = [str(x) for x in m.sensor_names]
+        if key[1] not in sn or int(m.sensor_type[sn.index(key[1])]) == 42:
+          raise UnsupportedTermError(f"observation term '{n}': builtin sensor '{key[1]}' is not in the scene (builtin sensors: "
+                                     f"{[x for x, ty in zip(sn, m.sensor_type) if int(ty) != 42]})")
+        if t["noise"] is not None and g["enable_corruption"]:
+          raise UnsupportedTermError(f"observation term '{n}': sensor '{key[1]}' carries no noise in the kernels (only the imu velocity sensors do)")
+        si = sn.index(key[1])
+        layout[group].append((n, int(m.sensor_dim[si]), "sensordata", int(m.sensor_adr[si])))
+        e = {k: t[k] for k in _POST_KEYS}
+        if g.get("history_length") is not None:
+          e["history_length"], e["flatten_history_dim"] = g["history_length"], g["flatten_history_dim"]
+        e["name"] = n
+        post[group].append(e)
+        continue
       if key not in bank_p and key not in bank_e:
         raise UnsupportedTermError(f"observation term '{n}' ({key[0]}{', ' + str(key[1]) if key[1] else ''}) is not in the env kernels' term bank "
                                    f"{[k[1] or k[0] for k in POLICY_OBS_TERMS + CRITIC_EXTRA_OBS_TERMS] + ['base_lin_vel', 'base_ang_vel']}")
@@ -688,7 +705,7 @@ def from_manager_cfg(cfg, m, robot: str) -> VelocityCfg:
   got = {g: [(o, w, sg) for _, w, sg, o in terms] for g, terms in layout.items()}
   # the kernel's own two groups, as they are: nothing to gather (a clean-copy source is the same data when the term has no noise)
   c.extra["obs_custom"] = set(got) != {"policy", "critic"} or any(
-    [(o, w, sg == "extra") for o, w, sg in got[g]] != [(o, w, False) for o, w, _ in default[g]] for g in ("policy", "critic"))
+    [(o, w, sg in ("extra", "sensordata")) for o, w, sg in got[g]] != [(o, w, False) for o, w, _ in default[g]] for g in ("policy", "critic"))
   # ---- actions ----------------------------------------------------------------------------------------------------------------
   acts = [a for a in d["actions"].values() if a is not None]
   if len(acts) != 1 or acts[0]["class_type"] != "JointPositionAction" or not acts[0]["use_default_offset"] or acts[0]["clip"]:

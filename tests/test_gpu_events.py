@@ -117,3 +117,30 @@ def test_reward_weight_curriculum_changes_the_kernel_weights_at_its_steps():
   raw = (D.actuator_force * D.qvel[:, jv]).clamp(min=0).sum(1)
   # (the forward pass after resets refreshed actuator_force for ALL envs from the post-step state, so only the sign / scale is checked)
   assert float(seen[6][1][alive].min()) < 0.0 and float(raw[alive].min()) >= 0.0
+
+
+def test_builtin_sensor_observation_terms_outside_the_bank():
+  """A cfg that adds the accelerometer and the root angular momentum to the critic: the extra columns are the physics kernels'
+  sensordata slices of the state the observations were computed from."""
+  from mjlab_b200.env import ManagerBasedRlEnv, VelocityEnvCfg
+  from tests.test_gpu_sim_api import _task_cfg
+  d = _task_cfg("Mjlab-Velocity-Flat-Unitree-Go1")
+  tmpl = d["observations"]["critic"]["terms"]["foot_height"]
+  d["observations"]["critic"]["terms"]["acc"] = dict(tmpl, func="builtin_sensor", params={"sensor_name": "robot/imu_lin_acc"})
+  d["observations"]["critic"]["terms"]["angmom"] = dict(tmpl, func="builtin_sensor", params={"sensor_name": "robot/root_angmom"})
+  n = 32
+  env = ManagerBasedRlEnv(VelocityEnvCfg.from_manager_cfg(d, "go1", "flat", num_envs=n, seed=3), DEV)
+  mj = env.sim.mj_model
+  sn = list(mj.sensor_names)
+  a0, m0 = int(mj.sensor_adr[sn.index("robot/imu_lin_acc")]), int(mj.sensor_adr[sn.index("robot/root_angmom")])
+  obs, _ = env.reset()
+  base = env._raw_obs["critic"].shape[1]
+  assert obs["critic"].shape == (n, base + 6) and env.observation_manager.group_obs_dim["critic"] == (base + 6,)
+  gen = torch.Generator(device=DEV).manual_seed(0)
+  for _ in range(4):
+    obs, *_ = env.step(torch.rand(n, env.vcfg.nj, device=DEV, generator=gen) * 2 - 1)
+    sd = env.sim.data.sensordata
+    torch.testing.assert_close(obs["critic"][:, base:base + 3], sd[:, a0:a0 + 3])
+    torch.testing.assert_close(obs["critic"][:, base + 3:], sd[:, m0:m0 + 3])
+    torch.testing.assert_close(obs["critic"][:, :base], env._raw_obs["critic"])
+  assert float(obs["critic"][:, base:base + 3].abs().max()) > 1.0       # an accelerometer at rest reads ~g

@@ -270,3 +270,24 @@ def test_reward_weight_curriculum_is_consumed():
   d["curriculum"]["torque_ramp"]["params"]["reward_name"] = "nope"
   with pytest.raises(envcfg.UnsupportedTermError, match="no reward term named 'nope'"):
     envcfg.from_manager_cfg(d, m, "go1")
+
+
+def test_any_builtin_sensor_is_an_observation_term():
+  """builtin_sensor(sensor_name) (envs/mdp/observations.py:102-108) for sensors outside the kernels' term bank: a gather from
+  sensordata; contact sensors and unknown names are refused by name."""
+  m = mjlab_b200.load_model("go1_flat")
+  d = _load("Mjlab-Velocity-Flat-Unitree-Go1", False)
+  tmpl = d["observations"]["critic"]["terms"]["foot_height"]
+  d["observations"]["critic"]["terms"]["acc"] = dict(tmpl, func="builtin_sensor", params={"sensor_name": "robot/imu_lin_acc"})
+  d["observations"]["critic"]["terms"]["angmom"] = dict(tmpl, func="builtin_sensor", params={"sensor_name": "robot/root_angmom"})
+  c = envcfg.from_manager_cfg(copy.deepcopy(d), m, "go1")
+  sn = list(m.sensor_names)
+  tail = c.extra["obs_layout"]["critic"][-2:]
+  assert tail == [("acc", 3, "sensordata", int(m.sensor_adr[sn.index("robot/imu_lin_acc")])),
+                  ("angmom", 3, "sensordata", int(m.sensor_adr[sn.index("robot/root_angmom")]))]
+  assert c.extra["obs_custom"]
+  for bad, match in (("robot/nope", "not in the scene"), ("feet_ground_contact_FR_foot_collision_found", "not in the scene")):
+    x = copy.deepcopy(d)
+    x["observations"]["critic"]["terms"]["acc"]["params"]["sensor_name"] = bad
+    with pytest.raises(envcfg.UnsupportedTermError, match=match):
+      envcfg.from_manager_cfg(x, m, "go1")
