@@ -956,12 +956,17 @@ B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, i
       gauss = b2_wsum(g1);
       real newcost = b2_wsum(c1) + gauss;
       B2_WSYNC();
-      if (nl > 0) {  // limit rows, gathered per dof (deterministic even if two rows share a dof)
+      if (FR && nf > 0) {  // friction-loss rows: at most one per dof, so lanes over rows scatter without a race (J = 1)
+        B2_UNROLL1
+        for (int r = B2_LANE; r < nf; r += B2_NLANE) qfc[rundofs[r]] = frc[r];
+        B2_WSYNC();
+      }
+      if (nl > nf) {  // limit rows, gathered per dof (deterministic even if two rows share a dof)
         B2_UNROLL1
         for (int e = B2_LANE; e < nv; e += B2_NLANE) {
           real ff = 0;
           B2_UNROLL1
-          for (int r = 0; r < nl; ++r)
+          for (int r = nf; r < nl; ++r)
             if (rundofs[r] == e) ff += jpool[r] * frc[r];
           qfc[e] += ff;
         }
@@ -1035,12 +1040,17 @@ B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, i
         chol_backsolve(H, nv, ld, invd, tmp);
       } else {
       copy_g2s(H, M, nv * ld);
-      if (nl > 0) {
+      if (FR && nf > 0) {  // friction-loss rows in the quadratic zone: D on their dof's diagonal entry (one row per dof at most)
+        B2_UNROLL1
+        for (int r = B2_LANE; r < nf; r += B2_NLANE) { const int e = rundofs[r]; H[e * ld + e] += wgt[r]; }
+        B2_WSYNC();
+      }
+      if (nl > nf) {
         B2_UNROLL1
         for (int e = B2_LANE; e < nv; e += B2_NLANE) {
           real hh = 0;
           B2_UNROLL1
-          for (int r = 0; r < nl; ++r)
+          for (int r = nf; r < nl; ++r)
             if (rundofs[r] == e) hh += wgt[r];
           H[e * ld + e] += hh;
         }
