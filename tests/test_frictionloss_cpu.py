@@ -149,3 +149,33 @@ def test_friction_rows_trajectory_kernel_source_vs_oracle():
   for w, d in enumerate(ds):
     np.testing.assert_allclose(hs.qpos[w], d.qpos, rtol=1e-6, atol=1e-7)
     np.testing.assert_allclose(hs.qvel[w], d.qvel, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("njmax,arena", [(8, 0), (14, 0), (300, 600)])
+def test_friction_rows_under_row_and_arena_overflow(njmax, arena):
+  """Friction-loss rows come first, so `njmax` truncation reaches them last: njmax below the friction-row count cuts friction rows,
+  a little above it drops limits / contacts; a deliberately small solver arena (host build knob) drops contact rows from the tail.
+  Same truncation in the oracle and the kernel source (njmax cases); the arena case must still agree on the rows it keeps."""
+  m = _go1_with_friction(2)
+  nfr = E.count_friction_dofs(m)
+  nw = 3
+  qpos, qvel, ctrl, xfrc = util.random_states(m, nw, seed=8, drop=0.06)
+  hs = HostSim(m, nw, 35, njmax, real="double")
+  if arena:
+    hs.lib.b2h_set_jpool_budget(arena)
+  try:
+    hs.qpos[:], hs.qvel[:], hs.ctrl[:] = qpos, qvel, ctrl
+    hs.forward()
+  finally:
+    hs.lib.b2h_set_jpool_budget(0)
+  ds = util.oracle_rollout(m, qpos, qvel, ctrl, xfrc, 1, 35, njmax, integrate_last=False)
+  for w, d in enumerate(ds):
+    assert hs.nf[w] == min(nfr, njmax)
+    if not arena:
+      assert hs.nf[w] == d.nf and hs.nefc[w] == d.nefc <= njmax
+      np.testing.assert_allclose(hs.qacc[w], d.qacc, rtol=1e-8, atol=1e-8)
+      np.testing.assert_allclose(hs.efc_force[w, : d.nefc], d.efc_force, rtol=1e-7, atol=1e-7)
+    else:
+      assert nfr <= hs.nefc[w] <= d.nefc and np.all(np.isfinite(hs.qacc[w]))
+  if arena:
+    assert hs.nefc_dropped.sum() > 0
