@@ -805,6 +805,41 @@ _TRACKING_POLICY_OBS = (("generated_commands", None), ("motion_anchor_pos_b", No
 _TRACKING_CRITIC_OBS = _TRACKING_POLICY_OBS[:3] + (("robot_body_pos_b", None), ("robot_body_ori_b", None)) + _TRACKING_POLICY_OBS[3:]
 
 
+TRACKING_POLICY_TERM_NAMES = ("command", "motion_anchor_pos_b", "motion_anchor_ori_b", "base_lin_vel", "base_ang_vel", "joint_pos", "joint_vel", "actions")
+
+
+def tracking_without_state_estimation(c: TrackingCfg, drop=("motion_anchor_pos_b", "base_lin_vel")) -> TrackingCfg:
+  """The built-in tracking table as the registered "...-No-State-Estimation" task (tasks/tracking/config/g1/env_cfgs.py:73-84): the
+  policy group loses `drop`; what remains is gathered from the kernels' term bank exactly as `tracking_from_manager_cfg` does for
+  the task's own cfg (noisy terms from obs_policy, noise-free ones from the clean copy, joint_pos(biased) from obs_policy)."""
+  nj, nb = c.nj, int(c.nbody)
+  widths_p = (2 * nj, 3, 6, 3, 3, nj, nj, nj)
+  off = np.concatenate([[0], np.cumsum(widths_p)])
+  plain_post = {k: (None if k in ("clip", "scale") else 0) for k in _POST_KEYS}
+  plain_post.update(delay_per_env=True, delay_per_env_phase=True, flatten_history_dim=True, delay_hold_prob=0.0)
+  pol = []
+  for i, (name, w) in enumerate(zip(TRACKING_POLICY_TERM_NAMES, widths_p)):
+    o = int(off[i])
+    if name in drop:
+      c.noise_lo[o:o + w] = 0
+      c.noise_hi[o:o + w] = 0
+      continue
+    noisy = c.enable_corruption and bool(np.any(c.noise_lo[o:o + w] != 0) or np.any(c.noise_hi[o:o + w] != 0))
+    if noisy or name == "joint_pos":
+      pol.append((name, w, "policy", o))
+    else:
+      pol.append((name, w, "critic", o + (9 * nb if i >= 3 else 0)))
+  cri_names = TRACKING_POLICY_TERM_NAMES[:3] + ("body_pos", "body_ori") + TRACKING_POLICY_TERM_NAMES[3:]
+  widths_c = widths_p[:3] + (3 * nb, 6 * nb) + widths_p[3:]
+  offc = np.concatenate([[0], np.cumsum(widths_c)])
+  cri = [(n, w, "critic", int(offc[i])) for i, (n, w) in enumerate(zip(cri_names, widths_c))]
+  c.extra = dict(getattr(c, "extra", None) or {})
+  c.extra["obs_layout"] = {"policy": pol, "critic": cri}
+  c.extra["obs_post"] = {g: [dict(plain_post, name=t[0]) for t in ts] for g, ts in c.extra["obs_layout"].items()}
+  c.extra["obs_custom"] = True
+  return c
+
+
 def tracking_from_manager_cfg(cfg, m, time_step_total: int, robot: str = "g1") -> TrackingCfg:
   """Resolve a reference `ManagerBasedRlEnvCfg` of the tracking task (live dataclass or `cfg_to_dict` view) into the tracking
   kernels' `TrackingCfg`: reward weights / stds by term FUNCTION, termination thresholds and end-effector bodies, the
@@ -878,40 +913,97 @@ def tracking_from_manager_cfg(cfg, m, time_step_total: int, robot: str = "g1") -
   c.sampling_mode = mc["sampling_mode"]
   c.adaptive_kernel_size, c.adaptive_lambda = int(mc["adaptive_kernel_size"]), float(mc["adaptive_lambda"])
   c.adaptive_uniform_ratio, c.adaptive_alpha = float(mc["adaptive_uniform_ratio"]), float(mc["adaptive_alpha"])
-  # ---- observations: the kernel's fixed layout, noise per policy term ----
+  # ---- observations ----
+  # The kernel writes a fixed term bank: the eight policy terms (joint_pos_rel BIASED, each term with the policy group's noise) into
+  # obs_policy and a clean copy of them (joint_pos_rel unbiased) plus robot_body_pos_b / robot_body_ori_b into obs_critic.  The
+  # shipped layout is returned as it is; any other set of groups - a subset (the registered "...-No-State-Estimation" task drops
+  # motion_anchor_pos_b and base_lin_vel from the policy, config/g1/env_cfgs.py:73-84), another order, further groups, clip /
+  # scale / delay / history - is a gather of bank segments by obs_pipeline.ObservationPipeline (`extra["obs_layout"]`).
   obs = d["observations"]
-  if set(k for k, g in obs.items() if g is not None) != {"policy", "critic"}:
-    raise UnsupportedTermError("tracking observation groups: the kernels write 'policy' and 'critic'")
-  nj = c.nj
-  seg = [(0, 2 * nj), (2 * nj, 2 * nj + 3), (2 * nj + 3, 2 * nj + 9), (2 * nj + 9, 2 * nj + 12), (2 * nj + 12, 2 * nj + 15),
-         (2 * nj + 15, 3 * nj + 15), (3 * nj + 15, 4 * nj + 15), (4 * nj + 15, 5 * nj + 15)]
+  groups = {k: g for k, g in obs.items() if g is not None}
+  if not {"policy", "critic"} <= set(groups):
+    raise UnsupportedTermError(f"tracking observation groups {sorted(groups)}: 'policy' and 'critic' are required (rsl_rl's actor / critic inputs)")
+  nj, nb = c.nj, int(c.nbody)
+  widths_p = (2 * nj, 3, 6, 3, 3, nj, nj, nj)
+  off = np.concatenate([[0], np.cumsum(widths_p)])
+  bank_p = {k: (int(off[i]), w) for i, (k, w) in enumerate(zip(_TRACKING_POLICY_OBS, widths_p))}
+  widths_c = widths_p[:3] + (3 * nb, 6 * nb) + widths_p[3:]
+  offc = np.concatenate([[0], np.cumsum(widths_c)])
+  bank_c = {k: (int(offc[i]), w) for i, (k, w) in enumerate(zip(_TRACKING_CRITIC_OBS, widths_c))}
   lo, hi = np.zeros(c.n_obs_policy), np.zeros(c.n_obs_policy)
-  for group, want in (("policy", _TRACKING_POLICY_OBS), ("critic", _TRACKING_CRITIC_OBS)):
-    g = obs[group]
-    terms = [(n, t) for n, t in g["terms"].items() if t is not None]
-    got = tuple((t["func"], t["params"].get("sensor_name") if t["func"] == "builtin_sensor" else None) for _, t in terms)
-    if got != want:
-      raise UnsupportedTermError(f"tracking observation group '{group}': terms {got} differ from the kernel's layout {want}")
-    for n, t in terms:
-      want_biased = group == "policy" and t["func"] == "joint_pos_rel"     # the kernels' layout: biased encoder reading for the policy only
-      _check_params("observation term", n, t["func"], t["params"], ("sensor_name",),
-                    {**motion, "asset_cfg": all_joints, "biased": (lambda v, wb=want_biased: bool(v) == wb)})
-      if want_biased and not t["params"].get("biased"):
-        raise UnsupportedTermError(f"tracking observation term '{n}': the kernels write joint_pos_rel(biased=True) into the policy group")
-      if t["clip"] or t["scale"] is not None or t["delay_max_lag"] > 0 or t["history_length"] > 0 or g.get("history_length"):
-        raise UnsupportedTermError(f"tracking observation term '{n}': clip / scale / delay / history are not wired for the tracking env")
-    if group == "policy":
-      for (a, b), (n, t) in zip(seg, terms):
-        nz = t["noise"]
-        if nz is None:
-          continue
-        if nz.get("__type__") != "UniformNoiseCfg" or nz.get("operation") != "add":
-          raise UnsupportedTermError(f"observation term '{n}': noise {nz} (only additive UniformNoiseCfg is implemented)")
-        lo[a:b], hi[a:b] = float(nz["n_min"]), float(nz["n_max"])
-  if obs["critic"]["enable_corruption"]:
-    raise UnsupportedTermError("critic.enable_corruption=True: the tracking kernels only corrupt the policy group")
-  c.enable_corruption = bool(obs["policy"]["enable_corruption"])
+  def _key(t):
+    return (t["func"], t["params"].get("sensor_name") if t["func"] == "builtin_sensor" else None)
+
+  def _noise(g, t):
+    return t["noise"] if g["enable_corruption"] else None
+
+  # pass 1: which bank terms carry noise (the kernel corrupts a segment of obs_policy for everyone who reads it)
+  noise_of: dict = {}
+  kept: dict = {}     # ranges of terms whose group is not corrupted: kept in the table (the reference keeps the term's cfg too), not applied
+  for group, g in groups.items():
+    for n, t in g["terms"].items():
+      nz = t["noise"] if t is not None else None
+      if nz is None:
+        continue
+      if nz.get("__type__") != "UniformNoiseCfg" or nz.get("operation") != "add":
+        raise UnsupportedTermError(f"observation term '{n}': noise {nz} (only additive UniformNoiseCfg is implemented)")
+      key, rng = _key(t), (float(nz["n_min"]), float(nz["n_max"]))
+      if not g["enable_corruption"]:
+        if key in bank_p:
+          kept.setdefault(key, rng)
+        continue
+      if key not in bank_c:
+        continue      # named as unknown by the second pass
+      if key not in bank_p:
+        raise UnsupportedTermError(f"tracking observation term '{n}': {key[0]} carries no noise in the kernels")
+      if noise_of.setdefault(key, rng) != rng:
+        raise UnsupportedTermError(f"observation term '{n}': one noise range per term function ({noise_of[key]} vs {rng})")
+  for key, rng in (noise_of if noise_of else kept).items():   # with any corrupted group the kernel's noise is live: only asked-for ranges
+    o, w = bank_p[key]
+    lo[o:o + w], hi[o:o + w] = rng
+  # pass 2: every term as a bank segment - noisy terms from obs_policy, clean ones from the clean copy in obs_critic; joint_pos_rel exists
+  # as (biased, obs_policy) and (unbiased, obs_critic)
+  layout, post, shape = {}, {}, {}
+  for group, g in groups.items():
+    if not g["concatenate_terms"]:
+      raise UnsupportedTermError("concatenate_terms=False")
+    layout[group], post[group], shape[group] = [], [], []
+    for n, t in g["terms"].items():
+      if t is None:
+        continue
+      key = _key(t)
+      if key not in bank_c:
+        raise UnsupportedTermError(f"tracking observation term '{n}' ({key[0]}{', ' + str(key[1]) if key[1] else ''}) is not in the tracking kernels' "
+                                   f"term bank {[k[1] or k[0] for k in _TRACKING_CRITIC_OBS]}")
+      _check_params("observation term", n, t["func"], t["params"], ("sensor_name", "biased"), {**motion, "asset_cfg": all_joints})
+      biased = bool(t["params"].get("biased")) if t["func"] == "joint_pos_rel" else False
+      noisy = _noise(g, t) is not None
+      if t["func"] == "joint_pos_rel" and not biased and noisy:
+        raise UnsupportedTermError(f"tracking observation term '{n}': the kernels corrupt joint_pos_rel(biased=True) only (the encoder reading of the policy group)")
+      if t["func"] == "joint_pos_rel" and biased and not noisy and key in noise_of:
+        raise UnsupportedTermError(f"tracking observation term '{n}': joint_pos_rel(biased=True) without noise next to a group that corrupts it")
+      if noisy or biased:
+        o, w = bank_p[key]
+        layout[group].append((n, w, "policy", o))
+      else:
+        o, w = bank_c[key]
+        layout[group].append((n, w, "critic", o))
+      shape[group].append((key, biased, noisy or key not in noise_of))    # last: obs_policy's copy of the term is what this term asks for
+      e = {k: t[k] for k in _POST_KEYS}
+      if g.get("history_length") is not None:
+        e["history_length"], e["flatten_history_dim"] = g["history_length"], g["flatten_history_dim"]
+      e["name"] = n
+      post[group].append(e)
+  c.enable_corruption = bool(noise_of)
   c.noise_lo, c.noise_hi = lo, hi
+  # the shipped layout (train or play): the kernel's two buffers are the two groups as they are, nothing to gather
+  plain = (set(layout) == {"policy", "critic"}
+           and shape["policy"] == [(k, k[0] == "joint_pos_rel", True) for k in _TRACKING_POLICY_OBS]
+           and [(k, b) for k, b, _ in shape["critic"]] == [(k, False) for k in _TRACKING_CRITIC_OBS]
+           and all(lay[2] == "critic" for lay in layout["critic"]))
+  needs_post = any(t["clip"] or t["scale"] is not None or t["delay_max_lag"] > 0 or t["history_length"] > 0 for ts in post.values() for t in ts)
+  c.extra = dict(getattr(c, "extra", {}) or {})
+  c.extra["obs_layout"], c.extra["obs_post"], c.extra["obs_custom"] = layout, post, (not plain) or needs_post
   # ---- actions ----
   acts = [a for a in d["actions"].values() if a is not None]
   if len(acts) != 1 or acts[0]["class_type"] != "JointPositionAction" or not acts[0]["use_default_offset"] or acts[0]["clip"]:

@@ -51,6 +51,9 @@ class TrackingEnvCfg:
   log_metrics: bool = True
   sim: SimulationCfg = field(default_factory=_default_sim_cfg)
   manager_cfg: Any = None   # a reference ManagerBasedRlEnvCfg of the tracking task (or its cfg_to_dict view): see from_manager_cfg
+  # False: the registered "Mjlab-Tracking-Flat-Unitree-G1-No-State-Estimation" task (tasks/tracking/config/g1/__init__.py:15-22) - the
+  # policy group without motion_anchor_pos_b and base_lin_vel (built-in table; a manager_cfg carries its own groups)
+  has_state_estimation: bool = True
 
   @classmethod
   def from_manager_cfg(cls, cfg, **kw) -> "TrackingEnvCfg":
@@ -91,6 +94,8 @@ class TrackingRlEnv:
       self.vcfg = envcfg.tracking_from_manager_cfg(cfg.manager_cfg, model, motion["joint_pos"].shape[0])
     else:
       self.vcfg = envcfg.tracking_cfg(model, motion["joint_pos"].shape[0], play=cfg.play)
+      if not cfg.has_state_estimation:
+        envcfg.tracking_without_state_estimation(self.vcfg)
     self.vcfg.seed = int(cfg.seed)
     if cfg.sampling_mode is not None:
       self.vcfg.sampling_mode = cfg.sampling_mode
@@ -130,6 +135,12 @@ class TrackingRlEnv:
     self.extras: dict[str, Any] = {"log": {}}
     self.common_step_counter = 0
     self.obs_buf = {"policy": self._buf["obs_policy"], "critic": self._buf["obs_critic"]}
+    self._raw_obs = dict(self.obs_buf)     # the kernels' term bank; a consumed cfg with its own groups gathers from it
+    self._obs_pipeline = None
+    ex = getattr(self.vcfg, "extra", None) or {}
+    if ex.get("obs_custom"):
+      from .obs_pipeline import ObservationPipeline
+      self._obs_pipeline = ObservationPipeline(ex["obs_layout"], ex["obs_post"], n, device)
     self.reward_buf = self._buf["reward"]
     self.reset_buf = self._buf["reset_buf"].view(torch.bool)
     self.reset_terminated = self._buf["terminated"].view(torch.bool)
@@ -184,6 +195,18 @@ class TrackingRlEnv:
 
     def compute(self, update_history: bool = False):
       return self._e.obs_buf
+
+    @property
+    def active_terms(self):
+      p = self._e._obs_pipeline
+      if p is not None:
+        return {g: [t["name"] for t in ts] for g, ts in p.groups.items()}
+      pol = ["command", "motion_anchor_pos_b", "motion_anchor_ori_b", "base_lin_vel", "base_ang_vel", "joint_pos", "joint_vel", "actions"]
+      return {"policy": pol, "critic": pol[:3] + ["body_pos", "body_ori"] + pol[3:]}
+
+    @property
+    def group_obs_dim(self):
+      return {g: tuple(v.shape[1:]) for g, v in self._e.obs_buf.items()}
 
   class _CM:
     def __init__(self, env):
@@ -280,6 +303,9 @@ class TrackingRlEnv:
     E.check_call(lib, lib.b2_forward(m, d, st))
     E.check_call(lib, lib.b2_trk_obs(m, d, e, 0, st))
     self._buf["step_counter"].add_(1)   # reset() consumes one draw-counter value (see env.ManagerBasedRlEnv.reset)
+    if self._obs_pipeline is not None:
+      self._obs_pipeline.reset(env_ids)
+      self.obs_buf = self._obs_pipeline.compute(self._raw_obs, update_history=True)
     self._publish_log()
     return self.obs_buf, self.extras
 
@@ -296,6 +322,11 @@ class TrackingRlEnv:
     else:
       self._enqueue_step()
     self.common_step_counter += 1
+    if self._obs_pipeline is not None:   # as env.ManagerBasedRlEnv.step: buffers of reset envs are cleared before this step's push
+      ids = self._buf["reset_buf"].nonzero().flatten()
+      if ids.numel():
+        self._obs_pipeline.reset(ids)
+      self.obs_buf = self._obs_pipeline.compute(self._raw_obs, update_history=True)
     self._publish_log()
     return self.obs_buf, self.reward_buf, self.reset_terminated, self.reset_time_outs, self.extras
 

@@ -210,3 +210,69 @@ def test_tracking_env_from_the_reference_manager_cfg_equals_the_builtin_task():
   assert env.vcfg.anchor_ori_threshold > 1e8 and env.vcfg.reward_weights[2] == 2.0
   env.reset()
   env.step(torch.zeros(8, env.vcfg.nj, device=DEV))
+
+
+def test_tracking_no_state_estimation_task():
+  """The reference's registered `Mjlab-Tracking-Flat-Unitree-G1-No-State-Estimation` (its cfg dump): the same physics, rewards and
+  resets as the full task (same seeds), a critic group equal to the full task's, and a policy group that is the full task's
+  policy group without the motion_anchor_pos_b and base_lin_vel columns - the noisy columns bit for bit, the noise-free ones
+  (command, last action) from the clean copy."""
+  import json
+  from pathlib import Path
+  from mjlab_b200.tracking_env import TrackingEnvCfg, TrackingRlEnv
+  cfgdir = Path(__file__).resolve().parent / "golden" / "task_cfg"
+  full = json.loads((cfgdir / "Mjlab-Tracking-Flat-Unitree-G1.json").read_text())
+  nse = json.loads((cfgdir / "Mjlab-Tracking-Flat-Unitree-G1-No-State-Estimation.json").read_text())
+  B = 32
+  outs = []
+  for d in (full, nse):
+    torch.manual_seed(11)
+    env = TrackingRlEnv(TrackingEnvCfg.from_manager_cfg(d, num_envs=B, seed=3), DEV)
+    g = torch.Generator(device=DEV).manual_seed(2)
+    obs, _ = env.reset()
+    hist = [(obs["policy"].clone(), obs["critic"].clone())]
+    for _ in range(8):
+      obs, rew, term, trunc, _ = env.step(torch.rand(B, env.vcfg.nj, device=DEV, generator=g) * 2 - 1)
+      hist.append((obs["policy"].clone(), obs["critic"].clone(), rew.clone(), term.clone(), trunc.clone()))
+    outs.append((env, hist))
+  (e_full, h_full), (e_nse, h_nse) = outs
+  nj = e_full.vcfg.nj
+  assert e_nse.observation_manager.active_terms["policy"] == ["command", "motion_anchor_ori_b", "base_ang_vel", "joint_pos", "joint_vel", "actions"]
+  assert e_nse.observation_manager.group_obs_dim["policy"] == (e_full.vcfg.n_obs_policy - 6,)
+  keep = torch.ones(e_full.vcfg.n_obs_policy, dtype=torch.bool, device=DEV)
+  keep[2 * nj: 2 * nj + 3] = False          # motion_anchor_pos_b
+  keep[2 * nj + 9: 2 * nj + 12] = False     # base_lin_vel
+  noisy = keep.clone()
+  noisy[: 2 * nj] = False                   # command: no noise -> clean copy (identical values)
+  noisy[4 * nj + 15:] = False               # last action: no noise
+  for a, b in zip(h_full, h_nse):
+    assert torch.equal(a[1], b[1])                                   # critic group: identical
+    assert b[0].shape == (B, int(keep.sum()))
+    sel = noisy[keep]
+    # same physics and same Philox draws; the dropped terms' noise draws do not shift the others' (draws are keyed per column)
+    torch.testing.assert_close(b[0][:, sel], a[0][:, keep][:, sel], rtol=0, atol=0)
+    torch.testing.assert_close(b[0][:, ~sel], a[0][:, keep][:, ~sel], rtol=0, atol=0)
+    for x, y in zip(a[2:], b[2:]):
+      assert torch.equal(x, y)                                       # rewards, terminations, truncations
+
+
+def test_builtin_no_state_estimation_equals_the_reference_cfg_variant():
+  """`TrackingEnvCfg(has_state_estimation=False)` (built-in table) steps bit-identically to the env built from the dump of the
+  reference's own `Mjlab-Tracking-Flat-Unitree-G1-No-State-Estimation` cfg."""
+  import json
+  from pathlib import Path
+  from mjlab_b200.tracking_env import TrackingEnvCfg, TrackingRlEnv
+  d = json.loads((Path(__file__).resolve().parent / "golden" / "task_cfg" / "Mjlab-Tracking-Flat-Unitree-G1-No-State-Estimation.json").read_text())
+  B = 24
+  outs = []
+  for cfg in (TrackingEnvCfg(num_envs=B, seed=5, has_state_estimation=False), TrackingEnvCfg.from_manager_cfg(d, num_envs=B, seed=5)):
+    torch.manual_seed(7)
+    env = TrackingRlEnv(cfg, DEV)
+    g = torch.Generator(device=DEV).manual_seed(1)
+    obs, _ = env.reset()
+    for _ in range(6):
+      obs, rew, term, trunc, _ = env.step(torch.rand(B, env.vcfg.nj, device=DEV, generator=g) * 2 - 1)
+    outs.append((obs["policy"].clone(), obs["critic"].clone(), rew.clone(), term.clone(), trunc.clone()))
+    assert obs["policy"].shape == (B, env.vcfg.n_obs_policy - 6)
+  for x, y in zip(*outs):
+    assert torch.equal(x, y)

@@ -194,7 +194,8 @@ def test_tracking_cfg_edits_and_unsupported_terms():
 
   bad(lambda x: x["rewards"].update(my=dict(func="my_reward", weight=1.0, params={})), "my")
   bad(lambda x: x["terminations"].update(t=dict(func="bad_orientation", time_out=False, params={"limit_angle": 1.0})), "bad_orientation")
-  bad(lambda x: x["observations"]["policy"]["terms"].pop("base_lin_vel"), "differ from the kernel's layout")
+  bad(lambda x: x["observations"]["policy"]["terms"].update(h=dict(x["observations"]["policy"]["terms"]["joint_vel"], func="foot_height", params={})), "term bank")
+  bad(lambda x: x["observations"].pop("critic"), "'policy' and 'critic' are required")
   bad(lambda x: x["events"].update(e=dict(func="reset_joints_by_offset", mode="reset", params={}, interval_range_s=None)), "reset_joints_by_offset")
   bad(lambda x: x["observations"]["policy"]["terms"]["joint_pos"]["params"].update(biased=False), "biased")
   bad(lambda x: x["observations"]["critic"]["terms"]["joint_pos"]["params"].update(biased=True), "biased")
@@ -291,3 +292,49 @@ def test_any_builtin_sensor_is_an_observation_term():
     x["observations"]["critic"]["terms"]["acc"]["params"]["sensor_name"] = bad
     with pytest.raises(envcfg.UnsupportedTermError, match=match):
       envcfg.from_manager_cfg(x, m, "go1")
+
+
+@pytest.mark.parametrize("play", [False, True])
+def test_tracking_no_state_estimation_task_resolves_to_gathers(play):
+  """The reference registers `Mjlab-Tracking-Flat-Unitree-G1-No-State-Estimation` (tasks/tracking/config/g1/__init__.py:15-22): the
+  policy group without motion_anchor_pos_b and base_lin_vel (config/g1/env_cfgs.py:73-84).  Its dump resolves to the same kernel
+  table as the full task plus a gather layout over the kernels' term bank; the full task stays on the kernel's buffers."""
+  import dataclasses
+  m = mjlab_b200.load_model("g1_flat")
+  full = envcfg.tracking_from_manager_cfg(_load("Mjlab-Tracking-Flat-Unitree-G1", play), m, 500)
+  assert not full.extra["obs_custom"]
+  c = envcfg.tracking_from_manager_cfg(_load("Mjlab-Tracking-Flat-Unitree-G1-No-State-Estimation", play), m, 500)
+  assert c.extra["obs_custom"]
+  nj, nb = c.nj, int(c.nbody)
+  lay = c.extra["obs_layout"]
+  assert [t[0] for t in lay["policy"]] == ["command", "motion_anchor_ori_b", "base_ang_vel", "joint_pos", "joint_vel", "actions"]
+  # a term with noise in a corrupted group reads the noisy copy (obs_policy), every other one the clean copy (obs_critic, where the
+  # two body terms sit between motion_anchor_ori_b and base_lin_vel); joint_pos(biased=True) only exists in obs_policy
+  dump = _load("Mjlab-Tracking-Flat-Unitree-G1-No-State-Estimation", play)["observations"]["policy"]
+  off_p = {"command": 0, "motion_anchor_ori_b": 2 * nj + 3, "base_ang_vel": 2 * nj + 12, "joint_pos": 2 * nj + 15, "joint_vel": 3 * nj + 15, "actions": 4 * nj + 15}
+  shift = 9 * nb
+  nsrc = {"policy": 0, "critic": 0}
+  for name, w, sg, o in lay["policy"]:
+    noisy = dump["enable_corruption"] and dump["terms"][name]["noise"] is not None
+    if name == "joint_pos" or noisy:
+      assert (sg, o) == ("policy", off_p[name]), name
+    else:
+      assert (sg, o) == ("critic", off_p[name] + (shift if off_p[name] >= 2 * nj + 9 else 0)), name
+    nsrc[sg] += 1
+  assert nsrc["policy"] == (1 if play else 4) and nsrc["critic"] == (5 if play else 2)
+  assert sum(t[1] for t in lay["policy"]) == c.n_obs_policy - 6 and sum(t[1] for t in lay["critic"]) == c.n_obs_critic
+  assert all(t[2] == "critic" for t in lay["critic"])
+  for f in dataclasses.fields(full):
+    if f.name in ("extra", "noise_lo", "noise_hi"):
+      continue
+    x, y = getattr(full, f.name), getattr(c, f.name)
+    if isinstance(x, (str, type(None))):
+      assert x == y, f.name
+    else:
+      np.testing.assert_array_equal(np.asarray(x), np.asarray(y), err_msg=f.name)
+  # noise table: the two dropped terms' segments carry no noise any more, the others are the full task's
+  keep = np.ones(c.n_obs_policy, bool)
+  keep[2 * nj: 2 * nj + 3] = False
+  keep[2 * nj + 9: 2 * nj + 12] = False
+  np.testing.assert_array_equal(c.noise_lo[keep], full.noise_lo[keep])
+  assert not c.noise_lo[~keep].any() and not c.noise_hi[~keep].any()

@@ -26,7 +26,7 @@ from mjlab.tasks.registry import load_env_cfg  # noqa: E402
 from mjlab_b200.envcfg import cfg_to_dict  # noqa: E402
 
 TASKS = ["Mjlab-Velocity-Flat-Unitree-G1", "Mjlab-Velocity-Flat-Unitree-Go1", "Mjlab-Velocity-Rough-Unitree-G1",
-         "Mjlab-Velocity-Rough-Unitree-Go1", "Mjlab-Tracking-Flat-Unitree-G1"]
+         "Mjlab-Velocity-Rough-Unitree-Go1", "Mjlab-Tracking-Flat-Unitree-G1", "Mjlab-Tracking-Flat-Unitree-G1-No-State-Estimation"]
 
 if __name__ == "__main__":
   out = ROOT / "tests" / "golden" / "task_cfg"
