@@ -48,6 +48,8 @@ enum b2t_ip {
   B2T_IP_ENABLE_CORRUPTION, B2T_IP_PUSH_ENABLED,
   B2T_IP_SAMPLING_MODE,     /* 0 start, 1 uniform, 2 adaptive */
   B2T_IP_TIME_STEP_TOTAL, B2T_IP_BIN_COUNT, B2T_IP_KERNEL_SIZE,
+  B2T_IP_TERM_FULL3D,       /* bit 0: bad_anchor_pos (3-D distance) instead of bad_anchor_pos_z_only; bit 1: bad_motion_body_pos
+                             * instead of bad_motion_body_pos_z_only (tasks/tracking/mdp/terminations.py:18-86) */
   B2T_IP_NEE,
   B2T_IP_EE_SEL,            /* [B2T_MAXEE] indices inside the tracked list */
   B2T_IP_COUNT = B2T_IP_EE_SEL + B2T_MAXEE

@@ -249,8 +249,10 @@ B2_DEV void trk_post_world(const KModel& m, const KData& d, const KTrk& e, int w
     real da[3] = {mb.ang[0] - rb.ang[0], mb.ang[1] - rb.ang[1], mb.ang[2] - rb.ang[2]};
     e_lin += dl[0] * dl[0] + dl[1] * dl[1] + dl[2] * dl[2];
     e_ang += da[0] * da[0] + da[1] * da[1] + da[2] * da[2];
+    // bad_motion_body_pos(_z_only): distance (or height difference) of an end-effector body to its motion target
+    const real ee_err = (TI(B2T_IP_TERM_FULL3D) & 2) ? sqrt(dp[0] * dp[0] + dp[1] * dp[1] + dp[2] * dp[2]) : fabs(dp[2]);
     for (int k = 0; k < TI(B2T_IP_NEE); ++k)
-      if (TI(B2T_IP_EE_SEL + k) == b && fabs(rp[2] - rb.pos[2]) > TF(B2T_FP_EE_POS_THRESHOLD)) ee_bad = 1;
+      if (TI(B2T_IP_EE_SEL + k) == b && ee_err > TF(B2T_FP_EE_POS_THRESHOLD)) ee_bad = 1;
   }
   e_pos = b2_wsum(e_pos) / (real)nb; e_ori = b2_wsum(e_ori) / (real)nb; e_lin = b2_wsum(e_lin) / (real)nb; e_ang = b2_wsum(e_ang) / (real)nb;
   const bool ee = b2_wor_i(ee_bad) != 0;
@@ -280,7 +282,8 @@ B2_DEV void trk_post_world(const KModel& m, const KData& d, const KTrk& e, int w
   env_quat_apply_inv(pgr, ra.quat, g);
   const long long ep = TBL(B2T_B_EPISODE_LENGTH)[w] + 1;
   const bool time_out = ep >= (long long)TI(B2T_IP_MAX_EPISODE_LENGTH);
-  const bool apos = fabs(ma.pos[2] - ra.pos[2]) > TF(B2T_FP_ANCHOR_POS_THRESHOLD);
+  const real adx = ma.pos[0] - ra.pos[0], ady = ma.pos[1] - ra.pos[1], adz = ma.pos[2] - ra.pos[2];
+  const bool apos = ((TI(B2T_IP_TERM_FULL3D) & 1) ? sqrt(adx * adx + ady * ady + adz * adz) : fabs(adz)) > TF(B2T_FP_ANCHOR_POS_THRESHOLD);
   const bool aori = fabs(pgm[2] - pgr[2]) > TF(B2T_FP_ANCHOR_ORI_THRESHOLD);
   const bool terminated = apos || aori || ee;
   const bool reset = terminated || time_out;

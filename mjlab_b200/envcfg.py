@@ -340,6 +340,7 @@ class TrackingCfg:
   max_episode_length: int = 500
   max_episode_length_s: float = 10.0
   anchor_pos_threshold: float = 0.25
+  term_full3d: int = 0       # bit 0: bad_anchor_pos instead of bad_anchor_pos_z_only; bit 1: bad_motion_body_pos instead of ..._z_only
   anchor_ori_threshold: float = 0.8
   ee_pos_threshold: float = 0.25
   std_anchor_pos: float = 0.3
@@ -851,7 +852,7 @@ def tracking_from_manager_cfg(cfg, m, time_step_total: int, robot: str = "g1") -
   if len(cmds) != 1 or cmds[0]["class_type"] != "MotionCommand":
     raise UnsupportedTermError("commands: one MotionCommand is implemented")
   mc = cmds[0]
-  ee_t = [t for t in d["terminations"].values() if t is not None and t["func"] == "bad_motion_body_pos_z_only"]
+  ee_t = [t for t in d["terminations"].values() if t is not None and t["func"] in ("bad_motion_body_pos_z_only", "bad_motion_body_pos")]
   ee = tuple(ee_t[0]["params"]["body_names"]) if ee_t else G1_EE_BODIES
   c = tracking_cfg(m, time_step_total, robot, play=False, tracked=tuple(mc["body_names"]), anchor=mc["anchor_body_name"], ee=ee)
   pre = "robot/"
@@ -895,17 +896,23 @@ def tracking_from_manager_cfg(cfg, m, time_step_total: int, robot: str = "g1") -
   c.reward_weights = w
   # ---- terminations ----
   tf = {t["func"]: t for t in d["terminations"].values() if t is not None}
-  bad = set(tf) - {"time_out", "bad_anchor_pos_z_only", "bad_anchor_ori", "bad_motion_body_pos_z_only"}
+  bad = set(tf) - {"time_out", "bad_anchor_pos_z_only", "bad_anchor_pos", "bad_anchor_ori", "bad_motion_body_pos_z_only", "bad_motion_body_pos"}
   if bad:
     raise UnsupportedTermError(f"termination functions {sorted(bad)} are not implemented by the tracking kernels")
+  for a_, b_ in (("bad_anchor_pos", "bad_anchor_pos_z_only"), ("bad_motion_body_pos", "bad_motion_body_pos_z_only")):
+    if a_ in tf and b_ in tf:
+      raise UnsupportedTermError(f"terminations {a_} and {b_} share one kernel slot (3-D distance or height difference)")
   if "time_out" not in tf or not tf["time_out"]["time_out"]:
     raise UnsupportedTermError("the kernels always apply the time_out truncation")
   for f, t in tf.items():
     _check_params("termination", f, f, t["params"], ("threshold", "body_names"), {**motion, "asset_cfg": all_joints})
   BIG = 1e9   # a threshold no error reaches = term absent
-  c.anchor_pos_threshold = float(tf["bad_anchor_pos_z_only"]["params"]["threshold"]) if "bad_anchor_pos_z_only" in tf else BIG
+  apf = "bad_anchor_pos" if "bad_anchor_pos" in tf else "bad_anchor_pos_z_only"
+  eef = "bad_motion_body_pos" if "bad_motion_body_pos" in tf else "bad_motion_body_pos_z_only"
+  c.term_full3d = (1 if "bad_anchor_pos" in tf else 0) | (2 if "bad_motion_body_pos" in tf else 0)
+  c.anchor_pos_threshold = float(tf[apf]["params"]["threshold"]) if apf in tf else BIG
   c.anchor_ori_threshold = float(tf["bad_anchor_ori"]["params"]["threshold"]) if "bad_anchor_ori" in tf else BIG
-  c.ee_pos_threshold = float(tf["bad_motion_body_pos_z_only"]["params"]["threshold"]) if "bad_motion_body_pos_z_only" in tf else BIG
+  c.ee_pos_threshold = float(tf[eef]["params"]["threshold"]) if eef in tf else BIG
   # ---- command ----
   r6 = VelocityCfg._ranges6
   c.pose_range, c.velocity_range = r6(_range6(mc.get("pose_range"))), r6(_range6(mc.get("velocity_range")))

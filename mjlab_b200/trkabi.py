@@ -133,7 +133,8 @@ def fill_params(ce: B2Trk, cfg) -> None:
                   ("N_OBS_POLICY", cfg.n_obs_policy), ("N_OBS_CRITIC", cfg.n_obs_critic), ("LINVEL_ADR", cfg.linvel_adr), ("ANGVEL_ADR", cfg.angvel_adr),
                   ("SELFCOL_ADR", cfg.selfcol_adr), ("MAX_EPISODE_LENGTH", min(int(cfg.max_episode_length), 2**31 - 1)),
                   ("ENABLE_CORRUPTION", int(cfg.enable_corruption)), ("PUSH_ENABLED", int(cfg.push_enabled)), ("SAMPLING_MODE", mode),
-                  ("TIME_STEP_TOTAL", cfg.time_step_total), ("BIN_COUNT", cfg.bin_count), ("KERNEL_SIZE", cfg.adaptive_kernel_size), ("NEE", len(cfg.ee_sel))):
+                  ("TIME_STEP_TOTAL", cfg.time_step_total), ("BIN_COUNT", cfg.bin_count), ("KERNEL_SIZE", cfg.adaptive_kernel_size), ("NEE", len(cfg.ee_sel)),
+                  ("TERM_FULL3D", int(getattr(cfg, "term_full3d", 0)))):
     ip[K["B2T_IP_" + name]] = int(v)
   for k, s in enumerate(cfg.ee_sel):
     ip[K["B2T_IP_EE_SEL"] + k] = int(s)

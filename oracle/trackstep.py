@@ -113,10 +113,17 @@ def robot_bodies(cfg, d) -> NS:
 def terminations(cfg, s, fr, rb):
   a = cfg.anchor_sel
   time_out = s.episode_length >= cfg.max_episode_length
-  anchor_pos = np.abs(fr.body_pos_w[:, a, 2] - rb.pos[:, a, 2]) > F(cfg.anchor_pos_threshold)                     # terminations.py:28-35
+  full = int(getattr(cfg, "term_full3d", 0))
+  if full & 1:
+    anchor_pos = np.sqrt(np.sum(np.square(fr.body_pos_w[:, a] - rb.pos[:, a]), -1)) > F(cfg.anchor_pos_threshold)   # terminations.py:18-25
+  else:
+    anchor_pos = np.abs(fr.body_pos_w[:, a, 2] - rb.pos[:, a, 2]) > F(cfg.anchor_pos_threshold)                   # terminations.py:28-35
   g = np.broadcast_to(np.array([0, 0, -1], F), (len(time_out), 3))
   anchor_ori = np.abs(quat_apply_inverse(fr.body_quat_w[:, a], g)[:, 2] - quat_apply_inverse(rb.quat[:, a], g)[:, 2]) > F(cfg.anchor_ori_threshold)  # :38-52
-  ee = np.any(np.abs(s.rel_pos[:, cfg.ee_sel, 2] - rb.pos[:, cfg.ee_sel, 2]) > F(cfg.ee_pos_threshold), -1)     # :73-86
+  if full & 2:
+    ee = np.any(np.sqrt(np.sum(np.square(s.rel_pos[:, cfg.ee_sel] - rb.pos[:, cfg.ee_sel]), -1)) > F(cfg.ee_pos_threshold), -1)   # :55-70
+  else:
+    ee = np.any(np.abs(s.rel_pos[:, cfg.ee_sel, 2] - rb.pos[:, cfg.ee_sel, 2]) > F(cfg.ee_pos_threshold), -1)   # :73-86
   return time_out, anchor_pos, anchor_ori, ee
 
 

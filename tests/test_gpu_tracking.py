@@ -276,3 +276,35 @@ def test_builtin_no_state_estimation_equals_the_reference_cfg_variant():
     assert obs["policy"].shape == (B, env.vcfg.n_obs_policy - 6)
   for x, y in zip(*outs):
     assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("full", [3, 0])
+def test_trk_3d_termination_variants(full):
+  """bad_anchor_pos / bad_motion_body_pos (3-D distance; tasks/tracking/mdp/terminations.py:18-25,55-70) on the GPU against the
+  reference's own functions; `full = 0`: the height-only variants at the same threshold (different flags on these states)."""
+  g = np.load(snapshot_from("mdp_tracking_g1"))
+  m, mo, _ = setup(g)
+
+  def edit(c):
+    c.enable_corruption, c.push_enabled, c.sampling_mode, c.max_episode_length = False, False, "start", 10**6
+    c.anchor_pos_threshold = c.ee_pos_threshold = 0.05
+    c.term_full3d = full
+
+  env = make_env(g, mo, edit)
+  S = Drv(env)
+  T, B = g["actions"].shape[:2]
+  S.put("env_origins", g["origins"]); S.put("encoder_bias", g["enc_bias"]); S.put("time_steps", g["time0"] + 1)
+  S.put("rel_pos", g["rel0_pos"]); S.put("rel_quat", g["rel0_quat"])
+  alive = np.ones(B, bool)
+  for t in range(T):
+    d = snapshot_from.load(g, t, m)
+    S.put("action_in", g["actions"][t])
+    S.run(0)
+    S.upload(d)
+    S.run(2)
+    td = S.get("term_dones").astype(bool)
+    np.testing.assert_array_equal(td[alive, 1], g["ref_term_anchor_pos_3d" if full else "ref_term_anchor_pos_z_at_thr3d"][t][alive])
+    np.testing.assert_array_equal(td[alive, 3], g["ref_term_ee_3d" if full else "ref_term_ee_z_at_thr3d"][t][alive])
+    alive &= ~S.get("reset_buf").astype(bool)
+    S.upload(d)
+    S.run(3)

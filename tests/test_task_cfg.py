@@ -338,3 +338,22 @@ def test_tracking_no_state_estimation_task_resolves_to_gathers(play):
   keep[2 * nj + 9: 2 * nj + 12] = False
   np.testing.assert_array_equal(c.noise_lo[keep], full.noise_lo[keep])
   assert not c.noise_lo[~keep].any() and not c.noise_hi[~keep].any()
+
+
+def test_tracking_3d_terminations_are_consumed():
+  """bad_anchor_pos / bad_motion_body_pos (tasks/tracking/mdp/terminations.py:18-25,55-70) share the kernel slots of their z-only
+  twins: the cfg chooses one of each pair."""
+  m = mjlab_b200.load_model("g1_flat")
+  d = _load("Mjlab-Tracking-Flat-Unitree-G1", False)
+  z = envcfg.tracking_from_manager_cfg(copy.deepcopy(d), m, 500)
+  assert z.term_full3d == 0
+  d["terminations"]["anchor_pos"] = dict(d["terminations"]["anchor_pos"], func="bad_anchor_pos")
+  d["terminations"]["anchor_pos"]["params"]["threshold"] = 0.3
+  c = envcfg.tracking_from_manager_cfg(copy.deepcopy(d), m, 500)
+  assert c.term_full3d == 1 and c.anchor_pos_threshold == 0.3 and c.ee_pos_threshold == z.ee_pos_threshold
+  d["terminations"]["ee_body_pos"] = dict(d["terminations"]["ee_body_pos"], func="bad_motion_body_pos")
+  c = envcfg.tracking_from_manager_cfg(copy.deepcopy(d), m, 500)
+  assert c.term_full3d == 3 and list(c.ee_sel) == list(z.ee_sel)
+  d["terminations"]["both"] = dict(d["terminations"]["anchor_pos"], func="bad_anchor_pos_z_only")
+  with pytest.raises(envcfg.UnsupportedTermError, match="share one kernel slot"):
+    envcfg.tracking_from_manager_cfg(d, m, 500)

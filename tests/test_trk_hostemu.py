@@ -118,3 +118,37 @@ def test_kernels_match_oracle_with_resets(mode, inject):
     np.testing.assert_allclose(sim.qpos, d.qpos, **TOL)
     assert int(env.step_counter[0]) == s.step_counter == t + 1
   assert nreset >= B
+
+
+@pytest.mark.parametrize("full", [3, 0])
+def test_3d_termination_variants_kernel_source_vs_reference(full):
+  """bad_anchor_pos / bad_motion_body_pos (3-D distance) against the reference's functions; `full = 0`: the z-only variants at the
+  same threshold, which give different flags on these states."""
+  g = np.load(snapshot_from("mdp_tracking_g1"))
+  m, mo, cfg = setup(g)
+  cfg.max_episode_length = 10**6
+  cfg.anchor_pos_threshold = cfg.ee_pos_threshold = 0.05
+  cfg.term_full3d = full
+  T, B = g["actions"].shape[:2]
+  sim = HostSim(m, B, nconmax=35, njmax=250)
+  env = HostTrk(sim, cfg, mo)
+  env.env_origins[:] = g["origins"]
+  env.encoder_bias[:] = g["enc_bias"]
+  env.time_steps[:] = g["time0"] + 1
+  env.rel_pos[:], env.rel_quat[:] = g["rel0_pos"], g["rel0_quat"]
+  alive = np.ones(B, bool)
+  checked = 0
+  for t in range(T):
+    d = snapshot_from.load(g, t, m)
+    env.action_in[:] = g["actions"][t]
+    env.stage(0)
+    upload(sim, d)
+    env.stage(2)
+    td = env.term_dones.astype(bool)
+    np.testing.assert_array_equal(td[alive, 1], g["ref_term_anchor_pos_3d" if full else "ref_term_anchor_pos_z_at_thr3d"][t][alive])
+    np.testing.assert_array_equal(td[alive, 3], g["ref_term_ee_3d" if full else "ref_term_ee_z_at_thr3d"][t][alive])
+    checked += int(alive.sum())
+    alive &= ~env.reset_buf.astype(bool)
+    upload(sim, d)
+    env.stage(3)
+  assert checked >= B

@@ -64,3 +64,31 @@ def test_adaptive_sampling_probabilities():
   s.bin_failed_count[:] = [0, 2, 0, 0, 1, 0]
   p = OT.sampling_probabilities(cfg, s)
   assert abs(p.sum() - 1) < 1e-6 and p.argmax() == 1 and p[0] > p[2] > 0   # non-causal kernel: bin 0 sees the failures ahead of it
+
+
+def test_3d_termination_variants_match_reference_functions():
+  """bad_anchor_pos / bad_motion_body_pos (tasks/tracking/mdp/terminations.py:18-25,55-70: 3-D distance instead of the height
+  difference), pinned by the reference's functions at a threshold where they differ from the z-only variants on these states."""
+  g = np.load(snapshot_from("mdp_tracking_g1"))
+  m, mo, cfg = setup(g)
+  thr = 0.05
+  assert (g["ref_term_anchor_pos_3d"] != g["ref_term_anchor_pos_z_at_thr3d"]).any() and (g["ref_term_ee_3d"] != g["ref_term_ee_z_at_thr3d"]).any()
+  for k in ("ref_term_anchor_pos_3d", "ref_term_ee_3d"):
+    assert g[k].any() and not g[k].all()
+  T, B = g["actions"].shape[:2]
+  for full in (3, 0):
+    cfg.anchor_pos_threshold = cfg.ee_pos_threshold = thr
+    cfg.term_full3d = full
+    s = OT.make_state(cfg, B, g["origins"])
+    s.encoder_bias[:] = g["enc_bias"]
+    s.time_steps[:] = g["time0"] + 1
+    s.rel_pos[:], s.rel_quat[:] = g["rel0_pos"], g["rel0_quat"]
+    for t in range(T):
+      d = snapshot_from.load(g, t, m)
+      OT.apply_action(cfg, s, d, g["actions"][t])
+      OT.post(cfg, m, mo, s, d, u=np.zeros((B, OT.A.NDRAW), np.float32), do_reset=False)
+      np.testing.assert_array_equal(s.term_dones[:, 1], g["ref_term_anchor_pos_3d" if full else "ref_term_anchor_pos_z_at_thr3d"][t])
+      np.testing.assert_array_equal(s.term_dones[:, 3], g["ref_term_ee_3d" if full else "ref_term_ee_z_at_thr3d"][t])
+      rb = OT.robot_bodies(cfg, d)
+      OT.update_metrics(cfg, s, d, OT.motion_frame(cfg, mo, s), rb)
+      OT.update_command(cfg, mo, s, d, rb, None)
