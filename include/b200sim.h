@@ -225,7 +225,7 @@ enum b2_di {
 typedef struct b2_model {
   int nq, nv, nu, nbody, njnt, ngeom, nsite, nsensor, nsensordata, npair, nmocap, nlevel;
   int integrator;    /* 0 euler, 3 implicitfast */
-  int cone;          /* 0 pyramidal (only supported cone) */
+  int cone;          /* 0 pyramidal, 1 elliptic (MujocoCfg.cone, src/mjlab/sim/sim.py:51-56) */
   int solver;        /* 2 newton (only supported solver) */
   int iterations, ls_iterations, disableflags;
   int has_accelerometer, has_subtreevel;

@@ -103,7 +103,7 @@ static __host__ __device__ inline int solve_slot(int p, int n, int cap) {
 // are still iterating - so the sensor stage fills the solver's tail instead of following it.  A claimed entry is waited
 // for only when all earlier-finished worlds are already taken, i.e. at the very end of the launch.  All CTAs are resident
 // (grid <= SMs x occupancy), so every claimed entry is eventually produced.
-template <bool CG, bool FR>
+template <bool CG, bool FR, bool EL = false>
 __global__ void __launch_bounds__(B2_WPB * 32, B2_SOLVE_MINB) k_solve_t(const KModel m, const KData d, const SolveSmem L, const PostSmem LP, int post_mode, const unsigned char* mask, const int* gate, int w0, int w1) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   real* smem = reinterpret_cast<real*>(smem_raw);
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(B2_WPB * 32, B2_SOLVE_MINB) k_solve_t(const KM
 #ifdef B2_TIMING
       unsigned long long t0 = b2_gtime();
 #endif
-      solve_world_t<CG, FR>(m, d, L, w, smem + (size_t)warp * L.fixed_total, arena, actl);
+      solve_world_t<CG, FR, EL>(m, d, L, w, smem + (size_t)warp * L.fixed_total, arena, actl);
       __syncwarp();
 #ifdef B2_TIMING
       if (lane == 0 && w < 16384) { g_tim[3 * w] = t0; g_tim[3 * w + 1] = b2_gtime(); g_tim[3 * w + 2] = b2_smid(); }
@@ -172,9 +172,13 @@ __global__ void __launch_bounds__(B2_WPB * 32, B2_SOLVE_MINB) k_solve_t(const KM
 #define k_solve_cg k_solve_t<true, false>
 #define k_solve_fr k_solve_t<false, true>
 #define k_solve_cg_fr k_solve_t<true, true>
+// elliptic friction cones (opt.cone = 1): Newton and CG; not combined with friction-loss rows (check_sizes refuses the pair)
+#define k_solve_el k_solve_t<false, false, true>
+#define k_solve_cg_el k_solve_t<true, false, true>
 typedef void (*solve_kernel_t)(const KModel, const KData, const SolveSmem, const PostSmem, int, const unsigned char*, const int*, int, int);
 static solve_kernel_t solve_kernel(const KModel& km) {
   const bool cg = km.solver == 1, fr = km.nfriction > 0;
+  if (km.cone == 1) return cg ? (solve_kernel_t)k_solve_cg_el : (solve_kernel_t)k_solve_el;
   return fr ? (cg ? (solve_kernel_t)k_solve_cg_fr : (solve_kernel_t)k_solve_fr) : (cg ? (solve_kernel_t)k_solve_cg : (solve_kernel_t)k_solve);
 }
 static void launch_solve(int grid, size_t smem, cudaStream_t st, const KModel& km, const KData& kd, const SolveSmem& lv, const PostSmem& lp,
@@ -349,7 +353,7 @@ static int g_nplans = 0;
 static PlanKey plan_key(const b2_model* m, const b2_data* d) {
   int dev = -1;
   cudaGetDevice(&dev);
-  PlanKey k = {{m->nq, m->nv, m->nu, m->nbody, m->njnt, m->nlimited, m->maxchain, d->nconmax, d->njmax, dev, m->solver, m->nfriction}};
+  PlanKey k = {{m->nq, m->nv, m->nu, m->nbody, m->njnt, m->nlimited, m->maxchain, d->nconmax, d->njmax, dev, m->solver, m->nfriction + (m->cone << 20)}};
   return k;
 }
 
@@ -381,7 +385,8 @@ static int check_sizes(const b2_model* m, const b2_data* d) {
   if (!m || !d) return fail("null model/data");
   if (m->nv > 64) return fail("nv=%d exceeds the 64-dof limit of the per-world dof masks", m->nv);
   if (m->nv < 1) return fail("nv must be >= 1");
-  if (m->cone != 0) return fail("only the pyramidal cone is supported");
+  if (m->cone != 0 && m->cone != 1) return fail("unknown friction cone %d (0 pyramidal, 1 elliptic)", m->cone);
+  if (m->cone == 1 && m->nfriction > 0) return fail("the elliptic cone is not combined with friction-loss rows (dof_frictionloss > 0) in this build");
   if (m->solver != 2 && m->solver != 1) return fail("supported solvers: Newton, CG (PGS is not implemented)");
   if (m->integrator != B2_INT_EULER && m->integrator != B2_INT_IMPLICITFAST) return fail("unsupported integrator %d", m->integrator);
   if (d->nworld < 1 || d->nconmax < 0 || d->njmax < 1) return fail("bad nworld/nconmax/njmax");

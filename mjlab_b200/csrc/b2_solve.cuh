@@ -172,15 +172,103 @@ B2_DEV void fric_quad(real x, real ja, real v, real D, real f, real& q0, real& q
   else { const real dj = D * ja; q0 += (real)0.5 * dj * ja; q1 += dj * v; q2 += (real)0.5 * D * v * v; }
 }
 
+// ---- elliptic friction cones (opt.cone = mjCONE_ELLIPTIC; mj_constraintUpdate / PrimalEval / HessianCone restated) ----------
+// A contact with dim > 1 owns `dim` rows along its frame axes (normal, tangents).  Its rows carry NEGATED D in the solver's D
+// array: that marks them for the per-row passes (which skip them) and the per-contact passes below recover D_j = -D[adr + j].
+// With U = (mu x_n, f_j x_tj), N = U_0 and T = |U_1..|: N >= mu T satisfied (no cost); mu N + T <= 0 fully violated (every row
+// quadratic, weight D_j); else the residual is outside both cones and pays 0.5 Dm (N - mu T)^2, Dm = D_n / (mu^2 (1 + mu^2)).
+// All of this sits behind the template parameter EL: pyramidal models run instantiations that carry none of it.
+struct ConeNone {};
+struct ConeArgs { int* cinfo; const real* fri; int ncon; };   // cinfo: 4 ints per contact (row address | -1, dim | zone << 8, body1, body2); fri: 5 per contact
+template <bool EL> struct ConeSel { typedef ConeNone type; };
+template <> struct ConeSel<true> { typedef ConeArgs type; };
+
+B2_DEV int cone_zone(real N, real T, real mu) {
+  if (N >= mu * T || (T <= 0 && N >= 0)) return 0;
+  if (mu * N + T <= 0 || (T <= 0 && N < 0)) return 1;
+  return 2;
+}
+// cost and its first / second derivative along jar + alpha jv, summed over this lane's cone contacts (lanes over contacts)
+B2_DEV void cone_ls(const ConeArgs& ca, real alpha, const real* jar, const real* jv, const real* D, real& e0, real& e1, real& e2) {
+  B2_UNROLL1
+  for (int c = B2_LANE; c < ca.ncon; c += B2_NLANE) {
+    const int adr = ca.cinfo[4 * c], dim = ca.cinfo[4 * c + 1] & 0xff;
+    if (adr < 0 || dim < 2) continue;
+    const real* fr = ca.fri + 5 * c;
+    const real D0 = -D[adr];
+    const real mu = fr[0] * sqrt(D0 / -D[adr + 1]);
+    const real U0 = jar[adr] * mu, V0 = jv[adr] * mu;
+    real UU = 0, UV = 0, VV = 0;
+    for (int j = 1; j < dim; ++j) {
+      const real u = jar[adr + j] * fr[j - 1], v = jv[adr + j] * fr[j - 1];
+      UU += u * u; UV += u * v; VV += v * v;
+    }
+    const real N = U0 + alpha * V0;
+    const real Tsq = UU + alpha * (2 * UV + alpha * VV);
+    const real T = Tsq > 0 ? sqrt(Tsq) : (real)0;
+    const int zone = cone_zone(N, T, mu);
+    if (zone == 1) {
+      for (int j = 0; j < dim; ++j) {
+        const real Dj = -D[adr + j], v = jv[adr + j], x = jar[adr + j] + alpha * v;
+        e0 += (real)0.5 * Dj * x * x; e1 += Dj * x * v; e2 += Dj * v * v;
+      }
+    } else if (zone == 2) {
+      const real Dm = D0 / (mu * mu * (1 + mu * mu));
+      const real t = UV + alpha * VV;
+      const real N1 = V0, T1 = t / T, T2 = VV / T - t * t / (T * T * T);
+      const real NmT = N - mu * T, s1 = N1 - mu * T1;
+      e0 += (real)0.5 * Dm * NmT * NmT; e1 += Dm * NmT * s1; e2 += Dm * (s1 * s1 - NmT * mu * T2);
+    }
+  }
+}
+// constraint update of the cone contacts at the current residual: returns this lane's share of the cost; with WRITE also the
+// rows' forces / Hessian weights (zone 1) and the zone, stored in cinfo[4 c + 1] >> 8 for the Hessian pass
+template <bool WRITE>
+B2_DEV real cone_update(const ConeArgs& ca, const real* jar, const real* D, real* wgt, real* frc) {
+  real cost = 0;
+  B2_UNROLL1
+  for (int c = B2_LANE; c < ca.ncon; c += B2_NLANE) {
+    const int adr = ca.cinfo[4 * c], dim = ca.cinfo[4 * c + 1] & 0xff;
+    if (adr < 0 || dim < 2) continue;
+    const real* fr = ca.fri + 5 * c;
+    const real D0 = -D[adr];
+    const real mu = fr[0] * sqrt(D0 / -D[adr + 1]);
+    const real N = jar[adr] * mu;
+    real U[3] = {N, 0, 0}, TT = 0;
+    for (int j = 1; j < dim; ++j) { U[j] = jar[adr + j] * fr[j - 1]; TT += U[j] * U[j]; }
+    const real T = TT > 0 ? sqrt(TT) : (real)0;
+    const int zone = cone_zone(N, T, mu);
+    if (WRITE) ca.cinfo[4 * c + 1] = dim | (zone << 8);
+    if (zone == 1) {
+      for (int j = 0; j < dim; ++j) {
+        const real Dj = -D[adr + j], x = jar[adr + j];
+        cost += (real)0.5 * Dj * x * x;
+        if (WRITE) { wgt[adr + j] = Dj; frc[adr + j] = -Dj * x; }
+      }
+    } else if (zone == 2) {
+      const real Dm = D0 / (mu * mu * (1 + mu * mu));
+      const real NmT = N - mu * T;
+      cost += (real)0.5 * Dm * NmT * NmT;
+      if (WRITE) {
+        const real f0 = -Dm * NmT * mu;
+        frc[adr] = f0;
+        for (int j = 1; j < dim; ++j) frc[adr + j] = -f0 / T * U[j] * fr[j - 1];
+      }
+    }
+  }
+  return cost;
+}
+
 // FR: the world may hold friction-loss rows (rows 0..nf-1, bounds in floss).  A template parameter like CG below: models
 // without friction loss run instantiations that carry none of this code.
-template <bool FR>
-B2_DEVN LsPnt ls_eval(real alpha, real q0g, real q1g, real q2g, const real* jar, const real* jv, const real* D, int nefc, int nf, const real* floss) {  // @region linesearch
+template <bool FR, bool EL>
+B2_DEVN LsPnt ls_eval(real alpha, real q0g, real q1g, real q2g, const real* jar, const real* jv, const real* D, int nefc, int nf, const real* floss, typename ConeSel<EL>::type ca) {  // @region linesearch
   B2_LS_COUNT();
   real q0 = 0, q1 = 0, q2 = 0;
   B2_UNROLL1   // (unrolling by 2 / 4 to overlap the passes' loads was measured: +2 % kernel time, code size again)
   for (int r = B2_LANE; r < nefc; r += B2_NLANE) {
     real x = jar[r] + alpha * jv[r];
+    if (EL && D[r] < 0) continue;   // cone rows: cone_ls below
     if (FR && r < nf) {
       fric_quad(x, jar[r], jv[r], D[r], floss[r], q0, q1, q2);
     } else if (x < 0) {
@@ -197,6 +285,12 @@ B2_DEVN LsPnt ls_eval(real alpha, real q0g, real q1g, real q2g, const real* jar,
   p.cost = alpha * alpha * q2 + alpha * q1 + q0;
   p.d1 = 2 * alpha * q2 + q1;
   p.d2 = 2 * q2;
+  if constexpr (EL) {
+    real e0 = 0, e1 = 0, e2 = 0;
+    cone_ls(ca, alpha, jar, jv, D, e0, e1, e2);
+    b2_wsum3(e0, e1, e2);
+    p.cost += e0; p.d1 += e1; p.d2 += e2;
+  }
   if (p.d2 <= 0) p.d2 = B2_MINVAL;
   return p;
 }
@@ -206,14 +300,15 @@ B2_DEVN LsPnt ls_eval(real alpha, real q0g, real q1g, real q2g, const real* jar,
 // together reads each row once and lets the three warp reductions overlap instead of running back to back - the line search
 // is a chain of dependent reductions, and on the heaviest worlds (which set the kernel's duration) it is a third of the time.
 // Each point's sums are accumulated in the same order as ls_eval does, so the values are bit-identical to three calls.
-template <bool FR>
-B2_DEVN void ls_eval3(const real* alpha, LsPnt* out, real q0g, real q1g, real q2g, const real* jar, const real* jv, const real* D, int nefc, int nf, const real* floss) {
+template <bool FR, bool EL>
+B2_DEVN void ls_eval3(const real* alpha, LsPnt* out, real q0g, real q1g, real q2g, const real* jar, const real* jv, const real* D, int nefc, int nf, const real* floss, typename ConeSel<EL>::type ca) {
   B2_LS_COUNT();
   real a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0, c0 = 0, c1 = 0, c2 = 0;
   const real al0 = alpha[0], al1 = alpha[1], al2 = alpha[2];
   B2_UNROLL1
   for (int r = B2_LANE; r < nefc; r += B2_NLANE) {
     const real ja = jar[r], v = jv[r], Dr = D[r];
+    if (EL && Dr < 0) continue;
     if (FR && r < nf) {
       const real f = floss[r];
       fric_quad(ja + al0 * v, ja, v, Dr, f, a0, a1, a2);
@@ -238,6 +333,12 @@ B2_DEVN void ls_eval3(const real* alpha, LsPnt* out, real q0g, real q1g, real q2
     p.cost = al * al * q2[k] + al * q1[k] + q0[k];
     p.d1 = 2 * al * q2[k] + q1[k];
     p.d2 = 2 * q2[k];
+    if constexpr (EL) {
+      real e0 = 0, e1 = 0, e2 = 0;
+      cone_ls(ca, al, jar, jv, D, e0, e1, e2);
+      b2_wsum3(e0, e1, e2);
+      p.cost += e0; p.d1 += e1; p.d2 += e2;
+    }
     if (p.d2 <= 0) p.d2 = B2_MINVAL;
     out[k] = p;
   }
@@ -266,9 +367,10 @@ B2_DEV bool ls_move_bracket(LsPnt& p, const LsPnt* cand) {
 // Exact 1-D minimisation along `search` (MuJoCo's iterative primal line search:
 // Newton steps until the derivative changes sign, then bracket refinement).
 // `cost0` / `slope0`: cost and directional derivative grad.search at alpha = 0, known from the Newton update.
-template <bool FR>
+template <bool FR, bool EL>
 B2_DEVN real linesearch(real q0g, real q1g, real q2g, real snorm, real tolerance, real ls_tolerance, int ls_iterations,
-                       real scale, const real* jar, const real* jv, const real* D, int nefc, real cost0, real slope0, int nf, const real* floss) {
+                       real scale, const real* jar, const real* jv, const real* D, int nefc, real cost0, real slope0, int nf, const real* floss,
+                       typename ConeSel<EL>::type ca) {
   if (snorm < B2_MINVAL) return 0;
   real gtol = tolerance * ls_tolerance * snorm / scale;
   int nev = 0;
@@ -282,9 +384,9 @@ B2_DEVN real linesearch(real q0g, real q1g, real q2g, real snorm, real tolerance
     p0.alpha = 0; p0.cost = cost0; p0.d1 = slope0; p0.d2 = -slope0;
   } else {
     B2_LSSTAT(1)
-    p0 = ls_eval<FR>(0, q0g, q1g, q2g, jar, jv, D, nefc, nf, floss);
+    p0 = ls_eval<FR, EL>(0, q0g, q1g, q2g, jar, jv, D, nefc, nf, floss, ca);
   }
-  LsPnt p1 = ls_eval<FR>(p0.alpha - p0.d1 / p0.d2, q0g, q1g, q2g, jar, jv, D, nefc, nf, floss); ++nev;
+  LsPnt p1 = ls_eval<FR, EL>(p0.alpha - p0.d1 / p0.d2, q0g, q1g, q2g, jar, jv, D, nefc, nf, floss, ca); ++nev;
   if (p0.cost < p1.cost) p1 = p0;
   if (fabs(p1.d1) < ls_gtol(p1, gtol)) return p1.alpha;
   real dir = p1.d1 < 0 ? (real)1 : (real)-1;
@@ -293,7 +395,7 @@ B2_DEVN real linesearch(real q0g, real q1g, real q2g, real snorm, real tolerance
   while (p1.d1 * dir <= -ls_gtol(p1, gtol) && nev < ls_iterations) {
     p2 = p1; p2set = true;
     B2_LSSTAT(1)
-    p1 = ls_eval<FR>(p1.alpha - p1.d1 / p1.d2, q0g, q1g, q2g, jar, jv, D, nefc, nf, floss); ++nev;
+    p1 = ls_eval<FR, EL>(p1.alpha - p1.d1 / p1.d2, q0g, q1g, q2g, jar, jv, D, nefc, nf, floss, ca); ++nev;
     if (fabs(p1.d1) < ls_gtol(p1, gtol)) return p1.alpha;
   }
   if (nev >= ls_iterations || !p2set) return p1.alpha;
@@ -309,7 +411,7 @@ B2_DEVN real linesearch(real q0g, real q1g, real q2g, real snorm, real tolerance
     const bool want_mid = nev < ls_iterations;
     real al[3] = {p1.alpha - p1.d1 / p1.d2, want_mid ? (real)0.5 * (p1.alpha + p2.alpha) : (real)0, 0};
     LsPnt out[3];
-    ls_eval3<FR>(al, out, q0g, q1g, q2g, jar, jv, D, nefc, nf, floss);
+    ls_eval3<FR, EL>(al, out, q0g, q1g, q2g, jar, jv, D, nefc, nf, floss, ca);
     p1next = out[0]; pmid = out[1];
   }
   while (nev < ls_iterations) {
@@ -328,7 +430,7 @@ B2_DEVN real linesearch(real q0g, real q1g, real q2g, real snorm, real tolerance
                   want_mid ? (real)0.5 * (p1.alpha + p2.alpha) : (real)0};
     LsPnt out[3];
     B2_LSSTAT(2)
-    ls_eval3<FR>(al, out, q0g, q1g, q2g, jar, jv, D, nefc, nf, floss);
+    ls_eval3<FR, EL>(al, out, q0g, q1g, q2g, jar, jv, D, nefc, nf, floss, ca);
     if (b1) p1next = out[0];
     if (b2) p2next = out[1];
     pmid = out[2];
@@ -339,10 +441,14 @@ B2_DEVN real linesearch(real q0g, real q1g, real q2g, real snorm, real tolerance
 }
 
 // contact-frame force [normal, t1, t2] decoded from the pyramid edge forces
-B2_DEV void contact_force(real* out, int adr, int dim, const real* fri, const real* efc_force) {  // @region sensor_helpers
+B2_DEV void contact_force(real* out, int adr, int dim, const real* fri, const real* efc_force, int cone) {  // @region sensor_helpers
   out[0] = out[1] = out[2] = 0;
   if (adr < 0) return;
   if (dim == 1) { out[0] = efc_force[adr]; return; }
+  if (cone == 1) {   // elliptic: the rows are the frame axes
+    for (int k = 0; k < dim && k < 3; ++k) out[k] = efc_force[adr + k];
+    return;
+  }
   for (int k = 1; k < dim; ++k) {
     int r = adr + 2 * (k - 1);
     real f1 = efc_force[r], f2 = efc_force[r + 1];
@@ -413,7 +519,7 @@ __device__ unsigned long long g_phase[8 * 16384];
 // CG: compile-time choice of the search direction (true = mjSOL_CG: M-preconditioned Polak-Ribiere; false = Newton).  A template
 // and not a run-time branch: the Newton kernel's loop is instruction-fetch bound, and the CG code inside it cost 5 % (0.394 ->
 // 0.414 ms per launch) even though it never ran.
-template <bool CG, bool FR>
+template <bool CG, bool FR, bool EL = false>
 B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, int w, real* sm, real* arena, int* actl) {  // @region setup_loads
   B2_PH_BEGIN()
   const int nv = m.nv, nb = m.nbody, nq = m.nq, nu = m.nu, njmax = d.njmax, nconmax = d.nconmax;
@@ -425,6 +531,8 @@ B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, i
   unsigned* actmask = (unsigned*)(sm + L.actmask);
   real* gold = sm + L.gold; real* mgold = sm + L.mgold;
   real* floss = sm + L.floss;   // FR only
+  // rows of a frictional contact: the pyramid's 2 (dim - 1) edges, or (EL) the dim axes of its frame
+  auto crows = [](int dim) { return dim == 1 ? 1 : (EL ? dim : 2 * (dim - 1)); };
   constexpr bool cg = CG;   // mjSOL_CG: M is the preconditioner, Polak-Ribiere directions (mj_solCG)
   const int ld = b2_ld(nv);
   const int* body_parent = MI(B2_MI_BODY_PARENTID);
@@ -491,7 +599,7 @@ B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, i
     B2_UNROLL1
     for (int c = B2_LANE; c < ncon; c += B2_NLANE) {
       if (c_dist[c] < c_inc[c]) {
-        int nrow = c_dim[c] == 1 ? 1 : 2 * (c_dim[c] - 1);
+        int nrow = crows(c_dim[c]);
         int b1 = geom_body[c_geom[2 * c]], b2 = geom_body[c_geom[2 * c + 1]];
         int wd = b2_popc((unsigned)(dofmask[2 * b1] | dofmask[2 * b2])) + b2_popc((unsigned)(dofmask[2 * b1 + 1] | dofmask[2 * b2 + 1]));
         crow += nrow; ckept += 1; cdofs += wd; cpool += nrow * (wd | 1);
@@ -655,7 +763,7 @@ B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, i
     for (int base = 0; base < ncon; base += B2_NLANE) {
       int c = base + B2_LANE;
       int nrow = 0;
-      if (c < ncon && c_dist[c] < c_inc[c]) nrow = c_dim[c] == 1 ? 1 : 2 * (c_dim[c] - 1);
+      if (c < ncon && c_dist[c] < c_inc[c]) nrow = crows(c_dim[c]);
       int incl = nrow;
 #ifndef B2_HOSTEMU
       B2_UNROLL1
@@ -694,7 +802,7 @@ B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, i
       int adr = cinfo[4 * c];
       if (adr < 0) continue;
       int dim = cinfo[4 * c + 1], b1 = cinfo[4 * c + 2], b2 = cinfo[4 * c + 3];
-      int nrow = dim == 1 ? 1 : 2 * (dim - 1);
+      int nrow = crows(dim);
       unsigned lo1 = (unsigned)dofmask[2 * b1], hi1 = (unsigned)dofmask[2 * b1 + 1];
       unsigned lo2 = (unsigned)dofmask[2 * b2], hi2 = (unsigned)dofmask[2 * b2 + 1];
       if (!overflow && (b1 != pb1 || b2 != pb2)) {
@@ -741,6 +849,11 @@ B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, i
         real jn = F[0] * jd[0] + F[1] * jd[1] + F[2] * jd[2];
         if (dim == 1) {
           jpool[pooloff + a] = jn;
+        } else if (EL) {
+          jpool[pooloff + a] = jn;
+          B2_UNROLL1
+          for (int k = 1; k < dim; ++k)
+            jpool[pooloff + k * wpad + a] = k < 3 ? F[3 * k] * jd[0] + F[3 * k + 1] * jd[1] + F[3 * k + 2] * jd[2] : (real)0;
         } else {
           B2_UNROLL1
           for (int k = 1; k < dim; ++k) {
@@ -769,7 +882,7 @@ B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, i
       B2_UNROLL1
       for (int c = 0; c < ncon; ++c) {
         int adr = cinfo[4 * c];
-        if (adr >= 0) { int dim = cinfo[4 * c + 1]; last = adr + (dim == 1 ? 1 : 2 * (dim - 1)); }
+        if (adr >= 0) last = adr + crows(cinfo[4 * c + 1]);
       }
       nefc = last;
     }
@@ -839,11 +952,27 @@ B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, i
       } else {
         int c = src;
         invw = biw[2 * cinfo[4 * c + 2]] + biw[2 * cinfo[4 * c + 3]];
-        if (cinfo[4 * c + 1] > 1) {
+        if (!EL && cinfo[4 * c + 1] > 1) {
           real f0 = c_fri[5 * c];
           invw = (invw + f0 * f0 * invw) * 2 * f0 * f0 / impratio;
         }
         kbi(timestep, c_solref + 2 * c, c_solimp + 5 * c, pos, k, b, imp);
+        if (EL && cinfo[4 * c + 1] > 1) {
+          // elliptic cone (mj_makeImpedance): the friction rows take R_n / impratio (scaled by mu_1^2 / mu_j^2 for the later
+          // axes) and have no position term; the negated D marks the contact's rows for the solver's per-contact passes
+          const int j = r - cinfo[4 * c];
+          real R = fmax(invw * (1 - imp) / imp, B2_MINVAL);
+          if (j > 0) {
+            R /= fmax(impratio, B2_MINVAL);
+            if (j > 1) { const real f0 = c_fri[5 * c], fj = c_fri[5 * c + j - 1]; R *= f0 * f0 / (fj * fj); }
+            k = 0;
+          }
+          const real Dr = (real)1 / R;
+          const real ar = -b * jar[r] - k * imp * pos;
+          D[r] = -Dr; aref[r] = ar;
+          g_efcD[r] = Dr; g_aref[r] = ar;
+          continue;
+        }
       }
       real R = fmax(invw * (1 - imp) / imp, B2_MINVAL);
       real Dr = (real)1 / R;
@@ -854,6 +983,8 @@ B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, i
     B2_WSYNC();
   }
 
+  typename ConeSel<EL>::type ca;
+  if constexpr (EL) { ca.cinfo = cinfo; ca.fri = c_fri; ca.ncon = ncon; }
   // ---- solve ------------------------------------------------------------------------------------------  // @region solve_init
   B2_PH(0)
   int niter = 0;
@@ -875,9 +1006,11 @@ B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, i
     B2_UNROLL1
     for (int r = B2_LANE; r < nefc; r += B2_NLANE) {
       real x = jar[r];
+      if (EL && D[r] < 0) continue;
       if (FR && r < nf) { real f_, w_; cs += fric_row(x, D[r], floss[r], f_, w_); }
       else if (x < 0) cs += (real)0.5 * D[r] * x * x;
     }
+    if constexpr (EL) cs += cone_update<false>(ca, jar, D, nullptr, nullptr);
     cs = b2_wsum(cs);
     // cost at the warm start
     B2_UNROLL1
@@ -888,9 +1021,11 @@ B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, i
     B2_UNROLL1
     for (int r = B2_LANE; r < nefc; r += B2_NLANE) {
       real x = jar[r];
+      if (EL && D[r] < 0) continue;
       if (FR && r < nf) { real f_, w_; cw += fric_row(x, D[r], floss[r], f_, w_); }
       else if (x < 0) cw += (real)0.5 * D[r] * x * x;
     }
+    if constexpr (EL) cw += cone_update<false>(ca, jar, D, nullptr, nullptr);
     real gw = 0;
     symv_global(M, nv, ld, qacc, Ma);
     B2_UNROLL1
@@ -914,7 +1049,7 @@ B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, i
       // The Hessian M + J^T diag(D*active) J only depends on WHICH rows are active: when the active set equals the one
       // of the last factorisation, the factor still in H is reused (same result, no copy / J^T D J / Cholesky).
       real c1 = 0;
-      bool same_set = it > 0;
+      bool same_set = !EL && it > 0;   // a cone Hessian changes with the residual itself, not only with the active set
 #ifdef B2_HOSTEMU
       int nflip_stat = 0;
 #endif
@@ -924,6 +1059,9 @@ B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, i
         bool act = false;
         if (r < nefc) {
           real x = jar[r];
+          if (EL && D[r] < 0) {   // row of an elliptic contact: written by cone_update below
+            wgt[r] = 0; frc[r] = 0;
+          } else
           if (FR && r < nf) {   // friction loss: "active" = in the quadratic zone (the only state that enters the Hessian)
             real f_, w_;
             c1 += fric_row(x, D[r], floss[r], f_, w_);
@@ -949,6 +1087,10 @@ B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, i
         B2_WSYNC();
         if (B2_LANE == 0) actmask[base >> 5] = bal;
 #endif
+      }
+      if constexpr (EL) {
+        B2_WSYNC();
+        c1 += cone_update<true>(ca, jar, D, wgt, frc);
       }
       real g1 = 0;
       B2_UNROLL1
@@ -1085,6 +1227,53 @@ B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, i
         }
         B2_WSYNC();
       }
+      if constexpr (EL) {
+        // cone Hessians (mj HessianCone): a contact on its cone's surface adds J_c^T Hc J_c, Hc the dim x dim second derivative
+        // of 0.5 Dm (N - mu T)^2 in the contact's residual; same dof pairs as the run the contact belongs to
+        B2_UNROLL1
+        for (int c = 0; c < ncon; ++c) {
+          const int adr = cinfo[4 * c], dz = cinfo[4 * c + 1];
+          if (adr < 0 || (dz >> 8) != 2) continue;
+          const int dim = dz & 0xff;
+          const real* fr = c_fri + 5 * c;
+          const real D0 = -D[adr];
+          const real mu = fr[0] * sqrt(D0 / -D[adr + 1]);
+          const real N = jar[adr] * mu;
+          real U[3] = {N, 0, 0}, sc[3] = {mu, 0, 0}, TT = 0;
+          for (int j = 1; j < dim; ++j) { sc[j] = fr[j - 1]; U[j] = jar[adr + j] * sc[j]; TT += U[j] * U[j]; }
+          const real T = sqrt(TT);
+          const real Dm = D0 / (mu * mu * (1 + mu * mu));
+          real Hc[3][3];
+          Hc[0][0] = 1;
+          const real k3 = mu * N / (T * T * T), kd = mu * mu - mu * N / T;
+          for (int i = 1; i < dim; ++i) {
+            Hc[0][i] = Hc[i][0] = -mu * U[i] / T;
+            for (int j = 1; j < dim; ++j) Hc[i][j] = k3 * U[i] * U[j] + (i == j ? kd : (real)0);
+          }
+          for (int i = 0; i < dim; ++i)
+            for (int j = 0; j < dim; ++j) Hc[i][j] *= Dm * sc[i] * sc[j];
+          const int info = rowinfo[adr];
+          const int off0 = info & 0xffff, run = info >> 16;
+          const int ri0 = runinfo[2 * run];
+          const int dofoff = ri0 & 0xffff, wd = ri0 >> 16;
+          const int wpad = wd | 1;
+          const unsigned char* dl = rundofs + dofoff;
+          const int npair = wd * (wd + 1) / 2;
+          B2_UNROLL1
+          for (int pr = B2_LANE; pr < npair; pr += B2_NLANE) {
+            const int ab = pairtab[pr];
+            const int a = ab >> 8, b = ab & 0xff;
+            real acc = 0;
+            for (int i = 0; i < dim; ++i) {
+              real t = 0;
+              for (int j = 0; j < dim; ++j) t = fma(Hc[i][j], jpool[off0 + j * wpad + b], t);
+              acc = fma(jpool[off0 + i * wpad + a], t, acc);
+            }
+            H[dl[a] * ld + dl[b]] += acc;
+          }
+          B2_WSYNC();
+        }
+      }
       B2_PH(3)
       spd_factor_solve(H, nv, ld, tmp, invd);  // @region factor_call
       }
@@ -1122,7 +1311,7 @@ B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, i
       b2_wsum3(q1, q2, gs);
       rows_dot(jpool, rowinfo, runinfo, rundofs, nefc, search, jv, nullptr);
       B2_PH(5)
-      real alpha = linesearch<FR>(gauss, q1, q2, sn, tolerance, ls_tolerance, m.ls_iterations, scale, jar, jv, D, nefc, cost, cg ? (real)0 : gs, nf, floss);   // the alpha = 0 shortcut needs H search = -grad: Newton only
+      real alpha = linesearch<FR, EL>(gauss, q1, q2, sn, tolerance, ls_tolerance, m.ls_iterations, scale, jar, jv, D, nefc, cost, cg ? (real)0 : gs, nf, floss, ca);   // the alpha = 0 shortcut needs H search = -grad: Newton only
       B2_PH(6)
       if (alpha == 0) break;
       B2_UNROLL1
@@ -1137,6 +1326,7 @@ B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, i
     B2_UNROLL1
     for (int r = B2_LANE; r < nefc; r += B2_NLANE) {
       real x = jar[r];
+      if (EL && D[r] < 0) { g_force[r] = frc[r]; continue; }   // cone rows: the last update's force (the loop ends right after an update)
       if (FR && r < nf) { real f_, w_; fric_row(x, D[r], floss[r], f_, w_); g_force[r] = f_; }
       else g_force[r] = x < 0 ? -D[r] * x : 0;
     }
@@ -1151,7 +1341,10 @@ B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, i
 
 // run-time dispatch for callers that are not templated themselves (the host builds: tests/hostemu, oracle/cport)
 B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int w, real* sm, real* arena, int* actl) {
-  if (m.nfriction > 0) {
+  if (m.cone == 1) {   // elliptic cones (not combined with friction-loss rows: b2_check refuses that pair)
+    if (m.solver == 1) solve_world_t<true, false, true>(m, d, L, w, sm, arena, actl);
+    else solve_world_t<false, false, true>(m, d, L, w, sm, arena, actl);
+  } else if (m.nfriction > 0) {
     if (m.solver == 1) solve_world_t<true, true>(m, d, L, w, sm, arena, actl);
     else solve_world_t<false, true>(m, d, L, w, sm, arena, actl);
   } else if (m.solver == 1) solve_world_t<true, false>(m, d, L, w, sm, arena, actl);
@@ -1368,7 +1561,7 @@ B2_DEV void post_world(const KModel& m, const KData& d, const PostSmem& L, int w
       canc[4 * c] = (unsigned)ancmask[2 * b1]; canc[4 * c + 1] = (unsigned)ancmask[2 * b1 + 1];
       canc[4 * c + 2] = (unsigned)ancmask[2 * b2]; canc[4 * c + 3] = (unsigned)ancmask[2 * b2 + 1];
       real fc[3], fg[3];
-      contact_force(fc, nefc > 0 ? c_adr[c] : -1, c_dim[c], c_fri + 5 * c, efc_force);
+      contact_force(fc, nefc > 0 ? c_adr[c] : -1, c_dim[c], c_fri + 5 * c, efc_force, m.cone);
       mulmTv3(fg, c_frame + 9 * c, fc);
       for (int e = 0; e < 3; ++e) { cfc[3 * c + e] = fc[e]; cfg[3 * c + e] = fg[e]; }
     }
@@ -1457,7 +1650,7 @@ B2_DEV void post_world(const KModel& m, const KData& d, const PostSmem& L, int w
             if (c < cpre) { fg[0] = cfg[3 * c]; fg[1] = cfg[3 * c + 1]; fg[2] = cfg[3 * c + 2]; }
             else {
               real fc[3];
-              contact_force(fc, nefc > 0 ? c_adr[c] : -1, c_dim[c], c_fri + 5 * c, efc_force);
+              contact_force(fc, nefc > 0 ? c_adr[c] : -1, c_dim[c], c_fri + 5 * c, efc_force, m.cone);
               mulmTv3(fg, c_frame + 9 * c, fc);
             }
             net[0] += sgn * fg[0]; net[1] += sgn * fg[1]; net[2] += sgn * fg[2];
@@ -1496,7 +1689,7 @@ B2_DEV void post_world(const KModel& m, const KData& d, const PostSmem& L, int w
                 else {
                   real fc[3];
                   if (c < cpre) { fc[0] = cfc[3 * c]; fc[1] = cfc[3 * c + 1]; fc[2] = cfc[3 * c + 2]; }
-                  else contact_force(fc, nefc > 0 ? c_adr[c] : -1, c_dim[c], c_fri + 5 * c, efc_force);
+                  else contact_force(fc, nefc > 0 ? c_adr[c] : -1, c_dim[c], c_fri + 5 * c, efc_force, m.cone);
                   key = -sqrt(dot3(fc, fc));
                 }
                 // strict ordering by (key, c) to enumerate matches in sorted order
@@ -1512,7 +1705,7 @@ B2_DEV void post_world(const KModel& m, const KData& d, const PostSmem& L, int w
               if (bits & 2) {
                 real fc[3];
                 if (c < cpre) { fc[0] = cfc[3 * c]; fc[1] = cfc[3 * c + 1]; fc[2] = cfc[3 * c + 2]; }
-                else contact_force(fc, nefc > 0 ? c_adr[c] : -1, c_dim[c], c_fri + 5 * c, efc_force);
+                else contact_force(fc, nefc > 0 ? c_adr[c] : -1, c_dim[c], c_fri + 5 * c, efc_force, m.cone);
                 out[p] = picksgn * fc[0]; out[p + 1] = picksgn * fc[1]; out[p + 2] = picksgn * fc[2]; p += 3;
               }
               if (bits & 4) p += 3;

@@ -257,8 +257,10 @@ def check_supported(m) -> None:
     t = (int(m.geom_type[g1]), int(m.geom_type[g2]))
     if t not in SUPPORTED_PAIRS:
       raise ValueError(f"collision between geom types {t} ({m.geom_names[g1]}, {m.geom_names[g2]}) is not supported")
-  if m.opt_cone != 0:
-    raise ValueError("only the pyramidal friction cone is supported")
+  if m.opt_cone not in (0, 1):
+    raise ValueError(f"unknown friction cone {m.opt_cone} (0 pyramidal, 1 elliptic)")
+  if m.opt_cone == 1 and np.any(np.asarray(getattr(m, "dof_frictionloss", 0.0)) > 0):
+    raise ValueError("the elliptic cone is not combined with friction-loss rows (dof_frictionloss > 0)")
   if m.opt_solver not in (1, 2):
     raise ValueError("supported solvers: Newton, CG (PGS is not implemented)")
   if m.opt_integrator not in (0, 3):

@@ -477,7 +477,7 @@ def from_manager_cfg(cfg, m, robot: str) -> VelocityCfg:
   local_names = [n.removeprefix(pre) for n in c.joint_names]
   # ---- timing ---------------------------------------------------------------------------------------------------------
   mj = d["sim"]["mujoco"]
-  if mj["solver"] != "newton" or mj["cone"] != "pyramidal" or mj["integrator"] not in ("implicitfast", "euler"):
+  if mj["solver"] not in ("newton", "cg") or mj["cone"] not in ("pyramidal", "elliptic") or mj["integrator"] not in ("implicitfast", "euler"):
     raise UnsupportedTermError(f"sim options {mj['solver']} / {mj['cone']} / {mj['integrator']} are outside the supported subset")
   c.decimation = int(d["decimation"])
   c.step_dt = float(mj["timestep"]) * c.decimation
@@ -858,7 +858,7 @@ def tracking_from_manager_cfg(cfg, m, time_step_total: int, robot: str = "g1") -
   pre = "robot/"
   local_names = [n.removeprefix(pre) for n in velocity_cfg(m, robot).joint_names]
   mj = d["sim"]["mujoco"]
-  if mj["solver"] != "newton" or mj["cone"] != "pyramidal" or mj["integrator"] not in ("implicitfast", "euler"):
+  if mj["solver"] not in ("newton", "cg") or mj["cone"] not in ("pyramidal", "elliptic") or mj["integrator"] not in ("implicitfast", "euler"):
     raise UnsupportedTermError(f"sim options {mj['solver']} / {mj['cone']} / {mj['integrator']} are outside the supported subset")
   c.step_dt = float(mj["timestep"]) * int(d["decimation"])
   c.max_episode_length_s = float(d["episode_length_s"])

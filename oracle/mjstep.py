@@ -802,7 +802,8 @@ def make_constraint(m, d, njmax=None):
     for lst in (rows_J, rows_pos, rows_margin, rows_invw, rows_solref, rows_solimp, rows_type, rows_id):
       del lst[njmax:]
   virtual_adr = len(rows_J)
-  # contacts (pyramidal cone)
+  cones = []
+  # contacts (pyramidal cone, or elliptic with opt_cone = 1)
   biw = getattr(d, "body_invweight0", m.body_invweight0)
   for ci, c in enumerate(d.contacts):
     c.efc_address = -1
@@ -812,7 +813,8 @@ def make_constraint(m, d, njmax=None):
     jd = _jac_point(m, d, b2, c.pos) - _jac_point(m, d, b1, c.pos)
     jc = c.frame @ jd  # rows: normal, t1, t2
     invw = biw[b1, 0] + biw[b2, 0]
-    nrow = 1 if c.dim == 1 else 2 * (c.dim - 1)
+    elliptic = int(getattr(m, "opt_cone", 0)) == 1 and c.dim > 1
+    nrow = 1 if c.dim == 1 else (c.dim if elliptic else 2 * (c.dim - 1))
     # row addresses are a running sum over all active contacts; a contact is kept iff
     # its rows fit below njmax (so everything after the first overflow is dropped)
     adr = virtual_adr
@@ -822,6 +824,11 @@ def make_constraint(m, d, njmax=None):
     c.efc_address = len(rows_J)
     if c.dim == 1:
       rows = [jc[0]]
+    elif elliptic:
+      # elliptic cone (mj_instantiateContact, mjCNSTR_CONTACT_ELLIPTIC): the contact-frame axes themselves are the rows -
+      # normal first, then the tangents; the friction rows' R is derived from the normal row's below
+      rows = [jc[k] for k in range(c.dim)]
+      cones.append((ci, c.efc_address, c.dim))
     else:
       fri0 = c.friction[0]
       invw = (invw + fri0 * fri0 * invw) * 2 * fri0 * fri0 / m.opt_impratio
@@ -855,6 +862,20 @@ def make_constraint(m, d, njmax=None):
     d.efc_k[i], d.efc_b[i], d.efc_imp[i] = k, b, imp
     d.efc_R[i] = max(rows_invw[i] * (1 - imp) / imp, MINVAL)
     d.efc_D[i] = 1.0 / d.efc_R[i]
+  # elliptic cones (mj_makeImpedance): friction rows have no position term (K = 0), their regulariser follows from the
+  # normal row's - R_t1 = R_n / impratio, R_tj = R_t1 mu_1^2 / mu_j^2 - and the cone's effective friction is
+  # mu = mu_1 sqrt(R_t1 / R_n)
+  d.efc_cones = []
+  for ci, a, dim in cones:
+    c = d.contacts[ci]
+    d.efc_R[a + 1] = d.efc_R[a] / max(MINVAL, m.opt_impratio)
+    for j in range(2, dim):
+      d.efc_R[a + j] = d.efc_R[a + 1] * c.friction[0] ** 2 / c.friction[j - 1] ** 2
+    for j in range(1, dim):
+      d.efc_D[a + j] = 1.0 / d.efc_R[a + j]
+      d.efc_k[a + j] = 0.0
+    mu = c.friction[0] * math.sqrt(d.efc_R[a + 1] / d.efc_R[a])
+    d.efc_cones.append((a, dim, mu, np.asarray(c.friction[: dim - 1], float).copy()))
 
 
 def reference_constraint(m, d):
@@ -976,12 +997,49 @@ class _Pnt:
   __slots__ = ("alpha", "cost", "d1", "d2")
 
 
-def _row_update(jar, D, R, floss, nf):
+def _cone_zone(N, T, mu):
+  """Zone of an elliptic-cone contact from its scaled residual: 0 = satisfied (inside the dual cone), 1 = fully violated
+  (quadratic in every row), 2 = on the cone surface."""
+  if N >= mu * T or (T <= 0 and N >= 0):
+    return 0
+  if mu * N + T <= 0 or (T <= 0 and N < 0):
+    return 1
+  return 2
+
+
+def _row_update(jar, D, R, floss, nf, cones=(), hcones=None):
   """mj_constraintUpdate per row: (cost terms, force, rows that enter the Hessian).  Rows [0, nf) are friction-loss rows:
-  quadratic for |jar| < R f, linear beyond with the force saturated at -/+ f; the others are active iff jar < 0."""
+  quadratic for |jar| < R f, linear beyond with the force saturated at -/+ f; the others are active iff jar < 0.
+  `cones`: elliptic contacts (address, dim, mu, friction); in the middle zone the cost is 0.5 Dm (N - mu T)^2 with
+  N = mu jar_n, T = |friction_j jar_tj| and Dm = D_n / (mu^2 (1 + mu^2)); such a contact's rows leave the diagonal
+  Hessian and its dense dim x dim block (second derivative of that cost) is appended to `hcones`."""
   act = jar < 0
   force = np.where(act, -D * jar, 0.0)
   cost = np.where(act, 0.5 * D * jar * jar, 0.0)
+  for a, dim, mu, fri in cones:
+    x = jar[a:a + dim]
+    sc = np.concatenate(([mu], fri))
+    U = x * sc
+    N, T = U[0], float(np.linalg.norm(U[1:]))
+    zone = _cone_zone(N, T, mu)
+    if zone == 0:
+      force[a:a + dim], cost[a:a + dim], act[a:a + dim] = 0.0, 0.0, False
+    elif zone == 1:
+      force[a:a + dim], cost[a:a + dim], act[a:a + dim] = -D[a:a + dim] * x, 0.5 * D[a:a + dim] * x * x, True
+    else:
+      Dm = D[a] / (mu * mu * (1 + mu * mu))
+      NmT = N - mu * T
+      cost[a:a + dim] = 0.0
+      cost[a] = 0.5 * Dm * NmT * NmT
+      force[a] = -Dm * NmT * mu
+      force[a + 1:a + dim] = -force[a] / T * U[1:] * fri
+      act[a:a + dim] = False
+      if hcones is not None:
+        Hc = np.zeros((dim, dim))
+        Hc[0, 0] = 1.0
+        Hc[0, 1:] = Hc[1:, 0] = -mu * U[1:] / T
+        Hc[1:, 1:] = mu * N / T ** 3 * np.outer(U[1:], U[1:]) + (mu * mu - mu * N / T) * np.eye(dim - 1)
+        hcones.append((a, dim, Dm * Hc * np.outer(sc, sc)))
   for i in range(nf):
     f, rf = floss[i], R[i] * floss[i]
     if jar[i] <= -rf:
@@ -993,10 +1051,29 @@ def _row_update(jar, D, R, floss, nf):
   return cost, force, act
 
 
-def _ls_eval(alpha, quad_gauss, jar, jv, D, R=None, floss=None, nf=0):
+def _ls_eval(alpha, quad_gauss, jar, jv, D, R=None, floss=None, nf=0, cones=()):
   x = jar + alpha * jv
   act = x < 0
   act[:nf] = False
+  ec = np.zeros(3)   # elliptic contacts add cost / first / second derivative at alpha directly (mj PrimalEval)
+  for a, dim, mu, fri in cones:
+    act[a:a + dim] = False
+    sc = np.concatenate(([mu], fri))
+    U, V = jar[a:a + dim] * sc, jv[a:a + dim] * sc
+    UU, UV, VV = np.dot(U[1:], U[1:]), np.dot(U[1:], V[1:]), np.dot(V[1:], V[1:])
+    N = U[0] + alpha * V[0]
+    Tsq = UU + alpha * (2 * UV + alpha * VV)
+    T = math.sqrt(Tsq) if Tsq > 0 else 0.0
+    zone = _cone_zone(N, T, mu)
+    if zone == 1:
+      Da, xa, va = D[a:a + dim], x[a:a + dim], jv[a:a + dim]
+      ec += (0.5 * np.sum(Da * xa * xa), np.sum(Da * xa * va), np.sum(Da * va * va))
+    elif zone == 2:
+      Dm = D[a] / (mu * mu * (1 + mu * mu))
+      N1, T1 = V[0], (UV + alpha * VV) / T
+      T2 = VV / T - (UV + alpha * VV) ** 2 / T ** 3
+      NmT = N - mu * T
+      ec += (0.5 * Dm * NmT * NmT, Dm * NmT * (N1 - mu * T1), Dm * ((N1 - mu * T1) ** 2 - NmT * mu * T2))
   q0 = quad_gauss[0] + 0.5 * np.sum(D[act] * jar[act] ** 2)
   q1 = quad_gauss[1] + np.sum(D[act] * jar[act] * jv[act])
   q2 = quad_gauss[2] + 0.5 * np.sum(D[act] * jv[act] ** 2)
@@ -1014,9 +1091,9 @@ def _ls_eval(alpha, quad_gauss, jar, jv, D, R=None, floss=None, nf=0):
       q1 += f * jv[i]
   p = _Pnt()
   p.alpha = alpha
-  p.cost = alpha * alpha * q2 + alpha * q1 + q0
-  p.d1 = 2 * alpha * q2 + q1
-  p.d2 = 2 * q2
+  p.cost = alpha * alpha * q2 + alpha * q1 + q0 + ec[0]
+  p.d1 = 2 * alpha * q2 + q1 + ec[1]
+  p.d2 = 2 * q2 + ec[2]
   if p.d2 <= 0:
     p.d2 = MINVAL
   return p
@@ -1035,9 +1112,9 @@ def _linesearch(m, d, st, search, tolerance, ls_tolerance, ls_iterations, scale)
 
   def ev(a):
     nev[0] += 1
-    return _ls_eval(a, quad_gauss, st["jar"], jv, d.efc_D, d.efc_R, d.efc_frictionloss, d.nf)
+    return _ls_eval(a, quad_gauss, st["jar"], jv, d.efc_D, d.efc_R, d.efc_frictionloss, d.nf, d.efc_cones)
 
-  p0 = _ls_eval(0.0, quad_gauss, st["jar"], jv, d.efc_D, d.efc_R, d.efc_frictionloss, d.nf)
+  p0 = _ls_eval(0.0, quad_gauss, st["jar"], jv, d.efc_D, d.efc_R, d.efc_frictionloss, d.nf, d.efc_cones)
   p1 = ev(p0.alpha - p0.d1 / p0.d2)
   if p0.cost < p1.cost:
     p1 = p0
@@ -1101,11 +1178,12 @@ def solve(m, d):
   scale = 1.0 / (m.stat_meaninertia * max(1, nv))
 
   R, floss, nf = d.efc_R, d.efc_frictionloss, d.nf
+  cones = getattr(d, "efc_cones", ())
 
   def cost_of(qacc):
     jar = J @ qacc - aref
     Ma = M @ qacc
-    return np.sum(_row_update(jar, D, R, floss, nf)[0]) + 0.5 * np.dot(Ma - d.qfrc_smooth, qacc - d.qacc_smooth)
+    return np.sum(_row_update(jar, D, R, floss, nf, cones)[0]) + 0.5 * np.dot(Ma - d.qfrc_smooth, qacc - d.qacc_smooth)
 
   # warm start: keep qacc_warmstart unless the unconstrained acceleration is cheaper
   qacc = d.qacc_warmstart.copy()
@@ -1115,7 +1193,8 @@ def solve(m, d):
 
   def update(st, qacc):
     jar = st["jar"]
-    rowcost, force, act = _row_update(jar, D, R, floss, nf)
+    hcones = []
+    rowcost, force, act = _row_update(jar, D, R, floss, nf, cones, hcones)
     st["active"], st["force"] = act, force
     st["gauss"] = 0.5 * np.dot(st["Ma"] - d.qfrc_smooth, qacc - d.qacc_smooth)
     st["cost"] = np.sum(rowcost) + st["gauss"]
@@ -1125,6 +1204,8 @@ def solve(m, d):
       st["Mgrad"] = np.linalg.solve(M, st["grad"])      # CG: the mass matrix is the preconditioner (mj_solCG)
     else:
       H = M + (J[act].T * D[act]) @ J[act]
+      for a, dim, Hc in hcones:   # cone Hessians of the contacts on their cone's surface (mj HessianCone)
+        H = H + J[a:a + dim].T @ Hc @ J[a:a + dim]
       st["Mgrad"] = np.linalg.solve(H, st["grad"])
 
   cg = int(getattr(m, "opt_solver", SOL_NEWTON)) == SOL_CG
@@ -1207,6 +1288,9 @@ def contact_force(m, d, c):
   a = c.efc_address
   if c.dim == 1:
     out[0] = d.efc_force[a]
+    return out
+  if int(getattr(m, "opt_cone", 0)) == 1:   # elliptic: the rows are the contact-frame axes
+    out[: min(c.dim, 3)] = d.efc_force[a:a + min(c.dim, 3)]
     return out
   for k in range(1, c.dim):
     f1, f2 = d.efc_force[a + 2 * (k - 1)], d.efc_force[a + 2 * (k - 1) + 1]
