@@ -239,13 +239,21 @@ def _scatter(ds, d):
     x.sensordata[:] = d.sensordata[w]
 
 
-@pytest.mark.parametrize("robot,mode,generic", [("go1", "reference", False), ("g1", "masked", False), ("go1", "reference", True)])
+@pytest.mark.parametrize("robot,mode,generic", [("go1", "reference", False), ("g1", "masked", False), ("go1", "reference", True),
+                                                ("go1", "elliptic", False)])
 def test_env_step_closed_loop_matches_oracle(robot, mode, generic):
   """env.step() for a few env steps (graph replay, resets included) against oracle physics + oracle env.  `generic`: with the
-  generic reward / termination library (envs/mdp/rewards.py, terminations.py) switched on next to the task's own terms."""
+  generic reward / termination library (envs/mdp/rewards.py, terminations.py) switched on next to the task's own terms.
+  "elliptic": the reference forward mode on the elliptic friction cone (`MujocoCfg.cone`)."""
   B, T = 4, 5
-  env = make_env(robot, B, seed=7, forward_mode=mode)
+  kw = {}
+  if mode == "elliptic":
+    from mjlab_b200.sim import MujocoCfg, SimulationCfg
+    mode = "reference"
+    kw["sim"] = SimulationCfg(nconmax=35, njmax=300, mujoco=MujocoCfg(timestep=0.005, iterations=10, ls_iterations=20, cone="elliptic"))
+  env = make_env(robot, B, seed=7, forward_mode=mode, **kw)
   m, cfg = env.sim.mj_model, env.vcfg
+  assert m.opt_cone == (1 if kw else 0)
   cfg.max_episode_length = 3
   if generic:
     cfg.reward_weights[14:] = GENERIC_WEIGHTS
