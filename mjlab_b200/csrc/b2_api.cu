@@ -310,7 +310,7 @@ static int make_plan(const b2_model* m, const b2_data* d, Plan* p) {
   // whenever their actual demand fits (the common case: demand is an order of magnitude below the bound)
   const SolveCaps caps = solve_caps(m->nlimited, m->nfriction, d->nconmax, d->njmax, m->maxchain);
   const int rows_max = caps.rows, runs_max = caps.runs, pool_max = caps.pool, dofs_max = caps.dofs;
-  int arena = solve_arena_need(rows_max, runs_max, dofs_max, pool_max, d->nconmax > 0 ? d->nconmax : 1);
+  int arena = solve_arena_need(rows_max, runs_max, dofs_max, pool_max, d->nconmax > 0 ? d->nconmax : 1, m->cone);
   // The strict bound assumes every contact couples the two longest kinematic chains (maxchain); real worlds stay an
   // order of magnitude below it (G1, random actions: median 30 rows, max 116 of 198).  Cap the arena so that
   // B2_SOLVE_MINB CTAs stay resident per SM, but never below half the strict bound.  A world beyond the cap loses rows
@@ -325,7 +325,7 @@ static int make_plan(const b2_model* m, const b2_data* d, Plan* p) {
   arena = env_int("B200SIM_ARENA", arena);  // experiments
   {
     // whatever the cap, a world reduced to one row and no Jacobian pool must fit (solve_world shrinks towards that)
-    int floor_ = solve_arena_need(1, runs_max, dofs_max, 0, d->nconmax > 0 ? d->nconmax : 1) + 64;
+    int floor_ = solve_arena_need(1, runs_max, dofs_max, 0, d->nconmax > 0 ? d->nconmax : 1, m->cone) + 64;
     if (arena < floor_) arena = floor_;
   }
   arena = (arena + 3) & ~3;   // the two-ended allocator of k_solve works in units of 4 floats

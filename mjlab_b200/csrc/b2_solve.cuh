@@ -26,15 +26,15 @@ struct SolveSmem {
 
 // Row storage is carved from an arena per CTA by actual demand (median world: ~30 rows; worst case: ~200), so the
 // resident warps per SM are set by what worlds typically need, not by the worst case.  Arena demand in reals:
-//   D, frc/aref, jar, jv/wgt, rowinfo [rows each] | runinfo [2 runs] | rundofs [dofs bytes] | cinfo [4 ncon] | jpool [pool]
+//   D, frc/aref, jar, jv/wgt, rowinfo [rows each] | runinfo [2 runs] | rundofs [dofs bytes] | cinfo [4 ncon] | (elliptic cone: cpar [12 ncon]) | jpool [pool]
 static inline
 #ifndef B2_HOSTEMU
 __host__ __device__
 #endif
-int solve_arena_need(int rows, int runs, int dofs, int pool, int ncon) {
+int solve_arena_need(int rows, int runs, int dofs, int pool, int ncon, int cone = 0) {
   auto r4 = [](int n) { return (n + 3) & ~3; };
   int cd = r4(2 * r4(rows));
-  return cd + 3 * r4(rows) + r4(2 * runs) + r4((dofs + 3) / 4) + r4(4 * ncon) + r4(pool);
+  return cd + 3 * r4(rows) + r4(2 * runs) + r4((dofs + 3) / 4) + r4(4 * ncon) + (cone ? r4(12 * ncon) : 0) + r4(pool);
 }
 
 // True upper bounds on the rows / runs / dof-list entries / Jacobian pool of ONE world (the arena of a CTA holds one such world).
@@ -173,13 +173,18 @@ B2_DEV void fric_quad(real x, real ja, real v, real D, real f, real& q0, real& q
 }
 
 // ---- elliptic friction cones (opt.cone = mjCONE_ELLIPTIC; mj_constraintUpdate / PrimalEval / HessianCone restated) ----------
-// A contact with dim > 1 owns `dim` rows along its frame axes (normal, tangents).  Its rows carry NEGATED D in the solver's D
-// array: that marks them for the per-row passes (which skip them) and the per-contact passes below recover D_j = -D[adr + j].
-// With U = (mu x_n, f_j x_tj), N = U_0 and T = |U_1..|: N >= mu T satisfied (no cost); mu N + T <= 0 fully violated (every row
-// quadratic, weight D_j); else the residual is outside both cones and pays 0.5 Dm (N - mu T)^2, Dm = D_n / (mu^2 (1 + mu^2)).
+// A frictional contact (condim 3) owns three rows along its frame axes (normal, two tangents).  Its rows carry NEGATED D in the
+// solver's D array: that marks them for the per-row passes (which skip them); the per-contact passes below recover D_j = -D[adr + j].
+// With U = (mu x_n, f_1 x_t1, f_2 x_t2), N = U_0 and T = |U_1, U_2|: N >= mu T satisfied (no cost); mu N + T <= 0 fully violated
+// (every row quadratic, weight D_j: the sticking contact); else the residual lies between the two cones and pays
+// 0.5 Dm (N - mu T)^2, Dm = D_n / (mu^2 (1 + mu^2)): the sliding contact, force on the cone's surface.
+// Per contact the solver keeps B2_CPAR reals (arena): [mu, Dm, f1, f2 | a0, a1, a2, b1, b2, Dm kd | -, -]; the second group is
+// the cone Hessian of a sliding contact as two weighted rank-one terms, Hc = Dm a a^T + Dm kd b b^T with
+// a = (mu, -mu f1 n1, -mu f2 n2), b = (0, -f1 n2, f2 n1), n = (U_1, U_2) / T, kd = mu^2 - mu N / T.
 // All of this sits behind the template parameter EL: pyramidal models run instantiations that carry none of it.
+#define B2_CPAR 12
 struct ConeNone {};
-struct ConeArgs { int* cinfo; const real* fri; int ncon; };   // cinfo: 4 ints per contact (row address | -1, dim | zone << 8, body1, body2); fri: 5 per contact
+struct ConeArgs { int* cinfo; real* cpar; int ncon; };   // cinfo: 4 ints per contact (row address | -1, dim | zone << 8, body1, body2)
 template <bool EL> struct ConeSel { typedef ConeNone type; };
 template <> struct ConeSel<true> { typedef ConeArgs type; };
 
@@ -188,71 +193,77 @@ B2_DEV int cone_zone(real N, real T, real mu) {
   if (mu * N + T <= 0 || (T <= 0 && N < 0)) return 1;
   return 2;
 }
-// cost and its first / second derivative along jar + alpha jv, summed over this lane's cone contacts (lanes over contacts)
-B2_DEV void cone_ls(const ConeArgs& ca, real alpha, const real* jar, const real* jv, const real* D, real& e0, real& e1, real& e2) {
-  B2_UNROLL1
-  for (int c = B2_LANE; c < ca.ncon; c += B2_NLANE) {
-    const int adr = ca.cinfo[4 * c], dim = ca.cinfo[4 * c + 1] & 0xff;
-    if (adr < 0 || dim < 2) continue;
-    const real* fr = ca.fri + 5 * c;
-    const real D0 = -D[adr];
-    const real mu = fr[0] * sqrt(D0 / -D[adr + 1]);
-    const real U0 = jar[adr] * mu, V0 = jv[adr] * mu;
-    real UU = 0, UV = 0, VV = 0;
-    for (int j = 1; j < dim; ++j) {
-      const real u = jar[adr + j] * fr[j - 1], v = jv[adr + j] * fr[j - 1];
-      UU += u * u; UV += u * v; VV += v * v;
-    }
-    const real N = U0 + alpha * V0;
-    const real Tsq = UU + alpha * (2 * UV + alpha * VV);
-    const real T = Tsq > 0 ? sqrt(Tsq) : (real)0;
-    const int zone = cone_zone(N, T, mu);
-    if (zone == 1) {
-      for (int j = 0; j < dim; ++j) {
-        const real Dj = -D[adr + j], v = jv[adr + j], x = jar[adr + j] + alpha * v;
-        e0 += (real)0.5 * Dj * x * x; e1 += Dj * x * v; e2 += Dj * v * v;
-      }
-    } else if (zone == 2) {
-      const real Dm = D0 / (mu * mu * (1 + mu * mu));
-      const real t = UV + alpha * VV;
-      const real N1 = V0, T1 = t / T, T2 = VV / T - t * t / (T * T * T);
-      const real NmT = N - mu * T, s1 = N1 - mu * T1;
-      e0 += (real)0.5 * Dm * NmT * NmT; e1 += Dm * NmT * s1; e2 += Dm * (s1 * s1 - NmT * mu * T2);
-    }
+// One contact's residual ray jar + alpha jv in cone coordinates, set up once per line-search pass
+struct ConeRay { real mu, Dm, U0, V0, UU, UV, VV, z0, z1, z2; };
+B2_DEV bool cone_ray(const ConeArgs& ca, int c, const real* jar, const real* jv, const real* D, ConeRay& r) {
+  const int adr = ca.cinfo[4 * c];
+  if (adr < 0 || (ca.cinfo[4 * c + 1] & 0xff) < 2) return false;
+  const real* cp = ca.cpar + B2_CPAR * c;
+  r.mu = cp[0]; r.Dm = cp[1];
+  const real x0 = jar[adr], x1 = jar[adr + 1], x2 = jar[adr + 2], v0 = jv[adr], v1 = jv[adr + 1], v2 = jv[adr + 2];
+  const real u1 = x1 * cp[2], u2 = x2 * cp[3], w1 = v1 * cp[2], w2 = v2 * cp[3];
+  r.U0 = x0 * r.mu; r.V0 = v0 * r.mu;
+  r.UU = u1 * u1 + u2 * u2; r.UV = u1 * w1 + u2 * w2; r.VV = w1 * w1 + w2 * w2;
+  const real D0 = -D[adr], D1 = -D[adr + 1], D2 = -D[adr + 2];   // the fully violated zone is an ordinary quadratic in alpha
+  r.z0 = (real)0.5 * (D0 * x0 * x0 + D1 * x1 * x1 + D2 * x2 * x2);
+  r.z1 = D0 * x0 * v0 + D1 * x1 * v1 + D2 * x2 * v2;
+  r.z2 = (real)0.5 * (D0 * v0 * v0 + D1 * v1 * v1 + D2 * v2 * v2);
+  return true;
+}
+// its contribution at alpha: a sticking contact adds to the pass's quadratic sums like any active row; a sliding one adds its
+// own cost / slope / curvature (e0, e1, e2), which are summed apart - folding them into the quadratic's coefficients would
+// cancel alpha e2 against itself in the slope, and e2 grows like 1 / T near the cone's axis (measured: 1e-3 force error in float32)
+B2_DEV void cone_at(const ConeRay& r, real alpha, real& q0, real& q1, real& q2, real& e0, real& e1, real& e2) {
+  const real N = r.U0 + alpha * r.V0;
+  const real Tsq = r.UU + alpha * (2 * r.UV + alpha * r.VV);
+  const real T = Tsq > 0 ? sqrt(Tsq) : (real)0;
+  const int zone = cone_zone(N, T, r.mu);
+  if (zone == 1) { q0 += r.z0; q1 += r.z1; q2 += r.z2; }
+  else if (zone == 2) {
+    const real rT = (real)1 / T;
+    const real T1 = (r.UV + alpha * r.VV) * rT, T2 = (r.VV - T1 * T1) * rT;
+    const real NmT = N - r.mu * T, s1 = r.V0 - r.mu * T1;
+    e0 += (real)0.5 * r.Dm * NmT * NmT; e1 += r.Dm * NmT * s1; e2 += r.Dm * (s1 * s1 - NmT * r.mu * T2);
   }
 }
-// constraint update of the cone contacts at the current residual: returns this lane's share of the cost; with WRITE also the
-// rows' forces / Hessian weights (zone 1) and the zone, stored in cinfo[4 c + 1] >> 8 for the Hessian pass
-template <bool WRITE>
-B2_DEV real cone_update(const ConeArgs& ca, const real* jar, const real* D, real* wgt, real* frc) {
+// constraint update of the cone contacts at the current residual: returns this lane's share of the cost; with `write` also the
+// rows' forces / Hessian weights (sticking), the zone (cinfo[4 c + 1] >> 8) and the sliding contacts' Hessian terms (cpar[4..9]).
+// `changed` is set when a contact's zone differs from the last update's or the contact slides (its Hessian then moves with the
+// residual): the factor of the previous Newton iteration cannot be reused.
+B2_DEVN real cone_update(ConeArgs ca, const real* jar, const real* D, real* wgt, real* frc, bool write, bool& changed) {
   real cost = 0;
   B2_UNROLL1
   for (int c = B2_LANE; c < ca.ncon; c += B2_NLANE) {
-    const int adr = ca.cinfo[4 * c], dim = ca.cinfo[4 * c + 1] & 0xff;
-    if (adr < 0 || dim < 2) continue;
-    const real* fr = ca.fri + 5 * c;
-    const real D0 = -D[adr];
-    const real mu = fr[0] * sqrt(D0 / -D[adr + 1]);
-    const real N = jar[adr] * mu;
-    real U[3] = {N, 0, 0}, TT = 0;
-    for (int j = 1; j < dim; ++j) { U[j] = jar[adr + j] * fr[j - 1]; TT += U[j] * U[j]; }
+    const int adr = ca.cinfo[4 * c], dz = ca.cinfo[4 * c + 1];
+    if (adr < 0 || (dz & 0xff) < 2) continue;
+    real* cp = ca.cpar + B2_CPAR * c;
+    const real mu = cp[0], Dm = cp[1], f1 = cp[2], f2 = cp[3];
+    const real x0 = jar[adr], x1 = jar[adr + 1], x2 = jar[adr + 2];
+    const real N = x0 * mu, U1 = x1 * f1, U2 = x2 * f2;
+    const real TT = U1 * U1 + U2 * U2;
     const real T = TT > 0 ? sqrt(TT) : (real)0;
     const int zone = cone_zone(N, T, mu);
-    if (WRITE) ca.cinfo[4 * c + 1] = dim | (zone << 8);
+    if (write) {
+      ca.cinfo[4 * c + 1] = (dz & 0xff) | (zone << 8);
+      if (zone != (dz >> 8) || zone == 2) changed = true;
+    }
     if (zone == 1) {
-      for (int j = 0; j < dim; ++j) {
-        const real Dj = -D[adr + j], x = jar[adr + j];
-        cost += (real)0.5 * Dj * x * x;
-        if (WRITE) { wgt[adr + j] = Dj; frc[adr + j] = -Dj * x; }
+      const real D0 = -D[adr], D1 = -D[adr + 1], D2 = -D[adr + 2];
+      cost += (real)0.5 * (D0 * x0 * x0 + D1 * x1 * x1 + D2 * x2 * x2);
+      if (write) {
+        wgt[adr] = D0; wgt[adr + 1] = D1; wgt[adr + 2] = D2;
+        frc[adr] = -D0 * x0; frc[adr + 1] = -D1 * x1; frc[adr + 2] = -D2 * x2;
       }
     } else if (zone == 2) {
-      const real Dm = D0 / (mu * mu * (1 + mu * mu));
       const real NmT = N - mu * T;
       cost += (real)0.5 * Dm * NmT * NmT;
-      if (WRITE) {
-        const real f0 = -Dm * NmT * mu;
-        frc[adr] = f0;
-        for (int j = 1; j < dim; ++j) frc[adr + j] = -f0 / T * U[j] * fr[j - 1];
+      if (write) {
+        const real rT = (real)1 / T;
+        const real n1 = U1 * rT, n2 = U2 * rT;
+        const real fn = -Dm * NmT * mu;
+        frc[adr] = fn; frc[adr + 1] = -fn * n1 * f1; frc[adr + 2] = -fn * n2 * f2;
+        cp[4] = mu; cp[5] = -mu * f1 * n1; cp[6] = -mu * f2 * n2;
+        cp[7] = -f1 * n2; cp[8] = f2 * n1; cp[9] = Dm * (mu * mu - mu * N * rT);
       }
     }
   }
@@ -268,7 +279,7 @@ B2_DEVN LsPnt ls_eval(real alpha, real q0g, real q1g, real q2g, const real* jar,
   B2_UNROLL1   // (unrolling by 2 / 4 to overlap the passes' loads was measured: +2 % kernel time, code size again)
   for (int r = B2_LANE; r < nefc; r += B2_NLANE) {
     real x = jar[r] + alpha * jv[r];
-    if (EL && D[r] < 0) continue;   // cone rows: cone_ls below
+    if (EL && D[r] < 0) continue;   // cone rows: per contact below
     if (FR && r < nf) {
       fric_quad(x, jar[r], jv[r], D[r], floss[r], q0, q1, q2);
     } else if (x < 0) {
@@ -278,6 +289,15 @@ B2_DEVN LsPnt ls_eval(real alpha, real q0g, real q1g, real q2g, const real* jar,
       q2 += (real)0.5 * D[r] * jv[r] * jv[r];
     }
   }
+  real e0 = 0, e1 = 0, e2 = 0;
+  if constexpr (EL) {
+    B2_UNROLL1
+    for (int c = B2_LANE; c < ca.ncon; c += B2_NLANE) {
+      ConeRay cr;
+      if (cone_ray(ca, c, jar, jv, D, cr)) cone_at(cr, alpha, q0, q1, q2, e0, e1, e2);
+    }
+    b2_wsum3(e0, e1, e2);
+  }
   b2_wsum3(q0, q1, q2);
   q0 += q0g; q1 += q1g; q2 += q2g;
   LsPnt p;
@@ -285,12 +305,7 @@ B2_DEVN LsPnt ls_eval(real alpha, real q0g, real q1g, real q2g, const real* jar,
   p.cost = alpha * alpha * q2 + alpha * q1 + q0;
   p.d1 = 2 * alpha * q2 + q1;
   p.d2 = 2 * q2;
-  if constexpr (EL) {
-    real e0 = 0, e1 = 0, e2 = 0;
-    cone_ls(ca, alpha, jar, jv, D, e0, e1, e2);
-    b2_wsum3(e0, e1, e2);
-    p.cost += e0; p.d1 += e1; p.d2 += e2;
-  }
+  if constexpr (EL) { p.cost += e0; p.d1 += e1; p.d2 += e2; }
   if (p.d2 <= 0) p.d2 = B2_MINVAL;
   return p;
 }
@@ -322,6 +337,20 @@ B2_DEVN void ls_eval3(const real* alpha, LsPnt* out, real q0g, real q1g, real q2
     if (ja + al1 * v < 0) { b0 += t0; b1 += t1; b2 += t2; }
     if (ja + al2 * v < 0) { c0 += t0; c1 += t1; c2 += t2; }
   }
+  real ea[3] = {0, 0, 0}, eb[3] = {0, 0, 0}, ec[3] = {0, 0, 0};   // sliding contacts: cost / slope / curvature at the three points
+  if constexpr (EL) {
+    B2_UNROLL1
+    for (int c = B2_LANE; c < ca.ncon; c += B2_NLANE) {
+      ConeRay cr;
+      if (!cone_ray(ca, c, jar, jv, D, cr)) continue;
+      cone_at(cr, al0, a0, a1, a2, ea[0], ea[1], ea[2]);
+      cone_at(cr, al1, b0, b1, b2, eb[0], eb[1], eb[2]);
+      cone_at(cr, al2, c0, c1, c2, ec[0], ec[1], ec[2]);
+    }
+    b2_wsum3(ea[0], ea[1], ea[2]);
+    b2_wsum3(eb[0], eb[1], eb[2]);
+    b2_wsum3(ec[0], ec[1], ec[2]);
+  }
   b2_wsum3(a0, a1, a2);
   b2_wsum3(b0, b1, b2);
   b2_wsum3(c0, c1, c2);
@@ -334,10 +363,8 @@ B2_DEVN void ls_eval3(const real* alpha, LsPnt* out, real q0g, real q1g, real q2
     p.d1 = 2 * al * q2[k] + q1[k];
     p.d2 = 2 * q2[k];
     if constexpr (EL) {
-      real e0 = 0, e1 = 0, e2 = 0;
-      cone_ls(ca, al, jar, jv, D, e0, e1, e2);
-      b2_wsum3(e0, e1, e2);
-      p.cost += e0; p.d1 += e1; p.d2 += e2;
+      const real* e = k == 0 ? ea : (k == 1 ? eb : ec);
+      p.cost += e[0]; p.d1 += e[1]; p.d2 += e[2];
     }
     if (p.d2 <= 0) p.d2 = B2_MINVAL;
     out[k] = p;
@@ -615,7 +642,7 @@ B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, i
     jpool_cap = nlim + cpool;
     if (jpool_cap > 65535) jpool_cap = 65535;
   }
-  int need = solve_arena_need(rows_cap, runs_cap, dofs_cap, jpool_cap, ncon > 0 ? ncon : 1);
+  int need = solve_arena_need(rows_cap, runs_cap, dofs_cap, jpool_cap, ncon > 0 ? ncon : 1, EL);
   // A world beyond the arena (the arena may be capped below the strict worst case, see make_plan) shrinks its Jacobian pool
   // first, then its row capacity: rows that do not fit are dropped from the tail and counted in nefc_dropped, as with njmax.
   // The loop ends with need <= arena_cap (make_plan guarantees that a one-row world fits), which the allocator below
@@ -626,7 +653,7 @@ B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, i
     if (jpool_cap > 0) jpool_cap = jpool_cap > over ? jpool_cap - over : 0;
     else if (rows_cap > 1) rows_cap = rows_cap > 8 ? rows_cap - 8 : 1;
     else break;
-    need = solve_arena_need(rows_cap, runs_cap, dofs_cap, jpool_cap, ncon > 0 ? ncon : 1);
+    need = solve_arena_need(rows_cap, runs_cap, dofs_cap, jpool_cap, ncon > 0 ? ncon : 1, EL);
   }
   if (need > L.arena_cap) need = L.arena_cap;
   int aoff = 0;
@@ -657,7 +684,7 @@ B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, i
     aoff = me ? (cap4 - need4) * 4 : 0;
   }
 #endif
-  real* D; real* aref; real* jar; real* jv; int* rowinfo; int* runinfo; unsigned char* rundofs; int* cinfo; real* jpool;
+  real* D; real* aref; real* jar; real* jv; int* rowinfo; int* runinfo; unsigned char* rundofs; int* cinfo; real* jpool; real* cpar = nullptr;
   {
     real* a = arena + aoff;
     const int r4 = (rows_cap + 3) & ~3;
@@ -666,6 +693,7 @@ B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, i
     runinfo = (int*)a; a += (2 * runs_cap + 3) & ~3;
     rundofs = (unsigned char*)a; a += ((dofs_cap + 3) / 4 + 3) & ~3;
     cinfo = (int*)a; a += (4 * (ncon > 0 ? ncon : 1) + 3) & ~3;
+    if (EL) { cpar = a; a += (B2_CPAR * (ncon > 0 ? ncon : 1) + 3) & ~3; }
     jpool = a;
   }
   real* wgt = jv;          // D*active per row; consumed by the Hessian pass before the line search reuses jv
@@ -971,6 +999,12 @@ B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, i
           const real ar = -b * jar[r] - k * imp * pos;
           D[r] = -Dr; aref[r] = ar;
           g_efcD[r] = Dr; g_aref[r] = ar;
+          if (j == 0) {   // the contact's constants for the per-contact passes: mu = mu_1 sqrt(R_t1 / R_n), Dm, mu_1, mu_2
+            const real f0 = c_fri[5 * c];
+            const real mu = f0 * sqrt((R / fmax(impratio, B2_MINVAL)) / R);
+            real* cp = cpar + B2_CPAR * c;
+            cp[0] = mu; cp[1] = Dr / (mu * mu * (1 + mu * mu)); cp[2] = f0; cp[3] = c_fri[5 * c + 1];
+          }
           continue;
         }
       }
@@ -984,7 +1018,8 @@ B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, i
   }
 
   typename ConeSel<EL>::type ca;
-  if constexpr (EL) { ca.cinfo = cinfo; ca.fri = c_fri; ca.ncon = ncon; }
+  if constexpr (EL) { ca.cinfo = cinfo; ca.cpar = cpar; ca.ncon = ncon; }
+  bool cone_changed = false;
   // ---- solve ------------------------------------------------------------------------------------------  // @region solve_init
   B2_PH(0)
   int niter = 0;
@@ -1010,7 +1045,7 @@ B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, i
       if (FR && r < nf) { real f_, w_; cs += fric_row(x, D[r], floss[r], f_, w_); }
       else if (x < 0) cs += (real)0.5 * D[r] * x * x;
     }
-    if constexpr (EL) cs += cone_update<false>(ca, jar, D, nullptr, nullptr);
+    if constexpr (EL) cs += cone_update(ca, jar, D, nullptr, nullptr, false, cone_changed);
     cs = b2_wsum(cs);
     // cost at the warm start
     B2_UNROLL1
@@ -1025,7 +1060,7 @@ B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, i
       if (FR && r < nf) { real f_, w_; cw += fric_row(x, D[r], floss[r], f_, w_); }
       else if (x < 0) cw += (real)0.5 * D[r] * x * x;
     }
-    if constexpr (EL) cw += cone_update<false>(ca, jar, D, nullptr, nullptr);
+    if constexpr (EL) cw += cone_update(ca, jar, D, nullptr, nullptr, false, cone_changed);
     real gw = 0;
     symv_global(M, nv, ld, qacc, Ma);
     B2_UNROLL1
@@ -1049,7 +1084,7 @@ B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, i
       // The Hessian M + J^T diag(D*active) J only depends on WHICH rows are active: when the active set equals the one
       // of the last factorisation, the factor still in H is reused (same result, no copy / J^T D J / Cholesky).
       real c1 = 0;
-      bool same_set = !EL && it > 0;   // a cone Hessian changes with the residual itself, not only with the active set
+      bool same_set = it > 0;
 #ifdef B2_HOSTEMU
       int nflip_stat = 0;
 #endif
@@ -1089,8 +1124,12 @@ B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, i
 #endif
       }
       if constexpr (EL) {
+        // cone contacts: sticking ones are quadratic rows like any other (Hessian fixed by the zone); a sliding contact's Hessian
+        // moves with the residual, so the factor is only reused when no contact slides and no zone changed
         B2_WSYNC();
-        c1 += cone_update<true>(ca, jar, D, wgt, frc);
+        cone_changed = false;
+        c1 += cone_update(ca, jar, D, wgt, frc, true, cone_changed);
+        if (b2_ballot(cone_changed) != 0) same_set = false;
       }
       real g1 = 0;
       B2_UNROLL1
@@ -1228,30 +1267,14 @@ B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, i
         B2_WSYNC();
       }
       if constexpr (EL) {
-        // cone Hessians (mj HessianCone): a contact on its cone's surface adds J_c^T Hc J_c, Hc the dim x dim second derivative
-        // of 0.5 Dm (N - mu T)^2 in the contact's residual; same dof pairs as the run the contact belongs to
+        // cone Hessians (mj HessianCone): a sliding contact adds J_c^T Hc J_c with Hc = Dm a a^T + Dm kd b b^T (cone_update left
+        // a, b and the weights in cpar), i.e. two weighted combinations of the contact's three rows; same dof pairs as its run
         B2_UNROLL1
         for (int c = 0; c < ncon; ++c) {
-          const int adr = cinfo[4 * c], dz = cinfo[4 * c + 1];
-          if (adr < 0 || (dz >> 8) != 2) continue;
-          const int dim = dz & 0xff;
-          const real* fr = c_fri + 5 * c;
-          const real D0 = -D[adr];
-          const real mu = fr[0] * sqrt(D0 / -D[adr + 1]);
-          const real N = jar[adr] * mu;
-          real U[3] = {N, 0, 0}, sc[3] = {mu, 0, 0}, TT = 0;
-          for (int j = 1; j < dim; ++j) { sc[j] = fr[j - 1]; U[j] = jar[adr + j] * sc[j]; TT += U[j] * U[j]; }
-          const real T = sqrt(TT);
-          const real Dm = D0 / (mu * mu * (1 + mu * mu));
-          real Hc[3][3];
-          Hc[0][0] = 1;
-          const real k3 = mu * N / (T * T * T), kd = mu * mu - mu * N / T;
-          for (int i = 1; i < dim; ++i) {
-            Hc[0][i] = Hc[i][0] = -mu * U[i] / T;
-            for (int j = 1; j < dim; ++j) Hc[i][j] = k3 * U[i] * U[j] + (i == j ? kd : (real)0);
-          }
-          for (int i = 0; i < dim; ++i)
-            for (int j = 0; j < dim; ++j) Hc[i][j] *= Dm * sc[i] * sc[j];
+          const int adr = cinfo[4 * c];
+          if (adr < 0 || (cinfo[4 * c + 1] >> 8) != 2) continue;
+          const real* cp = cpar + B2_CPAR * c;
+          const real a0 = cp[4], a1 = cp[5], a2 = cp[6], b1 = cp[7], b2 = cp[8], wa = cp[1], wb = cp[9];
           const int info = rowinfo[adr];
           const int off0 = info & 0xffff, run = info >> 16;
           const int ri0 = runinfo[2 * run];
@@ -1262,14 +1285,11 @@ B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, i
           B2_UNROLL1
           for (int pr = B2_LANE; pr < npair; pr += B2_NLANE) {
             const int ab = pairtab[pr];
-            const int a = ab >> 8, b = ab & 0xff;
-            real acc = 0;
-            for (int i = 0; i < dim; ++i) {
-              real t = 0;
-              for (int j = 0; j < dim; ++j) t = fma(Hc[i][j], jpool[off0 + j * wpad + b], t);
-              acc = fma(jpool[off0 + i * wpad + a], t, acc);
-            }
-            H[dl[a] * ld + dl[b]] += acc;
+            const real* ja = jpool + off0 + (ab >> 8);
+            const real* jb = jpool + off0 + (ab & 0xff);
+            const real pa = a0 * ja[0] + a1 * ja[wpad] + a2 * ja[2 * wpad], pb = a0 * jb[0] + a1 * jb[wpad] + a2 * jb[2 * wpad];
+            const real ta = b1 * ja[wpad] + b2 * ja[2 * wpad], tb = b1 * jb[wpad] + b2 * jb[2 * wpad];
+            H[dl[ab >> 8] * ld + dl[ab & 0xff]] += wa * pa * pb + wb * ta * tb;
           }
           B2_WSYNC();
         }

@@ -257,6 +257,8 @@ def check_supported(m) -> None:
     t = (int(m.geom_type[g1]), int(m.geom_type[g2]))
     if t not in SUPPORTED_PAIRS:
       raise ValueError(f"collision between geom types {t} ({m.geom_names[g1]}, {m.geom_names[g2]}) is not supported")
+  if np.any(~np.isin(np.asarray(m.geom_condim), (1, 3))):
+    raise ValueError("contact dimensions 4 / 6 (torsional / rolling friction rows) are outside the supported subset: condim must be 1 or 3")
   if m.opt_cone not in (0, 1):
     raise ValueError(f"unknown friction cone {m.opt_cone} (0 pyramidal, 1 elliptic)")
   if m.opt_cone == 1 and np.any(np.asarray(getattr(m, "dof_frictionloss", 0.0)) > 0):

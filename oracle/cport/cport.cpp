@@ -29,7 +29,7 @@ int cport_forward(const KModel* m, KData* d, int nthread) { return cport_run(m, 
 static int cport_run(const KModel* m, KData* d, int nstep, int nthread, int do_integrate) {
   SmoothSmem ls = smooth_smem_layout(m->nq, m->nv, m->nu, m->nbody, m->njnt, 256);
   const SolveCaps caps = solve_caps(m->nlimited, m->nfriction, d->nconmax, d->njmax, m->maxchain);
-  int arena = solve_arena_need(caps.rows, caps.runs, caps.dofs, caps.pool, d->nconmax > 0 ? d->nconmax : 1);
+  int arena = solve_arena_need(caps.rows, caps.runs, caps.dofs, caps.pool, d->nconmax > 0 ? d->nconmax : 1, m->cone);
   SolveSmem lv = solve_smem_layout(m->nv, caps.rows, m->maxchain, arena, 0, m->nfriction);
   PostSmem lp = post_smem_layout(m->nv);
   std::atomic<int> next(0);

@@ -34,7 +34,7 @@ long long b2h_memo_hit_count(void) { return b2h_memo_hits; }
 int b2h_run(const KModel* m, KData* d, int do_integrate, int world_lo, int world_hi) {
   SmoothSmem ls = smooth_smem_layout(m->nq, m->nv, m->nu, m->nbody, m->njnt, 256);
   const SolveCaps caps = solve_caps(m->nlimited, m->nfriction, d->nconmax, d->njmax, m->maxchain);
-  int arena = solve_arena_need(caps.rows, caps.runs, caps.dofs, caps.pool, d->nconmax > 0 ? d->nconmax : 1);
+  int arena = solve_arena_need(caps.rows, caps.runs, caps.dofs, caps.pool, d->nconmax > 0 ? d->nconmax : 1, m->cone);
   if (jpool_budget > 0) arena = jpool_budget;  // tests of the overflow path: an arena smaller than the worst case
   SolveSmem lv = solve_smem_layout(m->nv, caps.rows, m->maxchain, arena, 0, m->nfriction);
   PostSmem lp = post_smem_layout(m->nv);
