@@ -172,13 +172,15 @@ __global__ void __launch_bounds__(B2_WPB * 32, B2_SOLVE_MINB) k_solve_t(const KM
 #define k_solve_cg k_solve_t<true, false>
 #define k_solve_fr k_solve_t<false, true>
 #define k_solve_cg_fr k_solve_t<true, true>
-// elliptic friction cones (opt.cone = 1): Newton and CG; not combined with friction-loss rows (check_sizes refuses the pair)
+// elliptic friction cones (opt.cone = 1): Newton and CG, without / with friction-loss rows
 #define k_solve_el k_solve_t<false, false, true>
 #define k_solve_cg_el k_solve_t<true, false, true>
+#define k_solve_fr_el k_solve_t<false, true, true>
+#define k_solve_cg_fr_el k_solve_t<true, true, true>
 typedef void (*solve_kernel_t)(const KModel, const KData, const SolveSmem, const PostSmem, int, const unsigned char*, const int*, int, int);
 static solve_kernel_t solve_kernel(const KModel& km) {
   const bool cg = km.solver == 1, fr = km.nfriction > 0;
-  if (km.cone == 1) return cg ? (solve_kernel_t)k_solve_cg_el : (solve_kernel_t)k_solve_el;
+  if (km.cone == 1) return fr ? (cg ? (solve_kernel_t)k_solve_cg_fr_el : (solve_kernel_t)k_solve_fr_el) : (cg ? (solve_kernel_t)k_solve_cg_el : (solve_kernel_t)k_solve_el);
   return fr ? (cg ? (solve_kernel_t)k_solve_cg_fr : (solve_kernel_t)k_solve_fr) : (cg ? (solve_kernel_t)k_solve_cg : (solve_kernel_t)k_solve);
 }
 static void launch_solve(int grid, size_t smem, cudaStream_t st, const KModel& km, const KData& kd, const SolveSmem& lv, const PostSmem& lp,
@@ -386,7 +388,6 @@ static int check_sizes(const b2_model* m, const b2_data* d) {
   if (m->nv > 64) return fail("nv=%d exceeds the 64-dof limit of the per-world dof masks", m->nv);
   if (m->nv < 1) return fail("nv must be >= 1");
   if (m->cone != 0 && m->cone != 1) return fail("unknown friction cone %d (0 pyramidal, 1 elliptic)", m->cone);
-  if (m->cone == 1 && m->nfriction > 0) return fail("the elliptic cone is not combined with friction-loss rows (dof_frictionloss > 0) in this build");
   if (m->solver != 2 && m->solver != 1) return fail("supported solvers: Newton, CG (PGS is not implemented)");
   if (m->integrator != B2_INT_EULER && m->integrator != B2_INT_IMPLICITFAST) return fail("unsupported integrator %d", m->integrator);
   if (d->nworld < 1 || d->nconmax < 0 || d->njmax < 1) return fail("bad nworld/nconmax/njmax");

@@ -1361,8 +1361,11 @@ B2_DEV void solve_world_t(const KModel& m, const KData& d, const SolveSmem& L, i
 
 // run-time dispatch for callers that are not templated themselves (the host builds: tests/hostemu, oracle/cport)
 B2_DEV void solve_world(const KModel& m, const KData& d, const SolveSmem& L, int w, real* sm, real* arena, int* actl) {
-  if (m.cone == 1) {   // elliptic cones (not combined with friction-loss rows: b2_check refuses that pair)
-    if (m.solver == 1) solve_world_t<true, false, true>(m, d, L, w, sm, arena, actl);
+  if (m.cone == 1) {   // elliptic cones
+    if (m.nfriction > 0) {
+      if (m.solver == 1) solve_world_t<true, true, true>(m, d, L, w, sm, arena, actl);
+      else solve_world_t<false, true, true>(m, d, L, w, sm, arena, actl);
+    } else if (m.solver == 1) solve_world_t<true, false, true>(m, d, L, w, sm, arena, actl);
     else solve_world_t<false, false, true>(m, d, L, w, sm, arena, actl);
   } else if (m.nfriction > 0) {
     if (m.solver == 1) solve_world_t<true, true>(m, d, L, w, sm, arena, actl);

@@ -261,8 +261,6 @@ def check_supported(m) -> None:
     raise ValueError("contact dimensions 4 / 6 (torsional / rolling friction rows) are outside the supported subset: condim must be 1 or 3")
   if m.opt_cone not in (0, 1):
     raise ValueError(f"unknown friction cone {m.opt_cone} (0 pyramidal, 1 elliptic)")
-  if m.opt_cone == 1 and np.any(np.asarray(getattr(m, "dof_frictionloss", 0.0)) > 0):
-    raise ValueError("the elliptic cone is not combined with friction-loss rows (dof_frictionloss > 0)")
   if m.opt_solver not in (1, 2):
     raise ValueError("supported solvers: Newton, CG (PGS is not implemented)")
   if m.opt_integrator not in (0, 3):

@@ -111,10 +111,12 @@ def test_elliptic_cone_is_isotropic_where_the_pyramid_is_not(ang):
     np.testing.assert_allclose(ratio, mu / math.sqrt(2), rtol=1e-3)
 
 
-@pytest.mark.parametrize("name,solver", [("go1_flat", 2), ("g1_flat", 2), ("go1_flat", 1)])
-def test_elliptic_kernel_source_matches_oracle(name, solver):
+@pytest.mark.parametrize("name,solver,fl", [("go1_flat", 2, 0.0), ("g1_flat", 2, 0.0), ("go1_flat", 1, 0.0), ("go1_flat", 2, 0.3), ("go1_flat", 1, 0.3)])
+def test_elliptic_kernel_source_matches_oracle(name, solver, fl):
   m = copy.deepcopy(mjlab_b200.load_model(name))
   m.opt_cone, m.opt_solver, m.opt_impratio = 1, solver, 2.0
+  if fl > 0:                                      # friction-loss rows next to the cone contacts (k_solve_t<*, true, true>)
+    m.dof_frictionloss = np.concatenate((np.zeros(6), np.linspace(0.05, fl, m.nv - 6)))
   m.opt_iterations, m.opt_ls_iterations = (100, 50) if solver == 1 else (20, 50)
   nw = 6
   qpos, qvel, ctrl, xfrc = util.random_states(m, nw, seed=11)

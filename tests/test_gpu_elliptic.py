@@ -20,10 +20,13 @@ def _sim(m, nw, solver="newton", iterations=20, impratio=2.0):
   return Simulation(nw, cfg, m, "cuda:0")
 
 
-@pytest.mark.parametrize("name,solver", [("go1_flat", "newton"), ("g1_flat", "newton"), ("go1_flat", "cg")])
-def test_forward_on_the_elliptic_cone(name, solver):
+@pytest.mark.parametrize("name,solver,fl", [("go1_flat", "newton", 0.0), ("g1_flat", "newton", 0.0), ("go1_flat", "cg", 0.0),
+                                            ("go1_flat", "newton", 0.3)])
+def test_forward_on_the_elliptic_cone(name, solver, fl):
   import mjlab_b200
   m = copy.deepcopy(mjlab_b200.load_model(name))
+  if fl > 0:       # friction-loss rows next to the cone contacts: k_solve_t<false, true, true>
+    m.dof_frictionloss = np.concatenate((np.zeros(6), np.linspace(0.05, fl, m.nv - 6)))
   nw = 8
   qpos, qvel, ctrl, xfrc = util.random_states(m, nw, seed=11)
   sim = _sim(m, nw, solver, 100 if solver == "cg" else 20)
@@ -36,7 +39,7 @@ def test_forward_on_the_elliptic_cone(name, solver):
   ncone = 0
   tol = 1e-4 if solver == "newton" else 2e-3     # CG stops on the cost-improvement test: looser in float32
   for w, d in enumerate(ds):
-    assert int(D.nefc[w]) == d.nefc and int(D.ncon[w]) == len(d.contacts)
+    assert int(D.nefc[w]) == d.nefc and int(D.ncon[w]) == len(d.contacts) and int(D.nf[w]) == d.nf == (m.nv - 6 if fl > 0 else 0)
     np.testing.assert_array_equal(D.contact_efc_address[w, : len(d.contacts)].cpu().numpy(), [c.efc_address for c in d.contacts])
     n = d.nefc
     ncone += len(d.efc_cones)
