@@ -57,11 +57,12 @@ def test_simulation_config_is_piped():
   # gravity (0, 0, +7.5) really reaches the kernels: the free body accelerates upwards
   sim.step()
   assert float(sim.data.qvel[0, 2]) == pytest.approx(7.5 * 0.02, rel=1e-5)
-  # PGS and the elliptic cone are outside the supported subset: refused at setup, not ignored
+  # PGS is outside the supported subset: refused at setup, not ignored; the elliptic cone is piped like every other option
   with pytest.raises(ValueError, match="PGS"):
     _sim(1, SimulationCfg(mujoco=MujocoCfg(solver="pgs")))
-  with pytest.raises(ValueError, match="pyramidal"):
-    _sim(1, SimulationCfg(mujoco=MujocoCfg(cone="elliptic")))
+  ell = _sim(1, SimulationCfg(mujoco=MujocoCfg(cone="elliptic", impratio=3.0)))
+  assert ell.mj_model.opt.cone == mjcf.CONE_ELLIPTIC and ell.model.opt.cone == mjcf.CONE_ELLIPTIC
+  assert ell.mj_model.opt.impratio == 3.0
 
 
 def test_cg_solver_on_the_gpu_matches_oracle():
