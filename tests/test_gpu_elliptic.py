@@ -96,12 +96,13 @@ def test_elliptic_and_pyramidal_agree_where_no_contact_slides_and_differ_in_row_
   assert np.isfinite(qe).all() and np.abs(qe[:, 2] - qp[:, 2]).max() < 2e-3
 
 
-def test_velocity_env_runs_on_the_elliptic_cone():
+@pytest.mark.parametrize("solver", ["newton", "cg"])
+def test_velocity_env_runs_on_the_elliptic_cone(solver):
   from mjlab_b200.env import ManagerBasedRlEnv, VelocityEnvCfg
   from mjlab_b200.sim import MujocoCfg, SimulationCfg
-  sim = SimulationCfg(nconmax=35, njmax=300, mujoco=MujocoCfg(timestep=0.005, iterations=10, ls_iterations=20, cone="elliptic"))
+  sim = SimulationCfg(nconmax=35, njmax=300, mujoco=MujocoCfg(timestep=0.005, iterations=10, ls_iterations=20, cone="elliptic", solver=solver))
   env = ManagerBasedRlEnv(VelocityEnvCfg(robot="go1", num_envs=64, seed=3, sim=sim), "cuda:0")
-  assert env.sim.mj_model.opt_cone == 1
+  assert env.sim.mj_model.opt_cone == 1 and env.sim.mj_model.opt_solver == {"newton": 2, "cg": 1}[solver]
   obs, _ = env.reset()
   tot = 0.0
   for _ in range(30):

@@ -105,7 +105,7 @@ def test_unsupported_terms_raise():
       "carry no noise")
   bad(lambda d: d["events"].update(x=dict(func="apply_external_force_torque", mode="reset", params={}, interval_range_s=None)), "apply_external_force_torque")
   bad(lambda d: d["commands"]["twist"].update(init_velocity_prob=0.5), "init_velocity_prob")
-  bad(lambda d: d["sim"]["mujoco"].update(solver="cg"), "supported subset")
+  bad(lambda d: d["sim"]["mujoco"].update(solver="pgs"), "supported subset")
   bad(lambda d: d["observations"]["policy"]["terms"]["joint_pos"].update(noise=dict(__type__="GaussianNoiseCfg", operation="add", mean=0, std=1)), "UniformNoiseCfg")
 
 
@@ -357,3 +357,19 @@ def test_tracking_3d_terminations_are_consumed():
   d["terminations"]["both"] = dict(d["terminations"]["anchor_pos"], func="bad_anchor_pos_z_only")
   with pytest.raises(envcfg.UnsupportedTermError, match="share one kernel slot"):
     envcfg.tracking_from_manager_cfg(d, m, 500)
+
+
+def test_sim_options_of_the_cfg_are_consumed_or_refused():
+  """`cfg.sim.mujoco` (src/mjlab/sim/sim.py:45-60): both friction cones, Newton and CG, both integrators are accepted; PGS / RK4 are
+  refused by name.  The env built from such a cfg hands the options to `Simulation` (`ManagerBasedRlEnv.from_manager_cfg`)."""
+  m = mjlab_b200.load_model("go1_flat")
+  base = _load("Mjlab-Velocity-Flat-Unitree-Go1", False)
+  for key, val in (("cone", "elliptic"), ("solver", "cg"), ("integrator", "euler")):
+    d = copy.deepcopy(base)
+    d["sim"]["mujoco"][key] = val
+    envcfg.from_manager_cfg(d, m, "go1")
+  for key, val in (("solver", "pgs"), ("integrator", "rk4"), ("cone", "spherical")):
+    d = copy.deepcopy(base)
+    d["sim"]["mujoco"][key] = val
+    with pytest.raises(envcfg.UnsupportedTermError, match=val):
+      envcfg.from_manager_cfg(d, m, "go1")

@@ -38,5 +38,8 @@ def run(cone: str, n: int, steps: int = 200, warm: int = 300) -> dict:
 
 if __name__ == "__main__":
   n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+  if len(sys.argv) > 2:   # one cone only, few steps: the ncu capture (`ncu -k regex:k_solve -s 100 -c 1 python tools/time_cone.py 4096 elliptic`)
+    print(json.dumps(run(sys.argv[2], n, steps=5, warm=30)))
+    sys.exit(0)
   print(json.dumps(dict(workload="g1_flat velocity env step, random actions, no L2 flush (back-to-back replays)",
                         pyramidal=run("pyramidal", n), elliptic=run("elliptic", n))))
