@@ -157,3 +157,33 @@ def test_elliptic_trajectory_kernel_source_matches_oracle():
   for w, d in enumerate(ds):
     np.testing.assert_allclose(hs.qpos[w], d.qpos, rtol=1e-7, atol=1e-8)
     np.testing.assert_allclose(hs.qvel[w], d.qvel, rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("njmax,arena", [(10, 0), (17, 0), (300, 500)])
+def test_elliptic_rows_under_row_and_arena_overflow(njmax, arena):
+  """`njmax` truncation keeps whole contacts (three rows each) exactly as the oracle does; a deliberately small solver arena (host
+  build knob) drops contacts from the tail: the kept rows form a prefix of whole contacts and the solve stays finite."""
+  m = copy.deepcopy(mjlab_b200.load_model("go1_flat"))
+  m.opt_cone = 1
+  nw = 3
+  qpos, qvel, ctrl, xfrc = util.random_states(m, nw, seed=8, drop=0.06)
+  hs = HostSim(m, nw, 35, njmax, real="double")
+  if arena:
+    hs.lib.b2h_set_jpool_budget(arena)
+  try:
+    hs.qpos[:], hs.qvel[:], hs.ctrl[:] = qpos, qvel, ctrl
+    hs.forward()
+  finally:
+    hs.lib.b2h_set_jpool_budget(0)
+  ds = util.oracle_rollout(m, qpos, qvel, ctrl, xfrc, 1, 35, njmax, integrate_last=False)
+  for w, d in enumerate(ds):
+    if not arena:
+      assert hs.nefc[w] == d.nefc <= njmax
+      np.testing.assert_array_equal(hs.contact_efc_address[w, : len(d.contacts)], [c.efc_address for c in d.contacts])
+      np.testing.assert_allclose(hs.qacc[w], d.qacc, rtol=1e-8, atol=1e-8)
+      np.testing.assert_allclose(hs.efc_force[w, : d.nefc], d.efc_force, rtol=1e-7, atol=1e-7)
+    else:
+      assert hs.nefc[w] <= d.nefc and np.all(np.isfinite(hs.qacc[w]))
+      kept = hs.contact_efc_address[w, : len(d.contacts)]
+      assert (hs.nefc[w] - hs.nl[w]) == 3 * int(np.sum(kept >= 0))       # whole contacts only
+  assert hs.nefc_dropped.sum() > 0
