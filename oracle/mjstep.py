@@ -13,6 +13,9 @@ pin: pyproject.toml:106, uv.lock:1378-1380), which itself restates MuJoCo C
 algorithm (the "Computation" chapter of the MuJoCo documentation; field names
 from typings/mujoco/_structs.pyi:113-867,916).
 
+Friction cones: pyramidal (the BASELINE configs) and elliptic (`MujocoCfg.cone`, src/mjlab/sim/sim.py:51-56); solvers:
+Newton and CG; constraint rows: friction loss, joint limits, contacts.
+
 PARITY UNPINNED: the reference's own tests hold no golden vectors for this path
  and the reference cannot be executed in this container or on the
 GPU box, so this oracle is pinned only by analytic invariants
