@@ -213,16 +213,17 @@ B2_DEV bool cone_ray(const ConeArgs& ca, int c, const real* jar, const real* jv,
 // its contribution at alpha: a sticking contact adds to the pass's quadratic sums like any active row; a sliding one adds its
 // own cost / slope / curvature (e0, e1, e2), which are summed apart - folding them into the quadratic's coefficients would
 // cancel alpha e2 against itself in the slope, and e2 grows like 1 / T near the cone's axis (measured: 1e-3 force error in float32)
-// (1 / T comes from the reciprocal square root, T = Tsq / T.  A non-inlined single copy of this function was measured: its
+// (T and 1 / T are the IEEE square root and division: with rsqrt - 4.41 -> 4.29 ms per env step - a G1 world stopped an iteration early
+// and missed the 1e-4 force parity (1.5e-3), also with rsqrt kept for the directions only: measured, reverted.  A non-inlined single copy of this function was measured: its
 // by-reference arguments go through local memory, 4.80 against 4.41 ms per env step - reverted)
 B2_DEV void cone_at(const ConeRay& r, real alpha, real& q0, real& q1, real& q2, real& e0, real& e1, real& e2) {
   const real N = r.U0 + alpha * r.V0;
   const real Tsq = r.UU + alpha * (2 * r.UV + alpha * r.VV);
-  const real rT = Tsq > 0 ? b2_rsqrt(Tsq) : (real)0;
-  const real T = Tsq * rT;
+  const real T = Tsq > 0 ? sqrt(Tsq) : (real)0;
   const int zone = cone_zone(N, T, r.mu);
   if (zone == 1) { q0 += r.z0; q1 += r.z1; q2 += r.z2; }
   else if (zone == 2) {
+    const real rT = (real)1 / T;
     const real T1 = (r.UV + alpha * r.VV) * rT, T2 = (r.VV - T1 * T1) * rT;
     const real NmT = N - r.mu * T, s1 = r.V0 - r.mu * T1;
     e0 += (real)0.5 * r.Dm * NmT * NmT; e1 += r.Dm * NmT * s1; e2 += r.Dm * (s1 * s1 - NmT * r.mu * T2);
@@ -243,8 +244,7 @@ B2_DEVN real cone_update(ConeArgs ca, const real* jar, const real* D, real* wgt,
     const real x0 = jar[adr], x1 = jar[adr + 1], x2 = jar[adr + 2];
     const real N = x0 * mu, U1 = x1 * f1, U2 = x2 * f2;
     const real TT = U1 * U1 + U2 * U2;
-    const real rT = TT > 0 ? b2_rsqrt(TT) : (real)0;
-    const real T = TT * rT;
+    const real T = TT > 0 ? sqrt(TT) : (real)0;
     const int zone = cone_zone(N, T, mu);
     if (write) {
       ca.cinfo[4 * c + 1] = (dz & 0xff) | (zone << 8);
@@ -261,6 +261,7 @@ B2_DEVN real cone_update(ConeArgs ca, const real* jar, const real* D, real* wgt,
       const real NmT = N - mu * T;
       cost += (real)0.5 * Dm * NmT * NmT;
       if (write) {
+        const real rT = (real)1 / T;
         const real n1 = U1 * rT, n2 = U2 * rT;
         const real fn = -Dm * NmT * mu;
         frc[adr] = fn; frc[adr + 1] = -fn * n1 * f1; frc[adr + 2] = -fn * n2 * f2;
